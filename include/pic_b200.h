@@ -1,0 +1,191 @@
+/* pic_b200.h -- C ABI of the B200-native PIC step engine.
+ *
+ * Every entry point replaces ONE host-side call site of ECP-WarpX/WarpX's explicit
+ * electromagnetic PIC step (reference paths are relative to /root/reference).  WarpX has no
+ * plugin registry for this path: the seam is the argument set of each call site, which
+ * decays to raw device pointers + index metadata.  These are those argument sets, as POD.
+ *
+ * Conventions (identical to the reference):
+ *   - all arithmetic is fp64 (WarpX_PRECISION=DOUBLE); indices are global level-0 indices;
+ *   - arrays are Fortran ordered (i fastest), exactly amrex::Array4 / FArrayBox layout;
+ *   - memory is BORROWED: no entry point allocates persistent memory or frees anything
+ *     (WarpX callees never own MultiFab / ParticleTile storage);
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*), like
+ *     kernels on amrex::Gpu::gpuStream(); the caller synchronises (PhysicalParticleContainer.cpp:2076);
+ *   - errors: WarpX aborts (WARPX_ABORT_WITH_MESSAGE -> amrex::Abort).  Default here is the same:
+ *     print to stderr and abort().  Tests switch to return codes with pic_set_error_mode().
+ */
+#ifndef PIC_B200_H_
+#define PIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Data descriptors
+ * ---------------------------------------------------------------------------------------- */
+
+/* One component of a MultiFab on one box == amrex::FArrayBox / Array4<Real>
+ * (Source/FieldSolver/FiniteDifferenceSolver/EvolveB.cpp:143-148).
+ * p points at element (lo[0],lo[1],lo[2]); element (i,j,k) lives at
+ * p[(i-lo[0]) + (j-lo[1])*nx + (k-lo[2])*nx*ny], nx = hi[0]-lo[0]+1, ny = hi[1]-lo[1]+1. */
+typedef struct pic_fab {
+    double* p;
+    int lo[3];     /* smallest allocated index  (= valid lo - ng)            */
+    int hi[3];     /* largest  allocated index, inclusive (= valid hi + ng)  */
+    int ng[3];     /* guard cells per side (MultiFab::nGrowVect)             */
+    int stag[3];   /* amrex::IndexType: 1 = NODE, 0 = CELL                   */
+} pic_fab;
+
+/* Particle struct-of-arrays of one tile == ParticleContainerPureSoA<PIdx::nattribs,0>
+ * with PIdx {x,y,z,w,ux,uy,uz} (Source/Particles/NamedComponentParticleContainer.H:23-40)
+ * + the 64-bit idcpu.  u = gamma*v in m/s; w = physical particles per macro-particle. */
+typedef struct pic_soa {
+    double* x; double* y; double* z; double* w;
+    double* ux; double* uy; double* uz;
+    uint64_t* idcpu;
+    long np;
+} pic_soa;
+
+/* Stencil coefficients == FiniteDifferenceSolver::m_stencil_coefs_{x,y,z}
+ * (FiniteDifferenceSolver.cpp:30-103).  Yee: c[0] = 1/dx (CartesianYeeAlgorithm.H:37-42).
+ * CKC: {1/d, alpha, beta1, beta2, gamma/d} (CartesianCKCAlgorithm.H:84-101). */
+enum { PIC_SOLVER_YEE = 0, PIC_SOLVER_CKC = 1 };
+typedef struct pic_stencil {
+    int algo;
+    double cx[5]; double cy[5]; double cz[5];
+} pic_stencil;
+
+/* Particle pusher selection == ParticlePusherAlgo (Utils/WarpXAlgorithmSelection.H). */
+enum { PIC_PUSHER_BORIS = 0, PIC_PUSHER_VAY = 1, PIC_PUSHER_HC = 2 };
+
+/* Cell bins of a cell-sorted particle tile == amrex::DenseBins as built by
+ * SortParticlesForDeposition / the shared-memory deposition path
+ * (Source/Particles/WarpXParticleContainer.cpp:493-540, MultiParticleContainer.cpp:615-624).
+ * Cells are numbered i + nx*(j + ny*k) over the rank's valid box [box_lo, box_hi].
+ * Particles of cell c are [cell_start[c], cell_start[c+1]).  Optional everywhere (NULL =
+ * particle order unknown -> order-agnostic kernels). */
+typedef struct pic_bins {
+    const int* cell_start;  /* ncell+1 entries, device */
+    int box_lo[3];          /* first cell of the box                           */
+    int box_hi[3];          /* last cell of the box, inclusive                 */
+} pic_bins;
+
+/* Domain description for the periodic / neighbour guard-cell operations
+ * (amrex::Geometry + Periodicity). */
+typedef struct pic_geom {
+    int n_cell[3];          /* global number of cells                          */
+    double prob_lo[3];
+    double prob_hi[3];
+    int periodic[3];
+} pic_geom;
+
+enum { PIC_ERR_ABORT = 0, PIC_ERR_RETURN = 1 };
+void pic_set_error_mode(int mode);
+const char* pic_last_error(void);
+const char* pic_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Maxwell solver  (replaces FiniteDifferenceSolver::EvolveB / EvolveE)
+ * ---------------------------------------------------------------------------------------- */
+
+/* FiniteDifferenceSolver::EvolveBCartesian<T_Algo> (EvolveB.cpp:122-186), called from
+ * WarpX::EvolveB (WarpXPushFieldsEM.cpp:904-907).  B[c] += dt * curl-part over the valid
+ * points of each staggered component.  B = {Bx,By,Bz}, E = {Ex,Ey,Ez}. */
+int pic_evolve_b(const pic_fab B[3], const pic_fab E[3], const pic_stencil* st, double dt,
+                 void* stream);
+
+/* FiniteDifferenceSolver::EvolveECartesian<T_Algo> (EvolveE.cpp:120-216), called from
+ * WarpX::EvolveE (WarpXPushFieldsEM.cpp:958-962).  E += c^2 dt (curl B - mu0 J). */
+int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3],
+                 const pic_stencil* st, double dt, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Particles  (replaces PhysicalParticleContainer::PushPX / PushP and
+ *             WarpXParticleContainer::DepositCurrent)
+ * ---------------------------------------------------------------------------------------- */
+
+/* PhysicalParticleContainer::PushPX (PhysicalParticleContainer.cpp:2549-2786): per particle
+ * doGatherShapeN (Gather/FieldGather.H:36-424), doParticleMomentumPush (Pusher/PushSelector.H:38-102),
+ * UpdatePosition (Pusher/UpdatePosition.H:24-45).  xyzmin/lo describe the guard-grown tile box
+ * (:2575-2601).  push_position = 0 gives PushP (:2368-2513; momentum only).
+ * bins may be NULL. */
+int pic_gather_push(const pic_soa* p, long offset, long np,
+                    const pic_fab E[3], const pic_fab B[3],
+                    const double dinv[3], const double xyzmin[3], const int lo[3],
+                    double q, double m, double dt,
+                    int nox, int galerkin, int pusher, int push_position,
+                    const pic_bins* bins, void* stream);
+
+/* WarpXParticleContainer::DepositCurrent (WarpXParticleContainer.cpp:352-827) ->
+ * doEsirkepovDepositionShapeN<nox> (Deposition/CurrentDeposition.H:642-907).
+ * J = {jx,jy,jz} is ADDED to (the caller zeroes J, MultiParticleContainer.cpp:467-478).
+ * xyzmin/lo describe the ng_J-grown tile box (WarpXParticleContainer.cpp:424-479).
+ * bins may be NULL (-> order-agnostic kernel with global fp64 atomics, the reference's
+ * GPU strategy); with bins the shared-memory tile kernel is used. */
+int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
+                          const pic_fab J[3],
+                          const double dinv[3], const double xyzmin[3], const int lo[3],
+                          double q, double dt, double relative_time, int nox,
+                          const pic_bins* bins, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Guard cells  (replaces ablastr::utils::communication::FillBoundary / SumBoundary)
+ * ---------------------------------------------------------------------------------------- */
+
+/* FillBoundary along one dimension when the box spans the whole periodic domain in that
+ * dimension (self-neighbour): guards <- periodic image of valid points
+ * (WarpXComm.cpp:699-827 -> Communication.cpp:71-115).  Other dimensions are covered over
+ * their full allocated extent so that sweeping dim = 0,1,2 fills edges and corners. */
+int pic_fill_boundary_local(const pic_fab* f, int dim, int ng, const pic_geom* g, void* stream);
+
+/* SumBoundary along one dimension for a self-neighbour box: valid points accumulate the
+ * periodic images of guard points (and the duplicate nodal point)
+ * (WarpXComm.cpp:1386-1424 -> WarpXSumGuardCells.cpp:17-24 -> Communication.cpp:148-175). */
+int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, const pic_geom* g, void* stream);
+
+/* Neighbour (multi-GPU) versions: pack the slab that the neighbour on `side` (0 = low,
+ * 1 = high) of dimension `dim` needs, and unpack what it sent.  mode 0 = copy (FillBoundary),
+ * mode 1 = sum (SumBoundary).  pic_halo_slab_count returns the number of doubles. */
+long pic_halo_slab_count(const pic_fab* f, int dim, int ng, int mode);
+int pic_halo_pack(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, void* stream);
+int pic_halo_unpack(const pic_fab* f, int dim, int side, int ng, int mode, const double* buf,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Particle housekeeping  (replaces AMReX Redistribute periodic wrap and
+ *                         SortParticlesByBin / SortParticlesForDeposition)
+ * ---------------------------------------------------------------------------------------- */
+
+/* amrex enforcePeriodic as applied by ParticleContainer::Redistribute
+ * (WarpXEvolve.cpp:550-559 -> MultiParticleContainer.cpp:650-656; AMReX 24.10 @62c2a81
+ * AMReX_ParticleUtil.H, un-vendored dependency). */
+int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* stream);
+
+/* Counting sort of the particles by cell over the valid box [box_lo,box_hi]
+ * (WarpX: mypc->SortParticlesByBin, WarpXEvolve.cpp:575-580).  `in` is permuted into `out`;
+ * cell_start (ncell+1 ints) receives the bins.  work must hold pic_sort_workspace_bytes(). */
+long pic_sort_workspace_bytes(long np, long ncell);
+int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_geom* g,
+                               const int box_lo[3], const int box_hi[3],
+                               int* cell_start, void* work, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reduced diagnostics used as parity metrics
+ * ---------------------------------------------------------------------------------------- */
+
+/* Sum of squares over the unique (periodicity-aware) valid points of one component ==
+ * MultiFab::norm2(0, periodicity)^2 as used by FieldEnergy
+ * (Source/Diagnostics/ReducedDiags/FieldEnergy.cpp:120-144).  out: 1 double, device. */
+int pic_sum_squares_unique(const pic_fab* f, const pic_geom* g, double* out, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+long pic_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC_B200_H_ */

@@ -1,0 +1,428 @@
+// TEST INFRASTRUCTURE -- C API of the CPU oracle (see pic_oracle_core.hpp) plus a whole-loop
+// driver that restates WarpX::Evolve / OneStep_nosub for a single-level, periodic, explicit
+// FDTD run (Evolve/WarpXEvolve.cpp:93-347, 353-455, 473-531, 64-91).
+//
+// Built twice by oracle/Makefile:
+//   libpic_oracle.so           leaf arithmetic = hand restatement   (always; travels to the GPU box)
+//   _ref/libpic_oracle_ref.so  leaf arithmetic = reference headers compiled verbatim from
+//                              /root/reference through oracle/amrex_shim (only where the
+//                              reference tree exists; the built .so travels, sources do not)
+#ifdef ORC_LEAF_REFERENCE
+#include "leaf_reference.hpp"
+using Leaf = orc::LeafReference;
+#else
+#include "leaf_restated.hpp"
+using Leaf = orc::LeafRestated;
+#endif
+#include "pic_oracle_core.hpp"
+
+#include <array>
+#include <chrono>
+#include <memory>
+#include <string>
+
+using namespace orc;
+
+namespace {
+
+struct Species {
+    double q, m;
+    std::vector<double> a[7];           // x y z w ux uy uz  (PIdx order)
+    pic_soa soa() {
+        pic_soa s;
+        s.x = a[0].data(); s.y = a[1].data(); s.z = a[2].data(); s.w = a[3].data();
+        s.ux = a[4].data(); s.uy = a[5].data(); s.uz = a[6].data();
+        s.idcpu = nullptr; s.np = (long)a[0].size();
+        return s;
+    }
+};
+
+// One box == the whole periodic domain, or a brick decomposition nb[0] x nb[1] x nb[2]
+// (used as the oracle of the multi-GPU path).  All boxes live in this process.
+struct Sim {
+    pic_geom geom;
+    int nox, galerkin, pusher, solver;
+    double dx[3], dinv[3], dt, cfl;
+    int ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3], ng_depos_J[3];
+    pic_stencil st;
+    int nb[3];
+    struct Box {
+        int lo[3], hi[3];                // cells
+        std::vector<double> data[9];     // Ex Ey Ez Bx By Bz jx jy jz
+        pic_fab fab[9];
+        std::vector<Species> sp;
+    };
+    std::vector<Box> boxes;
+    int nspecies = 0;
+    bool is_synchronized = true;
+    int istep = 0;
+    double t_push = 0, t_dep = 0, t_fdtd = 0, t_halo = 0, t_other = 0;
+};
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Staggering, Source/WarpX.cpp:2117-2125 (Yee grid): 1 = nodal.
+const int STAG[9][3] = {{0, 1, 1}, {1, 0, 1}, {1, 1, 0},   // Ex Ey Ez
+                        {1, 0, 0}, {0, 1, 0}, {0, 0, 1},   // Bx By Bz
+                        {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};  // jx jy jz (= E)
+
+// guardCellManager::Init, Parallelization/GuardCellManager.cpp:62-161,310-343 (no MR, no NCI,
+// no moving window, no filter, not safe_guard_cells, FDTD).
+void guard_cells(Sim& s) {
+    for (int d = 0; d < 3; ++d) {
+        const int ngt = s.nox;                                   // :62-64
+        const int ng = (ngt % 2) ? ngt + 1 : ngt;                // :83-85 (even)
+        s.ng_EB[d] = ng;
+        s.ng_J[d] = ngt + (int)std::ceil(C_LIGHT * 0.5 * s.dt / s.dx[d]);   // :96-98,147,161
+        s.ng_depos_J[d] = s.ng_J[d];                             // :165
+        s.ng_FS[d] = 1;                                          // Yee/CKC GetMaxGuardCell
+        s.ng_EB[d] = std::max(s.ng_EB[d], s.ng_FS[d]);           // :297
+        int fg = std::min((s.nox + 1) / 2, s.ng_EB[d]);          // :314-316
+        fg = std::min(fg, s.ng_EB[d]);
+        s.ng_FG[d] = std::max(fg, s.ng_FS[d]);                   // :338
+    }
+}
+
+void alloc_box(Sim& s, Sim::Box& b) {
+    for (int c = 0; c < 9; ++c) {
+        pic_fab& f = b.fab[c];
+        const int* ng = (c < 6) ? s.ng_EB : s.ng_J;
+        for (int d = 0; d < 3; ++d) {
+            f.stag[d] = STAG[c][d];
+            f.ng[d] = ng[d];
+            f.lo[d] = b.lo[d] - ng[d];
+            f.hi[d] = b.hi[d] + STAG[c][d] + ng[d];
+        }
+        b.data[c].assign((size_t)fab_size(f), 0.0);
+        f.p = b.data[c].data();
+    }
+}
+
+void fill_EB(Sim& s, int c0, const int ng[3]) {  // FillBoundaryE (c0=0) / FillBoundaryB (c0=3)
+    const double t0 = now();
+    std::vector<pic_fab> fabs(s.boxes.size());
+    for (int c = c0; c < c0 + 3; ++c) {
+        for (size_t b = 0; b < s.boxes.size(); ++b) fabs[b] = s.boxes[b].fab[c];
+        fill_boundary(fabs.data(), (int)fabs.size(), ng, s.geom);
+    }
+    s.t_halo += now() - t0;
+}
+
+// xyzmin of a box grown by ng: RealBox(bx, dx, prob_lo).lo = prob_lo + lo_index*dx
+// (WarpX::getRealBox / LowerCorner, Source/WarpX.cpp:2851-2874; AMReX RealBox ctor).
+void lower_corner(const Sim& s, const Sim::Box& b, const int ng[3], double xyzmin[3], int lo[3]) {
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = b.lo[d] - ng[d];
+        xyzmin[d] = s.geom.prob_lo[d] + s.dx[d] * lo[d];
+    }
+}
+
+void push_p(Sim& s, double dtp) {  // mypc->PushP(lev, dt, E_aux, B_aux): box grown by Ex.nGrowVect (:2384-2385)
+    const double t0 = now();
+    for (auto& b : s.boxes) {
+        double xyzmin[3]; int lo[3];
+        lower_corner(s, b, s.ng_EB, xyzmin, lo);
+        for (auto& sp : b.sp) {
+            pic_soa P = sp.soa();
+            gather_push<Leaf>(P, 0, P.np, b.fab, b.fab + 3, s.dinv, xyzmin, lo, sp.q, sp.m, dtp,
+                              s.nox, s.galerkin, s.pusher, 0);
+        }
+    }
+    s.t_push += now() - t0;
+}
+
+// Move particles that left their box to the owning box after the periodic wrap
+// (ParticleContainer::Redistribute semantics; locate by cell index).
+void redistribute(Sim& s) {
+    const double t0 = now();
+    for (auto& b : s.boxes)
+        for (auto& sp : b.sp) { pic_soa P = sp.soa(); wrap_periodic(P, s.geom); }
+    if (s.boxes.size() > 1) {
+        for (int isp = 0; isp < s.nspecies; ++isp) {
+            std::vector<std::array<std::vector<double>, 7>> in(s.boxes.size());
+            for (size_t ib = 0; ib < s.boxes.size(); ++ib) {
+                Species& sp = s.boxes[ib].sp[isp];
+                std::array<std::vector<double>, 7> keep;
+                const long np = (long)sp.a[0].size();
+                for (long ip = 0; ip < np; ++ip) {
+                    int cell[3], owner[3];
+                    for (int d = 0; d < 3; ++d) {
+                        cell[d] = (int)std::floor((sp.a[d][ip] - s.geom.prob_lo[d]) * s.dinv[d]);
+                        cell[d] = std::min(std::max(cell[d], 0), s.geom.n_cell[d] - 1);
+                        owner[d] = cell[d] / (s.geom.n_cell[d] / s.nb[d]);
+                    }
+                    const size_t ob = owner[0] + (size_t)s.nb[0] * (owner[1] + (size_t)s.nb[1] * owner[2]);
+                    auto& dst = (ob == ib) ? keep : in[ob];
+                    for (int a = 0; a < 7; ++a) dst[a].push_back(sp.a[a][ip]);
+                }
+                for (int a = 0; a < 7; ++a) sp.a[a].swap(keep[a]);
+            }
+            for (size_t ib = 0; ib < s.boxes.size(); ++ib)
+                for (int a = 0; a < 7; ++a) {
+                    auto& v = s.boxes[ib].sp[isp].a[a];
+                    v.insert(v.end(), in[ib][a].begin(), in[ib][a].end());
+                }
+        }
+    }
+    s.t_other += now() - t0;
+}
+
+// WarpX::OneStep_nosub (WarpXEvolve.cpp:353-455) preceded by ExplicitFillBoundaryEBUpdateAux
+// (:473-531) and followed by the end-of-step bookkeeping of WarpX::Evolve (:221-256).
+void one_step(Sim& s, bool last_step) {
+    // ---- ExplicitFillBoundaryEBUpdateAux ----
+    if (s.is_synchronized) {
+        fill_EB(s, 0, s.ng_EB); fill_EB(s, 3, s.ng_EB);          // :487-488 (ng_alloc_EB)
+        push_p(s, -0.5 * s.dt);                                    // :492-504
+        s.is_synchronized = false;
+    } else {
+        fill_EB(s, 0, s.ng_FG); fill_EB(s, 3, s.ng_FG);          // :515-516
+    }
+    // ---- PushParticlesandDeposit (:366 -> MultiParticleContainer::Evolve) ----
+    double t0 = now();
+    for (auto& b : s.boxes)
+        for (int c = 6; c < 9; ++c) std::fill(b.data[c].begin(), b.data[c].end(), 0.0);  // J.setVal(0)
+    s.t_other += now() - t0;
+    for (auto& b : s.boxes) {
+        double xyzmin[3], xyzminJ[3]; int lo[3], loJ[3];
+        lower_corner(s, b, s.ng_EB, xyzmin, lo);                   // PushPX: box.grow(ngEB), :2583
+        lower_corner(s, b, s.ng_J, xyzminJ, loJ);                  // DepositCurrent: tilebox.grow(ng_J)
+        for (auto& sp : b.sp) {
+            pic_soa P = sp.soa();
+            t0 = now();
+            gather_push<Leaf>(P, 0, P.np, b.fab, b.fab + 3, s.dinv, xyzmin, lo, sp.q, sp.m, s.dt,
+                              s.nox, s.galerkin, s.pusher, 1);
+            s.t_push += now() - t0;
+            t0 = now();
+            deposit<Leaf>(P, 0, P.np, b.fab + 6, s.dinv, xyzminJ, loJ, sp.q, s.dt,
+                          -0.5 * s.dt /* relative_time, PhysicalParticleContainer.cpp:2029 */, s.nox);
+            s.t_dep += now() - t0;
+        }
+    }
+    // ---- SyncCurrentAndRho -> SumBoundaryJ (WarpXComm.cpp:1386-1424): src = ng_depos_J,
+    //      dst = all guards of J (WarpXSumGuardCells.cpp:22-23) ----
+    t0 = now();
+    {
+        std::vector<pic_fab> fabs(s.boxes.size());
+        for (int c = 6; c < 9; ++c) {
+            for (size_t b = 0; b < s.boxes.size(); ++b) fabs[b] = s.boxes[b].fab[c];
+            sum_boundary(fabs.data(), (int)fabs.size(), s.ng_depos_J, s.ng_J, s.geom);
+        }
+    }
+    s.t_halo += now() - t0;
+    // ---- field solve (:421-437) ----
+    auto evolveB = [&](double dtb) {
+        const double t1 = now();
+        for (auto& b : s.boxes) evolve_b<Leaf>(b.fab + 3, b.fab, s.st, dtb);
+        s.t_fdtd += now() - t1;
+    };
+    evolveB(0.5 * s.dt);
+    fill_EB(s, 3, s.ng_FS);
+    t0 = now();
+    for (auto& b : s.boxes) evolve_e<Leaf>(b.fab, b.fab + 3, b.fab + 6, s.st, s.dt);
+    s.t_fdtd += now() - t0;
+    fill_EB(s, 0, s.ng_FS);
+    evolveB(0.5 * s.dt);
+    // ---- end of step (WarpX::Evolve :219-256) ----
+    if (last_step) {  // Synchronize() (:64-91)
+        fill_EB(s, 0, s.ng_FG); fill_EB(s, 3, s.ng_FG);
+        push_p(s, 0.5 * s.dt);
+        s.is_synchronized = true;
+    }
+    ++s.istep;
+    redistribute(s);   // HandleParticlesAtBoundaries -> RedistributeLocal(1)
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_leaf_name() { return Leaf::name; }
+
+// ---- leaf probes (used to compare restated vs reference leaves bit for bit) -----------------
+int orc_shape(int order, double x, double* s) {
+    switch (order) {
+        case 0: return Leaf::shape<0>(s, x);
+        case 1: return Leaf::shape<1>(s, x);
+        case 2: return Leaf::shape<2>(s, x);
+        case 3: return Leaf::shape<3>(s, x);
+        case 4: return Leaf::shape<4>(s, x);
+    }
+    return -999;
+}
+int orc_shifted_shape(int order, double x_old, int i_new, double* s /* order+3, pre-zeroed */) {
+    switch (order) {
+        case 0: return Leaf::shifted_shape<0>(s, x_old, i_new);
+        case 1: return Leaf::shifted_shape<1>(s, x_old, i_new);
+        case 2: return Leaf::shifted_shape<2>(s, x_old, i_new);
+        case 3: return Leaf::shifted_shape<3>(s, x_old, i_new);
+        case 4: return Leaf::shifted_shape<4>(s, x_old, i_new);
+    }
+    return -999;
+}
+void orc_push_momentum(int pusher, double* u /*3*/, const double* EB /*6*/, double q, double m,
+                       double dt) {
+    if (pusher == PIC_PUSHER_BORIS) Leaf::boris(u[0], u[1], u[2], EB[0], EB[1], EB[2], EB[3], EB[4], EB[5], q, m, dt);
+    else if (pusher == PIC_PUSHER_VAY) Leaf::vay(u[0], u[1], u[2], EB[0], EB[1], EB[2], EB[3], EB[4], EB[5], q, m, dt);
+    else Leaf::higuera_cary(u[0], u[1], u[2], EB[0], EB[1], EB[2], EB[3], EB[4], EB[5], q, m, dt);
+}
+void orc_update_position(double* x /*3*/, const double* u /*3*/, double dt) {
+    Leaf::update_position(x[0], x[1], x[2], u[0], u[1], u[2], dt);
+}
+void orc_stencil_coefs(int algo, const double* dx, pic_stencil* st) { Leaf::stencil_coefs(algo, dx, st); }
+double orc_max_dt(int algo, const double* dx) { return Leaf::max_dt(algo, dx); }
+
+// ---- stage-level entry points: same argument sets as include/pic_b200.h, host pointers -----
+int orc_evolve_b(const pic_fab* B, const pic_fab* E, const pic_stencil* st, double dt) {
+    evolve_b<Leaf>(B, E, *st, dt); return 0;
+}
+int orc_evolve_e(const pic_fab* E, const pic_fab* B, const pic_fab* J, const pic_stencil* st, double dt) {
+    evolve_e<Leaf>(E, B, J, *st, dt); return 0;
+}
+int orc_gather_push(const pic_soa* p, long offset, long np, const pic_fab* E, const pic_fab* B,
+                    const double* dinv, const double* xyzmin, const int* lo, double q, double m,
+                    double dt, int nox, int galerkin, int pusher, int push_position) {
+    return gather_push<Leaf>(*p, offset, np, E, B, dinv, xyzmin, lo, q, m, dt, nox, galerkin, pusher,
+                             push_position);
+}
+int orc_deposit_esirkepov(const pic_soa* p, long offset, long np, const pic_fab* J,
+                          const double* dinv, const double* xyzmin, const int* lo, double q,
+                          double dt, double relative_time, int nox) {
+    return deposit<Leaf>(*p, offset, np, J, dinv, xyzmin, lo, q, dt, relative_time, nox);
+}
+void orc_fill_boundary(const pic_fab* fabs, int nfab, const int* ng, const pic_geom* g) {
+    fill_boundary(fabs, nfab, ng, *g);
+}
+void orc_sum_boundary(const pic_fab* fabs, int nfab, const int* src_ng, const int* dst_ng,
+                      const pic_geom* g) {
+    sum_boundary(fabs, nfab, src_ng, dst_ng, *g);
+}
+void orc_wrap_periodic(const pic_soa* p, const pic_geom* g) { wrap_periodic(*p, *g); }
+double orc_sum_squares_unique(const pic_fab* fabs, int nfab, const pic_geom* g) {
+    return sum_squares_unique(fabs, nfab, *g);
+}
+double orc_checksum_cell_centered(const pic_fab* f, const int* box_lo, const int* box_hi) {
+    return checksum_cell_centered(*f, box_lo, box_hi);
+}
+
+// ---- whole-loop driver --------------------------------------------------------------------
+// dt <= 0: dt = cfl * max_dt (WarpXComputeDt.cpp:56-95).
+void* orc_sim_create(const int* n_cell, const double* prob_lo, const double* prob_hi, int nox,
+                     int galerkin, int pusher, int solver, double cfl, double dt, const int* nb) {
+    auto* s = new Sim();
+    for (int d = 0; d < 3; ++d) {
+        s->geom.n_cell[d] = n_cell[d]; s->geom.prob_lo[d] = prob_lo[d]; s->geom.prob_hi[d] = prob_hi[d];
+        s->geom.periodic[d] = 1;
+        s->dx[d] = (prob_hi[d] - prob_lo[d]) / n_cell[d];       // amrex::Geometry cell size
+        s->dinv[d] = 1.0 / s->dx[d];                             // WarpX::InvCellSize
+        s->nb[d] = nb ? nb[d] : 1;
+        if (n_cell[d] % s->nb[d]) { delete s; return nullptr; }
+    }
+    s->nox = nox; s->galerkin = galerkin; s->pusher = pusher; s->solver = solver; s->cfl = cfl;
+    s->dt = dt > 0 ? dt : cfl * Leaf::max_dt(solver, s->dx);
+    Leaf::stencil_coefs(solver, s->dx, &s->st);
+    guard_cells(*s);
+    for (int bz = 0; bz < s->nb[2]; ++bz)
+        for (int by = 0; by < s->nb[1]; ++by)
+            for (int bx = 0; bx < s->nb[0]; ++bx) {
+                s->boxes.emplace_back();
+                Sim::Box& b = s->boxes.back();
+                const int bi[3] = {bx, by, bz};
+                for (int d = 0; d < 3; ++d) {
+                    const int w = n_cell[d] / s->nb[d];
+                    b.lo[d] = bi[d] * w; b.hi[d] = b.lo[d] + w - 1;
+                }
+                alloc_box(*s, b);
+            }
+    return s;
+}
+void orc_sim_destroy(void* h) { delete static_cast<Sim*>(h); }
+double orc_sim_dt(void* h) { return static_cast<Sim*>(h)->dt; }
+void orc_sim_guards(void* h, int* out /* ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3] */) {
+    Sim* s = static_cast<Sim*>(h);
+    for (int d = 0; d < 3; ++d) { out[d] = s->ng_EB[d]; out[3 + d] = s->ng_J[d]; out[6 + d] = s->ng_FG[d]; out[9 + d] = s->ng_FS[d]; }
+}
+int orc_sim_nboxes(void* h) { return (int)static_cast<Sim*>(h)->boxes.size(); }
+
+// Adds a species; particles are distributed to their owning boxes.
+int orc_sim_add_species(void* h, double q, double m, long np, const double* x, const double* y,
+                        const double* z, const double* w, const double* ux, const double* uy,
+                        const double* uz) {
+    Sim* s = static_cast<Sim*>(h);
+    const double* src[7] = {x, y, z, w, ux, uy, uz};
+    for (auto& b : s->boxes) { b.sp.emplace_back(); b.sp.back().q = q; b.sp.back().m = m; }
+    for (long ip = 0; ip < np; ++ip) {
+        int owner[3];
+        const double pos[3] = {x[ip], y[ip], z[ip]};
+        for (int d = 0; d < 3; ++d) {
+            int cell = (int)std::floor((pos[d] - s->geom.prob_lo[d]) * s->dinv[d]);
+            cell = std::min(std::max(cell, 0), s->geom.n_cell[d] - 1);
+            owner[d] = cell / (s->geom.n_cell[d] / s->nb[d]);
+        }
+        Sim::Box& b = s->boxes[owner[0] + (size_t)s->nb[0] * (owner[1] + (size_t)s->nb[1] * owner[2])];
+        for (int a = 0; a < 7; ++a) b.sp.back().a[a].push_back(src[a][ip]);
+    }
+    return s->nspecies++;
+}
+// Evolve(nsteps): the last step of this call synchronises u with x (WarpXEvolve.cpp:221-226)
+// when `synchronize_last` is set (what a full WarpX run does at max_step).
+void orc_sim_evolve(void* h, int nsteps, int synchronize_last) {
+    Sim* s = static_cast<Sim*>(h);
+    for (int n = 0; n < nsteps; ++n) one_step(*s, synchronize_last && n == nsteps - 1);
+}
+long orc_sim_np(void* h, int isp) {
+    Sim* s = static_cast<Sim*>(h); long n = 0;
+    for (auto& b : s->boxes) n += (long)b.sp[isp].a[0].size();
+    return n;
+}
+// comp: 0..6 = x y z w ux uy uz; concatenated over boxes in box order
+void orc_sim_get_particles(void* h, int isp, int comp, double* out) {
+    Sim* s = static_cast<Sim*>(h);
+    for (auto& b : s->boxes) {
+        auto& v = b.sp[isp].a[comp];
+        std::memcpy(out, v.data(), v.size() * sizeof(double)); out += v.size();
+    }
+}
+long orc_sim_box_np(void* h, int ibox, int isp) { return (long)static_cast<Sim*>(h)->boxes[ibox].sp[isp].a[0].size(); }
+// field access: comp 0..8 = Ex Ey Ez Bx By Bz jx jy jz
+void orc_sim_fab(void* h, int ibox, int comp, pic_fab* out) { *out = static_cast<Sim*>(h)->boxes[ibox].fab[comp]; }
+double orc_sim_checksum_field(void* h, int comp) {
+    Sim* s = static_cast<Sim*>(h); double t = 0;
+    for (auto& b : s->boxes) t += checksum_cell_centered(b.fab[comp], b.lo, b.hi);
+    return t;
+}
+// FieldEnergy (Diagnostics/ReducedDiags/FieldEnergy.cpp:120-144): out = {E energy, B energy}
+void orc_sim_field_energy(void* h, double* out) {
+    Sim* s = static_cast<Sim*>(h);
+    const double dV = s->dx[0] * s->dx[1] * s->dx[2];
+    double e2 = 0, b2 = 0;
+    std::vector<pic_fab> fabs(s->boxes.size());
+    for (int c = 0; c < 6; ++c) {
+        for (size_t b = 0; b < s->boxes.size(); ++b) fabs[b] = s->boxes[b].fab[c];
+        (c < 3 ? e2 : b2) += sum_squares_unique(fabs.data(), (int)fabs.size(), s->geom);
+    }
+    out[0] = 0.5 * e2 * EP0 * dV;
+    out[1] = 0.5 * b2 / MU0 * dV;
+}
+void orc_sim_timers(void* h, double* out /* push, deposit, fdtd, halo, other */) {
+    Sim* s = static_cast<Sim*>(h);
+    out[0] = s->t_push; out[1] = s->t_dep; out[2] = s->t_fdtd; out[3] = s->t_halo; out[4] = s->t_other;
+}
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""Deterministic initial conditions for the benchmark / parity configurations (host side, numpy).
+
+These restate what the reference's plasma injector produces for the decks named in
+BASELINE.json so that the oracle and the CUDA engine start from bit-identical arrays:
+
+* positions: ``NUniformPerCell`` regular lattice, ``InjectorPositionRegular::getPositionUnitBox``
+  (Source/Initialization/InjectorPosition.H:67-108) and ``getCellCoords``
+  (Source/Particles/PhysicalParticleContainer.cpp:151-173): ``pos = lo + (i + r) * dx``;
+* weights: ``w = n * dx*dy*dz / ppc`` (Source/Particles/AddPlasmaUtilities.H:73-77,
+  PhysicalParticleContainer.cpp:1275-1288);
+* momenta: ``u = (gamma*beta) * c`` (PhysicalParticleContainer.cpp:1271-1273).
+"""
+import numpy as np
+
+# CODATA 2018, Source/ablastr/constant.H:44-54
+C = 299792458.0
+EP0 = 8.8541878128e-12
+MU0 = 1.25663706212e-06
+Q_E = 1.602176634e-19
+M_E = 9.1093837015e-31
+
+
+def lattice_positions(n_cell, prob_lo, prob_hi, ppc, box_lo=None, box_hi=None):
+    """Cell-major regular lattice (cell index i fastest, then j, k; particle-in-cell slowest
+    varying inside a cell like the reference's i_part loop).  Returns x, y, z (float64)."""
+    n_cell = np.asarray(n_cell)
+    lo = np.zeros(3, dtype=int) if box_lo is None else np.asarray(box_lo)
+    hi = n_cell - 1 if box_hi is None else np.asarray(box_hi)
+    dx = (np.asarray(prob_hi, dtype=np.float64) - np.asarray(prob_lo, dtype=np.float64)) / n_cell
+    nx, ny, nz = (int(v) for v in ppc)
+    # i_part -> (ix, iy, iz) exactly as InjectorPosition.H:99-102
+    ip = np.arange(nx * ny * nz)
+    ixp = ip // (ny * nz)
+    izp = (ip - ixp * (ny * nz)) // ny
+    iyp = (ip - ixp * (ny * nz)) - ny * izp
+    r = [(0.5 + ixp) / nx, (0.5 + iyp) / ny, (0.5 + izp) / nz]
+    idx = [np.arange(lo[d], hi[d] + 1) for d in range(3)]
+    K, J, I = np.meshgrid(idx[2], idx[1], idx[0], indexing="ij")   # i fastest
+    cells = [I.ravel(), J.ravel(), K.ravel()]
+    out = []
+    for d in range(3):
+        # (ncell, ppc) -> flattened with the in-cell index fastest
+        p = prob_lo[d] + (cells[d][:, None] + r[d][None, :]) * dx[d]
+        out.append(np.ascontiguousarray(p.ravel()))
+    return out
+
+
+def langmuir_3d(n=64, ppc=(1, 1, 1), lx=40.0e-6, n0=2.0e24, epsilon=0.01):
+    """Config 1: Examples/Tests/langmuir/inputs_base_3d (two species, analytic momenta)."""
+    prob_lo, prob_hi = (-lx / 2,) * 3, (lx / 2,) * 3
+    n_cell = (n, n, n)
+    x, y, z = lattice_positions(n_cell, prob_lo, prob_hi, ppc)
+    dx = lx / n
+    wp = np.sqrt(2.0 * n0 * Q_E ** 2 / (EP0 * M_E))   # inputs_base_3d:8
+    kp = wp / C
+    k = 2.0 * 2.0 * np.pi / lx
+    a = epsilon * k / kp
+    ux = a * np.sin(k * x) * np.cos(k * y) * np.cos(k * z)
+    uy = a * np.cos(k * x) * np.sin(k * y) * np.cos(k * z)
+    uz = a * np.cos(k * x) * np.cos(k * y) * np.sin(k * z)
+    w = np.full_like(x, n0 * dx ** 3 / (ppc[0] * ppc[1] * ppc[2]))
+    species = [
+        dict(name="electrons", q=-Q_E, m=M_E, x=x, y=y, z=z, w=w, ux=ux * C, uy=uy * C, uz=uz * C),
+        dict(name="positrons", q=Q_E, m=M_E, x=x.copy(), y=y.copy(), z=z.copy(), w=w.copy(),
+             ux=-ux * C, uy=-uy * C, uz=-uz * C),
+    ]
+    return dict(n_cell=n_cell, prob_lo=prob_lo, prob_hi=prob_hi, species=species,
+                analytic=dict(k=k, wp=wp, epsilon=epsilon))
+
+
+def philox_normal(seed, first_id, count, ncomp=3):
+    """Counter-based N(0,1) numbers: particle `id` always gets the same values, independent of how
+    the domain is decomposed.  numpy Philox4x64 keyed by `seed`,
+    advanced to the particle id (one 4x64 block = 4 uint64 -> 2 Box-Muller pairs per particle)."""
+    bg = np.random.Philox(key=seed)
+    bg.advance(int(first_id))            # one counter increment per particle
+    raw = bg.random_raw(4 * count).reshape(count, 4)
+    u = (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)   # [0,1)
+    u1 = 1.0 - u[:, 0:2]                 # (0,1]
+    r = np.sqrt(-2.0 * np.log(u1))
+    th = 2.0 * np.pi * u[:, 2:4]
+    g = np.stack([r[:, 0] * np.cos(th[:, 0]), r[:, 0] * np.sin(th[:, 0]), r[:, 1] * np.cos(th[:, 1])],
+                 axis=1)
+    return g[:, :ncomp]
+
+
+def uniform_plasma_3d(n=256, ppc=(2, 2, 2), lx=40.0e-6, density=1.0e25, u_th=0.01,
+                      seed=20240923, box_lo=None, box_hi=None, perturbation=0.0, n_cell=None):
+    """Config 2 / 3 / 5: Examples/Physics_applications/uniform_plasma/inputs_base_3d scaled up:
+    electrons only, thermal u/c ~ N(0, u_th^2) per component from a counter-based generator so
+    that every decomposition sees the same particles.  `perturbation` adds the (non-chaotic)
+    Langmuir mode of config 1 on top."""
+    n_cell = (n, n, n) if n_cell is None else tuple(n_cell)
+    prob_lo, prob_hi = (-lx / 2,) * 3, (lx / 2,) * 3
+    lo = np.zeros(3, dtype=int) if box_lo is None else np.asarray(box_lo)
+    hi = np.asarray(n_cell) - 1 if box_hi is None else np.asarray(box_hi)
+    x, y, z = lattice_positions(n_cell, prob_lo, prob_hi, ppc, lo, hi)
+    nppc = ppc[0] * ppc[1] * ppc[2]
+    dxs = [lx / n_cell[d] for d in range(3)]
+    w = np.full_like(x, density * dxs[0] * dxs[1] * dxs[2] / nppc)
+    # global particle id = global cell number * nppc + in-cell index  (decomposition independent)
+    idx = [np.arange(lo[d], hi[d] + 1) for d in range(3)]
+    K, J, I = np.meshgrid(idx[2], idx[1], idx[0], indexing="ij")
+    gcell = (I + n_cell[0] * (J + n_cell[1] * K)).ravel().astype(np.int64)
+    u = np.empty((gcell.size * nppc, 3))
+    if box_lo is None and box_hi is None:
+        u[:] = philox_normal(seed, 0, gcell.size * nppc)
+    else:
+        # rows of consecutive cells along i are consecutive ids
+        ni = hi[0] - lo[0] + 1
+        rows = gcell.reshape(-1, ni)[:, 0]
+        for r, first_cell in enumerate(rows):
+            u[r * ni * nppc:(r + 1) * ni * nppc] = philox_normal(seed, int(first_cell) * nppc, ni * nppc)
+    u *= u_th * C
+    if perturbation:
+        k = 2.0 * 2.0 * np.pi / lx
+        wp = np.sqrt(density * Q_E ** 2 / (EP0 * M_E))
+        a = perturbation * k / (wp / C) * C
+        u[:, 0] += a * np.sin(k * x) * np.cos(k * y) * np.cos(k * z)
+        u[:, 1] += a * np.cos(k * x) * np.sin(k * y) * np.cos(k * z)
+        u[:, 2] += a * np.cos(k * x) * np.cos(k * y) * np.sin(k * z)
+    species = [dict(name="electrons", q=-Q_E, m=M_E, x=x, y=y, z=z, w=w,
+                    ux=np.ascontiguousarray(u[:, 0]), uy=np.ascontiguousarray(u[:, 1]),
+                    uz=np.ascontiguousarray(u[:, 2]))]
+    return dict(n_cell=n_cell, prob_lo=prob_lo, prob_hi=prob_hi, species=species)
