@@ -1,0 +1,289 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: particle-steps/s of the explicit EM-PIC step on the 3D
+uniform-plasma workload of BASELINE.json (configs[1]: 256^3 cells per GPU, 8 particles per cell,
+Yee FDTD, Boris pusher, order-3 Esirkepov deposition, fp64).
+
+    python bench.py --gpus N --steps K --warmup W                    # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU algorithm (oracle)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (3D uniform plasma, 256^3, 8 ppc)"
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": FALLBACK_HBM_GBS}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(n, ppc, steps, warmup, nox=3):
+    """The reference algorithm on the host cores: the oracle's whole-loop driver (OpenMP, all
+    cores) on a bounded sample of the workload (n^3 cells of the same plasma).  Test infrastructure
+    used as the measured CPU baseline -- the only place bench.py executes oracle/."""
+    from oracle import oracle
+    from warpx_b200 import workloads
+    oracle.build(ref=False)
+    # same cell size and plasma as the GPU run (dx = 40um/256), smaller box
+    lx = 40.0e-6 * n / 256.0
+    wl = workloads.uniform_plasma_3d(n=n, ppc=ppc, lx=lx)
+    kind = "reference" if oracle.have_ref() else "restated"
+    sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind)
+    s = wl["species"][0]
+    sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    npart = len(s["x"])
+    sim.evolve(max(warmup, 1), synchronize_last=False)
+    t0 = time.perf_counter()
+    sim.evolve(steps, synchronize_last=False)
+    dt = time.perf_counter() - t0
+    cores = sim.L.orc_num_threads()
+    return dict(value=npart * steps / dt, unit="particle-steps/s", cores=cores,
+                kind="reference-leaves+port" if kind == "reference" else "port",
+                sample="%d^3 cells x %d ppc (%d particles), order %d, %d steps, OpenMP %d threads; "
+                       "oracle = loop-for-loop restatement of the reference CPU path"
+                       % (n, ppc[0] * ppc[1] * ppc[2], npart, nox, steps, cores),
+                seconds=dt, ms_per_step=1e3 * dt / steps, timers=sim.timers())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ppc = (2, 2, 2)
+    r = cpu_reference_run(args.cpu_n, ppc, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D uniform plasma, Yee FDTD, Boris, order-3 Esirkepov, 8 ppc; CPU sample "
+                                   + r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_engine(args):
+    import numpy as np
+    import torch
+    from warpx_b200 import workloads
+    from warpx_b200.engine import Simulation
+    from warpx_b200.lib import lib
+    from warpx_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = lib()
+
+    n, ppc = args.n, (2, 2, 2)
+    nb = parallel.brick_grid(world)
+    n_cell = tuple(n * nb[d] for d in range(3))               # weak scaling: n^3 cells per GPU
+    lx = 40.0e-6 * np.array(nb)                                # same dx as configs[1]
+    dec = parallel.Decomposition(n_cell, nb, rank)
+    prob_lo = tuple(-0.5 * lx); prob_hi = tuple(0.5 * lx)
+
+    # ---- synthetic input, generated on the host into pinned memory (seeded, counter based) ----
+    t_gen = time.perf_counter()
+    wl = workloads.uniform_plasma_3d(n_cell=n_cell, ppc=ppc, lx=tuple(lx), box_lo=dec.box_lo if world > 1 else None,
+                                     box_hi=dec.box_hi if world > 1 else None)
+    s = wl["species"][0]
+    names = ("x", "y", "z", "w", "ux", "uy", "uz")
+    pinned = {k: torch.from_numpy(s[k]).pin_memory() for k in names}
+    npart_local = len(s["x"])
+    t_gen = time.perf_counter() - t_gen
+
+    def make_sim():
+        sim = Simulation(n_cell, prob_lo, prob_hi, nox=3, dist=dist, sort_interval=args.sort_interval)
+        sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
+        return sim
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # =================== device-resident measurement (`value`) ===================
+    sim = make_sim()
+    ntot = sim.total_particles()
+    sim.Evolve(args.warmup, synchronize_last=False)
+    sim.enable_stage_timing(True)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.pic_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sim.Evolve(args.steps, synchronize_last=False)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = L.pic_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    stage = sim.stage_ms()
+    fe = sim.field_energy()
+    value = ntot * args.steps / (ms * 1e-3)
+
+    # =================== end-to-end through the public API (`e2e`) ===================
+    # Job-level: every rank uploads its initial particle state from pinned host memory, runs K
+    # steps through Simulation.Evolve, and reads the FieldEnergy reduced diagnostic back to the
+    # host after EVERY step (what a WarpX run with reduced diagnostics does).
+    del sim
+    torch.cuda.empty_cache()
+    barrier()
+    t0 = time.perf_counter()
+    sim2 = make_sim()
+    d2h = 0
+    for _ in range(args.steps):
+        sim2.Evolve(1, synchronize_last=False)
+        sim2.field_energy()
+        d2h += 16
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    h2d_total = npart_local * 7 * 8
+    e2e = {"value": ntot * args.steps / t_e2e, "unit": "particle-steps/s",
+           "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "definition": "job-level: H2D upload of the initial particle state from pinned host memory + initial "
+                         "cell sort + K steps via Simulation.Evolve + per-step D2H of the FieldEnergy diagnostic, "
+                         "wall clock, max over ranks"}
+    del sim2
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # =================== roofline of the kernels (algorithmic bytes / CUDA-event time) ==========
+    peaks, peak_src = measured_peaks()
+    hbm = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+    ncell = n ** 3
+    alg = {  # bytes per launch, DESIGN.md "Kernels"
+        "evolve_b": 72.0 * ncell,
+        "evolve_e": 96.0 * ncell,
+        "gather_push": 96.0 * npart_local + 48.0 * ncell,
+        "deposit": 56.0 * npart_local + 72.0 * ncell,
+    }
+    kernels = {}
+    for k, b in alg.items():
+        if k in stage:
+            t_ms, calls = stage[k]
+            kernels[k] = {"ms": t_ms, "calls": calls, "achieved_gbs": b / (t_ms * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": b / (t_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": b}
+    dom = max((k for k in kernels), key=lambda k: kernels[k]["ms"] * kernels[k]["calls"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "kernels": kernels,
+                "note": "gather_push and deposit are fp64-FMA / shared-memory bound at order 3 (DESIGN.md); the "
+                        "HBM fraction is reported because BASELINE.json asks for it"}
+
+    cpu = cpu_reference_run(args.cpu_n, ppc, 2, 1)
+    line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D uniform plasma %dx%dx%d cells (%d^3 per GPU), 8 ppc (%d particles), Yee FDTD, "
+                                   "Boris pusher, order-3 Esirkepov, Galerkin gather, cfl 1, u_th 0.01c, "
+                                   "cell sort every %d steps" % (n_cell + (n, ntot, args.sort_interval)),
+                       "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
+                                                     % (npart_local * 56 / 1e9)},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "stage_ms": {k: v[0] for k, v in stage.items()}, "field_energy_J": list(fe),
+            "host_generation_s": t_gen}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per GPU and direction")
+    ap.add_argument("--cpu-n", type=int, default=48, help="cells per direction of the CPU sample")
+    ap.add_argument("--sort-interval", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,14 +64,21 @@ enum { PIC_PUSHER_BORIS = 0, PIC_PUSHER_VAY = 1, PIC_PUSHER_HC = 2 };
 
 /* Cell bins of a cell-sorted particle tile == amrex::DenseBins as built by
  * SortParticlesForDeposition / the shared-memory deposition path
- * (Source/Particles/WarpXParticleContainer.cpp:493-540, MultiParticleContainer.cpp:615-624).
- * Cells are numbered i + nx*(j + ny*k) over the rank's valid box [box_lo, box_hi].
- * Particles of cell c are [cell_start[c], cell_start[c+1]).  Optional everywhere (NULL =
- * particle order unknown -> order-agnostic kernels). */
+ * (Source/Particles/WarpXParticleContainer.cpp:493-540, MultiParticleContainer.cpp:615-624;
+ * the reference's bins are likewise grouped by a tile of WarpX::shared_tilesize cells,
+ * Source/WarpX.cpp:126,133).
+ * Cells of the rank's valid box [box_lo, box_hi] are numbered SUPERCELL-MAJOR: the box is cut
+ * into supercells of tile[0] x tile[1] x tile[2] cells (partial supercells at the high ends are
+ * padded), supercell t = ti + ntx*(tj + nty*tk), and inside a supercell
+ * l = li + tile[0]*(lj + tile[1]*lk); bin id = t*tile[0]*tile[1]*tile[2] + l.
+ * Particles of bin b are [cell_start[b], cell_start[b+1]).  All particles of one supercell are
+ * therefore contiguous.  pic_bins_count() gives the (padded) number of bins.
+ * Optional everywhere (NULL = particle order unknown -> order-agnostic kernels). */
 typedef struct pic_bins {
-    const int* cell_start;  /* ncell+1 entries, device */
+    const int* cell_start;  /* pic_bins_count()+1 entries, device              */
     int box_lo[3];          /* first cell of the box                           */
     int box_hi[3];          /* last cell of the box, inclusive                 */
+    int tile[3];            /* supercell size in cells (8,8,8 is what the kernels are tuned for) */
 } pic_bins;
 
 /* Domain description for the periodic / neighbour guard-cell operations
@@ -167,11 +174,13 @@ int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* strea
 
 /* Counting sort of the particles by cell over the valid box [box_lo,box_hi]
  * (WarpX: mypc->SortParticlesByBin, WarpXEvolve.cpp:575-580).  `in` is permuted into `out`;
- * cell_start (ncell+1 ints) receives the bins.  work must hold pic_sort_workspace_bytes(). */
-long pic_sort_workspace_bytes(long np, long ncell);
+ * bins->cell_start (pic_bins_count()+1 ints) receives the bins.  work must hold
+ * pic_sort_workspace_bytes(). */
+long pic_bins_count(const int box_lo[3], const int box_hi[3], const int tile[3]);
+long pic_sort_workspace_bytes(long np, long nbins);
 int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_geom* g,
-                               const int box_lo[3], const int box_hi[3],
-                               int* cell_start, void* work, void* stream);
+                               const pic_bins* bins /* cell_start is written */,
+                               void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Reduced diagnostics used as parity metrics

@@ -1,0 +1,205 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's golden vectors and against the
+reference's own leaf headers; host logic of the decomposition."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from warpx_b200 import abi, workloads
+
+
+def _close(v, g, rtol=1e-9):
+    return abs(v - g) <= rtol * abs(g) + 1e-40
+
+
+def test_langmuir_golden_checksums(orc, golden):
+    """Config 1 == Examples/Tests/langmuir/inputs_test_3d_langmuir_multi; WarpX's own regression
+    checksums at its own tolerance (Regression/Checksum/checksum.py:219: rtol 1e-9)."""
+    wl = workloads.langmuir_3d()
+    sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=1)
+    assert sim.guards() == {"ng_EB": [2, 2, 2], "ng_J": [2, 2, 2], "ng_FG": [1, 1, 1], "ng_FS": [1, 1, 1]}
+    assert sim.dt == pytest.approx(1.203645750966544e-15, rel=1e-14)
+    for s in wl["species"]:
+        sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.evolve(40)
+    g = golden["test_3d_langmuir_multi"]
+    for c, name in enumerate(abi.COMP_NAMES):
+        assert _close(sim.checksum_field(c), g["lev=0"][name]), name
+    for isp, sname in enumerate(("electrons", "positrons")):
+        P = sim.particles(isp)
+        vals = {"particle_position_x": P["x"], "particle_position_y": P["y"], "particle_position_z": P["z"],
+                "particle_momentum_x": P["ux"] * workloads.M_E, "particle_momentum_z": P["uz"] * workloads.M_E,
+                "particle_weight": P["w"]}
+        for key, gv in g[sname].items():
+            assert _close(float(np.sum(np.abs(vals[key]))), gv), (sname, key)
+    # analytic Langmuir field, 5 % (Examples/Tests/langmuir/analysis_3d.py:77-91,124-164)
+    an = wl["analytic"]
+    t = 40 * sim.dt
+    d, ex = sim.fab(0)
+    n = wl["n_cell"][0]
+    dx = (wl["prob_hi"][0] - wl["prob_lo"][0]) / n
+    exv = ex[d.valid_slices()]
+    x = wl["prob_lo"][0] + (np.arange(n) + 0.5) * dx           # Ex: cell-centred in x
+    yz = wl["prob_lo"][1] + np.arange(n + 1) * dx              # nodal in y, z
+    Z, Y, X = np.meshgrid(yz, yz, x, indexing="ij")
+    k, wp, eps = an["k"], an["wp"], an["epsilon"]
+    e_th = eps * (workloads.M_E * workloads.C ** 2 * k / workloads.Q_E) * np.sin(k * X) * np.cos(k * Y) \
+        * np.cos(k * Z) * np.sin(wp * t)
+    assert np.max(np.abs(exv - e_th)) / np.max(np.abs(e_th)) < 0.05
+
+
+@pytest.mark.parametrize("pusher,name", [(abi.PUSHER_HC, "higuera_cary"), (abi.PUSHER_VAY, "vay"),
+                                         (abi.PUSHER_BORIS, "boris")])
+def test_particle_pusher_known_answer(orc, golden, pusher, name):
+    """Examples/Tests/particle_pusher: force-free E x B drift at gamma = 20, 10 000 steps.
+    |x| < 1e-3 for Vay / Higuera-Cary, documented error magnitudes (analysis.py:17-21), and the
+    stored checksums for the Higuera-Cary run."""
+    L = orc.lib()
+    half = 2.077023075927835e+07
+    dx = 2 * half / 8
+    dt = 1.0 / (math.sqrt(3.0 / dx ** 2) * workloads.C)
+    q = m = 1.0
+    u = (C.c_double * 3)(0.0, 19.974984355438178 * workloads.C, 0.0)
+    x = (C.c_double * 3)(0.0, 0.0, 0.0)
+    EB = (C.c_double * 6)(-2.994174829214179e+08, 0.0, 0.0, 0.0, 0.0, 1.0)
+    P = orc.HostParticles(x=[0.0], y=[0.0], z=[0.0], w=[0.0], ux=[0.0], uy=[0.0], uz=[0.0])
+    geom = abi.make_geom((8, 8, 8), (-half,) * 3, (half,) * 3)
+    L.orc_push_momentum(pusher, u, EB, q, m, -0.5 * dt)        # first step: u^0 -> u^{-1/2}
+    for n in range(10000):
+        L.orc_push_momentum(pusher, u, EB, q, m, dt)
+        L.orc_update_position(x, u, dt)
+        if n == 9999:
+            L.orc_push_momentum(pusher, u, EB, q, m, 0.5 * dt)  # Synchronize()
+        P.x[0], P.y[0], P.z[0] = x[0], x[1], x[2]
+        L.orc_wrap_periodic(C.byref(P.soa), C.byref(geom))
+        x[0], x[1], x[2] = P.x[0], P.y[0], P.z[0]
+    expected = golden["_provenance"]["pusher_expected_error"][name]
+    assert abs(x[0]) == pytest.approx(expected, rel=2e-4)
+    if pusher != abi.PUSHER_BORIS:
+        assert abs(x[0]) < 1e-3
+    if pusher == abi.PUSHER_HC:
+        g = golden["test_3d_particle_pusher"]["positron"]
+        assert _close(abs(x[0]), g["particle_position_x"], 1e-9)
+        assert _close(abs(x[1]), g["particle_position_y"], 1e-9)
+        assert _close(abs(u[0] * m), g["particle_momentum_x"], 1e-9)
+        assert _close(abs(u[1] * m), g["particle_momentum_y"], 1e-9)
+
+
+def test_restated_leaves_match_reference_headers_bitwise(orc):
+    """The hand-restated leaf arithmetic vs the reference's own headers compiled verbatim
+    (oracle/_ref): identical bits on shape factors, pushers, stencil coefficients and dt."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    A, B = orc.lib("restated"), orc.lib("reference")
+    assert A.orc_leaf_name() == b"restated" and B.orc_leaf_name() == b"reference"
+    rng = np.random.default_rng(7)
+    for order in range(0, 5):
+        for x in rng.uniform(0.0, 40.0, 400):
+            sa, sb = (C.c_double * 8)(), (C.c_double * 8)()
+            assert A.orc_shape(order, x, sa) == B.orc_shape(order, x, sb)
+            assert list(sa) == list(sb)
+            i_new = A.orc_shape(order, x, sa)
+            xo = x + rng.uniform(-0.999, 0.999)
+            sa, sb = (C.c_double * 8)(), (C.c_double * 8)()
+            assert A.orc_shifted_shape(order, xo, i_new, sa) == B.orc_shifted_shape(order, xo, i_new, sb)
+            assert list(sa) == list(sb)
+    for pusher in (0, 1, 2):
+        for _ in range(300):
+            u0 = rng.normal(0, 3e8, 3)
+            eb = np.concatenate([rng.normal(0, 1e11, 3), rng.normal(0, 300.0, 3)])
+            ua, ub = (C.c_double * 3)(*u0), (C.c_double * 3)(*u0)
+            ebc = (C.c_double * 6)(*eb)
+            A.orc_push_momentum(pusher, ua, ebc, -workloads.Q_E, workloads.M_E, 1.3e-16)
+            B.orc_push_momentum(pusher, ub, ebc, -workloads.Q_E, workloads.M_E, 1.3e-16)
+            assert list(ua) == list(ub)
+            xa, xb = (C.c_double * 3)(1e-6, 2e-6, 3e-6), (C.c_double * 3)(1e-6, 2e-6, 3e-6)
+            A.orc_update_position(xa, ua, 1.3e-16)
+            B.orc_update_position(xb, ub, 1.3e-16)
+            assert list(xa) == list(xb)
+    for algo in (0, 1):
+        for dx in ([1e-6, 1e-6, 1e-6], [1e-6, 2e-6, 0.5e-6]):
+            sa, sb = abi.pic_stencil(), abi.pic_stencil()
+            dxc = (C.c_double * 3)(*dx)
+            A.orc_stencil_coefs(algo, dxc, C.byref(sa))
+            B.orc_stencil_coefs(algo, dxc, C.byref(sb))
+            assert list(sa.cx) == list(sb.cx) and list(sa.cy) == list(sb.cy) and list(sa.cz) == list(sb.cz)
+            assert A.orc_max_dt(algo, dxc) == B.orc_max_dt(algo, dxc)
+
+
+def test_restated_stages_match_reference_headers_bitwise(orc):
+    """Whole stages (FDTD Yee/CKC, gather+push, deposition) with restated vs reference leaves."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from helpers import random_fields, lower_corner
+    A, B = orc.lib("restated"), orc.lib("reference")
+    n = 12
+    box_lo, box_hi = (0, 0, 0), (n - 1,) * 3
+    prob_lo, prob_hi = (-1e-5,) * 3, (1e-5,) * 3
+    dx = [(prob_hi[d] - prob_lo[d]) / n for d in range(3)]
+    A.orc_set_num_threads(1); B.orc_set_num_threads(1)
+    for algo in (0, 1):
+        st = abi.pic_stencil()
+        A.orc_stencil_coefs(algo, (C.c_double * 3)(*dx), C.byref(st))
+        res = []
+        for L in (A, B):
+            F = random_fields(orc, box_lo, box_hi, (2, 2, 2), 3, comps=range(9), scale=[1e9] * 3 + [3.0] * 3 + [1e12] * 3)
+            E, Bf, J = orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), orc.fab_array(F[6:9])
+            L.orc_evolve_b(Bf, E, C.byref(st), 1e-15)
+            L.orc_evolve_e(E, Bf, J, C.byref(st), 2e-15)
+            res.append([f.a.copy() for f in F])
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+    wl = workloads.uniform_plasma_3d(n_cell=(n, n, n), ppc=(2, 1, 1), u_th=0.2, lx=2e-5)
+    sp = wl["species"][0]
+    for nox in (1, 2, 3):
+        ngEB = (4, 4, 4)
+        xyzmin, lo = lower_corner(prob_lo, dx, box_lo, ngEB)
+        dinv = [1.0 / v for v in dx]
+        res = []
+        for L in (A, B):
+            F = random_fields(orc, box_lo, box_hi, ngEB, 5, comps=range(9), scale=[1e10] * 3 + [30.0] * 3 + [0.0] * 3)
+            P = orc.HostParticles(**{k: sp[k] for k in orc.HostParticles.NAMES})
+            for pusher in (0, 1, 2):
+                L.orc_gather_push(C.byref(P.soa), 0, P.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
+                                  abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], 2e-15,
+                                  nox, 1, pusher, 1)
+            L.orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(F[6:9]), abi.dbl3(dinv),
+                                    abi.dbl3(xyzmin), abi.int3(lo), sp["q"], 2e-15, -1e-15, nox)
+            res.append([P.x.copy(), P.ux.copy(), P.uz.copy()] + [f.a.copy() for f in F[6:9]])
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+
+
+def test_decomposition_independence_of_oracle(orc):
+    """One box vs a 2x2x1 brick grid (the multi-GPU oracle): same physics after 6 steps."""
+    wl = workloads.uniform_plasma_3d(n_cell=(16, 16, 16), ppc=(1, 1, 2), u_th=0.05, lx=8e-6, perturbation=0.02)
+    sp = wl["species"][0]
+    out = []
+    for nb in ((1, 1, 1), (2, 2, 1)):
+        sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, nb=nb)
+        sim.add_species(sp["q"], sp["m"], sp["x"], sp["y"], sp["z"], sp["w"], sp["ux"], sp["uy"], sp["uz"])
+        sim.evolve(6)
+        P = sim.particles(0)
+        order = np.lexsort((P["z"], P["y"], P["x"]))
+        out.append((sim.field_energy(), [sim.checksum_field(c) for c in range(9)], {k: v[order] for k, v in P.items()}))
+    (e1, c1, p1), (e2, c2, p2) = out
+    assert e1[0] == pytest.approx(e2[0], rel=1e-11) and e1[1] == pytest.approx(e2[1], rel=1e-9)
+    for a, b in zip(c1, c2):
+        assert a == pytest.approx(b, rel=1e-10)
+    for k in p1:
+        scale = np.max(np.abs(p1[k]))
+        assert np.max(np.abs(p1[k] - p2[k])) <= 1e-11 * scale
+
+
+def test_counter_based_momenta_are_decomposition_independent():
+    full = workloads.uniform_plasma_3d(n_cell=(8, 8, 8), ppc=(2, 2, 2), lx=4e-6)["species"][0]
+    part = workloads.uniform_plasma_3d(n_cell=(8, 8, 8), ppc=(2, 2, 2), lx=4e-6, box_lo=(4, 0, 4),
+                                       box_hi=(7, 7, 7))["species"][0]
+    key = lambda s: np.round(np.stack([s["x"], s["y"], s["z"]], 1) * 1e12).astype(np.int64)
+    kf = {tuple(k): i for i, k in enumerate(key(full))}
+    idx = np.array([kf[tuple(k)] for k in key(part)])
+    for c in ("ux", "uy", "uz"):
+        assert np.array_equal(full[c][idx], part[c])
+    u = full["ux"] / workloads.C
+    assert abs(np.std(u) - 0.01) < 0.001 and abs(np.mean(u)) < 0.001

@@ -36,7 +36,8 @@ class pic_stencil(C.Structure):
 
 
 class pic_bins(C.Structure):
-    _fields_ = [("cell_start", C.c_void_p), ("box_lo", C.c_int * 3), ("box_hi", C.c_int * 3)]
+    _fields_ = [("cell_start", C.c_void_p), ("box_lo", C.c_int * 3), ("box_hi", C.c_int * 3),
+                ("tile", C.c_int * 3)]
 
 
 class pic_geom(C.Structure):
@@ -45,6 +46,7 @@ class pic_geom(C.Structure):
 
 
 SOLVER_YEE, SOLVER_CKC = 0, 1
+PIC_ERR_ABORT, PIC_ERR_RETURN = 0, 1
 PUSHER_BORIS, PUSHER_VAY, PUSHER_HC = 0, 1, 2
 
 # Yee staggering of WarpX (Source/WarpX.cpp:2117-2125): 1 = nodal.  Order Ex Ey Ez Bx By Bz jx jy jz.

@@ -1,0 +1,57 @@
+// Per-particle quantities of the Esirkepov deposition, shared by the global-atomic kernel and the
+// shared-memory tile kernel.  Follows Source/Particles/Deposition/CurrentDeposition.H:683-788.
+#ifndef PIC_DEPOSIT_COMMON_CUH_
+#define PIC_DEPOSIT_COMMON_CUH_
+#include "pic_common.cuh"
+
+namespace pic {
+
+struct DepositGeom {
+    double dinv[3];
+    double xyzmin[3];
+    int lo[3];
+    double q;
+    double dt;
+    double tshift;      // relative_time + 0.5*dt  (CurrentDeposition.H:725)
+    double invdtd[3];   // (1/dt)*dinv.y*dinv.z, ... (:671-673)
+};
+
+template <int N>
+struct EsirkepovWeights {
+    double sx_new[N + 3], sx_old[N + 3];
+    double sy_new[N + 3], sy_old[N + 3];
+    double sz_new[N + 3], sz_old[N + 3];
+    int i_new, j_new, k_new;
+    int dil, diu, djl, dju, dkl, dku;
+    double wqx, wqy, wqz;
+
+    __device__ __forceinline__ void compute(double xp, double yp, double zp, double wp, double uxp,
+                                            double uyp, double uzp, const DepositGeom& dg) {
+        const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);
+        const double wq = dg.q * wp;                                     // :691
+        wqx = wq * dg.invdtd[0]; wqy = wq * dg.invdtd[1]; wqz = wq * dg.invdtd[2];
+        // new and old positions in grid units (:725-736)
+        const double x_new = (xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0];
+        const double x_old = x_new - dg.dt * dg.dinv[0] * uxp * gaminv;
+        const double y_new = (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1];
+        const double y_old = y_new - dg.dt * dg.dinv[1] * uyp * gaminv;
+        const double z_new = (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2];
+        const double z_old = z_new - dg.dt * dg.dinv[2] * uzp * gaminv;
+#pragma unroll
+        for (int n = 0; n < N + 3; ++n) {
+            sx_new[n] = sx_old[n] = sy_new[n] = sy_old[n] = sz_new[n] = sz_old[n] = 0.0;
+        }
+        i_new = shape_factor<N>(sx_new + 1, x_new);                      // :759-773
+        const int i_old = shifted_shape_factor<N>(sx_old, x_old, i_new);
+        j_new = shape_factor<N>(sy_new + 1, y_new);
+        const int j_old = shifted_shape_factor<N>(sy_old, y_old, j_new);
+        k_new = shape_factor<N>(sz_new + 1, z_new);
+        const int k_old = shifted_shape_factor<N>(sz_old, z_old, k_new);
+        dil = (i_old < i_new) ? 0 : 1; diu = (i_old > i_new) ? 0 : 1;   // :777-788
+        djl = (j_old < j_new) ? 0 : 1; dju = (j_old > j_new) ? 0 : 1;
+        dkl = (k_old < k_new) ? 0 : 1; dku = (k_old > k_new) ? 0 : 1;
+    }
+};
+
+}  // namespace pic
+#endif

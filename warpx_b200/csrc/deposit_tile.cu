@@ -1,0 +1,322 @@
+// Shared-memory Esirkepov deposition for cell-sorted particles (the timed path).
+//
+// One CTA per supercell (pic_bins.tile, tuned for 8x8x8 cells).  The CTA owns a shared-memory
+// block of J covering the supercell plus the deposition halo, 3 components, fp64.
+//
+// The reference (CurrentDeposition.H:792-824) scatters (N+2)(N+3)^2 x 3 values per particle with
+// one fp64 global atomic each.  Here the scatter is reorganised around the structure of the
+// Esirkepov stencil: for one particle,
+//     Jx[i][j][k] += cdsx[i] * Wx[j][k],   cdsx[i] = sum_{i'<=i} wq/(dt dy dz) (Sx_old[i'] - Sx_new[i']),
+//     Wx[j][k]    = Sy_new[j] Az[k] + Sy_old[j] Bz[k],  Az = Sz_new/3 + Sz_old/6, Bz = Sz_old/3 + Sz_new/6
+// (and cyclically for Jy, Jz) -- an outer product of a (N+2)-vector and a (N+3)^2 matrix.
+// A warp works in two alternating phases on chunks of CH consecutive (cell-sorted) particles:
+//   phase 1 (lane = particle): positions, shape factors, prefix sums -> per-particle record in smem;
+//   phase 2 (lane = stencil line): lane (a, bh) owns the lines {(a, b)} of all three components
+//       and keeps their (N+2) partial sums in REGISTERS; it walks the particles of the chunk
+//       serially.  All particles of a run with the same stencil anchor (same new cell) accumulate
+//       into the same registers -- this is the warp-segmented reduction: the segment is the run,
+//       the reduction happens in registers without any atomic or shuffle.
+//   At the end of a run the registers are added to the shared J block (smem CAS-add, the lanes of
+//   a warp hit distinct addresses); at the end of the CTA the block is added to global J with one
+//   pass of coalesced fp64 reductions (the halo overlaps neighbouring supercells).
+// Particles whose stencil does not fit the block (drifted since the last sort) take the
+// per-particle global-atomic path, so any particle order is CORRECT; sorted order is FAST.
+#include "pic_common.cuh"
+#include "deposit_common.cuh"
+#include "bins.cuh"
+
+namespace pic {
+
+constexpr int DT_MARGIN_LO = 3;   // block starts 3 points below the supercell
+constexpr int DT_EXTRA = 7;       // block extent = tile + 7  (cell_new in [t0-1, t0+T], window -2..+3)
+
+template <int N> struct TileCfg {
+    static constexpr int S = N + 3;                 // window slots per direction
+    static constexpr int PN = N + 2;                // prefix entries actually deposited
+    static constexpr int NB = (S * S + 31) / 32;    // b values per lane
+    static constexpr int BH = (S + NB - 1) / NB;    // lane rows
+    static constexpr int NLANES = S * BH;           // active lanes in phase 2
+    // record fields: sn/so for x,y (4*S) ; A,B for y,z (4*S) ; cds x,y,z (3*PN)
+    static constexpr int F_SNX = 0, F_SOX = S, F_SNY = 2 * S, F_SOY = 3 * S;
+    static constexpr int F_AY = 4 * S, F_BY = 5 * S, F_AZ = 6 * S, F_BZ = 7 * S;
+    static constexpr int F_CDS = 8 * S;             // + comp*PN + i
+    static constexpr int NF = 8 * S + 3 * PN;
+};
+
+// shifted (old-position) weights without dynamic indexing: slot s holds w[s-1-sh], sh in {-1,0,1}
+template <int N>
+__device__ __forceinline__ void place_old(double* so /*N+3*/, const double* w /*N+1*/, int sh) {
+#pragma unroll
+    for (int s = 0; s < N + 3; ++s) {
+        const double wm = (s <= N) ? w[s] : 0.0;                  // sh = -1 -> index s
+        const double w0 = (s >= 1 && s - 1 <= N) ? w[s - 1] : 0.0;  // sh =  0 -> index s-1
+        const double wp = (s >= 2) ? w[s - 2] : 0.0;              // sh = +1 -> index s-2
+        so[s] = (sh < 0) ? wm : ((sh == 0) ? w0 : wp);
+    }
+}
+
+// one direction of the Esirkepov weights; returns i_new (leftmost index of the new stencil)
+template <int N>
+__device__ __forceinline__ int dir_weights(double x_new, double x_old, double* sn /*N+3*/,
+                                           double* so /*N+3*/, int& dl, int& du) {
+    double wn[N + 1], wo[N + 1];
+    const int i_new = shape_factor<N>(wn, x_new);
+    sn[0] = 0.0; sn[N + 2] = 0.0;
+#pragma unroll
+    for (int s = 0; s <= N; ++s) sn[s + 1] = wn[s];
+    // old position: same formulas as the new one evaluated at x_old; its leftmost index relative
+    // to i_new decides the slot shift (ShapeFactors.H:93-156; floor for N = 1, truncation otherwise)
+    int i_old;
+    if constexpr (N == 1) {
+        const int i = (int)floor(x_old);
+        const double d = x_old - (double)i;
+        wo[0] = 1.0 - d; wo[1] = d;
+        i_old = i;
+    } else {
+        i_old = shape_factor<N>(wo, x_old);
+    }
+    const int sh = i_old - i_new;
+    place_old<N>(so, wo, sh);
+    dl = (i_old < i_new) ? 0 : 1;
+    du = (i_old > i_new) ? 0 : 1;
+    return i_new;
+}
+
+__device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
+
+template <int N, int CH, int NW>
+__global__ void __launch_bounds__(NW * 32)
+deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz, DepositGeom dg) {
+    using T = TileCfg<N>;
+    constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF;
+    constexpr int CHP = CH + 1;
+    extern __shared__ double smem[];
+    const int BD0 = bins.tile[0] + DT_EXTRA, BD1 = bins.tile[1] + DT_EXTRA, BD2 = bins.tile[2] + DT_EXTRA;
+    const int bvol = BD0 * BD1 * BD2;
+    double* jblk = smem;                                  // [3][BD2][BD1][BD0]
+    double* recs = smem + 3 * bvol;                       // [NW][NF][CHP]
+    int* keys = (int*)(recs + (size_t)NW * NF * CHP);     // [NW][CH]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int n = tid; n < 3 * bvol; n += NW * 32) jblk[n] = 0.0;
+
+    // supercell and its particle range
+    const int t = blockIdx.x;
+    int tc[3];
+    tile_coords(bins, t, tc);
+    const long tvol = (long)bins.tile[0] * bins.tile[1] * bins.tile[2];
+    const int p_begin = bins.cell_start[(long)t * tvol];
+    const int p_end = bins.cell_start[(long)(t + 1) * tvol];
+    // block origin in global index space (same for all three components: node-based weights)
+    const int o0 = bins.box_lo[0] + tc[0] * bins.tile[0] - DT_MARGIN_LO;
+    const int o1 = bins.box_lo[1] + tc[1] * bins.tile[1] - DT_MARGIN_LO;
+    const int o2 = bins.box_lo[2] + tc[2] * bins.tile[2] - DT_MARGIN_LO;
+    __syncthreads();
+
+    // contiguous share of the supercell's particles for this warp, in multiples of CH
+    const int npt = p_end - p_begin;
+    const int nchunks = (npt + CH - 1) / CH;
+    const int cpw = (nchunks + NW - 1) / NW;
+    const int c_begin = warp * cpw, c_end = min(nchunks, c_begin + cpw);
+
+    double* rec = recs + (size_t)warp * NF * CHP;
+    int* key = keys + warp * CH;
+
+    // phase-2 role of this lane
+    const int a = lane % S, bh = lane / S;
+    const bool active = lane < T::NLANES;
+    double acc[NB][3][PN];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < PN; ++i) acc[nb][c][i] = 0.0;
+    int cur = -1;
+
+    auto flush = [&](int k) {
+        if (k < 0 || !active) return;
+        const int ax = k % BD0, ay = (k / BD0) % BD1, az = k / (BD0 * BD1);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const int b = bh + nb * T::BH;
+            if (b < S) {
+#pragma unroll
+                for (int i = 0; i < PN; ++i) {
+                    // x: line (j=a, k=b), prefix along i ; y: line (i=a, k=b), prefix along j ;
+                    // z: line (i=a, j=b), prefix along k
+                    const double vx = acc[nb][0][i], vy = acc[nb][1][i], vz = acc[nb][2][i];
+                    if (vx != 0.0) smem_add(&jblk[0 * bvol + (ax + i) + BD0 * ((ay + a) + BD1 * (az + b))], vx);
+                    if (vy != 0.0) smem_add(&jblk[1 * bvol + (ax + a) + BD0 * ((ay + i) + BD1 * (az + b))], vy);
+                    if (vz != 0.0) smem_add(&jblk[2 * bvol + (ax + a) + BD0 * ((ay + b) + BD1 * (az + i))], vz);
+                    acc[nb][0][i] = 0.0; acc[nb][1][i] = 0.0; acc[nb][2][i] = 0.0;
+                }
+            }
+        }
+    };
+
+    for (int ch = c_begin; ch < c_end; ++ch) {
+        const int base = p_begin + ch * CH;
+        const int nval = min(CH, p_end - base);
+        // ---------------- phase 1: lane = particle ----------------
+        if (lane < nval) {
+            const long ip = base + lane;
+            const double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip], wp = P.w[ip];
+            const double uxp = P.ux[ip], uyp = P.uy[ip], uzp = P.uz[ip];
+            const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);
+            const double wq = dg.q * wp;
+            const double pos_new[3] = {(xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0],
+                                       (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1],
+                                       (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2]};
+            const double pos_old[3] = {pos_new[0] - dg.dt * dg.dinv[0] * uxp * gaminv,
+                                       pos_new[1] - dg.dt * dg.dinv[1] * uyp * gaminv,
+                                       pos_new[2] - dg.dt * dg.dinv[2] * uzp * gaminv};
+            double sn[3][S], so[3][S];
+            int inew[3], dl[3], du[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) inew[d] = dir_weights<N>(pos_new[d], pos_old[d], sn[d], so[d], dl[d], du[d]);
+            // anchor in block coordinates
+            const int ax = dg.lo[0] + inew[0] - 1 - o0, ay = dg.lo[1] + inew[1] - 1 - o1, az = dg.lo[2] + inew[2] - 1 - o2;
+            const bool fits = ax >= 0 && ay >= 0 && az >= 0 && ax + S <= BD0 && ay + S <= BD1 && az + S <= BD2;
+            key[lane] = fits ? (ax + BD0 * (ay + BD1 * az)) : -1;
+            if (fits) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    rec[(T::F_SNX + s) * CHP + lane] = sn[0][s];
+                    rec[(T::F_SOX + s) * CHP + lane] = so[0][s];
+                    rec[(T::F_SNY + s) * CHP + lane] = sn[1][s];
+                    rec[(T::F_SOY + s) * CHP + lane] = so[1][s];
+                    rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * sn[1][s] + (1.0 / 6.0) * so[1][s];
+                    rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * so[1][s] + (1.0 / 6.0) * sn[1][s];
+                    rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * sn[2][s] + (1.0 / 6.0) * so[2][s];
+                    rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * so[2][s] + (1.0 / 6.0) * sn[2][s];
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double wqd = wq * dg.invdtd[d];
+                    double run = 0.0;
+#pragma unroll
+                    for (int i = 0; i < PN; ++i) {
+                        run += wqd * (so[d][i] - sn[d][i]);
+                        // loop trimming of the reference (:777-788): entries outside [dl, N+1-du] are not deposited
+                        const bool live = (i >= dl[d]) && (i <= N + 1 - du[d]);
+                        rec[(T::F_CDS + d * PN + i) * CHP + lane] = live ? run : 0.0;
+                    }
+                }
+            } else {
+                // drifted particle: per-particle global reductions (reference strategy)
+                const int bi = dg.lo[0] + inew[0] - 1, bj = dg.lo[1] + inew[1] - 1, bk = dg.lo[2] + inew[2] - 1;
+                for (int k = dl[2]; k <= N + 2 - du[2]; ++k)
+                    for (int j = dl[1]; j <= N + 2 - du[1]; ++j) {
+                        double sd = 0.0;
+                        const double w2 = (1.0 / 3.0) * (sn[1][j] * sn[2][k] + so[1][j] * so[2][k])
+                                        + (1.0 / 6.0) * (sn[1][j] * so[2][k] + so[1][j] * sn[2][k]);
+                        for (int i = dl[0]; i <= N + 1 - du[0]; ++i) {
+                            sd += wq * dg.invdtd[0] * (so[0][i] - sn[0][i]) * w2;
+                            atomicAdd(&Jx(bi + i, bj + j, bk + k), sd);
+                        }
+                    }
+                for (int k = dl[2]; k <= N + 2 - du[2]; ++k)
+                    for (int i = dl[0]; i <= N + 2 - du[0]; ++i) {
+                        double sd = 0.0;
+                        const double w2 = (1.0 / 3.0) * (sn[0][i] * sn[2][k] + so[0][i] * so[2][k])
+                                        + (1.0 / 6.0) * (sn[0][i] * so[2][k] + so[0][i] * sn[2][k]);
+                        for (int j = dl[1]; j <= N + 1 - du[1]; ++j) {
+                            sd += wq * dg.invdtd[1] * (so[1][j] - sn[1][j]) * w2;
+                            atomicAdd(&Jy(bi + i, bj + j, bk + k), sd);
+                        }
+                    }
+                for (int j = dl[1]; j <= N + 2 - du[1]; ++j)
+                    for (int i = dl[0]; i <= N + 2 - du[0]; ++i) {
+                        double sd = 0.0;
+                        const double w2 = (1.0 / 3.0) * (sn[0][i] * sn[1][j] + so[0][i] * so[1][j])
+                                        + (1.0 / 6.0) * (sn[0][i] * so[1][j] + so[0][i] * sn[1][j]);
+                        for (int k = dl[2]; k <= N + 1 - du[2]; ++k) {
+                            sd += wq * dg.invdtd[2] * (so[2][k] - sn[2][k]) * w2;
+                            atomicAdd(&Jz(bi + i, bj + j, bk + k), sd);
+                        }
+                    }
+            }
+        }
+        __syncwarp();
+        // ---------------- phase 2: lane = stencil lines ----------------
+        for (int pp = 0; pp < nval; ++pp) {
+            const int k = key[pp];                 // warp-uniform
+            if (k < 0) continue;
+            if (k != cur) { flush(cur); cur = k; }
+            if (active) {
+                const double snx = rec[(T::F_SNX + a) * CHP + pp], sox = rec[(T::F_SOX + a) * CHP + pp];
+                const double sny = rec[(T::F_SNY + a) * CHP + pp], soy = rec[(T::F_SOY + a) * CHP + pp];
+                double cds[3][PN];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int i = 0; i < PN; ++i) cds[c][i] = rec[(T::F_CDS + c * PN + i) * CHP + pp];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int b = bh + nb * T::BH;
+                    if (b < S) {
+                        const double ay_ = rec[(T::F_AY + b) * CHP + pp], by_ = rec[(T::F_BY + b) * CHP + pp];
+                        const double az_ = rec[(T::F_AZ + b) * CHP + pp], bz_ = rec[(T::F_BZ + b) * CHP + pp];
+                        const double wx = sny * az_ + soy * bz_;   // Jx line (j=a, k=b)
+                        const double wy = snx * az_ + sox * bz_;   // Jy line (i=a, k=b)
+                        const double wz = snx * ay_ + sox * by_;   // Jz line (i=a, j=b)
+#pragma unroll
+                        for (int i = 0; i < PN; ++i) {
+                            acc[nb][0][i] += cds[0][i] * wx;
+                            acc[nb][1][i] += cds[1][i] * wy;
+                            acc[nb][2][i] += cds[2][i] * wz;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    flush(cur);
+    __syncthreads();
+
+    // ---------------- block -> global J (coalesced along i; halo overlaps neighbours) ----------
+    for (int n = tid; n < 3 * bvol; n += NW * 32) {
+        const double v = jblk[n];
+        if (v == 0.0) continue;
+        const int c = n / bvol, r = n - c * bvol;
+        const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
+        const FabView& J = (c == 0) ? Jx : ((c == 1) ? Jy : Jz);
+        const int gi = o0 + li, gj = o1 + lj, gk = o2 + lk;
+        if (gi >= J.lo0 && gi < J.lo0 + J.n0 && gj >= J.lo1 && gj < J.lo1 + J.n1 && gk >= J.lo2 && gk < J.lo2 + J.n2)
+            atomicAdd(&J(gi, gj, gk), v);
+    }
+}
+
+template <int N, int CH, int NW>
+static int launch_tile(SoaView P, const BinsView& bv, const pic_fab J[3], const DepositGeom& dg,
+                       cudaStream_t s) {
+    using T = TileCfg<N>;
+    const long bvol = (long)(bv.tile[0] + DT_EXTRA) * (bv.tile[1] + DT_EXTRA) * (bv.tile[2] + DT_EXTRA);
+    const size_t smem = (size_t)(3 * bvol + (size_t)NW * T::NF * (CH + 1)) * sizeof(double) + (size_t)NW * CH * sizeof(int);
+    auto kern = deposit_tile_kernel<N, CH, NW>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail("pic_deposit_esirkepov: cannot raise dynamic shared memory limit");
+        attr_done = true;
+    }
+    if (smem > 227 * 1024) return fail("pic_deposit_esirkepov: supercell too large for shared memory (%zu B)", smem);
+    const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
+    kern<<<ntiles, NW * 32, smem, s>>>(P, bv, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg);
+    count_launch();
+    return check_launch("pic_deposit_esirkepov(tile)") ? 0 : 1;
+}
+
+int deposit_tile_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
+                        const DepositGeom& dg, int nox, const pic_bins* bins, cudaStream_t s) {
+    PIC_REQUIRE(offset == 0 && np == p->np, "pic_deposit_esirkepov: bins describe the whole tile (offset 0, np = all)");
+    BinsView bv = make_bins(*bins);
+    SoaView P = make_soa(*p, 0);
+    if (nox == 1) return launch_tile<1, 16, 16>(P, bv, J, dg, s);
+    if (nox == 2) return launch_tile<2, 16, 16>(P, bv, J, dg, s);
+    return launch_tile<3, 16, 16>(P, bv, J, dg, s);
+}
+
+}  // namespace pic

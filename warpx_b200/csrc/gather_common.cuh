@@ -1,0 +1,100 @@
+// Per-particle field gather shared by the order-agnostic and the supercell kernels.
+// Follows Source/Particles/Gather/FieldGather.H:36-424 (3D branch :368-422).
+#ifndef PIC_GATHER_COMMON_CUH_
+#define PIC_GATHER_COMMON_CUH_
+#include "pic_common.cuh"
+
+namespace pic {
+
+struct GatherGeom {
+    double dinv[3];
+    double xyzmin[3];
+    int lo[3];
+    int stag[6][3];   // Ex Ey Ez Bx By Bz
+};
+
+// Weights of one particle along one direction for the four (centering, order) combinations the
+// gather needs (FieldGather.H:98-121): [0] node/full, [1] cell/full, [2] node/lowered, [3] cell/lowered.
+template <int N, int G>
+struct DirWeights {
+    double s[4][N + 1];
+    int j0[4];
+    __device__ __forceinline__ void compute(double pos) {
+        constexpr int M = N - G;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int n = 0; n <= N; ++n) s[t][n] = 0.0;
+        j0[0] = shape_factor<N>(s[0], pos);
+        j0[1] = shape_factor<N>(s[1], pos - 0.5);
+        j0[2] = shape_factor<M>(s[2], pos);
+        j0[3] = shape_factor<M>(s[3], pos - 0.5);
+    }
+};
+
+// Field access policies -----------------------------------------------------------------------
+struct GlobalFields {
+    FabView v[6];
+    __device__ __forceinline__ double get(int c, int i, int j, int k) const { return v[c].ld(i, j, k); }
+};
+
+// Gathers the six components at one particle.  Accumulation order as the reference:
+// iz outer, iy, ix inner; components Ex,Ey,Ez,Bz,By,Bx (FieldGather.H:368-422).
+// YEE = true folds the staggering (Source/WarpX.cpp:2117-2125) into compile-time constants so
+// that every weight-array index is static (registers, no local memory).
+__host__ __device__ constexpr int yee_stag(int c, int d) { return c < 3 ? (d != c) : (d == c - 3); }
+
+template <int N, int G, bool YEE, class Fields>
+__device__ __forceinline__ void gather_fields(const Fields& fld, const GatherGeom& gg, double xp,
+                                              double yp, double zp, double F[6]) {
+    constexpr int M = N - G;
+    DirWeights<N, G> wx, wy, wz;
+    wx.compute((xp - gg.xyzmin[0]) * gg.dinv[0]);
+    wy.compute((yp - gg.xyzmin[1]) * gg.dinv[1]);
+    wz.compute((zp - gg.xyzmin[2]) * gg.dinv[2]);
+#pragma unroll
+    for (int oc = 0; oc < 6; ++oc) {
+        const int c = (oc < 3) ? oc : (8 - oc);   // 0,1,2,5,4,3
+        // lowered order along: E_c -> its own direction; B_c -> the two transverse directions
+        const bool lx = (c < 3) ? (c == 0) : (c != 3);
+        const bool ly = (c < 3) ? (c == 1) : (c != 4);
+        const bool lz = (c < 3) ? (c == 2) : (c != 5);
+        const int tx = (lx ? 2 : 0) + ((YEE ? yee_stag(c, 0) : gg.stag[c][0]) ? 0 : 1);
+        const int ty = (ly ? 2 : 0) + ((YEE ? yee_stag(c, 1) : gg.stag[c][1]) ? 0 : 1);
+        const int tz = (lz ? 2 : 0) + ((YEE ? yee_stag(c, 2) : gg.stag[c][2]) ? 0 : 1);
+        const int nx = lx ? M : N, ny = ly ? M : N, nz = lz ? M : N;
+        const int ix0 = gg.lo[0] + wx.j0[tx], iy0 = gg.lo[1] + wy.j0[ty], iz0 = gg.lo[2] + wz.j0[tz];
+        double acc = 0.0;
+#pragma unroll
+        for (int iz = 0; iz <= N; ++iz) {
+            if (iz > nz) break;
+#pragma unroll
+            for (int iy = 0; iy <= N; ++iy) {
+                if (iy > ny) break;
+#pragma unroll
+                for (int ix = 0; ix <= N; ++ix) {
+                    if (ix > nx) break;
+                    acc += wx.s[tx][ix] * wy.s[ty][iy] * wz.s[tz][iz] * fld.get(c, ix0 + ix, iy0 + iy, iz0 + iz);
+                }
+            }
+        }
+        F[c] = acc;
+    }
+}
+
+
+// momentum + position update of one particle (PushSelector.H:88-102, UpdatePosition.H:36-44)
+__device__ __forceinline__ void push_particle(double& xp, double& yp, double& zp, double& ux,
+                                              double& uy, double& uz, const double F[6],
+                                              double qdt2m, double dt, int pusher, int push_position) {
+    if (pusher == PIC_PUSHER_BORIS) push_boris(ux, uy, uz, F[0], F[1], F[2], F[3], F[4], F[5], qdt2m);
+    else if (pusher == PIC_PUSHER_VAY) push_vay(ux, uy, uz, F[0], F[1], F[2], F[3], F[4], F[5], qdt2m);
+    else push_hc(ux, uy, uz, F[0], F[1], F[2], F[3], F[4], F[5], qdt2m);
+    if (push_position) {
+        const double ig = 1.0 / sqrt(1.0 + (ux * ux + uy * uy + uz * uz) * INV_C2);
+        xp += ux * ig * dt; yp += uy * ig * dt; zp += uz * ig * dt;
+    }
+}
+
+}  // namespace pic
+#endif

@@ -1,0 +1,119 @@
+// Supercell gather + push for cell-sorted particles (the timed path of PushPX / PushP).
+//
+// One CTA per supercell (pic_bins.tile).  The six field components are staged ONCE into a
+// shared-memory block covering the supercell plus the gather halo (2 points each side: node
+// weights reach c-1..c+2, cell weights c-2..c+2 for order 3), then every particle of the supercell
+// gathers its 252 (order 3, Galerkin) grid values from shared memory.  Cell-sorted particles of
+// the same cell are adjacent lanes reading the same addresses -> shared-memory broadcasts.
+// Particles that drifted out of their supercell since the last sort gather from global memory,
+// so any particle order is correct.
+#include "pic_common.cuh"
+#include "gather_common.cuh"
+#include "bins.cuh"
+
+namespace pic {
+
+constexpr int GT_HALO = 2;
+constexpr int GT_THREADS = 256;
+
+struct SmemFields {
+    const double* blk;     // [6][BD2][BD1][BD0]
+    int o0, o1, o2;        // global index of block element (0,0,0)
+    int BD0, BD1, bvol;
+    __device__ __forceinline__ double get(int c, int i, int j, int k) const {
+        return blk[c * bvol + (i - o0) + BD0 * ((j - o1) + BD1 * (k - o2))];
+    }
+};
+
+template <int N, int G, bool YEE>
+__global__ void __launch_bounds__(GT_THREADS)
+gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
+                        double dt, int pusher, int push_position) {
+    extern __shared__ double smem[];
+    const int BD0 = bins.tile[0] + 2 * GT_HALO, BD1 = bins.tile[1] + 2 * GT_HALO, BD2 = bins.tile[2] + 2 * GT_HALO;
+    const int bvol = BD0 * BD1 * BD2;
+    const int t = blockIdx.x;
+    int tc[3];
+    tile_coords(bins, t, tc);
+    const long tvol = (long)bins.tile[0] * bins.tile[1] * bins.tile[2];
+    const int p_begin = bins.cell_start[(long)t * tvol];
+    const int p_end = bins.cell_start[(long)(t + 1) * tvol];
+    if (p_begin == p_end) return;
+    const int t0 = bins.box_lo[0] + tc[0] * bins.tile[0];
+    const int t1 = bins.box_lo[1] + tc[1] * bins.tile[1];
+    const int t2 = bins.box_lo[2] + tc[2] * bins.tile[2];
+    SmemFields sf;
+    sf.blk = smem; sf.o0 = t0 - GT_HALO; sf.o1 = t1 - GT_HALO; sf.o2 = t2 - GT_HALO;
+    sf.BD0 = BD0; sf.BD1 = BD1; sf.bvol = bvol;
+
+    // ---- stage the six sub-blocks (rows of BD0 consecutive doubles) ----
+    for (int n = threadIdx.x; n < 6 * bvol; n += GT_THREADS) {
+        const int c = n / bvol, r = n - c * bvol;
+        const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
+        const FabView& F = gf.v[c];
+        const int gi = sf.o0 + li, gj = sf.o1 + lj, gk = sf.o2 + lk;
+        const bool in = gi >= F.lo0 && gi < F.lo0 + F.n0 && gj >= F.lo1 && gj < F.lo1 + F.n1 &&
+                        gk >= F.lo2 && gk < F.lo2 + F.n2;
+        smem[n] = in ? F.ld(gi, gj, gk) : 0.0;
+    }
+    __syncthreads();
+
+    for (int ip = p_begin + threadIdx.x; ip < p_end; ip += GT_THREADS) {
+        double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip];
+        double ux = P.ux[ip], uy = P.uy[ip], uz = P.uz[ip];
+        // cell of the particle (global index) from the same coordinates the gather uses
+        const int ci = gg.lo[0] + (int)((xp - gg.xyzmin[0]) * gg.dinv[0]);
+        const int cj = gg.lo[1] + (int)((yp - gg.xyzmin[1]) * gg.dinv[1]);
+        const int ck = gg.lo[2] + (int)((zp - gg.xyzmin[2]) * gg.dinv[2]);
+        const bool in_tile = ci >= t0 && ci < t0 + bins.tile[0] && cj >= t1 && cj < t1 + bins.tile[1] &&
+                             ck >= t2 && ck < t2 + bins.tile[2];
+        double F[6];
+        if (in_tile) gather_fields<N, G, YEE>(sf, gg, xp, yp, zp, F);
+        else gather_fields<N, G, YEE>(gf, gg, xp, yp, zp, F);
+        push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
+        P.ux[ip] = ux; P.uy[ip] = uy; P.uz[ip] = uz;
+        if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; }
+    }
+}
+
+template <int N, int G>
+static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const GatherGeom& gg,
+                  bool yee, double qdt2m, double dt, int pusher, int push_position, cudaStream_t s) {
+    const long bvol = (long)(bv.tile[0] + 2 * GT_HALO) * (bv.tile[1] + 2 * GT_HALO) * (bv.tile[2] + 2 * GT_HALO);
+    const size_t smem = (size_t)6 * bvol * sizeof(double);
+    if (smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
+    const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
+    if (yee) {
+        auto k = gather_push_tile_kernel<N, G, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position);
+    } else {
+        auto k = gather_push_tile_kernel<N, G, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position);
+    }
+    count_launch();
+    return check_launch("pic_gather_push(tile)") ? 0 : 1;
+}
+
+int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fab E[3],
+                            const pic_fab B[3], const GatherGeom& gg, double qdt2m, double dt,
+                            int nox, int galerkin, int pusher, int push_position,
+                            const pic_bins* bins, cudaStream_t s) {
+    PIC_REQUIRE(offset == 0 && np == p->np, "pic_gather_push: bins describe the whole tile (offset 0, np = all)");
+    BinsView bv = make_bins(*bins);
+    GlobalFields gf;
+    for (int c = 0; c < 3; ++c) { gf.v[c] = make_view(E[c]); gf.v[3 + c] = make_view(B[c]); }
+    SoaView P = make_soa(*p, 0);
+    const bool yee = is_yee(E, B);
+#define PIC_GT(N, G) return launch<N, G>(P, bv, gf, gg, yee, qdt2m, dt, pusher, push_position, s)
+    if (nox == 1 && galerkin) PIC_GT(1, 1);
+    if (nox == 1) PIC_GT(1, 0);
+    if (nox == 2 && galerkin) PIC_GT(2, 1);
+    if (nox == 2) PIC_GT(2, 0);
+    if (nox == 3 && galerkin) PIC_GT(3, 1);
+    PIC_GT(3, 0);
+#undef PIC_GT
+}
+
+}  // namespace pic

@@ -1,0 +1,163 @@
+// Guard-cell operations: FillBoundary (copy) and SumBoundary (add), one dimension at a time.
+//
+// Replaces ablastr::utils::communication::FillBoundary / SumBoundary as called by
+// WarpX::FillBoundaryE/B (Source/Parallelization/WarpXComm.cpp:699-827) and
+// WarpX::SumBoundaryJ -> WarpXSumGuardCells (WarpXComm.cpp:1386-1424, WarpXSumGuardCells.cpp:17-24;
+// wrappers Source/ablastr/utils/Communication.cpp:71-115, :148-175).  AMReX exchanges all 26
+// neighbours at once; here the exchange is done as three axis sweeps (x, y, z), each slab
+// spanning the full allocated extent of the other two axes so that edges and corners propagate.
+//   * self-neighbour (box spans the periodic domain along the axis): one local kernel;
+//   * real neighbour (multi-GPU): pack -> NCCL send/recv (host side) -> unpack(+add).
+// All kernels are pure HBM streams with i (contiguous) innermost.
+#include "pic_common.cuh"
+
+namespace pic {
+
+struct Slab {
+    int dim;
+    int n[3];        // iteration extents (n[dim] = number of layers)
+    int start[3];    // first index (global) in each direction for the slab being written / read
+};
+
+__device__ __forceinline__ void decode(long t, const int n[3], int& a, int& b, int& c) {
+    a = (int)(t % n[0]);
+    b = (int)((t / n[0]) % n[1]);
+    c = (int)(t / ((long)n[0] * n[1]));
+}
+
+// guards <- periodic image of valid points (shift by +-N along dim)
+__global__ void fill_local_kernel(FabView F, int dim, int N, int vl, int vh, int ng, Slab sl, long total) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int a, b, c;
+    decode(t, sl.n, a, b, c);
+    int idx[3] = {sl.start[0] + a, sl.start[1] + b, sl.start[2] + c};
+    // layers 0..ng-1 -> low guards vl-ng .. vl-1 ; layers ng..2ng-1 -> high guards vh+1 .. vh+ng
+    const int layer = (dim == 0) ? a : ((dim == 1) ? b : c);
+    int src[3] = {idx[0], idx[1], idx[2]};
+    if (layer < ng) { idx[dim] = vl - ng + layer; src[dim] = idx[dim] + N; }
+    else { idx[dim] = vh + 1 + (layer - ng); src[dim] = idx[dim] - N; }
+    F(idx[0], idx[1], idx[2]) = F(src[0], src[1], src[2]);
+}
+
+// valid points accumulate the periodic images of guard points (and the nodal duplicate)
+__global__ void sum_local_kernel(FabView F, int dim, int N, int vl, int vh, int src_ng, int nodal,
+                                 Slab sl, long total) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int a, b, c;
+    decode(t, sl.n, a, b, c);
+    int idx[3] = {sl.start[0] + a, sl.start[1] + b, sl.start[2] + c};
+    const int layer = (dim == 0) ? a : ((dim == 1) ? b : c);   // 0 .. src_ng (0 only when nodal)
+    const int g = nodal ? layer : layer + 1;
+    int lo_i[3] = {idx[0], idx[1], idx[2]}, hi_i[3] = {idx[0], idx[1], idx[2]};
+    if (g == 0) {
+        // nodal duplicate: both copies get v(vl) + v(vh)
+        lo_i[dim] = vl; hi_i[dim] = vh;
+        const double s = F(lo_i[0], lo_i[1], lo_i[2]) + F(hi_i[0], hi_i[1], hi_i[2]);
+        F(lo_i[0], lo_i[1], lo_i[2]) = s;
+        F(hi_i[0], hi_i[1], hi_i[2]) = s;
+        return;
+    }
+    // low guard vl-g folds onto vl-g+N ; high guard vh+g folds onto vh+g-N
+    int tgt[3] = {idx[0], idx[1], idx[2]};
+    lo_i[dim] = vl - g; tgt[dim] = vl - g + N;
+    F(tgt[0], tgt[1], tgt[2]) += F(lo_i[0], lo_i[1], lo_i[2]);
+    hi_i[dim] = vh + g; tgt[dim] = vh + g - N;
+    F(tgt[0], tgt[1], tgt[2]) += F(hi_i[0], hi_i[1], hi_i[2]);
+}
+
+// mode 0 copy / 1 sum; dir 0 pack (fab -> buf) / 1 unpack (buf -> fab, adding when mode = 1)
+__global__ void slab_kernel(FabView F, double* __restrict__ buf, Slab sl, long total, int dir, int add) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int a, b, c;
+    decode(t, sl.n, a, b, c);
+    const int i = sl.start[0] + a, j = sl.start[1] + b, k = sl.start[2] + c;
+    if (dir == 0) buf[t] = F(i, j, k);
+    else if (add) F(i, j, k) += buf[t];
+    else F(i, j, k) = buf[t];
+}
+
+static void full_extent(const pic_fab& f, Slab& sl) {
+    for (int d = 0; d < 3; ++d) { sl.start[d] = f.lo[d]; sl.n[d] = f.hi[d] - f.lo[d] + 1; }
+}
+
+// index range along `dim` of the slab exchanged with the neighbour on `side`
+static void slab_range(const pic_fab& f, int dim, int side, int ng, int mode, int unpack, int& first, int& count) {
+    const int lc = vlo(f, dim);                          // first cell
+    const int hc = vhi(f, dim) - f.stag[dim];            // last cell
+    const int st = f.stag[dim];
+    if (mode == 0) {           // copy: send valid layers, receive into guards
+        count = ng;
+        if (!unpack) first = side ? (hc + 1 - ng) : (lc + st);
+        else first = side ? (hc + 1 + st) : (lc - ng);
+    } else {                   // sum: send guards (+ shared node), add into valid
+        count = ng + st;
+        if (!unpack) first = side ? (hc + 1) : (lc - ng);
+        else first = side ? (hc + 1 - ng) : lc;
+    }
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+extern "C" int pic_fill_boundary_local(const pic_fab* f, int dim, int ng, const pic_geom* g, void* stream) {
+    if (ng == 0) return 0;
+    const int N = g->n_cell[dim];
+    const int vl = vlo(*f, dim), vh = vhi(*f, dim);
+    PIC_REQUIRE(g->periodic[dim], "pic_fill_boundary_local: dimension %d is not periodic", dim);
+    PIC_REQUIRE(vh - vl + 1 - f->stag[dim] == N, "pic_fill_boundary_local: box does not span the domain in dim %d", dim);
+    PIC_REQUIRE(ng <= f->ng[dim] && ng <= N, "pic_fill_boundary_local: ng=%d exceeds allocated guards", ng);
+    Slab sl; full_extent(*f, sl); sl.dim = dim; sl.n[dim] = 2 * ng;
+    const long total = (long)sl.n[0] * sl.n[1] * sl.n[2];
+    fill_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        make_view(*f), dim, N, vl, vh, ng, sl, total);
+    count_launch();
+    return check_launch("pic_fill_boundary_local") ? 0 : 1;
+}
+
+extern "C" int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, const pic_geom* g, void* stream) {
+    const int N = g->n_cell[dim];
+    const int vl = vlo(*f, dim), vh = vhi(*f, dim);
+    const int nodal = f->stag[dim];
+    PIC_REQUIRE(g->periodic[dim], "pic_sum_boundary_local: dimension %d is not periodic", dim);
+    PIC_REQUIRE(vh - vl + 1 - nodal == N, "pic_sum_boundary_local: box does not span the domain in dim %d", dim);
+    PIC_REQUIRE(src_ng <= f->ng[dim] && 2 * src_ng + 1 <= N, "pic_sum_boundary_local: src_ng=%d too large", src_ng);
+    Slab sl; full_extent(*f, sl); sl.dim = dim; sl.n[dim] = src_ng + nodal;
+    const long total = (long)sl.n[0] * sl.n[1] * sl.n[2];
+    if (total == 0) return 0;
+    sum_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        make_view(*f), dim, N, vl, vh, src_ng, nodal, sl, total);
+    count_launch();
+    return check_launch("pic_sum_boundary_local") ? 0 : 1;
+}
+
+extern "C" long pic_halo_slab_count(const pic_fab* f, int dim, int ng, int mode) {
+    long n = 1;
+    for (int d = 0; d < 3; ++d) if (d != dim) n *= (f->hi[d] - f->lo[d] + 1);
+    return n * (mode == 0 ? ng : ng + f->stag[dim]);
+}
+
+static int slab_launch(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, int unpack, void* stream) {
+    PIC_REQUIRE(dim >= 0 && dim < 3 && (side == 0 || side == 1) && (mode == 0 || mode == 1), "pic_halo: bad arguments");
+    PIC_REQUIRE(ng <= f->ng[dim], "pic_halo: ng=%d exceeds allocated guards", ng);
+    Slab sl; full_extent(*f, sl); sl.dim = dim;
+    int first, count;
+    slab_range(*f, dim, side, ng, mode, unpack, first, count);
+    sl.start[dim] = first; sl.n[dim] = count;
+    const long total = (long)sl.n[0] * sl.n[1] * sl.n[2];
+    if (total == 0) return 0;
+    slab_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        make_view(*f), buf, sl, total, unpack, mode);
+    count_launch();
+    return check_launch("pic_halo_pack/unpack") ? 0 : 1;
+}
+
+extern "C" int pic_halo_pack(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, void* stream) {
+    return slab_launch(f, dim, side, ng, mode, buf, 0, stream);
+}
+extern "C" int pic_halo_unpack(const pic_fab* f, int dim, int side, int ng, int mode, const double* buf, void* stream) {
+    return slab_launch(f, dim, side, ng, mode, const_cast<double*>(buf), 1, stream);
+}

@@ -1,0 +1,130 @@
+// Particle housekeeping between steps: periodic wrap and counting sort by cell.
+//
+// Replaces what WarpX::HandleParticlesAtBoundaries obtains from AMReX
+// (Source/Evolve/WarpXEvolve.cpp:533-581): ParticleContainer::Redistribute's periodic shift
+// (amrex::enforcePeriodic, AMReX 24.10 AMReX_ParticleUtil.H -- un-vendored dependency) and
+// mypc->SortParticlesByBin (counting sort into cell bins, MultiParticleContainer.cpp:615-624).
+#include "pic_common.cuh"
+#include "bins.cuh"
+#include <cub/device/device_scan.cuh>
+
+namespace pic {
+
+struct WrapGeom { double lo[3], hi[3], len[3]; int periodic[3]; };
+
+__device__ __forceinline__ double wrap1(double v, double lo, double hi, double len) {
+    if (v > hi) {
+        while (v > hi) v -= len;
+        if (v < lo) v = lo;          // clamp round-off
+    } else if (v < lo) {
+        while (v < lo) v += len;
+        if (v > hi) v = hi;
+    }
+    return v;
+}
+
+__global__ void wrap_kernel(SoaView P, long np, WrapGeom g) {
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= np) return;
+    if (g.periodic[0]) P.x[ip] = wrap1(P.x[ip], g.lo[0], g.hi[0], g.len[0]);
+    if (g.periodic[1]) P.y[ip] = wrap1(P.y[ip], g.lo[1], g.hi[1], g.len[1]);
+    if (g.periodic[2]) P.z[ip] = wrap1(P.z[ip], g.lo[2], g.hi[2], g.len[2]);
+}
+
+struct SortGeom { double plo[3], dinv[3]; };
+
+__global__ void sort_count_kernel(SoaView P, long np, BinsView b, SortGeom sg, int* __restrict__ keys,
+                                  int* __restrict__ counts) {
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= np) return;
+    int ci = (int)floor((P.x[ip] - sg.plo[0]) * sg.dinv[0]) - b.box_lo[0];
+    int cj = (int)floor((P.y[ip] - sg.plo[1]) * sg.dinv[1]) - b.box_lo[1];
+    int ck = (int)floor((P.z[ip] - sg.plo[2]) * sg.dinv[2]) - b.box_lo[2];
+    ci = min(max(ci, 0), b.n[0] - 1); cj = min(max(cj, 0), b.n[1] - 1); ck = min(max(ck, 0), b.n[2] - 1);
+    const int bin = (int)bin_of_cell(b, ci, cj, ck);
+    keys[ip] = bin;
+    atomicAdd(&counts[bin], 1);
+}
+
+__global__ void sort_scatter_kernel(SoaView in, SoaView out, const uint64_t* __restrict__ id_in,
+                                    uint64_t* __restrict__ id_out, long np, const int* __restrict__ keys,
+                                    const int* __restrict__ cell_start, int* __restrict__ fill) {
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= np) return;
+    const int bin = keys[ip];
+    const int pos = cell_start[bin] + atomicAdd(&fill[bin], 1);
+    out.x[pos] = in.x[ip]; out.y[pos] = in.y[ip]; out.z[pos] = in.z[ip]; out.w[pos] = in.w[ip];
+    out.ux[pos] = in.ux[ip]; out.uy[pos] = in.uy[ip]; out.uz[pos] = in.uz[ip];
+    if (id_in && id_out) id_out[pos] = id_in[ip];
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+static size_t scan_temp_bytes(long n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, (int)n);
+    return bytes;
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+extern "C" int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* stream) {
+    if (p->np == 0) return 0;
+    WrapGeom wg;
+    for (int d = 0; d < 3; ++d) {
+        wg.lo[d] = g->prob_lo[d]; wg.hi[d] = g->prob_hi[d]; wg.len[d] = g->prob_hi[d] - g->prob_lo[d];
+        wg.periodic[d] = g->periodic[d];
+    }
+    wrap_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_soa(*p, 0), p->np, wg);
+    count_launch();
+    return check_launch("pic_particles_wrap_periodic") ? 0 : 1;
+}
+
+extern "C" long pic_bins_count(const int box_lo[3], const int box_hi[3], const int tile[3]) {
+    pic_bins b;
+    for (int d = 0; d < 3; ++d) { b.box_lo[d] = box_lo[d]; b.box_hi[d] = box_hi[d]; b.tile[d] = tile[d]; }
+    b.cell_start = nullptr;
+    return bins_count(make_bins(b));
+}
+
+extern "C" long pic_sort_workspace_bytes(long np, long nbins) {
+    return (long)(align256((size_t)np * 4) + 2 * align256((size_t)(nbins + 1) * 4) + align256(scan_temp_bytes(nbins + 1)));
+}
+
+extern "C" int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_geom* g,
+                                          const pic_bins* bins, void* work, void* stream) {
+    const long np = in->np;
+    PIC_REQUIRE(out->np == np, "pic_sort_particles_by_cell: in/out sizes differ");
+    PIC_REQUIRE(in->x != out->x, "pic_sort_particles_by_cell: in-place sort is not supported");
+    BinsView bv = make_bins(*bins);
+    const long nbins = bins_count(bv);
+    PIC_REQUIRE(nbins + 1 < (1L << 31) && np < (1L << 31), "pic_sort_particles_by_cell: too many bins/particles for int32");
+    cudaStream_t s = (cudaStream_t)stream;
+    char* w = (char*)work;
+    int* keys = (int*)w; w += align256((size_t)np * 4);
+    int* counts = (int*)w; w += align256((size_t)(nbins + 1) * 4);
+    int* fill = (int*)w; w += align256((size_t)(nbins + 1) * 4);
+    void* temp = w;
+    size_t temp_bytes = scan_temp_bytes(nbins + 1);
+    int* cell_start = const_cast<int*>(bins->cell_start);
+    cudaMemsetAsync(counts, 0, (size_t)(nbins + 1) * 4, s);
+    cudaMemsetAsync(fill, 0, (size_t)(nbins + 1) * 4, s);
+    SortGeom sg;
+    for (int d = 0; d < 3; ++d) {
+        sg.plo[d] = g->prob_lo[d];
+        sg.dinv[d] = 1.0 / ((g->prob_hi[d] - g->prob_lo[d]) / g->n_cell[d]);
+    }
+    if (np > 0) {
+        sort_count_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(make_soa(*in, 0), np, bv, sg, keys, counts);
+        count_launch();
+    }
+    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, cell_start, (int)(nbins + 1), s);
+    count_launch();
+    if (np > 0) {
+        sort_scatter_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(make_soa(*in, 0), make_soa(*out, 0),
+            in->idcpu, out->idcpu, np, keys, cell_start, fill);
+        count_launch();
+    }
+    return check_launch("pic_sort_particles_by_cell") ? 0 : 1;
+}

@@ -1,0 +1,411 @@
+"""Host-side mirror of the reference's explicit EM-PIC step (single level, periodic, FDTD).
+
+Method names, argument meaning and sequencing follow WarpX so that the parity tests read like the
+reference (paths relative to /root/reference/Source):
+
+    Simulation.Evolve                     <- WarpX::Evolve                     Evolve/WarpXEvolve.cpp:93-347
+    Simulation.ExplicitFillBoundaryEBUpdateAux                                 :473-531
+    Simulation.OneStep_nosub              <- WarpX::OneStep_nosub              :353-455
+    Simulation.PushParticlesandDeposit    <- MultiParticleContainer::Evolve    Particles/MultiParticleContainer.cpp:460-482
+                                             PhysicalParticleContainer::Evolve Particles/PhysicalParticleContainer.cpp:1812-2095
+    Simulation.SyncCurrent                <- WarpX::SyncCurrent/SumBoundaryJ   Parallelization/WarpXComm.cpp:1073-1240,1386-1424
+    Simulation.EvolveB / EvolveE          <- WarpX::EvolveB/E                  FieldSolver/WarpXPushFieldsEM.cpp:877-1011
+    Simulation.FillBoundaryE / B          <- WarpX::FillBoundaryE/B            Parallelization/WarpXComm.cpp:699-827
+    Simulation.Synchronize                <- WarpX::Synchronize                Evolve/WarpXEvolve.cpp:64-91
+    Simulation.HandleParticlesAtBoundaries                                     :533-581
+
+Every stage is one call through the C ABI (include/pic_b200.h) into hand-written sm_100a kernels;
+PyTorch only owns device memory, the stream and (multi-GPU) the NCCL transport.
+There is no CPU path: constructing a Simulation without a CUDA device raises.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import abi, parallel
+from .lib import check, lib, require_cuda
+
+C_LIGHT = 299792458.0
+EP0 = 8.8541878128e-12
+MU0 = 1.25663706212e-06
+
+
+def stencil_coefficients(solver, dx):
+    """FiniteDifferenceSolver ctor (FieldSolver/FiniteDifferenceSolver/FiniteDifferenceSolver.cpp:30-103):
+    Yee CartesianYeeAlgorithm.H:30-42, CKC CartesianCKCAlgorithm.H:31-101 (Cowan 2013)."""
+    st = abi.pic_stencil()
+    st.algo = solver
+    inv = [1.0 / d for d in dx]
+    for n in range(5):
+        st.cx[n] = st.cy[n] = st.cz[n] = 0.0
+    st.cx[0], st.cy[0], st.cz[0] = inv
+    if solver == abi.SOLVER_CKC:
+        delta = max(inv)
+        rx, ry, rz = ((v / delta) * (v / delta) for v in inv)
+        beta = 0.125 * (1.0 - rx * ry * rz / (ry * rz + rz * rx + rx * ry))
+        irf = 1.0 / (ry * rz + rz * rx + rx * ry)
+        gx = ry * rz * (0.0625 - 0.125 * ry * rz * irf)
+        gy = rx * rz * (0.0625 - 0.125 * rx * rz * irf)
+        gz = rx * ry * (0.0625 - 0.125 * rx * ry * irf)
+        st.cx[1] = (1.0 - 2.0 * ry * beta - 2.0 * rz * beta - 4.0 * gx) * inv[0]
+        st.cy[1] = (1.0 - 2.0 * rx * beta - 2.0 * rz * beta - 4.0 * gy) * inv[1]
+        st.cz[1] = (1.0 - 2.0 * rx * beta - 2.0 * ry * beta - 4.0 * gz) * inv[2]
+        st.cx[2], st.cx[3], st.cx[4] = ry * beta * inv[0], rz * beta * inv[0], gx * inv[0]
+        st.cy[2], st.cy[3], st.cy[4] = rz * beta * inv[1], rx * beta * inv[1], gy * inv[1]
+        st.cz[2], st.cz[3], st.cz[4] = rx * beta * inv[2], ry * beta * inv[2], gz * inv[2]
+    return st
+
+
+def max_dt(solver, dx):
+    """WarpX::ComputeDt (Evolve/WarpXComputeDt.cpp:56-95): Yee CartesianYeeAlgorithm.H:48-56,
+    CKC CartesianCKCAlgorithm.H:107-118."""
+    if solver == abi.SOLVER_YEE:
+        return 1.0 / (math.sqrt(sum(1.0 / (d * d) for d in dx)) * C_LIGHT)
+    return min(dx) / C_LIGHT
+
+
+def guard_cells(nox, dt, dx):
+    """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-161, 310-343) for: no MR, no
+    NCI corrector, no moving window, no filter, not safe_guard_cells, FDTD solver."""
+    ng_EB, ng_J, ng_FG, ng_FS = [], [], [], []
+    for d in range(3):
+        ngt = nox
+        ng = ngt + 1 if ngt % 2 else ngt
+        ngj = ngt + int(math.ceil(C_LIGHT * 0.5 * dt / dx[d]))
+        fs = 1
+        ng = max(ng, fs)
+        fg = max(min((nox + 1) // 2, ng), fs)
+        ng_EB.append(ng); ng_J.append(ngj); ng_FG.append(fg); ng_FS.append(fs)
+    return dict(ng_EB=ng_EB, ng_J=ng_J, ng_FG=ng_FG, ng_FS=ng_FS)
+
+
+class _DeviceOps:
+    """pack/unpack/local guard-cell kernels for parallel.HaloExchanger."""
+
+    def __init__(self, sim):
+        self.sim = sim
+
+    def empty(self, n):
+        return self.sim.torch.empty(n, dtype=self.sim.torch.float64, device=self.sim.device)
+
+    def sync(self):
+        self.sim.torch.cuda.current_stream().synchronize()
+
+    def fill_local(self, fab, dim, ng):
+        s = self.sim
+        check(s.L.pic_fill_boundary_local(C.byref(fab), dim, ng, C.byref(s.geom), s.stream))
+
+    def sum_local(self, fab, dim, ng):
+        s = self.sim
+        check(s.L.pic_sum_boundary_local(C.byref(fab), dim, ng, C.byref(s.geom), s.stream))
+
+    def slab_count(self, fab, dim, ng, mode):
+        return self.sim.L.pic_halo_slab_count(C.byref(fab), dim, ng, mode)
+
+    def pack(self, fab, dim, side, ng, mode, buf):
+        s = self.sim
+        check(s.L.pic_halo_pack(C.byref(fab), dim, side, ng, mode, buf.data_ptr(), s.stream))
+
+    def unpack(self, fab, dim, side, ng, mode, buf):
+        s = self.sim
+        check(s.L.pic_halo_unpack(C.byref(fab), dim, side, ng, mode, buf.data_ptr(), s.stream))
+
+
+class Species:
+    NAMES = ("x", "y", "z", "w", "ux", "uy", "uz")
+
+    def __init__(self, sim, name, q, m, arrays, capacity):
+        t = sim.torch
+        self.sim, self.name, self.q, self.m = sim, name, q, m
+        self.np = len(arrays["x"])
+        self.capacity = max(capacity, self.np)
+        # two SoA buffers: the counting sort permutes from one into the other
+        self.buf = [t.empty((7, self.capacity), dtype=t.float64, device=sim.device) for _ in range(2)]
+        self.cur = 0
+        for n, name_ in enumerate(self.NAMES):
+            a = arrays[name_]
+            src = a if isinstance(a, t.Tensor) else t.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+            self.buf[0][n, :self.np].copy_(src, non_blocking=True)
+        self.bins = None          # abi.pic_bins once sorted
+        self.cell_start = None
+        self.work = None
+
+    def soa(self, which=None):
+        b = self.buf[self.cur if which is None else which]
+        s = abi.pic_soa()
+        for n, name in enumerate(self.NAMES):
+            setattr(s, name, b[n].data_ptr())
+        s.idcpu = None
+        s.np = self.np
+        return s
+
+    def array(self, name):
+        return self.buf[self.cur][self.NAMES.index(name), :self.np]
+
+
+class Simulation:
+    def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
+                 solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
+                 tile=(8, 8, 8), use_bins=True, device=None):
+        self.torch = require_cuda()
+        t = self.torch
+        self.L = lib()
+        self.L.pic_set_error_mode(abi.PIC_ERR_RETURN)   # Python raises instead of abort()
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.device = t.device("cuda", t.cuda.current_device()) if device is None else device
+        self.n_cell = tuple(int(v) for v in n_cell)
+        self.prob_lo, self.prob_hi = tuple(prob_lo), tuple(prob_hi)
+        self.geom = abi.make_geom(n_cell, prob_lo, prob_hi)
+        self.dx = [(prob_hi[d] - prob_lo[d]) / n_cell[d] for d in range(3)]     # amrex::Geometry::CellSize
+        self.dinv = [1.0 / v for v in self.dx]                                   # WarpX::InvCellSize
+        self.nox, self.galerkin, self.pusher, self.solver = nox, galerkin, pusher, solver
+        self.dt = dt if dt else cfl * max_dt(solver, self.dx)
+        self.st = stencil_coefficients(solver, self.dx)
+        g = guard_cells(nox, self.dt, self.dx)
+        self.ng_EB, self.ng_J, self.ng_FG, self.ng_FS = g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]
+        self.ng_depos_J = list(self.ng_J)
+        self.dec = parallel.Decomposition(self.n_cell, parallel.brick_grid(self.world), self.rank)
+        self.box_lo, self.box_hi = self.dec.box_lo, self.dec.box_hi
+        self.sort_interval, self.tile, self.use_bins = sort_interval, tuple(tile), use_bins
+        # fields: Ex Ey Ez Bx By Bz jx jy jz, AMReX-shaped (valid + guards), Fortran order
+        self.data, descs = [], []
+        for c in range(9):
+            ng = self.ng_EB if c < 6 else self.ng_J
+            d = abi.make_fab(None, self.box_lo, self.box_hi, ng, abi.YEE_STAG[c])
+            a = t.zeros(d.shape, dtype=t.float64, device=self.device)
+            d.p = a.data_ptr()
+            self.data.append(a)
+            descs.append(d)
+        self.fab = descs
+        self.E = (abi.pic_fab * 3)(*descs[0:3])
+        self.B = (abi.pic_fab * 3)(*descs[3:6])
+        self.J = (abi.pic_fab * 3)(*descs[6:9])
+        self.halo = parallel.HaloExchanger(self.dec, _DeviceOps(self), dist)
+        self.species = []
+        self.is_synchronized = True
+        self.istep = 0
+        self._scratch = t.zeros(8, dtype=t.float64, device=self.device)
+        self.stage_events = None      # {stage: [(start, end), ...]} when enable_stage_timing() is on
+
+    def enable_stage_timing(self, on=True):
+        """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""
+        self.stage_events = {} if on else None
+
+    def _timed(self, name, fn, *a):
+        if self.stage_events is None:
+            return fn(*a)
+        t = self.torch
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a)
+        e1.record()
+        self.stage_events.setdefault(name, []).append((e0, e1))
+        return r
+
+    def stage_ms(self):
+        """Average milliseconds per call of every timed stage (synchronises)."""
+        self.torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in self.stage_events.items()}
+
+    # ------------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def add_species(self, name, q, m, x, y, z, w, ux, uy, uz, capacity_factor=None):
+        """Particles must lie inside this rank's box (use workloads.* with box_lo/box_hi)."""
+        if capacity_factor is None:
+            capacity_factor = 1.0 if self.world == 1 else 1.25
+        arrays = dict(x=x, y=y, z=z, w=w, ux=ux, uy=uy, uz=uz)
+        cap = int(len(x) * capacity_factor) + (0 if self.world == 1 else 65536)
+        sp = Species(self, name, q, m, arrays, cap)
+        self.species.append(sp)
+        if self.use_bins:
+            self.SortParticlesByBin(sp)
+        return sp
+
+    def lower_corner(self, ng):
+        """WarpX::LowerCorner of the box grown by ng (Source/WarpX.cpp:2851-2874; RealBox lo =
+        prob_lo + index*dx) and lbound of that box."""
+        lo = [self.box_lo[d] - ng[d] for d in range(3)]
+        xyzmin = [self.prob_lo[d] + self.dx[d] * lo[d] for d in range(3)]
+        return abi.dbl3(xyzmin), abi.int3(lo)
+
+    # ---- guard cells -------------------------------------------------------------------
+    def FillBoundaryE(self, ng):
+        for c in range(0, 3):
+            self.halo.fill_boundary(self.fab[c], ng)
+
+    def FillBoundaryB(self, ng):
+        for c in range(3, 6):
+            self.halo.fill_boundary(self.fab[c], ng)
+
+    def SyncCurrent(self):
+        """SumBoundaryJ: src = ng_depos_J (no filter), all guards of J updated afterwards."""
+        for c in range(6, 9):
+            self.halo.sum_boundary(self.fab[c], self.ng_depos_J, self.ng_J)
+
+    # ---- field solver ------------------------------------------------------------------
+    def EvolveB(self, dt):
+        self._timed("evolve_b", lambda: check(self.L.pic_evolve_b(self.B, self.E, C.byref(self.st), dt, self.stream)))
+
+    def EvolveE(self, dt):
+        self._timed("evolve_e", lambda: check(self.L.pic_evolve_e(self.E, self.B, self.J, C.byref(self.st), dt,
+                                                                   self.stream)))
+
+    # ---- particles ---------------------------------------------------------------------
+    def _bins(self, sp):
+        return C.byref(sp.bins) if (self.use_bins and sp.bins is not None) else None
+
+    def PushPX(self, sp, dt, push_position=1):
+        xyzmin, lo = self.lower_corner(self.ng_EB)          # box.grow(ngEB), PhysicalParticleContainer.cpp:2583
+        soa = sp.soa()
+        check(self.L.pic_gather_push(C.byref(soa), 0, sp.np, self.E, self.B, abi.dbl3(self.dinv), xyzmin, lo,
+                                     sp.q, sp.m, dt, self.nox, self.galerkin, self.pusher, push_position,
+                                     self._bins(sp), self.stream))
+
+    def PushP(self, dt):
+        for sp in self.species:
+            self.PushPX(sp, dt, push_position=0)
+
+    def DepositCurrent(self, sp, dt, relative_time):
+        xyzmin, lo = self.lower_corner(self.ng_J)           # tilebox.grow(ng_J), WarpXParticleContainer.cpp:424-479
+        soa = sp.soa()
+        check(self.L.pic_deposit_esirkepov(C.byref(soa), 0, sp.np, self.J, abi.dbl3(self.dinv), xyzmin, lo,
+                                           sp.q, dt, relative_time, self.nox, self._bins(sp), self.stream))
+
+    def PushParticlesandDeposit(self):
+        for c in range(6, 9):
+            self.data[c].zero_()                             # J.setVal(0), MultiParticleContainer.cpp:467-478
+        for sp in self.species:
+            self._timed("gather_push", self.PushPX, sp, self.dt)
+            self._timed("deposit", self.DepositCurrent, sp, self.dt, -0.5 * self.dt)  # relative_time, PhysicalParticleContainer.cpp:2029
+
+    def SortParticlesByBin(self, sp):
+        t = self.torch
+        bins = abi.pic_bins()
+        for d in range(3):
+            bins.box_lo[d], bins.box_hi[d], bins.tile[d] = self.box_lo[d], self.box_hi[d], self.tile[d]
+        nb = self.L.pic_bins_count(bins.box_lo, bins.box_hi, bins.tile)
+        if sp.cell_start is None or sp.cell_start.numel() < nb + 1:
+            sp.cell_start = t.empty(nb + 1, dtype=t.int32, device=self.device)
+        wb = self.L.pic_sort_workspace_bytes(sp.capacity, nb)
+        if sp.work is None or sp.work.numel() < wb:
+            sp.work = t.empty(wb, dtype=t.uint8, device=self.device)
+        bins.cell_start = sp.cell_start.data_ptr()
+        src, dst = sp.soa(sp.cur), sp.soa(1 - sp.cur)
+        check(self.L.pic_sort_particles_by_cell(C.byref(src), C.byref(dst), C.byref(self.geom), C.byref(bins),
+                                                sp.work.data_ptr(), self.stream))
+        sp.cur = 1 - sp.cur
+        sp.bins = bins
+
+    def _migrate(self, sp):
+        """Neighbour migration after the periodic wrap (RedistributeLocal(1)); axis sweeps."""
+        t = self.torch
+        for dim in range(3):
+            if self.dec.spans(dim):
+                continue
+            pos = sp.array(("x", "y", "z")[dim])
+            cell = t.floor((pos - self.prob_lo[dim]) * self.dinv[dim]).to(t.int64).clamp_(0, self.n_cell[dim] - 1)
+            down, up = parallel.particle_destinations(cell, self.dec, dim)
+            keep = ~(down | up)
+            cur = sp.buf[sp.cur][:, :sp.np]
+            s_lo, s_hi = cur[:, down].contiguous(), cur[:, up].contiguous()
+            counts = t.tensor([s_lo.shape[1], s_hi.shape[1]], dtype=t.int64, device=self.device)
+            rc = t.zeros(2, dtype=t.int64, device=self.device)
+            # counts: what I send low is received by my low neighbour as "from high"
+            parallel.exchange(self.dist, self.dec, dim, counts[0:1], counts[1:2], rc[0:1], rc[1:2])
+            n_lo, n_hi = int(rc[0].item()), int(rc[1].item())
+            r_lo = t.empty((7, n_lo), dtype=t.float64, device=self.device)
+            r_hi = t.empty((7, n_hi), dtype=t.float64, device=self.device)
+            parallel.exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
+            kept = cur[:, keep]
+            n_new = kept.shape[1] + n_lo + n_hi
+            if n_new > sp.capacity:
+                raise RuntimeError("particle capacity exceeded on rank %d" % self.rank)
+            nb = sp.buf[1 - sp.cur]
+            nb[:, :kept.shape[1]] = kept
+            nb[:, kept.shape[1]:kept.shape[1] + n_lo] = r_lo
+            nb[:, kept.shape[1] + n_lo:n_new] = r_hi
+            sp.cur = 1 - sp.cur
+            sp.np = n_new
+            sp.bins = None      # order changed: bins are stale until the next sort
+
+    def HandleParticlesAtBoundaries(self, step):
+        for sp in self.species:
+            soa = sp.soa()
+            check(self.L.pic_particles_wrap_periodic(C.byref(soa), C.byref(self.geom), self.stream))
+            moved = False
+            if self.world > 1:
+                self._migrate(sp)
+                moved = True
+            if self.use_bins and (moved or (self.sort_interval > 0 and (step + 1) % self.sort_interval == 0)):
+                self._timed("sort", self.SortParticlesByBin, sp)
+
+    # ---- the step ----------------------------------------------------------------------
+    def ExplicitFillBoundaryEBUpdateAux(self):
+        if self.is_synchronized:
+            self.FillBoundaryE(self.ng_EB); self.FillBoundaryB(self.ng_EB)      # ng_alloc_EB, :487-488
+            self.PushP(-0.5 * self.dt)                                           # :492-504
+            self.is_synchronized = False
+        else:
+            self.FillBoundaryE(self.ng_FG); self.FillBoundaryB(self.ng_FG)      # :515-516
+
+    def OneStep_nosub(self):
+        self.PushParticlesandDeposit()
+        self._timed("sync_current", self.SyncCurrent)
+        self.EvolveB(0.5 * self.dt)
+        self.FillBoundaryB(self.ng_FS)
+        self.EvolveE(self.dt)
+        self.FillBoundaryE(self.ng_FS)
+        self.EvolveB(0.5 * self.dt)
+
+    def Synchronize(self):
+        self.FillBoundaryE(self.ng_FG); self.FillBoundaryB(self.ng_FG)
+        self.PushP(0.5 * self.dt)
+        self.is_synchronized = True
+
+    def Evolve(self, numsteps, synchronize_last=True):
+        for n in range(numsteps):
+            self.ExplicitFillBoundaryEBUpdateAux()
+            self.OneStep_nosub()
+            if synchronize_last and n == numsteps - 1:
+                self.Synchronize()
+            step = self.istep
+            self.istep += 1
+            self.HandleParticlesAtBoundaries(step)
+
+    # ---- diagnostics -------------------------------------------------------------------
+    def field_energy(self):
+        """FieldEnergy reduced diagnostic (Diagnostics/ReducedDiags/FieldEnergy.cpp:120-144):
+        (E energy, B energy) in J, summed over ranks."""
+        t = self.torch
+        out = self._scratch
+        for c in range(6):
+            check(self.L.pic_sum_squares_unique(C.byref(self.fab[c]), C.byref(self.geom),
+                                                out[c:c + 1].data_ptr(), self.stream))
+        e2b2 = t.stack([out[0:3].sum(), out[3:6].sum()])
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(e2b2)
+        dV = self.dx[0] * self.dx[1] * self.dx[2]
+        v = e2b2.cpu().numpy()
+        return 0.5 * v[0] * EP0 * dV, 0.5 * v[1] / MU0 * dV
+
+    def total_particles(self):
+        n = sum(sp.np for sp in self.species)
+        if self.dist is not None and self.world > 1:
+            tt = self.torch.tensor([n], dtype=self.torch.int64, device=self.device)
+            self.dist.all_reduce(tt)
+            n = int(tt.item())
+        return n
+
+    def field_numpy(self, comp):
+        """(descriptor, numpy array [k, j, i]) of component comp (0..8 = Ex..jz)."""
+        return self.fab[comp], self.data[comp].cpu().numpy()
+
+    def species_numpy(self, isp):
+        sp = self.species[isp]
+        return {n: sp.array(n).cpu().numpy() for n in Species.NAMES}

@@ -1,0 +1,68 @@
+"""Loader of the C-ABI shared library (warpx_b200/libpic_b200.so).
+
+There is no CPU fallback: if the library is missing it is built with nvcc (sm_100a cross-compiles
+without a GPU); if that fails, or a kernel is requested without a CUDA device, the call raises.
+"""
+import ctypes as C
+import os
+
+from . import abi, build as _build
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path) or (os.path.isdir(_build.CSRC) and _build.stale()
+                                    and os.path.exists(_build.NVCC)):
+        path = _build.build()
+    L = C.CDLL(path)
+    fabp, soap, stp, gp, bp = (C.POINTER(abi.pic_fab), C.POINTER(abi.pic_soa),
+                               C.POINTER(abi.pic_stencil), C.POINTER(abi.pic_geom),
+                               C.POINTER(abi.pic_bins))
+    dp, ip, vp = abi.c_double_p, abi.c_int_p, C.c_void_p
+    sig = {
+        "pic_set_error_mode": (None, [C.c_int]),
+        "pic_last_error": (C.c_char_p, []),
+        "pic_version": (C.c_char_p, []),
+        "pic_launch_count": (C.c_long, []),
+        "pic_evolve_b": (C.c_int, [fabp, fabp, stp, C.c_double, vp]),
+        "pic_evolve_e": (C.c_int, [fabp, fabp, fabp, stp, C.c_double, vp]),
+        "pic_gather_push": (C.c_int, [soap, C.c_long, C.c_long, fabp, fabp, dp, dp, ip, C.c_double,
+                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, bp, vp]),
+        "pic_deposit_esirkepov": (C.c_int, [soap, C.c_long, C.c_long, fabp, dp, dp, ip, C.c_double,
+                                            C.c_double, C.c_double, C.c_int, bp, vp]),
+        "pic_fill_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
+        "pic_sum_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
+        "pic_halo_slab_count": (C.c_long, [fabp, C.c_int, C.c_int, C.c_int]),
+        "pic_halo_pack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "pic_halo_unpack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "pic_particles_wrap_periodic": (C.c_int, [soap, gp, vp]),
+        "pic_bins_count": (C.c_long, [ip, ip, ip]),
+        "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
+        "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),
+        "pic_sum_squares_unique": (C.c_int, [fabp, gp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)      # AttributeError if include/pic_b200.h and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _LIB = L
+    return L
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("warpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def check(rc, L=None):
+    if rc != 0:
+        L = L or lib()
+        raise RuntimeError("pic_b200: " + L.pic_last_error().decode())

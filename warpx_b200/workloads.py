@@ -72,16 +72,21 @@ def philox_normal(seed, first_id, count, ncomp=3):
     """Counter-based N(0,1) numbers: particle `id` always gets the same values, independent of how
     the domain is decomposed.  numpy Philox4x64 keyed by `seed`,
     advanced to the particle id (one 4x64 block = 4 uint64 -> 2 Box-Muller pairs per particle)."""
-    bg = np.random.Philox(key=seed)
-    bg.advance(int(first_id))            # one counter increment per particle
-    raw = bg.random_raw(4 * count).reshape(count, 4)
-    u = (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)   # [0,1)
-    u1 = 1.0 - u[:, 0:2]                 # (0,1]
-    r = np.sqrt(-2.0 * np.log(u1))
-    th = 2.0 * np.pi * u[:, 2:4]
-    g = np.stack([r[:, 0] * np.cos(th[:, 0]), r[:, 0] * np.sin(th[:, 0]), r[:, 1] * np.cos(th[:, 1])],
-                 axis=1)
-    return g[:, :ncomp]
+    out = np.empty((count, ncomp))
+    chunk = 1 << 22                      # bounded temporaries for the 10^8-particle configurations
+    for b in range(0, count, chunk):
+        n = min(chunk, count - b)
+        bg = np.random.Philox(key=seed)
+        bg.advance(int(first_id) + b)    # one counter increment (4 x uint64) per particle
+        raw = bg.random_raw(4 * n).reshape(n, 4)
+        u = (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)   # [0,1)
+        u1 = 1.0 - u[:, 0:2]             # (0,1]
+        r = np.sqrt(-2.0 * np.log(u1))
+        th = 2.0 * np.pi * u[:, 2:4]
+        g = (r[:, 0] * np.cos(th[:, 0]), r[:, 0] * np.sin(th[:, 0]), r[:, 1] * np.cos(th[:, 1]))
+        for c in range(ncomp):
+            out[b:b + n, c] = g[c]
+    return out
 
 
 def uniform_plasma_3d(n=256, ppc=(2, 2, 2), lx=40.0e-6, density=1.0e25, u_th=0.01,
@@ -91,12 +96,14 @@ def uniform_plasma_3d(n=256, ppc=(2, 2, 2), lx=40.0e-6, density=1.0e25, u_th=0.0
     that every decomposition sees the same particles.  `perturbation` adds the (non-chaotic)
     Langmuir mode of config 1 on top."""
     n_cell = (n, n, n) if n_cell is None else tuple(n_cell)
-    prob_lo, prob_hi = (-lx / 2,) * 3, (lx / 2,) * 3
+    lxs = tuple(float(v) for v in lx) if np.ndim(lx) else (float(lx),) * 3   # per-axis box length
+    prob_lo, prob_hi = tuple(-0.5 * v for v in lxs), tuple(0.5 * v for v in lxs)
+    lx = lxs[0]
     lo = np.zeros(3, dtype=int) if box_lo is None else np.asarray(box_lo)
     hi = np.asarray(n_cell) - 1 if box_hi is None else np.asarray(box_hi)
     x, y, z = lattice_positions(n_cell, prob_lo, prob_hi, ppc, lo, hi)
     nppc = ppc[0] * ppc[1] * ppc[2]
-    dxs = [lx / n_cell[d] for d in range(3)]
+    dxs = [lxs[d] / n_cell[d] for d in range(3)]
     w = np.full_like(x, density * dxs[0] * dxs[1] * dxs[2] / nppc)
     # global particle id = global cell number * nppc + in-cell index  (decomposition independent)
     idx = [np.arange(lo[d], hi[d] + 1) for d in range(3)]
