@@ -194,6 +194,11 @@ def run_engine(args):
     fe = sim.field_energy()
     value = ntot * args.steps / (ms * 1e-3)
 
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "stage_ms": {k: v[0] for k, v in stage.items()}}))
+        return
+
     # =================== end-to-end through the public API (`e2e`) ===================
     # Job-level: every rank uploads its initial particle state from pinned host memory, runs K
     # steps through Simulation.Evolve, and reads the FieldEnergy reduced diagnostic back to the
@@ -276,6 +281,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="cells per GPU and direction")
     ap.add_argument("--cpu-n", type=int, default=48, help="cells per direction of the CPU sample")
     ap.add_argument("--sort-interval", type=int, default=4)
+    ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

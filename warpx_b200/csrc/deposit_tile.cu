@@ -9,14 +9,18 @@
 //     Jx[i][j][k] += cdsx[i] * Wx[j][k],   cdsx[i] = sum_{i'<=i} wq/(dt dy dz) (Sx_old[i'] - Sx_new[i']),
 //     Wx[j][k]    = Sy_new[j] Az[k] + Sy_old[j] Bz[k],  Az = Sz_new/3 + Sz_old/6, Bz = Sz_old/3 + Sz_new/6
 // (and cyclically for Jy, Jz) -- an outer product of a (N+2)-vector and a (N+3)^2 matrix.
-// A warp works in two alternating phases on chunks of CH consecutive (cell-sorted) particles:
+// A warp works in two alternating phases on chunks of 32 consecutive (cell-sorted) particles:
 //   phase 1 (lane = particle): positions, shape factors, prefix sums -> per-particle record in smem;
-//   phase 2 (lane = stencil line): lane (a, bh) owns the lines {(a, b)} of all three components
-//       and keeps their (N+2) partial sums in REGISTERS; it walks the particles of the chunk
-//       serially.  All particles of a run with the same stencil anchor (same new cell) accumulate
-//       into the same registers -- this is the warp-segmented reduction: the segment is the run,
-//       the reduction happens in registers without any atomic or shuffle.
-//   At the end of a run the registers are added to the shared J block (smem CAS-add, the lanes of
+//   phase 2 (lane = stencil line): lanes own stencil lines of all three components and keep their
+//       partial sums in REGISTERS while the warp walks the particles of the chunk.  All particles
+//       of a run with the same stencil anchor (same new cell) accumulate into the same registers
+//       -- this is the warp-segmented reduction: the segment is the run, the reduction happens in
+//       registers without any atomic or shuffle.  Two lane layouts coexist:
+//         * "quiet" particles (old and new position in the same cell in all three directions, the
+//           overwhelming majority in a thermal plasma): the stencil shrinks to (N+1)^2 lines x N
+//           prefix entries, so 32/(N+1)^2 particles are processed per warp pass;
+//         * general particles: the full (N+3)^2 x (N+2) stencil, one particle per pass.
+//   At the end of a run the registers are added to the shared J block (smem CAS-add; the lanes of
 //   a warp hit distinct addresses); at the end of the CTA the block is added to global J with one
 //   pass of coalesced fp64 reductions (the halo overlaps neighbouring supercells).
 // Particles whose stencil does not fit the block (drifted since the last sort) take the
@@ -29,13 +33,19 @@ namespace pic {
 
 constexpr int DT_MARGIN_LO = 3;   // block starts 3 points below the supercell
 constexpr int DT_EXTRA = 7;       // block extent = tile + 7  (cell_new in [t0-1, t0+T], window -2..+3)
+constexpr int DT_CH = 32;         // particles per chunk
+constexpr int DT_CHP = DT_CH + 1; // record pitch (odd: conflict-free column access)
 
 template <int N> struct TileCfg {
     static constexpr int S = N + 3;                 // window slots per direction
     static constexpr int PN = N + 2;                // prefix entries actually deposited
-    static constexpr int NB = (S * S + 31) / 32;    // b values per lane
+    static constexpr int NB = (S * S + 31) / 32;    // b values per lane (general layout)
     static constexpr int BH = (S + NB - 1) / NB;    // lane rows
-    static constexpr int NLANES = S * BH;           // active lanes in phase 2
+    static constexpr int NLANES = S * BH;           // active lanes, general layout
+    static constexpr int QS = N + 1;                // quiet layout: slots 1..N+1
+    static constexpr int QL = QS * QS;              // lines per particle
+    static constexpr int NG = 32 / QL;              // particles per pass
+    static constexpr int QP = N;                    // live prefix entries (slots 1..N)
     // record fields: sn/so for x,y (4*S) ; A,B for y,z (4*S) ; cds x,y,z (3*PN)
     static constexpr int F_SNX = 0, F_SOX = S, F_SNY = 2 * S, F_SOY = 3 * S;
     static constexpr int F_AY = 4 * S, F_BY = 5 * S, F_AZ = 6 * S, F_BZ = 7 * S;
@@ -48,9 +58,9 @@ template <int N>
 __device__ __forceinline__ void place_old(double* so /*N+3*/, const double* w /*N+1*/, int sh) {
 #pragma unroll
     for (int s = 0; s < N + 3; ++s) {
-        const double wm = (s <= N) ? w[s] : 0.0;                  // sh = -1 -> index s
+        const double wm = (s <= N) ? w[s] : 0.0;                    // sh = -1 -> index s
         const double w0 = (s >= 1 && s - 1 <= N) ? w[s - 1] : 0.0;  // sh =  0 -> index s-1
-        const double wp = (s >= 2) ? w[s - 2] : 0.0;              // sh = +1 -> index s-2
+        const double wp = (s >= 2) ? w[s - 2] : 0.0;                // sh = +1 -> index s-2
         so[s] = (sh < 0) ? wm : ((sh == 0) ? w0 : wp);
     }
 }
@@ -58,14 +68,14 @@ __device__ __forceinline__ void place_old(double* so /*N+3*/, const double* w /*
 // one direction of the Esirkepov weights; returns i_new (leftmost index of the new stencil)
 template <int N>
 __device__ __forceinline__ int dir_weights(double x_new, double x_old, double* sn /*N+3*/,
-                                           double* so /*N+3*/, int& dl, int& du) {
+                                           double* so /*N+3*/, int& sh) {
     double wn[N + 1], wo[N + 1];
     const int i_new = shape_factor<N>(wn, x_new);
     sn[0] = 0.0; sn[N + 2] = 0.0;
 #pragma unroll
     for (int s = 0; s <= N; ++s) sn[s + 1] = wn[s];
-    // old position: same formulas as the new one evaluated at x_old; its leftmost index relative
-    // to i_new decides the slot shift (ShapeFactors.H:93-156; floor for N = 1, truncation otherwise)
+    // old position: same formulas evaluated at x_old; its leftmost index relative to i_new decides
+    // the slot shift (ShapeFactors.H:93-156; floor for N = 1, truncation otherwise)
     int i_old;
     if constexpr (N == 1) {
         const int i = (int)floor(x_old);
@@ -75,27 +85,66 @@ __device__ __forceinline__ int dir_weights(double x_new, double x_old, double* s
     } else {
         i_old = shape_factor<N>(wo, x_old);
     }
-    const int sh = i_old - i_new;
+    sh = i_old - i_new;
     place_old<N>(so, wo, sh);
-    dl = (i_old < i_new) ? 0 : 1;
-    du = (i_old > i_new) ? 0 : 1;
     return i_new;
 }
 
-__device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
+// Drifted particle: per-particle global reductions with the reference's loop nests
+// (CurrentDeposition.H:792-824).  Kept out of line so that its dynamically indexed arrays do
+// not push the hot path's weights into local memory.
+template <int N>
+__device__ __noinline__ void deposit_one_global(double xp, double yp, double zp, double wp, double uxp,
+                                                double uyp, double uzp, const FabView& Jx,
+                                                const FabView& Jy, const FabView& Jz, const DepositGeom& dg) {
+    EsirkepovWeights<N> ew;
+    ew.compute(xp, yp, zp, wp, uxp, uyp, uzp, dg);
+    const int bi = dg.lo[0] + ew.i_new - 1, bj = dg.lo[1] + ew.j_new - 1, bk = dg.lo[2] + ew.k_new - 1;
+    constexpr double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
+    for (int k = ew.dkl; k <= N + 2 - ew.dku; ++k)
+        for (int j = ew.djl; j <= N + 2 - ew.dju; ++j) {
+            double sd = 0.0;
+            const double w2 = one_third * (ew.sy_new[j] * ew.sz_new[k] + ew.sy_old[j] * ew.sz_old[k])
+                            + one_sixth * (ew.sy_new[j] * ew.sz_old[k] + ew.sy_old[j] * ew.sz_new[k]);
+            for (int i = ew.dil; i <= N + 1 - ew.diu; ++i) {
+                sd += ew.wqx * (ew.sx_old[i] - ew.sx_new[i]) * w2;
+                atomicAdd(&Jx(bi + i, bj + j, bk + k), sd);
+            }
+        }
+    for (int k = ew.dkl; k <= N + 2 - ew.dku; ++k)
+        for (int i = ew.dil; i <= N + 2 - ew.diu; ++i) {
+            double sd = 0.0;
+            const double w2 = one_third * (ew.sx_new[i] * ew.sz_new[k] + ew.sx_old[i] * ew.sz_old[k])
+                            + one_sixth * (ew.sx_new[i] * ew.sz_old[k] + ew.sx_old[i] * ew.sz_new[k]);
+            for (int j = ew.djl; j <= N + 1 - ew.dju; ++j) {
+                sd += ew.wqy * (ew.sy_old[j] - ew.sy_new[j]) * w2;
+                atomicAdd(&Jy(bi + i, bj + j, bk + k), sd);
+            }
+        }
+    for (int j = ew.djl; j <= N + 2 - ew.dju; ++j)
+        for (int i = ew.dil; i <= N + 2 - ew.diu; ++i) {
+            double sd = 0.0;
+            const double w2 = one_third * (ew.sx_new[i] * ew.sy_new[j] + ew.sx_old[i] * ew.sy_old[j])
+                            + one_sixth * (ew.sx_new[i] * ew.sy_old[j] + ew.sx_old[i] * ew.sy_new[j]);
+            for (int k = ew.dkl; k <= N + 1 - ew.dku; ++k) {
+                sd += ew.wqz * (ew.sz_old[k] - ew.sz_new[k]) * w2;
+                atomicAdd(&Jz(bi + i, bj + j, bk + k), sd);
+            }
+        }
+}
 
-template <int N, int CH, int NW>
-__global__ void __launch_bounds__(NW * 32)
+template <int N, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz, DepositGeom dg) {
     using T = TileCfg<N>;
-    constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF;
-    constexpr int CHP = CH + 1;
+    constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF, CHP = DT_CHP;
+    constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const int BD0 = bins.tile[0] + DT_EXTRA, BD1 = bins.tile[1] + DT_EXTRA, BD2 = bins.tile[2] + DT_EXTRA;
     const int bvol = BD0 * BD1 * BD2;
     double* jblk = smem;                                  // [3][BD2][BD1][BD0]
     double* recs = smem + 3 * bvol;                       // [NW][NF][CHP]
-    int* keys = (int*)(recs + (size_t)NW * NF * CHP);     // [NW][CH]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int n = tid; n < 3 * bvol; n += NW * 32) jblk[n] = 0.0;
@@ -113,52 +162,90 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
     const int o2 = bins.box_lo[2] + tc[2] * bins.tile[2] - DT_MARGIN_LO;
     __syncthreads();
 
-    // contiguous share of the supercell's particles for this warp, in multiples of CH
+    // contiguous share of the supercell's particles for this warp, in multiples of the chunk
     const int npt = p_end - p_begin;
-    const int nchunks = (npt + CH - 1) / CH;
+    const int nchunks = (npt + DT_CH - 1) / DT_CH;
     const int cpw = (nchunks + NW - 1) / NW;
     const int c_begin = warp * cpw, c_end = min(nchunks, c_begin + cpw);
 
     double* rec = recs + (size_t)warp * NF * CHP;
-    int* key = keys + warp * CH;
 
-    // phase-2 role of this lane
+    // ---- phase-2 roles of this lane ----
+    // general layout: lane (a, bh) owns lines (a, b), b = bh + nb*BH, of all three components
     const int a = lane % S, bh = lane / S;
-    const bool active = lane < T::NLANES;
-    double acc[NB][3][PN];
+    const bool active_g = lane < T::NLANES;
+    // quiet layout: lane (g, qa, qb): particle slot g of the pass, lines (1+qa, 1+qb)
+    const int g = lane / QL, ql = lane % QL, qa = ql % QS, qb = ql / QS;
+    const bool active_q = g < NG;
+
+    double accg[NB][3][PN];
+    double accq[3][QP];
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
+    for (int c = 0; c < 3; ++c) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-            for (int i = 0; i < PN; ++i) acc[nb][c][i] = 0.0;
+            for (int i = 0; i < PN; ++i) accg[nb][c][i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < QP; ++i) accq[c][i] = 0.0;
+    }
     int cur = -1;
+    bool dirty_g = false, dirty_q = false;
 
     auto flush = [&](int k) {
-        if (k < 0 || !active) return;
+        if (k < 0) return;
         const int ax = k % BD0, ay = (k / BD0) % BD1, az = k / (BD0 * BD1);
+        if (dirty_q) {
+            // fold the particle slots of the pass into slot 0, then one CAS-add per owned entry
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            const int b = bh + nb * T::BH;
-            if (b < S) {
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int i = 0; i < PN; ++i) {
-                    // x: line (j=a, k=b), prefix along i ; y: line (i=a, k=b), prefix along j ;
-                    // z: line (i=a, j=b), prefix along k
-                    const double vx = acc[nb][0][i], vy = acc[nb][1][i], vz = acc[nb][2][i];
-                    if (vx != 0.0) smem_add(&jblk[0 * bvol + (ax + i) + BD0 * ((ay + a) + BD1 * (az + b))], vx);
-                    if (vy != 0.0) smem_add(&jblk[1 * bvol + (ax + a) + BD0 * ((ay + i) + BD1 * (az + b))], vy);
-                    if (vz != 0.0) smem_add(&jblk[2 * bvol + (ax + a) + BD0 * ((ay + b) + BD1 * (az + i))], vz);
-                    acc[nb][0][i] = 0.0; acc[nb][1][i] = 0.0; acc[nb][2][i] = 0.0;
+                for (int i = 0; i < QP; ++i) {
+                    double v = accq[c][i];
+#pragma unroll
+                    for (int gg = 1; gg < NG; ++gg) {
+                        const double o = __shfl_down_sync(FULL, accq[c][i], gg * QL);
+                        if (lane + gg * QL < NG * QL) v += o;
+                    }
+                    if (lane < QL && v != 0.0) {
+                        const int e = 1 + i;   // prefix entry = slot 1 + i
+                        int ix, iy, iz;
+                        if (c == 0) { ix = ax + e; iy = ay + 1 + qa; iz = az + 1 + qb; }        // line (j, k)
+                        else if (c == 1) { ix = ax + 1 + qa; iy = ay + e; iz = az + 1 + qb; }   // line (i, k)
+                        else { ix = ax + 1 + qa; iy = ay + 1 + qb; iz = az + e; }               // line (i, j)
+                        atomicAdd(&jblk[c * bvol + ix + BD0 * (iy + BD1 * iz)], v);
+                    }
+                    accq[c][i] = 0.0;
+                }
+            dirty_q = false;
+        }
+        if (dirty_g) {
+            if (active_g) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int b = bh + nb * T::BH;
+                    if (b < S) {
+#pragma unroll
+                        for (int i = 0; i < PN; ++i) {
+                            const double vx = accg[nb][0][i], vy = accg[nb][1][i], vz = accg[nb][2][i];
+                            if (vx != 0.0) atomicAdd(&jblk[0 * bvol + (ax + i) + BD0 * ((ay + a) + BD1 * (az + b))], vx);
+                            if (vy != 0.0) atomicAdd(&jblk[1 * bvol + (ax + a) + BD0 * ((ay + i) + BD1 * (az + b))], vy);
+                            if (vz != 0.0) atomicAdd(&jblk[2 * bvol + (ax + a) + BD0 * ((ay + b) + BD1 * (az + i))], vz);
+                            accg[nb][0][i] = 0.0; accg[nb][1][i] = 0.0; accg[nb][2][i] = 0.0;
+                        }
+                    }
                 }
             }
+            dirty_g = false;
         }
     };
 
     for (int ch = c_begin; ch < c_end; ++ch) {
-        const int base = p_begin + ch * CH;
-        const int nval = min(CH, p_end - base);
+        const int base = p_begin + ch * DT_CH;
+        const int nval = min(DT_CH, p_end - base);
         // ---------------- phase 1: lane = particle ----------------
+        int key = -2;
+        bool quiet = false;
         if (lane < nval) {
             const long ip = base + lane;
             const double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip], wp = P.w[ip];
@@ -172,14 +259,15 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
                                        pos_new[1] - dg.dt * dg.dinv[1] * uyp * gaminv,
                                        pos_new[2] - dg.dt * dg.dinv[2] * uzp * gaminv};
             double sn[3][S], so[3][S];
-            int inew[3], dl[3], du[3];
+            int inew[3], sh[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) inew[d] = dir_weights<N>(pos_new[d], pos_old[d], sn[d], so[d], dl[d], du[d]);
+            for (int d = 0; d < 3; ++d) inew[d] = dir_weights<N>(pos_new[d], pos_old[d], sn[d], so[d], sh[d]);
             // anchor in block coordinates
             const int ax = dg.lo[0] + inew[0] - 1 - o0, ay = dg.lo[1] + inew[1] - 1 - o1, az = dg.lo[2] + inew[2] - 1 - o2;
             const bool fits = ax >= 0 && ay >= 0 && az >= 0 && ax + S <= BD0 && ay + S <= BD1 && az + S <= BD2;
-            key[lane] = fits ? (ax + BD0 * (ay + BD1 * az)) : -1;
             if (fits) {
+                key = ax + BD0 * (ay + BD1 * az);
+                quiet = (sh[0] == 0) && (sh[1] == 0) && (sh[2] == 0);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     rec[(T::F_SNX + s) * CHP + lane] = sn[0][s];
@@ -194,80 +282,94 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const double wqd = wq * dg.invdtd[d];
+                    // loop trimming of the reference (:777-788): entries outside [dl, N+1-du] are not deposited
+                    const int dl = (sh[d] < 0) ? 0 : 1, du = (sh[d] > 0) ? 0 : 1;
                     double run = 0.0;
 #pragma unroll
                     for (int i = 0; i < PN; ++i) {
                         run += wqd * (so[d][i] - sn[d][i]);
-                        // loop trimming of the reference (:777-788): entries outside [dl, N+1-du] are not deposited
-                        const bool live = (i >= dl[d]) && (i <= N + 1 - du[d]);
+                        const bool live = (i >= dl) && (i <= N + 1 - du);
                         rec[(T::F_CDS + d * PN + i) * CHP + lane] = live ? run : 0.0;
                     }
                 }
             } else {
-                // drifted particle: per-particle global reductions (reference strategy)
-                const int bi = dg.lo[0] + inew[0] - 1, bj = dg.lo[1] + inew[1] - 1, bk = dg.lo[2] + inew[2] - 1;
-                for (int k = dl[2]; k <= N + 2 - du[2]; ++k)
-                    for (int j = dl[1]; j <= N + 2 - du[1]; ++j) {
-                        double sd = 0.0;
-                        const double w2 = (1.0 / 3.0) * (sn[1][j] * sn[2][k] + so[1][j] * so[2][k])
-                                        + (1.0 / 6.0) * (sn[1][j] * so[2][k] + so[1][j] * sn[2][k]);
-                        for (int i = dl[0]; i <= N + 1 - du[0]; ++i) {
-                            sd += wq * dg.invdtd[0] * (so[0][i] - sn[0][i]) * w2;
-                            atomicAdd(&Jx(bi + i, bj + j, bk + k), sd);
-                        }
-                    }
-                for (int k = dl[2]; k <= N + 2 - du[2]; ++k)
-                    for (int i = dl[0]; i <= N + 2 - du[0]; ++i) {
-                        double sd = 0.0;
-                        const double w2 = (1.0 / 3.0) * (sn[0][i] * sn[2][k] + so[0][i] * so[2][k])
-                                        + (1.0 / 6.0) * (sn[0][i] * so[2][k] + so[0][i] * sn[2][k]);
-                        for (int j = dl[1]; j <= N + 1 - du[1]; ++j) {
-                            sd += wq * dg.invdtd[1] * (so[1][j] - sn[1][j]) * w2;
-                            atomicAdd(&Jy(bi + i, bj + j, bk + k), sd);
-                        }
-                    }
-                for (int j = dl[1]; j <= N + 2 - du[1]; ++j)
-                    for (int i = dl[0]; i <= N + 2 - du[0]; ++i) {
-                        double sd = 0.0;
-                        const double w2 = (1.0 / 3.0) * (sn[0][i] * sn[1][j] + so[0][i] * so[1][j])
-                                        + (1.0 / 6.0) * (sn[0][i] * so[1][j] + so[0][i] * sn[1][j]);
-                        for (int k = dl[2]; k <= N + 1 - du[2]; ++k) {
-                            sd += wq * dg.invdtd[2] * (so[2][k] - sn[2][k]) * w2;
-                            atomicAdd(&Jz(bi + i, bj + j, bk + k), sd);
-                        }
-                    }
+                key = -1;
+                deposit_one_global<N>(xp, yp, zp, wp, uxp, uyp, uzp, Jx, Jy, Jz, dg);
             }
         }
         __syncwarp();
         // ---------------- phase 2: lane = stencil lines ----------------
-        for (int pp = 0; pp < nval; ++pp) {
-            const int k = key[pp];                 // warp-uniform
-            if (k < 0) continue;
-            if (k != cur) { flush(cur); cur = k; }
-            if (active) {
-                const double snx = rec[(T::F_SNX + a) * CHP + pp], sox = rec[(T::F_SOX + a) * CHP + pp];
-                const double sny = rec[(T::F_SNY + a) * CHP + pp], soy = rec[(T::F_SOY + a) * CHP + pp];
-                double cds[3][PN];
+        {
+            const int prev = __shfl_up_sync(FULL, key, 1);
+            const bool head = (lane < nval) && (lane == 0 || key != prev);
+            unsigned heads = __ballot_sync(FULL, head);
+            const unsigned quietm = __ballot_sync(FULL, quiet);
+            while (heads) {
+                const int start = __ffs(heads) - 1;
+                heads &= heads - 1;
+                const int end = heads ? (__ffs(heads) - 1) : nval;
+                const unsigned runm = ((end >= 32) ? FULL : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+                const int k = __shfl_sync(FULL, key, start);
+                if (k < 0) continue;
+                if (k != cur) { flush(cur); cur = k; }
+                unsigned mq = runm & quietm, mg = runm & ~quietm;
+                // ---- quiet particles: NG per pass ----
+                while (mq) {
+                    int pq = -1;
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                    for (int gg = 0; gg < NG; ++gg) {
+                        const int p = mq ? (__ffs(mq) - 1) : -1;
+                        if (mq) mq &= mq - 1;
+                        if (gg == g) pq = p;
+                    }
+                    if (active_q && pq >= 0) {
+                        const double snx = rec[(T::F_SNX + 1 + qa) * CHP + pq], sox = rec[(T::F_SOX + 1 + qa) * CHP + pq];
+                        const double sny = rec[(T::F_SNY + 1 + qa) * CHP + pq], soy = rec[(T::F_SOY + 1 + qa) * CHP + pq];
+                        const double ay_ = rec[(T::F_AY + 1 + qb) * CHP + pq], by_ = rec[(T::F_BY + 1 + qb) * CHP + pq];
+                        const double az_ = rec[(T::F_AZ + 1 + qb) * CHP + pq], bz_ = rec[(T::F_BZ + 1 + qb) * CHP + pq];
+                        const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+qa, 1+qb)
+                        const double wy = snx * az_ + sox * bz_;   // Jy line (i, k)
+                        const double wz = snx * ay_ + sox * by_;   // Jz line (i, j)
 #pragma unroll
-                    for (int i = 0; i < PN; ++i) cds[c][i] = rec[(T::F_CDS + c * PN + i) * CHP + pp];
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const int b = bh + nb * T::BH;
-                    if (b < S) {
-                        const double ay_ = rec[(T::F_AY + b) * CHP + pp], by_ = rec[(T::F_BY + b) * CHP + pp];
-                        const double az_ = rec[(T::F_AZ + b) * CHP + pp], bz_ = rec[(T::F_BZ + b) * CHP + pp];
-                        const double wx = sny * az_ + soy * bz_;   // Jx line (j=a, k=b)
-                        const double wy = snx * az_ + sox * bz_;   // Jy line (i=a, k=b)
-                        const double wz = snx * ay_ + sox * by_;   // Jz line (i=a, j=b)
-#pragma unroll
-                        for (int i = 0; i < PN; ++i) {
-                            acc[nb][0][i] += cds[0][i] * wx;
-                            acc[nb][1][i] += cds[1][i] * wy;
-                            acc[nb][2][i] += cds[2][i] * wz;
+                        for (int i = 0; i < QP; ++i) {
+                            accq[0][i] += rec[(T::F_CDS + 0 * PN + 1 + i) * CHP + pq] * wx;
+                            accq[1][i] += rec[(T::F_CDS + 1 * PN + 1 + i) * CHP + pq] * wy;
+                            accq[2][i] += rec[(T::F_CDS + 2 * PN + 1 + i) * CHP + pq] * wz;
                         }
                     }
+                    dirty_q = true;
+                }
+                // ---- general particles: one per pass ----
+                while (mg) {
+                    const int pp = __ffs(mg) - 1;
+                    mg &= mg - 1;
+                    if (active_g) {
+                        const double snx = rec[(T::F_SNX + a) * CHP + pp], sox = rec[(T::F_SOX + a) * CHP + pp];
+                        const double sny = rec[(T::F_SNY + a) * CHP + pp], soy = rec[(T::F_SOY + a) * CHP + pp];
+                        double cds[3][PN];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int i = 0; i < PN; ++i) cds[c][i] = rec[(T::F_CDS + c * PN + i) * CHP + pp];
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            const int b = bh + nb * T::BH;
+                            if (b < S) {
+                                const double ay_ = rec[(T::F_AY + b) * CHP + pp], by_ = rec[(T::F_BY + b) * CHP + pp];
+                                const double az_ = rec[(T::F_AZ + b) * CHP + pp], bz_ = rec[(T::F_BZ + b) * CHP + pp];
+                                const double wx = sny * az_ + soy * bz_;   // Jx line (j=a, k=b)
+                                const double wy = snx * az_ + sox * bz_;   // Jy line (i=a, k=b)
+                                const double wz = snx * ay_ + sox * by_;   // Jz line (i=a, j=b)
+#pragma unroll
+                                for (int i = 0; i < PN; ++i) {
+                                    accg[nb][0][i] += cds[0][i] * wx;
+                                    accg[nb][1][i] += cds[1][i] * wy;
+                                    accg[nb][2][i] += cds[2][i] * wz;
+                                }
+                            }
+                        }
+                    }
+                    dirty_g = true;
                 }
             }
         }
@@ -289,13 +391,13 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
     }
 }
 
-template <int N, int CH, int NW>
+template <int N, int NW>
 static int launch_tile(SoaView P, const BinsView& bv, const pic_fab J[3], const DepositGeom& dg,
                        cudaStream_t s) {
     using T = TileCfg<N>;
     const long bvol = (long)(bv.tile[0] + DT_EXTRA) * (bv.tile[1] + DT_EXTRA) * (bv.tile[2] + DT_EXTRA);
-    const size_t smem = (size_t)(3 * bvol + (size_t)NW * T::NF * (CH + 1)) * sizeof(double) + (size_t)NW * CH * sizeof(int);
-    auto kern = deposit_tile_kernel<N, CH, NW>;
+    const size_t smem = (size_t)(3 * bvol + (size_t)NW * T::NF * DT_CHP) * sizeof(double);
+    auto kern = deposit_tile_kernel<N, NW>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -314,9 +416,9 @@ int deposit_tile_launch(const pic_soa* p, long offset, long np, const pic_fab J[
     PIC_REQUIRE(offset == 0 && np == p->np, "pic_deposit_esirkepov: bins describe the whole tile (offset 0, np = all)");
     BinsView bv = make_bins(*bins);
     SoaView P = make_soa(*p, 0);
-    if (nox == 1) return launch_tile<1, 16, 16>(P, bv, J, dg, s);
-    if (nox == 2) return launch_tile<2, 16, 16>(P, bv, J, dg, s);
-    return launch_tile<3, 16, 16>(P, bv, J, dg, s);
+    if (nox == 1) return launch_tile<1, 8>(P, bv, J, dg, s);
+    if (nox == 2) return launch_tile<2, 8>(P, bv, J, dg, s);
+    return launch_tile<3, 8>(P, bv, J, dg, s);
 }
 
 }  // namespace pic

@@ -26,7 +26,7 @@ struct SmemFields {
 };
 
 template <int N, int G, bool YEE>
-__global__ void __launch_bounds__(GT_THREADS)
+__global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
                         double dt, int pusher, int push_position) {
     extern __shared__ double smem[];

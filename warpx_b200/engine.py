@@ -122,6 +122,9 @@ class Species:
         self.capacity = max(capacity, self.np)
         # two SoA buffers: the counting sort permutes from one into the other
         self.buf = [t.empty((7, self.capacity), dtype=t.float64, device=sim.device) for _ in range(2)]
+        # 64-bit particle id (the reference's idcpu): rank in the upper bits, local index below
+        self.ids = [t.empty(self.capacity, dtype=t.int64, device=sim.device) for _ in range(2)]
+        self.ids[0][:self.np] = t.arange(self.np, dtype=t.int64, device=sim.device) + (sim.rank << 40)
         self.cur = 0
         for n, name_ in enumerate(self.NAMES):
             a = arrays[name_]
@@ -136,9 +139,12 @@ class Species:
         s = abi.pic_soa()
         for n, name in enumerate(self.NAMES):
             setattr(s, name, b[n].data_ptr())
-        s.idcpu = None
+        s.idcpu = self.ids[self.cur if which is None else which].data_ptr()
         s.np = self.np
         return s
+
+    def id_array(self):
+        return self.ids[self.cur][:self.np]
 
     def array(self, name):
         return self.buf[self.cur][self.NAMES.index(name), :self.np]
@@ -313,7 +319,9 @@ class Simulation:
             down, up = parallel.particle_destinations(cell, self.dec, dim)
             keep = ~(down | up)
             cur = sp.buf[sp.cur][:, :sp.np]
+            cur_id = sp.ids[sp.cur][:sp.np]
             s_lo, s_hi = cur[:, down].contiguous(), cur[:, up].contiguous()
+            i_lo, i_hi = cur_id[down].contiguous(), cur_id[up].contiguous()
             counts = t.tensor([s_lo.shape[1], s_hi.shape[1]], dtype=t.int64, device=self.device)
             rc = t.zeros(2, dtype=t.int64, device=self.device)
             # counts: what I send low is received by my low neighbour as "from high"
@@ -322,7 +330,11 @@ class Simulation:
             r_lo = t.empty((7, n_lo), dtype=t.float64, device=self.device)
             r_hi = t.empty((7, n_hi), dtype=t.float64, device=self.device)
             parallel.exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
+            ri_lo = t.empty(n_lo, dtype=t.int64, device=self.device)
+            ri_hi = t.empty(n_hi, dtype=t.int64, device=self.device)
+            parallel.exchange(self.dist, self.dec, dim, i_lo, i_hi, ri_lo, ri_hi)
             kept = cur[:, keep]
+            kept_id = cur_id[keep]
             n_new = kept.shape[1] + n_lo + n_hi
             if n_new > sp.capacity:
                 raise RuntimeError("particle capacity exceeded on rank %d" % self.rank)
@@ -330,6 +342,10 @@ class Simulation:
             nb[:, :kept.shape[1]] = kept
             nb[:, kept.shape[1]:kept.shape[1] + n_lo] = r_lo
             nb[:, kept.shape[1] + n_lo:n_new] = r_hi
+            ni = sp.ids[1 - sp.cur]
+            ni[:kept.shape[1]] = kept_id
+            ni[kept.shape[1]:kept.shape[1] + n_lo] = ri_lo
+            ni[kept.shape[1] + n_lo:n_new] = ri_hi
             sp.cur = 1 - sp.cur
             sp.np = n_new
             sp.bins = None      # order changed: bins are stale until the next sort
@@ -406,6 +422,11 @@ class Simulation:
         """(descriptor, numpy array [k, j, i]) of component comp (0..8 = Ex..jz)."""
         return self.fab[comp], self.data[comp].cpu().numpy()
 
-    def species_numpy(self, isp):
+    def species_numpy(self, isp, sort_by_id=False):
         sp = self.species[isp]
-        return {n: sp.array(n).cpu().numpy() for n in Species.NAMES}
+        out = {n: sp.array(n).cpu().numpy() for n in Species.NAMES}
+        out["id"] = sp.id_array().cpu().numpy()
+        if sort_by_id:
+            order = np.argsort(out["id"], kind="stable")
+            out = {k: v[order] for k, v in out.items()}
+        return out
