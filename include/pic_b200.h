@@ -139,6 +139,14 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
                           double q, double dt, double relative_time, int nox,
                           const pic_bins* bins, void* stream);
 
+/* Which kernel serves pic_deposit_esirkepov when bins are given (tuning / A-B measurements):
+ * PIC_DEPOSIT_RUNS (default): warp-segmented register reduction + fp64 L2 reductions;
+ * PIC_DEPOSIT_TILE: the same reduction staged through a shared-memory J block per supercell.
+ * Analogous to WarpX's runtime switch warpx.do_shared_mem_current_deposition
+ * (Source/WarpX.cpp:126, Docs/source/usage/parameters.rst:2608-2623). */
+enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1 };
+void pic_set_deposit_mode(int mode);
+
 /* ------------------------------------------------------------------------------------------
  * Guard cells  (replaces ablastr::utils::communication::FillBoundary / SumBoundary)
  * ---------------------------------------------------------------------------------------- */

@@ -202,13 +202,20 @@ def test_gather_push_matches_oracle(orc, dev, nox, galerkin, pusher, path):
 
 
 @pytest.mark.parametrize("nox", [1, 2, 3])
-@pytest.mark.parametrize("path", ["global", "tile", "tile_drifted", "tile_unsorted_bins"])
+@pytest.mark.parametrize("path", ["global", "tile", "tile_drifted", "tile_unsorted_bins",
+                                  "runs", "runs_drifted", "runs_relativistic"])
 def test_deposit_matches_oracle(orc, dev, nox, path):
+    """global: order-agnostic kernel; tile*: shared-memory-block kernel; runs*: register-run kernel
+    (the default with bins).  *_drifted: bins are stale; runs_relativistic: most particles change cell."""
     L = orc.lib()
+    dev.L.pic_set_deposit_mode(1 if path.startswith("tile") else 0)
+    kind = path
+    path = {"runs": "tile", "runs_drifted": "tile_drifted", "runs_relativistic": "tile"}.get(path, path)
     n = (20, 16, 12)
     lx = 1e-5
     box_lo, box_hi = box(n)
-    wl, sp = _particles(orc, n, (2, 2, 2), 0.5, lx, shuffle=(path == "global"))
+    u_th = {"runs_relativistic": 3.0, "runs": 0.02, "tile": 0.02}.get(kind, 0.5)
+    wl, sp = _particles(orc, n, (2, 2, 2), u_th, lx, shuffle=(path == "global"))
     prob_lo = wl["prob_lo"]
     dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
     dinv = [1.0 / v for v in dx]
@@ -235,6 +242,7 @@ def test_deposit_matches_oracle(orc, dev, nox, path):
     dev.sync()
     L.orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
                             abi.int3(lo), sp["q"], dt, -0.5 * dt, nox)
+    dev.L.pic_set_deposit_mode(0)
     for c in range(3):
         assert rel_linf(tens[c].cpu().numpy(), J[c].a) <= 1e-12, "j" + "xyz"[c]
     # Esirkepov identity (size independent): sum_cells J_x dV = sum_p q w (x_new - x_old)/dt

@@ -8,9 +8,11 @@
 //  * deposit_global -- order-agnostic: one thread per particle, fp64 red.global per grid point.
 //    This is the reference's GPU strategy (Gpu::Atomic::AddNoRet, :799,810,821) and is kept as the
 //    drop-in for callers that cannot provide cell bins.
-//  * deposit_tile (deposit_tile.cuh) -- cell-sorted particles: one CTA per supercell accumulates
-//    into a shared-memory J block; runs of same-cell particles are reduced in registers by a
-//    warp whose lanes own stencil lines; the block is flushed once.
+//  * deposit_runs.cu (default with bins) -- cell-sorted particles: runs of same-cell particles are
+//    reduced in registers by a warp whose lanes own stencil lines; retired planes go to J with
+//    fp64 L2 reductions (~7 per particle instead of 540).
+//  * deposit_tile.cu (pic_set_deposit_mode(PIC_DEPOSIT_TILE)) -- same reduction, staged through a shared-memory J block
+//    per supercell; kept for comparison (slower on sm_100a: shared fp64 atomics are CAS loops).
 #include "pic_common.cuh"
 #include "deposit_common.cuh"
 
@@ -60,10 +62,16 @@ deposit_global(SoaView P, long np, FabView Jx, FabView Jy, FabView Jz, DepositGe
 
 int deposit_tile_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
                         const DepositGeom& dg, int nox, const pic_bins* bins, cudaStream_t s);
+int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
+                        const DepositGeom& dg, int nox, cudaStream_t s);
+
+static int g_deposit_mode = PIC_DEPOSIT_RUNS;
 
 }  // namespace pic
 
 using namespace pic;
+
+extern "C" void pic_set_deposit_mode(int mode) { g_deposit_mode = mode; }
 
 extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, const pic_fab J[3],
                                      const double dinv[3], const double xyzmin[3], const int lo[3],
@@ -85,7 +93,13 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
     dg.invdtd[1] = (1.0 / dt) * dinv[0] * dinv[2];
     dg.invdtd[2] = (1.0 / dt) * dinv[0] * dinv[1];
     cudaStream_t s = (cudaStream_t)stream;
-    if (bins) return deposit_tile_launch(p, offset, np, J, dg, nox, bins, s);
+    if (bins) {
+        // cell-sorted particles: warp-segmented register reduction (deposit_runs.cu).  The
+        // shared-memory-block variant (deposit_tile.cu) is kept for comparison: pic_set_deposit_mode().
+        PIC_REQUIRE(np < (1L << 31), "pic_deposit_esirkepov: more than 2^31 particles in one tile");
+        if (g_deposit_mode == PIC_DEPOSIT_TILE) return deposit_tile_launch(p, offset, np, J, dg, nox, bins, s);
+        return deposit_runs_launch(p, offset, np, J, dg, nox, s);
+    }
     SoaView P = make_soa(*p, offset);
     const int tpb = 128;
     const unsigned nblk = (unsigned)((np + tpb - 1) / tpb);

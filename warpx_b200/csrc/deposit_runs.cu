@@ -1,0 +1,483 @@
+// Esirkepov deposition for cell-sorted particles by warp-segmented register reduction
+// (the timed path; replaces doEsirkepovDepositionShapeN, CurrentDeposition.H:642-907).
+//
+// For one particle the Esirkepov stencil is an outer product,
+//     Jx[i][j][k] += cdsx[i] * Wx[j][k],   cdsx[i] = sum_{i'<=i} wq/(dt dy dz) (Sx_old[i'] - Sx_new[i']),
+//     Wx[j][k]    = Sy_new[j] Az[k] + Sy_old[j] Bz[k],  Az = Sz_new/3 + Sz_old/6, Bz = Sz_old/3 + Sz_new/6
+// (cyclically for Jy, Jz).  A warp alternates two phases over chunks of 32 consecutive particles:
+//   phase 1 (lane = particle): positions, shape factors, prefix sums -> per-particle record in smem;
+//   phase 2 (lane = stencil line): every lane owns stencil lines of all three components and keeps
+//       their partial sums in REGISTERS while the warp walks the particles.  All particles of a
+//       run with the same stencil anchor (same new cell) accumulate into the same registers: the
+//       segment of the segmented reduction is the run of cell-sorted particles, and the reduction
+//       costs no atomic and no shuffle.
+// Two kernels:
+//   deposit_quiet_kernel  -- particles whose old and new position lie in the same cell in all three
+//       directions (the overwhelming majority in a thermal plasma).  Their stencil is (N+1)^2
+//       lines x N prefix entries, so 32/(N+1)^2 particles are processed per warp pass.  Cells are
+//       visited along x, and a lane owns the Jy/Jz lines of a fixed ABSOLUTE x (ring mapping): when
+//       the anchor advances by one cell only the plane leaving the window is retired -- 40 fp64
+//       reductions per cell instead of the reference's (N+2)(N+3)^2*3 = 540 per PARTICLE.
+//       Particles that changed cell are appended to a list.
+//   deposit_general_kernel -- the listed particles with the full (N+3)^2 x (N+2) stencil.
+// Retired sums go to J with fp64 red.global (L2 reductions, no return value, no shared-memory
+// staging: on sm_100a shared fp64 atomics are CAS loops and the staging block would cap the SM at
+// 8 resident warps -- measured in profiles/).  Any particle order is CORRECT (a run
+// may be a single particle); cell-sorted order is FAST.
+#include "pic_common.cuh"
+#include "deposit_common.cuh"
+
+namespace pic {
+
+constexpr int DR_CH = 32;          // particles per chunk
+constexpr int DR_CHP = DR_CH + 1;  // record pitch (odd: conflict-free column access)
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- per-direction weights without dynamic indexing -------------------------------------------
+// shifted (old-position) weights: slot s holds w[s-1-sh], sh in {-1,0,1}  (ShapeFactors.H:93-156)
+template <int N>
+__device__ __forceinline__ void dr_place_old(double* so /*N+3*/, const double* w /*N+1*/, int sh) {
+#pragma unroll
+    for (int s = 0; s < N + 3; ++s) {
+        const double wm = (s <= N) ? w[s] : 0.0;
+        const double w0 = (s >= 1 && s - 1 <= N) ? w[s - 1] : 0.0;
+        const double wp = (s >= 2) ? w[s - 2] : 0.0;
+        so[s] = (sh < 0) ? wm : ((sh == 0) ? w0 : wp);
+    }
+}
+
+// weights of the new (wn) and old (wo) position and the slot shift of the old stencil
+template <int N>
+__device__ __forceinline__ int dr_dir(double x_new, double x_old, double* wn, double* wo, int& sh) {
+    const int i_new = shape_factor<N>(wn, x_new);
+    int i_old;
+    if constexpr (N == 1) {   // order 1 uses floor for the old position (ShapeFactors.H:110)
+        const int i = (int)floor(x_old);
+        const double d = x_old - (double)i;
+        wo[0] = 1.0 - d; wo[1] = d;
+        i_old = i;
+    } else {
+        i_old = shape_factor<N>(wo, x_old);
+    }
+    sh = i_old - i_new;
+    return i_new;
+}
+
+struct ParticleGeom {   // new/old positions in grid units and charge factor of one particle
+    double pos_new[3], pos_old[3], wq;
+};
+__device__ __forceinline__ ParticleGeom particle_geom(double xp, double yp, double zp, double wp, double uxp,
+                                                      double uyp, double uzp, const DepositGeom& dg) {
+    ParticleGeom g;
+    const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);  // :687-689
+    g.wq = dg.q * wp;
+    g.pos_new[0] = (xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0];   // :725-736
+    g.pos_new[1] = (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1];
+    g.pos_new[2] = (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2];
+    g.pos_old[0] = g.pos_new[0] - dg.dt * dg.dinv[0] * uxp * gaminv;
+    g.pos_old[1] = g.pos_new[1] - dg.dt * dg.dinv[1] * uyp * gaminv;
+    g.pos_old[2] = g.pos_new[2] - dg.dt * dg.dinv[2] * uzp * gaminv;
+    return g;
+}
+
+// anchor (global index of slot 0 of the stencil) packed relative to the J arrays, 10 bits each
+struct KeyBase { int b0, b1, b2; };
+__device__ __forceinline__ int pack_key(int gx, int gy, int gz, const KeyBase& kb) {
+    return (gx - kb.b0) | ((gy - kb.b1) << 10) | ((gz - kb.b2) << 20);
+}
+
+// ================================================================================================
+// quiet particles
+// ================================================================================================
+template <int N> struct QuietCfg {
+    static constexpr int QS = N + 1;          // slots 1..N+1 of the (N+3)-slot window
+    static constexpr int QL = QS * QS;        // lines per particle
+    static constexpr int NG = 32 / QL;        // particles per warp pass
+    static constexpr int QP = N;              // live prefix entries (slots 1..N)
+    static constexpr int F_SNX = 0, F_SOX = QS, F_SNY = 2 * QS, F_SOY = 3 * QS;
+    static constexpr int F_AY = 4 * QS, F_BY = 5 * QS, F_AZ = 6 * QS, F_BZ = 7 * QS;
+    static constexpr int F_CDS = 8 * QS;      // + comp*QP + i
+    static constexpr int NF = 8 * QS + 3 * QP;
+};
+
+template <int N, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabView Jy, FabView Jz,
+                     DepositGeom dg, KeyBase kb, int* __restrict__ list, int* __restrict__ list_count) {
+    using T = QuietCfg<N>;
+    constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = DR_CHP;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = smem + (size_t)warp * NF * CHP;
+
+    const long nchunks = (np + DR_CH - 1) / DR_CH;
+    const long wg = (long)blockIdx.x * NW + warp;
+    const long c_begin = wg * chunks_per_warp;
+    const long c_end = min(nchunks, c_begin + chunks_per_warp);
+    if (c_begin >= c_end) return;
+
+    // lane (g, u, v): particle slot g of the pass;
+    //   Jx line (j, k) = (1+u, 1+v);  Jy line (i, k) = (1+ur, 1+v);  Jz line (i, j) = (1+ur, 1+v),
+    //   ur = (u - (ax+1)) mod QS  (ring mapping: a lane keeps the Jy/Jz lines of one absolute x)
+    const int g = lane / QL, ql = lane % QL, qu = ql % QS, qv = ql / QS;
+    const bool active_q = g < NG;
+    double acc[3][QP];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < QP; ++i) acc[c][i] = 0.0;
+    int cur = -1;
+
+    auto ring = [&](int ax) -> int {
+        int r = (qu - (ax + 1)) % QS;
+        return r < 0 ? r + QS : r;
+    };
+    auto fold = [&](double v) -> double {          // sum over the particle slots of the pass
+        double r = v;
+#pragma unroll
+        for (int gg = 1; gg < NG; ++gg) {
+            const double o = __shfl_down_sync(FULL, v, gg * QL);
+            if (lane + gg * QL < NG * QL) r += o;
+        }
+        return r;
+    };
+    // retire everything (anchor jumps) or only the plane x = ax+1 (anchor advances by one along x)
+    auto retire = [&](int k_old, int k_new) {
+        if (k_old < 0) return;
+        const int ax = (k_old & 1023), gx = ax + kb.b0, gy = ((k_old >> 10) & 1023) + kb.b1, gz = (k_old >> 20) + kb.b2;
+        const int ur = ring(ax);
+        const bool slide = (k_new == k_old + 1);
+        const bool leaving = (ur == 0);
+        double* px = &Jx(gx + 1, gy + 1 + qu, gz + 1 + qv);          // entries along x: + i
+        double* py = &Jy(gx + 1 + ur, gy + 1, gz + 1 + qv);          // entries along y: + i * sj
+        double* pz = &Jz(gx + 1 + ur, gy + 1 + qv, gz + 1);          // entries along z: + i * sk
+        if (slide) {
+            const double vx = fold(acc[0][0]);
+            if (lane < QL && vx != 0.0) atomicAdd(px, vx);
+#pragma unroll
+            for (int i = 0; i + 1 < QP; ++i) acc[0][i] = acc[0][i + 1];
+            acc[0][QP - 1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < QP; ++i) {
+                const double vy = fold(acc[1][i]), vz = fold(acc[2][i]);
+                if (lane < QL && leaving) {
+                    if (vy != 0.0) atomicAdd(py + i * Jy.sj, vy);
+                    if (vz != 0.0) atomicAdd(pz + i * Jz.sk, vz);
+                }
+                if (leaving) { acc[1][i] = 0.0; acc[2][i] = 0.0; }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < QP; ++i) {
+                const double vx = fold(acc[0][i]), vy = fold(acc[1][i]), vz = fold(acc[2][i]);
+                if (lane < QL) {
+                    if (vx != 0.0) atomicAdd(px + i, vx);
+                    if (vy != 0.0) atomicAdd(py + i * Jy.sj, vy);
+                    if (vz != 0.0) atomicAdd(pz + i * Jz.sk, vz);
+                }
+                acc[0][i] = 0.0; acc[1][i] = 0.0; acc[2][i] = 0.0;
+            }
+        }
+    };
+
+    // software prefetch: chunk ch+1 is requested before chunk ch is processed
+    double pf[7] = {0, 0, 0, 0, 0, 0, 0};
+    auto prefetch = [&](long ch) {
+        const long ip = ch * DR_CH + lane;
+        if (ch < c_end && ip < np) {
+            pf[0] = P.x[ip]; pf[1] = P.y[ip]; pf[2] = P.z[ip]; pf[3] = P.w[ip];
+            pf[4] = P.ux[ip]; pf[5] = P.uy[ip]; pf[6] = P.uz[ip];
+        }
+    };
+    prefetch(c_begin);
+
+    for (long ch = c_begin; ch < c_end; ++ch) {
+        const long base = ch * DR_CH;
+        const int nval = (int)min((long)DR_CH, np - base);
+        const double xp = pf[0], yp = pf[1], zp = pf[2], wp = pf[3], uxp = pf[4], uyp = pf[5], uzp = pf[6];
+        prefetch(ch + 1);
+        // ---------------- phase 1: lane = particle ----------------
+        int key = -2;
+        bool moved = false;
+        if (lane < nval) {
+            const ParticleGeom pg = particle_geom(xp, yp, zp, wp, uxp, uyp, uzp, dg);
+            double wn[3][N + 1], wo[3][N + 1];
+            int inew[3], sh[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn[d], wo[d], sh[d]);
+            moved = (sh[0] != 0) || (sh[1] != 0) || (sh[2] != 0);
+            if (!moved) {
+                key = pack_key(dg.lo[0] + inew[0] - 1, dg.lo[1] + inew[1] - 1, dg.lo[2] + inew[2] - 1, kb);
+                // slots 1..N+1 hold wn[0..N] (new) and wo[0..N] (old, no shift)
+#pragma unroll
+                for (int s = 0; s < QS; ++s) {
+                    rec[(T::F_SNX + s) * CHP + lane] = wn[0][s];
+                    rec[(T::F_SOX + s) * CHP + lane] = wo[0][s];
+                    rec[(T::F_SNY + s) * CHP + lane] = wn[1][s];
+                    rec[(T::F_SOY + s) * CHP + lane] = wo[1][s];
+                    rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * wn[1][s] + (1.0 / 6.0) * wo[1][s];
+                    rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * wo[1][s] + (1.0 / 6.0) * wn[1][s];
+                    rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * wn[2][s] + (1.0 / 6.0) * wo[2][s];
+                    rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * wo[2][s] + (1.0 / 6.0) * wn[2][s];
+                }
+                // prefix sums over slots 1..N (slot 0 is empty; the sum over 1..N+1 vanishes and is
+                // not deposited -- loop trimming of CurrentDeposition.H:777-788 with dl = du = 1)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double wqd = pg.wq * dg.invdtd[d];
+                    double run = 0.0;
+#pragma unroll
+                    for (int i = 0; i < QP; ++i) {
+                        run += wqd * (wo[d][i] - wn[d][i]);
+                        rec[(T::F_CDS + d * QP + i) * CHP + lane] = run;
+                    }
+                }
+            } else {
+                key = -1;
+            }
+        }
+        // particles that changed cell: append to the list (warp-aggregated)
+        {
+            const unsigned mm = __ballot_sync(FULL, moved);
+            if (mm) {
+                int basei = 0;
+                if (lane == 0) basei = atomicAdd(list_count, __popc(mm));
+                basei = __shfl_sync(FULL, basei, 0);
+                if (moved) list[basei + __popc(mm & ((1u << lane) - 1u))] = (int)(base + lane);
+            }
+        }
+        __syncwarp();
+        // ---------------- phase 2: lane = stencil lines ----------------
+        {
+            const int prev = __shfl_up_sync(FULL, key, 1);
+            const bool head = (lane < nval) && (lane == 0 || key != prev);
+            unsigned heads = __ballot_sync(FULL, head);
+            while (heads) {
+                const int start = __ffs(heads) - 1;
+                heads &= heads - 1;
+                const int end = heads ? (__ffs(heads) - 1) : nval;
+                unsigned mq = ((end >= 32) ? FULL : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+                const int k = __shfl_sync(FULL, key, start);
+                if (k < 0) continue;
+                if (k != cur) { retire(cur, k); cur = k; }
+                const int ur = ring(k & 1023);
+                while (mq) {
+                    int pq = -1;
+#pragma unroll
+                    for (int gg = 0; gg < NG; ++gg) {
+                        const int p = mq ? (__ffs(mq) - 1) : -1;
+                        if (mq) mq &= mq - 1;
+                        if (gg == g) pq = p;
+                    }
+                    if (active_q && pq >= 0) {
+                        const double snx = rec[(T::F_SNX + ur) * CHP + pq], sox = rec[(T::F_SOX + ur) * CHP + pq];
+                        const double sny = rec[(T::F_SNY + qu) * CHP + pq], soy = rec[(T::F_SOY + qu) * CHP + pq];
+                        const double ay_ = rec[(T::F_AY + qv) * CHP + pq], by_ = rec[(T::F_BY + qv) * CHP + pq];
+                        const double az_ = rec[(T::F_AZ + qv) * CHP + pq], bz_ = rec[(T::F_BZ + qv) * CHP + pq];
+                        const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+u, 1+v)
+                        const double wy = snx * az_ + sox * bz_;   // Jy line (i, k) = (1+ur, 1+v)
+                        const double wz = snx * ay_ + sox * by_;   // Jz line (i, j) = (1+ur, 1+v)
+#pragma unroll
+                        for (int i = 0; i < QP; ++i) {
+                            acc[0][i] += rec[(T::F_CDS + 0 * QP + i) * CHP + pq] * wx;
+                            acc[1][i] += rec[(T::F_CDS + 1 * QP + i) * CHP + pq] * wy;
+                            acc[2][i] += rec[(T::F_CDS + 2 * QP + i) * CHP + pq] * wz;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    retire(cur, -1);
+}
+
+// ================================================================================================
+// particles that changed cell: full stencil
+// ================================================================================================
+template <int N> struct GeneralCfg {
+    static constexpr int S = N + 3;                 // window slots per direction
+    static constexpr int PN = N + 2;                // prefix entries deposited
+    static constexpr int NB = (S * S + 31) / 32;    // b values per lane
+    static constexpr int BH = (S + NB - 1) / NB;
+    static constexpr int NLANES = S * BH;
+    static constexpr int F_SNX = 0, F_SOX = S, F_SNY = 2 * S, F_SOY = 3 * S;
+    static constexpr int F_AY = 4 * S, F_BY = 5 * S, F_AZ = 6 * S, F_BZ = 7 * S;
+    static constexpr int F_CDS = 8 * S;
+    static constexpr int NF = 8 * S + 3 * PN;
+};
+
+template <int N, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+deposit_general_kernel(SoaView P, const int* __restrict__ list, const int* __restrict__ list_count,
+                       FabView Jx, FabView Jy, FabView Jz, DepositGeom dg, KeyBase kb) {
+    using T = GeneralCfg<N>;
+    constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF, CHP = DR_CHP;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = smem + (size_t)warp * NF * CHP;
+    const int count = *list_count;
+    const int nchunks = (count + DR_CH - 1) / DR_CH;
+    // lane (a, bh) owns lines (a, b), b = bh + nb*BH:  Jx (j=a,k=b), Jy (i=a,k=b), Jz (i=a,j=b)
+    const int a = lane % S, bh = lane / S;
+    const bool active = lane < T::NLANES;
+    double acc[NB][3][PN];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < PN; ++i) acc[nb][c][i] = 0.0;
+
+    auto flush = [&](int k) {
+        if (k < 0 || !active) return;
+        const int gx = (k & 1023) + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const int b = bh + nb * T::BH;
+            if (b < S) {
+                double* px = &Jx(gx, gy + a, gz + b);
+                double* py = &Jy(gx + a, gy, gz + b);
+                double* pz = &Jz(gx + a, gy + b, gz);
+#pragma unroll
+                for (int i = 0; i < PN; ++i) {
+                    const double vx = acc[nb][0][i], vy = acc[nb][1][i], vz = acc[nb][2][i];
+                    if (vx != 0.0) atomicAdd(px + i, vx);
+                    if (vy != 0.0) atomicAdd(py + i * Jy.sj, vy);
+                    if (vz != 0.0) atomicAdd(pz + i * Jz.sk, vz);
+                    acc[nb][0][i] = 0.0; acc[nb][1][i] = 0.0; acc[nb][2][i] = 0.0;
+                }
+            }
+        }
+    };
+
+    for (int ch = blockIdx.x * NW + warp; ch < nchunks; ch += gridDim.x * NW) {
+        const int base = ch * DR_CH;
+        const int nval = min(DR_CH, count - base);
+        int key = -2;
+        if (lane < nval) {
+            const long ip = list[base + lane];
+            const ParticleGeom pg = particle_geom(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip], dg);
+            double sn[3][S], so[3][S];
+            int inew[3], sh[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                double wn[N + 1], wo[N + 1];
+                inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn, wo, sh[d]);
+                sn[d][0] = 0.0; sn[d][N + 2] = 0.0;
+#pragma unroll
+                for (int s = 0; s <= N; ++s) sn[d][s + 1] = wn[s];
+                dr_place_old<N>(so[d], wo, sh[d]);
+            }
+            key = pack_key(dg.lo[0] + inew[0] - 1, dg.lo[1] + inew[1] - 1, dg.lo[2] + inew[2] - 1, kb);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                rec[(T::F_SNX + s) * CHP + lane] = sn[0][s];
+                rec[(T::F_SOX + s) * CHP + lane] = so[0][s];
+                rec[(T::F_SNY + s) * CHP + lane] = sn[1][s];
+                rec[(T::F_SOY + s) * CHP + lane] = so[1][s];
+                rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * sn[1][s] + (1.0 / 6.0) * so[1][s];
+                rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * so[1][s] + (1.0 / 6.0) * sn[1][s];
+                rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * sn[2][s] + (1.0 / 6.0) * so[2][s];
+                rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * so[2][s] + (1.0 / 6.0) * sn[2][s];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double wqd = pg.wq * dg.invdtd[d];
+                // loop trimming of the reference (:777-788): entries outside [dl, N+1-du] are not deposited
+                const int dl = (sh[d] < 0) ? 0 : 1, du = (sh[d] > 0) ? 0 : 1;
+                double run = 0.0;
+#pragma unroll
+                for (int i = 0; i < PN; ++i) {
+                    run += wqd * (so[d][i] - sn[d][i]);
+                    const bool live = (i >= dl) && (i <= N + 1 - du);
+                    rec[(T::F_CDS + d * PN + i) * CHP + lane] = live ? run : 0.0;
+                }
+            }
+        }
+        __syncwarp();
+        int cur = -1;
+        for (int pp = 0; pp < nval; ++pp) {
+            const int k = __shfl_sync(FULL, key, pp);
+            if (k != cur) { flush(cur); cur = k; }
+            if (active) {
+                const double snx = rec[(T::F_SNX + a) * CHP + pp], sox = rec[(T::F_SOX + a) * CHP + pp];
+                const double sny = rec[(T::F_SNY + a) * CHP + pp], soy = rec[(T::F_SOY + a) * CHP + pp];
+                double cds[3][PN];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int i = 0; i < PN; ++i) cds[c][i] = rec[(T::F_CDS + c * PN + i) * CHP + pp];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int b = bh + nb * T::BH;
+                    if (b < S) {
+                        const double ay_ = rec[(T::F_AY + b) * CHP + pp], by_ = rec[(T::F_BY + b) * CHP + pp];
+                        const double az_ = rec[(T::F_AZ + b) * CHP + pp], bz_ = rec[(T::F_BZ + b) * CHP + pp];
+                        const double wx = sny * az_ + soy * bz_;
+                        const double wy = snx * az_ + sox * bz_;
+                        const double wz = snx * ay_ + sox * by_;
+#pragma unroll
+                        for (int i = 0; i < PN; ++i) {
+                            acc[nb][0][i] += cds[0][i] * wx;
+                            acc[nb][1][i] += cds[1][i] * wy;
+                            acc[nb][2][i] += cds[2][i] * wz;
+                        }
+                    }
+                }
+            }
+        }
+        flush(cur);
+        __syncwarp();
+    }
+}
+
+template <int N>
+static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom& dg, cudaStream_t s) {
+    constexpr int NWQ = 4, MINB = 4, NWG = 8;
+    using TQ = QuietCfg<N>;
+    using TG = GeneralCfg<N>;
+    for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < 3; ++c)
+            if (J[c].hi[d] - J[c].lo[d] + 2 > 1022) return fail("pic_deposit_esirkepov: J extent > 1020 points per rank");
+    KeyBase kb;
+    kb.b0 = min(J[0].lo[0], min(J[1].lo[0], J[2].lo[0])) - 1;
+    kb.b1 = min(J[0].lo[1], min(J[1].lo[1], J[2].lo[1])) - 1;
+    kb.b2 = min(J[0].lo[2], min(J[1].lo[2], J[2].lo[2])) - 1;
+    // list of particles that changed cell + its counter (stream-ordered scratch, freed after use)
+    int* scratch = nullptr;
+    if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(np + 1), s) != cudaSuccess)
+        return fail("pic_deposit_esirkepov: cannot allocate %ld B of scratch", (long)(sizeof(int) * (np + 1)));
+    int* list_count = scratch;
+    int* list = scratch + 1;
+    cudaMemsetAsync(list_count, 0, sizeof(int), s);
+    auto kq = deposit_quiet_kernel<N, NWQ, MINB>;
+    auto kg = deposit_general_kernel<N, NWG>;
+    const size_t smem_q = (size_t)NWQ * TQ::NF * DR_CHP * sizeof(double);
+    const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
+        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+        attr_done = true;
+    }
+    const long nchunks = (np + DR_CH - 1) / DR_CH;
+    const int cpw = 16;   // 512 consecutive particles per warp: long runs, few boundaries
+    const long nwarps = (nchunks + cpw - 1) / cpw;
+    const unsigned grid_q = (unsigned)((nwarps + NWQ - 1) / NWQ);
+    kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb, list, list_count);
+    kg<<<NUM_SMS, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
+    count_launch(2);
+    cudaFreeAsync(scratch, s);
+    return check_launch("pic_deposit_esirkepov(runs)") ? 0 : 1;
+}
+
+int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
+                        const DepositGeom& dg, int nox, cudaStream_t s) {
+    SoaView P = make_soa(*p, offset);
+    if (nox == 1) return launch_runs<1>(P, np, J, dg, s);
+    if (nox == 2) return launch_runs<2>(P, np, J, dg, s);
+    return launch_runs<3>(P, np, J, dg, s);
+}
+
+}  // namespace pic

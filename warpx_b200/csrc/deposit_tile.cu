@@ -21,8 +21,11 @@
 //           prefix entries, so 32/(N+1)^2 particles are processed per warp pass;
 //         * general particles: the full (N+3)^2 x (N+2) stencil, one particle per pass.
 //   At the end of a run the registers are added to the shared J block (smem CAS-add; the lanes of
-//   a warp hit distinct addresses); at the end of the CTA the block is added to global J with one
-//   pass of coalesced fp64 reductions (the halo overlaps neighbouring supercells).
+//   a warp hit distinct addresses, the per-component pitches of the block make them distinct banks).
+//   Cells are visited along x, so the quiet layout SLIDES instead of flushing: lines are owned by
+//   their absolute x (ring mapping), only the plane that leaves the window is retired
+//   (40 instead of 144 shared-memory updates per cell).  At the end of the CTA the block is added
+//   to global J with one pass of coalesced fp64 reductions (the halo overlaps neighbouring supercells).
 // Particles whose stencil does not fit the block (drifted since the last sort) take the
 // per-particle global-atomic path, so any particle order is CORRECT; sorted order is FAST.
 #include "pic_common.cuh"
@@ -133,21 +136,47 @@ __device__ __noinline__ void deposit_one_global(double xp, double yp, double zp,
         }
 }
 
+// Shared J block: component c is stored with its own row / plane pitch so that the (u, v) lanes
+// of the quiet layout fall into distinct 8-byte banks when they update one stencil plane.
+struct BlockGeom {
+    int bd[3];        // extent in points
+    int py[3], pz[3]; // pitches (doubles) of component c
+    int off[3];       // offset (doubles) of component c
+    int total;        // doubles
+};
+
+inline int round_up_residue(int v, int mod, int res) {   // smallest w >= v with w % mod == res
+    int w = v - (v % mod) + res;
+    return w >= v ? w : w + mod;
+}
+
+inline BlockGeom make_block_geom(const BinsView& bv) {
+    BlockGeom g;
+    for (int d = 0; d < 3; ++d) g.bd[d] = bv.tile[d] + DT_EXTRA;
+    // Jx lanes vary along (y, z): py = 1, pz = 4 (mod 16); Jy along (x, z): pz = 4; Jz along (x, y): py = 4
+    g.py[0] = round_up_residue(g.bd[0], 16, 1); g.pz[0] = round_up_residue(g.py[0] * g.bd[1], 16, 4);
+    g.py[1] = g.bd[0];                          g.pz[1] = round_up_residue(g.py[1] * g.bd[1], 16, 4);
+    g.py[2] = round_up_residue(g.bd[0], 16, 4); g.pz[2] = g.py[2] * g.bd[1];
+    int o = 0;
+    for (int c = 0; c < 3; ++c) { g.off[c] = o; o += g.pz[c] * g.bd[2]; }
+    g.total = o;
+    return g;
+}
+
 template <int N, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz, DepositGeom dg) {
+deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz, DepositGeom dg, BlockGeom bg) {
     using T = TileCfg<N>;
     constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF, CHP = DT_CHP;
     constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
-    const int BD0 = bins.tile[0] + DT_EXTRA, BD1 = bins.tile[1] + DT_EXTRA, BD2 = bins.tile[2] + DT_EXTRA;
-    const int bvol = BD0 * BD1 * BD2;
-    double* jblk = smem;                                  // [3][BD2][BD1][BD0]
-    double* recs = smem + 3 * bvol;                       // [NW][NF][CHP]
+    const int BD0 = bg.bd[0], BD1 = bg.bd[1], BD2 = bg.bd[2];
+    double* jblk = smem;                                  // 3 components, padded pitches (BlockGeom)
+    double* recs = smem + bg.total;                       // [NW][NF][CHP]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int n = tid; n < 3 * bvol; n += NW * 32) jblk[n] = 0.0;
+    for (int n = tid; n < bg.total; n += NW * 32) jblk[n] = 0.0;
 
     // supercell and its particle range
     const int t = blockIdx.x;
@@ -174,8 +203,11 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
     // general layout: lane (a, bh) owns lines (a, b), b = bh + nb*BH, of all three components
     const int a = lane % S, bh = lane / S;
     const bool active_g = lane < T::NLANES;
-    // quiet layout: lane (g, qa, qb): particle slot g of the pass, lines (1+qa, 1+qb)
-    const int g = lane / QL, ql = lane % QL, qa = ql % QS, qb = ql / QS;
+    // quiet layout: lane (g, u, v): particle slot g of the pass;
+    //   Jx line (j, k) = (1+u, 1+v);  Jy line (i, k) = (1+ur, 1+v);  Jz line (i, j) = (1+ur, 1+v)
+    // where ur = (u - (ax+1)) mod QS: a lane owns the Jy/Jz lines of a fixed ABSOLUTE x (ring
+    // mapping), so that moving the anchor by one cell along x keeps them in place.
+    const int g = lane / QL, ql = lane % QL, qu = ql % QS, qv = ql / QS;
     const bool active_q = g < NG;
 
     double accg[NB][3][PN];
@@ -192,64 +224,110 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
     int cur = -1;
     bool dirty_g = false, dirty_q = false;
 
-    auto flush = [&](int k) {
-        if (k < 0) return;
-        const int ax = k % BD0, ay = (k / BD0) % BD1, az = k / (BD0 * BD1);
-        if (dirty_q) {
-            // fold the particle slots of the pass into slot 0, then one CAS-add per owned entry
+    auto jaddr = [&](int c, int x, int y, int z) -> double* {
+        return jblk + bg.off[c] + x + bg.py[c] * y + bg.pz[c] * z;
+    };
+    auto ring = [&](int ax) -> int {               // relative x index of this lane's Jy/Jz lines
+        int r = (qu - (ax + 1)) % QS;
+        return r < 0 ? r + QS : r;
+    };
+    auto fold = [&](double v) -> double {          // sum over the particle slots of the pass
+        double r = v;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int i = 0; i < QP; ++i) {
-                    double v = accq[c][i];
-#pragma unroll
-                    for (int gg = 1; gg < NG; ++gg) {
-                        const double o = __shfl_down_sync(FULL, accq[c][i], gg * QL);
-                        if (lane + gg * QL < NG * QL) v += o;
-                    }
-                    if (lane < QL && v != 0.0) {
-                        const int e = 1 + i;   // prefix entry = slot 1 + i
-                        int ix, iy, iz;
-                        if (c == 0) { ix = ax + e; iy = ay + 1 + qa; iz = az + 1 + qb; }        // line (j, k)
-                        else if (c == 1) { ix = ax + 1 + qa; iy = ay + e; iz = az + 1 + qb; }   // line (i, k)
-                        else { ix = ax + 1 + qa; iy = ay + 1 + qb; iz = az + e; }               // line (i, j)
-                        atomicAdd(&jblk[c * bvol + ix + BD0 * (iy + BD1 * iz)], v);
-                    }
-                    accq[c][i] = 0.0;
-                }
-            dirty_q = false;
+        for (int gg = 1; gg < NG; ++gg) {
+            const double o = __shfl_down_sync(FULL, v, gg * QL);
+            if (lane + gg * QL < NG * QL) r += o;
         }
-        if (dirty_g) {
-            if (active_g) {
+        return r;
+    };
+    // keys pack the anchor as ax | ay << 8 | az << 16 (block extents are < 256)
+    auto flush_general = [&](int k) {
+        if (!dirty_g) return;
+        const int ax = k & 255, ay = (k >> 8) & 255, az = k >> 16;
+        if (active_g) {
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const int b = bh + nb * T::BH;
-                    if (b < S) {
+            for (int nb = 0; nb < NB; ++nb) {
+                const int b = bh + nb * T::BH;
+                if (b < S) {
 #pragma unroll
-                        for (int i = 0; i < PN; ++i) {
-                            const double vx = accg[nb][0][i], vy = accg[nb][1][i], vz = accg[nb][2][i];
-                            if (vx != 0.0) atomicAdd(&jblk[0 * bvol + (ax + i) + BD0 * ((ay + a) + BD1 * (az + b))], vx);
-                            if (vy != 0.0) atomicAdd(&jblk[1 * bvol + (ax + a) + BD0 * ((ay + i) + BD1 * (az + b))], vy);
-                            if (vz != 0.0) atomicAdd(&jblk[2 * bvol + (ax + a) + BD0 * ((ay + b) + BD1 * (az + i))], vz);
-                            accg[nb][0][i] = 0.0; accg[nb][1][i] = 0.0; accg[nb][2][i] = 0.0;
-                        }
+                    for (int i = 0; i < PN; ++i) {
+                        const double vx = accg[nb][0][i], vy = accg[nb][1][i], vz = accg[nb][2][i];
+                        if (vx != 0.0) atomicAdd(jaddr(0, ax + i, ay + a, az + b), vx);   // line (j=a, k=b)
+                        if (vy != 0.0) atomicAdd(jaddr(1, ax + a, ay + i, az + b), vy);   // line (i=a, k=b)
+                        if (vz != 0.0) atomicAdd(jaddr(2, ax + a, ay + b, az + i), vz);   // line (i=a, j=b)
+                        accg[nb][0][i] = 0.0; accg[nb][1][i] = 0.0; accg[nb][2][i] = 0.0;
                     }
                 }
             }
-            dirty_g = false;
+        }
+        dirty_g = false;
+    };
+    auto flush_quiet = [&](int k) {                // retire the whole quiet window
+        if (!dirty_q) return;
+        const int ax = k & 255, ay = (k >> 8) & 255, az = k >> 16;
+        const int ur = ring(ax);
+#pragma unroll
+        for (int i = 0; i < QP; ++i) {
+            const double vx = fold(accq[0][i]), vy = fold(accq[1][i]), vz = fold(accq[2][i]);
+            if (lane < QL) {
+                if (vx != 0.0) atomicAdd(jaddr(0, ax + 1 + i, ay + 1 + qu, az + 1 + qv), vx);
+                if (vy != 0.0) atomicAdd(jaddr(1, ax + 1 + ur, ay + 1 + i, az + 1 + qv), vy);
+                if (vz != 0.0) atomicAdd(jaddr(2, ax + 1 + ur, ay + 1 + qv, az + 1 + i), vz);
+            }
+            accq[0][i] = 0.0; accq[1][i] = 0.0; accq[2][i] = 0.0;
+        }
+        dirty_q = false;
+    };
+    auto slide_quiet = [&](int k) {                // anchor moves from k to k + 1 along x
+        if (!dirty_q) return;
+        const int ax = k & 255, ay = (k >> 8) & 255, az = k >> 16;
+        const bool leaving = ring(ax) == 0;        // this lane's Jy/Jz lines sit at x = ax + 1
+        // Jx: the plane x = ax + 1 (entry 0) leaves the window; the others shift down
+        {
+            const double vx = fold(accq[0][0]);
+            if (lane < QL && vx != 0.0) atomicAdd(jaddr(0, ax + 1, ay + 1 + qu, az + 1 + qv), vx);
+#pragma unroll
+            for (int i = 0; i + 1 < QP; ++i) accq[0][i] = accq[0][i + 1];
+            accq[0][QP - 1] = 0.0;
+        }
+        // Jy, Jz: the lines at x = ax + 1 leave; their lanes restart at zero for x = ax + 1 + QS
+#pragma unroll
+        for (int i = 0; i < QP; ++i) {
+            const double vy = fold(accq[1][i]), vz = fold(accq[2][i]);
+            if (lane < QL && leaving) {
+                if (vy != 0.0) atomicAdd(jaddr(1, ax + 1, ay + 1 + i, az + 1 + qv), vy);
+                if (vz != 0.0) atomicAdd(jaddr(2, ax + 1, ay + 1 + qv, az + 1 + i), vz);
+            }
+            if (leaving) { accq[1][i] = 0.0; accq[2][i] = 0.0; }
         }
     };
+    auto retire = [&](int k_old, int k_new) {      // anchor changes from k_old to k_new
+        if (k_old < 0) return;
+        flush_general(k_old);
+        if (k_new == k_old + 1 && (k_new & 255) + S <= BD0) slide_quiet(k_old);
+        else flush_quiet(k_old);
+    };
+
+    // software prefetch: the particle data of chunk ch+1 is requested before chunk ch is processed
+    double pf[7] = {0, 0, 0, 0, 0, 0, 0};
+    auto prefetch = [&](int ch) {
+        const int ip = p_begin + ch * DT_CH + lane;
+        if (ch < c_end && ip < p_end) {
+            pf[0] = P.x[ip]; pf[1] = P.y[ip]; pf[2] = P.z[ip]; pf[3] = P.w[ip];
+            pf[4] = P.ux[ip]; pf[5] = P.uy[ip]; pf[6] = P.uz[ip];
+        }
+    };
+    prefetch(c_begin);
 
     for (int ch = c_begin; ch < c_end; ++ch) {
         const int base = p_begin + ch * DT_CH;
         const int nval = min(DT_CH, p_end - base);
+        const double xp = pf[0], yp = pf[1], zp = pf[2], wp = pf[3], uxp = pf[4], uyp = pf[5], uzp = pf[6];
+        prefetch(ch + 1);
         // ---------------- phase 1: lane = particle ----------------
         int key = -2;
         bool quiet = false;
         if (lane < nval) {
-            const long ip = base + lane;
-            const double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip], wp = P.w[ip];
-            const double uxp = P.ux[ip], uyp = P.uy[ip], uzp = P.uz[ip];
             const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);
             const double wq = dg.q * wp;
             const double pos_new[3] = {(xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0],
@@ -266,7 +344,7 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
             const int ax = dg.lo[0] + inew[0] - 1 - o0, ay = dg.lo[1] + inew[1] - 1 - o1, az = dg.lo[2] + inew[2] - 1 - o2;
             const bool fits = ax >= 0 && ay >= 0 && az >= 0 && ax + S <= BD0 && ay + S <= BD1 && az + S <= BD2;
             if (fits) {
-                key = ax + BD0 * (ay + BD1 * az);
+                key = ax | (ay << 8) | (az << 16);
                 quiet = (sh[0] == 0) && (sh[1] == 0) && (sh[2] == 0);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
@@ -311,7 +389,7 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
                 const unsigned runm = ((end >= 32) ? FULL : ((1u << end) - 1u)) & ~((1u << start) - 1u);
                 const int k = __shfl_sync(FULL, key, start);
                 if (k < 0) continue;
-                if (k != cur) { flush(cur); cur = k; }
+                if (k != cur) { retire(cur, k); cur = k; }
                 unsigned mq = runm & quietm, mg = runm & ~quietm;
                 // ---- quiet particles: NG per pass ----
                 while (mq) {
@@ -323,13 +401,14 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
                         if (gg == g) pq = p;
                     }
                     if (active_q && pq >= 0) {
-                        const double snx = rec[(T::F_SNX + 1 + qa) * CHP + pq], sox = rec[(T::F_SOX + 1 + qa) * CHP + pq];
-                        const double sny = rec[(T::F_SNY + 1 + qa) * CHP + pq], soy = rec[(T::F_SOY + 1 + qa) * CHP + pq];
-                        const double ay_ = rec[(T::F_AY + 1 + qb) * CHP + pq], by_ = rec[(T::F_BY + 1 + qb) * CHP + pq];
-                        const double az_ = rec[(T::F_AZ + 1 + qb) * CHP + pq], bz_ = rec[(T::F_BZ + 1 + qb) * CHP + pq];
-                        const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+qa, 1+qb)
-                        const double wy = snx * az_ + sox * bz_;   // Jy line (i, k)
-                        const double wz = snx * ay_ + sox * by_;   // Jz line (i, j)
+                        const int ur = ring(k & 255);
+                        const double snx = rec[(T::F_SNX + 1 + ur) * CHP + pq], sox = rec[(T::F_SOX + 1 + ur) * CHP + pq];
+                        const double sny = rec[(T::F_SNY + 1 + qu) * CHP + pq], soy = rec[(T::F_SOY + 1 + qu) * CHP + pq];
+                        const double ay_ = rec[(T::F_AY + 1 + qv) * CHP + pq], by_ = rec[(T::F_BY + 1 + qv) * CHP + pq];
+                        const double az_ = rec[(T::F_AZ + 1 + qv) * CHP + pq], bz_ = rec[(T::F_BZ + 1 + qv) * CHP + pq];
+                        const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+u, 1+v)
+                        const double wy = snx * az_ + sox * bz_;   // Jy line (i, k) = (1+ur, 1+v)
+                        const double wz = snx * ay_ + sox * by_;   // Jz line (i, j) = (1+ur, 1+v)
 #pragma unroll
                         for (int i = 0; i < QP; ++i) {
                             accq[0][i] += rec[(T::F_CDS + 0 * PN + 1 + i) * CHP + pq] * wx;
@@ -375,19 +454,24 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
         }
         __syncwarp();
     }
-    flush(cur);
+    if (cur >= 0) { flush_general(cur); flush_quiet(cur); }
     __syncthreads();
 
     // ---------------- block -> global J (coalesced along i; halo overlaps neighbours) ----------
-    for (int n = tid; n < 3 * bvol; n += NW * 32) {
-        const double v = jblk[n];
-        if (v == 0.0) continue;
-        const int c = n / bvol, r = n - c * bvol;
-        const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
+    const int nrows = BD1 * BD2;
+    for (int c = 0; c < 3; ++c) {
         const FabView& J = (c == 0) ? Jx : ((c == 1) ? Jy : Jz);
-        const int gi = o0 + li, gj = o1 + lj, gk = o2 + lk;
-        if (gi >= J.lo0 && gi < J.lo0 + J.n0 && gj >= J.lo1 && gj < J.lo1 + J.n1 && gk >= J.lo2 && gk < J.lo2 + J.n2)
-            atomicAdd(&J(gi, gj, gk), v);
+        for (int row = warp; row < nrows; row += NW) {
+            const int lj = row % BD1, lk = row / BD1;
+            const int gj = o1 + lj, gk = o2 + lk;
+            if (gj < J.lo1 || gj >= J.lo1 + J.n1 || gk < J.lo2 || gk >= J.lo2 + J.n2) continue;
+            const double* src = jblk + bg.off[c] + bg.py[c] * lj + bg.pz[c] * lk;
+            for (int li = lane; li < BD0; li += 32) {
+                const double v = src[li];
+                const int gi = o0 + li;
+                if (v != 0.0 && gi >= J.lo0 && gi < J.lo0 + J.n0) atomicAdd(&J(gi, gj, gk), v);
+            }
+        }
     }
 }
 
@@ -395,8 +479,9 @@ template <int N, int NW>
 static int launch_tile(SoaView P, const BinsView& bv, const pic_fab J[3], const DepositGeom& dg,
                        cudaStream_t s) {
     using T = TileCfg<N>;
-    const long bvol = (long)(bv.tile[0] + DT_EXTRA) * (bv.tile[1] + DT_EXTRA) * (bv.tile[2] + DT_EXTRA);
-    const size_t smem = (size_t)(3 * bvol + (size_t)NW * T::NF * DT_CHP) * sizeof(double);
+    const BlockGeom bg = make_block_geom(bv);
+    if (bg.bd[0] > 255 || bg.bd[1] > 255 || bg.bd[2] > 255) return fail("pic_deposit_esirkepov: supercell too large");
+    const size_t smem = (size_t)(bg.total + (size_t)NW * T::NF * DT_CHP) * sizeof(double);
     auto kern = deposit_tile_kernel<N, NW>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -406,7 +491,7 @@ static int launch_tile(SoaView P, const BinsView& bv, const pic_fab J[3], const 
     }
     if (smem > 227 * 1024) return fail("pic_deposit_esirkepov: supercell too large for shared memory (%zu B)", smem);
     const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
-    kern<<<ntiles, NW * 32, smem, s>>>(P, bv, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg);
+    kern<<<ntiles, NW * 32, smem, s>>>(P, bv, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, bg);
     count_launch();
     return check_launch("pic_deposit_esirkepov(tile)") ? 0 : 1;
 }

@@ -58,9 +58,15 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     }
     __syncthreads();
 
-    for (int ip = p_begin + threadIdx.x; ip < p_end; ip += GT_THREADS) {
-        double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip];
-        double ux = P.ux[ip], uy = P.uy[ip], uz = P.uz[ip];
+    // software prefetch: the next particle of this thread is requested before the current one is
+    // gathered, so the HBM latency overlaps ~700 instructions of shared-memory gather + push
+    double nx = 0, ny = 0, nz = 0, nux = 0, nuy = 0, nuz = 0;
+    int ip = p_begin + threadIdx.x;
+    if (ip < p_end) { nx = P.x[ip]; ny = P.y[ip]; nz = P.z[ip]; nux = P.ux[ip]; nuy = P.uy[ip]; nuz = P.uz[ip]; }
+    for (; ip < p_end; ip += GT_THREADS) {
+        double xp = nx, yp = ny, zp = nz, ux = nux, uy = nuy, uz = nuz;
+        const int in = ip + GT_THREADS;
+        if (in < p_end) { nx = P.x[in]; ny = P.y[in]; nz = P.z[in]; nux = P.ux[in]; nuy = P.uy[in]; nuz = P.uz[in]; }
         // cell of the particle (global index) from the same coordinates the gather uses
         const int ci = gg.lo[0] + (int)((xp - gg.xyzmin[0]) * gg.dinv[0]);
         const int cj = gg.lo[1] + (int)((yp - gg.xyzmin[1]) * gg.dinv[1]);
