@@ -1,0 +1,110 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_check.py
+
+Config 1 (64^3 Langmuir, 40 steps) on a brick decomposition: WarpX's golden checksums at rtol 1e-9
+(what the reference's own 2-rank CI runs compare, Examples/CMakeLists.txt:98-104), particle-count
+conservation through migration, and an order-3 thermal run compared with the single-box oracle."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle  # noqa: E402  (test infrastructure: the checker)
+from warpx_b200 import abi, parallel, workloads  # noqa: E402
+from warpx_b200.engine import Simulation  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    ok = True
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "warpx_checksums.json")))["test_3d_langmuir_multi"]
+    L = oracle.lib()
+
+    # ---------------- config 1 on `world` GPUs ----------------
+    n = 64
+    nb = parallel.brick_grid(world)
+    dec = parallel.Decomposition((n, n, n), nb, rank)
+    full = workloads.langmuir_3d(n=n)
+    sim = Simulation(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=1, dist=dist, sort_interval=4)
+    dx = sim.dx[0]
+    for s in full["species"]:
+        cell = [np.floor((s[k] - full["prob_lo"][d]) / dx).astype(int) for d, k in enumerate("xyz")]
+        m = np.ones(len(s["x"]), dtype=bool)
+        for d in range(3):
+            m &= (cell[d] >= dec.box_lo[d]) & (cell[d] <= dec.box_hi[d])
+        sim.add_species(s["name"], s["q"], s["m"], *[s[k][m] for k in ("x", "y", "z", "w", "ux", "uy", "uz")])
+    ntot0 = sim.total_particles()
+    sim.Evolve(40)
+    torch.cuda.synchronize()
+    assert sim.total_particles() == ntot0 == 2 * n ** 3
+    sums = []
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        hf = oracle.HostFab(sim.box_lo, sim.box_hi, d.ng, abi.YEE_STAG[c], data=a)
+        sums.append(L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi)))
+    psum = []
+    for isp in range(2):
+        P = sim.species_numpy(isp)
+        psum += [np.sum(np.abs(P["x"])), np.sum(np.abs(P["y"])), np.sum(np.abs(P["z"])),
+                 np.sum(np.abs(P["ux"])) * workloads.M_E, np.sum(np.abs(P["uz"])) * workloads.M_E, np.sum(P["w"])]
+    t = torch.tensor(sums + psum, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)
+    v = t.cpu().numpy()
+    if rank == 0:
+        for c, name in enumerate(abi.COMP_NAMES):
+            g = golden["lev=0"][name]
+            good = abs(v[c] - g) <= 1e-9 * abs(g)
+            ok &= good
+            print(f"[langmuir x{world}] {name}: {v[c]:.15e} golden {g:.15e} {'ok' if good else 'FAIL'}")
+        keys = ["particle_position_x", "particle_position_y", "particle_position_z", "particle_momentum_x",
+                "particle_momentum_z", "particle_weight"]
+        for isp, sname in enumerate(("electrons", "positrons")):
+            for j, key in enumerate(keys):
+                if key in golden[sname]:
+                    g = golden[sname][key]
+                    good = abs(v[9 + 6 * isp + j] - g) <= 1e-9 * abs(g)
+                    ok &= good
+                    print(f"[langmuir x{world}] {sname}.{key}: {'ok' if good else 'FAIL'} ({v[9 + 6 * isp + j]:.15e} vs {g:.15e})")
+
+    # ---------------- order-3 thermal plasma with migration vs the single-box oracle ----------------
+    n3 = 32
+    wl = workloads.uniform_plasma_3d(n=n3, ppc=(2, 2, 2), u_th=0.05, lx=5e-6, perturbation=0.01)
+    dec3 = parallel.Decomposition((n3,) * 3, nb, rank)
+    mine = workloads.uniform_plasma_3d(n=n3, ppc=(2, 2, 2), u_th=0.05, lx=5e-6, perturbation=0.01,
+                                       box_lo=dec3.box_lo, box_hi=dec3.box_hi)
+    sim3 = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, dist=dist, sort_interval=4)
+    s = mine["species"][0]
+    sim3.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim3.Evolve(12)
+    e, b = sim3.field_energy()
+    npart = sim3.total_particles()
+    if rank == 0:
+        osim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3)
+        so = wl["species"][0]
+        osim.add_species(so["q"], so["m"], so["x"], so["y"], so["z"], so["w"], so["ux"], so["uy"], so["uz"])
+        osim.evolve(12)
+        eo, bo = osim.field_energy()
+        good = abs(e - eo) <= 1e-10 * eo and abs(b - bo) <= 1e-8 * bo and npart == len(so["x"])
+        ok &= good
+        print(f"[order3 x{world}] field energy E {e:.12e} vs oracle {eo:.12e}; B {b:.12e} vs {bo:.12e}; "
+              f"particles {npart}: {'ok' if good else 'FAIL'}")
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -367,7 +367,9 @@ def test_langmuir_loop_golden_and_oracle(orc, cuda, golden, use_bins):
         cs = L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
         assert abs(cs - g["lev=0"][name]) <= 1e-9 * abs(g["lev=0"][name]), name
         _, oa = osim.fab(c)
-        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= 1e-9, name
+        # B is at round-off level in this electrostatic mode (|B| c / |E| ~ 1e-5): looser bound
+        tol = 1e-9 if c not in (3, 4, 5) else 1e-7
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= tol, name
     for isp, sname in enumerate(("electrons", "positrons")):
         P = sim.species_numpy(isp)
         vals = {"particle_position_x": P["x"], "particle_position_y": P["y"], "particle_position_z": P["z"],
@@ -449,3 +451,17 @@ def test_full_size_properties(cuda):
     assert float(div.abs().max()) <= 1e-9 * scale
     e, b = sim.field_energy()
     assert np.isfinite(e) and np.isfinite(b) and e > 0
+
+
+def test_two_gpu_halo_and_migration(cuda):
+    """N > 1 on real GPUs (skipped on a single-GPU box): tests/multi_gpu_check.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
