@@ -278,8 +278,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per GPU and direction")
-    ap.add_argument("--cpu-n", type=int, default=48, help="cells per direction of the CPU sample")
+    ap.add_argument("--cells", dest="n", type=int, default=256, help="cells per GPU and direction")
+    ap.add_argument("--cpu-cells", dest="cpu_n", type=int, default=48, help="cells per direction of the CPU sample")
     ap.add_argument("--sort-interval", type=int, default=4)
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
     args = ap.parse_args()
