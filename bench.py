@@ -88,6 +88,7 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3):
     wl = workloads.uniform_plasma_3d(n=n, ppc=ppc, lx=lx)
     kind = "reference" if oracle.have_ref() else "restated"
     sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind)
+    sim.L.orc_set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
     s = wl["species"][0]
     sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
     npart = len(s["x"])

@@ -444,7 +444,18 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     kb.b0 = min(J[0].lo[0], min(J[1].lo[0], J[2].lo[0])) - 1;
     kb.b1 = min(J[0].lo[1], min(J[1].lo[1], J[2].lo[1])) - 1;
     kb.b2 = min(J[0].lo[2], min(J[1].lo[2], J[2].lo[2])) - 1;
-    // list of particles that changed cell + its counter (stream-ordered scratch, freed after use)
+    // list of particles that changed cell + its counter (stream-ordered scratch, freed after use).
+    // Keep the pool's memory across host synchronisations (default threshold 0 would unmap it).
+    static bool pool_done = false;
+    if (!pool_done) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_done = true;
+    }
     int* scratch = nullptr;
     if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(np + 1), s) != cudaSuccess)
         return fail("pic_deposit_esirkepov: cannot allocate %ld B of scratch", (long)(sizeof(int) * (np + 1)));

@@ -89,9 +89,6 @@ class _DeviceOps:
     def empty(self, n):
         return self.sim.torch.empty(n, dtype=self.sim.torch.float64, device=self.sim.device)
 
-    def sync(self):
-        self.sim.torch.cuda.current_stream().synchronize()
-
     def fill_local(self, fab, dim, ng):
         s = self.sim
         check(s.L.pic_fill_boundary_local(C.byref(fab), dim, ng, C.byref(s.geom), s.stream))
@@ -242,17 +239,18 @@ class Simulation:
 
     # ---- guard cells -------------------------------------------------------------------
     def FillBoundaryE(self, ng):
-        for c in range(0, 3):
-            self.halo.fill_boundary(self.fab[c], ng)
+        self.halo.fill_boundary(self.fab[0:3], ng)
 
     def FillBoundaryB(self, ng):
-        for c in range(3, 6):
-            self.halo.fill_boundary(self.fab[c], ng)
+        self.halo.fill_boundary(self.fab[3:6], ng)
+
+    def FillBoundaryEB(self, ng):
+        """FillBoundaryE + FillBoundaryB with the same ng in one exchange per direction."""
+        self.halo.fill_boundary(self.fab[0:6], ng)
 
     def SyncCurrent(self):
         """SumBoundaryJ: src = ng_depos_J (no filter), all guards of J updated afterwards."""
-        for c in range(6, 9):
-            self.halo.sum_boundary(self.fab[c], self.ng_depos_J, self.ng_J)
+        self.halo.sum_boundary(self.fab[6:9], self.ng_depos_J, self.ng_J)
 
     # ---- field solver ------------------------------------------------------------------
     def EvolveB(self, dt):
@@ -364,11 +362,11 @@ class Simulation:
     # ---- the step ----------------------------------------------------------------------
     def ExplicitFillBoundaryEBUpdateAux(self):
         if self.is_synchronized:
-            self.FillBoundaryE(self.ng_EB); self.FillBoundaryB(self.ng_EB)      # ng_alloc_EB, :487-488
+            self.FillBoundaryEB(self.ng_EB)                                      # ng_alloc_EB, :487-488
             self.PushP(-0.5 * self.dt)                                           # :492-504
             self.is_synchronized = False
         else:
-            self.FillBoundaryE(self.ng_FG); self.FillBoundaryB(self.ng_FG)      # :515-516
+            self.FillBoundaryEB(self.ng_FG)                                      # :515-516
 
     def OneStep_nosub(self):
         self.PushParticlesandDeposit()
@@ -380,7 +378,7 @@ class Simulation:
         self.EvolveB(0.5 * self.dt)
 
     def Synchronize(self):
-        self.FillBoundaryE(self.ng_FG); self.FillBoundaryB(self.ng_FG)
+        self.FillBoundaryEB(self.ng_FG)
         self.PushP(0.5 * self.dt)
         self.is_synchronized = True
 

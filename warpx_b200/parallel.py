@@ -100,37 +100,49 @@ class HaloExchanger:
             self._bufs[key] = b
         return b[:n]
 
-    def _sweep(self, fab, dim, ng, mode):
+    def _sweep(self, fabs, dim, ng, mode):
         if ng == 0 and mode == 0:
             return
         if self.dec.spans(dim):
-            if mode == 0:
-                self.ops.fill_local(fab, dim, ng)
-            else:
-                self.ops.sum_local(fab, dim, ng)
+            for fab in fabs:
+                if mode == 0:
+                    self.ops.fill_local(fab, dim, ng)
+                else:
+                    self.ops.sum_local(fab, dim, ng)
             return
-        n = self.ops.slab_count(fab, dim, ng, mode)
+        # one message per direction carries the slabs of ALL components (fewer, larger NCCL calls);
+        # pack -> send/recv -> unpack are ordered by the stream, no host synchronisation
+        counts = [self.ops.slab_count(fab, dim, ng, mode) for fab in fabs]
+        n = sum(counts)
         s_lo, s_hi = self._buf(("s", 0), n), self._buf(("s", 1), n)
         r_lo, r_hi = self._buf(("r", 0), n), self._buf(("r", 1), n)
-        self.ops.pack(fab, dim, 0, ng, mode, s_lo)
-        self.ops.pack(fab, dim, 1, ng, mode, s_hi)
-        self.ops.sync()
+        o = 0
+        for fab, c in zip(fabs, counts):
+            self.ops.pack(fab, dim, 0, ng, mode, s_lo[o:o + c])
+            self.ops.pack(fab, dim, 1, ng, mode, s_hi[o:o + c])
+            o += c
         exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
-        self.ops.unpack(fab, dim, 0, ng, mode, r_lo)
-        self.ops.unpack(fab, dim, 1, ng, mode, r_hi)
+        o = 0
+        for fab, c in zip(fabs, counts):
+            self.ops.unpack(fab, dim, 0, ng, mode, r_lo[o:o + c])
+            self.ops.unpack(fab, dim, 1, ng, mode, r_hi[o:o + c])
+            o += c
 
-    def fill_boundary(self, fab, ng):
-        """FillBoundary(ng): guards <- valid points of the periodic image / neighbour."""
+    def fill_boundary(self, fabs, ng):
+        """FillBoundary(ng) of a list of components: guards <- valid points of the periodic image /
+        neighbour.  Axis sweeps x, y, z; every slab spans the full extent of the other axes."""
+        fabs = fabs if isinstance(fabs, (list, tuple)) else [fabs]
         for dim in range(3):
-            self._sweep(fab, dim, int(ng[dim]), 0)
+            self._sweep(fabs, dim, int(ng[dim]), 0)
 
-    def sum_boundary(self, fab, src_ng, dst_ng):
+    def sum_boundary(self, fabs, src_ng, dst_ng):
         """SumBoundary(src_ng, dst_ng): fold guards (and shared nodes) into valid points, then
         refresh dst_ng guards with the sums (WarpXSumGuardCells.cpp:22-23 updates all guards)."""
+        fabs = fabs if isinstance(fabs, (list, tuple)) else [fabs]
         for dim in range(3):
-            self._sweep(fab, dim, int(src_ng[dim]), 1)
+            self._sweep(fabs, dim, int(src_ng[dim]), 1)
         if max(dst_ng) > 0:
-            self.fill_boundary(fab, dst_ng)
+            self.fill_boundary(fabs, dst_ng)
 
 
 def particle_destinations(cell, dec, dim):
