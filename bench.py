@@ -88,7 +88,14 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3):
     wl = workloads.uniform_plasma_3d(n=n, ppc=ppc, lx=lx)
     kind = "reference" if oracle.have_ref() else "restated"
     sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind)
-    sim.L.orc_set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; cgroup-limited boxes
+    # report more logical CPUs than they grant)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    env = os.environ.get("PIC_CPU_THREADS")
+    sim.L.orc_set_num_threads(int(env) if env else ncores)
     s = wl["species"][0]
     sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
     npart = len(s["x"])
@@ -280,7 +287,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cells", dest="n", type=int, default=256, help="cells per GPU and direction")
-    ap.add_argument("--cpu-cells", dest="cpu_n", type=int, default=48, help="cells per direction of the CPU sample")
+    ap.add_argument("--cpu-cells", dest="cpu_n", type=int, default=64, help="cells per direction of the CPU sample")
     ap.add_argument("--sort-interval", type=int, default=4)
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
     args = ap.parse_args()
