@@ -256,35 +256,29 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
                 const int start = __ffs(heads) - 1;
                 heads &= heads - 1;
                 const int end = heads ? (__ffs(heads) - 1) : nval;
-                unsigned mq = ((end >= 32) ? FULL : ((1u << end) - 1u)) & ~((1u << start) - 1u);
                 const int k = __shfl_sync(FULL, key, start);
                 if (k < 0) continue;
                 if (k != cur) { retire(cur, k); cur = k; }
                 const int ur = ring(k & 1023);
-                while (mq) {
-                    int pq = -1;
+                auto accumulate = [&](int pq) {
+                    const double snx = rec[(T::F_SNX + ur) * CHP + pq], sox = rec[(T::F_SOX + ur) * CHP + pq];
+                    const double sny = rec[(T::F_SNY + qu) * CHP + pq], soy = rec[(T::F_SOY + qu) * CHP + pq];
+                    const double ay_ = rec[(T::F_AY + qv) * CHP + pq], by_ = rec[(T::F_BY + qv) * CHP + pq];
+                    const double az_ = rec[(T::F_AZ + qv) * CHP + pq], bz_ = rec[(T::F_BZ + qv) * CHP + pq];
+                    const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+u, 1+v)
+                    const double wy = snx * az_ + sox * bz_;   // Jy line (i, k) = (1+ur, 1+v)
+                    const double wz = snx * ay_ + sox * by_;   // Jz line (i, j) = (1+ur, 1+v)
 #pragma unroll
-                    for (int gg = 0; gg < NG; ++gg) {
-                        const int p = mq ? (__ffs(mq) - 1) : -1;
-                        if (mq) mq &= mq - 1;
-                        if (gg == g) pq = p;
+                    for (int i = 0; i < QP; ++i) {
+                        acc[0][i] += rec[(T::F_CDS + 0 * QP + i) * CHP + pq] * wx;
+                        acc[1][i] += rec[(T::F_CDS + 1 * QP + i) * CHP + pq] * wy;
+                        acc[2][i] += rec[(T::F_CDS + 2 * QP + i) * CHP + pq] * wz;
                     }
-                    if (active_q && pq >= 0) {
-                        const double snx = rec[(T::F_SNX + ur) * CHP + pq], sox = rec[(T::F_SOX + ur) * CHP + pq];
-                        const double sny = rec[(T::F_SNY + qu) * CHP + pq], soy = rec[(T::F_SOY + qu) * CHP + pq];
-                        const double ay_ = rec[(T::F_AY + qv) * CHP + pq], by_ = rec[(T::F_BY + qv) * CHP + pq];
-                        const double az_ = rec[(T::F_AZ + qv) * CHP + pq], bz_ = rec[(T::F_BZ + qv) * CHP + pq];
-                        const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+u, 1+v)
-                        const double wy = snx * az_ + sox * bz_;   // Jy line (i, k) = (1+ur, 1+v)
-                        const double wz = snx * ay_ + sox * by_;   // Jz line (i, j) = (1+ur, 1+v)
-#pragma unroll
-                        for (int i = 0; i < QP; ++i) {
-                            acc[0][i] += rec[(T::F_CDS + 0 * QP + i) * CHP + pq] * wx;
-                            acc[1][i] += rec[(T::F_CDS + 1 * QP + i) * CHP + pq] * wy;
-                            acc[2][i] += rec[(T::F_CDS + 2 * QP + i) * CHP + pq] * wz;
-                        }
-                    }
-                }
+                };
+                // the run [start, end) is contiguous (moved particles have their own key): slot g of
+                // the pass takes particles start+g, start+g+NG, ...
+                if (active_q)
+                    for (int pq = start + g; pq < end; pq += NG) accumulate(pq);
             }
         }
         __syncwarp();

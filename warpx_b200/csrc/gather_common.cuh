@@ -33,9 +33,17 @@ struct DirWeights {
 };
 
 // Field access policies -----------------------------------------------------------------------
+// A field policy hands out, per component, an accessor positioned at the first stencil point;
+// the accessor is then indexed with the (compile-time) stencil offsets.
 struct GlobalFields {
     FabView v[6];
-    __device__ __forceinline__ double get(int c, int i, int j, int k) const { return v[c].ld(i, j, k); }
+    struct Acc {
+        const double* __restrict__ b; long sj, sk;
+        __device__ __forceinline__ double operator()(int ix, int iy, int iz) const { return __ldg(b + ix + iy * sj + iz * sk); }
+    };
+    __device__ __forceinline__ Acc at(int c, int i0, int j0, int k0) const {
+        return Acc{v[c].p + v[c].off(i0, j0, k0), v[c].sj, v[c].sk};
+    }
 };
 
 // Gathers the six components at one particle.  Accumulation order as the reference:
@@ -63,7 +71,7 @@ __device__ __forceinline__ void gather_fields(const Fields& fld, const GatherGeo
         const int ty = (ly ? 2 : 0) + ((YEE ? yee_stag(c, 1) : gg.stag[c][1]) ? 0 : 1);
         const int tz = (lz ? 2 : 0) + ((YEE ? yee_stag(c, 2) : gg.stag[c][2]) ? 0 : 1);
         const int nx = lx ? M : N, ny = ly ? M : N, nz = lz ? M : N;
-        const int ix0 = gg.lo[0] + wx.j0[tx], iy0 = gg.lo[1] + wy.j0[ty], iz0 = gg.lo[2] + wz.j0[tz];
+        const auto F3 = fld.at(c, gg.lo[0] + wx.j0[tx], gg.lo[1] + wy.j0[ty], gg.lo[2] + wz.j0[tz]);
         // separable contraction: sum_z sz ( sum_y sy ( sum_x sx F ) ) -- (n+1)^2 + (n+1) + 1 fewer
         // multiplies than the reference's sx*sy*sz*F form, identical up to rounding (1e-16 relative)
         double acc = 0.0;
@@ -78,7 +86,7 @@ __device__ __forceinline__ void gather_fields(const Fields& fld, const GatherGeo
 #pragma unroll
                 for (int ix = 0; ix <= N; ++ix) {
                     if (ix > nx) break;
-                    accx += wx.s[tx][ix] * fld.get(c, ix0 + ix, iy0 + iy, iz0 + iz);
+                    accx += wx.s[tx][ix] * F3(ix, iy, iz);
                 }
                 accy += wy.s[ty][iy] * accx;
             }

@@ -16,21 +16,42 @@ namespace pic {
 constexpr int GT_HALO = 2;
 constexpr int GT_THREADS = 256;
 
+// Shared-memory block of the six components.  BD* > 0: compile-time extents (the 8x8x8 supercell:
+// every stencil offset becomes an immediate of the LDS); BD0 == 0: run-time extents.
+template <int BD0, int BD1, int BD2>
 struct SmemFields {
     const double* blk;     // [6][BD2][BD1][BD0]
     int o0, o1, o2;        // global index of block element (0,0,0)
-    int BD0, BD1, bvol;
-    __device__ __forceinline__ double get(int c, int i, int j, int k) const {
-        return blk[c * bvol + (i - o0) + BD0 * ((j - o1) + BD1 * (k - o2))];
+    int rb0, rb01, rbvol;  // run-time extents (generic instance only)
+    struct Acc {
+        const double* b; int s1, s2;
+        __device__ __forceinline__ double operator()(int ix, int iy, int iz) const {
+            if constexpr (BD0 > 0) return b[ix + BD0 * iy + BD0 * BD1 * iz];
+            else return b[ix + s1 * iy + s2 * iz];
+        }
+    };
+    __device__ __forceinline__ Acc at(int c, int i0, int j0, int k0) const {
+        if constexpr (BD0 > 0)
+            return Acc{blk + c * (BD0 * BD1 * BD2) + (i0 - o0) + BD0 * ((j0 - o1) + BD1 * (k0 - o2)), 0, 0};
+        else
+            return Acc{blk + c * rbvol + (i0 - o0) + rb0 * ((j0 - o1) + rb01 / rb0 * (k0 - o2)), rb0, rb01};
     }
 };
 
-template <int N, int G, bool YEE>
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
+template <int N, int G, bool YEE, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
                         double dt, int pusher, int push_position) {
     extern __shared__ double smem[];
-    const int BD0 = bins.tile[0] + 2 * GT_HALO, BD1 = bins.tile[1] + 2 * GT_HALO, BD2 = bins.tile[2] + 2 * GT_HALO;
+    constexpr bool FIXED = TX > 0;
+    const int BD0 = FIXED ? TX + 2 * GT_HALO : bins.tile[0] + 2 * GT_HALO;
+    const int BD1 = FIXED ? TY + 2 * GT_HALO : bins.tile[1] + 2 * GT_HALO;
+    const int BD2 = FIXED ? TZ + 2 * GT_HALO : bins.tile[2] + 2 * GT_HALO;
     const int bvol = BD0 * BD1 * BD2;
     const int t = blockIdx.x;
     int tc[3];
@@ -42,11 +63,12 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     const int t0 = bins.box_lo[0] + tc[0] * bins.tile[0];
     const int t1 = bins.box_lo[1] + tc[1] * bins.tile[1];
     const int t2 = bins.box_lo[2] + tc[2] * bins.tile[2];
-    SmemFields sf;
+    SmemFields<FIXED ? TX + 2 * GT_HALO : 0, FIXED ? TY + 2 * GT_HALO : 0, FIXED ? TZ + 2 * GT_HALO : 0> sf;
     sf.blk = smem; sf.o0 = t0 - GT_HALO; sf.o1 = t1 - GT_HALO; sf.o2 = t2 - GT_HALO;
-    sf.BD0 = BD0; sf.BD1 = BD1; sf.bvol = bvol;
+    sf.rb0 = BD0; sf.rb01 = BD0 * BD1; sf.rbvol = bvol;
 
-    // ---- stage the six sub-blocks (rows of BD0 consecutive doubles) ----
+    // ---- stage the six sub-blocks with asynchronous 8-byte copies (LDGSTS): all ~40 copies of a
+    //      thread are in flight at once, no register staging ----
     for (int n = threadIdx.x; n < 6 * bvol; n += GT_THREADS) {
         const int c = n / bvol, r = n - c * bvol;
         const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
@@ -54,15 +76,19 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
         const int gi = sf.o0 + li, gj = sf.o1 + lj, gk = sf.o2 + lk;
         const bool in = gi >= F.lo0 && gi < F.lo0 + F.n0 && gj >= F.lo1 && gj < F.lo1 + F.n1 &&
                         gk >= F.lo2 && gk < F.lo2 + F.n2;
-        smem[n] = in ? F.ld(gi, gj, gk) : 0.0;
+        if (in) cp_async8(smem + n, F.p + F.off(gi, gj, gk));
+        else smem[n] = 0.0;
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     // software prefetch: the next particle of this thread is requested before the current one is
     // gathered, so the HBM latency overlaps ~700 instructions of shared-memory gather + push
     double nx = 0, ny = 0, nz = 0, nux = 0, nuy = 0, nuz = 0;
     int ip = p_begin + threadIdx.x;
     if (ip < p_end) { nx = P.x[ip]; ny = P.y[ip]; nz = P.z[ip]; nux = P.ux[ip]; nuy = P.uy[ip]; nuz = P.uz[ip]; }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
     for (; ip < p_end; ip += GT_THREADS) {
         double xp = nx, yp = ny, zp = nz, ux = nux, uy = nuy, uz = nuz;
         const int in = ip + GT_THREADS;
@@ -89,15 +115,15 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
     const size_t smem = (size_t)6 * bvol * sizeof(double);
     if (smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
     const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
-    if (yee) {
-        auto k = gather_push_tile_kernel<N, G, true>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position);
-    } else {
-        auto k = gather_push_tile_kernel<N, G, false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position);
-    }
+    const bool t888 = bv.tile[0] == 8 && bv.tile[1] == 8 && bv.tile[2] == 8;
+#define PIC_LAUNCH(YEE_, TX_, TY_, TZ_) do { \
+        auto k = gather_push_tile_kernel<N, G, YEE_, TX_, TY_, TZ_>; \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position); } while (0)
+    if (yee && t888) PIC_LAUNCH(true, 8, 8, 8);       // the tuned instance: immediate LDS offsets
+    else if (yee) PIC_LAUNCH(true, 0, 0, 0);
+    else PIC_LAUNCH(false, 0, 0, 0);
+#undef PIC_LAUNCH
     count_launch();
     return check_launch("pic_gather_push(tile)") ? 0 : 1;
 }

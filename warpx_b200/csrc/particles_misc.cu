@@ -26,9 +26,10 @@ __device__ __forceinline__ double wrap1(double v, double lo, double hi, double l
 __global__ void wrap_kernel(SoaView P, long np, WrapGeom g) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= np) return;
-    if (g.periodic[0]) P.x[ip] = wrap1(P.x[ip], g.lo[0], g.hi[0], g.len[0]);
-    if (g.periodic[1]) P.y[ip] = wrap1(P.y[ip], g.lo[1], g.hi[1], g.len[1]);
-    if (g.periodic[2]) P.z[ip] = wrap1(P.z[ip], g.lo[2], g.hi[2], g.len[2]);
+    // only particles outside the domain are rewritten (the others cost a read, not a read+write)
+    if (g.periodic[0]) { const double v = P.x[ip], w = wrap1(v, g.lo[0], g.hi[0], g.len[0]); if (w != v) P.x[ip] = w; }
+    if (g.periodic[1]) { const double v = P.y[ip], w = wrap1(v, g.lo[1], g.hi[1], g.len[1]); if (w != v) P.y[ip] = w; }
+    if (g.periodic[2]) { const double v = P.z[ip], w = wrap1(v, g.lo[2], g.hi[2], g.len[2]); if (w != v) P.z[ip] = w; }
 }
 
 struct SortGeom { double plo[3], dinv[3]; };
