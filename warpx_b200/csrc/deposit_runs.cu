@@ -98,6 +98,9 @@ template <int N> struct QuietCfg {
     static constexpr int F_AY = 4 * QS, F_BY = 5 * QS, F_AZ = 6 * QS, F_BZ = 7 * QS;
     static constexpr int F_CDS = 8 * QS;      // + comp*QP + i
     static constexpr int NF = 8 * QS + 3 * QP;
+    // record pitch (doubles): a pass reads rows r < QS of a field family at NG consecutive columns;
+    // with pitch = NG (mod 16) the 8-byte words pitch*r + c fall into distinct banks
+    static constexpr int CHP = DR_CH + NG;
 };
 
 template <int N, int NW, int MINB>
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabView Jy, FabView Jz,
                      DepositGeom dg, KeyBase kb, int* __restrict__ list, int* __restrict__ list_count) {
     using T = QuietCfg<N>;
-    constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = DR_CHP;
+    constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = T::CHP;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* rec = smem + (size_t)warp * NF * CHP;
@@ -141,42 +144,42 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
         }
         return r;
     };
-    // retire everything (anchor jumps) or only the plane x = ax+1 (anchor advances by one along x)
-    auto retire = [&](int k_old, int k_new) {
-        if (k_old < 0) return;
-        const int ax = (k_old & 1023), gx = ax + kb.b0, gy = ((k_old >> 10) & 1023) + kb.b1, gz = (k_old >> 20) + kb.b2;
-        const int ur = ring(ax);
-        const bool slide = (k_new == k_old + 1);
+    // Running state of the current anchor: this lane's ring index and the J addresses of its lines
+    //   px -> Jx(gx+1, gy+1+u, gz+1+v) (entries along x: +i), py -> Jy(gx+1+ur, gy+1, gz+1+v) (+i*sj),
+    //   pz -> Jz(gx+1+ur, gy+1+v, gz+1) (+i*sk)
+    int ur = 0;
+    double *px = nullptr, *py = nullptr, *pz = nullptr;
+    auto set_anchor = [&](int k) {
+        const int ax = (k & 1023), gx = ax + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
+        ur = ring(ax);
+        px = &Jx(gx + 1, gy + 1 + qu, gz + 1 + qv);
+        py = &Jy(gx + 1 + ur, gy + 1, gz + 1 + qv);
+        pz = &Jz(gx + 1 + ur, gy + 1 + qv, gz + 1);
+    };
+    // the anchor advances one cell along x: only the plane x = gx+1 leaves the window
+    auto slide = [&]() {
         const bool leaving = (ur == 0);
-        double* px = &Jx(gx + 1, gy + 1 + qu, gz + 1 + qv);          // entries along x: + i
-        double* py = &Jy(gx + 1 + ur, gy + 1, gz + 1 + qv);          // entries along y: + i * sj
-        double* pz = &Jz(gx + 1 + ur, gy + 1 + qv, gz + 1);          // entries along z: + i * sk
-        if (slide) {
-            const double vx = fold(acc[0][0]);
-            if (lane < QL && vx != 0.0) atomicAdd(px, vx);
+        const double vx = fold(acc[0][0]);
+        if (lane < QL) atomicAdd(px, vx);
 #pragma unroll
-            for (int i = 0; i + 1 < QP; ++i) acc[0][i] = acc[0][i + 1];
-            acc[0][QP - 1] = 0.0;
+        for (int i = 0; i + 1 < QP; ++i) acc[0][i] = acc[0][i + 1];
+        acc[0][QP - 1] = 0.0;
 #pragma unroll
-            for (int i = 0; i < QP; ++i) {
-                const double vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-                if (lane < QL && leaving) {
-                    if (vy != 0.0) atomicAdd(py + i * Jy.sj, vy);
-                    if (vz != 0.0) atomicAdd(pz + i * Jz.sk, vz);
-                }
-                if (leaving) { acc[1][i] = 0.0; acc[2][i] = 0.0; }
-            }
-        } else {
+        for (int i = 0; i < QP; ++i) {
+            const double vy = fold(acc[1][i]), vz = fold(acc[2][i]);
+            if (lane < QL && leaving) { atomicAdd(py + i * Jy.sj, vy); atomicAdd(pz + i * Jz.sk, vz); }
+            if (leaving) { acc[1][i] = 0.0; acc[2][i] = 0.0; }
+        }
+        px += 1;                                    // next x plane
+        if (leaving) { py += QS; pz += QS; ur = QS - 1; }   // this lane now owns x = gx + 1 + QS
+        else ur -= 1;                               // same absolute x, one slot lower
+    };
+    auto flush_all = [&]() {                        // the anchor jumps: retire the whole window
 #pragma unroll
-            for (int i = 0; i < QP; ++i) {
-                const double vx = fold(acc[0][i]), vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-                if (lane < QL) {
-                    if (vx != 0.0) atomicAdd(px + i, vx);
-                    if (vy != 0.0) atomicAdd(py + i * Jy.sj, vy);
-                    if (vz != 0.0) atomicAdd(pz + i * Jz.sk, vz);
-                }
-                acc[0][i] = 0.0; acc[1][i] = 0.0; acc[2][i] = 0.0;
-            }
+        for (int i = 0; i < QP; ++i) {
+            const double vx = fold(acc[0][i]), vy = fold(acc[1][i]), vz = fold(acc[2][i]);
+            if (lane < QL) { atomicAdd(px + i, vx); atomicAdd(py + i * Jy.sj, vy); atomicAdd(pz + i * Jz.sk, vz); }
+            acc[0][i] = 0.0; acc[1][i] = 0.0; acc[2][i] = 0.0;
         }
     };
 
@@ -258,8 +261,11 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
                 const int end = heads ? (__ffs(heads) - 1) : nval;
                 const int k = __shfl_sync(FULL, key, start);
                 if (k < 0) continue;
-                if (k != cur) { retire(cur, k); cur = k; }
-                const int ur = ring(k & 1023);
+                if (k != cur) {
+                    if (cur >= 0 && k == cur + 1) slide();
+                    else { if (cur >= 0) flush_all(); set_anchor(k); }
+                    cur = k;
+                }
                 auto accumulate = [&](int pq) {
                     const double snx = rec[(T::F_SNX + ur) * CHP + pq], sox = rec[(T::F_SOX + ur) * CHP + pq];
                     const double sny = rec[(T::F_SNY + qu) * CHP + pq], soy = rec[(T::F_SOY + qu) * CHP + pq];
@@ -283,7 +289,7 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
         }
         __syncwarp();
     }
-    retire(cur, -1);
+    if (cur >= 0) flush_all();
 }
 
 // ================================================================================================
@@ -458,7 +464,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     cudaMemsetAsync(list_count, 0, sizeof(int), s);
     auto kq = deposit_quiet_kernel<N, NWQ, MINB>;
     auto kg = deposit_general_kernel<N, NWG>;
-    const size_t smem_q = (size_t)NWQ * TQ::NF * DR_CHP * sizeof(double);
+    const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
