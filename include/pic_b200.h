@@ -79,6 +79,8 @@ typedef struct pic_bins {
     int box_lo[3];          /* first cell of the box                           */
     int box_hi[3];          /* last cell of the box, inclusive                 */
     int tile[3];            /* supercell size in cells (8,8,8 is what the kernels are tuned for) */
+    long np_binned;         /* particles [0, np_binned) are covered by cell_start; particles appended
+                               later (neighbour migration) are processed order-agnostically     */
 } pic_bins;
 
 /* Domain description for the periodic / neighbour guard-cell operations
@@ -179,6 +181,16 @@ int pic_halo_unpack(const pic_fab* f, int dim, int side, int ng, int mode, const
  * (WarpXEvolve.cpp:550-559 -> MultiParticleContainer.cpp:650-656; AMReX 24.10 @62c2a81
  * AMReX_ParticleUtil.H, un-vendored dependency). */
 int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* stream);
+
+/* Neighbour migration, step 1 (replaces the locate/partition phase of AMReX
+ * ParticleContainer::Redistribute, WarpXEvolve.cpp:550-559): indices of the particles whose cell
+ * along `dim` lies below cell_lo (-> idx_lo) or above cell_hi (-> idx_hi) after the periodic wrap.
+ * With `both_up` (two ranks along dim: both neighbours are the same rank) everything goes to
+ * idx_hi.  counts[0], counts[1] (device ints, zeroed here) receive the list lengths; lists hold at
+ * most `capacity` entries each (counts keep counting: the caller checks for overflow). */
+int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
+                           int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
+                           void* stream);
 
 /* Counting sort of the particles by cell over the valid box [box_lo,box_hi]
  * (WarpX: mypc->SortParticlesByBin, WarpXEvolve.cpp:575-580).  `in` is permuted into `out`;

@@ -124,6 +124,7 @@ def _sorted_device_species(dev, sp_host, n, prob_lo, prob_hi, tile=(8, 8, 8)):
     cell_start = t.empty(nb + 1, dtype=t.int32, device="cuda")
     work = t.empty(dev.L.pic_sort_workspace_bytes(P_in.np, nb), dtype=t.uint8, device="cuda")
     bins.cell_start = cell_start.data_ptr()
+    bins.np_binned = P_in.np
     geom = abi.make_geom(n, prob_lo, prob_hi)
     dev.ok(dev.L.pic_sort_particles_by_cell(C.byref(P_in), C.byref(P_out), C.byref(geom), C.byref(bins),
                                             work.data_ptr(), dev.stream))

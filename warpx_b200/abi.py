@@ -37,7 +37,7 @@ class pic_stencil(C.Structure):
 
 class pic_bins(C.Structure):
     _fields_ = [("cell_start", C.c_void_p), ("box_lo", C.c_int * 3), ("box_hi", C.c_int * 3),
-                ("tile", C.c_int * 3)]
+                ("tile", C.c_int * 3), ("np_binned", C.c_long)]
 
 
 class pic_geom(C.Structure):

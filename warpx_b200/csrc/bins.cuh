@@ -11,6 +11,7 @@ struct BinsView {
     int n[3];      // cells of the box
     int tile[3];
     int nt[3];     // supercells per direction (padded)
+    int np_limit;  // particles beyond this index are not covered by the bins
 };
 
 inline BinsView make_bins(const pic_bins& b) {
@@ -22,6 +23,7 @@ inline BinsView make_bins(const pic_bins& b) {
         v.tile[d] = b.tile[d];
         v.nt[d] = (v.n[d] + b.tile[d] - 1) / b.tile[d];
     }
+    v.np_limit = (int)b.np_binned;
     return v;
 }
 inline long bins_count(const BinsView& v) {

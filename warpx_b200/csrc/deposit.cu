@@ -97,8 +97,11 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
         // cell-sorted particles: warp-segmented register reduction (deposit_runs.cu).  The
         // shared-memory-block variant (deposit_tile.cu) is kept for comparison: pic_set_deposit_mode().
         PIC_REQUIRE(np < (1L << 31), "pic_deposit_esirkepov: more than 2^31 particles in one tile");
-        if (g_deposit_mode == PIC_DEPOSIT_TILE) return deposit_tile_launch(p, offset, np, J, dg, nox, bins, s);
-        return deposit_runs_launch(p, offset, np, J, dg, nox, s);
+        if (g_deposit_mode != PIC_DEPOSIT_TILE) return deposit_runs_launch(p, offset, np, J, dg, nox, s);
+        if (int rc = deposit_tile_launch(p, offset, np, J, dg, nox, bins, s)) return rc;
+        if (bins->np_binned >= np) return 0;
+        offset = bins->np_binned;           // particles appended after the last sort
+        np -= bins->np_binned;
     }
     SoaView P = make_soa(*p, offset);
     const int tpb = 128;

@@ -183,8 +183,8 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
     int tc[3];
     tile_coords(bins, t, tc);
     const long tvol = (long)bins.tile[0] * bins.tile[1] * bins.tile[2];
-    const int p_begin = bins.cell_start[(long)t * tvol];
-    const int p_end = bins.cell_start[(long)(t + 1) * tvol];
+    const int p_begin = min(bins.cell_start[(long)t * tvol], bins.np_limit);
+    const int p_end = min(bins.cell_start[(long)(t + 1) * tvol], bins.np_limit);
     // block origin in global index space (same for all three components: node-based weights)
     const int o0 = bins.box_lo[0] + tc[0] * bins.tile[0] - DT_MARGIN_LO;
     const int o1 = bins.box_lo[1] + tc[1] * bins.tile[1] - DT_MARGIN_LO;
@@ -500,6 +500,7 @@ int deposit_tile_launch(const pic_soa* p, long offset, long np, const pic_fab J[
                         const DepositGeom& dg, int nox, const pic_bins* bins, cudaStream_t s) {
     PIC_REQUIRE(offset == 0 && np == p->np, "pic_deposit_esirkepov: bins describe the whole tile (offset 0, np = all)");
     BinsView bv = make_bins(*bins);
+    bv.np_limit = (int)(bins->np_binned < np ? bins->np_binned : np);
     SoaView P = make_soa(*p, 0);
     if (nox == 1) return launch_tile<1, 8>(P, bv, J, dg, s);
     if (nox == 2) return launch_tile<2, 8>(P, bv, J, dg, s);

@@ -58,8 +58,12 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     const double qdt2m = 0.5 * q * dt / m;
     cudaStream_t s = (cudaStream_t)stream;
     if (bins) {
-        return gather_push_tile_launch(p, offset, np, E, B, gg, qdt2m, dt, nox, galerkin, pusher,
-                                       push_position, bins, s);
+        if (int rc = gather_push_tile_launch(p, offset, np, E, B, gg, qdt2m, dt, nox, galerkin, pusher,
+                                             push_position, bins, s)) return rc;
+        if (bins->np_binned >= np) return 0;
+        // particles appended after the last sort (neighbour migration): order-agnostic kernel
+        offset = bins->np_binned;
+        np -= bins->np_binned;
     }
     GlobalFields fld;
     for (int c = 0; c < 3; ++c) { fld.v[c] = make_view(E[c]); fld.v[3 + c] = make_view(B[c]); }

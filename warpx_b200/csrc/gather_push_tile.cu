@@ -10,6 +10,7 @@
 #include "pic_common.cuh"
 #include "gather_common.cuh"
 #include "bins.cuh"
+#include <algorithm>
 
 namespace pic {
 
@@ -57,9 +58,9 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     int tc[3];
     tile_coords(bins, t, tc);
     const long tvol = (long)bins.tile[0] * bins.tile[1] * bins.tile[2];
-    const int p_begin = bins.cell_start[(long)t * tvol];
-    const int p_end = bins.cell_start[(long)(t + 1) * tvol];
-    if (p_begin == p_end) return;
+    const int p_begin = min(bins.cell_start[(long)t * tvol], bins.np_limit);
+    const int p_end = min(bins.cell_start[(long)(t + 1) * tvol], bins.np_limit);
+    if (p_begin >= p_end) return;
     const int t0 = bins.box_lo[0] + tc[0] * bins.tile[0];
     const int t1 = bins.box_lo[1] + tc[1] * bins.tile[1];
     const int t2 = bins.box_lo[2] + tc[2] * bins.tile[2];
@@ -134,6 +135,7 @@ int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fa
                             const pic_bins* bins, cudaStream_t s) {
     PIC_REQUIRE(offset == 0 && np == p->np, "pic_gather_push: bins describe the whole tile (offset 0, np = all)");
     BinsView bv = make_bins(*bins);
+    bv.np_limit = (int)std::min<long>(bins->np_binned, np);   // the tile may have shrunk since the sort
     GlobalFields gf;
     for (int c = 0; c < 3; ++c) { gf.v[c] = make_view(E[c]); gf.v[3 + c] = make_view(B[c]); }
     SoaView P = make_soa(*p, 0);

@@ -59,6 +59,24 @@ __global__ void sort_scatter_kernel(SoaView in, SoaView out, const uint64_t* __r
     if (id_in && id_out) id_out[pos] = id_in[ip];
 }
 
+// which particles leave the rank's brick along one axis (cell index of the wrapped position)
+__global__ void classify_kernel(const double* __restrict__ pos, long np, double plo, double dinv, int ncell,
+                                int cell_lo, int cell_hi, int both_up, int* __restrict__ counts,
+                                int* __restrict__ idx_lo, int* __restrict__ idx_hi, int capacity) {
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= np) return;
+    int c = (int)floor((pos[ip] - plo) * dinv);
+    c = min(max(c, 0), ncell - 1);
+    if (c >= cell_lo && c <= cell_hi) return;
+    // neighbour ownership is periodic: cells just above cell_hi (or wrapped to the bottom of the
+    // domain when this brick is the last one) belong to the high neighbour
+    const int width = cell_hi - cell_lo + 1;
+    const int up_lo = (cell_hi + 1) % ncell;                       // first cell of the high neighbour
+    const bool up = both_up || (c >= up_lo && c < up_lo + width);
+    if (up) { const int n = atomicAdd(&counts[1], 1); if (n < capacity) idx_hi[n] = (int)ip; }
+    else    { const int n = atomicAdd(&counts[0], 1); if (n < capacity) idx_lo[n] = (int)ip; }
+}
+
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static size_t scan_temp_bytes(long n) {
     size_t bytes = 0;
@@ -80,6 +98,21 @@ extern "C" int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, 
     wrap_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_soa(*p, 0), p->np, wg);
     count_launch();
     return check_launch("pic_particles_wrap_periodic") ? 0 : 1;
+}
+
+extern "C" int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
+                                      int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
+                                      void* stream) {
+    PIC_REQUIRE(dim >= 0 && dim < 3, "pic_particles_classify: bad dimension");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(counts, 0, 2 * sizeof(int), s);
+    if (p->np == 0) return 0;
+    const double* pos = dim == 0 ? p->x : (dim == 1 ? p->y : p->z);
+    const double dinv = 1.0 / ((g->prob_hi[dim] - g->prob_lo[dim]) / g->n_cell[dim]);
+    classify_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, s>>>(pos, p->np, g->prob_lo[dim], dinv, g->n_cell[dim],
+                                                                  cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
+    count_launch();
+    return check_launch("pic_particles_classify") ? 0 : 1;
 }
 
 extern "C" long pic_bins_count(const int box_lo[3], const int box_hi[3], const int tile[3]) {

@@ -304,59 +304,77 @@ class Simulation:
         check(self.L.pic_sort_particles_by_cell(C.byref(src), C.byref(dst), C.byref(self.geom), C.byref(bins),
                                                 sp.work.data_ptr(), self.stream))
         sp.cur = 1 - sp.cur
+        bins.np_binned = sp.np
         sp.bins = bins
 
     def _migrate(self, sp):
-        """Neighbour migration after the periodic wrap (RedistributeLocal(1)); axis sweeps."""
+        """Neighbour migration after the periodic wrap (AMReX RedistributeLocal(1)), axis sweeps.
+        Only the particles that leave are touched: a classify kernel lists them, they are packed,
+        exchanged (counts, then payload) and the arrivals fill the holes; the particle order --
+        and therefore the cell bins -- stays valid for everything that did not move."""
         t = self.torch
+        cap = max(1 << 16, sp.capacity // 16)
+        if getattr(sp, "_mig", None) is None or sp._mig[1].numel() < cap:
+            sp._mig = (t.zeros(2, dtype=t.int32, device=self.device),
+                       t.empty(cap, dtype=t.int32, device=self.device),
+                       t.empty(cap, dtype=t.int32, device=self.device))
+        counts, idx_lo, idx_hi = sp._mig
         for dim in range(3):
             if self.dec.spans(dim):
                 continue
-            pos = sp.array(("x", "y", "z")[dim])
-            cell = t.floor((pos - self.prob_lo[dim]) * self.dinv[dim]).to(t.int64).clamp_(0, self.n_cell[dim] - 1)
-            down, up = parallel.particle_destinations(cell, self.dec, dim)
-            keep = ~(down | up)
-            cur = sp.buf[sp.cur][:, :sp.np]
-            cur_id = sp.ids[sp.cur][:sp.np]
-            s_lo, s_hi = cur[:, down].contiguous(), cur[:, up].contiguous()
-            i_lo, i_hi = cur_id[down].contiguous(), cur_id[up].contiguous()
-            counts = t.tensor([s_lo.shape[1], s_hi.shape[1]], dtype=t.int64, device=self.device)
+            soa = sp.soa()
+            check(self.L.pic_particles_classify(C.byref(soa), C.byref(self.geom), dim, self.box_lo[dim],
+                                                self.box_hi[dim], 1 if self.dec.nb[dim] == 2 else 0,
+                                                counts.data_ptr(), idx_lo.data_ptr(), idx_hi.data_ptr(), cap,
+                                                self.stream))
+            n_lo, n_hi = (int(v) for v in counts.tolist())          # host sync (8 bytes)
+            if max(n_lo, n_hi) > cap:
+                raise RuntimeError("migration list overflow on rank %d: %d particles leave" % (self.rank, max(n_lo, n_hi)))
+            buf, ids = sp.buf[sp.cur], sp.ids[sp.cur]
+            i_lo, i_hi = idx_lo[:n_lo].long(), idx_hi[:n_hi].long()
+            # payload: 7 doubles + the id (bit pattern) per particle
+            s_lo = t.cat([buf[:, i_lo], ids[i_lo].view(t.float64)[None, :]], 0).contiguous()
+            s_hi = t.cat([buf[:, i_hi], ids[i_hi].view(t.float64)[None, :]], 0).contiguous()
+            sc = t.tensor([n_lo, n_hi], dtype=t.int64, device=self.device)
             rc = t.zeros(2, dtype=t.int64, device=self.device)
-            # counts: what I send low is received by my low neighbour as "from high"
-            parallel.exchange(self.dist, self.dec, dim, counts[0:1], counts[1:2], rc[0:1], rc[1:2])
-            n_lo, n_hi = int(rc[0].item()), int(rc[1].item())
-            r_lo = t.empty((7, n_lo), dtype=t.float64, device=self.device)
-            r_hi = t.empty((7, n_hi), dtype=t.float64, device=self.device)
+            parallel.exchange(self.dist, self.dec, dim, sc[0:1], sc[1:2], rc[0:1], rc[1:2])
+            r_lo_n, r_hi_n = (int(v) for v in rc.tolist())          # host sync (16 bytes)
+            r_lo = t.empty((8, r_lo_n), dtype=t.float64, device=self.device)
+            r_hi = t.empty((8, r_hi_n), dtype=t.float64, device=self.device)
             parallel.exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
-            ri_lo = t.empty(n_lo, dtype=t.int64, device=self.device)
-            ri_hi = t.empty(n_hi, dtype=t.int64, device=self.device)
-            parallel.exchange(self.dist, self.dec, dim, i_lo, i_hi, ri_lo, ri_hi)
-            kept = cur[:, keep]
-            kept_id = cur_id[keep]
-            n_new = kept.shape[1] + n_lo + n_hi
-            if n_new > sp.capacity:
-                raise RuntimeError("particle capacity exceeded on rank %d" % self.rank)
-            nb = sp.buf[1 - sp.cur]
-            nb[:, :kept.shape[1]] = kept
-            nb[:, kept.shape[1]:kept.shape[1] + n_lo] = r_lo
-            nb[:, kept.shape[1] + n_lo:n_new] = r_hi
-            ni = sp.ids[1 - sp.cur]
-            ni[:kept.shape[1]] = kept_id
-            ni[kept.shape[1]:kept.shape[1] + n_lo] = ri_lo
-            ni[kept.shape[1] + n_lo:n_new] = ri_hi
-            sp.cur = 1 - sp.cur
-            sp.np = n_new
-            sp.bins = None      # order changed: bins are stale until the next sort
+            arrivals = t.cat([r_lo, r_hi], 1)
+            holes = t.cat([i_lo, i_hi])
+            n_arr, n_holes, np_old = arrivals.shape[1], holes.numel(), sp.np
+            n_fill = min(n_arr, n_holes)
+            if n_fill:
+                buf[:, holes[:n_fill]] = arrivals[:7, :n_fill]
+                ids[holes[:n_fill]] = arrivals[7, :n_fill].contiguous().view(t.int64)
+            if n_arr > n_holes:                                      # append the remaining arrivals
+                extra = n_arr - n_holes
+                if np_old + extra > sp.capacity:
+                    raise RuntimeError("particle capacity exceeded on rank %d" % self.rank)
+                buf[:, np_old:np_old + extra] = arrivals[:7, n_holes:]
+                ids[np_old:np_old + extra] = arrivals[7, n_holes:].contiguous().view(t.int64)
+                sp.np = np_old + extra
+            elif n_holes > n_arr:                                    # move tail particles into the open holes
+                open_holes = holes[n_arr:]
+                np_new = np_old - open_holes.numel()
+                tail_is_hole = t.zeros(np_old - np_new, dtype=t.bool, device=self.device)
+                in_tail = open_holes >= np_new
+                tail_is_hole[open_holes[in_tail] - np_new] = True
+                movers = t.nonzero(~tail_is_hole).flatten() + np_new
+                targets = open_holes[~in_tail]
+                buf[:, targets] = buf[:, movers]
+                ids[targets] = ids[movers]
+                sp.np = np_new
 
     def HandleParticlesAtBoundaries(self, step):
         for sp in self.species:
             soa = sp.soa()
             check(self.L.pic_particles_wrap_periodic(C.byref(soa), C.byref(self.geom), self.stream))
-            moved = False
             if self.world > 1:
-                self._migrate(sp)
-                moved = True
-            if self.use_bins and (moved or (self.sort_interval > 0 and (step + 1) % self.sort_interval == 0)):
+                self._timed("migrate", self._migrate, sp)
+            if self.use_bins and self.sort_interval > 0 and (step + 1) % self.sort_interval == 0:
                 self._timed("sort", self.SortParticlesByBin, sp)
 
     # ---- the step ----------------------------------------------------------------------

@@ -42,6 +42,7 @@ def lib():
         "pic_halo_pack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_halo_unpack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_particles_wrap_periodic": (C.c_int, [soap, gp, vp]),
+        "pic_particles_classify": (C.c_int, [soap, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]),
         "pic_bins_count": (C.c_long, [ip, ip, ip]),
         "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
         "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),
