@@ -192,6 +192,21 @@ int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cel
                            int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
                            void* stream);
 
+/* Neighbour migration, steps 2 and 3 (pack / unpack phases of Redistribute).  A message is
+ * pic_migrate_message_doubles(cap) doubles: header (true particle count) + 8 rows of cap doubles
+ * (x y z w ux uy uz id) -- a FIXED size, so the send/recv pair needs no count exchange.
+ * pic_migrate_unpack drops the arrivals (msg_lo from the low, msg_hi from the high neighbour) into
+ * the holes left by the particles listed in idx_lo/idx_hi, appends the rest, or moves tail
+ * particles into the remaining holes; work[0] receives the new particle count, work[1] a status
+ * (bit 0: a list or message overflowed `cap`; bit 1: `capacity` exceeded).  p->np is the count
+ * before migration. */
+long pic_migrate_message_doubles(int cap);
+long pic_migrate_workspace_bytes(int cap);
+int pic_migrate_pack(const pic_soa* p, const int* idx, const int* count, int cap, double* msg, void* stream);
+int pic_migrate_unpack(const pic_soa* p, const int* counts, const int* idx_lo, const int* idx_hi,
+                       const double* msg_lo, const double* msg_hi, int cap, long capacity,
+                       void* work, void* stream);
+
 /* Counting sort of the particles by cell over the valid box [box_lo,box_hi]
  * (WarpX: mypc->SortParticlesByBin, WarpXEvolve.cpp:575-580).  `in` is permuted into `out`;
  * bins->cell_start (pic_bins_count()+1 ints) receives the bins.  work must hold

@@ -239,14 +239,14 @@ class Simulation:
 
     # ---- guard cells -------------------------------------------------------------------
     def FillBoundaryE(self, ng):
-        self.halo.fill_boundary(self.fab[0:3], ng)
+        self._timed("fill_boundary_e", self.halo.fill_boundary, self.fab[0:3], ng)
 
     def FillBoundaryB(self, ng):
-        self.halo.fill_boundary(self.fab[3:6], ng)
+        self._timed("fill_boundary_b", self.halo.fill_boundary, self.fab[3:6], ng)
 
     def FillBoundaryEB(self, ng):
         """FillBoundaryE + FillBoundaryB with the same ng in one exchange per direction."""
-        self.halo.fill_boundary(self.fab[0:6], ng)
+        self._timed("fill_boundary_eb", self.halo.fill_boundary, self.fab[0:6], ng)
 
     def SyncCurrent(self):
         """SumBoundaryJ: src = ng_depos_J (no filter), all guards of J updated afterwards."""
@@ -308,70 +308,48 @@ class Simulation:
         sp.bins = bins
 
     def _migrate(self, sp):
-        """Neighbour migration after the periodic wrap (AMReX RedistributeLocal(1)), axis sweeps.
-        Only the particles that leave are touched: a classify kernel lists them, they are packed,
-        exchanged (counts, then payload) and the arrivals fill the holes; the particle order --
-        and therefore the cell bins -- stays valid for everything that did not move."""
+        """Neighbour migration after the periodic wrap (AMReX RedistributeLocal(1)), axis sweeps,
+        entirely on the device (csrc/migrate.cu): classify -> pack into fixed-size messages ->
+        NCCL send/recv -> arrivals fill the holes.  One 8-byte host read per sweep (new count)."""
         t = self.torch
-        cap = max(1 << 16, sp.capacity // 16)
-        if getattr(sp, "_mig", None) is None or sp._mig[1].numel() < cap:
-            sp._mig = (t.zeros(2, dtype=t.int32, device=self.device),
-                       t.empty(cap, dtype=t.int32, device=self.device),
-                       t.empty(cap, dtype=t.int32, device=self.device))
-        counts, idx_lo, idx_hi = sp._mig
+        cap = max(1 << 16, sp.capacity // 256)
+        if getattr(sp, "_mig", None) is None:
+            n = self.L.pic_migrate_message_doubles(cap)
+            f64 = dict(dtype=t.float64, device=self.device)
+            sp._mig = dict(cap=cap, counts=t.zeros(2, dtype=t.int32, device=self.device),
+                           idx_lo=t.empty(cap, dtype=t.int32, device=self.device),
+                           idx_hi=t.empty(cap, dtype=t.int32, device=self.device),
+                           s_lo=t.zeros(n, **f64), s_hi=t.zeros(n, **f64), r_lo=t.zeros(n, **f64), r_hi=t.zeros(n, **f64),
+                           work=t.zeros(self.L.pic_migrate_workspace_bytes(cap) // 4, dtype=t.int32, device=self.device))
+        m = sp._mig
+        cap = m["cap"]
         for dim in range(3):
             if self.dec.spans(dim):
                 continue
             soa = sp.soa()
             check(self.L.pic_particles_classify(C.byref(soa), C.byref(self.geom), dim, self.box_lo[dim],
                                                 self.box_hi[dim], 1 if self.dec.nb[dim] == 2 else 0,
-                                                counts.data_ptr(), idx_lo.data_ptr(), idx_hi.data_ptr(), cap,
-                                                self.stream))
-            n_lo, n_hi = (int(v) for v in counts.tolist())          # host sync (8 bytes)
-            if max(n_lo, n_hi) > cap:
-                raise RuntimeError("migration list overflow on rank %d: %d particles leave" % (self.rank, max(n_lo, n_hi)))
-            buf, ids = sp.buf[sp.cur], sp.ids[sp.cur]
-            i_lo, i_hi = idx_lo[:n_lo].long(), idx_hi[:n_hi].long()
-            # payload: 7 doubles + the id (bit pattern) per particle
-            s_lo = t.cat([buf[:, i_lo], ids[i_lo].view(t.float64)[None, :]], 0).contiguous()
-            s_hi = t.cat([buf[:, i_hi], ids[i_hi].view(t.float64)[None, :]], 0).contiguous()
-            sc = t.tensor([n_lo, n_hi], dtype=t.int64, device=self.device)
-            rc = t.zeros(2, dtype=t.int64, device=self.device)
-            parallel.exchange(self.dist, self.dec, dim, sc[0:1], sc[1:2], rc[0:1], rc[1:2])
-            r_lo_n, r_hi_n = (int(v) for v in rc.tolist())          # host sync (16 bytes)
-            r_lo = t.empty((8, r_lo_n), dtype=t.float64, device=self.device)
-            r_hi = t.empty((8, r_hi_n), dtype=t.float64, device=self.device)
-            parallel.exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
-            arrivals = t.cat([r_lo, r_hi], 1)
-            holes = t.cat([i_lo, i_hi])
-            n_arr, n_holes, np_old = arrivals.shape[1], holes.numel(), sp.np
-            n_fill = min(n_arr, n_holes)
-            if n_fill:
-                buf[:, holes[:n_fill]] = arrivals[:7, :n_fill]
-                ids[holes[:n_fill]] = arrivals[7, :n_fill].contiguous().view(t.int64)
-            if n_arr > n_holes:                                      # append the remaining arrivals
-                extra = n_arr - n_holes
-                if np_old + extra > sp.capacity:
-                    raise RuntimeError("particle capacity exceeded on rank %d" % self.rank)
-                buf[:, np_old:np_old + extra] = arrivals[:7, n_holes:]
-                ids[np_old:np_old + extra] = arrivals[7, n_holes:].contiguous().view(t.int64)
-                sp.np = np_old + extra
-            elif n_holes > n_arr:                                    # move tail particles into the open holes
-                open_holes = holes[n_arr:]
-                np_new = np_old - open_holes.numel()
-                tail_is_hole = t.zeros(np_old - np_new, dtype=t.bool, device=self.device)
-                in_tail = open_holes >= np_new
-                tail_is_hole[open_holes[in_tail] - np_new] = True
-                movers = t.nonzero(~tail_is_hole).flatten() + np_new
-                targets = open_holes[~in_tail]
-                buf[:, targets] = buf[:, movers]
-                ids[targets] = ids[movers]
-                sp.np = np_new
+                                                m["counts"].data_ptr(), m["idx_lo"].data_ptr(), m["idx_hi"].data_ptr(),
+                                                cap, self.stream))
+            check(self.L.pic_migrate_pack(C.byref(soa), m["idx_lo"].data_ptr(), m["counts"][0:1].data_ptr(), cap,
+                                          m["s_lo"].data_ptr(), self.stream))
+            check(self.L.pic_migrate_pack(C.byref(soa), m["idx_hi"].data_ptr(), m["counts"][1:2].data_ptr(), cap,
+                                          m["s_hi"].data_ptr(), self.stream))
+            parallel.exchange(self.dist, self.dec, dim, m["s_lo"], m["s_hi"], m["r_lo"], m["r_hi"])
+            check(self.L.pic_migrate_unpack(C.byref(soa), m["counts"].data_ptr(), m["idx_lo"].data_ptr(),
+                                            m["idx_hi"].data_ptr(), m["r_lo"].data_ptr(), m["r_hi"].data_ptr(), cap,
+                                            sp.capacity, m["work"].data_ptr(), self.stream))
+            np_new, status = (int(v) for v in m["work"][:2].tolist())       # the one host read of the sweep
+            if status:
+                raise RuntimeError("particle migration overflow on rank %d (status %d): raise capacity_factor"
+                                   % (self.rank, status))
+            sp.np = np_new
 
     def HandleParticlesAtBoundaries(self, step):
         for sp in self.species:
             soa = sp.soa()
-            check(self.L.pic_particles_wrap_periodic(C.byref(soa), C.byref(self.geom), self.stream))
+            self._timed("wrap", lambda: check(self.L.pic_particles_wrap_periodic(C.byref(soa), C.byref(self.geom),
+                                                                                  self.stream)))
             if self.world > 1:
                 self._timed("migrate", self._migrate, sp)
             if self.use_bins and self.sort_interval > 0 and (step + 1) % self.sort_interval == 0:
