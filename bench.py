@@ -166,8 +166,9 @@ def run_engine(args):
     npart_local = len(s["x"])
     t_gen = time.perf_counter() - t_gen
 
-    def make_sim():
-        sim = Simulation(n_cell, prob_lo, prob_hi, nox=3, dist=dist, sort_interval=args.sort_interval)
+    def make_sim(native=True):
+        sim = Simulation(n_cell, prob_lo, prob_hi, nox=3, dist=dist, sort_interval=args.sort_interval,
+                         native_driver=native)
         sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
         return sim
 
@@ -181,7 +182,6 @@ def run_engine(args):
     sim = make_sim()
     ntot = sim.total_particles()
     sim.Evolve(args.warmup, synchronize_last=False)
-    sim.enable_stage_timing(True)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -198,13 +198,23 @@ def run_engine(args):
     ms = float(ms.item())
     launches = L.pic_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
-    stage = sim.stage_ms()
     fe = sim.field_energy()
     value = ntot * args.steps / (ms * 1e-3)
+    # per-kernel durations for the roofline: a second, separately timed pass with CUDA events around
+    # every stage (Python sequencer; the timed region above ran the C++ driver on one rank)
+    del sim
+    torch.cuda.empty_cache()
+    sim = make_sim(native=False)
+    sim.Evolve(args.warmup, synchronize_last=False)
+    sim.enable_stage_timing(True)
+    sim.Evolve(min(args.steps, 4), synchronize_last=False)
+    stage = sim.stage_ms()
 
     if args.profile_only:
         if rank == 0:
             print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "stage_ms": {k: v[0] for k, v in stage.items()}}))
+        if dist is not None:
+            dist.destroy_process_group()
         return
 
     # =================== end-to-end through the public API (`e2e`) ===================

@@ -218,6 +218,24 @@ int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_
                                void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * C++ step driver (single rank, periodic): WarpX::Evolve / OneStep_nosub expressed through the
+ * entry points above (csrc/engine.cu cites the reference lines of every stage).  Memory is
+ * borrowed: fabs = Ex Ey Ez Bx By Bz jx jy jz with at least pic_engine_guards() guard cells;
+ * bufA/bufB = the two particle buffers of a species (the counting sort permutes one into the other).
+ * ---------------------------------------------------------------------------------------- */
+void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
+                        int galerkin, int pusher, int solver, double cfl, double dt /* <=0: cfl*max_dt */,
+                        int sort_interval);
+void pic_engine_destroy(void* engine);
+double pic_engine_dt(void* engine);
+void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);
+int pic_engine_set_fields(void* engine, const pic_fab fabs[9]);
+int pic_engine_add_species(void* engine, double q, double m, const pic_soa* bufA, const pic_soa* bufB,
+                           int* cell_start, const int tile[3], void* sort_work, void* stream);
+int pic_engine_species_buffer(void* engine, int isp, long* np);
+int pic_engine_evolve(void* engine, int numsteps, int synchronize_last, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Reduced diagnostics used as parity metrics
  * ---------------------------------------------------------------------------------------- */
 

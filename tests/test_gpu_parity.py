@@ -389,12 +389,16 @@ def test_langmuir_loop_golden_and_oracle(orc, cuda, golden, use_bins):
     assert b == pytest.approx(bo, rel=1e-7)     # B is at round-off level in this electrostatic mode
 
 
-@pytest.mark.parametrize("solver,pusher", [(abi.SOLVER_YEE, abi.PUSHER_BORIS), (abi.SOLVER_CKC, abi.PUSHER_VAY)])
-def test_order3_loop_matches_oracle(orc, cuda, solver, pusher):
+@pytest.mark.parametrize("solver,pusher,native", [(abi.SOLVER_YEE, abi.PUSHER_BORIS, True),
+                                                  (abi.SOLVER_YEE, abi.PUSHER_BORIS, False),
+                                                  (abi.SOLVER_CKC, abi.PUSHER_VAY, True)])
+def test_order3_loop_matches_oracle(orc, cuda, solver, pusher, native):
     """Config 2 / 3 physics (order-3 Esirkepov, 8 ppc, Yee or CKC) at 32^3, 10 steps, with a
     Langmuir perturbation on top of the thermal spread so that the fields are well above noise."""
     wl = workloads.uniform_plasma_3d(n=32, ppc=(2, 2, 2), u_th=0.01, lx=5e-6, perturbation=0.01)
-    sim, osim = _run_both(orc, cuda, wl, 3, 10, solver=solver, pusher=pusher, sort_interval=4)
+    # native: the library's C++ step driver (csrc/engine.cu); otherwise the Python sequencer
+    sim, osim = _run_both(orc, cuda, wl, 3, 10, solver=solver, pusher=pusher, sort_interval=4, native_driver=native)
+    assert bool(sim.native) == native
     for c in range(9):
         d, a = sim.field_numpy(c)
         _, oa = osim.fab(c)

@@ -150,7 +150,7 @@ class Species:
 class Simulation:
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
-                 tile=(8, 8, 8), use_bins=True, device=None):
+                 tile=(8, 8, 8), use_bins=True, device=None, native_driver=True):
         self.torch = require_cuda()
         t = self.torch
         self.L = lib()
@@ -192,6 +192,23 @@ class Simulation:
         self.istep = 0
         self._scratch = t.zeros(8, dtype=t.float64, device=self.device)
         self.stage_events = None      # {stage: [(start, end), ...]} when enable_stage_timing() is on
+        # Single rank: the step sequence runs in the library's C++ driver (csrc/engine.cu); this
+        # Python mirror of the same sequence is used for multi-rank runs (it interleaves the NCCL
+        # exchanges) and when per-stage timing is requested.
+        self.native = None
+        if native_driver and self.world == 1 and use_bins:
+            self.native = self.L.pic_engine_create(C.byref(self.geom), abi.int3(self.box_lo), abi.int3(self.box_hi),
+                                                   nox, galerkin, pusher, solver, cfl, self.dt, sort_interval)
+            g12 = (C.c_int * 12)()
+            self.L.pic_engine_guards(self.native, g12)
+            assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
+            assert self.L.pic_engine_dt(self.native) == self.dt
+            check(self.L.pic_engine_set_fields(self.native, (abi.pic_fab * 9)(*self.fab)))
+
+    def __del__(self):
+        if getattr(self, "native", None):
+            self.L.pic_engine_destroy(self.native)
+            self.native = None
 
     def enable_stage_timing(self, on=True):
         """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""
@@ -226,9 +243,38 @@ class Simulation:
         cap = int(len(x) * capacity_factor) + (0 if self.world == 1 else 65536)
         sp = Species(self, name, q, m, arrays, cap)
         self.species.append(sp)
-        if self.use_bins:
+        if self.native:
+            self._alloc_sort_scratch(sp)
+            a, b = sp.soa(0), sp.soa(1)
+            check(self.L.pic_engine_add_species(self.native, q, m, C.byref(a), C.byref(b), sp.cell_start.data_ptr(),
+                                                abi.int3(self.tile), sp.work.data_ptr(), self.stream))
+            self._sync_from_native()
+        elif self.use_bins:
             self.SortParticlesByBin(sp)
         return sp
+
+    def _alloc_sort_scratch(self, sp):
+        t = self.torch
+        nb = self.L.pic_bins_count(abi.int3(self.box_lo), abi.int3(self.box_hi), abi.int3(self.tile))
+        if sp.cell_start is None or sp.cell_start.numel() < nb + 1:
+            sp.cell_start = t.empty(nb + 1, dtype=t.int32, device=self.device)
+        wb = self.L.pic_sort_workspace_bytes(sp.capacity, nb)
+        if sp.work is None or sp.work.numel() < wb:
+            sp.work = t.empty(wb, dtype=t.uint8, device=self.device)
+        return nb
+
+    def _sync_from_native(self):
+        """Mirror the C++ driver's view (current buffer, count, bins) into the Python objects."""
+        for isp, sp in enumerate(self.species):
+            n = C.c_long()
+            sp.cur = self.L.pic_engine_species_buffer(self.native, isp, C.byref(n))
+            sp.np = n.value
+            bins = abi.pic_bins()
+            for d in range(3):
+                bins.box_lo[d], bins.box_hi[d], bins.tile[d] = self.box_lo[d], self.box_hi[d], self.tile[d]
+            bins.cell_start = sp.cell_start.data_ptr()
+            bins.np_binned = sp.np
+            sp.bins = bins
 
     def lower_corner(self, ng):
         """WarpX::LowerCorner of the box grown by ng (Source/WarpX.cpp:2851-2874; RealBox lo =
@@ -289,16 +335,10 @@ class Simulation:
             self._timed("deposit", self.DepositCurrent, sp, self.dt, -0.5 * self.dt)  # relative_time, PhysicalParticleContainer.cpp:2029
 
     def SortParticlesByBin(self, sp):
-        t = self.torch
         bins = abi.pic_bins()
         for d in range(3):
             bins.box_lo[d], bins.box_hi[d], bins.tile[d] = self.box_lo[d], self.box_hi[d], self.tile[d]
-        nb = self.L.pic_bins_count(bins.box_lo, bins.box_hi, bins.tile)
-        if sp.cell_start is None or sp.cell_start.numel() < nb + 1:
-            sp.cell_start = t.empty(nb + 1, dtype=t.int32, device=self.device)
-        wb = self.L.pic_sort_workspace_bytes(sp.capacity, nb)
-        if sp.work is None or sp.work.numel() < wb:
-            sp.work = t.empty(wb, dtype=t.uint8, device=self.device)
+        self._alloc_sort_scratch(sp)
         bins.cell_start = sp.cell_start.data_ptr()
         src, dst = sp.soa(sp.cur), sp.soa(1 - sp.cur)
         check(self.L.pic_sort_particles_by_cell(C.byref(src), C.byref(dst), C.byref(self.geom), C.byref(bins),
@@ -379,6 +419,14 @@ class Simulation:
         self.is_synchronized = True
 
     def Evolve(self, numsteps, synchronize_last=True):
+        if self.native and self.stage_events is None:
+            check(self.L.pic_engine_evolve(self.native, numsteps, 1 if synchronize_last else 0, self.stream))
+            self.istep += numsteps
+            self.is_synchronized = bool(synchronize_last)
+            self._sync_from_native()
+            return
+        if self.native:
+            raise RuntimeError("per-stage timing needs Simulation(native_driver=False)")
         for n in range(numsteps):
             self.ExplicitFillBoundaryEBUpdateAux()
             self.OneStep_nosub()

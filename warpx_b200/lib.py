@@ -51,6 +51,14 @@ def lib():
         "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
         "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),
         "pic_sum_squares_unique": (C.c_int, [fabp, gp, vp, vp]),
+        "pic_engine_create": (vp, [gp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
+        "pic_engine_destroy": (None, [vp]),
+        "pic_engine_dt": (C.c_double, [vp]),
+        "pic_engine_guards": (None, [vp, ip]),
+        "pic_engine_set_fields": (C.c_int, [vp, fabp]),
+        "pic_engine_add_species": (C.c_int, [vp, C.c_double, C.c_double, soap, soap, vp, ip, vp, vp]),
+        "pic_engine_species_buffer": (C.c_int, [vp, C.c_int, C.POINTER(C.c_long)]),
+        "pic_engine_evolve": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError if include/pic_b200.h and the library disagree
