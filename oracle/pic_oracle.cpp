@@ -183,7 +183,12 @@ void one_step(Sim& s, bool last_step) {
     // ---- PushParticlesandDeposit (:366 -> MultiParticleContainer::Evolve) ----
     double t0 = now();
     for (auto& b : s.boxes)
-        for (int c = 6; c < 9; ++c) std::fill(b.data[c].begin(), b.data[c].end(), 0.0);  // J.setVal(0)
+        for (int c = 6; c < 9; ++c) {                                                   // J.setVal(0)
+            double* p = b.data[c].data();
+            const long n = (long)b.data[c].size();
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < n; ++i) p[i] = 0.0;
+        }
     s.t_other += now() - t0;
     for (auto& b : s.boxes) {
         double xyzmin[3], xyzminJ[3]; int lo[3], loJ[3];

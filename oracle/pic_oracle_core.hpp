@@ -119,41 +119,41 @@ inline void gather_one(double xp, double yp, double zp, double F[6] /*Ex,Ey,Ez,B
     constexpr int M = N - G;  // galerkin-lowered order
     const double pos[3] = {(xp - xyzmin[0]) * dinv[0], (yp - xyzmin[1]) * dinv[1],
                            (zp - xyzmin[2]) * dinv[2]};
-    // [dim][0 = node full, 1 = cell full, 2 = node lowered, 3 = cell lowered]
+    // [dim][0 = node full, 1 = cell full, 2 = node lowered, 3 = cell lowered]; like the reference
+    // (FieldGather.H:98-109,134-145,170-181) only the combinations some component needs are computed
     double s[3][4][N + 1];
-    int j0[3][4];
+    int j0[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    bool need[3][4] = {{false, false, false, false}, {false, false, false, false}, {false, false, false, false}};
+    int sel[6][3], cnt[6][3];
+    for (int c = 0; c < 6; ++c)
+        for (int d = 0; d < 3; ++d) {
+            // lowered order along: E_c its own direction; B_c the two transverse directions
+            const bool lowered = (c < 3) ? (d == c) : (d != (c - 3));
+            sel[c][d] = (lowered ? 2 : 0) + (stag[c][d] == 1 ? 0 : 1);
+            cnt[c][d] = lowered ? M : N;
+            need[d][sel[c][d]] = true;
+        }
     for (int d = 0; d < 3; ++d) {
-        for (int n = 0; n <= N; ++n) { s[d][0][n] = s[d][1][n] = s[d][2][n] = s[d][3][n] = 0.0; }
-        j0[d][0] = L::template shape<N>(s[d][0], pos[d]);
-        j0[d][1] = L::template shape<N>(s[d][1], pos[d] - 0.5);
-        j0[d][2] = L::template shape<M>(s[d][2], pos[d]);
-        j0[d][3] = L::template shape<M>(s[d][3], pos[d] - 0.5);
+        if (need[d][0]) j0[d][0] = L::template shape<N>(s[d][0], pos[d]);
+        if (need[d][1]) j0[d][1] = L::template shape<N>(s[d][1], pos[d] - 0.5);
+        if (need[d][2]) j0[d][2] = L::template shape<M>(s[d][2], pos[d]);
+        if (need[d][3]) j0[d][3] = L::template shape<M>(s[d][3], pos[d] - 0.5);
     }
-    // component c has its own direction `own` where the lowered order applies:
-    // Ex:x Ey:y Ez:z (FieldGather.H:110-112,147-149,183-185); Bx: y and z, By: x and z, Bz: x and y.
-    auto sel = [&](int c, int d) -> int {
-        bool lowered;
-        if (c < 3) lowered = (d == c);          // E_c: own direction
-        else lowered = (d != (c - 3));          // B_c: the two transverse directions
-        const bool node = stag[c][d] == 1;
-        return (lowered ? 2 : 0) + (node ? 0 : 1);
-    };
-    auto cnt = [&](int c, int d) -> int {
-        bool lowered = (c < 3) ? (d == c) : (d != (c - 3));
-        return lowered ? M : N;
-    };
     const int order_of_comp[6] = {0, 1, 2, 5, 4, 3};  // Ex,Ey,Ez,Bz,By,Bx (:368-422)
     for (int oc = 0; oc < 6; ++oc) {
         const int c = order_of_comp[oc];
-        const int tx = sel(c, 0), ty = sel(c, 1), tz = sel(c, 2);
-        const int nx = cnt(c, 0), ny = cnt(c, 1), nz = cnt(c, 2);
+        const int tx = sel[c][0], ty = sel[c][1], tz = sel[c][2];
+        const int nx = cnt[c][0], ny = cnt[c][1], nz = cnt[c][2];
         const double* sx = s[0][tx]; const double* sy = s[1][ty]; const double* sz = s[2][tz];
-        const int ix0 = lo[0] + j0[0][tx], iy0 = lo[1] + j0[1][ty], iz0 = lo[2] + j0[2][tz];
+        const double* base = &A[c](lo[0] + j0[0][tx], lo[1] + j0[1][ty], lo[2] + j0[2][tz]);
+        const long sj = A[c].sj, sk = A[c].sk;
         double acc = F[c];
         for (int iz = 0; iz <= nz; ++iz)
-            for (int iy = 0; iy <= ny; ++iy)
+            for (int iy = 0; iy <= ny; ++iy) {
+                const double* row = base + iy * sj + iz * sk;
                 for (int ix = 0; ix <= nx; ++ix)
-                    acc += sx[ix] * sy[iy] * sz[iz] * A[c](ix0 + ix, iy0 + iy, iz0 + iz);
+                    acc += sx[ix] * sy[iy] * sz[iz] * row[ix];
+            }
         F[c] = acc;
     }
 }
@@ -292,7 +292,11 @@ void deposit_t(const pic_soa& P, long offset, long np, const pic_fab J[3], const
                               Jx, Jy, Jz, dt, relative_time, dinv, xyzmin, lo, q);
         return;
     }
-#pragma omp parallel
+    // thread-local tiles (WarpXParticleContainer.cpp:455-470) ...
+    std::vector<pic_fab> tiles((size_t)3 * nthreads);
+    std::vector<std::vector<double>> bufs((size_t)3 * nthreads);
+    std::vector<char> used((size_t)nthreads, 0);
+#pragma omp parallel num_threads(nthreads)
     {
 #ifdef _OPENMP
         const int t = omp_get_thread_num();
@@ -308,8 +312,7 @@ void deposit_t(const pic_soa& P, long offset, long np, const pic_fab J[3], const
                                      (P.z[ip] - xyzmin[2]) * dinv[2]};
                 for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], r[d]); mx[d] = std::max(mx[d], r[d]); }
             }
-            pic_fab T[3];
-            std::vector<double> buf[3];
+            pic_fab* T = &tiles[(size_t)3 * t];
             for (int c = 0; c < 3; ++c) {
                 T[c] = J[c];
                 for (int d = 0; d < 3; ++d) {
@@ -317,22 +320,30 @@ void deposit_t(const pic_soa& P, long offset, long np, const pic_fab J[3], const
                     T[c].lo[d] = std::max(J[c].lo[d], lo[d] + (int)std::floor(mn[d]) - (N + 3));
                     T[c].hi[d] = std::min(J[c].hi[d], lo[d] + (int)std::floor(mx[d]) + (N + 3));
                 }
-                buf[c].assign((size_t)fab_size(T[c]), 0.0);
-                T[c].p = buf[c].data();
+                bufs[(size_t)3 * t + c].assign((size_t)fab_size(T[c]), 0.0);
+                T[c].p = bufs[(size_t)3 * t + c].data();
             }
-            {
-                W Jx(T[0]), Jy(T[1]), Jz(T[2]);
-                for (long ip = b; ip < e; ++ip)
-                    deposit_one<L, N>(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip],
-                                      P.uz[ip], Jx, Jy, Jz, dt, relative_time, dinv, xyzmin, lo, q);
-            }
-#pragma omp critical(orc_lockadd)
-            for (int c = 0; c < 3; ++c) {
-                W G(J[c]), S(T[c]);
-                for (int k = T[c].lo[2]; k <= T[c].hi[2]; ++k)
-                    for (int j = T[c].lo[1]; j <= T[c].hi[1]; ++j)
-                        for (int i = T[c].lo[0]; i <= T[c].hi[0]; ++i) G(i, j, k) += S(i, j, k);
-            }
+            W Jx(T[0]), Jy(T[1]), Jz(T[2]);
+            for (long ip = b; ip < e; ++ip)
+                deposit_one<L, N>(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip],
+                                  P.uz[ip], Jx, Jy, Jz, dt, relative_time, dinv, xyzmin, lo, q);
+            used[t] = 1;
+        }
+#pragma omp barrier
+        // ... then added to the global J (the reference's lockAdd, :819-826), here k-plane by k-plane
+        // so that the reduction scales with the thread count
+        for (int c = 0; c < 3; ++c) {
+            W G(J[c]);
+#pragma omp for schedule(static)
+            for (int k = J[c].lo[2]; k <= J[c].hi[2]; ++k)
+                for (int tt = 0; tt < nthreads; ++tt) {
+                    if (!used[tt]) continue;
+                    const pic_fab& T = tiles[(size_t)3 * tt + c];
+                    if (k < T.lo[2] || k > T.hi[2]) continue;
+                    W S(T);
+                    for (int j = T.lo[1]; j <= T.hi[1]; ++j)
+                        for (int i = T.lo[0]; i <= T.hi[0]; ++i) G(i, j, k) += S(i, j, k);
+                }
         }
     }
 }
@@ -362,20 +373,22 @@ inline int wrap(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
 // valid point at the same location (any box; duplicates hold equal values by construction).
 inline void fill_boundary(const pic_fab* fabs, int nfab, const int ng[3], const pic_geom& g) {
     const int n0 = g.n_cell[0], n1 = g.n_cell[1], n2 = g.n_cell[2];
-    // canonical location -> value, from valid points (lowest box index wins, then lowest index)
+    // canonical value of a location = the valid point of the box that OWNS it (a box owns the
+    // points of its cells, i.e. its valid points minus the upper nodal layer); every location is
+    // written exactly once, so the fill is race-free.
     std::vector<double> canon((size_t)n0 * n1 * n2, 0.0);
-    std::vector<char> have((size_t)n0 * n1 * n2, 0);
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
-        for (int k = vlo(f, 2); k <= vhi(f, 2); ++k)
-            for (int j = vlo(f, 1); j <= vhi(f, 1); ++j)
-                for (int i = vlo(f, 0); i <= vhi(f, 0); ++i) {
-                    const size_t c = wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2));
-                    if (!have[c]) { have[c] = 1; canon[c] = v(i, j, k); }
-                }
+        const int h0 = vhi(f, 0) - f.stag[0], h1 = vhi(f, 1) - f.stag[1], h2 = vhi(f, 2) - f.stag[2];
+#pragma omp parallel for schedule(static)
+        for (int k = vlo(f, 2); k <= h2; ++k)
+            for (int j = vlo(f, 1); j <= h1; ++j)
+                for (int i = vlo(f, 0); i <= h0; ++i)
+                    canon[wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2))] = v(i, j, k);
     }
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
+#pragma omp parallel for schedule(static)
         for (int k = vlo(f, 2) - ng[2]; k <= vhi(f, 2) + ng[2]; ++k)
             for (int j = vlo(f, 1) - ng[1]; j <= vhi(f, 1) + ng[1]; ++j)
                 for (int i = vlo(f, 0) - ng[0]; i <= vhi(f, 0) + ng[0]; ++i) {
@@ -396,15 +409,22 @@ inline void sum_boundary(const pic_fab* fabs, int nfab, const int src_ng[3], con
     std::vector<double> canon((size_t)n0 * n1 * n2, 0.0);
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
-        for (int k = vlo(f, 2) - src_ng[2]; k <= vhi(f, 2) + src_ng[2]; ++k)
-            for (int j = vlo(f, 1) - src_ng[1]; j <= vhi(f, 1) + src_ng[1]; ++j)
-                for (int i = vlo(f, 0) - src_ng[0]; i <= vhi(f, 0) + src_ng[0]; ++i) {
-                    const size_t c = wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2));
-                    canon[c] += v(i, j, k);
-                }
+        // planes k that wrap onto each other (k, k +- n2) are visited in separate sweeps, so each
+        // sweep can run in parallel over k without atomics
+        const int kbeg = vlo(f, 2) - src_ng[2], kend = vhi(f, 2) + src_ng[2];
+        const int first_period = (int)std::floor((double)kbeg / n2), last_period = (int)std::floor((double)kend / n2);
+        for (int per = first_period; per <= last_period; ++per) {
+            const int ka = std::max(kbeg, per * n2), kb = std::min(kend, per * n2 + n2 - 1);
+#pragma omp parallel for schedule(static)
+            for (int k = ka; k <= kb; ++k)
+                for (int j = vlo(f, 1) - src_ng[1]; j <= vhi(f, 1) + src_ng[1]; ++j)
+                    for (int i = vlo(f, 0) - src_ng[0]; i <= vhi(f, 0) + src_ng[0]; ++i)
+                        canon[wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2))] += v(i, j, k);
+        }
     }
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
+#pragma omp parallel for schedule(static)
         for (int k = vlo(f, 2) - dst_ng[2]; k <= vhi(f, 2) + dst_ng[2]; ++k)
             for (int j = vlo(f, 1) - dst_ng[1]; j <= vhi(f, 1) + dst_ng[1]; ++j)
                 for (int i = vlo(f, 0) - dst_ng[0]; i <= vhi(f, 0) + dst_ng[0]; ++i) {
