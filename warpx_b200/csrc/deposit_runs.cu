@@ -103,10 +103,22 @@ template <int N> struct QuietCfg {
     static constexpr int CHP = DR_CH + NG;
 };
 
-template <int N, int NW, int MINB>
+// Direction roles.  The kernel is written for "role" directions X (the direction along which
+// consecutive cells are visited and the register window slides), Y and Z; R0/R1/R2 say which
+// physical direction plays each role.  The bins are numbered z-fastest, so X = z, and Y = x makes
+// the lanes of a retired plane walk contiguous memory (4 consecutive doubles per row).
+struct J3 { FabView v[3]; };
+__device__ __forceinline__ long fab_stride(const FabView& F, int d) { return d == 0 ? 1 : (d == 1 ? F.sj : F.sk); }
+
+template <int N, int NW, int MINB, int R0, int R1, int R2>
 __global__ void __launch_bounds__(NW * 32, MINB)
-deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabView Jy, FabView Jz,
-                     DepositGeom dg, KeyBase kb, int* __restrict__ list, int* __restrict__ list_count) {
+deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom dg, KeyBase kbp,
+                     int* __restrict__ list, int* __restrict__ list_count) {
+    // role views of the physical arrays / geometry
+    const FabView& Jx = Jp.v[R0]; const FabView& Jy = Jp.v[R1]; const FabView& Jz = Jp.v[R2];
+    const long stX = fab_stride(Jx, R0), stY = fab_stride(Jy, R1), stZ = fab_stride(Jz, R2);
+    const int kbb[3] = {kbp.b0, kbp.b1, kbp.b2};
+    const KeyBase kb = {kbb[R0], kbb[R1], kbb[R2]};
     using T = QuietCfg<N>;
     constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = T::CHP;
     extern __shared__ double smem[];
@@ -149,12 +161,17 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
     //   pz -> Jz(gx+1+ur, gy+1+v, gz+1) (+i*sk)
     int ur = 0;
     double *px = nullptr, *py = nullptr, *pz = nullptr;
+    auto at = [&](const FabView& F, int ix, int iy, int iz) -> double* {   // role indices -> element
+        int q[3];
+        q[R0] = ix; q[R1] = iy; q[R2] = iz;
+        return F.p + F.off(q[0], q[1], q[2]);
+    };
     auto set_anchor = [&](int k) {
         const int ax = (k & 1023), gx = ax + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
         ur = ring(ax);
-        px = &Jx(gx + 1, gy + 1 + qu, gz + 1 + qv);
-        py = &Jy(gx + 1 + ur, gy + 1, gz + 1 + qv);
-        pz = &Jz(gx + 1 + ur, gy + 1 + qv, gz + 1);
+        px = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
+        py = at(Jy, gx + 1 + ur, gy + 1, gz + 1 + qv);
+        pz = at(Jz, gx + 1 + ur, gy + 1 + qv, gz + 1);
     };
     // the anchor advances one cell along x: only the plane x = gx+1 leaves the window
     auto slide = [&]() {
@@ -167,18 +184,18 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
 #pragma unroll
         for (int i = 0; i < QP; ++i) {
             const double vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-            if (lane < QL && leaving) { atomicAdd(py + i * Jy.sj, vy); atomicAdd(pz + i * Jz.sk, vz); }
+            if (lane < QL && leaving) { atomicAdd(py + i * stY, vy); atomicAdd(pz + i * stZ, vz); }
             if (leaving) { acc[1][i] = 0.0; acc[2][i] = 0.0; }
         }
-        px += 1;                                    // next x plane
-        if (leaving) { py += QS; pz += QS; ur = QS - 1; }   // this lane now owns x = gx + 1 + QS
+        px += stX;                                  // next X plane
+        if (leaving) { py += QS * fab_stride(Jy, R0); pz += QS * fab_stride(Jz, R0); ur = QS - 1; }   // now owns X = gx + 1 + QS
         else ur -= 1;                               // same absolute x, one slot lower
     };
     auto flush_all = [&]() {                        // the anchor jumps: retire the whole window
 #pragma unroll
         for (int i = 0; i < QP; ++i) {
             const double vx = fold(acc[0][i]), vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-            if (lane < QL) { atomicAdd(px + i, vx); atomicAdd(py + i * Jy.sj, vy); atomicAdd(pz + i * Jz.sk, vz); }
+            if (lane < QL) { atomicAdd(px + i * stX, vx); atomicAdd(py + i * stY, vy); atomicAdd(pz + i * stZ, vz); }
             acc[0][i] = 0.0; acc[1][i] = 0.0; acc[2][i] = 0.0;
         }
     };
@@ -210,29 +227,31 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, FabView Jx, FabVie
             for (int d = 0; d < 3; ++d) inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn[d], wo[d], sh[d]);
             moved = (sh[0] != 0) || (sh[1] != 0) || (sh[2] != 0);
             if (!moved) {
-                key = pack_key(dg.lo[0] + inew[0] - 1, dg.lo[1] + inew[1] - 1, dg.lo[2] + inew[2] - 1, kb);
-                // slots 1..N+1 hold wn[0..N] (new) and wo[0..N] (old, no shift)
+                key = pack_key(dg.lo[R0] + inew[R0] - 1, dg.lo[R1] + inew[R1] - 1, dg.lo[R2] + inew[R2] - 1, kb);
+                // slots 1..N+1 hold wn[0..N] (new) and wo[0..N] (old, no shift); role X/Y/Z = dir R0/R1/R2
 #pragma unroll
                 for (int s = 0; s < QS; ++s) {
-                    rec[(T::F_SNX + s) * CHP + lane] = wn[0][s];
-                    rec[(T::F_SOX + s) * CHP + lane] = wo[0][s];
-                    rec[(T::F_SNY + s) * CHP + lane] = wn[1][s];
-                    rec[(T::F_SOY + s) * CHP + lane] = wo[1][s];
-                    rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * wn[1][s] + (1.0 / 6.0) * wo[1][s];
-                    rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * wo[1][s] + (1.0 / 6.0) * wn[1][s];
-                    rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * wn[2][s] + (1.0 / 6.0) * wo[2][s];
-                    rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * wo[2][s] + (1.0 / 6.0) * wn[2][s];
+                    rec[(T::F_SNX + s) * CHP + lane] = wn[R0][s];
+                    rec[(T::F_SOX + s) * CHP + lane] = wo[R0][s];
+                    rec[(T::F_SNY + s) * CHP + lane] = wn[R1][s];
+                    rec[(T::F_SOY + s) * CHP + lane] = wo[R1][s];
+                    rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * wn[R1][s] + (1.0 / 6.0) * wo[R1][s];
+                    rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * wo[R1][s] + (1.0 / 6.0) * wn[R1][s];
+                    rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * wn[R2][s] + (1.0 / 6.0) * wo[R2][s];
+                    rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * wo[R2][s] + (1.0 / 6.0) * wn[R2][s];
                 }
                 // prefix sums over slots 1..N (slot 0 is empty; the sum over 1..N+1 vanishes and is
                 // not deposited -- loop trimming of CurrentDeposition.H:777-788 with dl = du = 1)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
+                for (int r = 0; r < 3; ++r) {
+                    constexpr int RR[3] = {R0, R1, R2};
+                    const int d = RR[r];                 // role r component = physical component d
                     const double wqd = pg.wq * dg.invdtd[d];
                     double run = 0.0;
 #pragma unroll
                     for (int i = 0; i < QP; ++i) {
                         run += wqd * (wo[d][i] - wn[d][i]);
-                        rec[(T::F_CDS + d * QP + i) * CHP + lane] = run;
+                        rec[(T::F_CDS + r * QP + i) * CHP + lane] = run;
                     }
                 }
             } else {
@@ -462,7 +481,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     int* list_count = scratch;
     int* list = scratch + 1;
     cudaMemsetAsync(list_count, 0, sizeof(int), s);
-    auto kq = deposit_quiet_kernel<N, NWQ, MINB>;
+    auto kq = deposit_quiet_kernel<N, NWQ, MINB, 2, 0, 1>;   // slide along z (bins are z-fastest), lanes along x
     auto kg = deposit_general_kernel<N, NWG>;
     const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
@@ -476,7 +495,8 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     const int cpw = 16;   // 512 consecutive particles per warp: long runs, few boundaries
     const long nwarps = (nchunks + cpw - 1) / cpw;
     const unsigned grid_q = (unsigned)((nwarps + NWQ - 1) / NWQ);
-    kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb, list, list_count);
+    J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
+    kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, j3, dg, kb, list, list_count);
     kg<<<NUM_SMS, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
     count_launch(2);
     cudaFreeAsync(scratch, s);

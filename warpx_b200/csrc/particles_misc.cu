@@ -34,26 +34,47 @@ __global__ void wrap_kernel(SoaView P, long np, WrapGeom g) {
 
 struct SortGeom { double plo[3], dinv[3]; };
 
+// Warp-aggregated histogram / slot allocation: particles are nearly sorted already, so the lanes of a
+// warp mostly hit the same few bins; one atomic per distinct bin per warp instead of one per lane.
+__device__ __forceinline__ int warp_aggregated_add(int* counters, int bin, bool active, int* rank_out) {
+    const unsigned peers = __match_any_sync(__activemask(), active ? bin : -1 - (int)(threadIdx.x & 31));
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if (active && lane == leader) base = atomicAdd(&counters[bin], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    *rank_out = rank;
+    return base;
+}
+
 __global__ void sort_count_kernel(SoaView P, long np, BinsView b, SortGeom sg, int* __restrict__ keys,
                                   int* __restrict__ counts) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= np) return;
-    int ci = (int)floor((P.x[ip] - sg.plo[0]) * sg.dinv[0]) - b.box_lo[0];
-    int cj = (int)floor((P.y[ip] - sg.plo[1]) * sg.dinv[1]) - b.box_lo[1];
-    int ck = (int)floor((P.z[ip] - sg.plo[2]) * sg.dinv[2]) - b.box_lo[2];
-    ci = min(max(ci, 0), b.n[0] - 1); cj = min(max(cj, 0), b.n[1] - 1); ck = min(max(ck, 0), b.n[2] - 1);
-    const int bin = (int)bin_of_cell(b, ci, cj, ck);
-    keys[ip] = bin;
-    atomicAdd(&counts[bin], 1);
+    const bool active = ip < np;
+    int bin = 0;
+    if (active) {
+        int ci = (int)floor((P.x[ip] - sg.plo[0]) * sg.dinv[0]) - b.box_lo[0];
+        int cj = (int)floor((P.y[ip] - sg.plo[1]) * sg.dinv[1]) - b.box_lo[1];
+        int ck = (int)floor((P.z[ip] - sg.plo[2]) * sg.dinv[2]) - b.box_lo[2];
+        ci = min(max(ci, 0), b.n[0] - 1); cj = min(max(cj, 0), b.n[1] - 1); ck = min(max(ck, 0), b.n[2] - 1);
+        bin = (int)bin_of_cell(b, ci, cj, ck);
+        keys[ip] = bin;
+    }
+    int rank;
+    warp_aggregated_add(counts, bin, active, &rank);
 }
 
 __global__ void sort_scatter_kernel(SoaView in, SoaView out, const uint64_t* __restrict__ id_in,
                                     uint64_t* __restrict__ id_out, long np, const int* __restrict__ keys,
                                     const int* __restrict__ cell_start, int* __restrict__ fill) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= np) return;
-    const int bin = keys[ip];
-    const int pos = cell_start[bin] + atomicAdd(&fill[bin], 1);
+    const bool active = ip < np;
+    const int bin = active ? keys[ip] : 0;
+    int rank;
+    const int base = warp_aggregated_add(fill, bin, active, &rank);
+    if (!active) return;
+    const int pos = cell_start[bin] + base + rank;
     out.x[pos] = in.x[ip]; out.y[pos] = in.y[ip]; out.z[pos] = in.z[ip]; out.w[pos] = in.w[ip];
     out.ux[pos] = in.ux[ip]; out.uy[pos] = in.uy[ip]; out.uz[pos] = in.uz[ip];
     if (id_in && id_out) id_out[pos] = id_in[ip];
