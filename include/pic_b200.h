@@ -69,9 +69,8 @@ enum { PIC_PUSHER_BORIS = 0, PIC_PUSHER_VAY = 1, PIC_PUSHER_HC = 2 };
  * Source/WarpX.cpp:126,133).
  * Cells of the rank's valid box [box_lo, box_hi] are numbered SUPERCELL-MAJOR: the box is cut
  * into supercells of tile[0] x tile[1] x tile[2] cells (partial supercells at the high ends are
- * padded), supercell t = ti + ntx*(tj + nty*tk), and inside a supercell cells are numbered z-fastest,
- * l = lk + tile[2]*(lj + tile[1]*li); bin id = t*tile[0]*tile[1]*tile[2] + l (the deposition retires
- * x-y planes of its register window as it walks along z: contiguous rows in memory).
+ * padded), supercell t = ti + ntx*(tj + nty*tk), and inside a supercell
+ * l = li + tile[0]*(lj + tile[1]*lk); bin id = t*tile[0]*tile[1]*tile[2] + l.
  * Particles of bin b are [cell_start[b], cell_start[b+1]).  All particles of one supercell are
  * therefore contiguous.  pic_bins_count() gives the (padded) number of bins.
  * Optional everywhere (NULL = particle order unknown -> order-agnostic kernels). */

@@ -153,7 +153,7 @@ def test_sort_bins_are_consistent(orc, dev):
     nt = [(n[d] + T - 1) // T for d in range(3)]
     tcell = [c // T for c in cell]
     lcell = [c % T for c in cell]
-    binid = (tcell[0] + nt[0] * (tcell[1] + nt[1] * tcell[2])) * T ** 3 + lcell[2] + T * (lcell[1] + T * lcell[0])
+    binid = (tcell[0] + nt[0] * (tcell[1] + nt[1] * tcell[2])) * T ** 3 + lcell[0] + T * (lcell[1] + T * lcell[2])
     which = np.searchsorted(cs, np.arange(P.np), side="right") - 1
     assert np.array_equal(which, binid)
 

@@ -35,7 +35,7 @@ __host__ __device__ __forceinline__ long bin_of_cell(const BinsView& b, int ci, 
     const int ti = ci / b.tile[0], tj = cj / b.tile[1], tk = ck / b.tile[2];
     const int li = ci - ti * b.tile[0], lj = cj - tj * b.tile[1], lk = ck - tk * b.tile[2];
     const long t = ti + (long)b.nt[0] * (tj + (long)b.nt[1] * tk);
-    return t * ((long)b.tile[0] * b.tile[1] * b.tile[2]) + lk + b.tile[2] * (lj + b.tile[1] * li);   // z fastest
+    return t * ((long)b.tile[0] * b.tile[1] * b.tile[2]) + li + b.tile[0] * (lj + b.tile[1] * lk);   // x fastest
 }
 __host__ __device__ __forceinline__ void tile_coords(const BinsView& b, int t, int tc[3]) {
     tc[0] = t % b.nt[0];

@@ -105,8 +105,7 @@ template <int N> struct QuietCfg {
 
 // Direction roles.  The kernel is written for "role" directions X (the direction along which
 // consecutive cells are visited and the register window slides), Y and Z; R0/R1/R2 say which
-// physical direction plays each role.  The bins are numbered z-fastest, so X = z, and Y = x makes
-// the lanes of a retired plane walk contiguous memory (4 consecutive doubles per row).
+// physical direction plays each role (the bins are numbered x-fastest, so X = x).
 struct J3 { FabView v[3]; };
 __device__ __forceinline__ long fab_stride(const FabView& F, int d) { return d == 0 ? 1 : (d == 1 ? F.sj : F.sk); }
 
@@ -481,7 +480,11 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     int* list_count = scratch;
     int* list = scratch + 1;
     cudaMemsetAsync(list_count, 0, sizeof(int), s);
-    auto kq = deposit_quiet_kernel<N, NWQ, MINB, 2, 0, 1>;   // slide along z (bins are z-fastest), lanes along x
+    // roles X,Y,Z = x,y,z: bins are x-fastest, the window slides along x.  (Sliding along z with lanes
+    // along x -- <2,0,1> with z-fastest bins -- coalesces the retired planes but was measured no
+    // faster for the deposition and 2.2x slower for the gather: 4-way bank conflicts between the
+    // cells of a warp in the shared E/B block.)
+    auto kq = deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2>;
     auto kg = deposit_general_kernel<N, NWG>;
     const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
