@@ -94,12 +94,15 @@ template <int N> struct QuietCfg {
     static constexpr int QL = QS * QS;        // lines per particle
     static constexpr int NG = 32 / QL;        // particles per warp pass
     static constexpr int QP = N;              // live prefix entries (slots 1..N)
-    static constexpr int F_SNX = 0, F_SOX = QS, F_SNY = 2 * QS, F_SOY = 3 * QS;
-    static constexpr int F_AY = 4 * QS, F_BY = 5 * QS, F_AZ = 6 * QS, F_BZ = 7 * QS;
-    static constexpr int F_CDS = 8 * QS;      // + comp*QP + i
-    static constexpr int NF = 8 * QS + 3 * QP;
-    // record pitch (doubles): a pass reads rows r < QS of a field family at NG consecutive columns;
-    // with pitch = NG (mod 16) the 8-byte words pitch*r + c fall into distinct banks
+    // The record is an array of double2 (one LDS.128 fetches a pair the lane always needs together):
+    //   (Sx_new, Sx_old)[QS], (Sy_new, Sy_old)[QS], (Ay, By)[QS], (Az, Bz)[QS], then the 3*QP prefix
+    //   sums packed two per element.
+    static constexpr int F_SX = 0, F_SY = QS, F_ABY = 2 * QS, F_ABZ = 3 * QS;
+    static constexpr int F_CDS = 4 * QS;
+    static constexpr int NCDS = (3 * QP + 1) / 2;
+    static constexpr int NF = 4 * QS + NCDS;  // double2 elements per particle
+    // record pitch (double2 elements): a pass reads rows r < QS of a field family at NG consecutive
+    // columns; with pitch = NG (mod 8) the 16-byte words pitch*r + c fall into distinct bank groups
     static constexpr int CHP = DR_CH + NG;
 };
 
@@ -120,9 +123,9 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
     const KeyBase kb = {kbb[R0], kbb[R1], kbb[R2]};
     using T = QuietCfg<N>;
     constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = T::CHP;
-    extern __shared__ double smem[];
+    extern __shared__ double2 smem2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* rec = smem + (size_t)warp * NF * CHP;
+    double2* rec = smem2 + (size_t)warp * NF * CHP;
 
     const long nchunks = (np + DR_CH - 1) / DR_CH;
     const long wg = (long)blockIdx.x * NW + warp;
@@ -230,17 +233,17 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                 // slots 1..N+1 hold wn[0..N] (new) and wo[0..N] (old, no shift); role X/Y/Z = dir R0/R1/R2
 #pragma unroll
                 for (int s = 0; s < QS; ++s) {
-                    rec[(T::F_SNX + s) * CHP + lane] = wn[R0][s];
-                    rec[(T::F_SOX + s) * CHP + lane] = wo[R0][s];
-                    rec[(T::F_SNY + s) * CHP + lane] = wn[R1][s];
-                    rec[(T::F_SOY + s) * CHP + lane] = wo[R1][s];
-                    rec[(T::F_AY + s) * CHP + lane] = (1.0 / 3.0) * wn[R1][s] + (1.0 / 6.0) * wo[R1][s];
-                    rec[(T::F_BY + s) * CHP + lane] = (1.0 / 3.0) * wo[R1][s] + (1.0 / 6.0) * wn[R1][s];
-                    rec[(T::F_AZ + s) * CHP + lane] = (1.0 / 3.0) * wn[R2][s] + (1.0 / 6.0) * wo[R2][s];
-                    rec[(T::F_BZ + s) * CHP + lane] = (1.0 / 3.0) * wo[R2][s] + (1.0 / 6.0) * wn[R2][s];
+                    rec[(T::F_SX + s) * CHP + lane] = make_double2(wn[R0][s], wo[R0][s]);
+                    rec[(T::F_SY + s) * CHP + lane] = make_double2(wn[R1][s], wo[R1][s]);
+                    rec[(T::F_ABY + s) * CHP + lane] = make_double2((1.0 / 3.0) * wn[R1][s] + (1.0 / 6.0) * wo[R1][s],
+                                                                    (1.0 / 3.0) * wo[R1][s] + (1.0 / 6.0) * wn[R1][s]);
+                    rec[(T::F_ABZ + s) * CHP + lane] = make_double2((1.0 / 3.0) * wn[R2][s] + (1.0 / 6.0) * wo[R2][s],
+                                                                    (1.0 / 3.0) * wo[R2][s] + (1.0 / 6.0) * wn[R2][s]);
                 }
                 // prefix sums over slots 1..N (slot 0 is empty; the sum over 1..N+1 vanishes and is
                 // not deposited -- loop trimming of CurrentDeposition.H:777-788 with dl = du = 1)
+                double cds[3 * QP + 1];
+                cds[3 * QP] = 0.0;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     constexpr int RR[3] = {R0, R1, R2};
@@ -250,9 +253,12 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
 #pragma unroll
                     for (int i = 0; i < QP; ++i) {
                         run += wqd * (wo[d][i] - wn[d][i]);
-                        rec[(T::F_CDS + r * QP + i) * CHP + lane] = run;
+                        cds[r * QP + i] = run;
                     }
                 }
+#pragma unroll
+                for (int m = 0; m < T::NCDS; ++m)
+                    rec[(T::F_CDS + m) * CHP + lane] = make_double2(cds[2 * m], cds[2 * m + 1]);
             } else {
                 key = -1;
             }
@@ -285,19 +291,24 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                     cur = k;
                 }
                 auto accumulate = [&](int pq) {
-                    const double snx = rec[(T::F_SNX + ur) * CHP + pq], sox = rec[(T::F_SOX + ur) * CHP + pq];
-                    const double sny = rec[(T::F_SNY + qu) * CHP + pq], soy = rec[(T::F_SOY + qu) * CHP + pq];
-                    const double ay_ = rec[(T::F_AY + qv) * CHP + pq], by_ = rec[(T::F_BY + qv) * CHP + pq];
-                    const double az_ = rec[(T::F_AZ + qv) * CHP + pq], bz_ = rec[(T::F_BZ + qv) * CHP + pq];
-                    const double wx = sny * az_ + soy * bz_;   // Jx line (j, k) = (1+u, 1+v)
-                    const double wy = snx * az_ + sox * bz_;   // Jy line (i, k) = (1+ur, 1+v)
-                    const double wz = snx * ay_ + sox * by_;   // Jz line (i, j) = (1+ur, 1+v)
+                    const double2 sx = rec[(T::F_SX + ur) * CHP + pq];     // (Sx_new, Sx_old)[1+ur]
+                    const double2 sy = rec[(T::F_SY + qu) * CHP + pq];     // (Sy_new, Sy_old)[1+u]
+                    const double2 aby = rec[(T::F_ABY + qv) * CHP + pq];   // (Ay, By)[1+v]
+                    const double2 abz = rec[(T::F_ABZ + qv) * CHP + pq];   // (Az, Bz)[1+v]
+                    double w3[3];
+                    w3[0] = sy.x * abz.x + sy.y * abz.y;    // Jx line (j, k) = (1+u, 1+v)
+                    w3[1] = sx.x * abz.x + sx.y * abz.y;    // Jy line (i, k) = (1+ur, 1+v)
+                    w3[2] = sx.x * aby.x + sx.y * aby.y;    // Jz line (i, j) = (1+ur, 1+v)
+                    double cds[2 * T::NCDS];
 #pragma unroll
-                    for (int i = 0; i < QP; ++i) {
-                        acc[0][i] += rec[(T::F_CDS + 0 * QP + i) * CHP + pq] * wx;
-                        acc[1][i] += rec[(T::F_CDS + 1 * QP + i) * CHP + pq] * wy;
-                        acc[2][i] += rec[(T::F_CDS + 2 * QP + i) * CHP + pq] * wz;
+                    for (int m = 0; m < T::NCDS; ++m) {
+                        const double2 c2 = rec[(T::F_CDS + m) * CHP + pq];
+                        cds[2 * m] = c2.x; cds[2 * m + 1] = c2.y;
                     }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int i = 0; i < QP; ++i) acc[c][i] += cds[c * QP + i] * w3[c];
                 };
                 // the run [start, end) is contiguous (moved particles have their own key): slot g of
                 // the pass takes particles start+g, start+g+NG, ...
@@ -486,7 +497,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     // cells of a warp in the shared E/B block.)
     auto kq = deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2>;
     auto kg = deposit_general_kernel<N, NWG>;
-    const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double);
+    const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double2);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
