@@ -171,6 +171,12 @@ long pic_halo_slab_count(const pic_fab* f, int dim, int ng, int mode);
 int pic_halo_pack(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, void* stream);
 int pic_halo_unpack(const pic_fab* f, int dim, int side, int ng, int mode, const double* buf,
                     void* stream);
+/* All components of one exchange (e.g. Ex Ey Ez Bx By Bz) and both sides in ONE launch: buf_lo /
+ * buf_hi hold the slabs for the low / high neighbour concatenated in component order (nfab <= 8). */
+int pic_halo_pack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, double* buf_lo,
+                        double* buf_hi, void* stream);
+int pic_halo_unpack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, const double* buf_lo,
+                          const double* buf_hi, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Particle housekeeping  (replaces AMReX Redistribute periodic wrap and
@@ -190,6 +196,8 @@ int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* strea
  * most `capacity` entries each (counts keep counting: the caller checks for overflow). */
 int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
                            int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
+                           const int* np_dev /* NULL: p->np; else the count lives on the device and
+                                                p->np is only an upper bound for the launch */,
                            void* stream);
 
 /* Neighbour migration, steps 2 and 3 (pack / unpack phases of Redistribute).  A message is
@@ -198,14 +206,16 @@ int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cel
  * pic_migrate_unpack drops the arrivals (msg_lo from the low, msg_hi from the high neighbour) into
  * the holes left by the particles listed in idx_lo/idx_hi, appends the rest, or moves tail
  * particles into the remaining holes; work[0] receives the new particle count, work[1] a status
- * (bit 0: a list or message overflowed `cap`; bit 1: `capacity` exceeded).  p->np is the count
- * before migration. */
+ * (bit 0: a list or message overflowed `cap`; bit 1: `capacity` exceeded; bits are OR-ed into
+ * work[1], the caller clears it).  The count before migration is p->np, or *np_dev when given
+ * (np_dev may point at work[0] of the previous sweep: the sweeps of a step chain on the device and
+ * the host reads the count once). */
 long pic_migrate_message_doubles(int cap);
 long pic_migrate_workspace_bytes(int cap);
 int pic_migrate_pack(const pic_soa* p, const int* idx, const int* count, int cap, double* msg, void* stream);
 int pic_migrate_unpack(const pic_soa* p, const int* counts, const int* idx_lo, const int* idx_hi,
                        const double* msg_lo, const double* msg_hi, int cap, long capacity,
-                       void* work, void* stream);
+                       void* work, const int* np_dev /* NULL: p->np */, void* stream);
 
 /* Counting sort of the particles by cell over the valid box [box_lo,box_hi]
  * (WarpX: mypc->SortParticlesByBin, WarpXEvolve.cpp:575-580).  `in` is permuted into `out`;

@@ -79,6 +79,35 @@ __global__ void slab_kernel(FabView F, double* __restrict__ buf, Slab sl, long t
     else F(i, j, k) = buf[t];
 }
 
+// all components of an exchange in ONE launch per direction (pack) / per direction (unpack):
+// blockIdx.y = side, the x-grid walks the concatenated slabs of up to PIC_HALO_MAX_FABS components
+constexpr int HALO_MAX = 8;
+struct MultiSlab {
+    FabView v[HALO_MAX];
+    Slab sl[2][HALO_MAX];      // [side][component]
+    long off[HALO_MAX + 1];    // offsets of the components inside one side's buffer
+    int n;
+};
+__global__ void multi_slab_kernel(MultiSlab m, double* __restrict__ buf_lo, double* __restrict__ buf_hi,
+                                  int dir, int add) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m.off[m.n]) return;
+    const int side = blockIdx.y;
+    int f = 0;
+#pragma unroll
+    for (int q = 1; q < HALO_MAX; ++q) if (q < m.n && t >= m.off[q]) f = q;
+    const Slab& sl = m.sl[side][f];
+    const long tl = t - m.off[f];
+    int a, b, c;
+    decode(tl, sl.n, a, b, c);
+    const int i = sl.start[0] + a, j = sl.start[1] + b, k = sl.start[2] + c;
+    double* buf = side ? buf_hi : buf_lo;
+    const FabView& F = m.v[f];
+    if (dir == 0) buf[t] = F(i, j, k);
+    else if (add) F(i, j, k) += buf[t];
+    else F(i, j, k) = buf[t];
+}
+
 static void full_extent(const pic_fab& f, Slab& sl) {
     for (int d = 0; d < 3; ++d) { sl.start[d] = f.lo[d]; sl.n[d] = f.hi[d] - f.lo[d] + 1; }
 }
@@ -153,6 +182,47 @@ static int slab_launch(const pic_fab* f, int dim, int side, int ng, int mode, do
         make_view(*f), buf, sl, total, unpack, mode);
     count_launch();
     return check_launch("pic_halo_pack/unpack") ? 0 : 1;
+}
+
+static int multi_launch(const pic_fab* fabs, int nfab, int dim, int ng, int mode, double* buf_lo, double* buf_hi,
+                        int unpack, void* stream) {
+    PIC_REQUIRE(nfab >= 1 && nfab <= HALO_MAX, "pic_halo_*_multi: 1..%d components", HALO_MAX);
+    PIC_REQUIRE(dim >= 0 && dim < 3 && (mode == 0 || mode == 1), "pic_halo_*_multi: bad arguments");
+    MultiSlab m;
+    m.n = nfab;
+    m.off[0] = 0;
+    for (int f = 0; f < nfab; ++f) {
+        PIC_REQUIRE(ng <= fabs[f].ng[dim], "pic_halo_*_multi: ng=%d exceeds allocated guards", ng);
+        m.v[f] = make_view(fabs[f]);
+        long cnt = 0;
+        for (int side = 0; side < 2; ++side) {
+            Slab& sl = m.sl[side][f];
+            full_extent(fabs[f], sl); sl.dim = dim;
+            int first, count;
+            slab_range(fabs[f], dim, side, ng, mode, unpack, first, count);
+            sl.start[dim] = first; sl.n[dim] = count;
+            cnt = (long)sl.n[0] * sl.n[1] * sl.n[2];
+        }
+        m.off[f + 1] = m.off[f] + cnt;
+    }
+    for (int f = nfab; f < HALO_MAX; ++f) m.off[f + 1] = m.off[nfab];
+    const long total = m.off[nfab];
+    if (total == 0) return 0;
+    dim3 grid((unsigned)((total + 255) / 256), 2, 1);
+    multi_slab_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, buf_lo, buf_hi, unpack, mode);
+    count_launch();
+    return check_launch("pic_halo_pack/unpack_multi") ? 0 : 1;
+}
+
+// Pack the low-side and high-side slabs of nfab components (concatenated in component order, each
+// pic_halo_slab_count() doubles) into buf_lo / buf_hi with one launch; unpack likewise.
+extern "C" int pic_halo_pack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, double* buf_lo,
+                                   double* buf_hi, void* stream) {
+    return multi_launch(fabs, nfab, dim, ng, mode, buf_lo, buf_hi, 0, stream);
+}
+extern "C" int pic_halo_unpack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, const double* buf_lo,
+                                     const double* buf_hi, void* stream) {
+    return multi_launch(fabs, nfab, dim, ng, mode, const_cast<double*>(buf_lo), const_cast<double*>(buf_hi), 1, stream);
 }
 
 extern "C" int pic_halo_pack(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, void* stream) {

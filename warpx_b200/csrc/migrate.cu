@@ -40,15 +40,16 @@ __global__ void pack_kernel(SoaPtrs P, const int* __restrict__ idx, const int* _
     body[(long)7 * cap + j] = P.id ? __longlong_as_double((long long)P.id[ip]) : 0.0;
 }
 
-// work layout (ints): [0] np_new  [1] status  [2] #survivors  [3] #low holes
-//                     [4, 4+2cap) survivors   [.., +2cap) low holes   [.., +2cap) tail marks
+// work layout (ints): [0] np_new  [1] status (sticky)  [2] #survivors  [3] #low holes  [4] np_old  [5] np_new
+//                     [8, 8+2cap) survivors   [.., +2cap) low holes   [.., +2cap) tail marks
 struct UnpackArgs {
     SoaPtrs P;
     const int* counts;        // leaving: [0] low, [1] high
     const int* idx_lo; const int* idx_hi;
     const double* msg_lo; const double* msg_hi;   // arrivals from the low / high neighbour
-    int cap; long np_old; long capacity;
+    int cap; long np_host; const int* np_dev; long capacity;
     int* work;
+    __device__ __forceinline__ long np_old() const { return np_dev ? (long)*np_dev : np_host; }
 };
 
 __device__ __forceinline__ int hole_index(const UnpackArgs& a, int j, int n0) {
@@ -67,13 +68,15 @@ __global__ void unpack_fill_kernel(UnpackArgs a) {
     const int r0 = (int)a.msg_lo[0], r1 = (int)a.msg_hi[0];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_holes = n0 + n1, n_arr = min(r0, a.cap) + min(r1, a.cap);
+    const long np_old = a.np_old();
     if (j == 0) {
         int status = 0;
         if (a.counts[0] > a.cap || a.counts[1] > a.cap || r0 > a.cap || r1 > a.cap) status |= 1;   // list overflow
-        const long np_new = a.np_old + (long)n_arr - (long)n_holes;
+        const long np_new = np_old + (long)n_arr - (long)n_holes;
         if (np_new > a.capacity) status |= 2;                                                 // capacity
-        a.work[0] = (int)np_new;
-        a.work[1] = status;
+        a.work[4] = (int)np_old;     // kept for the follow-up kernels (work[0] may alias np_dev)
+        a.work[5] = (int)np_new;
+        a.work[1] |= status;
         a.work[2] = 0; a.work[3] = 0;
     }
     if (j >= n_arr) return;
@@ -82,7 +85,7 @@ __global__ void unpack_fill_kernel(UnpackArgs a) {
     const int jj = j < rr0 ? j : j - rr0;
     long dst;
     if (j < n_holes) dst = hole_index(a, j, n0);
-    else dst = a.np_old + (j - n_holes);
+    else dst = np_old + (j - n_holes);
     if (dst < a.capacity) write_particle(a.P, dst, body, a.cap, jj);
 }
 
@@ -92,8 +95,8 @@ __global__ void mark_tail_kernel(UnpackArgs a) {
     const int n_holes = n0 + n1, n_arr = min((int)a.msg_lo[0], a.cap) + min((int)a.msg_hi[0], a.cap);
     const int m = n_holes - n_arr;
     if (m <= 0) return;
-    const long np_new = a.np_old - m;
-    int* survivors = a.work + 4; int* lows = survivors + 2 * a.cap; int* marks = lows + 2 * a.cap;
+    const long np_new = (long)a.work[4] - m;
+    int* survivors = a.work + 8; int* lows = survivors + 2 * a.cap; int* marks = lows + 2 * a.cap;
     (void)survivors;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
@@ -105,16 +108,17 @@ __global__ void list_survivors_kernel(UnpackArgs a) {
     const int n0 = min(a.counts[0], a.cap), n1 = min(a.counts[1], a.cap);
     const int m = n0 + n1 - (min((int)a.msg_lo[0], a.cap) + min((int)a.msg_hi[0], a.cap));
     if (m <= 0) return;
-    const long np_new = a.np_old - m;
-    int* survivors = a.work + 4; int* marks = survivors + 4 * a.cap;
+    const long np_new = (long)a.work[4] - m;
+    int* survivors = a.work + 8; int* marks = survivors + 4 * a.cap;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     if (!marks[t]) survivors[atomicAdd(&a.work[2], 1)] = (int)(np_new + t);
 }
 __global__ void move_survivors_kernel(UnpackArgs a) {
     const int n = a.work[2];                              // == work[3]
-    int* survivors = a.work + 4; int* lows = survivors + 2 * a.cap;
+    int* survivors = a.work + 8; int* lows = survivors + 2 * a.cap;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) a.work[0] = a.work[5];                    // publish the new count last
     if (s >= n) return;
     const int src = survivors[s], dst = lows[s];
 #pragma unroll
@@ -127,7 +131,7 @@ __global__ void move_survivors_kernel(UnpackArgs a) {
 using namespace pic;
 
 extern "C" long pic_migrate_message_doubles(int cap) { return (long)MSG_HEADER + (long)MSG_ROWS * cap; }
-extern "C" long pic_migrate_workspace_bytes(int cap) { return (long)sizeof(int) * (4 + 6L * cap); }
+extern "C" long pic_migrate_workspace_bytes(int cap) { return (long)sizeof(int) * (8 + 6L * cap); }
 
 extern "C" int pic_migrate_pack(const pic_soa* p, const int* idx, const int* count, int cap, double* msg,
                                 void* stream) {
@@ -138,14 +142,14 @@ extern "C" int pic_migrate_pack(const pic_soa* p, const int* idx, const int* cou
 
 extern "C" int pic_migrate_unpack(const pic_soa* p, const int* counts, const int* idx_lo, const int* idx_hi,
                                   const double* msg_lo, const double* msg_hi, int cap, long capacity,
-                                  void* work, void* stream) {
+                                  void* work, const int* np_dev, void* stream) {
     UnpackArgs a;
     a.P = soa_ptrs(*p); a.counts = counts; a.idx_lo = idx_lo; a.idx_hi = idx_hi;
-    a.msg_lo = msg_lo; a.msg_hi = msg_hi; a.cap = cap; a.np_old = p->np; a.capacity = capacity;
+    a.msg_lo = msg_lo; a.msg_hi = msg_hi; a.cap = cap; a.np_host = p->np; a.np_dev = np_dev; a.capacity = capacity;
     a.work = (int*)work;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned g2 = (unsigned)((2L * cap + 255) / 256);
-    cudaMemsetAsync((int*)work + 4 + 4L * cap, 0, sizeof(int) * (size_t)(2L * cap), s);     // tail marks
+    cudaMemsetAsync((int*)work + 8 + 4L * cap, 0, sizeof(int) * (size_t)(2L * cap), s);     // tail marks
     unpack_fill_kernel<<<g2, 256, 0, s>>>(a);
     mark_tail_kernel<<<g2, 256, 0, s>>>(a);
     list_survivors_kernel<<<g2, 256, 0, s>>>(a);

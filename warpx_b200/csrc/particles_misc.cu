@@ -81,10 +81,12 @@ __global__ void sort_scatter_kernel(SoaView in, SoaView out, const uint64_t* __r
 }
 
 // which particles leave the rank's brick along one axis (cell index of the wrapped position)
-__global__ void classify_kernel(const double* __restrict__ pos, long np, double plo, double dinv, int ncell,
+__global__ void classify_kernel(const double* __restrict__ pos, long np_host, const int* __restrict__ np_dev,
+                                double plo, double dinv, int ncell,
                                 int cell_lo, int cell_hi, int both_up, int* __restrict__ counts,
                                 int* __restrict__ idx_lo, int* __restrict__ idx_hi, int capacity) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long np = np_dev ? (long)*np_dev : np_host;
     if (ip >= np) return;
     int c = (int)floor((pos[ip] - plo) * dinv);
     c = min(max(c, 0), ncell - 1);
@@ -123,14 +125,14 @@ extern "C" int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, 
 
 extern "C" int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
                                       int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
-                                      void* stream) {
+                                      const int* np_dev, void* stream) {
     PIC_REQUIRE(dim >= 0 && dim < 3, "pic_particles_classify: bad dimension");
     cudaStream_t s = (cudaStream_t)stream;
     cudaMemsetAsync(counts, 0, 2 * sizeof(int), s);
     if (p->np == 0) return 0;
     const double* pos = dim == 0 ? p->x : (dim == 1 ? p->y : p->z);
     const double dinv = 1.0 / ((g->prob_hi[dim] - g->prob_lo[dim]) / g->n_cell[dim]);
-    classify_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, s>>>(pos, p->np, g->prob_lo[dim], dinv, g->n_cell[dim],
+    classify_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, s>>>(pos, p->np, np_dev, g->prob_lo[dim], dinv, g->n_cell[dim],
                                                                   cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
     count_launch();
     return check_launch("pic_particles_classify") ? 0 : 1;

@@ -108,6 +108,16 @@ class _DeviceOps:
         s = self.sim
         check(s.L.pic_halo_unpack(C.byref(fab), dim, side, ng, mode, buf.data_ptr(), s.stream))
 
+    def pack_multi(self, fabs, dim, ng, mode, buf_lo, buf_hi):
+        s = self.sim
+        arr = (abi.pic_fab * len(fabs))(*fabs)
+        check(s.L.pic_halo_pack_multi(arr, len(fabs), dim, ng, mode, buf_lo.data_ptr(), buf_hi.data_ptr(), s.stream))
+
+    def unpack_multi(self, fabs, dim, ng, mode, buf_lo, buf_hi):
+        s = self.sim
+        arr = (abi.pic_fab * len(fabs))(*fabs)
+        check(s.L.pic_halo_unpack_multi(arr, len(fabs), dim, ng, mode, buf_lo.data_ptr(), buf_hi.data_ptr(), s.stream))
+
 
 class Species:
     NAMES = ("x", "y", "z", "w", "ux", "uy", "uz")
@@ -360,17 +370,23 @@ class Simulation:
                            idx_lo=t.empty(cap, dtype=t.int32, device=self.device),
                            idx_hi=t.empty(cap, dtype=t.int32, device=self.device),
                            s_lo=t.zeros(n, **f64), s_hi=t.zeros(n, **f64), r_lo=t.zeros(n, **f64), r_hi=t.zeros(n, **f64),
-                           work=t.zeros(self.L.pic_migrate_workspace_bytes(cap) // 4, dtype=t.int32, device=self.device))
+                           work=t.zeros(self.L.pic_migrate_workspace_bytes(cap) // 4, dtype=t.int32, device=self.device),
+                           head=t.zeros(2, dtype=t.int32).pin_memory())
         m = sp._mig
         cap = m["cap"]
+        # the particle count lives on the device (work[0]) while the sweeps chain; work[1] = sticky status
+        m["head"][0], m["head"][1] = sp.np, 0
+        m["work"][:2].copy_(m["head"], non_blocking=True)
+        np_dev = m["work"][0:1].data_ptr()
+        soa = sp.soa()
+        soa.np = sp.capacity                      # launch bound only: the kernels read the count from np_dev
         for dim in range(3):
             if self.dec.spans(dim):
                 continue
-            soa = sp.soa()
             check(self.L.pic_particles_classify(C.byref(soa), C.byref(self.geom), dim, self.box_lo[dim],
                                                 self.box_hi[dim], 1 if self.dec.nb[dim] == 2 else 0,
                                                 m["counts"].data_ptr(), m["idx_lo"].data_ptr(), m["idx_hi"].data_ptr(),
-                                                cap, self.stream))
+                                                cap, np_dev, self.stream))
             check(self.L.pic_migrate_pack(C.byref(soa), m["idx_lo"].data_ptr(), m["counts"][0:1].data_ptr(), cap,
                                           m["s_lo"].data_ptr(), self.stream))
             check(self.L.pic_migrate_pack(C.byref(soa), m["idx_hi"].data_ptr(), m["counts"][1:2].data_ptr(), cap,
@@ -378,12 +394,12 @@ class Simulation:
             parallel.exchange(self.dist, self.dec, dim, m["s_lo"], m["s_hi"], m["r_lo"], m["r_hi"])
             check(self.L.pic_migrate_unpack(C.byref(soa), m["counts"].data_ptr(), m["idx_lo"].data_ptr(),
                                             m["idx_hi"].data_ptr(), m["r_lo"].data_ptr(), m["r_hi"].data_ptr(), cap,
-                                            sp.capacity, m["work"].data_ptr(), self.stream))
-            np_new, status = (int(v) for v in m["work"][:2].tolist())       # the one host read of the sweep
-            if status:
-                raise RuntimeError("particle migration overflow on rank %d (status %d): raise capacity_factor"
-                                   % (self.rank, status))
-            sp.np = np_new
+                                            sp.capacity, m["work"].data_ptr(), np_dev, self.stream))
+        np_new, status = (int(v) for v in m["work"][:2].tolist())           # the one host read of the step
+        if status:
+            raise RuntimeError("particle migration overflow on rank %d (status %d): raise capacity_factor"
+                               % (self.rank, status))
+        sp.np = np_new
 
     def HandleParticlesAtBoundaries(self, step):
         for sp in self.species:

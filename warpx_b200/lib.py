@@ -42,11 +42,13 @@ def lib():
         "pic_halo_pack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_halo_unpack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_particles_wrap_periodic": (C.c_int, [soap, gp, vp]),
-        "pic_particles_classify": (C.c_int, [soap, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]),
+        "pic_particles_classify": (C.c_int, [soap, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp]),
+        "pic_halo_pack_multi": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+        "pic_halo_unpack_multi": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "pic_migrate_message_doubles": (C.c_long, [C.c_int]),
         "pic_migrate_workspace_bytes": (C.c_long, [C.c_int]),
         "pic_migrate_pack": (C.c_int, [soap, vp, vp, C.c_int, vp, vp]),
-        "pic_migrate_unpack": (C.c_int, [soap, vp, vp, vp, vp, vp, C.c_int, C.c_long, vp, vp]),
+        "pic_migrate_unpack": (C.c_int, [soap, vp, vp, vp, vp, vp, C.c_int, C.c_long, vp, vp, vp]),
         "pic_bins_count": (C.c_long, [ip, ip, ip]),
         "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
         "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),

@@ -116,17 +116,24 @@ class HaloExchanger:
         n = sum(counts)
         s_lo, s_hi = self._buf(("s", 0), n), self._buf(("s", 1), n)
         r_lo, r_hi = self._buf(("r", 0), n), self._buf(("r", 1), n)
-        o = 0
-        for fab, c in zip(fabs, counts):
-            self.ops.pack(fab, dim, 0, ng, mode, s_lo[o:o + c])
-            self.ops.pack(fab, dim, 1, ng, mode, s_hi[o:o + c])
-            o += c
+        fused = hasattr(self.ops, "pack_multi") and len(fabs) <= 8
+        if fused:                      # one launch for all components and both sides
+            self.ops.pack_multi(fabs, dim, ng, mode, s_lo, s_hi)
+        else:
+            o = 0
+            for fab, c in zip(fabs, counts):
+                self.ops.pack(fab, dim, 0, ng, mode, s_lo[o:o + c])
+                self.ops.pack(fab, dim, 1, ng, mode, s_hi[o:o + c])
+                o += c
         exchange(self.dist, self.dec, dim, s_lo, s_hi, r_lo, r_hi)
-        o = 0
-        for fab, c in zip(fabs, counts):
-            self.ops.unpack(fab, dim, 0, ng, mode, r_lo[o:o + c])
-            self.ops.unpack(fab, dim, 1, ng, mode, r_hi[o:o + c])
-            o += c
+        if fused:
+            self.ops.unpack_multi(fabs, dim, ng, mode, r_lo, r_hi)
+        else:
+            o = 0
+            for fab, c in zip(fabs, counts):
+                self.ops.unpack(fab, dim, 0, ng, mode, r_lo[o:o + c])
+                self.ops.unpack(fab, dim, 1, ng, mode, r_hi[o:o + c])
+                o += c
 
     def fill_boundary(self, fabs, ng):
         """FillBoundary(ng) of a list of components: guards <- valid points of the periodic image /
