@@ -76,7 +76,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(n, ppc, steps, warmup, nox=3):
+def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=True):
     """The reference algorithm on the host cores: the oracle's whole-loop driver (OpenMP, all
     cores) on a bounded sample of the workload (n^3 cells of the same plasma).  Test infrastructure
     used as the measured CPU baseline -- the only place bench.py executes oracle/."""
@@ -100,7 +100,7 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3):
     npart = len(s["x"])
     best = None
     for threads in candidates:
-        sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind)
+        sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind, use_filter=use_filter)
         sim.L.orc_set_num_threads(threads)
         sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
         sim.evolve(max(warmup, 1), synchronize_last=False)
@@ -113,9 +113,9 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3):
     dt, cores, timers = best
     return dict(value=npart * steps / dt, unit="particle-steps/s", cores=cores,
                 kind="reference-leaves+port" if kind == "reference" else "port",
-                sample="%d^3 cells x %d ppc (%d particles), order %d, %d steps, OpenMP %d threads (best of %s); "
-                       "oracle = loop-for-loop restatement of the reference CPU path"
-                       % (n, ppc[0] * ppc[1] * ppc[2], npart, nox, steps, cores, candidates),
+                sample="%d^3 cells x %d ppc (%d particles), order %d, bilinear filter %s, %d steps, OpenMP %d threads "
+                       "(best of %s); oracle = loop-for-loop restatement of the reference CPU path"
+                       % (n, ppc[0] * ppc[1] * ppc[2], npart, nox, "on" if use_filter else "off", steps, cores, candidates),
                 seconds=dt, ms_per_step=1e3 * dt / steps, timers=timers)
 
 
@@ -124,12 +124,12 @@ def run_reference(args):
     if rank != 0:
         return
     ppc = (2, 2, 2)
-    r = cpu_reference_run(args.cpu_n, ppc, args.steps, args.warmup)
+    r = cpu_reference_run(args.cpu_n, ppc, args.steps, args.warmup, use_filter=bool(args.filter))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D uniform plasma, Yee FDTD, Boris, order-3 Esirkepov, 8 ppc; CPU sample "
-                                   + r["sample"]},
+                                   + r["sample"], "use_filter": int(args.filter)},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -182,7 +182,7 @@ def run_engine(args):
 
     def make_sim(native=True):
         sim = Simulation(n_cell, prob_lo, prob_hi, nox=args.order, dist=dist, sort_interval=args.sort_interval,
-                         native_driver=native)
+                         native_driver=native, use_filter=bool(args.filter))
         sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
         return sim
 
@@ -276,6 +276,8 @@ def run_engine(args):
         "evolve_e": 96.0 * ncell,
         "gather_push": 96.0 * npart_local + 48.0 * ncell,
         "deposit": 56.0 * npart_local + 72.0 * ncell,
+        # 3 components x (filter: read + write, copy back: read + write) over the allocated J points
+        "filter": 3 * 32.0 * float(n + 1 + 2 * 5) ** 3,
     }
     try:     # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -296,15 +298,18 @@ def run_engine(args):
                 "note": "gather_push and deposit are fp64-FMA / shared-memory bound at order 3 (DESIGN.md); the "
                         "HBM fraction is reported because BASELINE.json asks for it"}
 
-    cpu = cpu_reference_run(args.cpu_n, ppc, 2, 1)
+    cpu = cpu_reference_run(args.cpu_n, ppc, 2, 1, use_filter=bool(args.filter))
     line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D uniform plasma %dx%dx%d cells (%d^3 per GPU), %d ppc (%d particles), Yee FDTD, "
                                    "Boris pusher, order-%d Esirkepov, Galerkin gather, cfl 1, u_th %gc%s, "
-                                   "cell sort every %d steps" % (n_cell + (n, args.ppc ** 3, ntot, args.order, args.u_th,
-                                                                 ", random in-cell positions" if args.jitter else "",
-                                                                 args.sort_interval)),
+                                   "bilinear current filter %s, cell sort every %d steps"
+                                   % (n_cell + (n, args.ppc ** 3, ntot, args.order, args.u_th,
+                                                ", random in-cell positions" if args.jitter else "",
+                                                "on (1 pass, the reference deck's default)" if args.filter else "off",
+                                                args.sort_interval)),
+                       "use_filter": int(args.filter),
                        "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
                                                      % (npart_local * 56 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
@@ -331,6 +336,9 @@ def main():
     ap.add_argument("--jitter", action="store_true", help="stress variant: random positions inside the cells "
                     "instead of the NUniformPerCell lattice (particles cross cell faces from step 1)")
     ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--filter", type=int, default=1, choices=[0, 1],
+                    help="warpx.use_filter: bilinear current filter, 1 pass (the default of the reference's "
+                         "uniform_plasma deck, which does not set it; WarpX.cpp:158)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

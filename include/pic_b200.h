@@ -164,6 +164,14 @@ int pic_fill_boundary_local(const pic_fab* f, int dim, int ng, const pic_geom* g
  * (WarpXComm.cpp:1386-1424 -> WarpXSumGuardCells.cpp:17-24 -> Communication.cpp:148-175). */
 int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, const pic_geom* g, void* stream);
 
+/* Bilinear (binomial) filter of one component: dst(i,j,k) = sum of the (1,2,1)/4 kernel applied
+ * npass[d] times along each direction d, over every allocated point of dst (valid + guards),
+ * src zero-padded outside its allocation.  src and dst must not alias; the caller copies dst
+ * back over src as WarpX::ApplyFilterJ does.
+ * Replaces BilinearFilter::ComputeStencils + Filter::ApplyStencil (Source/Filter/BilinearFilter.cpp:
+ * 64-88, Source/Filter/Filter.cpp:37-133) as called from WarpXComm.cpp:1357-1374. */
+int pic_apply_filter(const pic_fab* src, const pic_fab* dst, const int npass[3], void* stream);
+
 /* Neighbour (multi-GPU) versions: pack the slab that the neighbour on `side` (0 = low,
  * 1 = high) of dimension `dim` needs, and unpack what it sent.  mode 0 = copy (FillBoundary),
  * mode 1 = sum (SumBoundary).  pic_halo_slab_count returns the number of doubles. */
@@ -235,7 +243,8 @@ int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_
  * ---------------------------------------------------------------------------------------- */
 void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
                         int galerkin, int pusher, int solver, double cfl, double dt /* <=0: cfl*max_dt */,
-                        int sort_interval);
+                        int sort_interval, int use_filter /* warpx.use_filter */,
+                        const int filter_npass[3] /* warpx.filter_npass_each_dir; NULL = 1 1 1 */);
 void pic_engine_destroy(void* engine);
 double pic_engine_dt(void* engine);
 void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);

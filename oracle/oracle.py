@@ -67,7 +67,9 @@ def lib(kind="restated"):
         "orc_sum_squares_unique": (C.c_double, [fabp, C.c_int, gp]),
         "orc_checksum_cell_centered": (C.c_double, [fabp, ip, ip]),
         "orc_sim_create": (vp, [ip, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
-                                C.c_double, ip]),
+                                C.c_double, ip, C.c_int, ip]),
+        "orc_apply_filter": (None, [fabp, fabp, ip]),
+        "orc_filter_stencil": (None, [C.c_int, dp]),
         "orc_sim_destroy": (None, [vp]),
         "orc_sim_dt": (C.c_double, [vp]),
         "orc_sim_guards": (None, [vp, ip]),
@@ -145,10 +147,12 @@ class OracleSim:
     """Single-level periodic explicit-FDTD PIC run == WarpX::Evolve restated (pic_oracle.cpp)."""
 
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
-                 solver=abi.SOLVER_YEE, cfl=1.0, dt=0.0, nb=(1, 1, 1), kind="restated"):
+                 solver=abi.SOLVER_YEE, cfl=1.0, dt=0.0, nb=(1, 1, 1), kind="restated",
+                 use_filter=False, filter_npass=(1, 1, 1)):
         self.L = lib(kind)
         self.h = self.L.orc_sim_create(abi.int3(n_cell), abi.dbl3(prob_lo), abi.dbl3(prob_hi), nox,
-                                       galerkin, pusher, solver, cfl, dt, abi.int3(nb))
+                                       galerkin, pusher, solver, cfl, dt, abi.int3(nb),
+                                       1 if use_filter else 0, abi.int3(filter_npass))
         if not self.h:
             raise ValueError("bad oracle configuration")
         self.n_cell = tuple(n_cell)

@@ -42,6 +42,7 @@ struct Species {
 struct Sim {
     pic_geom geom;
     int nox, galerkin, pusher, solver;
+    int use_filter = 0, npass[3] = {1, 1, 1};      // warpx.use_filter / filter_npass_each_dir (WarpX.cpp:158,189)
     double dx[3], dinv[3], dt, cfl;
     int ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3], ng_depos_J[3];
     pic_stencil st;
@@ -77,6 +78,7 @@ void guard_cells(Sim& s) {
         s.ng_EB[d] = ng;
         s.ng_J[d] = ngt + (int)std::ceil(C_LIGHT * 0.5 * s.dt / s.dx[d]);   // :96-98,147,161
         s.ng_depos_J[d] = s.ng_J[d];                             // :165
+        if (s.use_filter) s.ng_J[d] += s.npass[d];               // + stencil_length - 1, :169-172
         s.ng_FS[d] = 1;                                          // Yee/CKC GetMaxGuardCell
         s.ng_EB[d] = std::max(s.ng_EB[d], s.ng_FS[d]);           // :297
         int fg = std::min((s.nox + 1) / 2, s.ng_EB[d]);          // :314-316
@@ -206,14 +208,27 @@ void one_step(Sim& s, bool last_step) {
             s.t_dep += now() - t0;
         }
     }
-    // ---- SyncCurrentAndRho -> SumBoundaryJ (WarpXComm.cpp:1386-1424): src = ng_depos_J,
+    // ---- SyncCurrentAndRho -> [ApplyFilterJ, WarpXComm.cpp:1233-1237,1357-1374] -> SumBoundaryJ
+    //      (:1386-1424): src = ng_depos_J (+ stencil_length-1 with the filter, :1413-1416),
     //      dst = all guards of J (WarpXSumGuardCells.cpp:22-23) ----
     t0 = now();
     {
+        int src_ng[3];
+        for (int d = 0; d < 3; ++d) src_ng[d] = std::min(s.ng_depos_J[d] + (s.use_filter ? s.npass[d] : 0), s.ng_J[d]);
+        if (s.use_filter)
+            for (auto& b : s.boxes)
+                for (int c = 6; c < 9; ++c) {
+                    std::vector<double> tmp(b.data[c].size());
+                    pic_fab dst = b.fab[c];
+                    dst.p = tmp.data();
+                    apply_filter(b.fab[c], dst, s.npass);
+                    b.data[c].swap(tmp);                         // MultiFab::Copy(J, Jf)
+                    b.fab[c].p = b.data[c].data();
+                }
         std::vector<pic_fab> fabs(s.boxes.size());
         for (int c = 6; c < 9; ++c) {
             for (size_t b = 0; b < s.boxes.size(); ++b) fabs[b] = s.boxes[b].fab[c];
-            sum_boundary(fabs.data(), (int)fabs.size(), s.ng_depos_J, s.ng_J, s.geom);
+            sum_boundary(fabs.data(), (int)fabs.size(), src_ng, s.ng_J, s.geom);
         }
     }
     s.t_halo += now() - t0;
@@ -308,6 +323,11 @@ void orc_wrap_periodic(const pic_soa* p, const pic_geom* g) { wrap_periodic(*p, 
 double orc_sum_squares_unique(const pic_fab* fabs, int nfab, const pic_geom* g) {
     return sum_squares_unique(fabs, nfab, *g);
 }
+void orc_apply_filter(const pic_fab* src, const pic_fab* dst, const int* npass) { apply_filter(*src, *dst, npass); }
+void orc_filter_stencil(int npass, double* out /* npass+1 */) {
+    const std::vector<double> st = filter_stencil(npass);
+    for (size_t n = 0; n < st.size(); ++n) out[n] = st[n];
+}
 double orc_checksum_cell_centered(const pic_fab* f, const int* box_lo, const int* box_hi) {
     return checksum_cell_centered(*f, box_lo, box_hi);
 }
@@ -315,8 +335,11 @@ double orc_checksum_cell_centered(const pic_fab* f, const int* box_lo, const int
 // ---- whole-loop driver --------------------------------------------------------------------
 // dt <= 0: dt = cfl * max_dt (WarpXComputeDt.cpp:56-95).
 void* orc_sim_create(const int* n_cell, const double* prob_lo, const double* prob_hi, int nox,
-                     int galerkin, int pusher, int solver, double cfl, double dt, const int* nb) {
+                     int galerkin, int pusher, int solver, double cfl, double dt, const int* nb,
+                     int use_filter, const int* npass) {
     auto* s = new Sim();
+    s->use_filter = use_filter;
+    for (int d = 0; d < 3; ++d) s->npass[d] = npass ? npass[d] : 1;
     for (int d = 0; d < 3; ++d) {
         s->geom.n_cell[d] = n_cell[d]; s->geom.prob_lo[d] = prob_lo[d]; s->geom.prob_hi[d] = prob_hi[d];
         s->geom.periodic[d] = 1;

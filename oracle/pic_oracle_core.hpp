@@ -434,6 +434,59 @@ inline void sum_boundary(const pic_fab* fabs, int nfab, const int src_ng[3], con
     }
 }
 
+// ============================================================================================
+// Bilinear (binomial) current filter.  Stencil: BilinearFilter.cpp:26-62 (compute_stencil: the
+// (1,2,1)/4 kernel convolved npass times, element 0 halved because it is used twice); application:
+// Filter::DoFilter, Filter/Filter.cpp:92-133 (3D), over the grown box, source zero-padded outside
+// the fab (:103-107).  dst and src must be different arrays (WarpX::ApplyFilterJ filters into a
+// temporary and copies back, Parallelization/WarpXComm.cpp:1357-1374).
+// ============================================================================================
+inline std::vector<double> filter_stencil(int npass) {
+    std::vector<double> old_s(1 + npass, 0.0), new_s(1 + npass, 0.0);
+    old_s[0] = 1.0;
+    int jmax = 1;
+    for (int ipass = 1; ipass < npass + 1; ++ipass) {
+        new_s[0] = 0.5 * old_s[0];
+        if (1 < jmax) new_s[0] += 0.5 * old_s[1];
+        for (int j = 1; j < jmax + 1; ++j) {
+            double loc = 0.5 * old_s[j];
+            loc += 0.25 * old_s[j - 1];
+            if (j < jmax) loc += 0.25 * old_s[j + 1];
+            new_s[j] = loc;
+        }
+        old_s = new_s;
+        jmax += 1;
+    }
+    old_s[0] *= 0.5;
+    return old_s;
+}
+
+inline void apply_filter(const pic_fab& src, const pic_fab& dst, const int npass[3]) {
+    const std::vector<double> s0 = filter_stencil(npass[0]), s1 = filter_stencil(npass[1]), s2 = filter_stencil(npass[2]);
+    const int l0 = npass[0] + 1, l1 = npass[1] + 1, l2 = npass[2] + 1;      // stencil_length_each_dir
+    W S(src), D(dst);
+    auto pad = [&](int i, int j, int k) -> double {
+        const bool in = i >= src.lo[0] && i <= src.hi[0] && j >= src.lo[1] && j <= src.hi[1] && k >= src.lo[2] && k <= src.hi[2];
+        return in ? S(i, j, k) : 0.0;
+    };
+#pragma omp parallel for schedule(static)
+    for (int k = dst.lo[2]; k <= dst.hi[2]; ++k)               // growntilebox: valid + guards
+        for (int j = dst.lo[1]; j <= dst.hi[1]; ++j)
+            for (int i = dst.lo[0]; i <= dst.hi[0]; ++i) {
+                double d = 0.0;
+                for (int i2 = 0; i2 < l2; ++i2)
+                    for (int i1 = 0; i1 < l1; ++i1)
+                        for (int i0 = 0; i0 < l0; ++i0) {
+                            const double sss = s0[i0] * s1[i1] * s2[i2];
+                            d += sss * (pad(i - i0, j - i1, k - i2) + pad(i + i0, j - i1, k - i2)
+                                      + pad(i - i0, j + i1, k - i2) + pad(i + i0, j + i1, k - i2)
+                                      + pad(i - i0, j - i1, k + i2) + pad(i + i0, j - i1, k + i2)
+                                      + pad(i - i0, j + i1, k + i2) + pad(i + i0, j + i1, k + i2));
+                        }
+                D(i, j, k) = d;
+            }
+}
+
 // amrex::enforcePeriodic (AMReX_ParticleUtil.H, AMReX 24.10) as applied by Redistribute
 // (WarpXEvolve.cpp:550-559): shift by the domain length until inside, then clamp round-off.
 inline void wrap_periodic(const pic_soa& P, const pic_geom& g) {

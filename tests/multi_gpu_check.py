@@ -83,22 +83,26 @@ def main():
     dec3 = parallel.Decomposition((n3,) * 3, nb, rank)
     mine = workloads.uniform_plasma_3d(n=n3, ppc=(2, 2, 2), u_th=0.05, lx=5e-6, perturbation=0.01,
                                        box_lo=dec3.box_lo, box_hi=dec3.box_hi)
-    sim3 = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, dist=dist, sort_interval=4)
     s = mine["species"][0]
-    sim3.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
-    sim3.Evolve(12)
-    e, b = sim3.field_energy()
-    npart = sim3.total_particles()
+    so = wl["species"][0]
+    for filt in (False, True):                     # warpx.use_filter = 0 / 1 (bilinear, 1 pass)
+        sim3 = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, dist=dist, sort_interval=4,
+                          use_filter=filt)
+        sim3.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+        sim3.Evolve(12)
+        e, b = sim3.field_energy()
+        npart = sim3.total_particles()
+        if rank == 0:
+            osim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, use_filter=filt)
+            osim.add_species(so["q"], so["m"], so["x"], so["y"], so["z"], so["w"], so["ux"], so["uy"], so["uz"])
+            osim.evolve(12)
+            eo, bo = osim.field_energy()
+            good = abs(e - eo) <= 1e-10 * eo and abs(b - bo) <= 1e-8 * bo and npart == len(so["x"])
+            ok &= good
+            print(f"[order3 x{world} filter={int(filt)}] field energy E {e:.12e} vs oracle {eo:.12e}; "
+                  f"B {b:.12e} vs {bo:.12e}; particles {npart}: {'ok' if good else 'FAIL'}")
+        del sim3
     if rank == 0:
-        osim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3)
-        so = wl["species"][0]
-        osim.add_species(so["q"], so["m"], so["x"], so["y"], so["z"], so["w"], so["ux"], so["uy"], so["uz"])
-        osim.evolve(12)
-        eo, bo = osim.field_energy()
-        good = abs(e - eo) <= 1e-10 * eo and abs(b - bo) <= 1e-8 * bo and npart == len(so["x"])
-        ok &= good
-        print(f"[order3 x{world}] field energy E {e:.12e} vs oracle {eo:.12e}; B {b:.12e} vs {bo:.12e}; "
-              f"particles {npart}: {'ok' if good else 'FAIL'}")
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

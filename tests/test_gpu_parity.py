@@ -291,6 +291,32 @@ def test_local_guard_cells_match_oracle(orc, dev, stag_comp):
     assert rel_linf(tens[0].cpu().numpy(), F2.a) <= 1e-14
 
 
+@pytest.mark.parametrize("npass", [(1, 1, 1), (2, 1, 3), (0, 4, 0), (0, 0, 0)])
+@pytest.mark.parametrize("stag_comp", [6, 8])
+def test_bilinear_filter_matches_oracle(orc, dev, stag_comp, npass):
+    """pic_apply_filter against the restated Filter::DoFilter over the grown box, zero padding at
+    the array edge included; the GPU folds the mirrored reads into the weights, so the tolerance
+    is a few ulp of the local magnitude (1e-14 relative to the field's max)."""
+    L = orc.lib()
+    n = (70, 9, 6)                                           # > one 64-wide block in i, ragged in j
+    box_lo, box_hi = box(n)
+    ng = (5, 5, 5)
+    src = random_fields(orc, box_lo, box_hi, ng, 31, comps=[stag_comp])[0]
+    dst = orc.HostFab(box_lo, box_hi, ng, abi.YEE_STAG[stag_comp])
+    L.orc_apply_filter(C.byref(src.desc), C.byref(dst.desc), abi.int3(npass))
+    arr, tens = dev.fabs([src, dst])
+    tens[1].fill_(7.0)                                       # every point of dst must be overwritten
+    dev.ok(dev.L.pic_apply_filter(C.byref(arr[0]), C.byref(arr[1]), abi.int3(npass), dev.stream))
+    dev.sync()
+    got = tens[1].cpu().numpy()
+    assert rel_linf(got, dst.a) <= 1e-14
+    assert np.array_equal(tens[0].cpu().numpy(), src.a)      # the source is read-only
+    if npass == (0, 0, 0):
+        assert np.array_equal(got, src.a)
+    # in-place use is refused (the reference filters into a temporary)
+    assert dev.L.pic_apply_filter(C.byref(arr[0]), C.byref(arr[0]), abi.int3(npass), dev.stream) != 0
+
+
 def test_wrap_periodic_and_field_energy(orc, dev):
     L = orc.lib()
     n = (8, 8, 8)
@@ -335,7 +361,8 @@ def _run_both(orc, cuda, wl, nox, nsteps, **kw):
     from warpx_b200.engine import Simulation
     sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, **kw)
     osim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, solver=kw.get("solver", 0),
-                         pusher=kw.get("pusher", 0))
+                         pusher=kw.get("pusher", 0), use_filter=kw.get("use_filter", False),
+                         filter_npass=kw.get("filter_npass", (1, 1, 1)))
     for s in wl["species"]:
         sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
         osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
@@ -407,6 +434,27 @@ def test_order3_loop_matches_oracle(orc, cuda, solver, pusher, native):
     e, b = sim.field_energy()
     eo, bo = osim.field_energy()
     assert e == pytest.approx(eo, rel=1e-10) and b == pytest.approx(bo, rel=1e-8)
+    A, B = _match_particles(sim, osim, 0)
+    for k in ("x", "y", "z"):
+        assert np.max(np.abs(A[k] - B[k])) / sim.dx[0] <= 1e-10
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(A[k] - B[k])) / workloads.C <= 1e-10
+
+
+@pytest.mark.parametrize("native,npass", [(True, (1, 1, 1)), (False, (1, 1, 1)), (True, (2, 1, 3))])
+def test_filtered_loop_matches_oracle(orc, cuda, native, npass):
+    """warpx.use_filter = 1 (the reference's default): J gets npass more guard cells, the bilinear
+    filter runs before SumBoundaryJ.  Same bar as the unfiltered order-3 loop."""
+    wl = workloads.uniform_plasma_3d(n=32, ppc=(2, 2, 2), u_th=0.01, lx=5e-6, perturbation=0.01)
+    sim, osim = _run_both(orc, cuda, wl, 3, 10, sort_interval=4, native_driver=native, use_filter=True,
+                          filter_npass=npass)
+    assert bool(sim.native) == native
+    assert sim.ng_J == osim.guards()["ng_J"] == [4 + v for v in npass]
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        _, oa = osim.fab(c)
+        tol = 1e-9 if c not in (3, 4, 5) else 1e-7
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= tol, abi.COMP_NAMES[c]
     A, B = _match_particles(sim, osim, 0)
     for k in ("x", "y", "z"):
         assert np.max(np.abs(A[k] - B[k])) / sim.dx[0] <= 1e-10

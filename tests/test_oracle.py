@@ -192,6 +192,57 @@ def test_decomposition_independence_of_oracle(orc):
         assert np.max(np.abs(p1[k] - p2[k])) <= 1e-11 * scale
 
 
+def test_bilinear_filter_stencil_and_properties(orc):
+    """BilinearFilter.cpp:26-62 known answers ((1,2,1)/4 per pass, first element halved), and
+    Filter.cpp:92-133 applied to a delta / a constant / zero padding at the array edge."""
+    import ctypes as C
+    L = orc.lib()
+    expect = {0: [0.5], 1: [0.25, 0.25], 2: [3 / 16, 4 / 16, 1 / 16], 3: [10 / 64, 15 / 64, 6 / 64, 1 / 64]}
+    for n, ref in expect.items():
+        out = (C.c_double * (n + 1))()
+        L.orc_filter_stencil(n, out)
+        assert list(out) == ref                           # dyadic rationals: exact
+    lo, hi, ng, stag = (0, 0, 0), (7, 7, 7), (3, 3, 3), (0, 1, 1)
+    src, dst = orc.HostFab(lo, hi, ng, stag), orc.HostFab(lo, hi, ng, stag)
+    # delta in the middle -> outer product of the 1D kernels
+    c = (7, 6, 5)
+    src.a[c] = 1.0
+    npass = (2, 1, 0)
+    L.orc_apply_filter(C.byref(src.desc), C.byref(dst.desc), abi.int3(npass))
+    k2, k1, k0 = np.array([1, 4, 6, 4, 1]) / 16, np.array([1, 2, 1]) / 4, np.array([1.0])
+    want = np.zeros_like(src.a)
+    want[c[0]:c[0] + 1, c[1] - 1:c[1] + 2, c[2] - 2:c[2] + 3] = k0[:, None, None] * k1[None, :, None] * k2[None, None, :]
+    assert np.array_equal(dst.a, want)                    # a.shape is [k, j, i]: npass[0] acts on the last axis
+    assert dst.a.sum() == 1.0
+    # constant: preserved where the stencil stays inside the array, reduced at the zero-padded rim
+    src.a[...] = 2.0
+    L.orc_apply_filter(C.byref(src.desc), C.byref(dst.desc), abi.int3((1, 1, 1)))
+    assert np.all(dst.a[1:-1, 1:-1, 1:-1] == 2.0)
+    assert dst.a[0, 0, 0] == 2.0 * 0.75 ** 3 and dst.a[0, 5, 5] == 2.0 * 0.75
+
+
+def test_filtered_loop_is_decomposition_independent(orc):
+    """use_filter=1 (the WarpX default): J guards grow by npass (GuardCellManager.cpp:169-172), the
+    filter runs per box before SumBoundaryJ; 1 box vs 2x1x2 boxes agree, and the filter matters."""
+    wl = workloads.uniform_plasma_3d(n_cell=(16, 16, 16), ppc=(1, 1, 2), u_th=0.05, lx=8e-6, perturbation=0.02)
+    sp = wl["species"][0]
+    out = {}
+    for key, nb, filt, npass in (("a", (1, 1, 1), True, (1, 1, 1)), ("b", (2, 1, 2), True, (1, 1, 1)),
+                                 ("c", (1, 1, 1), False, (1, 1, 1)), ("d", (1, 1, 1), True, (2, 1, 3)),
+                                 ("e", (1, 2, 2), True, (2, 1, 3))):
+        sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, nb=nb, use_filter=filt, filter_npass=npass)
+        g = sim.guards()
+        base = 4                                             # order 3 + ceil(c dt/2 / dx)
+        assert g["ng_J"] == ([base + n for n in npass] if filt else [base] * 3)
+        sim.add_species(sp["q"], sp["m"], sp["x"], sp["y"], sp["z"], sp["w"], sp["ux"], sp["uy"], sp["uz"])
+        sim.evolve(5)
+        out[key] = [sim.checksum_field(c) for c in range(9)]
+    for x, y in (("a", "b"), ("d", "e")):
+        for u, v in zip(out[x], out[y]):
+            assert u == pytest.approx(v, rel=1e-10)
+    assert abs(out["a"][6] - out["c"][6]) > 1e-4 * abs(out["c"][6])     # jx checksum changes with the filter
+
+
 def test_counter_based_momenta_are_decomposition_independent():
     full = workloads.uniform_plasma_3d(n_cell=(8, 8, 8), ppc=(2, 2, 2), lx=4e-6)["species"][0]
     part = workloads.uniform_plasma_3d(n_cell=(8, 8, 8), ppc=(2, 2, 2), lx=4e-6, box_lo=(4, 0, 4),

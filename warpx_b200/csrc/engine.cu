@@ -36,6 +36,9 @@ struct Engine {
     int nox, galerkin, pusher, solver, sort_interval;
     double dx[3], dinv[3], dt;
     int ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3];
+    int use_filter = 0, npass[3] = {1, 1, 1};   // warpx.use_filter / filter_npass_each_dir
+    double* filter_tmp = nullptr;               // one J-component-sized scratch array
+    size_t filter_tmp_bytes = 0;
     pic_stencil st;
     pic_fab fab[9];        // Ex Ey Ez Bx By Bz jx jy jz
     std::vector<Species> species;
@@ -76,6 +79,7 @@ static void guard_cells(Engine& e) {
         const int ngt = e.nox;
         int ng = (ngt % 2) ? ngt + 1 : ngt;
         e.ng_J[d] = ngt + (int)ceil(C_LIGHT * 0.5 * e.dt / e.dx[d]);
+        if (e.use_filter) e.ng_J[d] += e.npass[d];     // + stencil_length - 1, GuardCellManager.cpp:169-172
         e.ng_FS[d] = 1;
         ng = ng > e.ng_FS[d] ? ng : e.ng_FS[d];
         e.ng_EB[d] = ng;
@@ -103,7 +107,21 @@ static int fill_boundary(Engine& e, int c0, int c1, const int ng[3], void* s) {
 
 static int sync_current(Engine& e, void* s) {
     for (int c = 6; c < 9; ++c) {
-        for (int d = 0; d < 3; ++d) ENG_CALL(pic_sum_boundary_local(&e.fab[c], d, e.ng_J[d], &e.geom, s));   // src = ng_depos_J
+        if (e.use_filter) {
+            // WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter into a temporary over the grown box, copy back
+            const size_t bytes = sizeof(double) * (size_t)fab_size(e.fab[c]);
+            if (bytes > e.filter_tmp_bytes) {
+                if (e.filter_tmp) cudaFree(e.filter_tmp);
+                if (cudaMalloc(&e.filter_tmp, bytes) != cudaSuccess) return fail("pic_engine: filter scratch allocation failed");
+                e.filter_tmp_bytes = bytes;
+            }
+            pic_fab tmp = e.fab[c];
+            tmp.p = e.filter_tmp;
+            ENG_CALL(pic_apply_filter(&e.fab[c], &tmp, e.npass, s));
+            cudaMemcpyAsync(e.fab[c].p, tmp.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+        }
+        // src = ng_depos_J (+ stencil_length-1 with the filter, WarpXComm.cpp:1413-1416) == ng_J either way
+        for (int d = 0; d < 3; ++d) ENG_CALL(pic_sum_boundary_local(&e.fab[c], d, e.ng_J[d], &e.geom, s));
         for (int d = 0; d < 3; ++d) ENG_CALL(pic_fill_boundary_local(&e.fab[c], d, e.ng_J[d], &e.geom, s));  // all guards
     }
     return 0;
@@ -180,9 +198,11 @@ using namespace pic;
 
 extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
                                    int galerkin, int pusher, int solver, double cfl, double dt,
-                                   int sort_interval) {
+                                   int sort_interval, int use_filter, const int filter_npass[3]) {
     Engine* e = new Engine();
     e->geom = *geom;
+    e->use_filter = use_filter ? 1 : 0;
+    for (int d = 0; d < 3; ++d) e->npass[d] = filter_npass ? filter_npass[d] : 1;
     for (int d = 0; d < 3; ++d) {
         e->box_lo[d] = box_lo[d]; e->box_hi[d] = box_hi[d];
         e->dx[d] = (geom->prob_hi[d] - geom->prob_lo[d]) / geom->n_cell[d];
@@ -194,7 +214,11 @@ extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], co
     guard_cells(*e);
     return e;
 }
-extern "C" void pic_engine_destroy(void* h) { delete static_cast<Engine*>(h); }
+extern "C" void pic_engine_destroy(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e && e->filter_tmp) cudaFree(e->filter_tmp);
+    delete e;
+}
 extern "C" double pic_engine_dt(void* h) { return static_cast<Engine*>(h)->dt; }
 extern "C" void pic_engine_guards(void* h, int out[12]) {
     Engine* e = static_cast<Engine*>(h);

@@ -65,10 +65,11 @@ def max_dt(solver, dx):
     return min(dx) / C_LIGHT
 
 
-def guard_cells(nox, dt, dx):
-    """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-161, 310-343) for: no MR, no
-    NCI corrector, no moving window, no filter, not safe_guard_cells, FDTD solver."""
-    ng_EB, ng_J, ng_FG, ng_FS = [], [], [], []
+def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1)):
+    """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-172, 310-343) for: no MR, no
+    NCI corrector, no moving window, not safe_guard_cells, FDTD solver.  Returns also ng_depos_J
+    (:165) -- ng_J itself grows by stencil_length-1 = npass when the bilinear filter is on (:169-172)."""
+    ng_EB, ng_J, ng_FG, ng_FS, ng_depos_J = [], [], [], [], []
     for d in range(3):
         ngt = nox
         ng = ngt + 1 if ngt % 2 else ngt
@@ -76,8 +77,11 @@ def guard_cells(nox, dt, dx):
         fs = 1
         ng = max(ng, fs)
         fg = max(min((nox + 1) // 2, ng), fs)
+        ng_depos_J.append(ngj)
+        if use_filter:
+            ngj += filter_npass[d]
         ng_EB.append(ng); ng_J.append(ngj); ng_FG.append(fg); ng_FS.append(fs)
-    return dict(ng_EB=ng_EB, ng_J=ng_J, ng_FG=ng_FG, ng_FS=ng_FS)
+    return dict(ng_EB=ng_EB, ng_J=ng_J, ng_FG=ng_FG, ng_FS=ng_FS, ng_depos_J=ng_depos_J)
 
 
 class _DeviceOps:
@@ -160,7 +164,8 @@ class Species:
 class Simulation:
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
-                 tile=(8, 8, 8), use_bins=True, device=None, native_driver=True):
+                 tile=(8, 8, 8), use_bins=True, device=None, native_driver=True,
+                 use_filter=False, filter_npass=(1, 1, 1)):
         self.torch = require_cuda()
         t = self.torch
         self.L = lib()
@@ -177,9 +182,11 @@ class Simulation:
         self.nox, self.galerkin, self.pusher, self.solver = nox, galerkin, pusher, solver
         self.dt = dt if dt else cfl * max_dt(solver, self.dx)
         self.st = stencil_coefficients(solver, self.dx)
-        g = guard_cells(nox, self.dt, self.dx)
+        self.use_filter, self.filter_npass = bool(use_filter), tuple(int(v) for v in filter_npass)
+        g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass)
         self.ng_EB, self.ng_J, self.ng_FG, self.ng_FS = g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]
-        self.ng_depos_J = list(self.ng_J)
+        self.ng_depos_J = g["ng_depos_J"]
+        self._filter_tmp = None
         self.dec = parallel.Decomposition(self.n_cell, parallel.brick_grid(self.world), self.rank)
         self.box_lo, self.box_hi = self.dec.box_lo, self.dec.box_hi
         self.sort_interval, self.tile, self.use_bins = sort_interval, tuple(tile), use_bins
@@ -208,7 +215,8 @@ class Simulation:
         self.native = None
         if native_driver and self.world == 1 and use_bins:
             self.native = self.L.pic_engine_create(C.byref(self.geom), abi.int3(self.box_lo), abi.int3(self.box_hi),
-                                                   nox, galerkin, pusher, solver, cfl, self.dt, sort_interval)
+                                                   nox, galerkin, pusher, solver, cfl, self.dt, sort_interval,
+                                                   1 if self.use_filter else 0, abi.int3(self.filter_npass))
             g12 = (C.c_int * 12)()
             self.L.pic_engine_guards(self.native, g12)
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
@@ -305,8 +313,26 @@ class Simulation:
         self._timed("fill_boundary_eb", self.halo.fill_boundary, self.fab[0:6], ng)
 
     def SyncCurrent(self):
-        """SumBoundaryJ: src = ng_depos_J (no filter), all guards of J updated afterwards."""
-        self.halo.sum_boundary(self.fab[6:9], self.ng_depos_J, self.ng_J)
+        """[ApplyFilterJ ->] SumBoundaryJ (WarpXComm.cpp:1233-1237, 1386-1424): src = ng_depos_J
+        (+ stencil_length-1 with the filter, :1413-1416), all guards of J updated afterwards."""
+        src_ng = list(self.ng_depos_J)
+        if self.use_filter:
+            self._timed("filter", self.ApplyFilterJ)
+            src_ng = [min(a + n, b) for a, n, b in zip(self.ng_depos_J, self.filter_npass, self.ng_J)]
+        self.halo.sum_boundary(self.fab[6:9], src_ng, self.ng_J)
+
+    def ApplyFilterJ(self):
+        """WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter over the grown box into a temporary,
+        copy back (guards included)."""
+        t = self.torch
+        npass = abi.int3(self.filter_npass)
+        for c in range(6, 9):
+            if self._filter_tmp is None or self._filter_tmp.numel() < self.data[c].numel():
+                self._filter_tmp = t.empty(self.data[c].numel(), dtype=t.float64, device=self.device)
+            tmp = abi.pic_fab.from_buffer_copy(self.fab[c])
+            tmp.p = self._filter_tmp.data_ptr()
+            check(self.L.pic_apply_filter(C.byref(self.fab[c]), C.byref(tmp), npass, self.stream))
+            self.data[c].view(-1).copy_(self._filter_tmp[: self.data[c].numel()])
 
     # ---- field solver ------------------------------------------------------------------
     def EvolveB(self, dt):

@@ -38,6 +38,7 @@ def lib():
                                             C.c_double, C.c_double, C.c_int, bp, vp]),
         "pic_fill_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
         "pic_sum_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
+        "pic_apply_filter": (C.c_int, [fabp, fabp, ip, vp]),
         "pic_halo_slab_count": (C.c_long, [fabp, C.c_int, C.c_int, C.c_int]),
         "pic_halo_pack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_halo_unpack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -53,7 +54,8 @@ def lib():
         "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
         "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),
         "pic_sum_squares_unique": (C.c_int, [fabp, gp, vp, vp]),
-        "pic_engine_create": (vp, [gp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
+        "pic_engine_create": (vp, [gp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   C.c_int, ip]),
         "pic_engine_destroy": (None, [vp]),
         "pic_engine_dt": (C.c_double, [vp]),
         "pic_engine_guards": (None, [vp, ip]),
