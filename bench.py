@@ -76,7 +76,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=True):
+def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=False):
     """The reference algorithm on the host cores: the oracle's whole-loop driver (OpenMP, all
     cores) on a bounded sample of the workload (n^3 cells of the same plasma).  Test infrastructure
     used as the measured CPU baseline -- the only place bench.py executes oracle/."""
@@ -307,7 +307,7 @@ def run_engine(args):
                                    "bilinear current filter %s, cell sort every %d steps"
                                    % (n_cell + (n, args.ppc ** 3, ntot, args.order, args.u_th,
                                                 ", random in-cell positions" if args.jitter else "",
-                                                "on (1 pass, the reference deck's default)" if args.filter else "off",
+                                                "on (1 pass)" if args.filter else "off (SURVEY 8d)",
                                                 args.sort_interval)),
                        "use_filter": int(args.filter),
                        "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
@@ -336,9 +336,10 @@ def main():
     ap.add_argument("--jitter", action="store_true", help="stress variant: random positions inside the cells "
                     "instead of the NUniformPerCell lattice (particles cross cell faces from step 1)")
     ap.add_argument("--order", type=int, default=3)
-    ap.add_argument("--filter", type=int, default=1, choices=[0, 1],
-                    help="warpx.use_filter: bilinear current filter, 1 pass (the default of the reference's "
-                         "uniform_plasma deck, which does not set it; WarpX.cpp:158)")
+    ap.add_argument("--filter", type=int, default=0, choices=[0, 1],
+                    help="warpx.use_filter: bilinear current filter, 1 pass.  Off by default: SURVEY.md 8(d) "
+                         "fixes use_filter = 0 for the benchmark configurations; --filter 1 measures the "
+                         "reference's own default (WarpX.cpp:158)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

@@ -83,6 +83,19 @@ typedef struct pic_bins {
                                later (neighbour migration) are processed order-agnostically     */
 } pic_bins;
 
+/* Optional by-product of the position push: the indices of the particles whose NEW position lies
+ * outside [lo, hi] in some direction -- exactly the particles amrex enforcePeriodic will shift at
+ * the end of the step (set lo/hi to -/+inf in non-periodic directions).  Lets
+ * pic_particles_wrap_listed touch only those particles instead of re-reading every position.
+ * count is a device int the caller zeroes before the push; when more than `capacity` particles
+ * are found, count still holds the true number and the consumer falls back to a full sweep. */
+typedef struct pic_escape_list {
+    int* idx;               /* capacity entries, device                        */
+    int* count;             /* one int, device                                 */
+    int capacity;
+    double lo[3], hi[3];
+} pic_escape_list;
+
 /* Domain description for the periodic / neighbour guard-cell operations
  * (amrex::Geometry + Periodicity). */
 typedef struct pic_geom {
@@ -121,13 +134,13 @@ int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3],
  * doGatherShapeN (Gather/FieldGather.H:36-424), doParticleMomentumPush (Pusher/PushSelector.H:38-102),
  * UpdatePosition (Pusher/UpdatePosition.H:24-45).  xyzmin/lo describe the guard-grown tile box
  * (:2575-2601).  push_position = 0 gives PushP (:2368-2513; momentum only).
- * bins may be NULL. */
+ * bins may be NULL; escaped may be NULL (it is only written when push_position != 0). */
 int pic_gather_push(const pic_soa* p, long offset, long np,
                     const pic_fab E[3], const pic_fab B[3],
                     const double dinv[3], const double xyzmin[3], const int lo[3],
                     double q, double m, double dt,
                     int nox, int galerkin, int pusher, int push_position,
-                    const pic_bins* bins, void* stream);
+                    const pic_bins* bins, const pic_escape_list* escaped, void* stream);
 
 /* WarpXParticleContainer::DepositCurrent (WarpXParticleContainer.cpp:352-827) ->
  * doEsirkepovDepositionShapeN<nox> (Deposition/CurrentDeposition.H:642-907).
@@ -195,6 +208,11 @@ int pic_halo_unpack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mo
  * (WarpXEvolve.cpp:550-559 -> MultiParticleContainer.cpp:650-656; AMReX 24.10 @62c2a81
  * AMReX_ParticleUtil.H, un-vendored dependency). */
 int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, void* stream);
+
+/* Same result, but only the particles listed by the preceding pic_gather_push are visited
+ * (full sweep if the list overflowed).  Valid when every particle was inside the domain before
+ * that push, i.e. when this function (or pic_particles_wrap_periodic) ended the previous step. */
+int pic_particles_wrap_listed(const pic_soa* p, const pic_geom* g, const pic_escape_list* escaped, void* stream);
 
 /* Neighbour migration, step 1 (replaces the locate/partition phase of AMReX
  * ParticleContainer::Redistribute, WarpXEvolve.cpp:550-559): indices of the particles whose cell

@@ -189,12 +189,43 @@ def test_gather_push_matches_oracle(orc, dev, nox, galerkin, pusher, path):
             buf[0:3] += dev.t.tensor([[0.9 * dx[0]], [-0.7 * dx[1]], [0.8 * dx[2]]], device="cuda")
         host = buf.cpu().numpy()
         P = orc.HostParticles(**{k: host[i] for i, k in enumerate(orc.HostParticles.NAMES)})
+    # by-product of the position push: the particles that left the periodic domain (pic_escape_list)
+    geom = abi.make_geom(n, prob_lo, wl["prob_hi"])
+    cap = P.np if pusher == abi.PUSHER_BORIS else 3          # 3: overflow -> the consumer sweeps everything
+    esc_mem = dev.t.zeros(cap + 1, dtype=dev.t.int32, device="cuda")
+    esc = abi.pic_escape_list()
+    esc.count, esc.idx, esc.capacity = esc_mem.data_ptr(), esc_mem.data_ptr() + 4, cap
+    for d in range(3):
+        esc.lo[d], esc.hi[d] = prob_lo[d], wl["prob_hi"][d]
     for push_position in (1, 0):      # PushPX then PushP
         dev.ok(dev.L.pic_gather_push(C.byref(Pd), 0, P.np, E, B, abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
-                                     sp["q"], sp["m"], dt, nox, galerkin, pusher, push_position, bins, dev.stream))
+                                     sp["q"], sp["m"], dt, nox, galerkin, pusher, push_position, bins,
+                                     C.byref(esc), dev.stream))
         L.orc_gather_push(C.byref(P.soa), 0, P.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), abi.dbl3(dinv),
                           abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], dt, nox, galerkin, pusher, push_position)
+        if push_position:
+            dev.sync()
+            got = buf.cpu().numpy()
+            out = np.zeros(P.np, dtype=bool)
+            for d in range(3):
+                out |= (got[d] < prob_lo[d]) | (got[d] > wl["prob_hi"][d])
+            listed = esc_mem.cpu().numpy()
+            assert listed[0] == out.sum() > 0                 # PushP afterwards must not touch the list
+            if cap >= listed[0]:
+                assert np.array_equal(np.sort(listed[1:1 + listed[0]]), np.flatnonzero(out))
+            # ... and the wrap that consumes it == amrex enforcePeriodic on every particle
+            wrapped = buf.clone()
+            Pw = abi.pic_soa.from_buffer_copy(Pd)
+            for i, k in enumerate(orc.HostParticles.NAMES):
+                setattr(Pw, k, wrapped[i].data_ptr())
+            dev.ok(dev.L.pic_particles_wrap_listed(C.byref(Pw), C.byref(geom), C.byref(esc), dev.stream))
+            dev.sync()
+            Q = orc.HostParticles(**{k: got[i] for i, k in enumerate(orc.HostParticles.NAMES)})
+            L.orc_wrap_periodic(C.byref(Q.soa), C.byref(geom))
+            w = wrapped.cpu().numpy()
+            assert np.array_equal(w[0], Q.x) and np.array_equal(w[1], Q.y) and np.array_equal(w[2], Q.z)
     dev.sync()
+    assert int(esc_mem[0]) == listed[0]
     got = buf.cpu().numpy()
     for i, k in enumerate(("x", "y", "z")):
         assert np.max(np.abs(got[i] - getattr(P, k))) <= 1e-13 * lx, k
@@ -352,7 +383,7 @@ def test_preconditions_raise_like_the_reference_aborts(dev, orc):
     Pd, _ = dev.soa(P)
     rc = dev.L.pic_gather_push(C.byref(Pd), 0, 4, (abi.pic_fab * 3)(*arr[0:3]), (abi.pic_fab * 3)(*arr[3:6]),
                                abi.dbl3((1, 1, 1)), abi.dbl3((0, 0, 0)), abi.int3((0, 0, 0)), 1.0, 1.0, 1.0,
-                               7, 1, 0, 1, None, dev.stream)
+                               7, 1, 0, 1, None, None, dev.stream)
     assert rc != 0 and b"shape order" in dev.L.pic_last_error()
 
 

@@ -40,6 +40,11 @@ class pic_bins(C.Structure):
                 ("tile", C.c_int * 3), ("np_binned", C.c_long)]
 
 
+class pic_escape_list(C.Structure):
+    _fields_ = [("idx", C.c_void_p), ("count", C.c_void_p), ("capacity", C.c_int),
+                ("lo", C.c_double * 3), ("hi", C.c_double * 3)]
+
+
 class pic_geom(C.Structure):
     _fields_ = [("n_cell", C.c_int * 3), ("prob_lo", C.c_double * 3), ("prob_hi", C.c_double * 3),
                 ("periodic", C.c_int * 3)]

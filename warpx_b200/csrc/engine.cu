@@ -28,6 +28,8 @@ struct Species {
     pic_bins bins;
     bool has_bins;
     void* sort_work;
+    pic_escape_list esc;   // particles the last position push moved out of the domain (engine-owned)
+    bool has_esc;
 };
 
 struct Engine {
@@ -131,8 +133,10 @@ static int push(Engine& e, Species& sp, double dt, int push_position, void* s) {
     double xyzmin[3]; int lo[3];
     lower_corner(e, e.ng_EB, xyzmin, lo);
     const pic_soa& P = sp.buf[sp.cur];
+    if (push_position && sp.has_esc) cudaMemsetAsync(sp.esc.count, 0, sizeof(int), (cudaStream_t)s);
     return pic_gather_push(&P, 0, P.np, &e.fab[0], &e.fab[3], e.dinv, xyzmin, lo, sp.q, sp.m, dt, e.nox,
-                           e.galerkin, e.pusher, push_position, sp.has_bins ? &sp.bins : nullptr, s);
+                           e.galerkin, e.pusher, push_position, sp.has_bins ? &sp.bins : nullptr,
+                           sp.has_esc ? &sp.esc : nullptr, s);
 }
 
 static int push_particles_and_deposit(Engine& e, void* s) {
@@ -186,7 +190,9 @@ static int one_step(Engine& e, bool last, void* s) {
     // ---- HandleParticlesAtBoundaries ----
     const long step = e.istep++;
     for (auto& sp : e.species) {
-        ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
+        // amrex enforcePeriodic: only the particles the push of this step moved out of the domain
+        if (sp.has_esc) ENG_CALL(pic_particles_wrap_listed(&sp.buf[sp.cur], &e.geom, &sp.esc, s));
+        else ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
         if (sp.sort_work && e.sort_interval > 0 && (step + 1) % e.sort_interval == 0) ENG_CALL(sort_species(e, sp, s));
     }
     return 0;
@@ -217,6 +223,7 @@ extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], co
 extern "C" void pic_engine_destroy(void* h) {
     Engine* e = static_cast<Engine*>(h);
     if (e && e->filter_tmp) cudaFree(e->filter_tmp);
+    if (e) for (auto& sp : e->species) if (sp.has_esc) cudaFree(sp.esc.count);
     delete e;
 }
 extern "C" double pic_engine_dt(void* h) { return static_cast<Engine*>(h)->dt; }
@@ -243,6 +250,22 @@ extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa
     sp.bins.cell_start = cell_start;
     for (int d = 0; d < 3; ++d) sp.bins.tile[d] = tile ? tile[d] : 8;
     sp.bins.np_binned = 0;
+    // escape list: a layer of one cell next to every domain face can leave per step at most
+    sp.has_esc = false;
+    {
+        const long cap = bufA->np / 16 + 65536;
+        int* mem = nullptr;
+        if (cudaMalloc(&mem, sizeof(int) * (size_t)(cap + 1)) == cudaSuccess) {
+            sp.esc.count = mem; sp.esc.idx = mem + 1; sp.esc.capacity = (int)cap;
+            for (int d = 0; d < 3; ++d) {
+                sp.esc.lo[d] = e->geom.periodic[d] ? e->geom.prob_lo[d] : -INFINITY;
+                sp.esc.hi[d] = e->geom.periodic[d] ? e->geom.prob_hi[d] : INFINITY;
+            }
+            sp.has_esc = true;
+        } else {
+            cudaGetLastError();      // no list: the engine wraps with the full sweep
+        }
+    }
     e->species.push_back(sp);
     if (cell_start && sort_work) return sort_species(*e, e->species.back(), stream);
     return 0;

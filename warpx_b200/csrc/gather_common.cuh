@@ -13,6 +13,29 @@ struct GatherGeom {
     int stag[6][3];   // Ex Ey Ez Bx By Bz
 };
 
+// by-product of the position push: particles whose new position left [lo, hi] (pic_escape_list)
+struct EscapeView {
+    int* idx; int* count; int cap;
+    double lo[3], hi[3];
+    __device__ __forceinline__ void note(long ip, double x, double y, double z) const {
+        if (idx == nullptr) return;
+        if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) {
+            const int n = atomicAdd(count, 1);      // rare: a thin layer next to the domain faces
+            if (n < cap) idx[n] = (int)ip;
+        }
+    }
+};
+inline EscapeView make_escape(const pic_escape_list* e, int push_position) {
+    EscapeView v;
+    v.idx = nullptr; v.count = nullptr; v.cap = 0;
+    for (int d = 0; d < 3; ++d) { v.lo[d] = 0.0; v.hi[d] = 0.0; }
+    if (e && push_position) {
+        v.idx = e->idx; v.count = e->count; v.cap = e->capacity;
+        for (int d = 0; d < 3; ++d) { v.lo[d] = e->lo[d]; v.hi[d] = e->hi[d]; }
+    }
+    return v;
+}
+
 // Weights of one particle along one direction for the four (centering, order) combinations the
 // gather needs (FieldGather.H:98-121): [0] node/full, [1] cell/full, [2] node/lowered, [3] cell/lowered.
 template <int N, int G>

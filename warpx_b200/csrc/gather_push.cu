@@ -18,7 +18,7 @@ namespace pic {
 template <int N, int G, bool YEE>
 __global__ void __launch_bounds__(128)
 gather_push_global(SoaView P, long np, GlobalFields fld, GatherGeom gg, double qdt2m /*0.5*q*dt/m*/,
-                   double dt, int pusher, int push_position) {
+                   double dt, int pusher, int push_position, EscapeView esc, long ip0) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= np) return;
     double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip];
@@ -27,7 +27,7 @@ gather_push_global(SoaView P, long np, GlobalFields fld, GatherGeom gg, double q
     double ux = P.ux[ip], uy = P.uy[ip], uz = P.uz[ip];
     push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
     P.ux[ip] = ux; P.uy[ip] = uy; P.uz[ip] = uz;
-    if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; }
+    if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; esc.note(ip0 + ip, xp, yp, zp); }
 }
 
 }  // namespace pic
@@ -38,14 +38,14 @@ namespace pic {
 int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fab E[3],
                             const pic_fab B[3], const GatherGeom& gg, double qdt2m, double dt,
                             int nox, int galerkin, int pusher, int push_position,
-                            const pic_bins* bins, cudaStream_t s);
+                            const pic_bins* bins, const EscapeView& esc, cudaStream_t s);
 }
 
 extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic_fab E[3],
                                const pic_fab B[3], const double dinv[3], const double xyzmin[3],
                                const int lo[3], double q, double m, double dt, int nox,
                                int galerkin, int pusher, int push_position, const pic_bins* bins,
-                               void* stream) {
+                               const pic_escape_list* escaped, void* stream) {
     if (np == 0) return 0;                                   // PhysicalParticleContainer.cpp:2568
     PIC_REQUIRE(nox >= 1 && nox <= 3, "pic_gather_push: particle shape order %d not in 1..3", nox);
     PIC_REQUIRE(galerkin == 0 || galerkin == 1, "pic_gather_push: galerkin must be 0/1");
@@ -57,9 +57,10 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
         for (int d = 0; d < 3; ++d) { gg.stag[c][d] = E[c].stag[d]; gg.stag[3 + c][d] = B[c].stag[d]; }
     const double qdt2m = 0.5 * q * dt / m;
     cudaStream_t s = (cudaStream_t)stream;
+    const EscapeView esc = make_escape(escaped, push_position);
     if (bins) {
         if (int rc = gather_push_tile_launch(p, offset, np, E, B, gg, qdt2m, dt, nox, galerkin, pusher,
-                                             push_position, bins, s)) return rc;
+                                             push_position, bins, esc, s)) return rc;
         if (bins->np_binned >= np) return 0;
         // particles appended after the last sort (neighbour migration): order-agnostic kernel
         offset = bins->np_binned;
@@ -71,8 +72,8 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     const int tpb = 128;
     const unsigned nblk = (unsigned)((np + tpb - 1) / tpb);
     const bool yee = is_yee(E, B);
-#define PIC_GP(N, G) do { if (yee) gather_push_global<N, G, true><<<nblk, tpb, 0, s>>>(P, np, fld, gg, qdt2m, dt, pusher, push_position); \
-                          else gather_push_global<N, G, false><<<nblk, tpb, 0, s>>>(P, np, fld, gg, qdt2m, dt, pusher, push_position); } while (0)
+#define PIC_GP(N, G) do { if (yee) gather_push_global<N, G, true><<<nblk, tpb, 0, s>>>(P, np, fld, gg, qdt2m, dt, pusher, push_position, esc, offset); \
+                          else gather_push_global<N, G, false><<<nblk, tpb, 0, s>>>(P, np, fld, gg, qdt2m, dt, pusher, push_position, esc, offset); } while (0)
     if (nox == 1 && galerkin) PIC_GP(1, 1);
     else if (nox == 1) PIC_GP(1, 0);
     else if (nox == 2 && galerkin) PIC_GP(2, 1);

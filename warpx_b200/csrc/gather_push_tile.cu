@@ -47,7 +47,7 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 template <int N, int G, bool YEE, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
-                        double dt, int pusher, int push_position) {
+                        double dt, int pusher, int push_position, EscapeView esc) {
     extern __shared__ double smem[];
     constexpr bool FIXED = TX > 0;
     const int BD0 = FIXED ? TX + 2 * GT_HALO : bins.tile[0] + 2 * GT_HALO;
@@ -105,13 +105,14 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
         else gather_fields<N, G, YEE>(gf, gg, xp, yp, zp, F);
         push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
         P.ux[ip] = ux; P.uy[ip] = uy; P.uz[ip] = uz;
-        if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; }
+        if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; esc.note(ip, xp, yp, zp); }
     }
 }
 
 template <int N, int G>
 static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const GatherGeom& gg,
-                  bool yee, double qdt2m, double dt, int pusher, int push_position, cudaStream_t s) {
+                  bool yee, double qdt2m, double dt, int pusher, int push_position, const EscapeView& esc,
+                  cudaStream_t s) {
     const long bvol = (long)(bv.tile[0] + 2 * GT_HALO) * (bv.tile[1] + 2 * GT_HALO) * (bv.tile[2] + 2 * GT_HALO);
     const size_t smem = (size_t)6 * bvol * sizeof(double);
     if (smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
@@ -120,7 +121,7 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
 #define PIC_LAUNCH(YEE_, TX_, TY_, TZ_) do { \
         auto k = gather_push_tile_kernel<N, G, YEE_, TX_, TY_, TZ_>; \
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position); } while (0)
+        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc); } while (0)
     if (yee && t888) PIC_LAUNCH(true, 8, 8, 8);       // the tuned instance: immediate LDS offsets
     else if (yee) PIC_LAUNCH(true, 0, 0, 0);
     else PIC_LAUNCH(false, 0, 0, 0);
@@ -132,7 +133,7 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
 int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fab E[3],
                             const pic_fab B[3], const GatherGeom& gg, double qdt2m, double dt,
                             int nox, int galerkin, int pusher, int push_position,
-                            const pic_bins* bins, cudaStream_t s) {
+                            const pic_bins* bins, const EscapeView& esc, cudaStream_t s) {
     PIC_REQUIRE(offset == 0 && np == p->np, "pic_gather_push: bins describe the whole tile (offset 0, np = all)");
     BinsView bv = make_bins(*bins);
     bv.np_limit = (int)std::min<long>(bins->np_binned, np);   // the tile may have shrunk since the sort
@@ -140,7 +141,7 @@ int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fa
     for (int c = 0; c < 3; ++c) { gf.v[c] = make_view(E[c]); gf.v[3 + c] = make_view(B[c]); }
     SoaView P = make_soa(*p, 0);
     const bool yee = is_yee(E, B);
-#define PIC_GT(N, G) return launch<N, G>(P, bv, gf, gg, yee, qdt2m, dt, pusher, push_position, s)
+#define PIC_GT(N, G) return launch<N, G>(P, bv, gf, gg, yee, qdt2m, dt, pusher, push_position, esc, s)
     if (nox == 1 && galerkin) PIC_GT(1, 1);
     if (nox == 1) PIC_GT(1, 0);
     if (nox == 2 && galerkin) PIC_GT(2, 1);

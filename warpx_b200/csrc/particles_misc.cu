@@ -32,6 +32,20 @@ __global__ void wrap_kernel(SoaView P, long np, WrapGeom g) {
     if (g.periodic[2]) { const double v = P.z[ip], w = wrap1(v, g.lo[2], g.hi[2], g.len[2]); if (w != v) P.z[ip] = w; }
 }
 
+// the particles pic_gather_push listed (pic_escape_list); full grid-stride sweep if the list overflowed
+__global__ void wrap_listed_kernel(SoaView P, long np, WrapGeom g, const int* __restrict__ idx,
+                                   const int* __restrict__ count, int cap) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+    const int n = *count;
+    auto wrap_one = [&](long ip) {
+        if (g.periodic[0]) { const double v = P.x[ip], w = wrap1(v, g.lo[0], g.hi[0], g.len[0]); if (w != v) P.x[ip] = w; }
+        if (g.periodic[1]) { const double v = P.y[ip], w = wrap1(v, g.lo[1], g.hi[1], g.len[1]); if (w != v) P.y[ip] = w; }
+        if (g.periodic[2]) { const double v = P.z[ip], w = wrap1(v, g.lo[2], g.hi[2], g.len[2]); if (w != v) P.z[ip] = w; }
+    };
+    if (n <= cap) { for (long t = tid; t < n; t += stride) wrap_one(idx[t]); }
+    else { for (long ip = tid; ip < np; ip += stride) wrap_one(ip); }
+}
+
 struct SortGeom { double plo[3], dinv[3]; };
 
 // Warp-aggregated histogram / slot allocation: particles are nearly sorted already, so the lanes of a
@@ -121,6 +135,19 @@ extern "C" int pic_particles_wrap_periodic(const pic_soa* p, const pic_geom* g, 
     wrap_kernel<<<(unsigned)((p->np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_soa(*p, 0), p->np, wg);
     count_launch();
     return check_launch("pic_particles_wrap_periodic") ? 0 : 1;
+}
+
+extern "C" int pic_particles_wrap_listed(const pic_soa* p, const pic_geom* g, const pic_escape_list* e, void* stream) {
+    if (p->np == 0) return 0;
+    PIC_REQUIRE(e && e->idx && e->count, "pic_particles_wrap_listed: no escape list");
+    WrapGeom wg;
+    for (int d = 0; d < 3; ++d) {
+        wg.lo[d] = g->prob_lo[d]; wg.hi[d] = g->prob_hi[d]; wg.len[d] = g->prob_hi[d] - g->prob_lo[d];
+        wg.periodic[d] = g->periodic[d];
+    }
+    wrap_listed_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(make_soa(*p, 0), p->np, wg, e->idx, e->count, e->capacity);
+    count_launch();
+    return check_launch("pic_particles_wrap_listed") ? 0 : 1;
 }
 
 extern "C" int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,

@@ -141,6 +141,16 @@ class Species:
             a = arrays[name_]
             src = a if isinstance(a, t.Tensor) else t.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
             self.buf[0][n, :self.np].copy_(src, non_blocking=True)
+        # particles the position push moves out of the (periodic) domain: pic_escape_list
+        ecap = self.capacity // 16 + 65536
+        self.esc_mem = t.zeros(ecap + 1, dtype=t.int32, device=sim.device)
+        self.esc = abi.pic_escape_list()
+        self.esc.count = self.esc_mem.data_ptr()
+        self.esc.idx = self.esc_mem.data_ptr() + 4
+        self.esc.capacity = ecap
+        for d in range(3):
+            self.esc.lo[d] = sim.prob_lo[d] if sim.geom.periodic[d] else -math.inf
+            self.esc.hi[d] = sim.prob_hi[d] if sim.geom.periodic[d] else math.inf
         self.bins = None          # abi.pic_bins once sorted
         self.cell_start = None
         self.work = None
@@ -349,9 +359,11 @@ class Simulation:
     def PushPX(self, sp, dt, push_position=1):
         xyzmin, lo = self.lower_corner(self.ng_EB)          # box.grow(ngEB), PhysicalParticleContainer.cpp:2583
         soa = sp.soa()
+        if push_position:
+            sp.esc_mem[:1].zero_()
         check(self.L.pic_gather_push(C.byref(soa), 0, sp.np, self.E, self.B, abi.dbl3(self.dinv), xyzmin, lo,
                                      sp.q, sp.m, dt, self.nox, self.galerkin, self.pusher, push_position,
-                                     self._bins(sp), self.stream))
+                                     self._bins(sp), C.byref(sp.esc), self.stream))
 
     def PushP(self, dt):
         for sp in self.species:
@@ -430,8 +442,9 @@ class Simulation:
     def HandleParticlesAtBoundaries(self, step):
         for sp in self.species:
             soa = sp.soa()
-            self._timed("wrap", lambda: check(self.L.pic_particles_wrap_periodic(C.byref(soa), C.byref(self.geom),
-                                                                                  self.stream)))
+            # amrex enforcePeriodic; only the particles this step's push moved out of the domain
+            self._timed("wrap", lambda: check(self.L.pic_particles_wrap_listed(C.byref(soa), C.byref(self.geom),
+                                                                                C.byref(sp.esc), self.stream)))
             if self.world > 1:
                 self._timed("migrate", self._migrate, sp)
             if self.use_bins and self.sort_interval > 0 and (step + 1) % self.sort_interval == 0:

@@ -24,6 +24,7 @@ def lib():
                                C.POINTER(abi.pic_stencil), C.POINTER(abi.pic_geom),
                                C.POINTER(abi.pic_bins))
     dp, ip, vp = abi.c_double_p, abi.c_int_p, C.c_void_p
+    escp = C.POINTER(abi.pic_escape_list)
     sig = {
         "pic_set_error_mode": (None, [C.c_int]),
         "pic_last_error": (C.c_char_p, []),
@@ -33,7 +34,8 @@ def lib():
         "pic_evolve_b": (C.c_int, [fabp, fabp, stp, C.c_double, vp]),
         "pic_evolve_e": (C.c_int, [fabp, fabp, fabp, stp, C.c_double, vp]),
         "pic_gather_push": (C.c_int, [soap, C.c_long, C.c_long, fabp, fabp, dp, dp, ip, C.c_double,
-                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, bp, vp]),
+                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, bp, escp, vp]),
+        "pic_particles_wrap_listed": (C.c_int, [soap, gp, escp, vp]),
         "pic_deposit_esirkepov": (C.c_int, [soap, C.c_long, C.c_long, fabp, dp, dp, ip, C.c_double,
                                             C.c_double, C.c_double, C.c_int, bp, vp]),
         "pic_fill_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
