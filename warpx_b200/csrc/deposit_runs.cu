@@ -202,6 +202,38 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
         }
     };
 
+    // one particle (record column pq) of anchor k, deposited without the register window
+    auto deposit_lone = [&](int k, int pq) {
+        if (lane >= QL) return;
+        const int ax = (k & 1023), gx = ax + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
+        const int us = ring(ax);
+        double* qx = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
+        double* qy = at(Jy, gx + 1 + us, gy + 1, gz + 1 + qv);
+        double* qz = at(Jz, gx + 1 + us, gy + 1 + qv, gz + 1);
+        const double2 sx = rec[(T::F_SX + us) * CHP + pq];
+        const double2 sy = rec[(T::F_SY + qu) * CHP + pq];
+        const double2 aby = rec[(T::F_ABY + qv) * CHP + pq];
+        const double2 abz = rec[(T::F_ABZ + qv) * CHP + pq];
+        const double wx = sy.x * abz.x + sy.y * abz.y;
+        const double wy = sx.x * abz.x + sx.y * abz.y;
+        const double wz = sx.x * aby.x + sx.y * aby.y;
+#pragma unroll
+        for (int m = 0; m < T::NCDS; ++m) {
+            const double2 c2 = rec[(T::F_CDS + m) * CHP + pq];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = 2 * m + h;                 // entry e = component (e / QP), prefix index (e % QP)
+                if (e < 3 * QP) {
+                    const double cv = h ? c2.y : c2.x;
+                    const int c = e / QP, i = e % QP;
+                    if (c == 0) atomicAdd(qx + i * stX, cv * wx);
+                    else if (c == 1) atomicAdd(qy + i * stY, cv * wy);
+                    else atomicAdd(qz + i * stZ, cv * wz);
+                }
+            }
+        }
+    };
+
     // software prefetch: chunk ch+1 is requested before chunk ch is processed
     double pf[7] = {0, 0, 0, 0, 0, 0, 0};
     auto prefetch = [&](long ch) {
@@ -277,13 +309,22 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
         // ---------------- phase 2: lane = stencil lines ----------------
         {
             const int prev = __shfl_up_sync(FULL, key, 1);
+            const int next = __shfl_down_sync(FULL, key, 1);
             const bool head = (lane < nval) && (lane == 0 || key != prev);
             unsigned heads = __ballot_sync(FULL, head);
+            // A lone particle of another cell between two particles of the same (or of consecutive)
+            // cells moved there after the last sort.  As a run of its own it would retire the whole
+            // register window twice; instead its 3 x QP x QL contributions go straight to J and the
+            // surrounding run continues untouched.
+            const bool lone = lane > 0 && lane < nval - 1 && key >= 0 && prev >= 0 && next >= 0 && key != prev &&
+                              key != next && (next == prev || next == prev + 1);
+            const unsigned lones = __ballot_sync(FULL, lone);
             while (heads) {
                 const int start = __ffs(heads) - 1;
                 heads &= heads - 1;
                 const int end = heads ? (__ffs(heads) - 1) : nval;
                 const int k = __shfl_sync(FULL, key, start);
+                if ((lones >> start) & 1u) { deposit_lone(k, start); continue; }
                 if (k < 0) continue;
                 if (k != cur) {
                     if (cur >= 0 && k == cur + 1) slide();

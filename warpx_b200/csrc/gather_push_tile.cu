@@ -5,8 +5,10 @@
 // weights reach c-1..c+2, cell weights c-2..c+2 for order 3), then every particle of the supercell
 // gathers its 252 (order 3, Galerkin) grid values from shared memory.  Cell-sorted particles of
 // the same cell are adjacent lanes reading the same addresses -> shared-memory broadcasts.
-// Particles that drifted out of their supercell since the last sort gather from global memory,
-// so any particle order is correct.
+// Particles that drifted out of their supercell since the last sort are NOT gathered inline (one
+// such lane would drag its whole warp through ~250 dependent global loads -- measured +40% kernel
+// time per step since the last sort): they are appended to a list and a second, order-agnostic
+// kernel pushes them with one thread each.  Any particle order is correct.
 #include "pic_common.cuh"
 #include "gather_common.cuh"
 #include "bins.cuh"
@@ -16,6 +18,7 @@ namespace pic {
 
 constexpr int GT_HALO = 2;
 constexpr int GT_THREADS = 256;
+constexpr int GT_LOCAL_STRAYS = 1022;   // per-CTA list of particles that changed row inside the supercell
 
 // Shared-memory block of the six components.  BD* > 0: compile-time extents (the 8x8x8 supercell:
 // every stencil offset becomes an immediate of the LDS); BD0 == 0: run-time extents.
@@ -44,10 +47,12 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
+struct StrayList { int* idx; int* count; int cap; };
+
 template <int N, int G, bool YEE, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
-                        double dt, int pusher, int push_position, EscapeView esc) {
+                        double dt, int pusher, int push_position, EscapeView esc, StrayList stray) {
     extern __shared__ double smem[];
     constexpr bool FIXED = TX > 0;
     const int BD0 = FIXED ? TX + 2 * GT_HALO : bins.tile[0] + 2 * GT_HALO;
@@ -90,19 +95,74 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    for (; ip < p_end; ip += GT_THREADS) {
-        double xp = nx, yp = ny, zp = nz, ux = nux, uy = nuy, uz = nuz;
-        const int in = ip + GT_THREADS;
-        if (in < p_end) { nx = P.x[in]; ny = P.y[in]; nz = P.z[in]; nux = P.ux[in]; nuy = P.uy[in]; nuz = P.uz[in]; }
+    // Lanes of a warp hold consecutive cell-sorted particles, i.e. particles of ONE (y,z) row of
+    // cells (or two at a row end): their stencil reads hit the same few shared-memory rows and
+    // cost about one wavefront each.  A particle that changed row since the sort makes every LDS of
+    // its warp conflict; such particles (isolated row among their neighbours) are deferred to a
+    // CTA-local list and gathered after the main sweep, so the regular warps stay conflict-free.
+    __shared__ int s_stray[GT_LOCAL_STRAYS];
+    __shared__ int s_nstray;
+    if (threadIdx.x == 0) s_nstray = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    auto finish = [&](int ipp, double xp, double yp, double zp, double ux, double uy, double uz, bool in_tile) {
+        double F[6];
+        if (in_tile) gather_fields<N, G, YEE>(sf, gg, xp, yp, zp, F);
+        else gather_fields<N, G, YEE>(gf, gg, xp, yp, zp, F);      // global list full: inline, slow but correct
+        push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
+        P.ux[ipp] = ux; P.uy[ipp] = uy; P.uz[ipp] = uz;
+        if (push_position) { P.x[ipp] = xp; P.y[ipp] = yp; P.z[ipp] = zp; esc.note(ipp, xp, yp, zp); }
+    };
+    auto cell_in_tile = [&](double xp, double yp, double zp, int& row) -> bool {
         // cell of the particle (global index) from the same coordinates the gather uses
         const int ci = gg.lo[0] + (int)((xp - gg.xyzmin[0]) * gg.dinv[0]);
         const int cj = gg.lo[1] + (int)((yp - gg.xyzmin[1]) * gg.dinv[1]);
         const int ck = gg.lo[2] + (int)((zp - gg.xyzmin[2]) * gg.dinv[2]);
-        const bool in_tile = ci >= t0 && ci < t0 + bins.tile[0] && cj >= t1 && cj < t1 + bins.tile[1] &&
-                             ck >= t2 && ck < t2 + bins.tile[2];
+        row = cj * 65536 + ck;
+        return ci >= t0 && ci < t0 + bins.tile[0] && cj >= t1 && cj < t1 + bins.tile[1] &&
+               ck >= t2 && ck < t2 + bins.tile[2];
+    };
+
+    for (; ip - lane < p_end; ip += GT_THREADS) {          // warp-uniform trip count
+        const bool valid = ip < p_end;
+        double xp = nx, yp = ny, zp = nz, ux = nux, uy = nuy, uz = nuz;
+        const int in = ip + GT_THREADS;
+        if (in < p_end) { nx = P.x[in]; ny = P.y[in]; nz = P.z[in]; nux = P.ux[in]; nuy = P.uy[in]; nuz = P.uz[in]; }
+        int row = -1 - lane;
+        const bool in_tile = valid && cell_in_tile(xp, yp, zp, row);
+        const int row_prev = __shfl_up_sync(0xffffffffu, row, 1), row_next = __shfl_down_sync(0xffffffffu, row, 1);
+        const bool isolated = !(lane > 0 && row == row_prev) && !(lane < 31 && row == row_next);
+        bool now = valid;
+        if (valid && !in_tile) {                  // left the supercell since the sort: second kernel
+            const int n = atomicAdd(stray.count, 1);
+            if (n < stray.cap) { stray.idx[n] = ip; now = false; }
+        } else if (valid && isolated) {           // changed row inside the supercell: after the sweep
+            const int n = atomicAdd(&s_nstray, 1);
+            if (n < GT_LOCAL_STRAYS) { s_stray[n] = ip; now = false; }
+        }
+        __syncwarp();                             // one convergent pass through the 700-instruction body
+        if (now) finish(ip, xp, yp, zp, ux, uy, uz, in_tile);
+    }
+    __syncthreads();
+    const int nloc = min(s_nstray, GT_LOCAL_STRAYS);
+    for (int t2l = threadIdx.x; t2l < nloc; t2l += GT_THREADS) {
+        const int ipp = s_stray[t2l];
+        finish(ipp, P.x[ipp], P.y[ipp], P.z[ipp], P.ux[ipp], P.uy[ipp], P.uz[ipp], true);
+    }
+}
+
+// the listed strays, one thread each, fields through the read-only global path
+template <int N, int G, bool YEE>
+__global__ void __launch_bounds__(128)
+gather_push_listed_kernel(SoaView P, StrayList stray, GlobalFields fld, GatherGeom gg, double qdt2m, double dt,
+                          int pusher, int push_position, EscapeView esc) {
+    const int n = min(*stray.count, stray.cap);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int ip = stray.idx[t];
+        double xp = P.x[ip], yp = P.y[ip], zp = P.z[ip];
         double F[6];
-        if (in_tile) gather_fields<N, G, YEE>(sf, gg, xp, yp, zp, F);
-        else gather_fields<N, G, YEE>(gf, gg, xp, yp, zp, F);
+        gather_fields<N, G, YEE>(fld, gg, xp, yp, zp, F);
+        double ux = P.ux[ip], uy = P.uy[ip], uz = P.uz[ip];
         push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
         P.ux[ip] = ux; P.uy[ip] = uy; P.uz[ip] = uz;
         if (push_position) { P.x[ip] = xp; P.y[ip] = yp; P.z[ip] = zp; esc.note(ip, xp, yp, zp); }
@@ -115,18 +175,31 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
                   cudaStream_t s) {
     const long bvol = (long)(bv.tile[0] + 2 * GT_HALO) * (bv.tile[1] + 2 * GT_HALO) * (bv.tile[2] + 2 * GT_HALO);
     const size_t smem = (size_t)6 * bvol * sizeof(double);
-    if (smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
+    constexpr size_t static_smem = sizeof(int) * (GT_LOCAL_STRAYS + 2);       // s_stray + s_nstray
+    if (smem + static_smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
     const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
     const bool t888 = bv.tile[0] == 8 && bv.tile[1] == 8 && bv.tile[2] == 8;
+    // stray list (stream-ordered scratch): a few per mille of the particles per step since the sort
+    StrayList stray;
+    stray.cap = (int)(bv.np_limit / 8 + 1024);
+    int* scratch = nullptr;
+    if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(stray.cap + 1), s) != cudaSuccess)
+        return fail("pic_gather_push: cannot allocate %ld B of scratch", (long)(sizeof(int) * (stray.cap + 1)));
+    stray.count = scratch; stray.idx = scratch + 1;
+    cudaMemsetAsync(stray.count, 0, sizeof(int), s);
 #define PIC_LAUNCH(YEE_, TX_, TY_, TZ_) do { \
         auto k = gather_push_tile_kernel<N, G, YEE_, TX_, TY_, TZ_>; \
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc); } while (0)
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - static_smem - 1024)) != cudaSuccess) \
+            return fail("pic_gather_push: cannot raise the dynamic shared memory limit"); \
+        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc, stray); } while (0)
     if (yee && t888) PIC_LAUNCH(true, 8, 8, 8);       // the tuned instance: immediate LDS offsets
     else if (yee) PIC_LAUNCH(true, 0, 0, 0);
     else PIC_LAUNCH(false, 0, 0, 0);
 #undef PIC_LAUNCH
-    count_launch();
+    if (yee) gather_push_listed_kernel<N, G, true><<<NUM_SMS * 8, 128, 0, s>>>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc);
+    else gather_push_listed_kernel<N, G, false><<<NUM_SMS * 8, 128, 0, s>>>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc);
+    count_launch(2);
+    cudaFreeAsync(scratch, s);
     return check_launch("pic_gather_push(tile)") ? 0 : 1;
 }
 
