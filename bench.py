@@ -196,10 +196,10 @@ def run_engine(args):
     sim = make_sim()
     ntot = sim.total_particles()
     sim.Evolve(args.warmup, synchronize_last=False)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()       # before the barrier: spawning the sampler must not delay rank 0 inside the timed region
+    barrier()
     launches0 = L.pic_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

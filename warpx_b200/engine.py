@@ -400,22 +400,30 @@ class Simulation:
         entirely on the device (csrc/migrate.cu): classify -> pack into fixed-size messages ->
         NCCL send/recv -> arrivals fill the holes.  One 8-byte host read per sweep (new count)."""
         t = self.torch
-        cap = max(1 << 16, sp.capacity // 256)
+        cap_max = max(1 << 16, sp.capacity // 256)
         if getattr(sp, "_mig", None) is None:
-            n = self.L.pic_migrate_message_doubles(cap)
+            n = self.L.pic_migrate_message_doubles(cap_max)
             f64 = dict(dtype=t.float64, device=self.device)
-            sp._mig = dict(cap=cap, counts=t.zeros(2, dtype=t.int32, device=self.device),
-                           idx_lo=t.empty(cap, dtype=t.int32, device=self.device),
-                           idx_hi=t.empty(cap, dtype=t.int32, device=self.device),
+            sp._mig = dict(cap_max=cap_max, cap=cap_max, counts=t.zeros(2, dtype=t.int32, device=self.device),
+                           idx_lo=t.empty(cap_max, dtype=t.int32, device=self.device),
+                           idx_hi=t.empty(cap_max, dtype=t.int32, device=self.device),
                            s_lo=t.zeros(n, **f64), s_hi=t.zeros(n, **f64), r_lo=t.zeros(n, **f64), r_hi=t.zeros(n, **f64),
-                           work=t.zeros(self.L.pic_migrate_workspace_bytes(cap) // 4, dtype=t.int32, device=self.device),
-                           head=t.zeros(2, dtype=t.int32).pin_memory())
+                           work=t.zeros(self.L.pic_migrate_workspace_bytes(cap_max) // 4, dtype=t.int32, device=self.device),
+                           head=t.zeros(8, dtype=t.int32).pin_memory())
         m = sp._mig
+        # Messages have a fixed size (count in the header) so that no host round trip is needed
+        # before the NCCL calls.  The size adapts: every rank uses the same capacity, derived from
+        # the largest per-face count ANY rank saw in the previous step (all-reduced below), with 8x
+        # headroom; the first step uses the worst case (one full layer of cells).
         cap = m["cap"]
-        # the particle count lives on the device (work[0]) while the sweeps chain; work[1] = sticky status
-        m["head"][0], m["head"][1] = sp.np, 0
-        m["work"][:2].copy_(m["head"], non_blocking=True)
+        nmsg = self.L.pic_migrate_message_doubles(cap)
+        # the particle count lives on the device (work[0]) while the sweeps chain; work[1] = sticky
+        # status; work[6] = largest per-face count of this step
+        m["head"].zero_()
+        m["head"][0] = sp.np
+        m["work"][:8].copy_(m["head"], non_blocking=True)
         np_dev = m["work"][0:1].data_ptr()
+        peak = m["work"][6:7]
         soa = sp.soa()
         soa.np = sp.capacity                      # launch bound only: the kernels read the count from np_dev
         for dim in range(3):
@@ -425,19 +433,25 @@ class Simulation:
                                                 self.box_hi[dim], 1 if self.dec.nb[dim] == 2 else 0,
                                                 m["counts"].data_ptr(), m["idx_lo"].data_ptr(), m["idx_hi"].data_ptr(),
                                                 cap, np_dev, self.stream))
+            t.maximum(peak, m["counts"].max(), out=peak)
             check(self.L.pic_migrate_pack(C.byref(soa), m["idx_lo"].data_ptr(), m["counts"][0:1].data_ptr(), cap,
                                           m["s_lo"].data_ptr(), self.stream))
             check(self.L.pic_migrate_pack(C.byref(soa), m["idx_hi"].data_ptr(), m["counts"][1:2].data_ptr(), cap,
                                           m["s_hi"].data_ptr(), self.stream))
-            parallel.exchange(self.dist, self.dec, dim, m["s_lo"], m["s_hi"], m["r_lo"], m["r_hi"])
+            parallel.exchange(self.dist, self.dec, dim, m["s_lo"][:nmsg], m["s_hi"][:nmsg], m["r_lo"][:nmsg],
+                              m["r_hi"][:nmsg])
             check(self.L.pic_migrate_unpack(C.byref(soa), m["counts"].data_ptr(), m["idx_lo"].data_ptr(),
                                             m["idx_hi"].data_ptr(), m["r_lo"].data_ptr(), m["r_hi"].data_ptr(), cap,
                                             sp.capacity, m["work"].data_ptr(), np_dev, self.stream))
-        np_new, status = (int(v) for v in m["work"][:2].tolist())           # the one host read of the step
+        self.dist.all_reduce(peak, op=self.dist.ReduceOp.MAX)
+        head = m["work"][:8].tolist()                                       # the one host read of the step
+        np_new, status, seen = int(head[0]), int(head[1]), int(head[6])
         if status:
-            raise RuntimeError("particle migration overflow on rank %d (status %d): raise capacity_factor"
-                               % (self.rank, status))
+            raise RuntimeError("particle migration overflow on rank %d (status %d, %d particles through one face, "
+                               "message capacity %d): raise capacity_factor" % (self.rank, status, seen, cap))
         sp.np = np_new
+        want = 1 << max(14, (8 * seen + 1024).bit_length())                 # power of two >= 8 x seen, >= 16384
+        m["cap"] = min(m["cap_max"], want)
 
     def HandleParticlesAtBoundaries(self, step):
         for sp in self.species:
