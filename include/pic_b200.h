@@ -254,10 +254,24 @@ int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_
                                void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * C++ step driver (single rank, periodic): WarpX::Evolve / OneStep_nosub expressed through the
- * entry points above (csrc/engine.cu cites the reference lines of every stage).  Memory is
+ * NCCL transport (one process per GPU).  Replaces the MPI layer under
+ * ablastr::utils::communication::FillBoundary / SumBoundary (Source/ablastr/utils/Communication.cpp:
+ * 71-175) and AMReX ParticleContainer::Redistribute (Source/Evolve/WarpXEvolve.cpp:550-559).
+ * NCCL is bound at run time (libnccl.so.2 of the host process).  Bootstrap: rank 0 obtains the
+ * 128-byte id, the host broadcasts it out of band (MPI_Bcast in WarpX), every rank creates.
+ * ---------------------------------------------------------------------------------------- */
+int pic_comm_unique_id(unsigned char out[128]);
+void* pic_comm_create(const unsigned char id[128], int nranks, int rank);   /* collective; NULL on failure */
+void pic_comm_destroy(void* comm);
+
+/* ------------------------------------------------------------------------------------------
+ * C++ step driver (periodic, one brick per rank): WarpX::Evolve / OneStep_nosub expressed through
+ * the entry points above (csrc/engine.cu cites the reference lines of every stage).  Memory is
  * borrowed: fabs = Ex Ey Ez Bx By Bz jx jy jz with at least pic_engine_guards() guard cells;
- * bufA/bufB = the two particle buffers of a species (the counting sort permutes one into the other).
+ * bufA/bufB = the two particle buffers of a species (the counting sort permutes one into the
+ * other), every SoA array with `capacity` entries.  With pic_engine_set_comm (before the species
+ * are added) the guard-cell exchanges and the particle migration run over NCCL on the same stream:
+ * the brick grid is nb[0] x nb[1] x nb[2], rank = cx + nb[0]*(cy + nb[1]*cz), box = that brick.
  * ---------------------------------------------------------------------------------------- */
 void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
                         int galerkin, int pusher, int solver, double cfl, double dt /* <=0: cfl*max_dt */,
@@ -267,8 +281,9 @@ void pic_engine_destroy(void* engine);
 double pic_engine_dt(void* engine);
 void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);
 int pic_engine_set_fields(void* engine, const pic_fab fabs[9]);
+int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
 int pic_engine_add_species(void* engine, double q, double m, const pic_soa* bufA, const pic_soa* bufB,
-                           int* cell_start, const int tile[3], void* sort_work, void* stream);
+                           long capacity, int* cell_start, const int tile[3], void* sort_work, void* stream);
 int pic_engine_species_buffer(void* engine, int isp, long* np);
 int pic_engine_evolve(void* engine, int numsteps, int synchronize_last, void* stream);
 

@@ -12,10 +12,15 @@
 //   handle_particles_at_boundaries <- WarpX::HandleParticlesAtBoundaries   :533-581
 //   guard cells                  <- guardCellManager::Init                 Parallelization/GuardCellManager.cpp:62-161,310-343
 //   dt                           <- WarpX::ComputeDt                       Evolve/WarpXComputeDt.cpp:56-95
-// All memory is borrowed from the caller (fields, particle SoA double buffers, bins, scratch);
-// every stage is an asynchronous launch on the caller's stream.  Multi-rank runs keep the same
-// stage functions and interleave the neighbour exchanges from the host (warpx_b200/engine.py).
+// All memory is borrowed from the caller (fields, particle SoA double buffers, bins, sort scratch);
+// every stage is an asynchronous launch on the caller's stream.
+// Multi-rank (one process per GPU, one brick per rank, pic_engine_set_comm): the guard-cell
+// exchanges and the particle migration go through NCCL send/recv on the same stream (csrc/comm.cu),
+// as three axis sweeps with two neighbours each; the host reads 32 bytes once per step (new particle
+// count, overflow status, peak migration count).  warpx_b200/engine.py keeps a Python mirror of the
+// same sequence (torch.distributed transport) for per-stage timing and as a cross-check.
 #include "pic_common.cuh"
+#include "comm.cuh"
 #include <cmath>
 #include <vector>
 
@@ -30,6 +35,14 @@ struct Species {
     void* sort_work;
     pic_escape_list esc;   // particles the last position push moved out of the domain (engine-owned)
     bool has_esc;
+    // neighbour migration (multi-rank), engine-owned device scratch
+    long capacity = 0;           // entries of every SoA array of both buffers
+    int mig_cap_max = 0, mig_cap = 0;
+    int* mig_counts = nullptr;   // [2]
+    int* mig_idx[2] = {nullptr, nullptr};
+    double* mig_msg[4] = {nullptr, nullptr, nullptr, nullptr};   // send lo/hi, recv lo/hi
+    int* mig_work = nullptr;
+    int* mig_head = nullptr;     // pinned host, 8 ints
 };
 
 struct Engine {
@@ -46,7 +59,36 @@ struct Engine {
     std::vector<Species> species;
     bool is_synchronized = true;
     long istep = 0;
+    // multi-rank
+    Comm* comm = nullptr;
+    int nb[3] = {1, 1, 1}, coord[3] = {0, 0, 0};
+    double* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // halo send lo/hi, recv lo/hi
+    size_t hbuf_doubles = 0;
 };
+
+static bool spans(const Engine& e, int dim) { return e.comm == nullptr || e.nb[dim] == 1; }
+static int neighbour(const Engine& e, int dim, int side) {
+    int c[3] = {e.coord[0], e.coord[1], e.coord[2]};
+    c[dim] = (c[dim] + (side ? 1 : -1) + e.nb[dim]) % e.nb[dim];
+    return c[0] + e.nb[0] * (c[1] + e.nb[1] * c[2]);
+}
+
+#define ENG_NCCL(x) do { if (int rc_ = (x)) return nccl_fail("pic_engine", rc_); } while (0)
+
+// Low/high neighbour exchange along one axis.  A message travelling upwards (sent to hi, received
+// from lo) is posted first on both sides: with two bricks per axis both neighbours are the same
+// rank and NCCL matches sends and receives of a pair of ranks in posting order.
+static int exchange(Engine& e, int dim, const double* s_lo, const double* s_hi, double* r_lo, double* r_hi,
+                    size_t n, cudaStream_t s) {
+    const int lo = neighbour(e, dim, 0), hi = neighbour(e, dim, 1);
+    ENG_NCCL(g_nccl.GroupStart());
+    ENG_NCCL(g_nccl.Send(s_hi, n, PIC_NCCL_FLOAT64, hi, e.comm->comm, s));
+    ENG_NCCL(g_nccl.Recv(r_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
+    ENG_NCCL(g_nccl.Send(s_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
+    ENG_NCCL(g_nccl.Recv(r_hi, n, PIC_NCCL_FLOAT64, hi, e.comm->comm, s));
+    ENG_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
 
 static void stencil_coefficients(int solver, const double dx[3], pic_stencil* st) {
     // FiniteDifferenceSolver ctor: Yee CartesianYeeAlgorithm.H:30-42, CKC CartesianCKCAlgorithm.H:31-101
@@ -101,15 +143,41 @@ static void lower_corner(const Engine& e, const int ng[3], double xyzmin[3], int
 
 #define ENG_CALL(x) do { if (int rc_ = (x)) return rc_; } while (0)
 
+// One axis sweep of FillBoundary (mode 0) / SumBoundary (mode 1) over nfab components: local kernels
+// when this rank spans the periodic domain along dim, otherwise pack -> NCCL -> unpack(+add) with
+// one message per direction carrying the slabs of all components.
+static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng, int mode, void* s) {
+    if (ng == 0 && mode == 0) return 0;
+    if (spans(e, dim)) {
+        for (int c = 0; c < nfab; ++c) {
+            if (mode == 0) ENG_CALL(pic_fill_boundary_local(&fabs[c], dim, ng, &e.geom, s));
+            else ENG_CALL(pic_sum_boundary_local(&fabs[c], dim, ng, &e.geom, s));
+        }
+        return 0;
+    }
+    size_t n = 0;
+    for (int c = 0; c < nfab; ++c) n += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
+    if (n > e.hbuf_doubles) {
+        for (int b = 0; b < 4; ++b) {
+            if (e.hbuf[b]) cudaFree(e.hbuf[b]);
+            if (cudaMalloc(&e.hbuf[b], sizeof(double) * n) != cudaSuccess) return fail("pic_engine: halo buffer allocation failed");
+        }
+        e.hbuf_doubles = n;
+    }
+    ENG_CALL(pic_halo_pack_multi(fabs, nfab, dim, ng, mode, e.hbuf[0], e.hbuf[1], s));
+    ENG_CALL(exchange(e, dim, e.hbuf[0], e.hbuf[1], e.hbuf[2], e.hbuf[3], n, (cudaStream_t)s));
+    ENG_CALL(pic_halo_unpack_multi(fabs, nfab, dim, ng, mode, e.hbuf[2], e.hbuf[3], s));
+    return 0;
+}
+
 static int fill_boundary(Engine& e, int c0, int c1, const int ng[3], void* s) {
-    for (int c = c0; c < c1; ++c)
-        for (int d = 0; d < 3; ++d) ENG_CALL(pic_fill_boundary_local(&e.fab[c], d, ng[d], &e.geom, s));
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(e, &e.fab[c0], c1 - c0, d, ng[d], 0, s));
     return 0;
 }
 
 static int sync_current(Engine& e, void* s) {
-    for (int c = 6; c < 9; ++c) {
-        if (e.use_filter) {
+    if (e.use_filter)
+        for (int c = 6; c < 9; ++c) {
             // WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter into a temporary over the grown box, copy back
             const size_t bytes = sizeof(double) * (size_t)fab_size(e.fab[c]);
             if (bytes > e.filter_tmp_bytes) {
@@ -122,11 +190,10 @@ static int sync_current(Engine& e, void* s) {
             ENG_CALL(pic_apply_filter(&e.fab[c], &tmp, e.npass, s));
             cudaMemcpyAsync(e.fab[c].p, tmp.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
         }
-        // src = ng_depos_J (+ stencil_length-1 with the filter, WarpXComm.cpp:1413-1416) == ng_J either way
-        for (int d = 0; d < 3; ++d) ENG_CALL(pic_sum_boundary_local(&e.fab[c], d, e.ng_J[d], &e.geom, s));
-        for (int d = 0; d < 3; ++d) ENG_CALL(pic_fill_boundary_local(&e.fab[c], d, e.ng_J[d], &e.geom, s));  // all guards
-    }
-    return 0;
+    // SumBoundaryJ: src = ng_depos_J (+ stencil_length-1 with the filter, WarpXComm.cpp:1413-1416) == ng_J
+    // either way; then all guards of J are refreshed (WarpXSumGuardCells.cpp:22-23)
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(e, &e.fab[6], 3, d, e.ng_J[d], 1, s));
+    return fill_boundary(e, 6, 9, e.ng_J, s);
 }
 
 static int push(Engine& e, Species& sp, double dt, int push_position, void* s) {
@@ -165,6 +232,50 @@ static int sort_species(Engine& e, Species& sp, void* s) {
     return 0;
 }
 
+__global__ void peak_kernel(int* peak, const int* counts) { *peak = max(*peak, max(counts[0], counts[1])); }
+
+// Neighbour migration after the periodic wrap (AMReX RedistributeLocal(1), WarpXEvolve.cpp:550-559):
+// axis sweeps, classify -> pack into fixed-size messages -> NCCL -> arrivals fill the holes
+// (csrc/migrate.cu).  The particle count stays on the device (work[0]) while the sweeps chain; the
+// host reads {count, status, peak per-face count} once.  Every rank sizes the next step's messages
+// from the all-reduced peak (8x headroom); the first step uses the worst case (one layer of cells).
+static int migrate(Engine& e, Species& sp, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    pic_soa& P = sp.buf[sp.cur];
+    const int cap = sp.mig_cap;
+    const size_t nmsg = (size_t)pic_migrate_message_doubles(cap);
+    for (int n = 0; n < 8; ++n) sp.mig_head[n] = 0;
+    sp.mig_head[0] = (int)P.np;
+    cudaMemcpyAsync(sp.mig_work, sp.mig_head, 8 * sizeof(int), cudaMemcpyHostToDevice, s);
+    const int* np_dev = sp.mig_work;
+    pic_soa view = P;
+    view.np = sp.capacity;                       // launch bound only: the kernels read the count from np_dev
+    for (int dim = 0; dim < 3; ++dim) {
+        if (spans(e, dim)) continue;
+        ENG_CALL(pic_particles_classify(&view, &e.geom, dim, e.box_lo[dim], e.box_hi[dim], e.nb[dim] == 2 ? 1 : 0,
+                                        sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], cap, np_dev, s));
+        peak_kernel<<<1, 1, 0, s>>>(sp.mig_work + 6, sp.mig_counts);
+        count_launch();
+        ENG_CALL(pic_migrate_pack(&view, sp.mig_idx[0], sp.mig_counts, cap, sp.mig_msg[0], s));
+        ENG_CALL(pic_migrate_pack(&view, sp.mig_idx[1], sp.mig_counts + 1, cap, sp.mig_msg[1], s));
+        ENG_CALL(exchange(e, dim, sp.mig_msg[0], sp.mig_msg[1], sp.mig_msg[2], sp.mig_msg[3], nmsg, s));
+        ENG_CALL(pic_migrate_unpack(&view, sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], sp.mig_msg[2], sp.mig_msg[3], cap,
+                                    sp.capacity, sp.mig_work, np_dev, s));
+    }
+    ENG_NCCL(g_nccl.AllReduce(sp.mig_work + 6, sp.mig_work + 6, 1, PIC_NCCL_INT32, PIC_NCCL_MAX, e.comm->comm, s));
+    cudaMemcpyAsync(sp.mig_head, sp.mig_work, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail("pic_engine: migration failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    const int np_new = sp.mig_head[0], status = sp.mig_head[1], seen = sp.mig_head[6];
+    if (status)
+        return fail("pic_engine: particle migration overflow on rank %d (status %d, %d particles through one face, "
+                    "message capacity %d, tile capacity %ld)", e.comm->rank, status, seen, cap, sp.capacity);
+    P.np = np_new;
+    long want = 16384;
+    while (want < 8L * seen + 1024) want *= 2;
+    sp.mig_cap = (int)(want < sp.mig_cap_max ? want : sp.mig_cap_max);
+    return 0;
+}
+
 static int one_step(Engine& e, bool last, void* s) {
     // ---- ExplicitFillBoundaryEBUpdateAux ----
     if (e.is_synchronized) {
@@ -193,6 +304,7 @@ static int one_step(Engine& e, bool last, void* s) {
         // amrex enforcePeriodic: only the particles the push of this step moved out of the domain
         if (sp.has_esc) ENG_CALL(pic_particles_wrap_listed(&sp.buf[sp.cur], &e.geom, &sp.esc, s));
         else ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
+        if (e.comm) ENG_CALL(migrate(e, sp, s));
         if (sp.sort_work && e.sort_interval > 0 && (step + 1) % e.sort_interval == 0) ENG_CALL(sort_species(e, sp, s));
     }
     return 0;
@@ -223,7 +335,17 @@ extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], co
 extern "C" void pic_engine_destroy(void* h) {
     Engine* e = static_cast<Engine*>(h);
     if (e && e->filter_tmp) cudaFree(e->filter_tmp);
-    if (e) for (auto& sp : e->species) if (sp.has_esc) cudaFree(sp.esc.count);
+    if (e) {
+        for (auto& sp : e->species) {
+            if (sp.has_esc) cudaFree(sp.esc.count);
+            if (sp.mig_counts) cudaFree(sp.mig_counts);
+            for (int b = 0; b < 2; ++b) if (sp.mig_idx[b]) cudaFree(sp.mig_idx[b]);
+            for (int b = 0; b < 4; ++b) if (sp.mig_msg[b]) cudaFree(sp.mig_msg[b]);
+            if (sp.mig_work) cudaFree(sp.mig_work);
+            if (sp.mig_head) cudaFreeHost(sp.mig_head);
+        }
+        for (int b = 0; b < 4; ++b) if (e->hbuf[b]) cudaFree(e->hbuf[b]);
+    }
     delete e;
 }
 extern "C" double pic_engine_dt(void* h) { return static_cast<Engine*>(h)->dt; }
@@ -243,9 +365,12 @@ extern "C" int pic_engine_set_fields(void* h, const pic_fab fabs[9]) {
 }
 // bufA holds the particles; bufB is the sort target.  cell_start / sort_work may be NULL (no bins).
 extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa* bufA, const pic_soa* bufB,
-                                      int* cell_start, const int tile[3], void* sort_work, void* stream) {
+                                      long capacity, int* cell_start, const int tile[3], void* sort_work,
+                                      void* stream) {
     Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(capacity >= bufA->np, "pic_engine_add_species: capacity %ld < np %ld", capacity, (long)bufA->np);
     Species sp;
+    sp.capacity = capacity;
     sp.q = q; sp.m = m; sp.buf[0] = *bufA; sp.buf[1] = *bufB; sp.cur = 0; sp.has_bins = false; sp.sort_work = sort_work;
     sp.bins.cell_start = cell_start;
     for (int d = 0; d < 3; ++d) sp.bins.tile[d] = tile ? tile[d] : 8;
@@ -253,7 +378,7 @@ extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa
     // escape list: a layer of one cell next to every domain face can leave per step at most
     sp.has_esc = false;
     {
-        const long cap = bufA->np / 16 + 65536;
+        const long cap = capacity / 16 + 65536;
         int* mem = nullptr;
         if (cudaMalloc(&mem, sizeof(int) * (size_t)(cap + 1)) == cudaSuccess) {
             sp.esc.count = mem; sp.esc.idx = mem + 1; sp.esc.capacity = (int)cap;
@@ -266,8 +391,43 @@ extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa
             cudaGetLastError();      // no list: the engine wraps with the full sweep
         }
     }
+    if (e->comm) {
+        // migration scratch; worst case per face and step = one full layer of cells ~ capacity/256
+        sp.mig_cap_max = (int)(capacity / 256 > 65536 ? capacity / 256 : 65536);
+        sp.mig_cap = sp.mig_cap_max;
+        const size_t nmsg = (size_t)pic_migrate_message_doubles(sp.mig_cap_max);
+        bool ok = cudaMalloc(&sp.mig_counts, 2 * sizeof(int)) == cudaSuccess;
+        for (int b = 0; b < 2 && ok; ++b) ok = cudaMalloc(&sp.mig_idx[b], sizeof(int) * (size_t)sp.mig_cap_max) == cudaSuccess;
+        for (int b = 0; b < 4 && ok; ++b) ok = cudaMalloc(&sp.mig_msg[b], sizeof(double) * nmsg) == cudaSuccess;
+        ok = ok && cudaMalloc(&sp.mig_work, (size_t)pic_migrate_workspace_bytes(sp.mig_cap_max)) == cudaSuccess;
+        ok = ok && cudaMallocHost(&sp.mig_head, 8 * sizeof(int)) == cudaSuccess;
+        if (!ok) return fail("pic_engine_add_species: cannot allocate the migration buffers");
+        for (int b = 0; b < 4; ++b) cudaMemsetAsync(sp.mig_msg[b], 0, sizeof(double) * nmsg, (cudaStream_t)stream);
+        cudaMemsetAsync(sp.mig_work, 0, (size_t)pic_migrate_workspace_bytes(sp.mig_cap_max), (cudaStream_t)stream);
+    }
     e->species.push_back(sp);
     if (cell_start && sort_work) return sort_species(*e, e->species.back(), stream);
+    return 0;
+}
+// Multi-rank: this rank's brick is box_lo..box_hi of pic_engine_create, rank = coord[0] + nb[0]*(coord[1]
+// + nb[1]*coord[2]) in the communicator (pic_comm_create).  Call before pic_engine_add_species.
+extern "C" int pic_engine_set_comm(void* h, void* comm, const int nb[3]) {
+    Engine* e = static_cast<Engine*>(h);
+    Comm* c = static_cast<Comm*>(comm);
+    PIC_REQUIRE(c && c->comm, "pic_engine_set_comm: no communicator");
+    PIC_REQUIRE(nb[0] * nb[1] * nb[2] == c->nranks, "pic_engine_set_comm: brick grid %dx%dx%d != %d ranks", nb[0], nb[1], nb[2], c->nranks);
+    PIC_REQUIRE(e->species.empty(), "pic_engine_set_comm: call before pic_engine_add_species");
+    e->comm = c;
+    int r = c->rank;
+    for (int d = 0; d < 3; ++d) {
+        e->nb[d] = nb[d];
+        e->coord[d] = r % nb[d];
+        r /= nb[d];
+        const int width = e->geom.n_cell[d] / nb[d];
+        PIC_REQUIRE(width * nb[d] == e->geom.n_cell[d] && e->box_lo[d] == e->coord[d] * width &&
+                    e->box_hi[d] == e->box_lo[d] + width - 1,
+                    "pic_engine_set_comm: box [%d,%d] along %d is not brick %d of %d", e->box_lo[d], e->box_hi[d], d, e->coord[d], nb[d]);
+    }
     return 0;
 }
 // which of the two buffers currently holds species isp, and its particle count

@@ -20,6 +20,7 @@ There is no CPU path: constructing a Simulation without a CUDA device raises.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -219,11 +220,14 @@ class Simulation:
         self.istep = 0
         self._scratch = t.zeros(8, dtype=t.float64, device=self.device)
         self.stage_events = None      # {stage: [(start, end), ...]} when enable_stage_timing() is on
-        # Single rank: the step sequence runs in the library's C++ driver (csrc/engine.cu); this
-        # Python mirror of the same sequence is used for multi-rank runs (it interleaves the NCCL
-        # exchanges) and when per-stage timing is requested.
+        # The step sequence runs in the library's C++ driver (csrc/engine.cu); with several ranks it
+        # exchanges guard cells and particles over its own NCCL communicator (csrc/comm.cu; the
+        # 128-byte id is broadcast through torch.distributed, the only thing torch transports then).
+        # This Python mirror of the same sequence is used when per-stage timing is requested
+        # (native_driver=False) and as a cross-check of the C++ driver in the tests.
         self.native = None
-        if native_driver and self.world == 1 and use_bins:
+        self.comm = None
+        if native_driver and use_bins and (self.world == 1 or os.environ.get("PIC_NATIVE_NCCL", "1") != "0"):
             self.native = self.L.pic_engine_create(C.byref(self.geom), abi.int3(self.box_lo), abi.int3(self.box_hi),
                                                    nox, galerkin, pusher, solver, cfl, self.dt, sort_interval,
                                                    1 if self.use_filter else 0, abi.int3(self.filter_npass))
@@ -231,12 +235,28 @@ class Simulation:
             self.L.pic_engine_guards(self.native, g12)
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
             assert self.L.pic_engine_dt(self.native) == self.dt
+            if self.world > 1:
+                ident = t.zeros(128, dtype=t.uint8, device=self.device)
+                if self.rank == 0:
+                    raw = (C.c_ubyte * 128)()
+                    check(self.L.pic_comm_unique_id(raw))
+                    ident.copy_(t.tensor(list(raw), dtype=t.uint8))
+                dist.broadcast(ident, 0)
+                raw = (C.c_ubyte * 128)(*ident.cpu().tolist())
+                t.cuda.synchronize()
+                self.comm = self.L.pic_comm_create(raw, self.world, self.rank)
+                if not self.comm:
+                    raise RuntimeError(self.L.pic_last_error().decode())
+                check(self.L.pic_engine_set_comm(self.native, self.comm, abi.int3(self.dec.nb)))
             check(self.L.pic_engine_set_fields(self.native, (abi.pic_fab * 9)(*self.fab)))
 
     def __del__(self):
         if getattr(self, "native", None):
             self.L.pic_engine_destroy(self.native)
             self.native = None
+        if getattr(self, "comm", None):
+            self.L.pic_comm_destroy(self.comm)
+            self.comm = None
 
     def enable_stage_timing(self, on=True):
         """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""
@@ -274,8 +294,9 @@ class Simulation:
         if self.native:
             self._alloc_sort_scratch(sp)
             a, b = sp.soa(0), sp.soa(1)
-            check(self.L.pic_engine_add_species(self.native, q, m, C.byref(a), C.byref(b), sp.cell_start.data_ptr(),
-                                                abi.int3(self.tile), sp.work.data_ptr(), self.stream))
+            check(self.L.pic_engine_add_species(self.native, q, m, C.byref(a), C.byref(b), sp.capacity,
+                                                sp.cell_start.data_ptr(), abi.int3(self.tile), sp.work.data_ptr(),
+                                                self.stream))
             self._sync_from_native()
         elif self.use_bins:
             self.SortParticlesByBin(sp)

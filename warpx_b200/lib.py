@@ -62,7 +62,11 @@ def lib():
         "pic_engine_dt": (C.c_double, [vp]),
         "pic_engine_guards": (None, [vp, ip]),
         "pic_engine_set_fields": (C.c_int, [vp, fabp]),
-        "pic_engine_add_species": (C.c_int, [vp, C.c_double, C.c_double, soap, soap, vp, ip, vp, vp]),
+        "pic_engine_add_species": (C.c_int, [vp, C.c_double, C.c_double, soap, soap, C.c_long, vp, ip, vp, vp]),
+        "pic_engine_set_comm": (C.c_int, [vp, vp, ip]),
+        "pic_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+        "pic_comm_create": (vp, [C.POINTER(C.c_ubyte), C.c_int, C.c_int]),
+        "pic_comm_destroy": (None, [vp]),
         "pic_engine_species_buffer": (C.c_int, [vp, C.c_int, C.POINTER(C.c_long)]),
         "pic_engine_evolve": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     }
