@@ -105,6 +105,42 @@ typedef struct pic_geom {
     int periodic[3];
 } pic_geom;
 
+/* Boundary types per domain face == WarpX::field_boundary_lo/hi (FieldBoundaryType) and
+ * particle_boundary_lo/hi (ParticleBoundaryType), Source/Utils/WarpXAlgorithmSelection.H;
+ * parsed from boundary.field_lo/hi, boundary.particle_lo/hi (Source/Utils/WarpXUtil.cpp:470-540).
+ * A periodic field face implies a periodic particle face.  Supported subset: periodic / PEC fields,
+ * periodic / absorbing / reflecting particles. */
+enum { PIC_FIELD_PERIODIC = 0, PIC_FIELD_PEC = 1 };
+enum { PIC_PARTICLE_PERIODIC = 0, PIC_PARTICLE_ABSORBING = 1, PIC_PARTICLE_REFLECTING = 2 };
+typedef struct pic_boundaries {
+    int field_lo[3], field_hi[3];
+    int particle_lo[3], particle_hi[3];
+} pic_boundaries;
+
+/* Laser antenna with the Gaussian profile == LaserParticleContainer (Source/Particles/
+ * LaserParticleContainer.cpp:84-270: position, direction, polarization, wavelength, e_max) +
+ * GaussianLaserProfile (Source/Laser/LaserProfilesImpl/LaserProfileGaussian.cpp:32-86:
+ * profile_waist, profile_duration, profile_t_peak, profile_focal_distance, phi0; the
+ * spatio-temporal couplings zeta, beta, phi2 are 0).  Lab frame (gamma_boost = 1). */
+typedef struct pic_laser_antenna {
+    double position[3];     /* a point of the antenna plane                    */
+    double nvec[3];         /* plane normal = propagation direction (normalised by the library) */
+    double p_X[3];          /* main polarisation vector (normalised by the library)             */
+    double wavelength, e_max;
+    double waist, duration, t_peak, focal_distance, phi0;
+} pic_laser_antenna;
+
+/* Plasma injector of one species: NUniformPerCell positions (InjectorPositionRegular,
+ * Source/Initialization/InjectorPosition.H:67-108), constant density, momentum at rest
+ * (<species>.injection_style / num_particles_per_cell_each_dim / xmin..zmax / profile = constant /
+ * momentum_distribution_type = at_rest / do_continuous_injection of Source/Initialization/PlasmaInjector.cpp). */
+typedef struct pic_plasma_injector {
+    int ppc[3];
+    double bound_lo[3], bound_hi[3];   /* xmin,ymin,zmin / xmax,ymax,zmax (+-inf when unset) */
+    double density;
+    int do_continuous_injection;
+} pic_plasma_injector;
+
 enum { PIC_ERR_ABORT = 0, PIC_ERR_RETURN = 1 };
 void pic_set_error_mode(int mode);
 const char* pic_last_error(void);

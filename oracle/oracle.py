@@ -83,6 +83,20 @@ def lib(kind="restated"):
         "orc_sim_checksum_field": (C.c_double, [vp, C.c_int]),
         "orc_sim_field_energy": (None, [vp, dp]),
         "orc_sim_timers": (None, [vp, dp]),
+        "orc_sim_set_boundaries": (C.c_int, [vp, C.POINTER(abi.pic_boundaries)]),
+        "orc_sim_set_moving_window": (C.c_int, [vp, C.c_int, C.c_double]),
+        "orc_sim_add_plasma": (C.c_int, [vp, C.c_double, C.c_double, C.POINTER(abi.pic_plasma_injector)]),
+        "orc_sim_add_laser": (C.c_int, [vp, C.POINTER(abi.pic_laser_antenna)]),
+        "orc_sim_laser_np": (C.c_long, [vp, C.c_int]),
+        "orc_sim_get_laser_particles": (None, [vp, C.c_int, C.c_int, dp]),
+        "orc_sim_laser_info": (None, [vp, C.c_int, dp]),
+        "orc_sim_get_z_inj": (None, [vp, C.c_int, dp]),
+        "orc_sim_time": (C.c_double, [vp]),
+        "orc_sim_prob_domain": (None, [vp, dp]),
+        "orc_apply_pec_field": (None, [fabp, C.c_int, gp, C.POINTER(abi.pic_boundaries), ip]),
+        "orc_apply_pec_current": (None, [fabp, gp, C.POINTER(abi.pic_boundaries)]),
+        "orc_shift_fab": (None, [fabp, gp, C.c_int, C.c_int, C.c_double]),
+        "orc_antenna_push": (None, [C.POINTER(abi.pic_laser_antenna), dp, soap, C.c_double, C.c_double]),
         "orc_num_threads": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
     }
@@ -174,6 +188,51 @@ class OracleSim:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, w, ux, uy, uz)]
         self.nspecies += 1
         return self.L.orc_sim_add_species(self.h, q, m, len(arrs[0]), *[_dp(a) for a in arrs])
+
+    # ---- laser-wakefield additions (single box; configure before adding particles) ----
+    def set_boundaries(self, bnd):
+        rc = self.L.orc_sim_set_boundaries(self.h, C.byref(bnd))
+        if rc:
+            raise ValueError("orc_sim_set_boundaries: %d" % rc)
+
+    def set_moving_window(self, direction, v_over_c):
+        rc = self.L.orc_sim_set_moving_window(self.h, direction, v_over_c)
+        if rc:
+            raise ValueError("orc_sim_set_moving_window: %d" % rc)
+
+    def add_plasma(self, q, m, injector):
+        self.nspecies += 1
+        return self.L.orc_sim_add_plasma(self.h, q, m, C.byref(injector))
+
+    def add_laser(self, laser):
+        return self.L.orc_sim_add_laser(self.h, C.byref(laser))
+
+    def laser_particles(self, il):
+        n = self.L.orc_sim_laser_np(self.h, il)
+        out = {}
+        for c, name in enumerate(HostParticles.NAMES):
+            a = np.empty(n)
+            self.L.orc_sim_get_laser_particles(self.h, il, c, _dp(a))
+            out[name] = a
+        return out
+
+    def laser_info(self, il):
+        out = (C.c_double * 4)()
+        self.L.orc_sim_laser_info(self.h, il, out)
+        return dict(zip(("S_X", "S_Y", "mobility", "weight"), list(out)))
+
+    def z_at_injection(self, isp):
+        a = np.empty(self.L.orc_sim_np(self.h, isp))
+        self.L.orc_sim_get_z_inj(self.h, isp, _dp(a))
+        return a
+
+    def time(self):
+        return self.L.orc_sim_time(self.h)
+
+    def prob_domain(self):
+        out = (C.c_double * 6)()
+        self.L.orc_sim_prob_domain(self.h, out)
+        return list(out[0:3]), list(out[3:6])
 
     def evolve(self, nsteps, synchronize_last=True):
         self.L.orc_sim_evolve(self.h, nsteps, 1 if synchronize_last else 0)

@@ -15,6 +15,7 @@ using Leaf = orc::LeafReference;
 using Leaf = orc::LeafRestated;
 #endif
 #include "pic_oracle_core.hpp"
+#include "pic_oracle_lwfa.hpp"
 
 #include <array>
 #include <chrono>
@@ -28,6 +29,12 @@ namespace {
 struct Species {
     double q, m;
     std::vector<double> a[7];           // x y z w ux uy uz  (PIdx order)
+    // plasma injector (continuous injection with the moving window); z_inj = z at creation, the
+    // input of user attributes such as regionofinterest(x,y,z,...) of the laser_acceleration deck
+    bool has_injector = false;
+    pic_plasma_injector inj{};
+    double current_injection_position = 0.0;      // WarpXParticleContainer::m_current_injection_position
+    std::vector<double> z_inj;
     pic_soa soa() {
         pic_soa s;
         s.x = a[0].data(); s.y = a[1].data(); s.z = a[2].data(); s.w = a[3].data();
@@ -57,6 +64,15 @@ struct Sim {
     int nspecies = 0;
     bool is_synchronized = true;
     int istep = 0;
+    double cur_time = 0.0;                         // t_new[0]
+    // laser-wakefield additions (single box): boundaries, moving window, antennas
+    pic_boundaries bnd{};
+    bool any_pec = false;
+    bool do_moving_window = false;
+    int mw_dir = 2;
+    double mw_v = 0.0, mw_x = 0.0;                 // moving_window_v [m/s], moving_window_x
+    struct Laser { Antenna ant; std::vector<double> a[7]; };
+    std::vector<Laser> lasers;
     double t_push = 0, t_dep = 0, t_fdtd = 0, t_halo = 0, t_other = 0;
 };
 
@@ -70,13 +86,15 @@ const int STAG[9][3] = {{0, 1, 1}, {1, 0, 1}, {1, 1, 0},   // Ex Ey Ez
                         {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};  // jx jy jz (= E)
 
 // guardCellManager::Init, Parallelization/GuardCellManager.cpp:62-161,310-343 (no MR, no NCI,
-// no moving window, no filter, not safe_guard_cells, FDTD).
+// not safe_guard_cells, FDTD).
 void guard_cells(Sim& s) {
     for (int d = 0; d < 3; ++d) {
         const int ngt = s.nox;                                   // :62-64
-        const int ng = (ngt % 2) ? ngt + 1 : ngt;                // :83-85 (even)
+        int ng = (ngt % 2) ? ngt + 1 : ngt;                      // :83-85 (even)
+        int ngJ = ngt;                                           // :96-98
+        if (s.do_moving_window) { ng = std::max(ng, 2); ngJ = std::max(ngJ, 2); }   // :103-115 (max_r = 2 on one level)
         s.ng_EB[d] = ng;
-        s.ng_J[d] = ngt + (int)std::ceil(C_LIGHT * 0.5 * s.dt / s.dx[d]);   // :96-98,147,161
+        s.ng_J[d] = ngJ + (int)std::ceil(C_LIGHT * 0.5 * s.dt / s.dx[d]);   // :147,161
         s.ng_depos_J[d] = s.ng_J[d];                             // :165
         if (s.use_filter) s.ng_J[d] += s.npass[d];               // + stencil_length - 1, :169-172
         s.ng_FS[d] = 1;                                          // Yee/CKC GetMaxGuardCell
@@ -137,10 +155,43 @@ void push_p(Sim& s, double dtp) {  // mypc->PushP(lev, dt, E_aux, B_aux): box gr
 
 // Move particles that left their box to the owning box after the periodic wrap
 // (ParticleContainer::Redistribute semantics; locate by cell index).
+void erase_marked(std::vector<double>* a, int na, const std::vector<char>& keep) {
+    for (int c = 0; c < na; ++c) {
+        if (a[c].empty()) continue;
+        size_t o = 0;
+        for (size_t ip = 0; ip < keep.size(); ++ip) if (keep[ip]) a[c][o++] = a[c][ip];
+        a[c].resize(o);
+    }
+}
+
 void redistribute(Sim& s) {
     const double t0 = now();
+    const bool all_periodic = s.geom.periodic[0] && s.geom.periodic[1] && s.geom.periodic[2];
+    if (!all_periodic) {
+        // mypc->ApplyBoundaryConditions() over all containers (species and lasers,
+        // MultiParticleContainer.cpp:659-664), then Redistribute drops the lost particles
+        std::vector<char> keep;
+        for (auto& b : s.boxes)
+            for (auto& sp : b.sp) {
+                pic_soa P = sp.soa();
+                apply_particle_boundaries(P, s.geom, s.bnd, keep);
+                erase_marked(sp.a, 7, keep);
+                erase_marked(&sp.z_inj, 1, keep);
+            }
+        for (auto& L : s.lasers) {
+            pic_soa P; P.x = L.a[0].data(); P.y = L.a[1].data(); P.z = L.a[2].data(); P.w = L.a[3].data();
+            P.ux = L.a[4].data(); P.uy = L.a[5].data(); P.uz = L.a[6].data(); P.idcpu = nullptr; P.np = (long)L.a[0].size();
+            apply_particle_boundaries(P, s.geom, s.bnd, keep);
+            erase_marked(L.a, 7, keep);
+        }
+    }
     for (auto& b : s.boxes)
         for (auto& sp : b.sp) { pic_soa P = sp.soa(); wrap_periodic(P, s.geom); }
+    for (auto& L : s.lasers) {
+        pic_soa P; P.x = L.a[0].data(); P.y = L.a[1].data(); P.z = L.a[2].data(); P.w = nullptr;
+        P.ux = P.uy = P.uz = nullptr; P.idcpu = nullptr; P.np = (long)L.a[0].size();
+        wrap_periodic(P, s.geom);
+    }
     if (s.boxes.size() > 1) {
         for (int isp = 0; isp < s.nspecies; ++isp) {
             std::vector<std::array<std::vector<double>, 7>> in(s.boxes.size());
@@ -169,6 +220,60 @@ void redistribute(Sim& s) {
         }
     }
     s.t_other += now() - t0;
+}
+
+pic_soa laser_soa(Sim::Laser& L) {
+    pic_soa P;
+    P.x = L.a[0].data(); P.y = L.a[1].data(); P.z = L.a[2].data(); P.w = L.a[3].data();
+    P.ux = L.a[4].data(); P.uy = L.a[5].data(); P.uz = L.a[6].data(); P.idcpu = nullptr;
+    P.np = (long)L.a[0].size();
+    return P;
+}
+
+// WarpX::MoveWindow (Utils/WarpXMovingWindow.cpp:139-476), one level, no PML, lab frame:
+// advance moving_window_x, shift E, B (and J when move_j) by the whole number of cells the window
+// has covered, move the domain, continuously inject plasma into the uncovered slab.
+int move_window(Sim& s, int step, bool move_j) {
+    (void)step;                                          // start_moving_window_step = 0, no end step
+    if (!s.do_moving_window) return 0;
+    const int dir = s.mw_dir;
+    s.mw_x += (s.mw_v - 0.0 * C_LIGHT) / (1 - s.mw_v * 0.0 / C_LIGHT) * s.dt;                    // :155
+    // UpdateInjectionPosition (:59-136): plasma at rest -> v_shift = 0; antennas: lab frame, nothing
+    const double cdx = s.dx[dir];
+    const int num_shift_base = static_cast<int>((s.mw_x - s.geom.prob_lo[dir]) / cdx);            // :171
+    if (num_shift_base == 0) return 0;
+    s.geom.prob_lo[dir] = s.geom.prob_lo[dir] + num_shift_base * cdx;                              // :181-184
+    s.geom.prob_hi[dir] = s.geom.prob_hi[dir] + num_shift_base * cdx;
+    for (auto& b : s.boxes)
+        for (int dim = 0; dim < 3; ++dim) {                                                        // :226-266
+            shift_fab(b.fab[3 + dim], s.geom, num_shift_base, dir, 0.0);
+            shift_fab(b.fab[dim], s.geom, num_shift_base, dir, 0.0);
+            if (move_j) shift_fab(b.fab[6 + dim], s.geom, num_shift_base, dir, 0.0);
+        }
+    // continuous injection (:388-438)
+    for (auto& b : s.boxes)
+        for (auto& sp : b.sp) {
+            if (!sp.has_injector || !sp.inj.do_continuous_injection) continue;
+            double new_pos = sp.current_injection_position;
+            if (s.mw_v > 0.0)
+                new_pos = sp.current_injection_position +
+                          std::floor((s.geom.prob_hi[dir] - sp.current_injection_position) / cdx) * cdx;
+            else if (s.mw_v < 0.0)
+                new_pos = sp.current_injection_position -
+                          std::floor((sp.current_injection_position - s.geom.prob_lo[dir]) / cdx) * cdx;
+            double plo[3], phi[3];
+            for (int d = 0; d < 3; ++d) { plo[d] = s.geom.prob_lo[d]; phi[d] = s.geom.prob_hi[d]; }
+            if (s.mw_v > 0.0) { plo[dir] = sp.current_injection_position; phi[dir] = new_pos; }
+            else if (s.mw_v < 0.0) { plo[dir] = new_pos; phi[dir] = sp.current_injection_position; }
+            const bool ok = plo[0] < phi[0] && plo[1] < phi[1] && plo[2] < phi[2];               // RealBox::ok
+            if (ok && sp.current_injection_position != new_pos) {
+                const size_t n0 = sp.a[2].size();
+                add_plasma(sp.inj, s.geom, s.dx, plo, phi, sp.a);
+                for (size_t ip = n0; ip < sp.a[2].size(); ++ip) sp.z_inj.push_back(sp.a[2][ip]);
+                sp.current_injection_position = new_pos;
+            }
+        }
+    return num_shift_base;
 }
 
 // WarpX::OneStep_nosub (WarpXEvolve.cpp:353-455) preceded by ExplicitFillBoundaryEBUpdateAux
@@ -207,6 +312,13 @@ void one_step(Sim& s, bool last_step) {
                           -0.5 * s.dt /* relative_time, PhysicalParticleContainer.cpp:2029 */, s.nox);
             s.t_dep += now() - t0;
         }
+        // laser antennas come after the species in allcontainers (MultiParticleContainer.cpp:60-75);
+        // LaserParticleContainer::Evolve (LaserParticleContainer.cpp:563-700): charge = 1 (:88)
+        for (auto& L : s.lasers) {
+            pic_soa P = laser_soa(L);
+            antenna_push(L.ant, P, s.cur_time, s.dt);
+            deposit<Leaf>(P, 0, P.np, b.fab + 6, s.dinv, xyzminJ, loJ, 1.0, s.dt, -0.5 * s.dt, s.nox);
+        }
     }
     // ---- SyncCurrentAndRho -> [ApplyFilterJ, WarpXComm.cpp:1233-1237,1357-1374] -> SumBoundaryJ
     //      (:1386-1424): src = ng_depos_J (+ stencil_length-1 with the filter, :1413-1416),
@@ -230,18 +342,27 @@ void one_step(Sim& s, bool last_step) {
             for (size_t b = 0; b < s.boxes.size(); ++b) fabs[b] = s.boxes[b].fab[c];
             sum_boundary(fabs.data(), (int)fabs.size(), src_ng, s.ng_J, s.geom);
         }
+        // reflect J over PEC / reflecting boundaries (WarpXEvolve.cpp:629-640)
+        if (s.any_pec) for (auto& b : s.boxes) apply_pec_current(b.fab + 6, s.geom, s.bnd);
     }
     s.t_halo += now() - t0;
-    // ---- field solve (:421-437) ----
+    // ---- field solve (:421-437); WarpX::EvolveB / EvolveE end with ApplyB/EfieldBoundary
+    //      (FieldSolver/WarpXPushFieldsEM.cpp:926,990) ----
     auto evolveB = [&](double dtb) {
         const double t1 = now();
-        for (auto& b : s.boxes) evolve_b<Leaf>(b.fab + 3, b.fab, s.st, dtb);
+        for (auto& b : s.boxes) {
+            evolve_b<Leaf>(b.fab + 3, b.fab, s.st, dtb);
+            if (s.any_pec) apply_pec_field(b.fab + 3, false, s.geom, s.bnd, s.ng_FG);
+        }
         s.t_fdtd += now() - t1;
     };
     evolveB(0.5 * s.dt);
     fill_EB(s, 3, s.ng_FS);
     t0 = now();
-    for (auto& b : s.boxes) evolve_e<Leaf>(b.fab, b.fab + 3, b.fab + 6, s.st, s.dt);
+    for (auto& b : s.boxes) {
+        evolve_e<Leaf>(b.fab, b.fab + 3, b.fab + 6, s.st, s.dt);
+        if (s.any_pec) apply_pec_field(b.fab, true, s.geom, s.bnd, s.ng_FG);
+    }
     s.t_fdtd += now() - t0;
     fill_EB(s, 0, s.ng_FS);
     evolveB(0.5 * s.dt);
@@ -252,7 +373,9 @@ void one_step(Sim& s, bool last_step) {
         s.is_synchronized = true;
     }
     ++s.istep;
-    redistribute(s);   // HandleParticlesAtBoundaries -> RedistributeLocal(1)
+    s.cur_time += s.dt;                                           // :232
+    move_window(s, s.istep, s.is_synchronized);                   // :247 (move_j = is_synchronized)
+    redistribute(s);   // HandleParticlesAtBoundaries -> ApplyBoundaryConditions, RedistributeLocal
 }
 
 }  // namespace
@@ -366,6 +489,89 @@ void* orc_sim_create(const int* n_cell, const double* prob_lo, const double* pro
             }
     return s;
 }
+// ---- laser-wakefield configuration (single box; call before adding particles) ----------------
+// boundary.field_lo/hi, boundary.particle_lo/hi (Utils/WarpXUtil.cpp:470-540)
+int orc_sim_set_boundaries(void* h, const pic_boundaries* b) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1 || s->nspecies) return 1;
+    s->bnd = *b;
+    s->any_pec = false;
+    for (int d = 0; d < 3; ++d) {
+        const bool per = b->field_lo[d] == PIC_FIELD_PERIODIC;
+        if (per != (b->field_hi[d] == PIC_FIELD_PERIODIC)) return 2;
+        s->geom.periodic[d] = per ? 1 : 0;
+        if (per) s->bnd.particle_lo[d] = s->bnd.particle_hi[d] = PIC_PARTICLE_PERIODIC;
+        else if (b->particle_lo[d] == PIC_PARTICLE_PERIODIC || b->particle_hi[d] == PIC_PARTICLE_PERIODIC) return 3;
+        s->any_pec = s->any_pec || b->field_lo[d] == PIC_FIELD_PEC || b->field_hi[d] == PIC_FIELD_PEC;
+    }
+    return 0;
+}
+// warpx.do_moving_window / moving_window_dir / moving_window_v (in units of c; WarpX.cpp:619-650)
+int orc_sim_set_moving_window(void* h, int dir, double v_over_c) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1 || s->nspecies || s->geom.periodic[dir]) return 1;
+    s->do_moving_window = true; s->mw_dir = dir; s->mw_v = v_over_c * C_LIGHT;
+    s->mw_x = s->geom.prob_lo[dir];
+    guard_cells(*s);
+    alloc_box(*s, s->boxes[0]);
+    return 0;
+}
+// A species created by its plasma injector (PhysicalParticleContainer::InitData -> AddPlasma over
+// the whole domain, PhysicalParticleContainer.cpp:450-454,855-922)
+int orc_sim_add_plasma(void* h, double q, double m, const pic_plasma_injector* inj) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1) return -1;
+    Sim::Box& b = s->boxes[0];
+    b.sp.emplace_back();
+    Species& sp = b.sp.back();
+    sp.q = q; sp.m = m; sp.has_injector = true; sp.inj = *inj;
+    if (s->do_moving_window)                                     // WarpX.cpp:288-307
+        sp.current_injection_position = s->mw_v > 0 ? s->geom.prob_hi[s->mw_dir] : s->geom.prob_lo[s->mw_dir];
+    add_plasma(sp.inj, s->geom, s->dx, s->geom.prob_lo, s->geom.prob_hi, sp.a);
+    sp.z_inj = sp.a[2];
+    return s->nspecies++;
+}
+// lasers.names / <laser>.* (LaserParticleContainer ctor + InitData)
+int orc_sim_add_laser(void* h, const pic_laser_antenna* prm) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1) return -1;
+    s->lasers.emplace_back();
+    Sim::Laser& L = s->lasers.back();
+    L.ant = antenna_setup(*prm, s->dx);
+    antenna_init_particles(L.ant, s->geom.prob_lo, s->geom.prob_hi, L.a);     // m_laser_injection_box = ProbDomain (:224)
+    return (int)s->lasers.size() - 1;
+}
+long orc_sim_laser_np(void* h, int il) { return (long)static_cast<Sim*>(h)->lasers[il].a[0].size(); }
+void orc_sim_get_laser_particles(void* h, int il, int comp, double* out) {
+    auto& v = static_cast<Sim*>(h)->lasers[il].a[comp];
+    std::memcpy(out, v.data(), v.size() * sizeof(double));
+}
+void orc_sim_laser_info(void* h, int il, double* out /* S_X S_Y mobility weight */) {
+    const Antenna& a = static_cast<Sim*>(h)->lasers[il].ant;
+    out[0] = a.S_X; out[1] = a.S_Y; out[2] = a.mobility; out[3] = a.weight;
+}
+void orc_sim_get_z_inj(void* h, int isp, double* out) {
+    auto& v = static_cast<Sim*>(h)->boxes[0].sp[isp].z_inj;
+    std::memcpy(out, v.data(), v.size() * sizeof(double));
+}
+double orc_sim_time(void* h) { return static_cast<Sim*>(h)->cur_time; }
+void orc_sim_prob_domain(void* h, double* out /* lo[3] hi[3] */) {
+    Sim* s = static_cast<Sim*>(h);
+    for (int d = 0; d < 3; ++d) { out[d] = s->geom.prob_lo[d]; out[3 + d] = s->geom.prob_hi[d]; }
+}
+// ---- stage-level entry points of the laser-wakefield additions (host pointers) ---------------
+void orc_apply_pec_field(const pic_fab* F, int is_E, const pic_geom* g, const pic_boundaries* b, const int* ng_fg) {
+    apply_pec_field(F, is_E != 0, *g, *b, ng_fg);
+}
+void orc_apply_pec_current(const pic_fab* J, const pic_geom* g, const pic_boundaries* b) { apply_pec_current(J, *g, *b); }
+void orc_shift_fab(const pic_fab* f, const pic_geom* g, int num_shift, int dir, double external_field) {
+    shift_fab(*f, *g, num_shift, dir, external_field);
+}
+void orc_antenna_push(const pic_laser_antenna* prm, const double* dx, const pic_soa* p, double t, double dt) {
+    const Antenna a = antenna_setup(*prm, dx);
+    antenna_push(a, *p, t, dt);
+}
+
 void orc_sim_destroy(void* h) { delete static_cast<Sim*>(h); }
 double orc_sim_dt(void* h) { return static_cast<Sim*>(h)->dt; }
 void orc_sim_guards(void* h, int* out /* ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3] */) {

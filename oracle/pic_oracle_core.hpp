@@ -369,22 +369,51 @@ int deposit(const pic_soa& P, long offset, long np, const pic_fab J[3], const do
 // ============================================================================================
 inline int wrap(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
 
+// Location map of one dimension: periodic -> index wrapped into [0, n_cell); non-periodic -> the
+// index itself, offset so that guard points beyond the domain have their own (unshared) location.
+struct LocMap {
+    int n[3], per[3], off[3], size[3];
+    LocMap(const pic_geom& g, const pic_fab* fabs, int nfab) {
+        for (int d = 0; d < 3; ++d) {
+            n[d] = g.n_cell[d]; per[d] = g.periodic[d];
+            int mg = 0;
+            for (int b = 0; b < nfab; ++b) mg = std::max(mg, fabs[b].ng[d]);
+            off[d] = per[d] ? 0 : mg;
+            size[d] = per[d] ? n[d] : n[d] + 1 + 2 * mg;
+        }
+    }
+    int at(int i, int d) const { return per[d] ? wrap(i, n[d]) : i + off[d]; }
+    size_t idx(int i, int j, int k) const {
+        return at(i, 0) + (size_t)size[0] * (at(j, 1) + (size_t)size[1] * at(k, 2));
+    }
+    size_t total() const { return (size_t)size[0] * size[1] * size[2]; }
+};
+
 // FillBoundary(ng): every guard point within ng of the valid region receives the value of a
 // valid point at the same location (any box; duplicates hold equal values by construction).
+// Guard points beyond a non-periodic domain face have no valid image and are left untouched
+// (AMReX FabArray::FillBoundary with a Periodicity that is off in that direction).
 inline void fill_boundary(const pic_fab* fabs, int nfab, const int ng[3], const pic_geom& g) {
-    const int n0 = g.n_cell[0], n1 = g.n_cell[1], n2 = g.n_cell[2];
+    const LocMap M(g, fabs, nfab);
+    const bool all_periodic = g.periodic[0] && g.periodic[1] && g.periodic[2];
     // canonical value of a location = the valid point of the box that OWNS it (a box owns the
-    // points of its cells, i.e. its valid points minus the upper nodal layer); every location is
-    // written exactly once, so the fill is race-free.
-    std::vector<double> canon((size_t)n0 * n1 * n2, 0.0);
+    // points of its cells, i.e. its valid points minus the upper nodal layer; along a non-periodic
+    // direction the upper nodal layer is a location of its own and is owned too); within one box
+    // every location is written exactly once, so the fill is race-free.
+    std::vector<double> canon(M.total(), 0.0);
+    std::vector<char> have(all_periodic ? 0 : M.total(), 0);
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
-        const int h0 = vhi(f, 0) - f.stag[0], h1 = vhi(f, 1) - f.stag[1], h2 = vhi(f, 2) - f.stag[2];
+        const int h0 = vhi(f, 0) - (g.periodic[0] ? f.stag[0] : 0), h1 = vhi(f, 1) - (g.periodic[1] ? f.stag[1] : 0),
+                  h2 = vhi(f, 2) - (g.periodic[2] ? f.stag[2] : 0);
 #pragma omp parallel for schedule(static)
         for (int k = vlo(f, 2); k <= h2; ++k)
             for (int j = vlo(f, 1); j <= h1; ++j)
-                for (int i = vlo(f, 0); i <= h0; ++i)
-                    canon[wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2))] = v(i, j, k);
+                for (int i = vlo(f, 0); i <= h0; ++i) {
+                    const size_t c = M.idx(i, j, k);
+                    canon[c] = v(i, j, k);
+                    if (!all_periodic) have[c] = 1;
+                }
     }
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
@@ -395,31 +424,37 @@ inline void fill_boundary(const pic_fab* fabs, int nfab, const int ng[3], const 
                     const bool valid = i >= vlo(f, 0) && i <= vhi(f, 0) && j >= vlo(f, 1) &&
                                        j <= vhi(f, 1) && k >= vlo(f, 2) && k <= vhi(f, 2);
                     if (valid) continue;
-                    const size_t c = wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2));
+                    const size_t c = M.idx(i, j, k);
+                    if (!all_periodic && !have[c]) continue;
                     v(i, j, k) = canon[c];
                 }
     }
 }
 
 // SumBoundary(src_ng, dst_ng): every point (valid + dst_ng guards) receives the sum over ALL
-// copies (valid + src_ng guards of every box) at the same location.
+// copies (valid + src_ng guards of every box) at the same location (AMReX FabArray::SumBoundary:
+// copy to a temporary, zero valid + dst_ng, ParallelAdd the temporary back).  Along a non-periodic
+// direction a guard point beyond the domain face only has itself as a copy.
 inline void sum_boundary(const pic_fab* fabs, int nfab, const int src_ng[3], const int dst_ng[3],
                          const pic_geom& g) {
-    const int n0 = g.n_cell[0], n1 = g.n_cell[1], n2 = g.n_cell[2];
-    std::vector<double> canon((size_t)n0 * n1 * n2, 0.0);
+    const LocMap M(g, fabs, nfab);
+    const int n2 = g.n_cell[2];
+    std::vector<double> canon(M.total(), 0.0);
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
         // planes k that wrap onto each other (k, k +- n2) are visited in separate sweeps, so each
         // sweep can run in parallel over k without atomics
         const int kbeg = vlo(f, 2) - src_ng[2], kend = vhi(f, 2) + src_ng[2];
-        const int first_period = (int)std::floor((double)kbeg / n2), last_period = (int)std::floor((double)kend / n2);
+        const int first_period = g.periodic[2] ? (int)std::floor((double)kbeg / n2) : 0;
+        const int last_period = g.periodic[2] ? (int)std::floor((double)kend / n2) : 0;
         for (int per = first_period; per <= last_period; ++per) {
-            const int ka = std::max(kbeg, per * n2), kb = std::min(kend, per * n2 + n2 - 1);
+            const int ka = g.periodic[2] ? std::max(kbeg, per * n2) : kbeg;
+            const int kb = g.periodic[2] ? std::min(kend, per * n2 + n2 - 1) : kend;
 #pragma omp parallel for schedule(static)
             for (int k = ka; k <= kb; ++k)
                 for (int j = vlo(f, 1) - src_ng[1]; j <= vhi(f, 1) + src_ng[1]; ++j)
                     for (int i = vlo(f, 0) - src_ng[0]; i <= vhi(f, 0) + src_ng[0]; ++i)
-                        canon[wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2))] += v(i, j, k);
+                        canon[M.idx(i, j, k)] += v(i, j, k);
         }
     }
     for (int b = 0; b < nfab; ++b) {
@@ -427,10 +462,8 @@ inline void sum_boundary(const pic_fab* fabs, int nfab, const int src_ng[3], con
 #pragma omp parallel for schedule(static)
         for (int k = vlo(f, 2) - dst_ng[2]; k <= vhi(f, 2) + dst_ng[2]; ++k)
             for (int j = vlo(f, 1) - dst_ng[1]; j <= vhi(f, 1) + dst_ng[1]; ++j)
-                for (int i = vlo(f, 0) - dst_ng[0]; i <= vhi(f, 0) + dst_ng[0]; ++i) {
-                    const size_t c = wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2));
-                    v(i, j, k) = canon[c];
-                }
+                for (int i = vlo(f, 0) - dst_ng[0]; i <= vhi(f, 0) + dst_ng[0]; ++i)
+                    v(i, j, k) = canon[M.idx(i, j, k)];
     }
 }
 
@@ -516,15 +549,15 @@ inline void wrap_periodic(const pic_soa& P, const pic_geom& g) {
 // MultiFab::norm2(0, periodicity)^2: sum of squares counting each periodic/nodal duplicate once
 // (Diagnostics/ReducedDiags/FieldEnergy.cpp:123-144).
 inline double sum_squares_unique(const pic_fab* fabs, int nfab, const pic_geom& g) {
-    const int n0 = g.n_cell[0], n1 = g.n_cell[1], n2 = g.n_cell[2];
-    std::vector<char> seen((size_t)n0 * n1 * n2, 0);
+    const LocMap M(g, fabs, nfab);
+    std::vector<char> seen(M.total(), 0);
     double s = 0.0;
     for (int b = 0; b < nfab; ++b) {
         const pic_fab& f = fabs[b]; W v(f);
         for (int k = vlo(f, 2); k <= vhi(f, 2); ++k)
             for (int j = vlo(f, 1); j <= vhi(f, 1); ++j)
                 for (int i = vlo(f, 0); i <= vhi(f, 0); ++i) {
-                    const size_t c = wrap(i, n0) + (size_t)n0 * (wrap(j, n1) + (size_t)n1 * wrap(k, n2));
+                    const size_t c = M.idx(i, j, k);
                     if (seen[c]) continue;
                     seen[c] = 1;
                     s += v(i, j, k) * v(i, j, k);

@@ -2,8 +2,10 @@
 """Regenerates tests/golden/warpx_checksums.json from the reference tree (run in the authoring
 container only; /root/reference does not exist on the GPU box).
 
-The values are WarpX's own regression checksums for the two tests that pin the hot path
-(SURVEY.md section 8c): the 3D Langmuir wave (full loop, order 1) and the force-free particle pusher.
+The values are WarpX's own regression checksums for the tests that pin the hot path
+(SURVEY.md section 8c): the 3D Langmuir wave (full loop, order 1), the force-free particle pusher and
+the 3D laser-acceleration deck (full loop at order 3 with the bilinear filter, PEC walls, the moving
+window, the laser antenna and continuous injection -- no RNG in that deck).
 Nothing else is taken from the reference."""
 import json
 import os
@@ -13,15 +15,16 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "warpx_checksums.
 
 gold = {
     "_provenance": {
-        "source": "ECP-WarpX/WarpX Regression/Checksum/benchmarks_json/{test_3d_langmuir_multi,test_3d_particle_pusher}.json",
+        "source": "ECP-WarpX/WarpX Regression/Checksum/benchmarks_json/{test_3d_langmuir_multi,test_3d_particle_pusher,test_3d_laser_acceleration}.json",
         "tolerance": "rtol 1e-9, atol 1e-40 (Regression/Checksum/checksum.py:219-301)",
         "decks": ["Examples/Tests/langmuir/inputs_test_3d_langmuir_multi",
-                  "Examples/Tests/particle_pusher/inputs_test_3d_particle_pusher"],
+                  "Examples/Tests/particle_pusher/inputs_test_3d_particle_pusher",
+                  "Examples/Physics_applications/laser_acceleration/inputs_test_3d_laser_acceleration"],
         "pusher_expected_error": {"boris": 2321.3958529, "vay": 0.00010467, "higuera_cary": 0.00011403,
                                   "source": "Examples/Tests/particle_pusher/analysis.py:17-21"},
     }
 }
-for name in ("test_3d_langmuir_multi", "test_3d_particle_pusher"):
+for name in ("test_3d_langmuir_multi", "test_3d_particle_pusher", "test_3d_laser_acceleration"):
     with open(os.path.join(REF, name + ".json")) as f:
         gold[name] = json.load(f)
 with open(OUT, "w") as f:

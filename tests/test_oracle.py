@@ -254,3 +254,147 @@ def test_counter_based_momenta_are_decomposition_independent():
         assert np.array_equal(full[c][idx], part[c])
     u = full["ux"] / workloads.C
     assert abs(np.std(u) - 0.01) < 0.001 and abs(np.mean(u)) < 0.001
+
+
+# ---------------------------------------------------------------------------------------------
+# Laser-wakefield additions: PEC, moving window, antenna, continuous injection
+# ---------------------------------------------------------------------------------------------
+def make_lwfa_oracle(orc, wl, kind="restated"):
+    sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"],
+                        use_filter=wl["use_filter"], kind=kind)
+    sim.set_boundaries(abi.make_boundaries(wl["field_lo"], wl["field_hi"]))
+    sim.set_moving_window(wl["moving_window_dir"], wl["moving_window_v"])
+    for s in wl["species"]:
+        sim.add_plasma(s["q"], s["m"], abi.make_injector(s["ppc"], s["bound_lo"], s["bound_hi"], s["density"],
+                                                         s["do_continuous_injection"]))
+    for la in wl["lasers"]:
+        sim.add_laser(abi.make_laser(la["position"], la["direction"], la["polarization"], la["wavelength"],
+                                     la["e_max"], la["waist"], la["duration"], la["t_peak"], la["focal_distance"]))
+    return sim
+
+
+def test_laser_acceleration_golden_checksums(orc, golden):
+    """Examples/Physics_applications/laser_acceleration/inputs_test_3d_laser_acceleration: WarpX's own
+    regression checksums (100 steps, 32x32x256, order 3, filter, PEC z, moving window, Gaussian antenna,
+    continuous injection; no RNG) at WarpX's tolerance.  This is the reference-golden pin of the
+    order-3 gather / Esirkepov deposition, the bilinear filter and every config-4 enabler built so far.
+    (`rho` and `part_per_cell` of that file are diagnostics outside the path and are not compared.)"""
+    wl = workloads.laser_acceleration_3d()
+    sim = make_lwfa_oracle(orc, wl, kind="reference" if orc.have_ref() else "restated")
+    assert sim.guards() == {"ng_EB": [4, 4, 4], "ng_J": [5, 5, 5], "ng_FG": [2, 2, 2], "ng_FS": [1, 1, 1]}
+    info = sim.laser_info(0)
+    assert info["S_X"] == 1.875e-6 and info["S_Y"] == 1.875e-6
+    assert sim.L.orc_sim_laser_np(sim.h, 0) == 2 * 32 * 32
+    assert sim.L.orc_sim_np(sim.h, 0) == 22 * 22 * 45
+    sim.evolve(wl["max_step"])
+    g = golden["test_3d_laser_acceleration"]
+    for c, name in enumerate(abi.COMP_NAMES):
+        assert _close(sim.checksum_field(c), g["lev=0"][name]), name
+    P = sim.particles(0)
+    vals = {"particle_position_x": P["x"], "particle_position_y": P["y"], "particle_position_z": P["z"],
+            "particle_momentum_x": P["ux"] * workloads.M_E, "particle_momentum_y": P["uy"] * workloads.M_E,
+            "particle_momentum_z": P["uz"] * workloads.M_E, "particle_weight": P["w"]}
+    for key, arr in vals.items():
+        assert _close(float(np.sum(np.abs(arr))), g["electrons"][key]), key
+    lo, hi = wl["region_of_interest"]
+    z0 = sim.z_at_injection(0)
+    assert float(np.sum((z0 > lo) & (z0 < hi))) == g["electrons"]["particle_regionofinterest"]
+    # the window moved 98 cells and injected 98 layers of 22 x 22 electrons
+    plo, phi = sim.prob_domain()
+    dz = (wl["prob_hi"][2] - wl["prob_lo"][2]) / wl["n_cell"][2]
+    assert round((plo[2] - wl["prob_lo"][2]) / dz) == 98 and len(P["x"]) == 22 * 22 * (45 + 98)
+
+
+def test_pec_known_answers(orc):
+    """PEC::ApplyPECtoEfield / ApplyPECtoBfield semantics on a z-PEC box (WarpX_PEC.cpp:120-318):
+    tangential E (normal B) vanish on the wall and are odd across it; normal E (tangential B) are even."""
+    L = orc.lib()
+    n, ng = (4, 4, 8), (2, 2, 2)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"))
+    rng = np.random.default_rng(5)
+    for is_E in (1, 0):
+        F = [orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[c + (0 if is_E else 3)])
+             for c in range(3)]
+        for f in F:
+            f.a[...] = rng.standard_normal(f.a.shape)
+        before = [f.a.copy() for f in F]
+        L.orc_apply_pec_field(orc.fab_array(F), is_E, C.byref(geom), C.byref(bnd), abi.int3(ng))
+        for c, f in enumerate(F):
+            a, b0 = f.a, before[c]
+            nodal_z = f.desc.stag[2]
+            flips = (c != 2) if is_E else (c == 2)
+            sgn = -1.0 if flips else 1.0
+            klo, khi = ng[2], a.shape[0] - 1 - ng[2]           # first / last valid k (array index)
+            if nodal_z:
+                if flips:
+                    assert np.all(a[klo] == 0.0) and np.all(a[khi] == 0.0)
+                else:
+                    assert np.array_equal(a[klo], b0[klo])
+                for gk in (1, 2):
+                    assert np.array_equal(a[klo - gk], sgn * a[klo + gk])
+                    assert np.array_equal(a[khi + gk], sgn * a[khi - gk])
+            else:
+                for gk in (1, 2):
+                    assert np.array_equal(a[klo - gk], sgn * a[klo + gk - 1])
+                    assert np.array_equal(a[khi + gk], sgn * a[khi - gk + 1])
+            # interior untouched
+            assert np.array_equal(a[klo + 1:khi], b0[klo + 1:khi])
+
+
+def test_pec_current_known_answers(orc):
+    """PEC::ApplyReflectiveBoundarytoJfield (WarpX_PEC.cpp:702-880) with absorbing particles: the image
+    of what was deposited beyond the wall is subtracted from tangential J / added to normal J, wall
+    values of the nodal (tangential) components vanish, guards hold the image current."""
+    L = orc.lib()
+    n, ng = (4, 4, 8), (3, 3, 3)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"))
+    rng = np.random.default_rng(6)
+    J = [orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[6 + c]) for c in range(3)]
+    for f in J:
+        f.a[...] = rng.standard_normal(f.a.shape)
+    before = [f.a.copy() for f in J]
+    L.orc_apply_pec_current(orc.fab_array(J), C.byref(geom), C.byref(bnd))
+    vx = slice(ng[0], -ng[0]); vy = slice(ng[1], -ng[1])      # the reference loops over valid points only
+    for c, f in enumerate(J):
+        a, b0 = f.a[:, vy, vx], before[c][:, vy, vx]
+        klo, khi = ng[2], f.a.shape[0] - 1 - ng[2]
+        if f.desc.stag[2]:          # jx, jy: nodal in z, tangential
+            assert np.all(a[klo] == 0.0) and np.all(a[khi] == 0.0)
+            for gk in (1, 2, 3):
+                assert np.allclose(a[klo + gk], b0[klo + gk] - b0[klo - gk], rtol=0, atol=1e-15)
+                assert np.array_equal(a[klo - gk], -a[klo + gk])
+                assert np.allclose(a[khi - gk], b0[khi - gk] - b0[khi + gk], rtol=0, atol=1e-15)
+                assert np.array_equal(a[khi + gk], -a[khi - gk])
+        else:                        # jz: cell-centred in z, normal
+            for gk in (1, 2, 3):
+                assert np.allclose(a[klo + gk - 1], b0[klo + gk - 1] + b0[klo - gk], rtol=0, atol=1e-15)
+                assert np.array_equal(a[klo - gk], a[klo + gk - 1])
+                assert np.allclose(a[khi - gk + 1], b0[khi - gk + 1] + b0[khi + gk], rtol=0, atol=1e-15)
+                assert np.array_equal(a[khi + gk], a[khi - gk + 1])
+
+
+def test_shift_fab_known_answers(orc):
+    """WarpX::shiftMF (Utils/WarpXMovingWindow.cpp:478-604): data move down by num_shift cells, zeros
+    enter at the top, the last num_shift allocated planes keep their old values."""
+    L = orc.lib()
+    n, ng = (4, 4, 8), (2, 2, 3)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    rng = np.random.default_rng(7)
+    for c in (0, 2):     # Ex nodal in z, Ez cell-centred in z
+        f = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[c])
+        f.a[...] = rng.standard_normal(f.a.shape)
+        b0 = f.a.copy()
+        L.orc_shift_fab(C.byref(f.desc), C.byref(geom), 1, 2, 0.0)
+        vx = slice(ng[0], -ng[0]); vy = slice(ng[1], -ng[1])
+        khi = f.a.shape[0] - 1 - ng[2]                            # last valid plane
+        nk = f.a.shape[0]
+        # valid x,y: planes shifted by one; zeros from beyond the old domain face
+        assert np.array_equal(f.a[0:khi, vy, vx], b0[1:khi + 1, vy, vx])
+        assert np.all(f.a[khi:nk - 1] == 0.0)
+        assert np.array_equal(f.a[nk - 1], b0[nk - 1])
+        # the first x/y guard layer was refreshed periodically before the shift (ng_mw = 1)
+        # (rows below the periodic duplicate j = N: the oracle fills from the owner of a location)
+        klo, vyo = ng[2], slice(ng[1], ng[1] + n[1])
+        assert np.array_equal(f.a[klo - 1:khi, vyo, ng[0] - 1], b0[klo:khi + 1, vyo, ng[0] - 1 + n[0]])

@@ -50,6 +50,62 @@ class pic_geom(C.Structure):
                 ("periodic", C.c_int * 3)]
 
 
+class pic_boundaries(C.Structure):
+    _fields_ = [("field_lo", C.c_int * 3), ("field_hi", C.c_int * 3),
+                ("particle_lo", C.c_int * 3), ("particle_hi", C.c_int * 3)]
+
+
+class pic_laser_antenna(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("nvec", C.c_double * 3), ("p_X", C.c_double * 3),
+                ("wavelength", C.c_double), ("e_max", C.c_double), ("waist", C.c_double),
+                ("duration", C.c_double), ("t_peak", C.c_double), ("focal_distance", C.c_double),
+                ("phi0", C.c_double)]
+
+
+class pic_plasma_injector(C.Structure):
+    _fields_ = [("ppc", C.c_int * 3), ("bound_lo", C.c_double * 3), ("bound_hi", C.c_double * 3),
+                ("density", C.c_double), ("do_continuous_injection", C.c_int)]
+
+
+FIELD_PERIODIC, FIELD_PEC = 0, 1
+PARTICLE_PERIODIC, PARTICLE_ABSORBING, PARTICLE_REFLECTING = 0, 1, 2
+_FIELD_BC = {"periodic": FIELD_PERIODIC, "pec": FIELD_PEC}
+_PARTICLE_BC = {"periodic": PARTICLE_PERIODIC, "absorbing": PARTICLE_ABSORBING, "reflecting": PARTICLE_REFLECTING}
+
+
+def make_boundaries(field_lo, field_hi, particle_lo=None, particle_hi=None):
+    """boundary.field_lo/hi and boundary.particle_lo/hi by name; particles default to periodic on
+    periodic field faces and absorbing elsewhere (Source/Utils/WarpXUtil.cpp:470-540)."""
+    b = pic_boundaries()
+    for d in range(3):
+        b.field_lo[d], b.field_hi[d] = _FIELD_BC[field_lo[d]], _FIELD_BC[field_hi[d]]
+        dflt_lo = "periodic" if field_lo[d] == "periodic" else "absorbing"
+        dflt_hi = "periodic" if field_hi[d] == "periodic" else "absorbing"
+        b.particle_lo[d] = _PARTICLE_BC[particle_lo[d] if particle_lo else dflt_lo]
+        b.particle_hi[d] = _PARTICLE_BC[particle_hi[d] if particle_hi else dflt_hi]
+    return b
+
+
+def make_laser(position, direction, polarization, wavelength, e_max, waist, duration, t_peak,
+               focal_distance, phi0=0.0):
+    a = pic_laser_antenna()
+    for d in range(3):
+        a.position[d], a.nvec[d], a.p_X[d] = float(position[d]), float(direction[d]), float(polarization[d])
+    a.wavelength, a.e_max, a.waist, a.duration = float(wavelength), float(e_max), float(waist), float(duration)
+    a.t_peak, a.focal_distance, a.phi0 = float(t_peak), float(focal_distance), float(phi0)
+    return a
+
+
+def make_injector(ppc, bound_lo, bound_hi, density, do_continuous_injection=False):
+    inj = pic_plasma_injector()
+    for d in range(3):
+        inj.ppc[d] = int(ppc[d])
+        inj.bound_lo[d], inj.bound_hi[d] = float(bound_lo[d]), float(bound_hi[d])
+    inj.density = float(density)
+    inj.do_continuous_injection = 1 if do_continuous_injection else 0
+    return inj
+
+
 SOLVER_YEE, SOLVER_CKC = 0, 1
 PIC_ERR_ABORT, PIC_ERR_RETURN = 0, 1
 PUSHER_BORIS, PUSHER_VAY, PUSHER_HC = 0, 1, 2
