@@ -290,6 +290,67 @@ int pic_sort_particles_by_cell(const pic_soa* in, const pic_soa* out, const pic_
                                void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Non-periodic domains: PEC walls, moving window, laser antenna, continuous injection, particle
+ * boundaries (SURVEY.md 8f rank 3 -- what BASELINE.json's config 4, the laser-wakefield deck, adds
+ * to the periodic step).  Boxes must span the domain along a non-periodic direction.
+ * ---------------------------------------------------------------------------------------- */
+
+/* PEC::ApplyPECtoEfield (is_E = 1) / ApplyPECtoBfield (is_E = 0), Source/BoundaryConditions/WarpX_PEC.cpp:
+ * 456-612, called at the end of WarpX::EvolveE / EvolveB (Source/FieldSolver/WarpXPushFieldsEM.cpp:926,990
+ * -> Source/BoundaryConditions/WarpXFieldBoundaries.cpp:51-159).  Acts on the valid points of each
+ * component grown by ng_fieldgather: tangential E / normal B vanish on the wall and are odd across
+ * it, the other components are even. */
+int pic_apply_pec_field(const pic_fab F[3], int is_E, const pic_geom* g, const pic_boundaries* b,
+                        const int ng_fieldgather[3], void* stream);
+
+/* PEC::ApplyReflectiveBoundarytoJfield (WarpX_PEC.cpp:702-880), called at the end of
+ * WarpX::SyncCurrentAndRho (Source/Evolve/WarpXEvolve.cpp:629-652): current deposited beyond a PEC /
+ * reflecting face is folded back as an image current, the guards receive the image of the interior. */
+int pic_apply_pec_current(const pic_fab J[3], const pic_geom* g, const pic_boundaries* b, void* stream);
+
+/* WarpX::shiftMF (Source/Utils/WarpXMovingWindow.cpp:478-604) for one component: the data move by
+ * num_shift cells against `dir`, `external_field` enters from the face the window moves into.
+ * tmp: scratch with as many doubles as the fab (borrowed). */
+int pic_shift_fab(const pic_fab* f, double* tmp, const pic_geom* g, int num_shift, int dir,
+                  double external_field, void* stream);
+
+/* Laser antenna (LaserParticleContainer, Source/Particles/LaserParticleContainer.cpp).
+ * _info: out = {S_X, S_Y, mobility, weight} (ComputeSpacing :727-761, ComputeWeightMobility :763-781).
+ * _particles: InitData (:369-560) -- HOST arrays x y z w receive one +w/-w pair per antenna cell inside
+ *   the box (the reference builds host vectors and hands them to AddNParticles); returns the particle
+ *   count (call with x = NULL to size), -1 when `capacity` is too small.  Momenta start at 0.
+ * _push: one step at time t = start of the step (Evolve :614-626): plane coordinates, Gaussian
+ *   amplitude (LaserProfileGaussian.cpp:100-162), u and x update (:860-951).  The antenna then
+ *   deposits through pic_deposit_esirkepov with q = 1 (:88). */
+int pic_laser_antenna_info(const pic_laser_antenna* prm, const double dx[3], double out[4]);
+long pic_laser_antenna_particles(const pic_laser_antenna* prm, const double dx[3], const double box_lo[3],
+                                 const double box_hi[3], double* x, double* y, double* z, double* w,
+                                 long capacity);
+int pic_laser_antenna_push(const pic_laser_antenna* prm, const double dx[3], const pic_soa* p, double t,
+                           double dt, void* stream);
+
+/* PhysicalParticleContainer::AddPlasma (Source/Particles/PhysicalParticleContainer.cpp:924-1333) for
+ * the injector described by pic_plasma_injector, restricted to the RealBox [part_lo, part_hi] (the
+ * whole domain at start-up, the slab uncovered by the moving window for ContinuousInjection, :2518-2527).
+ * Particles are appended on the device after p->np, in the order the reference creates them, with
+ * ids first_id, first_id+1, ...  cell_size = Geometry::CellSize() (NULL: (prob_hi - prob_lo) / n_cell;
+ * a moving window translates the domain but keeps the cell size it started with).
+ * Returns how many were added (the caller adds it to np), -1 on error. */
+long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double cell_size[3],
+                    const double part_lo[3], const double part_hi[3], const pic_soa* p, long capacity,
+                    uint64_t first_id, void* stream);
+
+/* WarpXParticleContainer::ApplyBoundaryConditions (Source/Particles/WarpXParticleContainer.cpp:1574-1638,
+ * ParticleBoundaries_K.H:21-75) + the removal AMReX Redistribute performs.  _mark reflects at
+ * reflecting faces and lists the particles lost at absorbing faces: work[0] = number lost (device int;
+ * work has pic_particles_boundary_workspace_ints(cap) ints).  After reading work[0] the caller
+ * calls _compact, which moves tail particles into the holes; the new count is np - n_lost. */
+long pic_particles_boundary_workspace_ints(int cap);
+int pic_particles_boundary_mark(const pic_soa* p, const pic_geom* g, const pic_boundaries* b, int* work,
+                                int cap, void* stream);
+int pic_particles_boundary_compact(const pic_soa* p, int* work, int cap, int n_lost, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * NCCL transport (one process per GPU).  Replaces the MPI layer under
  * ablastr::utils::communication::FillBoundary / SumBoundary (Source/ablastr/utils/Communication.cpp:
  * 71-175) and AMReX ParticleContainer::Redistribute (Source/Evolve/WarpXEvolve.cpp:550-559).
@@ -318,6 +379,23 @@ double pic_engine_dt(void* engine);
 void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);
 int pic_engine_set_fields(void* engine, const pic_fab fabs[9]);
 int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
+/* Non-periodic runs (one rank; call in this order, before pic_engine_set_fields / add_species):
+ *   set_boundaries     boundary.field_lo/hi + boundary.particle_lo/hi (PEC walls, absorbing / reflecting particles);
+ *   set_moving_window  warpx.do_moving_window / moving_window_dir / moving_window_v [c] (grows the guard
+ *                      cells like guardCellManager::Init, GuardCellManager.cpp:103-115 -- query pic_engine_guards after);
+ *   set_injector       the plasma injector of species isp (its particles must have been created by
+ *                      pic_add_plasma over the whole domain, ids 0..np-1); with do_continuous_injection
+ *                      the moving window refills the uncovered slab (WarpXMovingWindow.cpp:388-438);
+ *   add_laser          a Gaussian antenna whose particles (pic_laser_antenna_particles, momenta 0) the
+ *                      caller has uploaded into p (capacity >= p->np).
+ * pic_engine_time = t_new[0]; pic_engine_prob_domain = the (moving) problem domain, out = lo[3] hi[3]. */
+int pic_engine_set_boundaries(void* engine, const pic_boundaries* b);
+int pic_engine_set_moving_window(void* engine, int dir, double v_over_c);
+int pic_engine_set_injector(void* engine, int isp, const pic_plasma_injector* inj);
+int pic_engine_add_laser(void* engine, const pic_laser_antenna* prm, const pic_soa* p, long capacity);
+long pic_engine_laser_np(void* engine, int ilaser);
+double pic_engine_time(void* engine);
+void pic_engine_prob_domain(void* engine, double out[6]);
 int pic_engine_add_species(void* engine, double q, double m, const pic_soa* bufA, const pic_soa* bufB,
                            long capacity, int* cell_start, const int tile[3], void* sort_work, void* stream);
 int pic_engine_species_buffer(void* engine, int isp, long* np);

@@ -97,6 +97,9 @@ def lib(kind="restated"):
         "orc_apply_pec_current": (None, [fabp, gp, C.POINTER(abi.pic_boundaries)]),
         "orc_shift_fab": (None, [fabp, gp, C.c_int, C.c_int, C.c_double]),
         "orc_antenna_push": (None, [C.POINTER(abi.pic_laser_antenna), dp, soap, C.c_double, C.c_double]),
+        "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long]),
+        "orc_apply_particle_boundaries": (None, [soap, gp, C.POINTER(abi.pic_boundaries), C.c_char_p]),
+        "orc_antenna_particles": (C.c_long, [C.POINTER(abi.pic_laser_antenna), dp, dp, dp, dp, dp, dp, dp, C.c_long]),
         "orc_num_threads": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
     }

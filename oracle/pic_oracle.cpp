@@ -567,6 +567,33 @@ void orc_apply_pec_current(const pic_fab* J, const pic_geom* g, const pic_bounda
 void orc_shift_fab(const pic_fab* f, const pic_geom* g, int num_shift, int dir, double external_field) {
     shift_fab(*f, *g, num_shift, dir, external_field);
 }
+// AddPlasma into caller arrays (x y z w; momenta are 0): returns the count, -1 if capacity is too small
+long orc_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double* part_lo, const double* part_hi,
+                    double* x, double* y, double* z, double* w, long capacity) {
+    double dx[3];
+    for (int d = 0; d < 3; ++d) dx[d] = (g->prob_hi[d] - g->prob_lo[d]) / g->n_cell[d];
+    std::vector<double> out[7];
+    const long n = add_plasma(*inj, *g, dx, part_lo, part_hi, out);
+    if (n > capacity) return -1;
+    for (long i = 0; i < n; ++i) { x[i] = out[0][i]; y[i] = out[1][i]; z[i] = out[2][i]; w[i] = out[3][i]; }
+    return n;
+}
+// ApplyBoundaryConditions: positions / momenta are updated in place, keep[ip] = 0 marks lost particles
+void orc_apply_particle_boundaries(const pic_soa* p, const pic_geom* g, const pic_boundaries* b, char* keep) {
+    std::vector<char> k;
+    apply_particle_boundaries(*p, *g, *b, k);
+    std::memcpy(keep, k.data(), k.size());
+}
+long orc_antenna_particles(const pic_laser_antenna* prm, const double* dx, const double* box_lo, const double* box_hi,
+                           double* x, double* y, double* z, double* w, long capacity) {
+    const Antenna a = antenna_setup(*prm, dx);
+    std::vector<double> out[7];
+    antenna_init_particles(a, box_lo, box_hi, out);
+    const long n = (long)out[0].size();
+    if (n > capacity) return -1;
+    for (long i = 0; i < n; ++i) { x[i] = out[0][i]; y[i] = out[1][i]; z[i] = out[2][i]; w[i] = out[3][i]; }
+    return n;
+}
 void orc_antenna_push(const pic_laser_antenna* prm, const double* dx, const pic_soa* p, double t, double dt) {
     const Antenna a = antenna_setup(*prm, dx);
     antenna_push(a, *p, t, dt);

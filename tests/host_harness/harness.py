@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE -- host harness for the thin kernels of warpx_b200/csrc/lwfa.cu.
+
+The authoring container has no GPU.  lwfa.cu keeps every kernel as a `__host__ __device__` body
+(lwfa_body.cuh) behind a launch macro; compiled with -DPIC_HOST_HARNESS the launches become host
+loops over the same thread ids.  This module builds that variant into tests/host_harness/_build/
+and loads it, so that the CPU test-suite can check the bodies and the host-side argument builders
+(index ranges, closed-form slots, laser constants) against the oracle.  It proves nothing about
+launch geometry or device memory -- the `-m gpu` tests do that through the real library -- and it is
+never imported by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+from warpx_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "warpx_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libpic_lwfa_host.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SRCS = ["lwfa.cu", "runtime.cu"]
+_LIB = None
+
+
+def build():
+    deps = [os.path.join(CSRC, f) for f in SRCS + ["lwfa_body.cuh", "pic_common.cuh"]] + \
+           [os.path.join(ROOT, "include", "pic_b200.h")]
+    if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = [NVCC, "-DPIC_HOST_HARNESS", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC",
+           "-Xcompiler", "-ffp-contract=off", "--fmad=false", "--expt-relaxed-constexpr",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + \
+          [os.path.join(CSRC, f) for f in SRCS] + ["-lcudart"]
+    subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return OUT
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    fabp, soap, gp = C.POINTER(abi.pic_fab), C.POINTER(abi.pic_soa), C.POINTER(abi.pic_geom)
+    bp, lp, jp = C.POINTER(abi.pic_boundaries), C.POINTER(abi.pic_laser_antenna), C.POINTER(abi.pic_plasma_injector)
+    dp, ip, vp = abi.c_double_p, abi.c_int_p, C.c_void_p
+    for name, (res, args) in abi.LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp).items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    L.pic_set_error_mode.argtypes = [C.c_int]
+    L.pic_last_error.restype = C.c_char_p
+    L.pic_set_error_mode(abi.PIC_ERR_RETURN)
+    _LIB = L
+    return L

@@ -30,7 +30,7 @@ def test_ctypes_mirror_matches_header_layout():
     import subprocess
     import tempfile
     from warpx_b200 import abi
-    code = '#include <stdio.h>\n#include "pic_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(pic_fab), sizeof(pic_soa), sizeof(pic_stencil), sizeof(pic_bins), sizeof(pic_geom), sizeof(pic_escape_list));return 0;}\n'
+    code = '#include <stdio.h>\n#include "pic_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pic_fab), sizeof(pic_soa), sizeof(pic_stencil), sizeof(pic_bins), sizeof(pic_geom), sizeof(pic_escape_list), sizeof(pic_boundaries), sizeof(pic_laser_antenna), sizeof(pic_plasma_injector));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
         open(src, "w").write(code)
@@ -38,7 +38,8 @@ def test_ctypes_mirror_matches_header_layout():
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(abi.pic_fab), C.sizeof(abi.pic_soa), C.sizeof(abi.pic_stencil),
-                     C.sizeof(abi.pic_bins), C.sizeof(abi.pic_geom), C.sizeof(abi.pic_escape_list)]
+                     C.sizeof(abi.pic_bins), C.sizeof(abi.pic_geom), C.sizeof(abi.pic_escape_list),
+                     C.sizeof(abi.pic_boundaries), C.sizeof(abi.pic_laser_antenna), C.sizeof(abi.pic_plasma_injector)]
 
 
 def test_no_cpu_fallback():

@@ -1,0 +1,250 @@
+"""CPU tests (-m "not gpu") of the thin kernels in warpx_b200/csrc/lwfa.cu (PEC walls, moving-window
+shift, laser antenna, plasma injection, particle boundaries): the kernel BODIES and the host-side
+argument builders, run over the same thread ids by tests/host_harness (no GPU in the authoring
+container), against the oracle.  The same comparisons run on the device in test_gpu_lwfa.py."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from warpx_b200 import abi, workloads
+
+
+@pytest.fixture(scope="module")
+def hh():
+    from host_harness import harness
+    return harness.lib()
+
+
+def _check(L, rc):
+    assert rc == 0, L.pic_last_error().decode()
+
+
+def _sync_periodic_duplicates(f, periodic):
+    """Make the upper nodal layer of every periodic direction equal to the lower one (what
+    FillBoundaryAndSync / SumBoundary maintain in a run), guards included."""
+    a = f.a
+    for d in range(3):
+        if periodic[d] and f.desc.stag[d]:
+            ax = 2 - d
+            ng = f.desc.ng[d]
+            n = a.shape[ax] - 2 * ng - 1
+            sl_hi = [slice(None)] * 3
+            sl_lo = [slice(None)] * 3
+            sl_hi[ax], sl_lo[ax] = ng + n, ng
+            a[tuple(sl_hi)] = a[tuple(sl_lo)]
+
+
+BND = {
+    "pec_z": dict(field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"), periodic=(1, 1, 0)),
+    "pec_xz": dict(field_lo=("pec", "periodic", "pec"), field_hi=("pec", "periodic", "pec"), periodic=(0, 1, 0)),
+    "pec_zlo_only": dict(field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
+                         periodic=(1, 1, 0)),
+}
+
+
+@pytest.mark.parametrize("case", ["pec_z", "pec_xz"])
+@pytest.mark.parametrize("is_E", [1, 0])
+def test_pec_field_body_matches_oracle(orc, hh, case, is_E):
+    n, ng, ngfg = (6, 5, 9), (4, 4, 4), (2, 2, 2)
+    cfg = BND[case]
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=cfg["periodic"])
+    bnd = abi.make_boundaries(cfg["field_lo"], cfg["field_hi"])
+    rng = np.random.default_rng(11)
+    box_hi = tuple(v - 1 for v in n)
+    F = [orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[c + (0 if is_E else 3)]) for c in range(3)]
+    for f in F:
+        f.a[...] = rng.standard_normal(f.a.shape)
+    G = [orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[c + (0 if is_E else 3)], data=f.a.copy()) for c, f in enumerate(F)]
+    orc.lib().orc_apply_pec_field(orc.fab_array(F), is_E, C.byref(geom), C.byref(bnd), abi.int3(ngfg))
+    _check(hh, hh.pic_apply_pec_field(orc.fab_array(G), is_E, C.byref(geom), C.byref(bnd), abi.int3(ngfg), None))
+    for f, gq in zip(F, G):
+        assert np.array_equal(f.a, gq.a)
+
+
+@pytest.mark.parametrize("case,pbc", [("pec_z", None), ("pec_xz", None),
+                                      ("pec_z", (("periodic", "periodic", "reflecting"), ("periodic", "periodic", "absorbing")))])
+def test_pec_current_body_matches_oracle(orc, hh, case, pbc):
+    n, ng = (6, 5, 9), (5, 5, 5)
+    cfg = BND[case]
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=cfg["periodic"])
+    bnd = abi.make_boundaries(cfg["field_lo"], cfg["field_hi"], *(pbc or (None, None)))
+    rng = np.random.default_rng(12)
+    box_hi = tuple(v - 1 for v in n)
+    J = [orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[6 + c]) for c in range(3)]
+    for f in J:
+        f.a[...] = rng.standard_normal(f.a.shape)
+    K = [orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[6 + c], data=f.a.copy()) for c, f in enumerate(J)]
+    orc.lib().orc_apply_pec_current(orc.fab_array(J), C.byref(geom), C.byref(bnd))
+    _check(hh, hh.pic_apply_pec_current(orc.fab_array(K), C.byref(geom), C.byref(bnd), None))
+    for f, gq in zip(J, K):
+        assert np.array_equal(f.a, gq.a)
+
+
+@pytest.mark.parametrize("shift", [1, 2, -1])
+@pytest.mark.parametrize("comp", [0, 2, 4, 6, 8])
+def test_shift_body_matches_oracle(orc, hh, shift, comp):
+    n, ng = (6, 5, 9), (4, 4, 5) if comp >= 6 else (4, 4, 4)
+    periodic = (1, 1, 0)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=periodic)
+    rng = np.random.default_rng(13)
+    box_hi = tuple(v - 1 for v in n)
+    f = orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[comp])
+    f.a[...] = rng.standard_normal(f.a.shape)
+    _sync_periodic_duplicates(f, periodic)
+    h = orc.HostFab((0, 0, 0), box_hi, ng, abi.YEE_STAG[comp], data=f.a.copy())
+    tmp = np.empty(h.a.size)
+    orc.lib().orc_shift_fab(C.byref(f.desc), C.byref(geom), shift, 2, 0.25)
+    _check(hh, hh.pic_shift_fab(C.byref(h.desc), tmp.ctypes.data, C.byref(geom), shift, 2, 0.25, None))
+    assert np.array_equal(f.a, h.a)
+
+
+def _laser():
+    la = workloads.laser_acceleration_3d()["lasers"][0]
+    return abi.make_laser(la["position"], la["direction"], la["polarization"], la["wavelength"], la["e_max"],
+                          la["waist"], la["duration"], la["t_peak"], la["focal_distance"])
+
+
+@pytest.mark.parametrize("tilted", [False, True])
+def test_laser_antenna_setup_and_push_match_oracle(orc, hh, tilted):
+    wl = workloads.laser_acceleration_3d()
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+    las = _laser()
+    if tilted:      # propagation along x, polarisation in the y-z plane
+        for d, v in enumerate((1.0, 0.0, 0.0)):
+            las.nvec[d] = v
+        for d, v in enumerate((0.0, 1.0, 1.0)):
+            las.p_X[d] = v
+        for d, v in enumerate((-10.e-6, 1.e-6, -20.e-6)):
+            las.position[d] = v
+    dxa = abi.dbl3(dx)
+    info = (C.c_double * 4)()
+    _check(hh, hh.pic_laser_antenna_info(C.byref(las), dxa, info))
+    n = hh.pic_laser_antenna_particles(C.byref(las), dxa, abi.dbl3(wl["prob_lo"]), abi.dbl3(wl["prob_hi"]),
+                                       None, None, None, None, 0)
+    assert n > 0
+    A = [np.empty(n) for _ in range(4)]
+    assert hh.pic_laser_antenna_particles(C.byref(las), dxa, abi.dbl3(wl["prob_lo"]), abi.dbl3(wl["prob_hi"]),
+                                          *[a.ctypes.data for a in A], n) == n
+    B = [np.empty(n) for _ in range(4)]
+    dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
+    assert orc.lib().orc_antenna_particles(C.byref(las), dxa, abi.dbl3(wl["prob_lo"]), abi.dbl3(wl["prob_hi"]),
+                                           *[dp(b) for b in B], n) == n
+    for a, b in zip(A, B):
+        assert np.array_equal(a, b)
+    if not tilted:
+        assert n == 2 * 32 * 32 and info[0] == 1.875e-6 and info[3] == pytest.approx(9.960961289400001e-09, rel=1e-15)
+    z = np.zeros(n)
+    dt = 8.687655225973464e-16
+    for t in (0.0, 17 * dt, 30.e-15, 61 * dt):
+        P = orc.HostParticles(x=A[0], y=A[1], z=A[2], w=A[3], ux=z, uy=z, uz=z)
+        Q = P.copy()
+        orc.lib().orc_antenna_push(C.byref(las), dxa, C.byref(P.soa), t, dt)
+        _check(hh, hh.pic_laser_antenna_push(C.byref(las), dxa, C.byref(Q.soa), t, dt, None))
+        umax = max(np.max(np.abs(P.ux)), np.max(np.abs(P.uy)), np.max(np.abs(P.uz)))
+        assert umax > 0
+        for k in ("ux", "uy", "uz"):
+            assert np.max(np.abs(getattr(P, k) - getattr(Q, k))) <= 1e-13 * umax
+        for k in ("x", "y", "z"):
+            assert np.max(np.abs(getattr(P, k) - getattr(Q, k))) <= 1e-15 * dx[0]
+
+
+def _host_soa(n):
+    arrs = {k: np.full(n, np.nan) for k in ("x", "y", "z", "w", "ux", "uy", "uz")}
+    ids = np.zeros(n, dtype=np.uint64)
+    s = abi.pic_soa()
+    for k, a in arrs.items():
+        setattr(s, k, a.ctypes.data)
+    s.idcpu = ids.ctypes.data
+    s.np = 0
+    return s, arrs, ids
+
+
+@pytest.mark.parametrize("ppc", [(1, 1, 1), (2, 2, 2), (1, 2, 3), (3, 1, 2)])
+@pytest.mark.parametrize("slab", ["domain", "top_slab", "two_cells", "cut"])
+def test_add_plasma_matches_oracle(orc, hh, ppc, slab):
+    """PhysicalParticleContainer::AddPlasma on the regular lattice: positions, weights, creation order
+    and count, for the start-up call (whole domain) and for continuous-injection slabs, with plasma
+    bounds that cut through cells."""
+    n_cell, prob_lo, prob_hi = (8, 6, 16), (-30.e-6, -20.e-6, -56.e-6 + 3.1e-7), (30.e-6, 25.e-6, 12.e-6 + 3.1e-7)
+    geom = abi.make_geom(n_cell, prob_lo, prob_hi, periodic=(1, 1, 0))
+    dz = (prob_hi[2] - prob_lo[2]) / n_cell[2]
+    inf = math.inf
+    blo, bhi = (-20.e-6, -20.e-6, 0.0), (20.e-6, 11.e-6, inf)
+    if slab == "cut":
+        blo, bhi = (-7.3e-6, -3.1e-6, -31.7e-6), (9.9e-6, 8.4e-6, -2.2e-6)
+    inj = abi.make_injector(ppc, blo, bhi, 2.e23, True)
+    plo, phi = list(prob_lo), list(prob_hi)
+    if slab == "top_slab":
+        plo[2] = prob_hi[2] - dz
+    elif slab == "two_cells":
+        plo[2], phi[2] = prob_hi[2] - 2 * dz - 1e-22, prob_hi[2] - 1e-22
+    cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
+    s, arrs, ids = _host_soa(cap + 5)
+    s.np = 5                                  # appended after the particles already present
+    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s), cap + 5, 1000, None)
+    assert n >= 0, hh.pic_last_error().decode()
+    B = [np.empty(cap) for _ in range(4)]
+    dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
+    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(plo), abi.dbl3(phi), *[dp(b) for b in B], cap)
+    assert m == n and n > 0
+    for k, b in zip(("x", "y", "z", "w"), B):
+        assert np.array_equal(arrs[k][5:5 + n], b[:n]), k
+        assert np.all(np.isnan(arrs[k][:5])) and np.all(np.isnan(arrs[k][5 + n:]))
+    for k in ("ux", "uy", "uz"):
+        assert np.all(arrs[k][5:5 + n] == 0.0)
+    assert np.array_equal(ids[5:5 + n], 1000 + np.arange(n, dtype=np.uint64))
+
+
+def test_add_plasma_capacity_and_empty(hh):
+    geom = abi.make_geom((4, 4, 4), (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    inj = abi.make_injector((1, 1, 1), (0, 0, 0), (1, 1, 1), 1.0, True)
+    s, arrs, ids = _host_soa(10)
+    assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == -1
+    assert b"capacity" in hh.pic_last_error()
+    # a slab that lies outside the plasma bounds adds nothing
+    inj2 = abi.make_injector((1, 1, 1), (0, 0, 2.0), (1, 1, 3.0), 1.0, True)
+    assert hh.pic_add_plasma(C.byref(inj2), C.byref(geom), None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == 0
+
+
+@pytest.mark.parametrize("pbc_z", [("absorbing", "absorbing"), ("reflecting", "absorbing")])
+def test_particle_boundaries_match_oracle(orc, hh, pbc_z):
+    """ApplyBoundaryConditions + removal: the surviving particles (matched by id) and their reflected
+    positions / momenta equal the oracle's; the survivors are compacted into [0, np - n_lost)."""
+    rng = np.random.default_rng(21)
+    n = 5000
+    geom = abi.make_geom((8, 8, 8), (-1.0, -1.0, -2.0), (1.0, 1.0, 2.0), periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"),
+                              ("periodic", "periodic", pbc_z[0]), ("periodic", "periodic", pbc_z[1]))
+    arr = {k: rng.uniform(-1.2, 1.2, n) for k in ("x", "y")}
+    arr["z"] = rng.uniform(-2.3, 2.3, n)
+    arr["z"][-40:] = 2.2           # a lost tail
+    arr["z"][-80:-60] = 0.0        # survivors inside the tail
+    for k in ("w", "ux", "uy", "uz"):
+        arr[k] = rng.standard_normal(n)
+    P = orc.HostParticles(**arr)
+    keep = C.create_string_buffer(n)
+    orc.lib().orc_apply_particle_boundaries(C.byref(P.soa), C.byref(geom), C.byref(bnd), keep)
+    keep = np.frombuffer(keep.raw, dtype=np.int8)[:n].astype(bool)
+    Q = orc.HostParticles(**arr)
+    ids = np.arange(n, dtype=np.uint64)
+    Q.soa.idcpu = ids.ctypes.data
+    cap = 4096
+    work = np.zeros(hh.pic_particles_boundary_workspace_ints(cap), dtype=np.int32)
+    _check(hh, hh.pic_particles_boundary_mark(C.byref(Q.soa), C.byref(geom), C.byref(bnd), work.ctypes.data, cap, None))
+    n_lost = int(work[0])
+    assert n_lost == int(np.sum(~keep)) and 0 < n_lost < cap
+    _check(hh, hh.pic_particles_boundary_compact(C.byref(Q.soa), work.ctypes.data, cap, n_lost, None))
+    m = n - n_lost
+    got = ids[:m]
+    assert np.array_equal(np.sort(got), np.flatnonzero(keep).astype(np.uint64))
+    order = np.argsort(got)
+    for k in ("x", "y", "z", "w", "ux", "uy", "uz"):
+        assert np.array_equal(getattr(Q, k)[:m][order], getattr(P, k)[keep]), k
+    # list overflow is reported, not silently truncated
+    work[:] = 0
+    _check(hh, hh.pic_particles_boundary_mark(C.byref(orc.HostParticles(**arr).soa), C.byref(geom), C.byref(bnd),
+                                              work.ctypes.data, 8, None))
+    assert int(work[0]) == n_lost
+    assert hh.pic_particles_boundary_compact(C.byref(Q.soa), work.ctypes.data, 8, n_lost, None) != 0

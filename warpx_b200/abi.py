@@ -106,6 +106,22 @@ def make_injector(ppc, bound_lo, bound_hi, density, do_continuous_injection=Fals
     return inj
 
 
+def LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp):
+    """ctypes signatures of the non-periodic-domain entry points of include/pic_b200.h."""
+    return {
+        "pic_apply_pec_field": (C.c_int, [fabp, C.c_int, gp, bp, ip, vp]),
+        "pic_apply_pec_current": (C.c_int, [fabp, gp, bp, vp]),
+        "pic_shift_fab": (C.c_int, [fabp, vp, gp, C.c_int, C.c_int, C.c_double, vp]),
+        "pic_laser_antenna_info": (C.c_int, [lp, dp, dp]),
+        "pic_laser_antenna_particles": (C.c_long, [lp, dp, dp, dp, vp, vp, vp, vp, C.c_long]),
+        "pic_laser_antenna_push": (C.c_int, [lp, dp, soap, C.c_double, C.c_double, vp]),
+        "pic_add_plasma": (C.c_long, [jp, gp, dp, dp, dp, soap, C.c_long, C.c_uint64, vp]),
+        "pic_particles_boundary_workspace_ints": (C.c_long, [C.c_int]),
+        "pic_particles_boundary_mark": (C.c_int, [soap, gp, bp, vp, C.c_int, vp]),
+        "pic_particles_boundary_compact": (C.c_int, [soap, vp, C.c_int, C.c_int, vp]),
+    }
+
+
 SOLVER_YEE, SOLVER_CKC = 0, 1
 PIC_ERR_ABORT, PIC_ERR_RETURN = 0, 1
 PUSHER_BORIS, PUSHER_VAY, PUSHER_HC = 0, 1, 2

@@ -14,6 +14,11 @@
 //   dt                           <- WarpX::ComputeDt                       Evolve/WarpXComputeDt.cpp:56-95
 // All memory is borrowed from the caller (fields, particle SoA double buffers, bins, sort scratch);
 // every stage is an asynchronous launch on the caller's stream.
+// Non-periodic domains (pic_engine_set_boundaries / set_moving_window / set_injector / add_laser, one
+// rank): PEC walls after every field push and on J (BoundaryConditions/WarpXFieldBoundaries.cpp:51-190),
+// WarpX::MoveWindow with continuous injection (Utils/WarpXMovingWindow.cpp:139-476), laser antennas
+// (Particles/LaserParticleContainer.cpp:563-700), absorbing / reflecting particle boundaries
+// (Particles/WarpXParticleContainer.cpp:1574-1638) -- the additions of the laser-wakefield decks.
 // Multi-rank (one process per GPU, one brick per rank, pic_engine_set_comm): the guard-cell
 // exchanges and the particle migration go through NCCL send/recv on the same stream (csrc/comm.cu),
 // as three axis sweeps with two neighbours each; the host reads 32 bytes once per step (new particle
@@ -43,6 +48,23 @@ struct Species {
     double* mig_msg[4] = {nullptr, nullptr, nullptr, nullptr};   // send lo/hi, recv lo/hi
     int* mig_work = nullptr;
     int* mig_head = nullptr;     // pinned host, 8 ints
+    // plasma injector (continuous injection behind the moving window) and absorbing boundaries
+    bool has_injector = false;
+    pic_plasma_injector inj{};
+    double current_injection_position = 0.0;     // WarpXParticleContainer::m_current_injection_position
+    uint64_t next_id = 0;
+    int* bnd_work = nullptr;     // pic_particles_boundary_workspace_ints(bnd_cap) ints, engine-owned
+    int bnd_cap = 0;
+    bool bins_stale = false;     // particles were removed / the window moved: re-sort before the next step
+};
+
+// Laser antenna: its own particle container (LaserParticleContainer), no gather, order-agnostic deposit
+struct Laser {
+    pic_laser_antenna prm;
+    pic_soa P;                   // borrowed device arrays, P.np particles
+    long capacity;
+    int* bnd_work = nullptr;
+    int bnd_cap = 0;
 };
 
 struct Engine {
@@ -64,6 +86,17 @@ struct Engine {
     int nb[3] = {1, 1, 1}, coord[3] = {0, 0, 0};
     double* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // halo send lo/hi, recv lo/hi
     size_t hbuf_doubles = 0;
+    // non-periodic domains
+    pic_boundaries bnd{};
+    bool any_pec = false, all_periodic = true;
+    bool do_moving_window = false;
+    int mw_dir = 2;
+    double mw_v = 0.0, mw_x = 0.0;               // moving_window_v [m/s], moving_window_x
+    double cur_time = 0.0;                       // t_new[0]
+    double* shift_tmp = nullptr;                 // one component-sized scratch array
+    size_t shift_tmp_bytes = 0;
+    int* host_count = nullptr;                   // pinned host int (particles lost per boundary pass)
+    std::vector<Laser> lasers;
 };
 
 static bool spans(const Engine& e, int dim) { return e.comm == nullptr || e.nb[dim] == 1; }
@@ -122,7 +155,9 @@ static void guard_cells(Engine& e) {
     for (int d = 0; d < 3; ++d) {
         const int ngt = e.nox;
         int ng = (ngt % 2) ? ngt + 1 : ngt;
-        e.ng_J[d] = ngt + (int)ceil(C_LIGHT * 0.5 * e.dt / e.dx[d]);
+        int ngJ = ngt;
+        if (e.do_moving_window) { ng = ng > 2 ? ng : 2; ngJ = ngJ > 2 ? ngJ : 2; }   // GuardCellManager.cpp:103-115
+        e.ng_J[d] = ngJ + (int)ceil(C_LIGHT * 0.5 * e.dt / e.dx[d]);
         if (e.use_filter) e.ng_J[d] += e.npass[d];     // + stencil_length - 1, GuardCellManager.cpp:169-172
         e.ng_FS[d] = 1;
         ng = ng > e.ng_FS[d] ? ng : e.ng_FS[d];
@@ -146,11 +181,16 @@ static void lower_corner(const Engine& e, const int ng[3], double xyzmin[3], int
 // One axis sweep of FillBoundary (mode 0) / SumBoundary (mode 1) over nfab components: local kernels
 // when this rank spans the periodic domain along dim, otherwise pack -> NCCL -> unpack(+add) with
 // one message per direction carrying the slabs of all components.
-static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng, int mode, void* s) {
+// all_guards: the refresh after SumBoundary also covers the guards beyond a non-periodic face (they are
+// part of SumBoundary's destination); a plain FillBoundary leaves them alone (see pic_fill_boundary_local).
+static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng, int mode, void* s, bool all_guards = false) {
     if (ng == 0 && mode == 0) return 0;
+    if (!e.geom.periodic[dim]) return 0;     // domain-spanning box (set_boundaries enforces it): no image, guards keep their values
     if (spans(e, dim)) {
+        pic_geom gfull = e.geom;
+        if (all_guards) gfull.periodic[0] = gfull.periodic[1] = gfull.periodic[2] = 1;
         for (int c = 0; c < nfab; ++c) {
-            if (mode == 0) ENG_CALL(pic_fill_boundary_local(&fabs[c], dim, ng, &e.geom, s));
+            if (mode == 0) ENG_CALL(pic_fill_boundary_local(&fabs[c], dim, ng, all_guards ? &gfull : &e.geom, s));
             else ENG_CALL(pic_sum_boundary_local(&fabs[c], dim, ng, &e.geom, s));
         }
         return 0;
@@ -170,8 +210,8 @@ static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng,
     return 0;
 }
 
-static int fill_boundary(Engine& e, int c0, int c1, const int ng[3], void* s) {
-    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(e, &e.fab[c0], c1 - c0, d, ng[d], 0, s));
+static int fill_boundary(Engine& e, int c0, int c1, const int ng[3], void* s, bool all_guards = false) {
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(e, &e.fab[c0], c1 - c0, d, ng[d], 0, s, all_guards));
     return 0;
 }
 
@@ -193,7 +233,10 @@ static int sync_current(Engine& e, void* s) {
     // SumBoundaryJ: src = ng_depos_J (+ stencil_length-1 with the filter, WarpXComm.cpp:1413-1416) == ng_J
     // either way; then all guards of J are refreshed (WarpXSumGuardCells.cpp:22-23)
     for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(e, &e.fab[6], 3, d, e.ng_J[d], 1, s));
-    return fill_boundary(e, 6, 9, e.ng_J, s);
+    ENG_CALL(fill_boundary(e, 6, 9, e.ng_J, s, true));
+    // reflect J over PEC / reflecting boundaries (WarpX::SyncCurrentAndRho, WarpXEvolve.cpp:629-640)
+    if (!e.all_periodic) ENG_CALL(pic_apply_pec_current(&e.fab[6], &e.geom, &e.bnd, s));
+    return 0;
 }
 
 static int push(Engine& e, Species& sp, double dt, int push_position, void* s) {
@@ -216,6 +259,14 @@ static int push_particles_and_deposit(Engine& e, void* s) {
         const pic_soa& P = sp.buf[sp.cur];
         ENG_CALL(pic_deposit_esirkepov(&P, 0, P.np, &e.fab[6], e.dinv, xyzmin, lo, sp.q, e.dt, -0.5 * e.dt,
                                        e.nox, sp.has_bins ? &sp.bins : nullptr, s));
+    }
+    // the antennas come after the species in allcontainers (MultiParticleContainer.cpp:60-75);
+    // LaserParticleContainer::Evolve (:563-700): push at t^n, deposit with charge = 1 (:88)
+    for (auto& L : e.lasers) {
+        if (L.P.np == 0) continue;
+        ENG_CALL(pic_laser_antenna_push(&L.prm, e.dx, &L.P, e.cur_time, e.dt, s));
+        ENG_CALL(pic_deposit_esirkepov(&L.P, 0, L.P.np, &e.fab[6], e.dinv, xyzmin, lo, 1.0, e.dt, -0.5 * e.dt,
+                                       e.nox, nullptr, s));
     }
     return 0;
 }
@@ -276,6 +327,103 @@ static int migrate(Engine& e, Species& sp, void* stream) {
     return 0;
 }
 
+// WarpX::EvolveB / EvolveE end with ApplyBfieldBoundary / ApplyEfieldBoundary
+// (FieldSolver/WarpXPushFieldsEM.cpp:926,990): PEC over the valid points grown by ng_FieldGather.
+static int evolve_b(Engine& e, double dt, void* s) {
+    ENG_CALL(pic_evolve_b(&e.fab[3], &e.fab[0], &e.st, dt, s));
+    if (e.any_pec) ENG_CALL(pic_apply_pec_field(&e.fab[3], 0, &e.geom, &e.bnd, e.ng_FG, s));
+    return 0;
+}
+static int evolve_e(Engine& e, double dt, void* s) {
+    ENG_CALL(pic_evolve_e(&e.fab[0], &e.fab[3], &e.fab[6], &e.st, dt, s));
+    if (e.any_pec) ENG_CALL(pic_apply_pec_field(&e.fab[0], 1, &e.geom, &e.bnd, e.ng_FG, s));
+    return 0;
+}
+
+static int shift_component(Engine& e, int c, int num_shift, void* s) {
+    const size_t bytes = sizeof(double) * (size_t)fab_size(e.fab[c]);
+    if (bytes > e.shift_tmp_bytes) {
+        if (e.shift_tmp) cudaFree(e.shift_tmp);
+        if (cudaMalloc(&e.shift_tmp, bytes) != cudaSuccess) return fail("pic_engine: moving-window scratch allocation failed");
+        e.shift_tmp_bytes = bytes;
+    }
+    return pic_shift_fab(&e.fab[c], e.shift_tmp, &e.geom, num_shift, e.mw_dir, 0.0 /* no external field */, s);
+}
+
+// WarpX::MoveWindow (Utils/WarpXMovingWindow.cpp:139-476), one level, lab frame, no PML: advance
+// moving_window_x; when it has covered whole cells shift E, B (and J when move_j), move the problem
+// domain, and let the continuously injected species fill the uncovered slab.
+static int move_window(Engine& e, bool move_j, int* num_moved, void* s) {
+    *num_moved = 0;
+    if (!e.do_moving_window) return 0;
+    const int dir = e.mw_dir;
+    e.mw_x += (e.mw_v - 0.0 * C_LIGHT) / (1 - e.mw_v * 0.0 / C_LIGHT) * e.dt;            // :155 (beta_boost = 0)
+    const double cdx = e.dx[dir];
+    const int nsb = static_cast<int>((e.mw_x - e.geom.prob_lo[dir]) / cdx);              // :171
+    if (nsb == 0) return 0;
+    e.geom.prob_lo[dir] = e.geom.prob_lo[dir] + nsb * cdx;                                // :181-186
+    e.geom.prob_hi[dir] = e.geom.prob_hi[dir] + nsb * cdx;
+    for (int dim = 0; dim < 3; ++dim) {                                                   // :226-266
+        ENG_CALL(shift_component(e, 3 + dim, nsb, s));
+        ENG_CALL(shift_component(e, dim, nsb, s));
+        if (move_j) ENG_CALL(shift_component(e, 6 + dim, nsb, s));
+    }
+    for (auto& sp : e.species) {                                                          // :388-438
+        if (!sp.has_injector || !sp.inj.do_continuous_injection) continue;
+        double new_pos = sp.current_injection_position;
+        if (e.mw_v > 0.0)
+            new_pos = sp.current_injection_position + floor((e.geom.prob_hi[dir] - sp.current_injection_position) / cdx) * cdx;
+        else if (e.mw_v < 0.0)
+            new_pos = sp.current_injection_position - floor((sp.current_injection_position - e.geom.prob_lo[dir]) / cdx) * cdx;
+        double plo[3], phi[3];
+        for (int d = 0; d < 3; ++d) { plo[d] = e.geom.prob_lo[d]; phi[d] = e.geom.prob_hi[d]; }
+        if (e.mw_v > 0.0) { plo[dir] = sp.current_injection_position; phi[dir] = new_pos; }
+        else if (e.mw_v < 0.0) { plo[dir] = new_pos; phi[dir] = sp.current_injection_position; }
+        const bool ok = plo[0] < phi[0] && plo[1] < phi[1] && plo[2] < phi[2];            // RealBox::ok
+        if (ok && sp.current_injection_position != new_pos) {
+            pic_soa& P = sp.buf[sp.cur];
+            const long added = pic_add_plasma(&sp.inj, &e.geom, e.dx, plo, phi, &P, sp.capacity, sp.next_id, s);
+            if (added < 0) return 1;
+            P.np += added;
+            sp.next_id += (uint64_t)added;
+            sp.current_injection_position = new_pos;
+        }
+    }
+    for (auto& sp : e.species) sp.bins_stale = true;     // every particle changed cell along dir
+    *num_moved = nsb;
+    return 0;
+}
+
+// mypc->ApplyBoundaryConditions() over species and lasers (MultiParticleContainer.cpp:659-664) and the
+// removal AMReX Redistribute performs: all marks first, ONE host read of the counts, then the compactions.
+static int apply_particle_boundaries(Engine& e, void* stream) {
+    if (e.all_periodic) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nsp = e.species.size(), ncont = nsp + e.lasers.size();
+    if (ncont == 0) return 0;
+    for (size_t n = 0; n < ncont; ++n) {
+        const bool is_sp = n < nsp;
+        pic_soa& P = is_sp ? e.species[n].buf[e.species[n].cur] : e.lasers[n - nsp].P;
+        int* work = is_sp ? e.species[n].bnd_work : e.lasers[n - nsp].bnd_work;
+        const int cap = is_sp ? e.species[n].bnd_cap : e.lasers[n - nsp].bnd_cap;
+        ENG_CALL(pic_particles_boundary_mark(&P, &e.geom, &e.bnd, work, cap, s));
+        cudaMemcpyAsync(e.host_count + n, work, sizeof(int), cudaMemcpyDeviceToHost, s);
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail("pic_engine: particle boundary pass failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    for (size_t n = 0; n < ncont; ++n) {
+        const int lost = e.host_count[n];
+        if (lost == 0) continue;
+        const bool is_sp = n < nsp;
+        pic_soa& P = is_sp ? e.species[n].buf[e.species[n].cur] : e.lasers[n - nsp].P;
+        int* work = is_sp ? e.species[n].bnd_work : e.lasers[n - nsp].bnd_work;
+        const int cap = is_sp ? e.species[n].bnd_cap : e.lasers[n - nsp].bnd_cap;
+        ENG_CALL(pic_particles_boundary_compact(&P, work, cap, lost, s));
+        P.np -= lost;
+        if (is_sp) e.species[n].bins_stale = true;
+    }
+    return 0;
+}
+
 static int one_step(Engine& e, bool last, void* s) {
     // ---- ExplicitFillBoundaryEBUpdateAux ----
     if (e.is_synchronized) {
@@ -288,24 +436,36 @@ static int one_step(Engine& e, bool last, void* s) {
     // ---- OneStep_nosub ----
     ENG_CALL(push_particles_and_deposit(e, s));
     ENG_CALL(sync_current(e, s));
-    ENG_CALL(pic_evolve_b(&e.fab[3], &e.fab[0], &e.st, 0.5 * e.dt, s));
+    ENG_CALL(evolve_b(e, 0.5 * e.dt, s));
     ENG_CALL(fill_boundary(e, 3, 6, e.ng_FS, s));
-    ENG_CALL(pic_evolve_e(&e.fab[0], &e.fab[3], &e.fab[6], &e.st, e.dt, s));
+    ENG_CALL(evolve_e(e, e.dt, s));
     ENG_CALL(fill_boundary(e, 0, 3, e.ng_FS, s));
-    ENG_CALL(pic_evolve_b(&e.fab[3], &e.fab[0], &e.st, 0.5 * e.dt, s));
+    ENG_CALL(evolve_b(e, 0.5 * e.dt, s));
     if (last) {                                                           // Synchronize(), :64-91
         ENG_CALL(fill_boundary(e, 0, 6, e.ng_FG, s));
         for (auto& sp : e.species) ENG_CALL(push(e, sp, 0.5 * e.dt, 0, s));
         e.is_synchronized = true;
     }
-    // ---- HandleParticlesAtBoundaries ----
     const long step = e.istep++;
+    e.cur_time += e.dt;                                                   // :232
+    // ---- MoveWindow(step+1, move_j = is_synchronized), :247 ----
+    int num_moved = 0;
+    ENG_CALL(move_window(e, e.is_synchronized, &num_moved, s));
+    // ---- HandleParticlesAtBoundaries ----
     for (auto& sp : e.species) {
         // amrex enforcePeriodic: only the particles the push of this step moved out of the domain
+        // (done before the removal below, while the indices listed by the push are still valid; the
+        // two act on different directions)
         if (sp.has_esc) ENG_CALL(pic_particles_wrap_listed(&sp.buf[sp.cur], &e.geom, &sp.esc, s));
         else ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
+    }
+    for (auto& L : e.lasers) ENG_CALL(pic_particles_wrap_periodic(&L.P, &e.geom, s));
+    ENG_CALL(apply_particle_boundaries(e, s));
+    for (auto& sp : e.species) {
         if (e.comm) ENG_CALL(migrate(e, sp, s));
-        if (sp.sort_work && e.sort_interval > 0 && (step + 1) % e.sort_interval == 0) ENG_CALL(sort_species(e, sp, s));
+        const bool due = e.sort_interval > 0 && (step + 1) % e.sort_interval == 0;
+        if (sp.sort_work && (due || (sp.bins_stale && sp.has_bins))) ENG_CALL(sort_species(e, sp, s));
+        sp.bins_stale = false;
     }
     return 0;
 }
@@ -313,6 +473,9 @@ static int one_step(Engine& e, bool last, void* s) {
 }  // namespace pic
 
 using namespace pic;
+
+static int alloc_boundary_scratch(long capacity, int** work, int* cap);
+static int grow_host_counts(Engine& e);
 
 extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
                                    int galerkin, int pusher, int solver, double cfl, double dt,
@@ -343,7 +506,11 @@ extern "C" void pic_engine_destroy(void* h) {
             for (int b = 0; b < 4; ++b) if (sp.mig_msg[b]) cudaFree(sp.mig_msg[b]);
             if (sp.mig_work) cudaFree(sp.mig_work);
             if (sp.mig_head) cudaFreeHost(sp.mig_head);
+            if (sp.bnd_work) cudaFree(sp.bnd_work);
         }
+        for (auto& L : e->lasers) if (L.bnd_work) cudaFree(L.bnd_work);
+        if (e->shift_tmp) cudaFree(e->shift_tmp);
+        if (e->host_count) cudaFreeHost(e->host_count);
         for (int b = 0; b < 4; ++b) if (e->hbuf[b]) cudaFree(e->hbuf[b]);
     }
     delete e;
@@ -405,7 +572,9 @@ extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa
         for (int b = 0; b < 4; ++b) cudaMemsetAsync(sp.mig_msg[b], 0, sizeof(double) * nmsg, (cudaStream_t)stream);
         cudaMemsetAsync(sp.mig_work, 0, (size_t)pic_migrate_workspace_bytes(sp.mig_cap_max), (cudaStream_t)stream);
     }
+    if (!e->all_periodic) ENG_CALL(alloc_boundary_scratch(capacity, &sp.bnd_work, &sp.bnd_cap));
     e->species.push_back(sp);
+    ENG_CALL(grow_host_counts(*e));
     if (cell_start && sort_work) return sort_species(*e, e->species.back(), stream);
     return 0;
 }
@@ -417,6 +586,7 @@ extern "C" int pic_engine_set_comm(void* h, void* comm, const int nb[3]) {
     PIC_REQUIRE(c && c->comm, "pic_engine_set_comm: no communicator");
     PIC_REQUIRE(nb[0] * nb[1] * nb[2] == c->nranks, "pic_engine_set_comm: brick grid %dx%dx%d != %d ranks", nb[0], nb[1], nb[2], c->nranks);
     PIC_REQUIRE(e->species.empty(), "pic_engine_set_comm: call before pic_engine_add_species");
+    PIC_REQUIRE(e->all_periodic, "pic_engine_set_comm: the multi-rank driver is periodic only");
     e->comm = c;
     int r = c->rank;
     for (int d = 0; d < 3; ++d) {
@@ -429,6 +599,81 @@ extern "C" int pic_engine_set_comm(void* h, void* comm, const int nb[3]) {
                     "pic_engine_set_comm: box [%d,%d] along %d is not brick %d of %d", e->box_lo[d], e->box_hi[d], d, e->coord[d], nb[d]);
     }
     return 0;
+}
+// ---- non-periodic runs ------------------------------------------------------------------------
+static int alloc_boundary_scratch(long capacity, int** work, int* cap) {
+    const long c = capacity / 16 + 65536;
+    *cap = (int)(c < capacity + 1 ? c : capacity + 1);
+    if (cudaMalloc(work, sizeof(int) * (size_t)pic_particles_boundary_workspace_ints(*cap)) != cudaSuccess)
+        return fail("pic_engine: cannot allocate the particle-boundary scratch");
+    return 0;
+}
+static int grow_host_counts(Engine& e) {
+    const size_t n = e.species.size() + e.lasers.size() + 1;
+    int* mem = nullptr;
+    if (cudaMallocHost(&mem, sizeof(int) * n) != cudaSuccess) return fail("pic_engine: cannot allocate pinned host memory");
+    if (e.host_count) cudaFreeHost(e.host_count);
+    e.host_count = mem;
+    return 0;
+}
+extern "C" int pic_engine_set_boundaries(void* h, const pic_boundaries* b) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(e->species.empty() && e->lasers.empty(), "pic_engine_set_boundaries: call before adding particles");
+    e->bnd = *b;
+    e->any_pec = false; e->all_periodic = true;
+    for (int d = 0; d < 3; ++d) {
+        const bool per = b->field_lo[d] == PIC_FIELD_PERIODIC;
+        PIC_REQUIRE(per == (b->field_hi[d] == PIC_FIELD_PERIODIC), "pic_engine_set_boundaries: direction %d is periodic on one side only", d);
+        e->geom.periodic[d] = per ? 1 : 0;
+        if (per) e->bnd.particle_lo[d] = e->bnd.particle_hi[d] = PIC_PARTICLE_PERIODIC;
+        else {
+            PIC_REQUIRE(b->particle_lo[d] != PIC_PARTICLE_PERIODIC && b->particle_hi[d] != PIC_PARTICLE_PERIODIC,
+                        "pic_engine_set_boundaries: periodic particles on the non-periodic direction %d", d);
+            PIC_REQUIRE(e->nb[d] == 1 && e->box_lo[d] == 0 && e->box_hi[d] == e->geom.n_cell[d] - 1,
+                        "pic_engine_set_boundaries: the box must span the domain along the non-periodic direction %d", d);
+            e->all_periodic = false;
+        }
+        e->any_pec = e->any_pec || b->field_lo[d] == PIC_FIELD_PEC || b->field_hi[d] == PIC_FIELD_PEC;
+    }
+    return 0;
+}
+extern "C" int pic_engine_set_moving_window(void* h, int dir, double v_over_c) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(dir >= 0 && dir < 3, "pic_engine_set_moving_window: bad direction");
+    PIC_REQUIRE(!e->geom.periodic[dir], "The problem must be non-periodic in the moving window direction");   // WarpX.cpp:646-648
+    PIC_REQUIRE(e->species.empty() && e->lasers.empty(), "pic_engine_set_moving_window: call before adding particles");
+    PIC_REQUIRE(e->comm == nullptr, "pic_engine_set_moving_window: one rank only");
+    e->do_moving_window = true; e->mw_dir = dir; e->mw_v = v_over_c * C_LIGHT;
+    e->mw_x = e->geom.prob_lo[dir];                      // WarpX.cpp:649
+    guard_cells(*e);
+    return 0;
+}
+extern "C" int pic_engine_set_injector(void* h, int isp, const pic_plasma_injector* inj) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(isp >= 0 && isp < (int)e->species.size(), "pic_engine_set_injector: no species %d", isp);
+    Species& sp = e->species[isp];
+    sp.has_injector = true; sp.inj = *inj;
+    sp.next_id = (uint64_t)sp.buf[sp.cur].np;
+    if (e->do_moving_window)                            // WarpX.cpp:288-307
+        sp.current_injection_position = e->mw_v > 0 ? e->geom.prob_hi[e->mw_dir] : e->geom.prob_lo[e->mw_dir];
+    return 0;
+}
+extern "C" int pic_engine_add_laser(void* h, const pic_laser_antenna* prm, const pic_soa* p, long capacity) {
+    Engine* e = static_cast<Engine*>(h);
+    double info[4];
+    ENG_CALL(pic_laser_antenna_info(prm, e->dx, info));
+    PIC_REQUIRE(capacity >= p->np, "pic_engine_add_laser: capacity %ld < np %ld", capacity, (long)p->np);
+    Laser L;
+    L.prm = *prm; L.P = *p; L.capacity = capacity;
+    if (!e->all_periodic) ENG_CALL(alloc_boundary_scratch(capacity, &L.bnd_work, &L.bnd_cap));
+    e->lasers.push_back(L);
+    return grow_host_counts(*e);
+}
+extern "C" long pic_engine_laser_np(void* h, int il) { return (long)static_cast<Engine*>(h)->lasers[il].P.np; }
+extern "C" double pic_engine_time(void* h) { return static_cast<Engine*>(h)->cur_time; }
+extern "C" void pic_engine_prob_domain(void* h, double out[6]) {
+    Engine* e = static_cast<Engine*>(h);
+    for (int d = 0; d < 3; ++d) { out[d] = e->geom.prob_lo[d]; out[3 + d] = e->geom.prob_hi[d]; }
 }
 // which of the two buffers currently holds species isp, and its particle count
 extern "C" int pic_engine_species_buffer(void* h, int isp, long* np) {

@@ -140,6 +140,11 @@ extern "C" int pic_fill_boundary_local(const pic_fab* f, int dim, int ng, const 
     PIC_REQUIRE(vh - vl + 1 - f->stag[dim] == N, "pic_fill_boundary_local: box does not span the domain in dim %d", dim);
     PIC_REQUIRE(ng <= f->ng[dim] && ng <= N, "pic_fill_boundary_local: ng=%d exceeds allocated guards", ng);
     Slab sl; full_extent(*f, sl); sl.dim = dim; sl.n[dim] = 2 * ng;
+    // Along a non-periodic direction the guards beyond the domain face have no periodic image: AMReX
+    // FillBoundary leaves (guard of dim) x (guard beyond that face) untouched, so the slab covers
+    // only the valid indices there.  (Periodic directions keep the full allocated extent.)
+    for (int d = 0; d < 3; ++d)
+        if (d != dim && !g->periodic[d]) { sl.start[d] = vlo(*f, d); sl.n[d] = vhi(*f, d) - vlo(*f, d) + 1; }
     const long total = (long)sl.n[0] * sl.n[1] * sl.n[2];
     fill_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         make_view(*f), dim, N, vl, vh, ng, sl, total);

@@ -25,6 +25,8 @@ def lib():
                                C.POINTER(abi.pic_bins))
     dp, ip, vp = abi.c_double_p, abi.c_int_p, C.c_void_p
     escp = C.POINTER(abi.pic_escape_list)
+    bndp, lasp, injp = (C.POINTER(abi.pic_boundaries), C.POINTER(abi.pic_laser_antenna),
+                        C.POINTER(abi.pic_plasma_injector))
     sig = {
         "pic_set_error_mode": (None, [C.c_int]),
         "pic_last_error": (C.c_char_p, []),
@@ -69,7 +71,15 @@ def lib():
         "pic_comm_destroy": (None, [vp]),
         "pic_engine_species_buffer": (C.c_int, [vp, C.c_int, C.POINTER(C.c_long)]),
         "pic_engine_evolve": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "pic_engine_set_boundaries": (C.c_int, [vp, bndp]),
+        "pic_engine_set_moving_window": (C.c_int, [vp, C.c_int, C.c_double]),
+        "pic_engine_set_injector": (C.c_int, [vp, C.c_int, injp]),
+        "pic_engine_add_laser": (C.c_int, [vp, lasp, soap, C.c_long]),
+        "pic_engine_laser_np": (C.c_long, [vp, C.c_int]),
+        "pic_engine_time": (C.c_double, [vp]),
+        "pic_engine_prob_domain": (None, [vp, dp]),
     }
+    sig.update(abi.LWFA_SIGNATURES(fabp, soap, gp, bndp, lasp, injp, dp, ip, vp))
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError if include/pic_b200.h and the library disagree
         fn.restype = res
