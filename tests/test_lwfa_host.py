@@ -248,3 +248,19 @@ def test_particle_boundaries_match_oracle(orc, hh, pbc_z):
                                               work.ctypes.data, 8, None))
     assert int(work[0]) == n_lost
     assert hh.pic_particles_boundary_compact(C.byref(Q.soa), work.ctypes.data, 8, n_lost, None) != 0
+
+
+def test_host_guard_cells_with_moving_window_match_oracle(orc):
+    """engine.guard_cells (the Python mirror of guardCellManager::Init) against the oracle's, for the
+    laser-acceleration deck: the moving window raises ng_EB / ng_J to at least 2."""
+    from test_oracle import make_lwfa_oracle
+    from warpx_b200 import engine
+    wl = workloads.laser_acceleration_3d()
+    osim = make_lwfa_oracle(orc, wl)
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+    g = engine.guard_cells(wl["nox"], osim.dt, dx, True, (1, 1, 1), do_moving_window=True)
+    og = osim.guards()
+    assert (g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]) == (og["ng_EB"], og["ng_J"], og["ng_FG"], og["ng_FS"])
+    assert engine.max_dt(abi.SOLVER_YEE, dx) == osim.dt
+    g1 = engine.guard_cells(1, osim.dt, dx, False, (1, 1, 1), do_moving_window=True)
+    assert g1["ng_EB"] == [2, 2, 2] and g1["ng_J"] == [3, 3, 3]

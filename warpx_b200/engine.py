@@ -66,15 +66,19 @@ def max_dt(solver, dx):
     return min(dx) / C_LIGHT
 
 
-def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1)):
+def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1), do_moving_window=False):
     """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-172, 310-343) for: no MR, no
-    NCI corrector, no moving window, not safe_guard_cells, FDTD solver.  Returns also ng_depos_J
-    (:165) -- ng_J itself grows by stencil_length-1 = npass when the bilinear filter is on (:169-172)."""
+    NCI corrector, not safe_guard_cells, FDTD solver.  Returns also ng_depos_J (:165) -- ng_J itself
+    grows by stencil_length-1 = npass when the bilinear filter is on (:169-172); a moving window needs
+    at least 2 guard cells everywhere (:103-115, one level)."""
     ng_EB, ng_J, ng_FG, ng_FS, ng_depos_J = [], [], [], [], []
     for d in range(3):
         ngt = nox
         ng = ngt + 1 if ngt % 2 else ngt
-        ngj = ngt + int(math.ceil(C_LIGHT * 0.5 * dt / dx[d]))
+        ngj0 = ngt
+        if do_moving_window:
+            ng, ngj0 = max(ng, 2), max(ngj0, 2)
+        ngj = ngj0 + int(math.ceil(C_LIGHT * 0.5 * dt / dx[d]))
         fs = 1
         ng = max(ng, fs)
         fg = max(min((nox + 1) // 2, ng), fs)
@@ -176,7 +180,10 @@ class Simulation:
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
                  tile=(8, 8, 8), use_bins=True, device=None, native_driver=True,
-                 use_filter=False, filter_npass=(1, 1, 1)):
+                 use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None):
+        """boundaries: abi.pic_boundaries (boundary.field_lo/hi, boundary.particle_lo/hi; default all
+        periodic); moving_window: (direction, v/c) == warpx.do_moving_window / moving_window_dir /
+        moving_window_v.  Non-periodic runs use the C++ driver on one rank."""
         self.torch = require_cuda()
         t = self.torch
         self.L = lib()
@@ -194,7 +201,16 @@ class Simulation:
         self.dt = dt if dt else cfl * max_dt(solver, self.dx)
         self.st = stencil_coefficients(solver, self.dx)
         self.use_filter, self.filter_npass = bool(use_filter), tuple(int(v) for v in filter_npass)
-        g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass)
+        self.boundaries, self.moving_window = boundaries, moving_window
+        if boundaries is not None:
+            for d in range(3):
+                self.geom.periodic[d] = 1 if boundaries.field_lo[d] == abi.FIELD_PERIODIC else 0
+        self.nonperiodic = not all(self.geom.periodic[d] for d in range(3))
+        if (self.nonperiodic or moving_window is not None) and not (native_driver and use_bins and dist is None):
+            raise NotImplementedError("non-periodic / moving-window runs need the C++ driver on one rank")
+        self.lasers = []
+        self.time = 0.0
+        g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass, moving_window is not None)
         self.ng_EB, self.ng_J, self.ng_FG, self.ng_FS = g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]
         self.ng_depos_J = g["ng_depos_J"]
         self._filter_tmp = None
@@ -231,6 +247,10 @@ class Simulation:
             self.native = self.L.pic_engine_create(C.byref(self.geom), abi.int3(self.box_lo), abi.int3(self.box_hi),
                                                    nox, galerkin, pusher, solver, cfl, self.dt, sort_interval,
                                                    1 if self.use_filter else 0, abi.int3(self.filter_npass))
+            if boundaries is not None:
+                check(self.L.pic_engine_set_boundaries(self.native, C.byref(boundaries)))
+            if moving_window is not None:
+                check(self.L.pic_engine_set_moving_window(self.native, int(moving_window[0]), float(moving_window[1])))
             g12 = (C.c_int * 12)()
             self.L.pic_engine_guards(self.native, g12)
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
@@ -301,6 +321,66 @@ class Simulation:
         elif self.use_bins:
             self.SortParticlesByBin(sp)
         return sp
+
+    def add_plasma_species(self, name, q, m, injector, capacity):
+        """A species created on the device by its plasma injector (PhysicalParticleContainer::InitData ->
+        AddPlasma over the whole domain, PhysicalParticleContainer.cpp:450-454,855-922); with
+        injector.do_continuous_injection the moving window keeps refilling the uncovered slab.
+        capacity: entries of every particle array (the run must never exceed it)."""
+        if not self.native:
+            raise NotImplementedError("plasma injectors need the C++ driver")
+        empty = np.empty(0)
+        sp = Species(self, name, q, m, {k: empty for k in Species.NAMES}, int(capacity))
+        soa = sp.soa(0)
+        n = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.dbl3(self.prob_lo),
+                                  abi.dbl3(self.prob_hi), C.byref(soa), sp.capacity, 0, self.stream)
+        if n < 0:
+            raise RuntimeError("pic_b200: " + self.L.pic_last_error().decode())
+        sp.np = int(n)
+        self.species.append(sp)
+        self._alloc_sort_scratch(sp)
+        a, b = sp.soa(0), sp.soa(1)
+        check(self.L.pic_engine_add_species(self.native, q, m, C.byref(a), C.byref(b), sp.capacity,
+                                            sp.cell_start.data_ptr(), abi.int3(self.tile), sp.work.data_ptr(),
+                                            self.stream))
+        check(self.L.pic_engine_set_injector(self.native, len(self.species) - 1, C.byref(injector)))
+        self._sync_from_native()
+        return sp
+
+    def add_laser(self, laser):
+        """lasers.names / <laser>.*: a Gaussian antenna (LaserParticleContainer ctor + InitData,
+        LaserParticleContainer.cpp:84-270,369-560).  The antenna particles are generated on the host like
+        the reference does and uploaded once."""
+        if not self.native:
+            raise NotImplementedError("laser antennas need the C++ driver")
+        t = self.torch
+        dxa, lo, hi = abi.dbl3(self.dx), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi)
+        n = self.L.pic_laser_antenna_particles(C.byref(laser), dxa, lo, hi, None, None, None, None, 0)
+        host = np.zeros((7, max(n, 1)))
+        if n > 0:
+            got = self.L.pic_laser_antenna_particles(C.byref(laser), dxa, lo, hi, host[0].ctypes.data, host[1].ctypes.data,
+                                                     host[2].ctypes.data, host[3].ctypes.data, n)
+            assert got == n
+        buf = t.from_numpy(host).to(self.device)
+        ids = t.arange(max(n, 1), dtype=t.int64, device=self.device)
+        soa = abi.pic_soa()
+        for k, name in enumerate(Species.NAMES):
+            setattr(soa, name, buf[k].data_ptr())
+        soa.idcpu = ids.data_ptr()
+        soa.np = n
+        check(self.L.pic_engine_add_laser(self.native, C.byref(laser), C.byref(soa), max(n, 1)))
+        self.lasers.append(dict(laser=laser, buf=buf, ids=ids, np=n))
+        return len(self.lasers) - 1
+
+    def laser_numpy(self, il, sort_by_id=True):
+        la = self.lasers[il]
+        n = int(self.L.pic_engine_laser_np(self.native, il))
+        out = {name: la["buf"][k, :n].cpu().numpy() for k, name in enumerate(Species.NAMES)}
+        out["id"] = la["ids"][:n].cpu().numpy()
+        if sort_by_id:
+            order = np.argsort(out["id"], kind="stable")
+            out = {k: v[order] for k, v in out.items()}
+        return out
 
     def _alloc_sort_scratch(self, sp):
         t = self.torch
@@ -514,6 +594,13 @@ class Simulation:
             self.istep += numsteps
             self.is_synchronized = bool(synchronize_last)
             self._sync_from_native()
+            # the moving window translates the problem domain; t_new
+            dom = (C.c_double * 6)()
+            self.L.pic_engine_prob_domain(self.native, dom)
+            self.prob_lo, self.prob_hi = tuple(dom[0:3]), tuple(dom[3:6])
+            for d in range(3):
+                self.geom.prob_lo[d], self.geom.prob_hi[d] = dom[d], dom[3 + d]
+            self.time = self.L.pic_engine_time(self.native)
             return
         if self.native:
             raise RuntimeError("per-stage timing needs Simulation(native_driver=False)")
