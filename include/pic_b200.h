@@ -410,6 +410,11 @@ int pic_engine_evolve(void* engine, int numsteps, int synchronize_last, void* st
  * (Source/Diagnostics/ReducedDiags/FieldEnergy.cpp:120-144).  out: 1 double, device. */
 int pic_sum_squares_unique(const pic_fab* f, const pic_geom* g, double* out, void* stream);
 
+/* ParticleEnergy reduced diagnostic of one species (Source/Diagnostics/ReducedDiags/ParticleEnergy.cpp:
+ * 86-170 with Algorithms::KineticEnergy, Source/Particles/Algorithms/KineticEnergy.H:31-46):
+ * out[0] = sum w m u^2 / (1 + gamma) [J], out[1] = sum w.  out: 2 doubles, device. */
+int pic_particle_energy(const pic_soa* p, double mass, double* out, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 long pic_launch_count(void);
 

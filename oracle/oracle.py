@@ -100,6 +100,8 @@ def lib(kind="restated"):
         "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long]),
         "orc_apply_particle_boundaries": (None, [soap, gp, C.POINTER(abi.pic_boundaries), C.c_char_p]),
         "orc_antenna_particles": (C.c_long, [C.POINTER(abi.pic_laser_antenna), dp, dp, dp, dp, dp, dp, dp, C.c_long]),
+        "orc_particle_energy": (None, [soap, C.c_double, dp]),
+        "orc_sim_particle_energy": (None, [vp, C.c_int, dp]),
         "orc_num_threads": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
     }
@@ -262,6 +264,11 @@ class OracleSim:
     def field_energy(self):
         out = (C.c_double * 2)()
         self.L.orc_sim_field_energy(self.h, out)
+        return out[0], out[1]
+
+    def particle_energy(self, isp):
+        out = (C.c_double * 2)()
+        self.L.orc_sim_particle_energy(self.h, isp, out)
         return out[0], out[1]
 
     def timers(self):

@@ -667,6 +667,18 @@ void orc_sim_field_energy(void* h, double* out) {
     out[0] = 0.5 * e2 * EP0 * dV;
     out[1] = 0.5 * b2 / MU0 * dV;
 }
+void orc_particle_energy(const pic_soa* p, double mass, double* out) { particle_energy(*p, mass, out); }
+// ParticleEnergy of species isp: out = {total kinetic energy [J], sum of weights}
+void orc_sim_particle_energy(void* h, int isp, double* out) {
+    Sim* s = static_cast<Sim*>(h);
+    out[0] = out[1] = 0.0;
+    for (auto& b : s->boxes) {
+        double o[2];
+        pic_soa P = b.sp[isp].soa();
+        particle_energy(P, b.sp[isp].m, o);
+        out[0] += o[0]; out[1] += o[1];
+    }
+}
 void orc_sim_timers(void* h, double* out /* push, deposit, fdtd, halo, other */) {
     Sim* s = static_cast<Sim*>(h);
     out[0] = s->t_push; out[1] = s->t_dep; out[2] = s->t_fdtd; out[3] = s->t_halo; out[4] = s->t_other;

@@ -566,6 +566,20 @@ inline double sum_squares_unique(const pic_fab* fabs, int nfab, const pic_geom& 
     return s;
 }
 
+// ParticleEnergy (Diagnostics/ReducedDiags/ParticleEnergy.cpp:86-170) with Algorithms::KineticEnergy
+// (Particles/Algorithms/KineticEnergy.H:31-46): out = {sum w * m u^2 / (1 + gamma), sum w}.
+inline void particle_energy(const pic_soa& P, double mass, double out[2]) {
+    constexpr double inv_c2 = 1.0 / (C_LIGHT * C_LIGHT);
+    double e = 0.0, ws = 0.0;
+    for (long ip = 0; ip < P.np; ++ip) {
+        const double u2 = P.ux[ip] * P.ux[ip] + P.uy[ip] * P.uy[ip] + P.uz[ip] * P.uz[ip];
+        const double gamma = std::sqrt(1.0 + u2 * inv_c2);
+        e += P.w[ip] * (1.0 / (1.0 + gamma) * mass * u2);
+        ws += P.w[ip];
+    }
+    out[0] = e; out[1] = ws;
+}
+
 // Sum over the N^3 cells of |cell-centred average| -- what Regression/Checksum/checksum.py:110-116
 // computes from a plotfile whose fields were averaged to cell centres by
 // ablastr/coarsen/sample.H:69-103 (cr = 1: for each nodal direction the two neighbouring nodes

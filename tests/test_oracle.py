@@ -261,7 +261,7 @@ def test_counter_based_momenta_are_decomposition_independent():
 # ---------------------------------------------------------------------------------------------
 def make_lwfa_oracle(orc, wl, kind="restated"):
     sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"],
-                        use_filter=wl["use_filter"], kind=kind)
+                        use_filter=wl["use_filter"], kind=kind, solver=wl["solver"], pusher=wl["pusher"])
     sim.set_boundaries(abi.make_boundaries(wl["field_lo"], wl["field_hi"]))
     sim.set_moving_window(wl["moving_window_dir"], wl["moving_window_v"])
     for s in wl["species"]:
@@ -398,3 +398,28 @@ def test_shift_fab_known_answers(orc):
         # (rows below the periodic duplicate j = N: the oracle fills from the owner of a location)
         klo, vyo = ng[2], slice(ng[1], ng[1] + n[1])
         assert np.array_equal(f.a[klo - 1:khi, vyo, ng[0] - 1], b0[klo:khi + 1, vyo, ng[0] - 1 + n[0]])
+
+
+def test_particle_energy_known_answer_and_conservation(orc):
+    """ParticleEnergy (ReducedDiags/ParticleEnergy.cpp:86-170): (gamma - 1) m c^2 per particle, and
+    field + kinetic energy of the Langmuir deck conserved to the level the scheme allows."""
+    L = orc.lib()
+    g = np.array([1.0, 1.5, 20.0])
+    u = np.sqrt(g * g - 1.0) * workloads.C
+    P = orc.HostParticles(x=[0, 0, 0], y=[0, 0, 0], z=[0, 0, 0], w=[2.0, 3.0, 0.5], ux=[u[0], 0, 0], uy=[0, u[1], 0],
+                          uz=[0, 0, u[2]])
+    out = (C.c_double * 2)()
+    L.orc_particle_energy(C.byref(P.soa), workloads.M_E, out)
+    assert out[1] == 5.5
+    assert out[0] == pytest.approx(float(np.sum(P.w * (g - 1.0)) * workloads.M_E * workloads.C ** 2), rel=1e-14)
+    wl = workloads.langmuir_3d(n=16)
+    sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=1)
+    for s in wl["species"]:
+        sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    k0 = sum(sim.particle_energy(i)[0] for i in range(2))
+    assert sim.particle_energy(0)[1] == pytest.approx(float(np.sum(wl["species"][0]["w"])), rel=1e-14)
+    sim.evolve(20)
+    k1 = sum(sim.particle_energy(i)[0] for i in range(2))
+    e1 = sum(sim.field_energy())
+    assert k1 < k0 and e1 > 0                      # the wave draws its energy from the particles ...
+    assert abs((k1 + e1) - k0) <= 0.05 * k0        # ... and the total is conserved to a few per cent at 16^3

@@ -187,6 +187,17 @@ struct InjectArgs {
     long total;
 };
 
+// lo + (cell + r) * dx exactly as the reference's host/CPU build evaluates getCellCoords: a product
+// rounded to double, then a sum (no fused multiply-add), so that the particle positions a moving
+// window injects are bit-identical to the CPU reference's.
+PIC_HD double cell_coord(double lo, double cr, double dx) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(lo, __dmul_rn(cr, dx));
+#else
+    return lo + cr * dx;
+#endif
+}
+
 PIC_HD int inject_prefix(int cell, int ppc, int m_lo, int m_hi) {   // valid lattice points below `cell`
     const int v = cell * ppc - m_lo, M = m_hi - m_lo + 1;
     return v < 0 ? 0 : (v > M ? M : v);
@@ -217,9 +228,9 @@ PIC_HD void inject_body(long t, const InjectArgs& a) {
     const long cell_off = (long)pre[2] * M[1] * M[0] + (long)cnt[2] * ((long)pre[1] * M[0] + (long)cnt[1] * pre[0]);
     const long slot = cell_off + ((long)rank[0] * cnt[2] + rank[2]) * cnt[1] + rank[1];
     const double r[3] = {(0.5 + ixp) / a.ppc[0], (0.5 + iyp) / a.ppc[1], (0.5 + izp) / a.ppc[2]};
-    a.P.x[slot] = a.ov_lo[0] + (iv[0] + r[0]) * a.dx[0];            // getCellCoords (:151-175)
-    a.P.y[slot] = a.ov_lo[1] + (iv[1] + r[1]) * a.dx[1];
-    a.P.z[slot] = a.ov_lo[2] + (iv[2] + r[2]) * a.dx[2];
+    a.P.x[slot] = cell_coord(a.ov_lo[0], iv[0] + r[0], a.dx[0]);    // getCellCoords (:151-175)
+    a.P.y[slot] = cell_coord(a.ov_lo[1], iv[1] + r[1], a.dx[1]);
+    a.P.z[slot] = cell_coord(a.ov_lo[2], iv[2] + r[2], a.dx[2]);
     a.P.w[slot] = a.weight;
     a.P.ux[slot] = 0.0; a.P.uy[slot] = 0.0; a.P.uz[slot] = 0.0;
     if (a.id) a.id[slot] = a.id0 + (uint64_t)slot;

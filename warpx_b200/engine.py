@@ -629,6 +629,19 @@ class Simulation:
         v = e2b2.cpu().numpy()
         return 0.5 * v[0] * EP0 * dV, 0.5 * v[1] / MU0 * dV
 
+    def particle_energy(self):
+        """ParticleEnergy reduced diagnostic (Diagnostics/ReducedDiags/ParticleEnergy.cpp:86-170):
+        per species (total kinetic energy [J], sum of weights), summed over ranks."""
+        t = self.torch
+        out = t.zeros((max(len(self.species), 1), 2), dtype=t.float64, device=self.device)
+        for isp, sp in enumerate(self.species):
+            soa = sp.soa()
+            check(self.L.pic_particle_energy(C.byref(soa), sp.m, out[isp].data_ptr(), self.stream))
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(out)
+        v = out.cpu().numpy()
+        return [(float(v[i, 0]), float(v[i, 1])) for i in range(len(self.species))]
+
     def total_particles(self):
         n = sum(sp.np for sp in self.species)
         if self.dist is not None and self.world > 1:

@@ -58,6 +58,7 @@ def lib():
         "pic_sort_workspace_bytes": (C.c_long, [C.c_long, C.c_long]),
         "pic_sort_particles_by_cell": (C.c_int, [soap, soap, gp, bp, vp, vp]),
         "pic_sum_squares_unique": (C.c_int, [fabp, gp, vp, vp]),
+        "pic_particle_energy": (C.c_int, [soap, C.c_double, vp, vp]),
         "pic_engine_create": (vp, [gp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                    C.c_int, ip]),
         "pic_engine_destroy": (None, [vp]),

@@ -132,7 +132,7 @@ def uniform_plasma_3d(n=256, ppc=(2, 2, 2), lx=40.0e-6, density=1.0e25, u_th=0.0
     return dict(n_cell=n_cell, prob_lo=prob_lo, prob_hi=prob_hi, species=species)
 
 
-def laser_acceleration_3d(n_cell=(32, 32, 256), max_step=100):
+def laser_acceleration_3d(n_cell=(32, 32, 256), max_step=100, solver=0, pusher=0):
     """Config 4's deterministic ancestor: Examples/Physics_applications/laser_acceleration/
     inputs_base_3d (test_3d_laser_acceleration): Yee, Boris, order 3, bilinear filter on (WarpX
     default), z moving window at c with PEC walls, Gaussian laser antenna, electrons at rest on the
@@ -143,6 +143,7 @@ def laser_acceleration_3d(n_cell=(32, 32, 256), max_step=100):
         n_cell=tuple(n_cell), prob_lo=(-30.e-6, -30.e-6, -56.e-6), prob_hi=(30.e-6, 30.e-6, 12.e-6),
         field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
         nox=3, use_filter=True, cfl=1.0, moving_window_dir=2, moving_window_v=1.0, max_step=max_step,
+        solver=solver, pusher=pusher,      # 0 = Yee / Boris (the deck); 1 = CKC / Vay (BASELINE.json config 4)
         species=[dict(name="electrons", q=-Q_E, m=M_E, ppc=(1, 1, 1),
                       bound_lo=(-20.e-6, -20.e-6, 0.0), bound_hi=(20.e-6, 20.e-6, inf),
                       density=2.e23, do_continuous_injection=True)],
