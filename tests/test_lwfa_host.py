@@ -244,8 +244,8 @@ def test_particle_boundaries_match_oracle(orc, hh, pbc_z):
         assert np.array_equal(getattr(Q, k)[:m][order], getattr(P, k)[keep]), k
     # list overflow is reported, not silently truncated
     work[:] = 0
-    _check(hh, hh.pic_particles_boundary_mark(C.byref(orc.HostParticles(**arr).soa), C.byref(geom), C.byref(bnd),
-                                              work.ctypes.data, 8, None))
+    R = orc.HostParticles(**arr)              # (kept alive: its arrays back the descriptor)
+    _check(hh, hh.pic_particles_boundary_mark(C.byref(R.soa), C.byref(geom), C.byref(bnd), work.ctypes.data, 8, None))
     assert int(work[0]) == n_lost
     assert hh.pic_particles_boundary_compact(C.byref(Q.soa), work.ctypes.data, 8, n_lost, None) != 0
 
