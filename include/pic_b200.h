@@ -170,6 +170,8 @@ int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3],
  * doGatherShapeN (Gather/FieldGather.H:36-424), doParticleMomentumPush (Pusher/PushSelector.H:38-102),
  * UpdatePosition (Pusher/UpdatePosition.H:24-45).  xyzmin/lo describe the guard-grown tile box
  * (:2575-2601).  push_position = 0 gives PushP (:2368-2513; momentum only).
+ * nox = 1..4 (algo.particle_shape); the supercell kernel behind `bins` serves orders 1..3, order 4
+ * always takes the order-agnostic kernel.
  * bins may be NULL; escaped may be NULL (it is only written when push_position != 0). */
 int pic_gather_push(const pic_soa* p, long offset, long np,
                     const pic_fab E[3], const pic_fab B[3],

@@ -197,6 +197,8 @@ int gather_push(const pic_soa& P, long offset, long np, const pic_fab E[3], cons
     else if (nox == 2) ORC_GP(2, 0);
     else if (nox == 3 && galerkin) ORC_GP(3, 1);
     else if (nox == 3) ORC_GP(3, 0);
+    else if (nox == 4 && galerkin) ORC_GP(4, 1);
+    else if (nox == 4) ORC_GP(4, 0);
     else return 1;
 #undef ORC_GP
     return 0;
@@ -355,6 +357,7 @@ int deposit(const pic_soa& P, long offset, long np, const pic_fab J[3], const do
     if (nox == 1) deposit_t<L, 1>(P, offset, np, J, dinv, xyzmin, lo, q, dt, relative_time);
     else if (nox == 2) deposit_t<L, 2>(P, offset, np, J, dinv, xyzmin, lo, q, dt, relative_time);
     else if (nox == 3) deposit_t<L, 3>(P, offset, np, J, dinv, xyzmin, lo, q, dt, relative_time);
+    else if (nox == 4) deposit_t<L, 4>(P, offset, np, J, dinv, xyzmin, lo, q, dt, relative_time);
     else return 1;
     return 0;
 }

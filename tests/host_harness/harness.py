@@ -19,19 +19,20 @@ CSRC = os.path.join(ROOT, "warpx_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libpic_lwfa_host.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SRCS = ["lwfa.cu", "runtime.cu"]
+PROBES = [os.path.join(HERE, "shape_probe.cu")]
 _LIB = None
 
 
 def build():
     deps = [os.path.join(CSRC, f) for f in SRCS + ["lwfa_body.cuh", "pic_common.cuh"]] + \
-           [os.path.join(ROOT, "include", "pic_b200.h")]
+           [os.path.join(ROOT, "include", "pic_b200.h")] + PROBES
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [NVCC, "-DPIC_HOST_HARNESS", "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC",
            "-Xcompiler", "-ffp-contract=off", "--fmad=false", "--expt-relaxed-constexpr",
            "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + \
-          [os.path.join(CSRC, f) for f in SRCS] + ["-lcudart"]
+          ["-I", CSRC] + [os.path.join(CSRC, f) for f in SRCS] + PROBES + ["-lcudart"]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return OUT
 
@@ -47,6 +48,8 @@ def lib():
     for name, (res, args) in abi.LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp).items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
+    L.pic_host_shape.restype, L.pic_host_shape.argtypes = C.c_int, [C.c_int, C.c_double, dp]
+    L.pic_host_shifted_shape.restype, L.pic_host_shifted_shape.argtypes = C.c_int, [C.c_int, C.c_double, C.c_int, dp]
     L.pic_set_error_mode.argtypes = [C.c_int]
     L.pic_last_error.restype = C.c_char_p
     L.pic_set_error_mode(abi.PIC_ERR_RETURN)

@@ -13,7 +13,8 @@ import numpy as np
 import pytest
 
 from helpers import rel_linf
-from test_gpu_parity import Dev, box  # noqa: F401
+from helpers import lower_corner, random_fields
+from test_gpu_parity import Dev, _particles, _run_both, _match_particles, box  # noqa: F401
 from test_oracle import make_lwfa_oracle
 from warpx_b200 import abi, workloads
 
@@ -366,3 +367,78 @@ def test_absorbing_walls_remove_particles_like_the_oracle(orc, cuda):
         assert np.max(np.abs(A[k] - B[k])) / sim.dx[2] <= 1e-9, k
     for k in ("ux", "uy", "uz"):
         assert np.max(np.abs(A[k] - B[k])) / workloads.C <= 1e-9, k
+
+
+# ---------------------------------------------------------------------------------------------
+# algo.particle_shape = 4 (the order-agnostic kernels; the supercell / run kernels cover 1..3)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("galerkin", [1, 0])
+def test_order4_gather_push_matches_oracle(orc, dev, galerkin):
+    L = orc.lib()
+    n, lx = (20, 16, 12), 1e-5
+    box_lo, box_hi = box(n)
+    wl, sp = _particles(orc, n, (2, 1, 2), 0.3, lx, shuffle=True)
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    ngEB = (4, 4, 4)
+    xyzmin, lo = lower_corner(prob_lo, dx, box_lo, ngEB)
+    F = random_fields(orc, box_lo, box_hi, ngEB, 5, comps=range(6), scale=[1e10] * 3 + [30.0] * 3)
+    P = orc.HostParticles(**{k: sp[k] for k in orc.HostParticles.NAMES})
+    arr, _ = dev.fabs(F)
+    E, B = (abi.pic_fab * 3)(*arr[0:3]), (abi.pic_fab * 3)(*arr[3:6])
+    dt = 0.9 * dx[0] / workloads.C
+    Pd, buf = dev.soa(P)
+    for push_position in (1, 0):
+        dev.ok(dev.L.pic_gather_push(C.byref(Pd), 0, P.np, E, B, abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                     sp["q"], sp["m"], dt, 4, galerkin, abi.PUSHER_BORIS, push_position, None, None,
+                                     dev.stream))
+        assert L.orc_gather_push(C.byref(P.soa), 0, P.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), abi.dbl3(dinv),
+                                 abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], dt, 4, galerkin, abi.PUSHER_BORIS,
+                                 push_position) == 0
+    dev.sync()
+    got = buf.cpu().numpy()
+    for i, k in enumerate(orc.HostParticles.NAMES):
+        assert rel_linf(got[i], getattr(P, k)) <= 1e-13, k
+
+
+def test_order4_deposit_matches_oracle(orc, dev):
+    L = orc.lib()
+    n, lx = (20, 16, 12), 1e-5
+    box_lo, box_hi = box(n)
+    wl, sp = _particles(orc, n, (2, 2, 2), 0.5, lx, shuffle=True)
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    dt = 0.95 / (np.sqrt(sum(1.0 / v ** 2 for v in dx)) * workloads.C)
+    ngJ = (5, 5, 5)
+    xyzmin, lo = lower_corner(prob_lo, dx, box_lo, ngJ)
+    J = [orc.HostFab(box_lo, box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    P = orc.HostParticles(**{k: sp[k] for k in orc.HostParticles.NAMES})
+    arr, tens = dev.fabs(J)
+    Pd, buf = dev.soa(P)
+    dev.ok(dev.L.pic_deposit_esirkepov(C.byref(Pd), 0, P.np, (abi.pic_fab * 3)(*arr), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                       abi.int3(lo), sp["q"], dt, -0.5 * dt, 4, None, dev.stream))
+    dev.sync()
+    assert L.orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                   abi.int3(lo), sp["q"], dt, -0.5 * dt, 4) == 0
+    for c in range(3):
+        assert rel_linf(tens[c].cpu().numpy(), J[c].a) <= 1e-12, "j" + "xyz"[c]
+
+
+def test_order4_loop_matches_oracle(orc, cuda):
+    """Whole loop at order 4 through the C++ driver (bins present: the driver falls back to the
+    order-agnostic kernels for this order)."""
+    wl = workloads.uniform_plasma_3d(n=24, ppc=(2, 2, 2), u_th=0.01, lx=3.75e-6, perturbation=0.01)
+    sim, osim = _run_both(orc, cuda, wl, 4, 8, sort_interval=4)
+    assert sim.ng_EB == [4, 4, 4] and sim.ng_J == osim.guards()["ng_J"] == [5, 5, 5]
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        _, oa = osim.fab(c)
+        tol = 1e-9 if c not in (3, 4, 5) else 1e-7
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= tol, abi.COMP_NAMES[c]
+    A, B = _match_particles(sim, osim, 0)
+    for k in ("x", "y", "z"):
+        assert np.max(np.abs(A[k] - B[k])) / sim.dx[0] <= 1e-10
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(A[k] - B[k])) / workloads.C <= 1e-10

@@ -78,7 +78,7 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
                                      double q, double dt, double relative_time, int nox,
                                      const pic_bins* bins, void* stream) {
     if (np == 0 || q == 0.0) return 0;                 // WarpXParticleContainer.cpp:367-370
-    PIC_REQUIRE(nox >= 1 && nox <= 3, "pic_deposit_esirkepov: particle shape order %d not in 1..3", nox);
+    PIC_REQUIRE(nox >= 1 && nox <= 4, "pic_deposit_esirkepov: particle shape order %d not in 1..4", nox);
     PIC_REQUIRE(offset >= 0 && offset + np <= p->np, "pic_deposit_esirkepov: range outside the tile");
     PIC_REQUIRE(p->w != nullptr, "pic_deposit_esirkepov: weights missing");
     for (int c = 0; c < 3; ++c)
@@ -93,7 +93,7 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
     dg.invdtd[1] = (1.0 / dt) * dinv[0] * dinv[2];
     dg.invdtd[2] = (1.0 / dt) * dinv[0] * dinv[1];
     cudaStream_t s = (cudaStream_t)stream;
-    if (bins) {
+    if (bins && nox <= 3) {        // order 4: order-agnostic kernel (the run kernels are built for orders 1..3)
         // cell-sorted particles: warp-segmented register reduction (deposit_runs.cu).  The
         // shared-memory-block variant (deposit_tile.cu) is kept for comparison: pic_set_deposit_mode().
         PIC_REQUIRE(np < (1L << 31), "pic_deposit_esirkepov: more than 2^31 particles in one tile");
@@ -109,7 +109,8 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
     FabView jx = make_view(J[0]), jy = make_view(J[1]), jz = make_view(J[2]);
     if (nox == 1) deposit_global<1><<<nblk, tpb, 0, s>>>(P, np, jx, jy, jz, dg);
     else if (nox == 2) deposit_global<2><<<nblk, tpb, 0, s>>>(P, np, jx, jy, jz, dg);
-    else deposit_global<3><<<nblk, tpb, 0, s>>>(P, np, jx, jy, jz, dg);
+    else if (nox == 3) deposit_global<3><<<nblk, tpb, 0, s>>>(P, np, jx, jy, jz, dg);
+    else deposit_global<4><<<nblk, tpb, 0, s>>>(P, np, jx, jy, jz, dg);
     count_launch();
     return check_launch("pic_deposit_esirkepov") ? 0 : 1;
 }

@@ -47,7 +47,7 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
                                int galerkin, int pusher, int push_position, const pic_bins* bins,
                                const pic_escape_list* escaped, void* stream) {
     if (np == 0) return 0;                                   // PhysicalParticleContainer.cpp:2568
-    PIC_REQUIRE(nox >= 1 && nox <= 3, "pic_gather_push: particle shape order %d not in 1..3", nox);
+    PIC_REQUIRE(nox >= 1 && nox <= 4, "pic_gather_push: particle shape order %d not in 1..4", nox);
     PIC_REQUIRE(galerkin == 0 || galerkin == 1, "pic_gather_push: galerkin must be 0/1");
     PIC_REQUIRE(pusher >= 0 && pusher <= 2, "pic_gather_push: unknown particle pusher %d", pusher);
     PIC_REQUIRE(offset >= 0 && offset + np <= p->np, "pic_gather_push: range outside the tile");
@@ -58,7 +58,7 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     const double qdt2m = 0.5 * q * dt / m;
     cudaStream_t s = (cudaStream_t)stream;
     const EscapeView esc = make_escape(escaped, push_position);
-    if (bins) {
+    if (bins && nox <= 3) {        // the supercell kernel is built for orders 1..3; order 4 takes the order-agnostic one
         if (int rc = gather_push_tile_launch(p, offset, np, E, B, gg, qdt2m, dt, nox, galerkin, pusher,
                                              push_position, bins, esc, s)) return rc;
         if (bins->np_binned >= np) return 0;
@@ -79,7 +79,9 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     else if (nox == 2 && galerkin) PIC_GP(2, 1);
     else if (nox == 2) PIC_GP(2, 0);
     else if (nox == 3 && galerkin) PIC_GP(3, 1);
-    else PIC_GP(3, 0);
+    else if (nox == 3) PIC_GP(3, 0);
+    else if (galerkin) PIC_GP(4, 1);
+    else PIC_GP(4, 0);
 #undef PIC_GP
     count_launch();
     return check_launch("pic_gather_push") ? 0 : 1;

@@ -73,8 +73,17 @@ inline SoaView make_soa(const pic_soa& p, long offset) {
 
 // ---- B-spline shape factors (Source/Particles/ShapeFactors.H:27-84) --------------------------
 // Written for the evaluation order of the reference; returns the leftmost index.
+// Quartic spline around the nearest node, d in [-1/2, 1/2] (ShapeFactors.H:66-77).
+__host__ __device__ __forceinline__ void quartic_weights(double* s, double d) {
+    const double a = 0.5 - d, b = 0.5 + d;        // products left to right, as the reference evaluates them
+    s[0] = (1.0 / 24.0) * a * a * a * a;
+    s[1] = (1.0 / 24.0) * (4.75 - 11.0 * d + 4.0 * d * d * (1.5 + d - d * d));
+    s[2] = (1.0 / 24.0) * (14.375 + 6.0 * d * d * (d * d - 2.5));
+    s[3] = (1.0 / 24.0) * (4.75 + 11.0 * d + 4.0 * d * d * (1.5 - d - d * d));
+    s[4] = (1.0 / 24.0) * b * b * b * b;
+}
 template <int N>
-__device__ __forceinline__ int shape_factor(double* s, double xmid) {
+__host__ __device__ __forceinline__ int shape_factor(double* s, double xmid) {
     if constexpr (N == 0) {
         const int j = (int)(xmid + 0.5);
         s[0] = 1.0;
@@ -90,8 +99,7 @@ __device__ __forceinline__ int shape_factor(double* s, double xmid) {
         const double a = 0.5 - d, b = 0.5 + d;
         s[0] = 0.5 * a * a; s[1] = 0.75 - d * d; s[2] = 0.5 * b * b;
         return j - 1;
-    } else {
-        static_assert(N == 3, "orders 0..3");
+    } else if constexpr (N == 3) {
         const int j = (int)xmid;
         const double d = xmid - (double)j;
         const double e = 1.0 - d;
@@ -100,13 +108,17 @@ __device__ __forceinline__ int shape_factor(double* s, double xmid) {
         s[2] = (2.0 / 3.0) - e * e * (1.0 - 0.5 * e);
         s[3] = (1.0 / 6.0) * d * d * d;
         return j - 1;
+    } else {
+        static_assert(N == 4, "orders 0..4");
+        quartic_weights(s, xmid - (double)(int)(xmid + 0.5));
+        return (int)(xmid + 0.5) - 2;
     }
 }
 
 // Shifted shape factor of the OLD position (ShapeFactors.H:93-156): slot 1 of the (N+3)-slot
 // array is the leftmost point of the NEW position's stencil.  s must be pre-zeroed.
 template <int N>
-__device__ __forceinline__ int shifted_shape_factor(double* s, double x_old, int i_new) {
+__host__ __device__ __forceinline__ int shifted_shape_factor(double* s, double x_old, int i_new) {
     if constexpr (N == 1) {
         const int i = (int)floor(x_old);
         const int sh = i - i_new;
@@ -120,8 +132,7 @@ __device__ __forceinline__ int shifted_shape_factor(double* s, double x_old, int
         const double a = 0.5 - d, b = 0.5 + d;
         s[1 + sh] = 0.5 * a * a; s[2 + sh] = 0.75 - d * d; s[3 + sh] = 0.5 * b * b;
         return i - 1;
-    } else {
-        static_assert(N == 3, "orders 1..3");
+    } else if constexpr (N == 3) {
         const int i = (int)x_old;
         const int sh = i - (i_new + 1);
         const double d = x_old - (double)i;
@@ -131,6 +142,12 @@ __device__ __forceinline__ int shifted_shape_factor(double* s, double x_old, int
         s[3 + sh] = (2.0 / 3.0) - e * e * (1.0 - 0.5 * e);
         s[4 + sh] = (1.0 / 6.0) * d * d * d;
         return i - 1;
+    } else {
+        static_assert(N == 4, "orders 1..4");
+        const int i = (int)(x_old + 0.5);
+        const int sh = i - (i_new + 2);
+        quartic_weights(s + 1 + sh, x_old - (double)i);
+        return i - 2;
     }
 }
 
