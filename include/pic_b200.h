@@ -255,8 +255,9 @@ int pic_particles_wrap_listed(const pic_soa* p, const pic_geom* g, const pic_esc
 /* Neighbour migration, step 1 (replaces the locate/partition phase of AMReX
  * ParticleContainer::Redistribute, WarpXEvolve.cpp:550-559): indices of the particles whose cell
  * along `dim` lies below cell_lo (-> idx_lo) or above cell_hi (-> idx_hi) after the periodic wrap.
- * With `both_up` (two ranks along dim: both neighbours are the same rank) everything goes to
- * idx_hi.  counts[0], counts[1] (device ints, zeroed here) receive the list lengths; lists hold at
+ * With `both_up` = 1 (two ranks along a periodic dim: both neighbours are the same rank) everything
+ * goes to idx_hi; `both_up` = 2 marks a NON-periodic dim (no wrap-around ownership: below cell_lo -> low
+ * neighbour, above cell_hi -> high neighbour).  counts[0], counts[1] (device ints, zeroed here) receive the list lengths; lists hold at
  * most `capacity` entries each (counts keep counting: the caller checks for overflow). */
 int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
                            int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
@@ -336,11 +337,17 @@ int pic_laser_antenna_push(const pic_laser_antenna* prm, const double dx[3], con
  * whole domain at start-up, the slab uncovered by the moving window for ContinuousInjection, :2518-2527).
  * Particles are appended on the device after p->np, in the order the reference creates them, with
  * ids first_id, first_id+1, ...  cell_size = Geometry::CellSize() (NULL: (prob_hi - prob_lo) / n_cell;
- * a moving window translates the domain but keeps the cell size it started with).
- * Returns how many were added (the caller adds it to np), -1 on error. */
+ * a moving window translates the domain but keeps the cell size it started with).  box_lo/box_hi =
+ * the cells of this rank's box (the tile whose RealBox must contain a particle, :1141-1156; NULL = the
+ * whole domain).  p = NULL only counts.  Returns how many were (would be) added, -1 on error. */
 long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double cell_size[3],
-                    const double part_lo[3], const double part_hi[3], const pic_soa* p, long capacity,
-                    uint64_t first_id, void* stream);
+                    const int box_lo[3], const int box_hi[3], const double part_lo[3], const double part_hi[3],
+                    const pic_soa* p, long capacity, uint64_t first_id, void* stream);
+
+/* w_out[ip] = w[ip] for particles inside [own_lo, own_hi), 0 elsewhere.  Used for containers that are
+ * replicated on every rank (laser antennas): each rank deposits only what lies in its own box. */
+int pic_particles_owned_weights(const pic_soa* p, const double own_lo[3], const double own_hi[3], double* w_out,
+                                void* stream);
 
 /* WarpXParticleContainer::ApplyBoundaryConditions (Source/Particles/WarpXParticleContainer.cpp:1574-1638,
  * ParticleBoundaries_K.H:21-75) + the removal AMReX Redistribute performs.  _mark reflects at

@@ -105,6 +105,51 @@ def main():
             print(f"[order3 x{world} filter={int(filt)} native={int(native)}] field energy E {e:.12e} vs oracle {eo:.12e}; "
                   f"B {b:.12e} vs {bo:.12e}; particles {npart}: {'ok' if good else 'FAIL'}")
         del sim3
+    # ---------------- laser-acceleration deck on z slabs: moving window over several ranks ----------------
+    # (PEC walls on the end slabs, neighbour planes pulled in by the window shift, one cell layer of
+    #  particles migrating down per shift, injection on the top slab, replicated antenna) against WarpX's
+    #  golden checksums of test_3d_laser_acceleration -- the decomposition must not change them.
+    if 256 % world == 0 and 256 // world >= 16:
+        gl = json.load(open(os.path.join(ROOT, "tests", "golden", "warpx_checksums.json")))["test_3d_laser_acceleration"]
+        wl = workloads.laser_acceleration_3d()
+        simw = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], dist=dist,
+                          use_filter=wl["use_filter"], sort_interval=4, nb=(1, 1, world),
+                          boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]),
+                          moving_window=(wl["moving_window_dir"], wl["moving_window_v"]))
+        sp = wl["species"][0]
+        simw.add_plasma_species(sp["name"], sp["q"], sp["m"],
+                                abi.make_injector(sp["ppc"], sp["bound_lo"], sp["bound_hi"], sp["density"], True),
+                                capacity=22 * 22 * 256)
+        la = wl["lasers"][0]
+        simw.add_laser(abi.make_laser(la["position"], la["direction"], la["polarization"], la["wavelength"], la["e_max"],
+                                      la["waist"], la["duration"], la["t_peak"], la["focal_distance"]))
+        simw.Evolve(wl["max_step"])
+        torch.cuda.synchronize()
+        sums = []
+        for c in range(9):
+            d, a = simw.field_numpy(c)
+            hf = oracle.HostFab(simw.box_lo, simw.box_hi, d.ng, abi.YEE_STAG[c], data=a)
+            sums.append(L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(simw.box_lo), abi.int3(simw.box_hi)))
+        P = simw.species_numpy(0)
+        psum = [np.sum(np.abs(P["x"])), np.sum(np.abs(P["y"])), np.sum(np.abs(P["z"])),
+                np.sum(np.abs(P["ux"])) * workloads.M_E, np.sum(np.abs(P["uy"])) * workloads.M_E,
+                np.sum(np.abs(P["uz"])) * workloads.M_E, np.sum(P["w"]), float(len(P["x"]))]
+        t = torch.tensor(sums + psum, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        v = t.cpu().numpy()
+        if rank == 0:
+            keys = ["particle_position_x", "particle_position_y", "particle_position_z", "particle_momentum_x",
+                    "particle_momentum_y", "particle_momentum_z", "particle_weight"]
+            pairs = [(name, v[c], gl["lev=0"][name]) for c, name in enumerate(abi.COMP_NAMES)] + \
+                    [("electrons." + k, v[9 + j], gl["electrons"][k]) for j, k in enumerate(keys)]
+            for name, got, g in pairs:
+                good = abs(got - g) <= 1e-9 * abs(g)
+                ok &= good
+                print(f"[lwfa z-slabs x{world}] {name}: {got:.15e} golden {g:.15e} {'ok' if good else 'FAIL'}")
+            good = int(v[9 + 7]) == 22 * 22 * (45 + 98)
+            ok &= good
+            print(f"[lwfa z-slabs x{world}] particles {int(v[9 + 7])}: {'ok' if good else 'FAIL'}")
+        del simw
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
     flag = torch.tensor([1 if ok else 0], device="cuda")

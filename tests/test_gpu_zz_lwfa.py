@@ -181,7 +181,7 @@ def test_add_plasma_matches_oracle(orc, dev, ppc, slab):
     for k, name in enumerate(("x", "y", "z", "w", "ux", "uy", "uz")):
         setattr(soa, name, buf[k].data_ptr())
     soa.idcpu, soa.np = ids.data_ptr(), 7
-    n = dev.L.pic_add_plasma(C.byref(inj), C.byref(geom), None, abi.dbl3(plo), abi.dbl3(phi), C.byref(soa), cap, 500, dev.stream)
+    n = dev.L.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(soa), cap, 500, dev.stream)
     assert n > 0, dev.L.pic_last_error().decode()
     dev.sync()
     B = [np.empty(cap) for _ in range(4)]

@@ -183,7 +183,7 @@ def test_add_plasma_matches_oracle(orc, hh, ppc, slab):
     cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
     s, arrs, ids = _host_soa(cap + 5)
     s.np = 5                                  # appended after the particles already present
-    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s), cap + 5, 1000, None)
+    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s), cap + 5, 1000, None)
     assert n >= 0, hh.pic_last_error().decode()
     B = [np.empty(cap) for _ in range(4)]
     dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
@@ -201,11 +201,11 @@ def test_add_plasma_capacity_and_empty(hh):
     geom = abi.make_geom((4, 4, 4), (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
     inj = abi.make_injector((1, 1, 1), (0, 0, 0), (1, 1, 1), 1.0, True)
     s, arrs, ids = _host_soa(10)
-    assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == -1
+    assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == -1
     assert b"capacity" in hh.pic_last_error()
     # a slab that lies outside the plasma bounds adds nothing
     inj2 = abi.make_injector((1, 1, 1), (0, 0, 2.0), (1, 1, 3.0), 1.0, True)
-    assert hh.pic_add_plasma(C.byref(inj2), C.byref(geom), None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == 0
+    assert hh.pic_add_plasma(C.byref(inj2), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == 0
 
 
 @pytest.mark.parametrize("pbc_z", [("absorbing", "absorbing"), ("reflecting", "absorbing")])

@@ -65,6 +65,7 @@ struct Laser {
     long capacity;
     int* bnd_work = nullptr;
     int bnd_cap = 0;
+    double* w_owned = nullptr;   // multi-rank: weights masked to this rank's brick (engine-owned)
 };
 
 struct Engine {
@@ -106,6 +107,13 @@ static int neighbour(const Engine& e, int dim, int side) {
     return c[0] + e.nb[0] * (c[1] + e.nb[1] * c[2]);
 }
 
+// A brick at a non-periodic domain face has no neighbour beyond it.
+static bool has_neighbour(const Engine& e, int dim, int side) {
+    if (e.geom.periodic[dim]) return true;
+    const int c = e.coord[dim] + (side ? 1 : -1);
+    return c >= 0 && c < e.nb[dim];
+}
+
 #define ENG_NCCL(x) do { if (int rc_ = (x)) return nccl_fail("pic_engine", rc_); } while (0)
 
 // Low/high neighbour exchange along one axis.  A message travelling upwards (sent to hi, received
@@ -119,6 +127,20 @@ static int exchange(Engine& e, int dim, const double* s_lo, const double* s_hi, 
     ENG_NCCL(g_nccl.Recv(r_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
     ENG_NCCL(g_nccl.Send(s_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
     ENG_NCCL(g_nccl.Recv(r_hi, n, PIC_NCCL_FLOAT64, hi, e.comm->comm, s));
+    ENG_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// The same exchange along a NON-periodic axis: the bricks at the domain faces skip the missing side.
+static int exchange_np(Engine& e, int dim, const double* s_lo, const double* s_hi, double* r_lo, double* r_hi,
+                       size_t n, cudaStream_t s) {
+    const bool hl = has_neighbour(e, dim, 0), hh = has_neighbour(e, dim, 1);
+    const int lo = neighbour(e, dim, 0), hi = neighbour(e, dim, 1);
+    ENG_NCCL(g_nccl.GroupStart());
+    if (hh) ENG_NCCL(g_nccl.Send(s_hi, n, PIC_NCCL_FLOAT64, hi, e.comm->comm, s));
+    if (hl) ENG_NCCL(g_nccl.Recv(r_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
+    if (hl) ENG_NCCL(g_nccl.Send(s_lo, n, PIC_NCCL_FLOAT64, lo, e.comm->comm, s));
+    if (hh) ENG_NCCL(g_nccl.Recv(r_hi, n, PIC_NCCL_FLOAT64, hi, e.comm->comm, s));
     ENG_NCCL(g_nccl.GroupEnd());
     return 0;
 }
@@ -185,7 +207,38 @@ static void lower_corner(const Engine& e, const int ng[3], double xyzmin[3], int
 // part of SumBoundary's destination); a plain FillBoundary leaves them alone (see pic_fill_boundary_local).
 static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng, int mode, void* s, bool all_guards = false) {
     if (ng == 0 && mode == 0) return 0;
-    if (!e.geom.periodic[dim]) return 0;     // domain-spanning box (set_boundaries enforces it): no image, guards keep their values
+    if (!e.geom.periodic[dim]) {
+        if (spans(e, dim)) return 0;         // the box spans the domain: no image, the guards beyond the faces keep their values
+        // slabs along a non-periodic axis: per-side pack / unpack, the face bricks skip the missing side
+        size_t n = 0;
+        for (int c = 0; c < nfab; ++c) n += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
+        if (n == 0) return 0;
+        if (n > e.hbuf_doubles) {
+            for (int b = 0; b < 4; ++b) {
+                if (e.hbuf[b]) cudaFree(e.hbuf[b]);
+                if (cudaMalloc(&e.hbuf[b], sizeof(double) * n) != cudaSuccess) return fail("pic_engine: halo buffer allocation failed");
+            }
+            e.hbuf_doubles = n;
+        }
+        for (int side = 0; side < 2; ++side) {
+            if (!has_neighbour(e, dim, side)) continue;
+            size_t off = 0;
+            for (int c = 0; c < nfab; ++c) {
+                ENG_CALL(pic_halo_pack(&fabs[c], dim, side, ng, mode, e.hbuf[side] + off, s));
+                off += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
+            }
+        }
+        ENG_CALL(exchange_np(e, dim, e.hbuf[0], e.hbuf[1], e.hbuf[2], e.hbuf[3], n, (cudaStream_t)s));
+        for (int side = 0; side < 2; ++side) {
+            if (!has_neighbour(e, dim, side)) continue;
+            size_t off = 0;
+            for (int c = 0; c < nfab; ++c) {
+                ENG_CALL(pic_halo_unpack(&fabs[c], dim, side, ng, mode, e.hbuf[2 + side] + off, s));
+                off += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
+            }
+        }
+        return 0;
+    }
     if (spans(e, dim)) {
         pic_geom gfull = e.geom;
         if (all_guards) gfull.periodic[0] = gfull.periodic[1] = gfull.periodic[2] = 1;
@@ -262,10 +315,22 @@ static int push_particles_and_deposit(Engine& e, void* s) {
     }
     // the antennas come after the species in allcontainers (MultiParticleContainer.cpp:60-75);
     // LaserParticleContainer::Evolve (:563-700): push at t^n, deposit with charge = 1 (:88)
+    // Over several ranks every rank carries the whole antenna (a few thousand particles, pushed
+    // identically everywhere) and deposits the particles inside its own brick.
     for (auto& L : e.lasers) {
         if (L.P.np == 0) continue;
         ENG_CALL(pic_laser_antenna_push(&L.prm, e.dx, &L.P, e.cur_time, e.dt, s));
-        ENG_CALL(pic_deposit_esirkepov(&L.P, 0, L.P.np, &e.fab[6], e.dinv, xyzmin, lo, 1.0, e.dt, -0.5 * e.dt,
+        pic_soa dep = L.P;
+        if (e.comm) {
+            double own_lo[3], own_hi[3];
+            for (int d = 0; d < 3; ++d) {
+                own_lo[d] = (e.nb[d] == 1 || !has_neighbour(e, d, 0)) ? -INFINITY : e.geom.prob_lo[d] + e.dx[d] * e.box_lo[d];
+                own_hi[d] = (e.nb[d] == 1 || !has_neighbour(e, d, 1)) ? INFINITY : e.geom.prob_lo[d] + e.dx[d] * (e.box_hi[d] + 1);
+            }
+            ENG_CALL(pic_particles_owned_weights(&L.P, own_lo, own_hi, L.w_owned, s));
+            dep.w = L.w_owned;
+        }
+        ENG_CALL(pic_deposit_esirkepov(&dep, 0, dep.np, &e.fab[6], e.dinv, xyzmin, lo, 1.0, e.dt, -0.5 * e.dt,
                                        e.nox, nullptr, s));
     }
     return 0;
@@ -303,12 +368,20 @@ static int migrate(Engine& e, Species& sp, void* stream) {
     view.np = sp.capacity;                       // launch bound only: the kernels read the count from np_dev
     for (int dim = 0; dim < 3; ++dim) {
         if (spans(e, dim)) continue;
-        ENG_CALL(pic_particles_classify(&view, &e.geom, dim, e.box_lo[dim], e.box_hi[dim], e.nb[dim] == 2 ? 1 : 0,
+        const bool np_dim = !e.geom.periodic[dim];
+        ENG_CALL(pic_particles_classify(&view, &e.geom, dim, e.box_lo[dim], e.box_hi[dim],
+                                        np_dim ? 2 : (e.nb[dim] == 2 ? 1 : 0),
                                         sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], cap, np_dev, s));
         peak_kernel<<<1, 1, 0, s>>>(sp.mig_work + 6, sp.mig_counts);
         count_launch();
         ENG_CALL(pic_migrate_pack(&view, sp.mig_idx[0], sp.mig_counts, cap, sp.mig_msg[0], s));
         ENG_CALL(pic_migrate_pack(&view, sp.mig_idx[1], sp.mig_counts + 1, cap, sp.mig_msg[1], s));
+        if (np_dim) {
+            // a missing neighbour sends nothing: its message reads "0 particles"
+            for (int side = 0; side < 2; ++side)
+                if (!has_neighbour(e, dim, side)) cudaMemsetAsync(sp.mig_msg[2 + side], 0, sizeof(double), s);
+            ENG_CALL(exchange_np(e, dim, sp.mig_msg[0], sp.mig_msg[1], sp.mig_msg[2], sp.mig_msg[3], nmsg, s));
+        } else
         ENG_CALL(exchange(e, dim, sp.mig_msg[0], sp.mig_msg[1], sp.mig_msg[2], sp.mig_msg[3], nmsg, s));
         ENG_CALL(pic_migrate_unpack(&view, sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], sp.mig_msg[2], sp.mig_msg[3], cap,
                                     sp.capacity, sp.mig_work, np_dev, s));
@@ -363,6 +436,12 @@ static int move_window(Engine& e, bool move_j, int* num_moved, void* s) {
     if (nsb == 0) return 0;
     e.geom.prob_lo[dir] = e.geom.prob_lo[dir] + nsb * cdx;                                // :181-186
     e.geom.prob_hi[dir] = e.geom.prob_hi[dir] + nsb * cdx;
+    if (e.comm && e.nb[dir] > 1) {
+        // FillBoundary of shiftMF's temporary (:499-505): the planes the shift pulls in from the next slab
+        const int mag = nsb > 0 ? nsb : -nsb;
+        ENG_CALL(halo_sweep(e, &e.fab[0], 6, dir, mag, 0, s));
+        if (move_j) ENG_CALL(halo_sweep(e, &e.fab[6], 3, dir, mag, 0, s));
+    }
     for (int dim = 0; dim < 3; ++dim) {                                                   // :226-266
         ENG_CALL(shift_component(e, 3 + dim, nsb, s));
         ENG_CALL(shift_component(e, dim, nsb, s));
@@ -382,10 +461,13 @@ static int move_window(Engine& e, bool move_j, int* num_moved, void* s) {
         const bool ok = plo[0] < phi[0] && plo[1] < phi[1] && plo[2] < phi[2];            // RealBox::ok
         if (ok && sp.current_injection_position != new_pos) {
             pic_soa& P = sp.buf[sp.cur];
-            const long added = pic_add_plasma(&sp.inj, &e.geom, e.dx, plo, phi, &P, sp.capacity, sp.next_id, s);
-            if (added < 0) return 1;
+            // every rank advances the id counter by the global count; the rank whose brick contains the
+            // slab creates the particles (tile_realbox.contains, :1141-1156)
+            const long total = pic_add_plasma(&sp.inj, &e.geom, e.dx, nullptr, nullptr, plo, phi, nullptr, 0, 0, s);
+            const long added = pic_add_plasma(&sp.inj, &e.geom, e.dx, e.box_lo, e.box_hi, plo, phi, &P, sp.capacity, sp.next_id, s);
+            if (added < 0 || total < 0) return 1;
             P.np += added;
-            sp.next_id += (uint64_t)added;
+            sp.next_id += (uint64_t)total;
             sp.current_injection_position = new_pos;
         }
     }
@@ -508,7 +590,7 @@ extern "C" void pic_engine_destroy(void* h) {
             if (sp.mig_head) cudaFreeHost(sp.mig_head);
             if (sp.bnd_work) cudaFree(sp.bnd_work);
         }
-        for (auto& L : e->lasers) if (L.bnd_work) cudaFree(L.bnd_work);
+        for (auto& L : e->lasers) { if (L.bnd_work) cudaFree(L.bnd_work); if (L.w_owned) cudaFree(L.w_owned); }
         if (e->shift_tmp) cudaFree(e->shift_tmp);
         if (e->host_count) cudaFreeHost(e->host_count);
         for (int b = 0; b < 4; ++b) if (e->hbuf[b]) cudaFree(e->hbuf[b]);
@@ -561,6 +643,11 @@ extern "C" int pic_engine_add_species(void* h, double q, double m, const pic_soa
     if (e->comm) {
         // migration scratch; worst case per face and step = one full layer of cells ~ capacity/256
         sp.mig_cap_max = (int)(capacity / 256 > 65536 ? capacity / 256 : 65536);
+        if (e->do_moving_window) {
+            // every shift sends one whole layer of cells to the slab below
+            const long layer = capacity / (e->box_hi[e->mw_dir] - e->box_lo[e->mw_dir] + 1);
+            if (2 * layer + 65536 > sp.mig_cap_max) sp.mig_cap_max = (int)(2 * layer + 65536);
+        }
         sp.mig_cap = sp.mig_cap_max;
         const size_t nmsg = (size_t)pic_migrate_message_doubles(sp.mig_cap_max);
         bool ok = cudaMalloc(&sp.mig_counts, 2 * sizeof(int)) == cudaSuccess;
@@ -586,7 +673,9 @@ extern "C" int pic_engine_set_comm(void* h, void* comm, const int nb[3]) {
     PIC_REQUIRE(c && c->comm, "pic_engine_set_comm: no communicator");
     PIC_REQUIRE(nb[0] * nb[1] * nb[2] == c->nranks, "pic_engine_set_comm: brick grid %dx%dx%d != %d ranks", nb[0], nb[1], nb[2], c->nranks);
     PIC_REQUIRE(e->species.empty(), "pic_engine_set_comm: call before pic_engine_add_species");
-    PIC_REQUIRE(e->all_periodic, "pic_engine_set_comm: the multi-rank driver is periodic only");
+    if (e->do_moving_window)      // the shift folds the periodic refresh of the other directions into its read
+        for (int d = 0; d < 3; ++d)
+            PIC_REQUIRE(d == e->mw_dir || nb[d] == 1, "pic_engine_set_comm: a moving window needs slabs along its direction (nb[%d] = %d)", d, nb[d]);
     e->comm = c;
     int r = c->rank;
     for (int d = 0; d < 3; ++d) {
@@ -629,8 +718,8 @@ extern "C" int pic_engine_set_boundaries(void* h, const pic_boundaries* b) {
         else {
             PIC_REQUIRE(b->particle_lo[d] != PIC_PARTICLE_PERIODIC && b->particle_hi[d] != PIC_PARTICLE_PERIODIC,
                         "pic_engine_set_boundaries: periodic particles on the non-periodic direction %d", d);
-            PIC_REQUIRE(e->nb[d] == 1 && e->box_lo[d] == 0 && e->box_hi[d] == e->geom.n_cell[d] - 1,
-                        "pic_engine_set_boundaries: the box must span the domain along the non-periodic direction %d", d);
+            PIC_REQUIRE(e->box_hi[d] - e->box_lo[d] + 1 >= 2 * e->ng_J[d],
+                        "pic_engine_set_boundaries: the box is too thin along the non-periodic direction %d", d);
             e->all_periodic = false;
         }
         e->any_pec = e->any_pec || b->field_lo[d] == PIC_FIELD_PEC || b->field_hi[d] == PIC_FIELD_PEC;
@@ -642,7 +731,7 @@ extern "C" int pic_engine_set_moving_window(void* h, int dir, double v_over_c) {
     PIC_REQUIRE(dir >= 0 && dir < 3, "pic_engine_set_moving_window: bad direction");
     PIC_REQUIRE(!e->geom.periodic[dir], "The problem must be non-periodic in the moving window direction");   // WarpX.cpp:646-648
     PIC_REQUIRE(e->species.empty() && e->lasers.empty(), "pic_engine_set_moving_window: call before adding particles");
-    PIC_REQUIRE(e->comm == nullptr, "pic_engine_set_moving_window: one rank only");
+    PIC_REQUIRE(e->comm == nullptr, "pic_engine_set_moving_window: call before pic_engine_set_comm");
     e->do_moving_window = true; e->mw_dir = dir; e->mw_v = v_over_c * C_LIGHT;
     e->mw_x = e->geom.prob_lo[dir];                      // WarpX.cpp:649
     guard_cells(*e);
@@ -653,7 +742,11 @@ extern "C" int pic_engine_set_injector(void* h, int isp, const pic_plasma_inject
     PIC_REQUIRE(isp >= 0 && isp < (int)e->species.size(), "pic_engine_set_injector: no species %d", isp);
     Species& sp = e->species[isp];
     sp.has_injector = true; sp.inj = *inj;
-    sp.next_id = (uint64_t)sp.buf[sp.cur].np;
+    // ids continue after the particles the injector created at start-up on ALL ranks
+    const long created = pic_add_plasma(inj, &e->geom, e->dx, nullptr, nullptr, e->geom.prob_lo, e->geom.prob_hi,
+                                        nullptr, 0, 0, nullptr);
+    PIC_REQUIRE(created >= 0, "pic_engine_set_injector: bad injector");
+    sp.next_id = (uint64_t)created;
     if (e->do_moving_window)                            // WarpX.cpp:288-307
         sp.current_injection_position = e->mw_v > 0 ? e->geom.prob_hi[e->mw_dir] : e->geom.prob_lo[e->mw_dir];
     return 0;
@@ -666,6 +759,8 @@ extern "C" int pic_engine_add_laser(void* h, const pic_laser_antenna* prm, const
     Laser L;
     L.prm = *prm; L.P = *p; L.capacity = capacity;
     if (!e->all_periodic) ENG_CALL(alloc_boundary_scratch(capacity, &L.bnd_work, &L.bnd_cap));
+    if (e->comm && cudaMalloc(&L.w_owned, sizeof(double) * (size_t)(capacity > 0 ? capacity : 1)) != cudaSuccess)
+        return fail("pic_engine_add_laser: cannot allocate the weight scratch");
     e->lasers.push_back(L);
     return grow_host_counts(*e);
 }

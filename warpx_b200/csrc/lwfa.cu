@@ -165,9 +165,6 @@ extern "C" int pic_apply_pec_field(const pic_fab F[3], int is_E, const pic_geom*
         a.total = 1;
         for (int d = 0; d < 3; ++d) {
             PIC_REQUIRE(ng_fieldgather[d] <= F[c].ng[d], "pic_apply_pec_field: ng_fieldgather exceeds the allocated guard cells");
-            PIC_REQUIRE((vlo(F[c], d) == 0 && vhi(F[c], d) == g->n_cell[d] - 1 + F[c].stag[d]) ||
-                        (b->field_lo[d] != PIC_FIELD_PEC && b->field_hi[d] != PIC_FIELD_PEC),
-                        "pic_apply_pec_field: the box must span the domain along the PEC direction %d", d);
             a.stag[d] = F[c].stag[d];
             a.lo[d] = vlo(F[c], d) - ng_fieldgather[d];
             a.n[d] = vhi(F[c], d) + ng_fieldgather[d] - a.lo[d] + 1;
@@ -230,8 +227,15 @@ extern "C" int pic_shift_fab(const pic_fab* f, double* tmp, const pic_geom* g, i
         a.lo[d] = f->lo[d]; a.n[d] = f->hi[d] - f->lo[d] + 1;
         a.per[d] = g->periodic[d]; a.vlo[d] = vlo(*f, d); a.vhi[d] = vhi(*f, d); a.ncell[d] = g->n_cell[d];
     }
-    if (num_shift > 0) { a.n[dir] -= mag; a.adj_lo = vhi(*f, dir) + 1; a.adj_hi = vhi(*f, dir) + f->ng[dir]; }
-    else { a.lo[dir] += mag; a.n[dir] -= mag; a.adj_lo = vlo(*f, dir) - f->ng[dir]; a.adj_hi = vlo(*f, dir) - 1; }
+    // adjBox = the allocated points beyond the DOMAIN face the window moves into: only a box that touches
+    // that face has them; elsewhere those guard planes hold the neighbour's data (exchanged by the caller
+    // with ng = |num_shift|, the FillBoundary of shiftMF's temporary, :499-505)
+    const bool top = vhi(*f, dir) == g->n_cell[dir] - 1 + f->stag[dir], bottom = vlo(*f, dir) == 0;
+    if (num_shift > 0) { a.n[dir] -= mag; a.adj_lo = vhi(*f, dir) + 1; a.adj_hi = top ? vhi(*f, dir) + f->ng[dir] : vhi(*f, dir); }
+    else { a.lo[dir] += mag; a.n[dir] -= mag; a.adj_lo = bottom ? vlo(*f, dir) - f->ng[dir] : vlo(*f, dir); a.adj_hi = vlo(*f, dir) - 1; }
+    for (int d = 0; d < 3; ++d)
+        PIC_REQUIRE(d == dir || !g->periodic[d] || vhi(*f, d) - vlo(*f, d) + 1 - f->stag[d] == g->n_cell[d],
+                    "pic_shift_fab: the box must span the periodic direction %d (slabs along the moving direction)", d);
     for (int d = 0; d < 3; ++d) a.total *= a.n[d];
     PIC_LAUNCH(shift_kernel, shift_body, a, a.total, stream);
     return launched_ok("pic_shift_fab") ? 0 : 1;
@@ -314,20 +318,46 @@ extern "C" int pic_laser_antenna_push(const pic_laser_antenna* prm, const double
     return launched_ok("pic_laser_antenna_push") ? 0 : 1;
 }
 
+// Multi-rank antennas are replicated on every rank (a few thousand particles); each rank deposits
+// only the particles inside its own box: w_out = w inside [own_lo, own_hi), 0 elsewhere.
+namespace pic {
+struct OwnedArgs { const double* x; const double* y; const double* z; const double* w; double* w_out; long np; double lo[3], hi[3]; };
+PIC_HD void owned_body(long ip, const OwnedArgs& a) {
+    const bool in = a.x[ip] >= a.lo[0] && a.x[ip] < a.hi[0] && a.y[ip] >= a.lo[1] && a.y[ip] < a.hi[1] &&
+                    a.z[ip] >= a.lo[2] && a.z[ip] < a.hi[2];
+    a.w_out[ip] = in ? a.w[ip] : 0.0;
+}
+__global__ void owned_kernel(OwnedArgs a) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.np) owned_body(t, a);
+}
+}  // namespace pic
+extern "C" int pic_particles_owned_weights(const pic_soa* p, const double own_lo[3], const double own_hi[3],
+                                           double* w_out, void* stream) {
+    if (p->np == 0) return 0;
+    OwnedArgs a;
+    a.x = p->x; a.y = p->y; a.z = p->z; a.w = p->w; a.w_out = w_out; a.np = p->np;
+    for (int d = 0; d < 3; ++d) { a.lo[d] = own_lo[d]; a.hi[d] = own_hi[d]; }
+    PIC_LAUNCH(owned_kernel, owned_body, a, a.np, stream);
+    return launched_ok("pic_particles_owned_weights") ? 0 : 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // AddPlasma for NUniformPerCell / constant density / at rest, one tile = the rank's whole domain box.
 // Particles are appended after p->np (ids first_id, first_id+1, ... in creation order).
 // Returns the number of particles added (>= 0) or -1 on error.
 extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double cell_size[3],
-                               const double part_lo[3], const double part_hi[3], const pic_soa* p, long capacity,
-                               uint64_t first_id, void* stream) {
+                               const int box_lo[3], const int box_hi[3], const double part_lo[3],
+                               const double part_hi[3], const pic_soa* p, long capacity, uint64_t first_id,
+                               void* stream) {
     double dx[3], tile_lo[3], tile_hi[3], ov_lo[3], ov_hi[3];
     int nov[3];
     for (int d = 0; d < 3; ++d) {
         // geom.CellSize(): fixed at start-up; the moving window only translates prob_lo / prob_hi
         dx[d] = cell_size ? cell_size[d] : (g->prob_hi[d] - g->prob_lo[d]) / g->n_cell[d];
-        tile_lo[d] = g->prob_lo[d] + dx[d] * 0;
-        tile_hi[d] = g->prob_lo[d] + dx[d] * (g->n_cell[d] - 1 + 1);
+        // tile_realbox = RealBox(tile_box, dx, prob_lo) (WarpX::getRealBox, Source/WarpX.cpp:2852-2857)
+        tile_lo[d] = g->prob_lo[d] + dx[d] * (box_lo ? box_lo[d] : 0);
+        tile_hi[d] = g->prob_lo[d] + dx[d] * ((box_hi ? box_hi[d] : g->n_cell[d] - 1) + 1);
         // find_overlap (Particles/AddPlasmaUtilities.cpp:12-43)
         if (tile_lo[d] <= part_hi[d]) {
             const double adj = std::floor((tile_lo[d] - part_lo[d]) / dx[d]);
@@ -381,6 +411,7 @@ extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g
         count *= (m_hi - m_lo + 1);
         a.total *= a.nc[d];
     }
+    if (p == nullptr) return count;                      // count only (ranks that do not own the slab keep the id counter in step)
     if (p->np + count > capacity) { fail("pic_add_plasma: %ld + %ld particles exceed the capacity %ld", (long)p->np, count, capacity); return -1; }
     a.P = make_soa(*p, p->np);
     a.id = p->idcpu ? p->idcpu + p->np : nullptr;

@@ -109,7 +109,9 @@ __global__ void classify_kernel(const double* __restrict__ pos, long np_host, co
     // domain when this brick is the last one) belong to the high neighbour
     const int width = cell_hi - cell_lo + 1;
     const int up_lo = (cell_hi + 1) % ncell;                       // first cell of the high neighbour
-    const bool up = both_up || (c >= up_lo && c < up_lo + width);
+    // both_up: 1 = two ranks along a periodic dim (both neighbours are the same rank); 2 = non-periodic
+    // dim (ownership does not wrap: above the brick -> high neighbour, below -> low neighbour)
+    const bool up = both_up == 2 ? (c > cell_hi) : (both_up || (c >= up_lo && c < up_lo + width));
     if (up) { const int n = atomicAdd(&counts[1], 1); if (n < capacity) idx_hi[n] = (int)ip; }
     else    { const int n = atomicAdd(&counts[0], 1); if (n < capacity) idx_lo[n] = (int)ip; }
 }

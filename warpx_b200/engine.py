@@ -180,10 +180,11 @@ class Simulation:
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
                  tile=(8, 8, 8), use_bins=True, device=None, native_driver=True,
-                 use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None):
+                 use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None, nb=None):
         """boundaries: abi.pic_boundaries (boundary.field_lo/hi, boundary.particle_lo/hi; default all
         periodic); moving_window: (direction, v/c) == warpx.do_moving_window / moving_window_dir /
-        moving_window_v.  Non-periodic runs use the C++ driver on one rank."""
+        moving_window_v; nb: brick grid (default parallel.brick_grid(world); a moving window needs slabs
+        along its direction, e.g. (1, 1, world)).  Non-periodic runs use the C++ driver."""
         self.torch = require_cuda()
         t = self.torch
         self.L = lib()
@@ -206,15 +207,16 @@ class Simulation:
             for d in range(3):
                 self.geom.periodic[d] = 1 if boundaries.field_lo[d] == abi.FIELD_PERIODIC else 0
         self.nonperiodic = not all(self.geom.periodic[d] for d in range(3))
-        if (self.nonperiodic or moving_window is not None) and not (native_driver and use_bins and dist is None):
-            raise NotImplementedError("non-periodic / moving-window runs need the C++ driver on one rank")
+        if (self.nonperiodic or moving_window is not None) and not (native_driver and use_bins):
+            raise NotImplementedError("non-periodic / moving-window runs need the C++ driver")
         self.lasers = []
         self.time = 0.0
         g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass, moving_window is not None)
         self.ng_EB, self.ng_J, self.ng_FG, self.ng_FS = g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]
         self.ng_depos_J = g["ng_depos_J"]
         self._filter_tmp = None
-        self.dec = parallel.Decomposition(self.n_cell, parallel.brick_grid(self.world), self.rank)
+        self.dec = parallel.Decomposition(self.n_cell, tuple(nb) if nb is not None else parallel.brick_grid(self.world),
+                                          self.rank)
         self.box_lo, self.box_hi = self.dec.box_lo, self.dec.box_hi
         self.sort_interval, self.tile, self.use_bins = sort_interval, tuple(tile), use_bins
         # fields: Ex Ey Ez Bx By Bz jx jy jz, AMReX-shaped (valid + guards), Fortran order
@@ -332,8 +334,20 @@ class Simulation:
         empty = np.empty(0)
         sp = Species(self, name, q, m, {k: empty for k in Species.NAMES}, int(capacity))
         soa = sp.soa(0)
-        n = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.dbl3(self.prob_lo),
-                                  abi.dbl3(self.prob_hi), C.byref(soa), sp.capacity, 0, self.stream)
+        # ids = creation index in the order a single box would create the particles (k slowest): the
+        # ranks below this one come first when the bricks are slabs along z
+        first_id = 0
+        for r in range(self.rank):
+            other = parallel.Decomposition(self.n_cell, self.dec.nb, r)
+            cnt = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.int3(other.box_lo),
+                                        abi.int3(other.box_hi), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi), None, 0, 0,
+                                        None)
+            if cnt < 0:
+                raise RuntimeError("pic_b200: " + self.L.pic_last_error().decode())
+            first_id += cnt
+        n = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.int3(self.box_lo),
+                                  abi.int3(self.box_hi), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi), C.byref(soa),
+                                  sp.capacity, first_id, self.stream)
         if n < 0:
             raise RuntimeError("pic_b200: " + self.L.pic_last_error().decode())
         sp.np = int(n)
