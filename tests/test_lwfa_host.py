@@ -289,3 +289,102 @@ def test_device_shape_factors_match_reference_leaves(orc, hh, order):
             ia = hh.pic_host_shifted_shape(order, x_old, i_new, sa)
             ib = L.orc_shifted_shape(order, x_old, i_new, sb)
             assert ia == ib and list(sa) == list(sb), (x, x_old)
+
+
+# ---------------------------------------------------------------------------------------------
+# Slab decomposition along a non-periodic z (what the C++ driver does over several ranks), emulated on
+# the host: split the single-box arrays into two slabs, give each slab the neighbour planes a halo
+# exchange would deliver, run the kernels per slab, compare with the single-box oracle.
+# ---------------------------------------------------------------------------------------------
+def _slab_of(orc, full, comp, ng, klo, khi):
+    """HostFab of the cells [klo, khi] along z cut out of the single-box HostFab `full` (guards included:
+    they hold the neighbour's valid data or, beyond the domain faces, the box's own guards)."""
+    n = full.desc
+    blo = (n.lo[0] + ng[0], n.lo[1] + ng[1], klo)
+    bhi = (n.hi[0] - ng[0] - n.stag[0], n.hi[1] - ng[1] - n.stag[1], khi)
+    f = orc.HostFab(blo, bhi, ng, abi.YEE_STAG[comp])
+    k0 = f.desc.lo[2] - n.lo[2]
+    f.a[...] = full.a[k0:k0 + f.a.shape[0]]
+    return f
+
+
+@pytest.mark.parametrize("comp", [0, 2, 5, 6])
+@pytest.mark.parametrize("shift", [1, 2])
+def test_shift_on_slabs_equals_single_box(orc, hh, comp, shift):
+    n, ng = (6, 5, 24), (4, 4, 5) if comp >= 6 else (4, 4, 4)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    rng = np.random.default_rng(71)
+    full = orc.HostFab((0, 0, 0), tuple(v - 1 for v in n), ng, abi.YEE_STAG[comp])
+    full.a[...] = rng.standard_normal(full.a.shape)
+    _sync_periodic_duplicates(full, (1, 1, 0))
+    slabs = [_slab_of(orc, full, comp, ng, 0, 11), _slab_of(orc, full, comp, ng, 12, 23)]
+    orc.lib().orc_shift_fab(C.byref(full.desc), C.byref(geom), shift, 2, 0.0)
+    for f in slabs:
+        tmp = np.empty(f.a.size)
+        _check(hh, hh.pic_shift_fab(C.byref(f.desc), tmp.ctypes.data, C.byref(geom), shift, 2, 0.0, None))
+        k0 = f.desc.lo[2] - full.desc.lo[2]
+        vz = slice(ng[2], f.a.shape[0] - ng[2])               # the slab's valid planes (shared node included)
+        # x / y: the valid points and the first guard layer (what FillBoundary(1) of the temporary refreshes);
+        # rows at the periodic duplicate j = N: the oracle fills guards from the owner j = 0
+        sl = (vz, slice(ng[1] - 1, ng[1] + n[1]), slice(ng[0] - 1, -ng[0] + 1))
+        ref = full.a[k0:k0 + f.a.shape[0]]
+        assert np.array_equal(f.a[sl], ref[sl]), (comp, shift)
+
+
+@pytest.mark.parametrize("is_E", [1, 0])
+def test_pec_on_slabs_equals_single_box(orc, hh, is_E):
+    n, ng, ngfg = (6, 5, 24), (4, 4, 4), (2, 2, 2)
+    geom = abi.make_geom(n, (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"))
+    rng = np.random.default_rng(72)
+    comps = [c + (0 if is_E else 3) for c in range(3)]
+    full = [orc.HostFab((0, 0, 0), tuple(v - 1 for v in n), ng, abi.YEE_STAG[c]) for c in comps]
+    for f in full:
+        f.a[...] = rng.standard_normal(f.a.shape)
+    slabs = [[_slab_of(orc, f, c, ng, klo, khi) for f, c in zip(full, comps)] for klo, khi in ((0, 11), (12, 23))]
+    orc.lib().orc_apply_pec_field(orc.fab_array(full), is_E, C.byref(geom), C.byref(bnd), abi.int3(ngfg))
+    for S in slabs:
+        _check(hh, hh.pic_apply_pec_field(orc.fab_array(S), is_E, C.byref(geom), C.byref(bnd), abi.int3(ngfg), None))
+        for f, ref in zip(S, full):
+            k0 = f.desc.lo[2] - ref.desc.lo[2]
+            assert np.array_equal(f.a, ref.a[k0:k0 + f.a.shape[0]])
+
+
+@pytest.mark.parametrize("ppc", [(1, 1, 1), (2, 1, 2)])
+def test_add_plasma_on_slabs_equals_single_box(orc, hh, ppc):
+    """Initial plasma created slab by slab (tile = the rank's box, ids offset by the lower slabs' counts)
+    is the single-box creation, particle for particle; a continuous-injection slab at the top of the
+    domain is created by the top slab only, and the count-only call agrees with it."""
+    n_cell, prob_lo, prob_hi = (8, 6, 16), (-30.e-6, -20.e-6, -56.e-6), (30.e-6, 25.e-6, 12.e-6)
+    geom = abi.make_geom(n_cell, prob_lo, prob_hi, periodic=(1, 1, 0))
+    dz = (prob_hi[2] - prob_lo[2]) / n_cell[2]
+    inj = abi.make_injector(ppc, (-20.e-6, -20.e-6, -30.e-6), (20.e-6, 11.e-6, math.inf), 2.e23, True)
+    cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
+    for plo, phi in ((list(prob_lo), list(prob_hi)), ([prob_lo[0], prob_lo[1], prob_hi[2] - dz], list(prob_hi))):
+        s1, a1, id1 = _host_soa(cap)
+        n1 = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s1), cap, 0, None)
+        assert n1 > 0
+        assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, None) == n1
+        got = {k: [] for k in ("x", "y", "z", "w")}
+        ids, first = [], 0
+        for klo, khi in ((0, 7), (8, 15)):
+            blo, bhi = abi.int3((0, 0, klo)), abi.int3((n_cell[0] - 1, n_cell[1] - 1, khi))
+            s2, a2, id2 = _host_soa(cap)
+            m = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), C.byref(s2), cap, first, None)
+            assert m >= 0
+            assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, None) == m
+            for k in got:
+                got[k].append(a2[k][:m])
+            ids.append(id2[:m])
+            first += m
+        assert first == n1
+        for k in got:
+            cat = np.concatenate(got[k])
+            if k == "z" and plo[2] == prob_lo[2]:
+                # whole-domain creation: a slab's lattice starts from ITS overlap corner (find_overlap,
+                # AddPlasmaUtilities.cpp:22-23), so z agrees with the single-box value to rounding only --
+                # the reference's positions depend on the box decomposition in exactly the same way
+                assert np.max(np.abs(cat - a1[k][:n1])) <= 4 * np.finfo(float).eps * abs(prob_lo[2])
+            else:
+                assert np.array_equal(cat, a1[k][:n1]), k
+        assert np.array_equal(np.concatenate(ids), id1[:n1])

@@ -233,6 +233,10 @@ extern "C" int pic_shift_fab(const pic_fab* f, double* tmp, const pic_geom* g, i
     const bool top = vhi(*f, dir) == g->n_cell[dir] - 1 + f->stag[dir], bottom = vlo(*f, dir) == 0;
     if (num_shift > 0) { a.n[dir] -= mag; a.adj_lo = vhi(*f, dir) + 1; a.adj_hi = top ? vhi(*f, dir) + f->ng[dir] : vhi(*f, dir); }
     else { a.lo[dir] += mag; a.n[dir] -= mag; a.adj_lo = bottom ? vlo(*f, dir) - f->ng[dir] : vlo(*f, dir); a.adj_hi = vlo(*f, dir) - 1; }
+    // the planes just exchanged with the next slab count as valid for the folded periodic refresh
+    // (FillBoundary reaches them: their periodic image is a valid point of the neighbour)
+    if (num_shift > 0 && !top) a.vhi[dir] += mag;
+    if (num_shift < 0 && !bottom) a.vlo[dir] -= mag;
     for (int d = 0; d < 3; ++d)
         PIC_REQUIRE(d == dir || !g->periodic[d] || vhi(*f, d) - vlo(*f, d) + 1 - f->stag[d] == g->n_cell[d],
                     "pic_shift_fab: the box must span the periodic direction %d (slabs along the moving direction)", d);
