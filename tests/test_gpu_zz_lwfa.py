@@ -15,7 +15,7 @@ import pytest
 from helpers import rel_linf
 from helpers import lower_corner, random_fields
 from test_gpu_parity import Dev, _particles, _run_both, _match_particles, box  # noqa: F401
-from test_oracle import make_lwfa_oracle
+from test_oracle import check_pec_particle, make_lwfa_oracle
 from warpx_b200 import abi, workloads
 
 pytestmark = pytest.mark.gpu
@@ -442,3 +442,46 @@ def test_order4_loop_matches_oracle(orc, cuda):
         assert np.max(np.abs(A[k] - B[k])) / sim.dx[0] <= 1e-10
     for k in ("ux", "uy", "uz"):
         assert np.max(np.abs(A[k] - B[k])) / workloads.C <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's PEC decks (Examples/Tests/pec) on the GPU against WarpX's golden checksums
+# ---------------------------------------------------------------------------------------------
+def test_pec_field_golden_checksums(orc, cuda, golden):
+    from warpx_b200.engine import Simulation
+    wl = workloads.pec_field_3d()
+    sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], use_filter=wl["use_filter"],
+                     boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]))
+    for c, fn in wl["init_fields"].items():
+        d, a = sim.field_numpy(c)
+        sim.set_field(c, fn(*workloads.staggered_coordinates(d, wl["prob_lo"], sim.dx)) + 0.0 * a)
+    sim.Evolve(wl["max_step"])
+    cuda.cuda.synchronize()
+    g = golden["test_3d_pec_field"]["lev=0"]
+    L = orc.lib()
+    for name, c in (("Ey", 1), ("Bx", 3)):
+        d, a = sim.field_numpy(c)
+        hf = orc.HostFab(sim.box_lo, sim.box_hi, d.ng, abi.YEE_STAG[c], data=a)
+        cs = L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
+        assert abs(cs - g[name]) <= 1e-9 * abs(g[name]), name
+
+
+def test_pec_particle_golden_checksums(orc, cuda, golden):
+    """PEC walls in x with two particles 2 nm from the wall (Vay, order 3, filter); jx: see tests/test_oracle.py."""
+    from warpx_b200.engine import Simulation
+    wl = workloads.pec_particle_3d()
+    sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], use_filter=wl["use_filter"],
+                     pusher=abi.PUSHER_VAY, boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]))
+    for s in wl["species"]:
+        sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.Evolve(wl["max_step"])
+    cuda.cuda.synchronize()
+    L = orc.lib()
+
+    def checksum(c):
+        d, a = sim.field_numpy(c)
+        hf = orc.HostFab(sim.box_lo, sim.box_hi, d.ng, abi.YEE_STAG[c], data=a)
+        return L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
+
+    ratio = check_pec_particle(golden, checksum, lambda isp: sim.species_numpy(isp), wl["mass"])
+    assert ratio == pytest.approx(2.0, rel=1e-9)

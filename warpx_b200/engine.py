@@ -664,6 +664,13 @@ class Simulation:
             n = int(tt.item())
         return n
 
+    def set_field(self, comp, values):
+        """Overwrite component comp (0..8 = Ex..jz), guards included, with a host array shaped like
+        field_numpy(comp)[1] (e.g. warpx.E/B_ext_grid_init_style = parse_*_ext_grid_function at start-up)."""
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        assert a.shape == tuple(self.data[comp].shape)
+        self.data[comp].copy_(self.torch.from_numpy(a))
+
     def field_numpy(self, comp):
         """(descriptor, numpy array [k, j, i]) of component comp (0..8 = Ex..jz)."""
         return self.fab[comp], self.data[comp].cpu().numpy()

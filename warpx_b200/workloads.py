@@ -151,3 +151,51 @@ def laser_acceleration_3d(n_cell=(32, 32, 256), max_step=100, solver=0, pusher=0
                      polarization=(0., 1., 0.), e_max=16.e12, waist=5.e-6, duration=15.e-15,
                      t_peak=30.e-15, focal_distance=100.e-6, wavelength=0.8e-6)],
         region_of_interest=(12.0e-6, 13.0e-6))
+
+
+def staggered_coordinates(fab, prob_lo, dx):
+    """x, y, z (numpy, broadcastable to the fab's [k, j, i] array) of every ALLOCATED point of a
+    component, as WarpX::ComputeExternalFieldOnGridUsingParser evaluates them
+    (Source/Initialization/WarpXInitData.cpp:1140-1147): index * dx + prob_lo + (1 - nodal) * dx / 2."""
+    out = []
+    for d in range(3):
+        idx = np.arange(fab.lo[d], fab.hi[d] + 1, dtype=np.float64)
+        fac = (1.0 - fab.stag[d]) * dx[d] * 0.5
+        c = idx * dx[d] + prob_lo[d] + fac
+        shape = [1, 1, 1]
+        shape[2 - d] = len(c)
+        out.append(c.reshape(shape))
+    return out
+
+
+def pec_field_3d():
+    """Examples/Tests/pec/inputs_test_3d_pec_field: a wave packet between two PEC walls (no particles),
+    125 steps at cfl 0.9; initial Ey / Bx from warpx.E/B_ext_grid_init_style = parse_*_ext_grid_function."""
+    z1, z2, wavelength = -2.e-6, 2.e-6, 1.e-6
+
+    def ey(x, y, z):
+        return ((1.e5 * np.sin(2 * np.pi * (z) / wavelength)) * (z < z2) * (z > z1)) + 0.0 * (x + y)
+
+    def bx(x, y, z):
+        return (((-1.e5 * np.sin(2 * np.pi * (z) / wavelength)) / C)) * (z < z2) * (z > z1) + 0.0 * (x + y)
+
+    return dict(n_cell=(32, 32, 256), prob_lo=(-8.e-6, -8.e-6, -4.e-6), prob_hi=(8.e-6, 8.e-6, 4.e-6),
+                field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
+                nox=1, use_filter=True, cfl=0.9, max_step=125, init_fields={1: ey, 3: bx}, species=[])
+
+
+def pec_particle_3d():
+    """Examples/Tests/pec/inputs_test_3d_pec_particle: two heavy particles 2 nm from a PEC wall in x
+    (order 3, Vay pusher, bilinear filter, cfl 0.9, 20 steps)."""
+    M_P = 1.67262192369e-27          # ablastr/constant.H:54
+    pos = (31.998e-6, 0.0, 0.0)
+    one = lambda v: np.array([v], dtype=np.float64)   # noqa: E731
+    species = [
+        dict(name="electron", q=-Q_E, m=M_P, x=one(pos[0]), y=one(pos[1]), z=one(pos[2]), w=one(1.0),
+             ux=one(0.0), uy=one(0.0), uz=one(0.0)),
+        dict(name="proton", q=Q_E, m=M_P, x=one(pos[0]), y=one(pos[1]), z=one(pos[2]), w=one(1.0),
+             ux=one(0.0), uy=one(-2.0 * C), uz=one(0.0)),
+    ]
+    return dict(n_cell=(128, 64, 64), prob_lo=(-32.e-6,) * 3, prob_hi=(32.e-6,) * 3,
+                field_lo=("pec", "periodic", "periodic"), field_hi=("pec", "periodic", "periodic"),
+                nox=3, use_filter=True, cfl=0.9, max_step=20, pusher=1, species=species, mass=M_P)
