@@ -466,6 +466,23 @@ def test_pec_field_golden_checksums(orc, cuda, golden):
         assert abs(cs - g[name]) <= 1e-9 * abs(g[name]), name
 
 
+def test_laser_injection_golden_checksums(orc, cuda, golden):
+    """Examples/Tests/laser_injection (order 1, no filter, antenna in vacuum, moving window) on the GPU."""
+    wl = workloads.laser_injection_3d()
+    sim = make_lwfa_sim(wl, capacity=1)
+    sim.Evolve(wl["max_step"])
+    cuda.cuda.synchronize()
+    g = golden["test_3d_laser_injection"]["lev=0"]
+    L = orc.lib()
+    for c, name in enumerate(abi.COMP_NAMES):
+        if name not in g:
+            continue
+        d, a = sim.field_numpy(c)
+        hf = orc.HostFab(sim.box_lo, sim.box_hi, d.ng, abi.YEE_STAG[c], data=a)
+        cs = L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
+        assert abs(cs - g[name]) <= 1e-9 * abs(g[name]) + 1e-40, name
+
+
 def test_pec_particle_golden_checksums(orc, cuda, golden):
     """PEC walls in x with two particles 2 nm from the wall (Vay, order 3, filter); jx: see tests/test_oracle.py."""
     from warpx_b200.engine import Simulation

@@ -524,3 +524,17 @@ def test_pec_particle_golden_checksums(orc, golden):
     sim.evolve(wl["max_step"])
     ratio = check_pec_particle(golden, sim.checksum_field, sim.particles, wl["mass"])
     assert ratio == pytest.approx(2.0, rel=1e-12)
+
+
+def test_laser_injection_golden_checksums(orc, golden):
+    """Examples/Tests/laser_injection/inputs_test_3d_laser_injection (test_3d_laser_injection.json): the
+    Gaussian antenna radiating into vacuum, order 1, no filter, moving window, 20 steps.  jy at 1e-12; the
+    radiated Ey / Bx sit 8.2e-10 below the stored values (inside WarpX's 1e-9, same on every build and
+    thread count here -- the stored file was produced on another platform)."""
+    wl = workloads.laser_injection_3d()
+    sim = make_lwfa_oracle(orc, wl)
+    sim.evolve(wl["max_step"])
+    g = golden["test_3d_laser_injection"]["lev=0"]
+    for c, name in enumerate(abi.COMP_NAMES):
+        if name in g:
+            assert _close(sim.checksum_field(c), g[name]), name

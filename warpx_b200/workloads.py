@@ -199,3 +199,16 @@ def pec_particle_3d():
     return dict(n_cell=(128, 64, 64), prob_lo=(-32.e-6,) * 3, prob_hi=(32.e-6,) * 3,
                 field_lo=("pec", "periodic", "periodic"), field_hi=("pec", "periodic", "periodic"),
                 nox=3, use_filter=True, cfl=0.9, max_step=20, pusher=1, species=species, mass=M_P)
+
+
+def laser_injection_3d():
+    """Examples/Tests/laser_injection/inputs_test_3d_laser_injection: a Gaussian antenna radiating into
+    vacuum between PEC walls, moving window at c, order 1, no filter, 20 steps (no plasma)."""
+    return dict(
+        n_cell=(32, 32, 240), prob_lo=(-20.e-6, -20.e-6, -12.e-6), prob_hi=(20.e-6, 20.e-6, 12.e-6),
+        field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
+        nox=1, use_filter=False, cfl=1.0, moving_window_dir=2, moving_window_v=1.0, max_step=20,
+        solver=0, pusher=0, species=[],
+        lasers=[dict(name="laser1", position=(0., 0., 9.e-6), direction=(0., 0., 1.), polarization=(0., 1., 0.),
+                     e_max=4.e12, waist=5.e-6, duration=15.e-15, t_peak=30.e-15, focal_distance=100.e-6,
+                     wavelength=0.8e-6)])
