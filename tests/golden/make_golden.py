@@ -15,19 +15,20 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "warpx_checksums.
 
 gold = {
     "_provenance": {
-        "source": "ECP-WarpX/WarpX Regression/Checksum/benchmarks_json/{test_3d_langmuir_multi,test_3d_particle_pusher,test_3d_laser_acceleration,test_3d_pec_field,test_3d_pec_particle,test_3d_laser_injection}.json",
+        "source": "ECP-WarpX/WarpX Regression/Checksum/benchmarks_json/{test_3d_langmuir_multi,test_3d_particle_pusher,test_3d_laser_acceleration,test_3d_pec_field,test_3d_pec_particle,test_3d_laser_injection,test_3d_particle_boundaries}.json",
         "tolerance": "rtol 1e-9, atol 1e-40 (Regression/Checksum/checksum.py:219-301)",
         "decks": ["Examples/Tests/langmuir/inputs_test_3d_langmuir_multi",
                   "Examples/Tests/particle_pusher/inputs_test_3d_particle_pusher",
                   "Examples/Physics_applications/laser_acceleration/inputs_test_3d_laser_acceleration",
                   "Examples/Tests/pec/inputs_test_3d_pec_field", "Examples/Tests/pec/inputs_test_3d_pec_particle",
-                  "Examples/Tests/laser_injection/inputs_test_3d_laser_injection"],
+                  "Examples/Tests/laser_injection/inputs_test_3d_laser_injection",
+                  "Examples/Tests/boundaries/inputs_test_3d_particle_boundaries"],
         "pusher_expected_error": {"boris": 2321.3958529, "vay": 0.00010467, "higuera_cary": 0.00011403,
                                   "source": "Examples/Tests/particle_pusher/analysis.py:17-21"},
     }
 }
 for name in ("test_3d_langmuir_multi", "test_3d_particle_pusher", "test_3d_laser_acceleration", "test_3d_pec_field",
-             "test_3d_pec_particle", "test_3d_laser_injection"):
+             "test_3d_pec_particle", "test_3d_laser_injection", "test_3d_particle_boundaries"):
     with open(os.path.join(REF, name + ".json")) as f:
         gold[name] = json.load(f)
 with open(OUT, "w") as f:

@@ -15,7 +15,7 @@ import pytest
 from helpers import rel_linf
 from helpers import lower_corner, random_fields
 from test_gpu_parity import Dev, _particles, _run_both, _match_particles, box  # noqa: F401
-from test_oracle import check_pec_particle, make_lwfa_oracle
+from test_oracle import check_particle_boundaries, check_pec_particle, make_lwfa_oracle
 from warpx_b200 import abi, workloads
 
 pytestmark = pytest.mark.gpu
@@ -502,3 +502,17 @@ def test_pec_particle_golden_checksums(orc, cuda, golden):
 
     ratio = check_pec_particle(golden, checksum, lambda isp: sim.species_numpy(isp), wl["mass"])
     assert ratio == pytest.approx(2.0, rel=1e-9)
+
+
+def test_particle_boundaries_golden_checksums(orc, cuda, golden):
+    """Examples/Tests/boundaries (reflecting x, absorbing y, periodic z, neutral particles) on the GPU."""
+    from warpx_b200.engine import Simulation
+    wl = workloads.particle_boundaries_3d()
+    sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], use_filter=wl["use_filter"],
+                     boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"], wl["particle_lo"], wl["particle_hi"]))
+    for s in wl["species"]:
+        sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.Evolve(wl["max_step"])
+    cuda.cuda.synchronize()
+    check_particle_boundaries(golden, lambda isp: sim.species_numpy(isp))
+    assert sim.species[1].np == 1

@@ -538,3 +538,28 @@ def test_laser_injection_golden_checksums(orc, golden):
     for c, name in enumerate(abi.COMP_NAMES):
         if name in g:
             assert _close(sim.checksum_field(c), g[name]), name
+
+
+def check_particle_boundaries(golden, particles):
+    g = golden["test_3d_particle_boundaries"]
+    for isp, sname in enumerate(("reflecting_particles", "absorbing_particles", "periodic_particles")):
+        P = particles(isp)
+        vals = {"particle_position_x": P["x"], "particle_position_y": P["y"], "particle_position_z": P["z"],
+                "particle_momentum_x": P["ux"] * workloads.M_E, "particle_momentum_y": P["uy"] * workloads.M_E,
+                "particle_momentum_z": P["uz"] * workloads.M_E, "particle_weight": P["w"]}
+        for key, arr in vals.items():
+            assert _close(float(np.sum(np.abs(arr))), g[sname][key]), (sname, key)
+
+
+def test_particle_boundaries_golden_checksums(orc, golden):
+    """Examples/Tests/boundaries/inputs_test_3d_particle_boundaries (test_3d_particle_boundaries.json):
+    reflecting x, absorbing y, periodic z for neutral particles -- the golden pin of
+    ApplyBoundaryConditions + Redistribute (two of the three absorbing particles disappear)."""
+    wl = workloads.particle_boundaries_3d()
+    sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], use_filter=wl["use_filter"])
+    sim.set_boundaries(abi.make_boundaries(wl["field_lo"], wl["field_hi"], wl["particle_lo"], wl["particle_hi"]))
+    for s in wl["species"]:
+        sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.evolve(wl["max_step"])
+    check_particle_boundaries(golden, sim.particles)
+    assert sim.checksum_field(0) == 0.0 and len(sim.particles(1)["x"]) == 1

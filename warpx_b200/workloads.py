@@ -212,3 +212,23 @@ def laser_injection_3d():
         lasers=[dict(name="laser1", position=(0., 0., 9.e-6), direction=(0., 0., 1.), polarization=(0., 1., 0.),
                      e_max=4.e12, waist=5.e-6, duration=15.e-15, t_peak=30.e-15, focal_distance=100.e-6,
                      wavelength=0.8e-6)])
+
+
+def particle_boundaries_3d():
+    """Examples/Tests/boundaries/inputs_test_3d_particle_boundaries: neutral particles flying into
+    reflecting (x), absorbing (y) and periodic (z) faces of a 16^3 box, 8 steps, order 1."""
+    c = C
+    arr = lambda *v: np.array(v, dtype=np.float64)   # noqa: E731
+    z2, z3 = arr(0., 0.), arr(0., 0., 0.)
+    species = [
+        dict(name="reflecting_particles", q=0.0, m=M_E, x=arr(-0.9, 0.91), y=z2, z=z2, w=arr(1., 1.),
+             ux=arr(-0.9, 0.91) * c, uy=z2, uz=z2),
+        dict(name="absorbing_particles", q=0.0, m=M_E, x=z3, y=arr(-0.92, 0.93, 0.), z=z3, w=arr(1., 1., 1.),
+             ux=z3, uy=arr(-0.92, 0.93, 0.) * c, uz=z3),
+        dict(name="periodic_particles", q=0.0, m=M_E, x=z2, y=z2, z=arr(-0.94, 0.95), w=arr(1., 1.),
+             ux=z2, uy=z2, uz=arr(-0.94, 0.95) * c),
+    ]
+    return dict(n_cell=(16, 16, 16), prob_lo=(-1.0,) * 3, prob_hi=(1.0,) * 3,
+                field_lo=("pec", "pec", "periodic"), field_hi=("pec", "pec", "periodic"),
+                particle_lo=("reflecting", "absorbing", "periodic"), particle_hi=("reflecting", "absorbing", "periodic"),
+                nox=1, use_filter=True, cfl=1.0, max_step=8, species=species)
