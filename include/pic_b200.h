@@ -424,6 +424,16 @@ int pic_sum_squares_unique(const pic_fab* f, const pic_geom* g, double* out, voi
  * out[0] = sum w m u^2 / (1 + gamma) [J], out[1] = sum w.  out: 2 doubles, device. */
 int pic_particle_energy(const pic_soa* p, double mass, double* out, void* stream);
 
+/* The `rho` diagnostic (not on the per-step path of the FDTD loop).
+ * pic_deposit_charge: WarpXParticleContainer::DepositCharge (Source/Particles/WarpXParticleContainer.cpp:
+ *   890-1216) -> doChargeDepositionShapeN<nox> (Source/Particles/Deposition/ChargeDeposition.H:37-157);
+ *   rho is ADDED to; xyzmin / lo describe the tile box grown by rho's guard cells.
+ * pic_apply_pec_rho: PEC::ApplyReflectiveBoundarytoRhofield (Source/BoundaryConditions/WarpX_PEC.cpp:624-699),
+ *   applied per container before the containers are summed (WarpXParticleContainer.cpp:1277-1283). */
+int pic_deposit_charge(const pic_soa* p, long offset, long np, const pic_fab* rho, const double dinv[3],
+                       const double xyzmin[3], const int lo[3], double q, int nox, void* stream);
+int pic_apply_pec_rho(const pic_fab* rho, const pic_geom* g, const pic_boundaries* b, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 long pic_launch_count(void);
 

@@ -100,6 +100,9 @@ def lib(kind="restated"):
         "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long]),
         "orc_apply_particle_boundaries": (None, [soap, gp, C.POINTER(abi.pic_boundaries), C.c_char_p]),
         "orc_antenna_particles": (C.c_long, [C.POINTER(abi.pic_laser_antenna), dp, dp, dp, dp, dp, dp, dp, C.c_long]),
+        "orc_sim_rho_checksum": (C.c_double, [vp]),
+        "orc_deposit_charge": (C.c_int, [soap, fabp, dp, dp, ip, C.c_double, C.c_int]),
+        "orc_apply_pec_rho": (None, [fabp, gp, C.POINTER(abi.pic_boundaries)]),
         "orc_particle_energy": (None, [soap, C.c_double, dp]),
         "orc_sim_particle_energy": (None, [vp, C.c_int, dp]),
         "orc_num_threads": (C.c_int, []),
@@ -265,6 +268,10 @@ class OracleSim:
         out = (C.c_double * 2)()
         self.L.orc_sim_field_energy(self.h, out)
         return out[0], out[1]
+
+    def rho_checksum(self):
+        """Checksum of the cell-centred `rho` diagnostic (all containers; single box)."""
+        return self.L.orc_sim_rho_checksum(self.h)
 
     def particle_energy(self, isp):
         out = (C.c_double * 2)()

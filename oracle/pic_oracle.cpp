@@ -667,6 +667,69 @@ void orc_sim_field_energy(void* h, double* out) {
     out[0] = 0.5 * e2 * EP0 * dV;
     out[1] = 0.5 * b2 / MU0 * dV;
 }
+// The `rho` diagnostic of a plotfile (Diagnostics/ComputeDiagFunctors/RhoFunctor.cpp:35-81): every
+// container deposits into its own nodal rho with ng_depos_rho guard cells (Particles/
+// WarpXParticleContainer.cpp:1287-1310; GuardCellManager.cpp:130-165) and applies the PEC / reflecting
+// boundary (:1277-1283), the containers are added (Particles/MultiParticleContainer.cpp:593-612), then
+// WarpX::ApplyFilterandSumBoundaryRho (Parallelization/WarpXComm.cpp:1552-1568): with the bilinear
+// filter the filtered copy has stencil_length-1 more guard cells and is summed back into rho.
+// Returns the checksum of the cell-centred rho (single box).
+double orc_sim_rho_checksum(void* h) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1) return -1.0;
+    Sim::Box& b = s->boxes[0];
+    int ng = 0;
+    for (int d = 0; d < 3; ++d) {
+        int base = s->nox;
+        if (s->do_moving_window) base = std::max(base, 2);
+        ng = std::max(ng, base + 1 + (int)std::ceil(C_LIGHT * s->dt / s->dx[d]));
+    }
+    auto make = [&](int g, std::vector<double>& store) {
+        pic_fab f;
+        for (int d = 0; d < 3; ++d) { f.stag[d] = 1; f.ng[d] = g; f.lo[d] = b.lo[d] - g; f.hi[d] = b.hi[d] + 1 + g; }
+        store.assign((size_t)fab_size(f), 0.0);
+        f.p = store.data();
+        return f;
+    };
+    std::vector<double> tot_s, one_s, filt_s;
+    pic_fab rho = make(ng, tot_s);
+    double xyzmin[3]; int lo[3];
+    const int ngv[3] = {ng, ng, ng};
+    lower_corner(*s, b, ngv, xyzmin, lo);
+    auto add_container = [&](const pic_soa& P, double q) {
+        pic_fab one = make(ng, one_s);
+        deposit_charge<Leaf>(P, one, s->dinv, xyzmin, lo, q, s->nox);
+        if (s->any_pec) apply_pec_rho(one, s->geom, s->bnd);
+        for (size_t n = 0; n < tot_s.size(); ++n) tot_s[n] += one_s[n];
+    };
+    for (auto& sp : b.sp) add_container(sp.soa(), sp.q);
+    for (auto& L : s->lasers) add_container(laser_soa(L), 1.0);
+    if (s->use_filter) {
+        int ngf = ng;
+        for (int d = 0; d < 3; ++d) ngf = std::max(ngf, ng + s->npass[d]);
+        pic_fab rf = make(ng, filt_s);                          // per-direction growth below
+        for (int d = 0; d < 3; ++d) { rf.ng[d] = ng + s->npass[d]; rf.lo[d] = b.lo[d] - rf.ng[d]; rf.hi[d] = b.hi[d] + 1 + rf.ng[d]; }
+        filt_s.assign((size_t)fab_size(rf), 0.0);
+        rf.p = filt_s.data();
+        apply_filter(rho, rf, s->npass);
+        // WarpXSumGuardCells(rho, rf, ...): rho = 0, then every point of rho receives all copies of rf
+        int src_ng[3];
+        for (int d = 0; d < 3; ++d) src_ng[d] = rf.ng[d];
+        sum_boundary(&rf, 1, src_ng, src_ng, s->geom);
+        W R(rho), F(rf);
+        for (int k = rho.lo[2]; k <= rho.hi[2]; ++k)
+            for (int j = rho.lo[1]; j <= rho.hi[1]; ++j)
+                for (int i = rho.lo[0]; i <= rho.hi[0]; ++i) R(i, j, k) = F(i, j, k);
+    } else {
+        sum_boundary(&rho, 1, ngv, ngv, s->geom);
+    }
+    return checksum_cell_centered(rho, b.lo, b.hi);
+}
+int orc_deposit_charge(const pic_soa* p, const pic_fab* rho, const double* dinv, const double* xyzmin, const int* lo,
+                       double q, int nox) {
+    return deposit_charge<Leaf>(*p, *rho, dinv, xyzmin, lo, q, nox);
+}
+void orc_apply_pec_rho(const pic_fab* rho, const pic_geom* g, const pic_boundaries* b) { apply_pec_rho(*rho, *g, *b); }
 void orc_particle_energy(const pic_soa* p, double mass, double* out) { particle_energy(*p, mass, out); }
 // ParticleEnergy of species isp: out = {total kinetic energy [J], sum of weights}
 void orc_sim_particle_energy(void* h, int isp, double* out) {

@@ -363,6 +363,41 @@ int deposit(const pic_soa& P, long offset, long np, const pic_fab J[3], const do
 }
 
 // ============================================================================================
+// Charge deposition (diagnostic: the `rho` of the golden checksum files).
+// doChargeDepositionShapeN<N> (Particles/Deposition/ChargeDeposition.H:37-157, 3D :146-155) into a
+// nodal rho: wq = q w / dV, weights = Compute_shape_factor at (x - xyzmin) * dinv.
+// ============================================================================================
+template <class L, int N>
+void deposit_charge_t(const pic_soa& P, const pic_fab& rho, const double dinv[3], const double xyzmin[3],
+                      const int lo[3], double q) {
+    W R(rho);
+    const double invvol = dinv[0] * dinv[1] * dinv[2];
+    for (long ip = 0; ip < P.np; ++ip) {
+        const double wq = q * P.w[ip] * invvol;
+        double sx[N + 1] = {0.}, sy[N + 1] = {0.}, sz[N + 1] = {0.};
+        const double x = (P.x[ip] - xyzmin[0]) * dinv[0], y = (P.y[ip] - xyzmin[1]) * dinv[1],
+                     z = (P.z[ip] - xyzmin[2]) * dinv[2];
+        const int i = L::template shape<N>(sx, rho.stag[0] ? x : x - 0.5);
+        const int j = L::template shape<N>(sy, rho.stag[1] ? y : y - 0.5);
+        const int k = L::template shape<N>(sz, rho.stag[2] ? z : z - 0.5);
+        for (int iz = 0; iz <= N; ++iz)
+            for (int iy = 0; iy <= N; ++iy)
+                for (int ix = 0; ix <= N; ++ix)
+                    R(lo[0] + i + ix, lo[1] + j + iy, lo[2] + k + iz) += sx[ix] * sy[iy] * sz[iz] * wq;
+    }
+}
+template <class L>
+int deposit_charge(const pic_soa& P, const pic_fab& rho, const double dinv[3], const double xyzmin[3],
+                   const int lo[3], double q, int nox) {
+    if (nox == 1) deposit_charge_t<L, 1>(P, rho, dinv, xyzmin, lo, q);
+    else if (nox == 2) deposit_charge_t<L, 2>(P, rho, dinv, xyzmin, lo, q);
+    else if (nox == 3) deposit_charge_t<L, 3>(P, rho, dinv, xyzmin, lo, q);
+    else if (nox == 4) deposit_charge_t<L, 4>(P, rho, dinv, xyzmin, lo, q);
+    else return 1;
+    return 0;
+}
+
+// ============================================================================================
 // Guard cells on a set of boxes tiling a periodic domain (semantics of AMReX FabArray
 // FillBoundary / SumBoundary, AMReX 24.10 @62c2a81 -- un-vendored dependency; call sites
 // ablastr/utils/Communication.cpp:71-115 and :148-175).

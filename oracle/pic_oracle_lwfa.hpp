@@ -123,6 +123,54 @@ inline void apply_pec_current(const pic_fab J[3], const pic_geom& g, const pic_b
     }
 }
 
+// PEC::ApplyReflectiveBoundarytoRhofield (WarpX_PEC.cpp:624-699): like the tangential current --
+// the wall value vanishes, the interior loses the image charge deposited beyond the wall (psign = -1
+// unless the particles are reflected), the guards hold minus the interior.  mirrorfac: :679-680.
+inline void apply_pec_rho(const pic_fab& f, const pic_geom& g, const pic_boundaries& bnd) {
+    W A(f);
+    bool is_refl[3][2];
+    double psign[3][2];
+    int mirrorfac[3][2];
+    bool any = false;
+    for (int idim = 0; idim < 3; ++idim) {
+        const bool plo = bnd.particle_lo[idim] == PIC_PARTICLE_REFLECTING;
+        const bool phi = bnd.particle_hi[idim] == PIC_PARTICLE_REFLECTING;
+        is_refl[idim][0] = plo || bnd.field_lo[idim] == PIC_FIELD_PEC;
+        is_refl[idim][1] = phi || bnd.field_hi[idim] == PIC_FIELD_PEC;
+        any = any || is_refl[idim][0] || is_refl[idim][1];
+        psign[idim][0] = plo ? 1.0 : -1.0;
+        psign[idim][1] = phi ? 1.0 : -1.0;
+        const int dom_lo = 0, dom_hi = g.n_cell[idim] - 1 + f.stag[idim];     // domain box converted to rho's type
+        mirrorfac[idim][0] = 2 * dom_lo - (1 - f.stag[idim]);
+        mirrorfac[idim][1] = 2 * dom_hi + (1 - f.stag[idim]);
+    }
+    if (!any) return;
+    auto contains = [&](const int* iv) {
+        return iv[0] >= f.lo[0] && iv[0] <= f.hi[0] && iv[1] >= f.lo[1] && iv[1] <= f.hi[1] &&
+               iv[2] >= f.lo[2] && iv[2] <= f.hi[2];
+    };
+    for (int k = vlo(f, 2); k <= vhi(f, 2); ++k)
+        for (int j = vlo(f, 1); j <= vhi(f, 1); ++j)
+            for (int i = vlo(f, 0); i <= vhi(f, 0); ++i) {
+                const int ijk[3] = {i, j, k};
+                for (int idim = 0; idim < 3; ++idim)
+                    for (int iside = 0; iside < 2; ++iside) {
+                        if (!is_refl[idim][iside]) continue;
+                        int mir[3] = {i, j, k};
+                        mir[idim] = mirrorfac[idim][iside] - ijk[idim];
+                        if (mir[idim] == ijk[idim]) A(i, j, k) = 0.0;
+                        else if (contains(mir)) A(i, j, k) += psign[idim][iside] * A(mir[0], mir[1], mir[2]);
+                    }
+                for (int idim = 0; idim < 3; ++idim)
+                    for (int iside = 0; iside < 2; ++iside) {
+                        if (!is_refl[idim][iside]) continue;
+                        int mir[3] = {i, j, k};
+                        mir[idim] = mirrorfac[idim][iside] - ijk[idim];
+                        if (mir[idim] != ijk[idim] && contains(mir)) A(mir[0], mir[1], mir[2]) = -A(i, j, k);
+                    }
+            }
+}
+
 // ============================================================================================
 // Moving window: shift of one field component by num_shift cells along dir.
 // WarpX::shiftMF (Utils/WarpXMovingWindow.cpp:478-604), single box:

@@ -18,13 +18,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "warpx_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libpic_lwfa_host.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SRCS = ["lwfa.cu", "runtime.cu"]
+SRCS = ["lwfa.cu", "charge.cu", "runtime.cu"]
 PROBES = [os.path.join(HERE, "shape_probe.cu")]
 _LIB = None
 
 
 def build():
-    deps = [os.path.join(CSRC, f) for f in SRCS + ["lwfa_body.cuh", "pic_common.cuh"]] + \
+    deps = [os.path.join(CSRC, f) for f in SRCS + ["lwfa_body.cuh", "harness_launch.cuh", "pic_common.cuh"]] + \
            [os.path.join(ROOT, "include", "pic_b200.h")] + PROBES
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT

@@ -335,6 +335,11 @@ def test_laser_acceleration_golden_checksums(orc, cuda, golden):
     for key, arr in vals.items():
         assert abs(float(np.sum(np.abs(arr))) - g["electrons"][key]) <= 1e-9 * abs(g["electrons"][key]), key
     assert len(P["x"]) == 22 * 22 * (45 + 98)
+    # the rho diagnostic: electrons + antenna, PEC image charge, filter, SumBoundary
+    d, a = sim.rho_numpy()
+    hf = orc.HostFab(sim.box_lo, sim.box_hi, d.ng, (1, 1, 1), data=a)
+    cs = L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
+    assert abs(cs - g["lev=0"]["rho"]) <= 1e-9 * g["lev=0"]["rho"]
 
 
 def test_absorbing_walls_remove_particles_like_the_oracle(orc, cuda):
@@ -516,3 +521,33 @@ def test_particle_boundaries_golden_checksums(orc, cuda, golden):
     cuda.cuda.synchronize()
     check_particle_boundaries(golden, lambda isp: sim.species_numpy(isp))
     assert sim.species[1].np == 1
+
+
+@pytest.mark.parametrize("nox", [1, 3, 4])
+def test_charge_deposition_matches_oracle(orc, dev, nox):
+    rng = np.random.default_rng(90 + nox)
+    n, ng = (20, 16, 24), (5, 5, 5)
+    prob_lo, prob_hi = (-1.0, -2.0, 0.5), (1.5, 2.0, 3.5)
+    dx = [(prob_hi[d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    npart = 200000
+    arr = {k: rng.uniform(prob_lo[d], prob_hi[d], npart) for d, k in enumerate(("x", "y", "z"))}
+    arr["w"] = rng.uniform(0.5, 2.0, npart)
+    for k in ("ux", "uy", "uz"):
+        arr[k] = np.zeros(npart)
+    P = orc.HostParticles(**arr)
+    lo = [-ng[d] for d in range(3)]
+    xyzmin = [prob_lo[d] + dx[d] * lo[d] for d in range(3)]
+    geom = abi.make_geom(n, prob_lo, prob_hi, periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"))
+    A = orc.HostFab(*box(n), ng, (1, 1, 1))
+    arr_d, tens = dev.fabs([A])
+    soa, buf = dev.soa(P)
+    dev.ok(dev.L.pic_deposit_charge(C.byref(soa), 0, npart, C.byref(arr_d[0]), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                    abi.int3(lo), -1.6e-19, nox, dev.stream))
+    dev.ok(dev.L.pic_apply_pec_rho(C.byref(arr_d[0]), C.byref(geom), C.byref(bnd), dev.stream))
+    dev.sync()
+    assert orc.lib().orc_deposit_charge(C.byref(P.soa), C.byref(A.desc), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                        -1.6e-19, nox) == 0
+    orc.lib().orc_apply_pec_rho(C.byref(A.desc), C.byref(geom), C.byref(bnd))
+    assert rel_linf(tens[0].cpu().numpy(), A.a) <= 1e-12

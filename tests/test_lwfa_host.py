@@ -388,3 +388,38 @@ def test_add_plasma_on_slabs_equals_single_box(orc, hh, ppc):
             else:
                 assert np.array_equal(cat, a1[k][:n1]), k
         assert np.array_equal(np.concatenate(ids), id1[:n1])
+
+
+@pytest.mark.parametrize("nox", [1, 2, 3, 4])
+def test_charge_deposition_and_pec_rho_match_oracle(orc, hh, nox):
+    """doChargeDepositionShapeN on a nodal rho and ApplyReflectiveBoundarytoRhofield (the `rho`
+    diagnostic): body + argument builder against the oracle, bit for bit on the host."""
+    rng = np.random.default_rng(80 + nox)
+    n, ng = (10, 8, 12), (5, 5, 5)
+    prob_lo, prob_hi = (-1.0, -2.0, 0.5), (1.5, 2.0, 3.5)
+    dx = [(prob_hi[d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    npart = 3000
+    arr = {k: rng.uniform(prob_lo[d], prob_hi[d], npart) for d, k in enumerate(("x", "y", "z"))}
+    arr["w"] = rng.uniform(0.5, 2.0, npart)
+    for k in ("ux", "uy", "uz"):
+        arr[k] = np.zeros(npart)
+    P = orc.HostParticles(**arr)
+    lo = [-ng[d] for d in range(3)]
+    xyzmin = [prob_lo[d] + dx[d] * lo[d] for d in range(3)]
+    geom = abi.make_geom(n, prob_lo, prob_hi, periodic=(1, 1, 0))
+    bnd = abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec"))
+    A = orc.HostFab((0, 0, 0), tuple(v - 1 for v in n), ng, (1, 1, 1))
+    B = orc.HostFab((0, 0, 0), tuple(v - 1 for v in n), ng, (1, 1, 1))
+    assert orc.lib().orc_deposit_charge(C.byref(P.soa), C.byref(A.desc), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                        -1.6e-19, nox) == 0
+    _check(hh, hh.pic_deposit_charge(C.byref(P.soa), 0, npart, C.byref(B.desc), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                     abi.int3(lo), -1.6e-19, nox, None))
+    assert np.array_equal(A.a, B.a) and np.abs(A.a).max() > 0
+    # total charge: sum rho dV = q sum w
+    assert A.a.sum() * dx[0] * dx[1] * dx[2] == pytest.approx(-1.6e-19 * arr["w"].sum(), rel=1e-12)
+    orc.lib().orc_apply_pec_rho(C.byref(A.desc), C.byref(geom), C.byref(bnd))
+    _check(hh, hh.pic_apply_pec_rho(C.byref(B.desc), C.byref(geom), C.byref(bnd), None))
+    assert np.array_equal(A.a, B.a)
+    kz, vy, vx = ng[2], slice(ng[1], -ng[1]), slice(ng[0], -ng[0])
+    assert np.all(A.a[kz, vy, vx] == 0.0) and np.all(A.a[-kz - 1, vy, vx] == 0.0)   # the wall planes (valid x, y)

@@ -33,6 +33,10 @@ def test_langmuir_golden_checksums(orc, golden):
                 "particle_weight": P["w"]}
         for key, gv in g[sname].items():
             assert _close(float(np.sum(np.abs(vals[key]))), gv), (sname, key)
+    # the diagnostics of that file that lie outside the path: rho (charge deposition + SumBoundary) and
+    # part_per_cell (the particle count)
+    assert _close(sim.rho_checksum(), g["lev=0"]["rho"])
+    assert float(sum(len(sim.particles(i)["x"]) for i in range(2))) == g["lev=0"]["part_per_cell"]
     # analytic Langmuir field, 5 % (Examples/Tests/langmuir/analysis_3d.py:77-91,124-164)
     an = wl["analytic"]
     t = 40 * sim.dt
@@ -278,7 +282,8 @@ def test_laser_acceleration_golden_checksums(orc, golden):
     regression checksums (100 steps, 32x32x256, order 3, filter, PEC z, moving window, Gaussian antenna,
     continuous injection; no RNG) at WarpX's tolerance.  This is the reference-golden pin of the
     order-3 gather / Esirkepov deposition, the bilinear filter and every config-4 enabler built so far.
-    (`rho` and `part_per_cell` of that file are diagnostics outside the path and are not compared.)"""
+    Every key of the file is compared, the `rho` diagnostic included (charge deposition of the electrons
+    and of the antenna, PEC image charge, filter, SumBoundary)."""
     wl = workloads.laser_acceleration_3d()
     sim = make_lwfa_oracle(orc, wl, kind="reference" if orc.have_ref() else "restated")
     assert sim.guards() == {"ng_EB": [4, 4, 4], "ng_J": [5, 5, 5], "ng_FG": [2, 2, 2], "ng_FS": [1, 1, 1]}
@@ -296,6 +301,8 @@ def test_laser_acceleration_golden_checksums(orc, golden):
             "particle_momentum_z": P["uz"] * workloads.M_E, "particle_weight": P["w"]}
     for key, arr in vals.items():
         assert _close(float(np.sum(np.abs(arr))), g["electrons"][key]), key
+    assert _close(sim.rho_checksum(), g["lev=0"]["rho"])
+    assert g["electrons"]["particle_initialenergy"] == 0.0          # ux^2 + uy^2 + uz^2 at injection: at rest
     lo, hi = wl["region_of_interest"]
     z0 = sim.z_at_injection(0)
     assert float(np.sum((z0 > lo) & (z0 < hi))) == g["electrons"]["particle_regionofinterest"]

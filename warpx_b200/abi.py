@@ -117,6 +117,8 @@ def LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp):
         "pic_laser_antenna_push": (C.c_int, [lp, dp, soap, C.c_double, C.c_double, vp]),
         "pic_add_plasma": (C.c_long, [jp, gp, dp, ip, ip, dp, dp, soap, C.c_long, C.c_uint64, vp]),
         "pic_particles_owned_weights": (C.c_int, [soap, dp, dp, vp, vp]),
+        "pic_deposit_charge": (C.c_int, [soap, C.c_long, C.c_long, fabp, dp, dp, ip, C.c_double, C.c_int, vp]),
+        "pic_apply_pec_rho": (C.c_int, [fabp, gp, bp, vp]),
         "pic_particles_boundary_workspace_ints": (C.c_long, [C.c_int]),
         "pic_particles_boundary_mark": (C.c_int, [soap, gp, bp, vp, C.c_int, vp]),
         "pic_particles_boundary_compact": (C.c_int, [soap, vp, C.c_int, C.c_int, vp]),

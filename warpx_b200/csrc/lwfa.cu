@@ -18,6 +18,7 @@
 // bodies and the host-side argument builders with the oracle where no GPU exists; the product library
 // is never built that way.
 #include "lwfa_body.cuh"
+#include "harness_launch.cuh"
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -25,22 +26,6 @@
 #include <vector>
 
 namespace pic {
-
-#ifdef PIC_HOST_HARNESS
-#define PIC_LAUNCH(kernel, body, args, total, stream) \
-    do { for (long t_ = 0; t_ < (total); ++t_) body(t_, args); } while (0)
-static void dev_copy(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); }
-static void dev_zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); }
-static bool launched_ok(const char*) { return true; }
-#else
-#define PIC_LAUNCH(kernel, body, args, total, stream) \
-    do { if ((total) > 0) { kernel<<<(unsigned)(((total) + 255) / 256), 256, 0, (cudaStream_t)(stream)>>>(args); count_launch(); } } while (0)
-static void dev_copy(void* dst, const void* src, size_t bytes, void* s) {
-    cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-}
-static void dev_zero(void* dst, size_t bytes, void* s) { cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)s); }
-static bool launched_ok(const char* what) { return check_launch(what); }
-#endif
 
 __global__ void pec_field_kernel(PecFieldArgs a) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,13 +48,6 @@ __global__ void inject_kernel(InjectArgs a) {
     if (t < a.total) inject_body(t, a);
 }
 
-PIC_HD int slot_add(int* c) {
-#ifdef __CUDA_ARCH__
-    return atomicAdd(c, 1);
-#else
-    return (*c)++;
-#endif
-}
 PIC_HD void boundary_mark_body(long ip, const BoundaryArgs& a) {
     if (boundary_body(ip, a)) { const int n = slot_add(a.count); if (n < a.cap) a.list[n] = (int)ip; }
 }

@@ -656,6 +656,58 @@ class Simulation:
         v = out.cpu().numpy()
         return [(float(v[i, 0]), float(v[i, 1])) for i in range(len(self.species))]
 
+    def rho_numpy(self):
+        """The `rho` diagnostic of a plotfile (Diagnostics/ComputeDiagFunctors/RhoFunctor.cpp:35-81): every
+        container (species, then laser antennas) deposits its charge on a nodal array with ng_depos_rho guard
+        cells and applies the PEC / reflecting image charge, the containers are added, then
+        WarpX::ApplyFilterandSumBoundaryRho (Parallelization/WarpXComm.cpp:1552-1568).  Returns
+        (descriptor, numpy array [k, j, i]).  One rank."""
+        if self.world > 1:
+            raise NotImplementedError("rho diagnostic: one rank")
+        t = self.torch
+        base = max(self.nox, 2) if self.moving_window is not None else self.nox
+        ng = max(base + 1 + int(math.ceil(C_LIGHT * self.dt / self.dx[d])) for d in range(3))   # GuardCellManager.cpp:130-165
+
+        def make(ngv):
+            d = abi.make_fab(None, self.box_lo, self.box_hi, ngv, (1, 1, 1))
+            a = t.zeros(d.shape, dtype=t.float64, device=self.device)
+            d.p = a.data_ptr()
+            return d, a
+
+        rho_d, rho = make((ng,) * 3)
+        one_d, one = make((ng,) * 3)
+        xyzmin, lo = self.lower_corner((ng,) * 3)
+        containers = [(sp.soa(), sp.q) for sp in self.species]
+        for il, la in enumerate(self.lasers):
+            soa = abi.pic_soa()
+            for k, name in enumerate(Species.NAMES):
+                setattr(soa, name, la["buf"][k].data_ptr())
+            soa.idcpu, soa.np = la["ids"].data_ptr(), int(self.L.pic_engine_laser_np(self.native, il))
+            containers.append((soa, 1.0))                                  # LaserParticleContainer: charge = 1
+        for soa, q in containers:
+            one.zero_()
+            check(self.L.pic_deposit_charge(C.byref(soa), 0, soa.np, C.byref(one_d), abi.dbl3(self.dinv), xyzmin, lo, q,
+                                            self.nox, self.stream))
+            if self.nonperiodic:
+                check(self.L.pic_apply_pec_rho(C.byref(one_d), C.byref(self.geom), C.byref(self.boundaries), self.stream))
+            rho += one
+        work_d, work, ngw = rho_d, rho, [ng] * 3
+        if self.use_filter:
+            ngw = [ng + self.filter_npass[d] for d in range(3)]
+            work_d, work = make(ngw)
+            check(self.L.pic_apply_filter(C.byref(rho_d), C.byref(work_d), abi.int3(self.filter_npass), self.stream))
+        allper = abi.make_geom(self.n_cell, self.prob_lo, self.prob_hi)      # the refresh after the sum covers every guard
+        for dim in range(3):
+            if self.geom.periodic[dim]:
+                check(self.L.pic_sum_boundary_local(C.byref(work_d), dim, ngw[dim], C.byref(self.geom), self.stream))
+        for dim in range(3):
+            if self.geom.periodic[dim]:
+                check(self.L.pic_fill_boundary_local(C.byref(work_d), dim, ngw[dim], C.byref(allper), self.stream))
+        if self.use_filter:
+            n = self.filter_npass
+            rho.copy_(work[n[2]:work.shape[0] - n[2], n[1]:work.shape[1] - n[1], n[0]:work.shape[2] - n[0]])
+        return rho_d, rho.cpu().numpy()
+
     def total_particles(self):
         n = sum(sp.np for sp in self.species)
         if self.dist is not None and self.world > 1:
