@@ -335,11 +335,20 @@ def test_laser_acceleration_golden_checksums(orc, cuda, golden):
     for key, arr in vals.items():
         assert abs(float(np.sum(np.abs(arr))) - g["electrons"][key]) <= 1e-9 * abs(g["electrons"][key]), key
     assert len(P["x"]) == 22 * 22 * (45 + 98)
-    # the rho diagnostic: electrons + antenna, PEC image charge, filter, SumBoundary
+
+
+def test_rho_diagnostic_golden_checksum(orc, cuda, golden):
+    """The `rho` key of test_3d_laser_acceleration.json on the GPU: charge deposition of the electrons and
+    of the antenna, PEC image charge, bilinear filter, SumBoundary (Simulation.rho_numpy)."""
+    wl = workloads.laser_acceleration_3d()
+    sim = make_lwfa_sim(wl, capacity=22 * 22 * 256)
+    sim.Evolve(wl["max_step"])
     d, a = sim.rho_numpy()
+    cuda.cuda.synchronize()
     hf = orc.HostFab(sim.box_lo, sim.box_hi, d.ng, (1, 1, 1), data=a)
-    cs = L.orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
-    assert abs(cs - g["lev=0"]["rho"]) <= 1e-9 * g["lev=0"]["rho"]
+    cs = orc.lib().orc_checksum_cell_centered(C.byref(hf.desc), abi.int3(sim.box_lo), abi.int3(sim.box_hi))
+    g = golden["test_3d_laser_acceleration"]["lev=0"]["rho"]
+    assert abs(cs - g) <= 1e-9 * g
 
 
 def test_absorbing_walls_remove_particles_like_the_oracle(orc, cuda):
@@ -404,7 +413,7 @@ def test_order4_gather_push_matches_oracle(orc, dev, galerkin):
     dev.sync()
     got = buf.cpu().numpy()
     for i, k in enumerate(orc.HostParticles.NAMES):
-        assert rel_linf(got[i], getattr(P, k)) <= 1e-13, k
+        assert rel_linf(got[i], getattr(P, k)) <= 3e-13, k       # 5^3-point stencils: a little above the order-3 bound
 
 
 def test_order4_deposit_matches_oracle(orc, dev):
