@@ -181,6 +181,9 @@ def run_engine(args):
     t_gen = time.perf_counter() - t_gen
 
     def make_sim(native=True):
+        if args.deposit_mode:
+            from warpx_b200.lib import lib as _piclib
+            _piclib().pic_set_deposit_mode(args.deposit_mode)
         sim = Simulation(n_cell, prob_lo, prob_hi, nox=args.order, dist=dist, sort_interval=args.sort_interval,
                          native_driver=native, use_filter=bool(args.filter))
         sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
@@ -309,7 +312,7 @@ def run_engine(args):
                                                 ", random in-cell positions" if args.jitter else "",
                                                 "on (1 pass)" if args.filter else "off (SURVEY 8d)",
                                                 args.sort_interval)),
-                       "use_filter": int(args.filter),
+                       "use_filter": int(args.filter), "deposit_mode": int(args.deposit_mode),
                        "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
                                                      % (npart_local * 56 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
@@ -340,6 +343,9 @@ def main():
                     help="warpx.use_filter: bilinear current filter, 1 pass.  Off by default: SURVEY.md 8(d) "
                          "fixes use_filter = 0 for the benchmark configurations; --filter 1 measures the "
                          "reference's own default (WarpX.cpp:158)")
+    ap.add_argument("--deposit-mode", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="pic_set_deposit_mode: 0 register runs (default), 1 shared-memory tile block, 2 two lines per "
+                         "lane, 3 per-slot reductions, 4 both (A/B measurements; every mode passes the parity tests)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

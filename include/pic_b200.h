@@ -194,10 +194,16 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
 
 /* Which kernel serves pic_deposit_esirkepov when bins are given (tuning / A-B measurements):
  * PIC_DEPOSIT_RUNS (default): warp-segmented register reduction + fp64 L2 reductions;
- * PIC_DEPOSIT_TILE: the same reduction staged through a shared-memory J block per supercell.
+ * PIC_DEPOSIT_TILE: the same reduction staged through a shared-memory J block per supercell;
+ * PIC_DEPOSIT_RUNS2: PIC_DEPOSIT_RUNS with two stencil lines per lane (fewer shared-memory reads per
+ *   particle; orders 1 and 3 -- order 2 falls back to PIC_DEPOSIT_RUNS);
+ * PIC_DEPOSIT_RUNS_SLOTRED / PIC_DEPOSIT_RUNS2_SLOTRED: the particle slots of a warp pass send their own
+ *   partial sums to L2 instead of being summed by shuffles first.
+ * The last three are experiments until measured; all pass the same parity tests.
  * Analogous to WarpX's runtime switch warpx.do_shared_mem_current_deposition
  * (Source/WarpX.cpp:126, Docs/source/usage/parameters.rst:2608-2623). */
-enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1 };
+enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1, PIC_DEPOSIT_RUNS2 = 2, PIC_DEPOSIT_RUNS_SLOTRED = 3,
+       PIC_DEPOSIT_RUNS2_SLOTRED = 4 };
 void pic_set_deposit_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------

@@ -55,3 +55,41 @@ def lib():
     L.pic_set_error_mode(abi.PIC_ERR_RETURN)
     _LIB = L
     return L
+
+
+# --------------------------------------------------------------------------------------------
+# SIMT emulation of the warp-level kernels (simt_host.h): the kernel SOURCE of csrc/deposit_runs.cu
+# compiled by g++ with every CUDA thread as a cooperative fiber.
+# --------------------------------------------------------------------------------------------
+SIMT_OUT = os.path.join(HERE, "_build", "libpic_simt.so")
+_SIMT = None
+
+
+def build_simt():
+    deps = [os.path.join(HERE, "simt_host.h"), os.path.join(HERE, "simt_deposit.cpp"),
+            os.path.join(ROOT, "include", "pic_b200.h")] + \
+           [os.path.join(CSRC, f) for f in ("deposit_runs.cu", "deposit_common.cuh", "pic_common.cuh", "runtime.cu")]
+    if os.path.exists(SIMT_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SIMT_OUT) for d in deps):
+        return SIMT_OUT
+    os.makedirs(os.path.dirname(SIMT_OUT), exist_ok=True)
+    cuda = os.path.dirname(os.path.dirname(NVCC))
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DPIC_SIMT_HOST", "-include",
+           os.path.join(HERE, "simt_host.h"), "-x", "c++", "-I", os.path.join(cuda, "include"), "-I", CSRC,
+           "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas",
+           os.path.join(HERE, "simt_deposit.cpp"), os.path.join(CSRC, "runtime.cu"), "-o", SIMT_OUT,
+           "-L", os.path.join(cuda, "lib64"), "-lcudart"]
+    subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return SIMT_OUT
+
+
+def simt():
+    global _SIMT
+    if _SIMT is not None:
+        return _SIMT
+    L = C.CDLL(build_simt())
+    fabp, soap = C.POINTER(abi.pic_fab), C.POINTER(abi.pic_soa)
+    L.simt_deposit_runs.restype = C.c_int
+    L.simt_deposit_runs.argtypes = [soap, C.c_long, C.c_long, fabp, abi.c_double_p, abi.c_double_p, abi.c_int_p,
+                                    C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    _SIMT = L
+    return L

@@ -14,7 +14,7 @@ import pytest
 
 from helpers import rel_linf
 from helpers import lower_corner, random_fields
-from test_gpu_parity import Dev, _particles, _run_both, _match_particles, box  # noqa: F401
+from test_gpu_parity import Dev, _particles, _run_both, _match_particles, _sorted_device_species, box  # noqa: F401
 from test_oracle import check_particle_boundaries, check_pec_particle, make_lwfa_oracle
 from warpx_b200 import abi, workloads
 
@@ -560,3 +560,42 @@ def test_charge_deposition_matches_oracle(orc, dev, nox):
                                         -1.6e-19, nox) == 0
     orc.lib().orc_apply_pec_rho(C.byref(A.desc), C.byref(geom), C.byref(bnd))
     assert rel_linf(tens[0].cpu().numpy(), A.a) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# Experimental variants of the register-run deposition (pic_set_deposit_mode 2, 3, 4):
+# same parity bar as the default kernel.  (Checked under the SIMT emulator on the host: test_simt_host.py.)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [2, 3, 4])
+@pytest.mark.parametrize("nox,kind", [(3, "sorted"), (3, "drifted"), (1, "sorted"), (2, "sorted"), (3, "relativistic")])
+def test_deposit_variants_match_oracle(orc, dev, mode, nox, kind):
+    L = orc.lib()
+    n, lx = (20, 16, 12), 1e-5
+    box_lo, box_hi = box(n)
+    u_th = {"relativistic": 3.0, "sorted": 0.02}.get(kind, 0.5)
+    wl, sp = _particles(orc, n, (2, 2, 2), u_th, lx)
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    dt = 0.95 / (np.sqrt(sum(1.0 / v ** 2 for v in dx)) * workloads.C)
+    ngJ = tuple(nox + 1 + (1 if kind == "drifted" else 0) for _ in range(3))
+    xyzmin, lo = lower_corner(prob_lo, dx, box_lo, ngJ)
+    J = [orc.HostFab(box_lo, box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    P = orc.HostParticles(**{k: sp[k] for k in orc.HostParticles.NAMES})
+    arr, tens = dev.fabs(J)
+    Pd, buf, bins_s, _, _ = _sorted_device_species(dev, P, n, prob_lo, wl["prob_hi"])
+    if kind == "drifted":
+        buf[0:3] += dev.t.tensor([[0.8 * dx[0]], [-0.9 * dx[1]], [0.6 * dx[2]]], device="cuda")
+    host = buf.cpu().numpy()
+    P = orc.HostParticles(**{k: host[i] for i, k in enumerate(orc.HostParticles.NAMES)})
+    dev.L.pic_set_deposit_mode(mode)
+    try:
+        dev.ok(dev.L.pic_deposit_esirkepov(C.byref(Pd), 0, P.np, (abi.pic_fab * 3)(*arr), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                           abi.int3(lo), sp["q"], dt, -0.5 * dt, nox, C.byref(bins_s), dev.stream))
+        dev.sync()
+    finally:
+        dev.L.pic_set_deposit_mode(0)
+    L.orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                            abi.int3(lo), sp["q"], dt, -0.5 * dt, nox)
+    for c in range(3):
+        assert rel_linf(tens[c].cpu().numpy(), J[c].a) <= 1e-12, "j" + "xyz"[c]

@@ -66,12 +66,16 @@ int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[
                         const DepositGeom& dg, int nox, cudaStream_t s);
 
 static int g_deposit_mode = PIC_DEPOSIT_RUNS;
+extern int g_runs_variant;      // deposit_runs.cu
 
 }  // namespace pic
 
 using namespace pic;
 
-extern "C" void pic_set_deposit_mode(int mode) { g_deposit_mode = mode; }
+extern "C" void pic_set_deposit_mode(int mode) {
+    g_deposit_mode = mode;
+    g_runs_variant = (mode == PIC_DEPOSIT_RUNS2) ? 1 : (mode == PIC_DEPOSIT_RUNS_SLOTRED) ? 2 : (mode == PIC_DEPOSIT_RUNS2_SLOTRED) ? 3 : 0;
+}
 
 extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, const pic_fab J[3],
                                      const double dinv[3], const double xyzmin[3], const int lo[3],

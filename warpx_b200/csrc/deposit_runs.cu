@@ -26,8 +26,15 @@
 // may be a single particle); cell-sorted order is FAST.
 #include "pic_common.cuh"
 #include "deposit_common.cuh"
+#ifdef PIC_SIMT_HOST
+#include <vector>
+#endif
 
 namespace pic {
+
+// bit 0: two v-lines per lane where N+1 is even; bit 1: per-slot reductions instead of the shuffle fold
+// (pic_set_deposit_mode: PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_RUNS2 = 1, PIC_DEPOSIT_RUNS_SLOTRED = 2, both = 3)
+int g_runs_variant = 0;
 
 constexpr int DR_CH = 32;          // particles per chunk
 constexpr int DR_CHP = DR_CH + 1;  // record pitch (odd: conflict-free column access)
@@ -89,9 +96,14 @@ __device__ __forceinline__ int pack_key(int gx, int gy, int gz, const KeyBase& k
 // ================================================================================================
 // quiet particles
 // ================================================================================================
-template <int N> struct QuietCfg {
+// VL = lines along role Z that one lane owns ("v" values per lane).  VL = 1: one lane per line,
+// QS*QS lanes per particle.  VL = 2 (experiment, pic_set_deposit_mode(PIC_DEPOSIT_RUNS2)): a lane owns
+// the lines of two consecutive v, so the pairs (Sx, Sy) and the prefix sums are fetched once for
+// twice the lines -- the kernel is bound by the shared-memory return path.
+template <int N, int VL = 1> struct QuietCfg {
     static constexpr int QS = N + 1;          // slots 1..N+1 of the (N+3)-slot window
-    static constexpr int QL = QS * QS;        // lines per particle
+    static_assert(QS % VL == 0, "VL must divide N+1");
+    static constexpr int QL = QS * (QS / VL); // lanes per particle
     static constexpr int NG = 32 / QL;        // particles per warp pass
     static constexpr int QP = N;              // live prefix entries (slots 1..N)
     // The record is an array of double2 (one LDS.128 fetches a pair the lane always needs together):
@@ -112,7 +124,9 @@ template <int N> struct QuietCfg {
 struct J3 { FabView v[3]; };
 __device__ __forceinline__ long fab_stride(const FabView& F, int d) { return d == 0 ? 1 : (d == 1 ? F.sj : F.sk); }
 
-template <int N, int NW, int MINB, int R0, int R1, int R2>
+// SLOTRED = true: the NG particle slots of a pass are not summed by shuffles before a plane is retired --
+// every slot sends its own partial sums to L2 (NG times the reductions, no SHFL; experiment).
+template <int N, int NW, int MINB, int R0, int R1, int R2, int VL = 1, bool SLOTRED = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom dg, KeyBase kbp,
                      int* __restrict__ list, int* __restrict__ list_count) {
@@ -121,9 +135,9 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
     const long stX = fab_stride(Jx, R0), stY = fab_stride(Jy, R1), stZ = fab_stride(Jz, R2);
     const int kbb[3] = {kbp.b0, kbp.b1, kbp.b2};
     const KeyBase kb = {kbb[R0], kbb[R1], kbb[R2]};
-    using T = QuietCfg<N>;
+    using T = QuietCfg<N, VL>;
     constexpr int QS = T::QS, QL = T::QL, NG = T::NG, QP = T::QP, NF = T::NF, CHP = T::CHP;
-    extern __shared__ double2 smem2[];
+    PIC_DYNAMIC_SMEM(double2, smem2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2* rec = smem2 + (size_t)warp * NF * CHP;
 
@@ -133,16 +147,18 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
     const long c_end = min(nchunks, c_begin + chunks_per_warp);
     if (c_begin >= c_end) return;
 
-    // lane (g, u, v): particle slot g of the pass;
+    // lane (g, u, h): particle slot g of the pass; the lane owns the VL values v = h*VL + m, m < VL:
     //   Jx line (j, k) = (1+u, 1+v);  Jy line (i, k) = (1+ur, 1+v);  Jz line (i, j) = (1+ur, 1+v),
     //   ur = (u - (ax+1)) mod QS  (ring mapping: a lane keeps the Jy/Jz lines of one absolute x)
-    const int g = lane / QL, ql = lane % QL, qu = ql % QS, qv = ql / QS;
+    const int g = lane / QL, ql = lane % QL, qu = ql % QS, qv0 = (ql / QS) * VL;
     const bool active_q = g < NG;
-    double acc[3][QP];
+    double acc[VL][3][QP];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int m = 0; m < VL; ++m)
 #pragma unroll
-        for (int i = 0; i < QP; ++i) acc[c][i] = 0.0;
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < QP; ++i) acc[m][c][i] = 0.0;
     int cur = -1;
 
     auto ring = [&](int ax) -> int {
@@ -150,19 +166,29 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
         return r < 0 ? r + QS : r;
     };
     auto fold = [&](double v) -> double {          // sum over the particle slots of the pass
+        if constexpr (SLOTRED) return v;
         double r = v;
+        if constexpr ((NG & (NG - 1)) == 0) {       // power of two: butterfly, log2(NG) steps; slot 0 ends with the sum
 #pragma unroll
-        for (int gg = 1; gg < NG; ++gg) {
-            const double o = __shfl_down_sync(FULL, v, gg * QL);
-            if (lane + gg * QL < NG * QL) r += o;
+            for (int off = NG / 2; off >= 1; off >>= 1) r += __shfl_down_sync(FULL, r, off * QL);
+        } else {
+#pragma unroll
+            for (int gg = 1; gg < NG; ++gg) {
+                const double o = __shfl_down_sync(FULL, v, gg * QL);
+                if (lane + gg * QL < NG * QL) r += o;
+            }
         }
         return r;
     };
+    // which lanes send retired sums to J: slot 0 after the fold, or every slot with its own partial sum
+    const bool sender = SLOTRED ? active_q : (lane < QL);
     // Running state of the current anchor: this lane's ring index and the J addresses of its lines
     //   px -> Jx(gx+1, gy+1+u, gz+1+v) (entries along x: +i), py -> Jy(gx+1+ur, gy+1, gz+1+v) (+i*sj),
     //   pz -> Jz(gx+1+ur, gy+1+v, gz+1) (+i*sk)
     int ur = 0;
-    double *px = nullptr, *py = nullptr, *pz = nullptr;
+    double *px[VL], *py[VL], *pz[VL];
+#pragma unroll
+    for (int m = 0; m < VL; ++m) { px[m] = nullptr; py[m] = nullptr; pz[m] = nullptr; }
     auto at = [&](const FabView& F, int ix, int iy, int iz) -> double* {   // role indices -> element
         int q[3];
         q[R0] = ix; q[R1] = iy; q[R2] = iz;
@@ -171,35 +197,45 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
     auto set_anchor = [&](int k) {
         const int ax = (k & 1023), gx = ax + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
         ur = ring(ax);
-        px = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
-        py = at(Jy, gx + 1 + ur, gy + 1, gz + 1 + qv);
-        pz = at(Jz, gx + 1 + ur, gy + 1 + qv, gz + 1);
+#pragma unroll
+        for (int m = 0; m < VL; ++m) {
+            const int qv = qv0 + m;
+            px[m] = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
+            py[m] = at(Jy, gx + 1 + ur, gy + 1, gz + 1 + qv);
+            pz[m] = at(Jz, gx + 1 + ur, gy + 1 + qv, gz + 1);
+        }
     };
     // the anchor advances one cell along x: only the plane x = gx+1 leaves the window
     auto slide = [&]() {
         const bool leaving = (ur == 0);
-        const double vx = fold(acc[0][0]);
-        if (lane < QL) atomicAdd(px, vx);
 #pragma unroll
-        for (int i = 0; i + 1 < QP; ++i) acc[0][i] = acc[0][i + 1];
-        acc[0][QP - 1] = 0.0;
+        for (int m = 0; m < VL; ++m) {
+            const double vx = fold(acc[m][0][0]);
+            if (sender) atomicAdd(px[m], vx);
 #pragma unroll
-        for (int i = 0; i < QP; ++i) {
-            const double vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-            if (lane < QL && leaving) { atomicAdd(py + i * stY, vy); atomicAdd(pz + i * stZ, vz); }
-            if (leaving) { acc[1][i] = 0.0; acc[2][i] = 0.0; }
+            for (int i = 0; i + 1 < QP; ++i) acc[m][0][i] = acc[m][0][i + 1];
+            acc[m][0][QP - 1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < QP; ++i) {
+                const double vy = fold(acc[m][1][i]), vz = fold(acc[m][2][i]);
+                if (sender && leaving) { atomicAdd(py[m] + i * stY, vy); atomicAdd(pz[m] + i * stZ, vz); }
+                if (leaving) { acc[m][1][i] = 0.0; acc[m][2][i] = 0.0; }
+            }
+            px[m] += stX;                               // next X plane
+            if (leaving) { py[m] += QS * fab_stride(Jy, R0); pz[m] += QS * fab_stride(Jz, R0); }   // now owns X = gx + 1 + QS
         }
-        px += stX;                                  // next X plane
-        if (leaving) { py += QS * fab_stride(Jy, R0); pz += QS * fab_stride(Jz, R0); ur = QS - 1; }   // now owns X = gx + 1 + QS
-        else ur -= 1;                               // same absolute x, one slot lower
+        if (leaving) ur = QS - 1;
+        else ur -= 1;                                   // same absolute x, one slot lower
     };
     auto flush_all = [&]() {                        // the anchor jumps: retire the whole window
 #pragma unroll
-        for (int i = 0; i < QP; ++i) {
-            const double vx = fold(acc[0][i]), vy = fold(acc[1][i]), vz = fold(acc[2][i]);
-            if (lane < QL) { atomicAdd(px + i * stX, vx); atomicAdd(py + i * stY, vy); atomicAdd(pz + i * stZ, vz); }
-            acc[0][i] = 0.0; acc[1][i] = 0.0; acc[2][i] = 0.0;
-        }
+        for (int m = 0; m < VL; ++m)
+#pragma unroll
+            for (int i = 0; i < QP; ++i) {
+                const double vx = fold(acc[m][0][i]), vy = fold(acc[m][1][i]), vz = fold(acc[m][2][i]);
+                if (sender) { atomicAdd(px[m] + i * stX, vx); atomicAdd(py[m] + i * stY, vy); atomicAdd(pz[m] + i * stZ, vz); }
+                acc[m][0][i] = 0.0; acc[m][1][i] = 0.0; acc[m][2][i] = 0.0;
+            }
     };
 
     // one particle (record column pq) of anchor k, deposited without the register window
@@ -207,28 +243,32 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
         if (lane >= QL) return;
         const int ax = (k & 1023), gx = ax + kb.b0, gy = ((k >> 10) & 1023) + kb.b1, gz = (k >> 20) + kb.b2;
         const int us = ring(ax);
-        double* qx = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
-        double* qy = at(Jy, gx + 1 + us, gy + 1, gz + 1 + qv);
-        double* qz = at(Jz, gx + 1 + us, gy + 1 + qv, gz + 1);
         const double2 sx = rec[(T::F_SX + us) * CHP + pq];
         const double2 sy = rec[(T::F_SY + qu) * CHP + pq];
-        const double2 aby = rec[(T::F_ABY + qv) * CHP + pq];
-        const double2 abz = rec[(T::F_ABZ + qv) * CHP + pq];
-        const double wx = sy.x * abz.x + sy.y * abz.y;
-        const double wy = sx.x * abz.x + sx.y * abz.y;
-        const double wz = sx.x * aby.x + sx.y * aby.y;
 #pragma unroll
-        for (int m = 0; m < T::NCDS; ++m) {
-            const double2 c2 = rec[(T::F_CDS + m) * CHP + pq];
+        for (int mv = 0; mv < VL; ++mv) {
+            const int qv = qv0 + mv;
+            double* qx = at(Jx, gx + 1, gy + 1 + qu, gz + 1 + qv);
+            double* qy = at(Jy, gx + 1 + us, gy + 1, gz + 1 + qv);
+            double* qz = at(Jz, gx + 1 + us, gy + 1 + qv, gz + 1);
+            const double2 aby = rec[(T::F_ABY + qv) * CHP + pq];
+            const double2 abz = rec[(T::F_ABZ + qv) * CHP + pq];
+            const double wx = sy.x * abz.x + sy.y * abz.y;
+            const double wy = sx.x * abz.x + sx.y * abz.y;
+            const double wz = sx.x * aby.x + sx.y * aby.y;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = 2 * m + h;                 // entry e = component (e / QP), prefix index (e % QP)
-                if (e < 3 * QP) {
-                    const double cv = h ? c2.y : c2.x;
-                    const int c = e / QP, i = e % QP;
-                    if (c == 0) atomicAdd(qx + i * stX, cv * wx);
-                    else if (c == 1) atomicAdd(qy + i * stY, cv * wy);
-                    else atomicAdd(qz + i * stZ, cv * wz);
+            for (int m = 0; m < T::NCDS; ++m) {
+                const double2 c2 = rec[(T::F_CDS + m) * CHP + pq];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = 2 * m + h;                 // entry e = component (e / QP), prefix index (e % QP)
+                    if (e < 3 * QP) {
+                        const double cv = h ? c2.y : c2.x;
+                        const int c = e / QP, i = e % QP;
+                        if (c == 0) atomicAdd(qx + i * stX, cv * wx);
+                        else if (c == 1) atomicAdd(qy + i * stY, cv * wy);
+                        else atomicAdd(qz + i * stZ, cv * wz);
+                    }
                 }
             }
         }
@@ -334,12 +374,6 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                 auto accumulate = [&](int pq) {
                     const double2 sx = rec[(T::F_SX + ur) * CHP + pq];     // (Sx_new, Sx_old)[1+ur]
                     const double2 sy = rec[(T::F_SY + qu) * CHP + pq];     // (Sy_new, Sy_old)[1+u]
-                    const double2 aby = rec[(T::F_ABY + qv) * CHP + pq];   // (Ay, By)[1+v]
-                    const double2 abz = rec[(T::F_ABZ + qv) * CHP + pq];   // (Az, Bz)[1+v]
-                    double w3[3];
-                    w3[0] = sy.x * abz.x + sy.y * abz.y;    // Jx line (j, k) = (1+u, 1+v)
-                    w3[1] = sx.x * abz.x + sx.y * abz.y;    // Jy line (i, k) = (1+ur, 1+v)
-                    w3[2] = sx.x * aby.x + sx.y * aby.y;    // Jz line (i, j) = (1+ur, 1+v)
                     double cds[2 * T::NCDS];
 #pragma unroll
                     for (int m = 0; m < T::NCDS; ++m) {
@@ -347,9 +381,18 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                         cds[2 * m] = c2.x; cds[2 * m + 1] = c2.y;
                     }
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
+                    for (int mv = 0; mv < VL; ++mv) {
+                        const double2 aby = rec[(T::F_ABY + qv0 + mv) * CHP + pq];   // (Ay, By)[1+v]
+                        const double2 abz = rec[(T::F_ABZ + qv0 + mv) * CHP + pq];   // (Az, Bz)[1+v]
+                        double w3[3];
+                        w3[0] = sy.x * abz.x + sy.y * abz.y;    // Jx line (j, k) = (1+u, 1+v)
+                        w3[1] = sx.x * abz.x + sx.y * abz.y;    // Jy line (i, k) = (1+ur, 1+v)
+                        w3[2] = sx.x * aby.x + sx.y * aby.y;    // Jz line (i, j) = (1+ur, 1+v)
 #pragma unroll
-                        for (int i = 0; i < QP; ++i) acc[c][i] += cds[c * QP + i] * w3[c];
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int i = 0; i < QP; ++i) acc[mv][c][i] += cds[c * QP + i] * w3[c];
+                    }
                 };
                 // the run [start, end) is contiguous (moved particles have their own key): slot g of
                 // the pass takes particles start+g, start+g+NG, ...
@@ -383,7 +426,7 @@ deposit_general_kernel(SoaView P, const int* __restrict__ list, const int* __res
                        FabView Jx, FabView Jy, FabView Jz, DepositGeom dg, KeyBase kb) {
     using T = GeneralCfg<N>;
     constexpr int S = T::S, PN = T::PN, NB = T::NB, NF = T::NF, CHP = DR_CHP;
-    extern __shared__ double smem[];
+    PIC_DYNAMIC_SMEM(double, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* rec = smem + (size_t)warp * NF * CHP;
     const int count = *list_count;
@@ -514,6 +557,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     kb.b0 = min(J[0].lo[0], min(J[1].lo[0], J[2].lo[0])) - 1;
     kb.b1 = min(J[0].lo[1], min(J[1].lo[1], J[2].lo[1])) - 1;
     kb.b2 = min(J[0].lo[2], min(J[1].lo[2], J[2].lo[2])) - 1;
+#ifndef PIC_SIMT_HOST
     // list of particles that changed cell + its counter (stream-ordered scratch, freed after use).
     // Keep the pool's memory across host synchronisations (default threshold 0 would unmap it).
     static bool pool_done = false;
@@ -536,15 +580,20 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     // along x -- <2,0,1> with z-fastest bins -- coalesces the retired planes but was measured no
     // faster for the deposition and 2.2x slower for the gather: 4-way bank conflicts between the
     // cells of a warp in the shared E/B block.)
-    auto kq = deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2>;
+    constexpr int VL2 = ((N + 1) % 2 == 0) ? 2 : 1;
+    using TQ2 = QuietCfg<N, VL2>;
+    const bool two = (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
+    auto kq = two ? (slotred ? deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true> : deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>)
+                  : (slotred ? deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true> : deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>);
     auto kg = deposit_general_kernel<N, NWG>;
-    const size_t smem_q = (size_t)NWQ * TQ::NF * TQ::CHP * sizeof(double2);
+    const size_t smem_q = (size_t)NWQ * TQ::NF * (two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[4] = {false, false, false, false};
+    const int vidx = (two ? 1 : 0) + (slotred ? 2 : 0);
+    if (!attr_done[vidx]) {
         cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
         cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
-        attr_done = true;
+        attr_done[vidx] = true;
     }
     const long nchunks = (np + DR_CH - 1) / DR_CH;
     const int cpw = 16;   // 512 consecutive particles per warp: long runs, few boundaries
@@ -557,6 +606,34 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     cudaFreeAsync(scratch, s);
     return check_launch("pic_deposit_esirkepov(runs)") ? 0 : 1;
 }
+#else
+    // tests/host_harness: the same two kernels under the SIMT emulator (host memory, no CUDA runtime)
+    std::vector<int> scratch_h((size_t)np + 1, 0);
+    int* list_count = scratch_h.data();
+    int* list = scratch_h.data() + 1;
+    constexpr int VL2 = ((N + 1) % 2 == 0) ? 2 : 1;
+    using TQ2 = QuietCfg<N, VL2>;
+    const bool two = (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
+    const size_t smem_q = (size_t)NWQ * TQ::NF * (two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
+    const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
+    const long nchunks = (np + DR_CH - 1) / DR_CH;
+    const int cpw = 16;
+    const long nwarps = (nchunks + cpw - 1) / cpw;
+    const unsigned grid_q = (unsigned)((nwarps + NWQ - 1) / NWQ);
+    J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
+    const FabView v0 = make_view(J[0]), v1 = make_view(J[1]), v2 = make_view(J[2]);
+    (void)s;
+    ::simt::launch(dim3(grid_q), dim3(NWQ * 32), smem_q, [&] {
+        if (two && slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (two) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>(P, np, cpw, j3, dg, kb, list, list_count);
+    });
+    ::simt::launch(dim3(4), dim3(NWG * 32), smem_g,
+                   [&] { deposit_general_kernel<N, NWG>(P, list, list_count, v0, v1, v2, dg, kb); });
+    return 0;
+}
+#endif
 
 int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
                         const DepositGeom& dg, int nox, cudaStream_t s) {

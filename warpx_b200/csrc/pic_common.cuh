@@ -25,6 +25,14 @@ bool check_launch(const char* what);  // cudaGetLastError after a launch
 
 #define PIC_REQUIRE(cond, ...) do { if (!(cond)) return ::pic::fail(__VA_ARGS__); } while (0)
 
+// Dynamic shared memory of a kernel.  PIC_SIMT_HOST is only ever defined by tests/host_harness (the SIMT
+// emulator that runs the kernel source on the host, see tests/host_harness/simt_host.h).
+#ifdef PIC_SIMT_HOST
+#define PIC_DYNAMIC_SMEM(T, name) T* name = reinterpret_cast<T*>(::simt::dynamic_smem())
+#else
+#define PIC_DYNAMIC_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 // ---- array view: amrex::Array4 indexing (Fortran order, arbitrary lower bound) --------------
 struct FabView {
     double* __restrict__ p;
