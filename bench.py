@@ -343,9 +343,10 @@ def main():
                     help="warpx.use_filter: bilinear current filter, 1 pass.  Off by default: SURVEY.md 8(d) "
                          "fixes use_filter = 0 for the benchmark configurations; --filter 1 measures the "
                          "reference's own default (WarpX.cpp:158)")
-    ap.add_argument("--deposit-mode", type=int, default=0, choices=[0, 1, 2, 3, 4],
+    ap.add_argument("--deposit-mode", type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6],
                     help="pic_set_deposit_mode: 0 register runs (default), 1 shared-memory tile block, 2 two lines per "
-                         "lane, 3 per-slot reductions, 4 both (A/B measurements; every mode passes the parity tests)")
+                         "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions "
+                         "(A/B measurements; every mode passes the parity tests)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

@@ -199,11 +199,12 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
  *   particle; orders 1 and 3 -- order 2 falls back to PIC_DEPOSIT_RUNS);
  * PIC_DEPOSIT_RUNS_SLOTRED / PIC_DEPOSIT_RUNS2_SLOTRED: the particle slots of a warp pass send their own
  *   partial sums to L2 instead of being summed by shuffles first.
- * The last three are experiments until measured; all pass the same parity tests.
+ * PIC_DEPOSIT_RUNS4 / PIC_DEPOSIT_RUNS4_SLOTRED: four lines per lane (order 3 only; 168 registers).
+ * Modes 2..6 are experiments until measured; all pass the same parity tests.
  * Analogous to WarpX's runtime switch warpx.do_shared_mem_current_deposition
  * (Source/WarpX.cpp:126, Docs/source/usage/parameters.rst:2608-2623). */
 enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1, PIC_DEPOSIT_RUNS2 = 2, PIC_DEPOSIT_RUNS_SLOTRED = 3,
-       PIC_DEPOSIT_RUNS2_SLOTRED = 4 };
+       PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6 };
 void pic_set_deposit_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------

@@ -24,11 +24,13 @@ CASES = [(3, 0.02, "sorted"), (3, 0.5, "sorted"), (3, 0.02, "jitter"), (3, 0.3, 
          (2, 0.3, "sorted")]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("nox,u_th,order", CASES)
 def test_deposit_runs_kernels_under_simt_emulation(orc, simt, variant, nox, u_th, order):
     if variant and (nox, order) not in ((3, "sorted"), (3, "jitter"), (1, "jitter"), (2, "sorted")):
         pytest.skip("the experimental variants are covered on a subset")
+    if variant >= 4 and nox != 3:
+        pytest.skip("four lines per lane: order 3 only")
     n, lx = (8, 6, 6), (4e-6, 3e-6, 3e-6)
     wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(2, 2, 2), u_th=u_th, lx=lx, seed=3)
     s = wl["species"][0]

@@ -32,8 +32,8 @@
 
 namespace pic {
 
-// bit 0: two v-lines per lane where N+1 is even; bit 1: per-slot reductions instead of the shuffle fold
-// (pic_set_deposit_mode: PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_RUNS2 = 1, PIC_DEPOSIT_RUNS_SLOTRED = 2, both = 3)
+// bit 0: two v-lines per lane where N+1 is even; bit 1: per-slot reductions instead of the shuffle fold;
+// bit 2: four v-lines per lane (order 3 only; 168 registers -> 3 CTAs of 4 warps per SM)
 int g_runs_variant = 0;
 
 constexpr int DR_CH = 32;          // particles per chunk
@@ -582,14 +582,18 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     // cells of a warp in the shared E/B block.)
     constexpr int VL2 = ((N + 1) % 2 == 0) ? 2 : 1;
     using TQ2 = QuietCfg<N, VL2>;
-    const bool two = (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
-    auto kq = two ? (slotred ? deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true> : deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>)
+    const bool four = (g_runs_variant & 4) && N == 3;
+    const bool two = !four && (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
+    constexpr int VL4 = (N == 3) ? 4 : 1;
+    using TQ4 = QuietCfg<N, VL4>;
+    auto kq = four ? (slotred ? deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, true> : deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, false>)
+            : two ? (slotred ? deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true> : deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>)
                   : (slotred ? deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true> : deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>);
     auto kg = deposit_general_kernel<N, NWG>;
-    const size_t smem_q = (size_t)NWQ * TQ::NF * (two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
+    const size_t smem_q = (size_t)NWQ * TQ::NF * (four ? TQ4::CHP : two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
-    static bool attr_done[4] = {false, false, false, false};
-    const int vidx = (two ? 1 : 0) + (slotred ? 2 : 0);
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    const int vidx = (two ? 1 : 0) + (slotred ? 2 : 0) + (four ? 4 : 0);
     if (!attr_done[vidx]) {
         cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
         cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
@@ -613,8 +617,11 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     int* list = scratch_h.data() + 1;
     constexpr int VL2 = ((N + 1) % 2 == 0) ? 2 : 1;
     using TQ2 = QuietCfg<N, VL2>;
-    const bool two = (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
-    const size_t smem_q = (size_t)NWQ * TQ::NF * (two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
+    const bool four = (g_runs_variant & 4) && N == 3;
+    const bool two = !four && (g_runs_variant & 1) && VL2 == 2, slotred = (g_runs_variant & 2) != 0;
+    constexpr int VL4 = (N == 3) ? 4 : 1;
+    using TQ4 = QuietCfg<N, VL4>;
+    const size_t smem_q = (size_t)NWQ * TQ::NF * (four ? TQ4::CHP : two ? TQ2::CHP : TQ::CHP) * sizeof(double2);
     const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
     const long nchunks = (np + DR_CH - 1) / DR_CH;
     const int cpw = 16;
@@ -624,7 +631,9 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     const FabView v0 = make_view(J[0]), v1 = make_view(J[1]), v2 = make_view(J[2]);
     (void)s;
     ::simt::launch(dim3(grid_q), dim3(NWQ * 32), smem_q, [&] {
-        if (two && slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        if (four && slotred) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (four) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, false>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (two && slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true>(P, np, cpw, j3, dg, kb, list, list_count);
         else if (two) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>(P, np, cpw, j3, dg, kb, list, list_count);
         else if (slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true>(P, np, cpw, j3, dg, kb, list, list_count);
         else deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>(P, np, cpw, j3, dg, kb, list, list_count);
