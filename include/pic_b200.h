@@ -121,24 +121,35 @@ typedef struct pic_boundaries {
  * LaserParticleContainer.cpp:84-270: position, direction, polarization, wavelength, e_max) +
  * GaussianLaserProfile (Source/Laser/LaserProfilesImpl/LaserProfileGaussian.cpp:32-86:
  * profile_waist, profile_duration, profile_t_peak, profile_focal_distance, phi0; the
- * spatio-temporal couplings zeta, beta, phi2 are 0).  Lab frame (gamma_boost = 1). */
+ * spatio-temporal couplings zeta, beta, phi2 are 0).  All parameters are lab-frame values, as in the
+ * deck.  gamma_boost > 1 (warpx.gamma_boost, with beta_boost = sqrt(1 - 1/gamma_boost^2),
+ * Source/Utils/WarpXUtil.cpp:114-121): the simulation frame moves along nvec (the reference asserts
+ * boost_direction == nvec, LaserParticleContainer.cpp:183-190); the library moves the antenna plane to
+ * Z0/gamma_boost (:191-197), evaluates the profile at the lab time of the plane (:573-579), divides the
+ * mobility by gamma_boost (:775) and lets the antenna drift with -beta_boost c nvec (:908-915).
+ * gamma_boost <= 1 (0 included) = lab frame. */
 typedef struct pic_laser_antenna {
     double position[3];     /* a point of the antenna plane                    */
     double nvec[3];         /* plane normal = propagation direction (normalised by the library) */
     double p_X[3];          /* main polarisation vector (normalised by the library)             */
     double wavelength, e_max;
     double waist, duration, t_peak, focal_distance, phi0;
+    double gamma_boost, beta_boost;
 } pic_laser_antenna;
 
 /* Plasma injector of one species: NUniformPerCell positions (InjectorPositionRegular,
  * Source/Initialization/InjectorPosition.H:67-108), constant density, momentum at rest
  * (<species>.injection_style / num_particles_per_cell_each_dim / xmin..zmax / profile = constant /
- * momentum_distribution_type = at_rest / do_continuous_injection of Source/Initialization/PlasmaInjector.cpp). */
+ * momentum_distribution_type = at_rest / do_continuous_injection of Source/Initialization/PlasmaInjector.cpp).
+ * gamma_boost > 1: frame boosted along +z; bound_lo/hi and density stay lab-frame values, the library
+ * tests the bounds at z_lab = gamma (z + beta c t), scales the density by gamma and gives every particle
+ * uz = -gamma beta c (PhysicalParticleContainer.cpp:138-148,1209-1247). */
 typedef struct pic_plasma_injector {
     int ppc[3];
     double bound_lo[3], bound_hi[3];   /* xmin,ymin,zmin / xmax,ymax,zmax (+-inf when unset) */
     double density;
     int do_continuous_injection;
+    double gamma_boost, beta_boost;
 } pic_plasma_injector;
 
 enum { PIC_ERR_ABORT = 0, PIC_ERR_RETURN = 1 };
@@ -346,10 +357,11 @@ int pic_laser_antenna_push(const pic_laser_antenna* prm, const double dx[3], con
  * ids first_id, first_id+1, ...  cell_size = Geometry::CellSize() (NULL: (prob_hi - prob_lo) / n_cell;
  * a moving window translates the domain but keeps the cell size it started with).  box_lo/box_hi =
  * the cells of this rank's box (the tile whose RealBox must contain a particle, :1141-1156; NULL = the
- * whole domain).  p = NULL only counts.  Returns how many were (would be) added, -1 on error. */
+ * whole domain).  t = WarpX::gett_new(0), used only in a boosted frame (:956).  p = NULL only counts.
+ * Returns how many were (would be) added, -1 on error. */
 long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double cell_size[3],
                     const int box_lo[3], const int box_hi[3], const double part_lo[3], const double part_hi[3],
-                    const pic_soa* p, long capacity, uint64_t first_id, void* stream);
+                    const pic_soa* p, long capacity, uint64_t first_id, double t, void* stream);
 
 /* w_out[ip] = w[ip] for particles inside [own_lo, own_hi), 0 elsewhere.  Used for containers that are
  * replicated on every rank (laser antennas): each rank deposits only what lies in its own box. */
@@ -399,6 +411,10 @@ int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
  *   set_boundaries     boundary.field_lo/hi + boundary.particle_lo/hi (PEC walls, absorbing / reflecting particles);
  *   set_moving_window  warpx.do_moving_window / moving_window_dir / moving_window_v [c] (grows the guard
  *                      cells like guardCellManager::Init, GuardCellManager.cpp:103-115 -- query pic_engine_guards after);
+ *   set_boost          warpx.gamma_boost with boost_direction = z: the window and the injection front move with the
+ *                      boosted velocities (WarpXMovingWindow.cpp:108-133,156); injectors and antennas added afterwards
+ *                      take the engine's gamma_boost / beta_boost; prob_lo/hi are the caller's boosted-frame values
+ *                      (ConvertLabParamsToBoost, Source/Utils/WarpXUtil.cpp:180-262);
  *   set_injector       the plasma injector of species isp (its particles must have been created by
  *                      pic_add_plasma over the whole domain, ids 0..np-1); with do_continuous_injection
  *                      the moving window refills the uncovered slab (WarpXMovingWindow.cpp:388-438);
@@ -407,6 +423,7 @@ int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
  * pic_engine_time = t_new[0]; pic_engine_prob_domain = the (moving) problem domain, out = lo[3] hi[3]. */
 int pic_engine_set_boundaries(void* engine, const pic_boundaries* b);
 int pic_engine_set_moving_window(void* engine, int dir, double v_over_c);
+int pic_engine_set_boost(void* engine, double gamma_boost, double beta_boost);
 int pic_engine_set_injector(void* engine, int isp, const pic_plasma_injector* inj);
 int pic_engine_add_laser(void* engine, const pic_laser_antenna* prm, const pic_soa* p, long capacity);
 long pic_engine_laser_np(void* engine, int ilaser);

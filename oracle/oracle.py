@@ -97,7 +97,9 @@ def lib(kind="restated"):
         "orc_apply_pec_current": (None, [fabp, gp, C.POINTER(abi.pic_boundaries)]),
         "orc_shift_fab": (None, [fabp, gp, C.c_int, C.c_int, C.c_double]),
         "orc_antenna_push": (None, [C.POINTER(abi.pic_laser_antenna), dp, soap, C.c_double, C.c_double]),
-        "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long]),
+        "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long,
+                                      C.c_double, dp]),
+        "orc_sim_set_boost": (C.c_int, [vp, C.c_double, C.c_double]),
         "orc_apply_particle_boundaries": (None, [soap, gp, C.POINTER(abi.pic_boundaries), C.c_char_p]),
         "orc_antenna_particles": (C.c_long, [C.POINTER(abi.pic_laser_antenna), dp, dp, dp, dp, dp, dp, dp, C.c_long]),
         "orc_sim_rho_checksum": (C.c_double, [vp]),
@@ -207,6 +209,12 @@ class OracleSim:
         rc = self.L.orc_sim_set_moving_window(self.h, direction, v_over_c)
         if rc:
             raise ValueError("orc_sim_set_moving_window: %d" % rc)
+
+    def set_boost(self, gamma_boost):
+        """warpx.gamma_boost, boost_direction = z; injectors and antennas added later take it over."""
+        rc = self.L.orc_sim_set_boost(self.h, gamma_boost, abi.beta_of_gamma(gamma_boost))
+        if rc:
+            raise ValueError("orc_sim_set_boost: call before adding species / lasers")
 
     def add_plasma(self, q, m, injector):
         self.nspecies += 1

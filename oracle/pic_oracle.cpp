@@ -71,6 +71,7 @@ struct Sim {
     bool do_moving_window = false;
     int mw_dir = 2;
     double mw_v = 0.0, mw_x = 0.0;                 // moving_window_v [m/s], moving_window_x
+    double gamma_boost = 1.0, beta_boost = 0.0;    // warpx.gamma_boost, boost_direction = z (WarpXUtil.cpp:114-121)
     struct Laser { Antenna ant; std::vector<double> a[7]; };
     std::vector<Laser> lasers;
     double t_push = 0, t_dep = 0, t_fdtd = 0, t_halo = 0, t_other = 0;
@@ -237,8 +238,19 @@ int move_window(Sim& s, int step, bool move_j) {
     (void)step;                                          // start_moving_window_step = 0, no end step
     if (!s.do_moving_window) return 0;
     const int dir = s.mw_dir;
-    s.mw_x += (s.mw_v - 0.0 * C_LIGHT) / (1 - s.mw_v * 0.0 / C_LIGHT) * s.dt;                    // :155
-    // UpdateInjectionPosition (:59-136): plasma at rest -> v_shift = 0; antennas: lab frame, nothing
+    s.mw_x += (s.mw_v - s.beta_boost * C_LIGHT) / (1 - s.mw_v * s.beta_boost / C_LIGHT) * s.dt;  // :156
+    // UpdateInjectionPosition (:59-136): plasma at rest in the lab -> v_shift = 0, transformed to the
+    // boosted frame (:108-133; boost_direction[dir] = 1, the boost is along the window)
+    for (auto& b : s.boxes)
+        for (auto& sp : b.sp) {
+            if (!sp.has_injector || !sp.inj.do_continuous_injection) continue;
+            double v_shift = C_LIGHT * 0.0 / std::sqrt(1. + 0.0 * 0.0);
+            if (s.gamma_boost > 1.) {
+                v_shift = (v_shift - C_LIGHT * s.beta_boost) / (1. - v_shift * s.beta_boost / C_LIGHT);
+                v_shift *= (dir == 2) ? 1 : 0;
+            }
+            sp.current_injection_position += v_shift * s.dt;
+        }
     const double cdx = s.dx[dir];
     const int num_shift_base = static_cast<int>((s.mw_x - s.geom.prob_lo[dir]) / cdx);            // :171
     if (num_shift_base == 0) return 0;
@@ -268,7 +280,7 @@ int move_window(Sim& s, int step, bool move_j) {
             const bool ok = plo[0] < phi[0] && plo[1] < phi[1] && plo[2] < phi[2];               // RealBox::ok
             if (ok && sp.current_injection_position != new_pos) {
                 const size_t n0 = sp.a[2].size();
-                add_plasma(sp.inj, s.geom, s.dx, plo, phi, sp.a);
+                add_plasma(sp.inj, s.geom, s.dx, plo, phi, sp.a, s.cur_time);   // t = t_new (WarpXEvolve.cpp:232-246)
                 for (size_t ip = n0; ip < sp.a[2].size(); ++ip) sp.z_inj.push_back(sp.a[2][ip]);
                 sp.current_injection_position = new_pos;
             }
@@ -516,6 +528,13 @@ int orc_sim_set_moving_window(void* h, int dir, double v_over_c) {
     alloc_box(*s, s->boxes[0]);
     return 0;
 }
+// warpx.gamma_boost with warpx.boost_direction = z; call before adding species / lasers
+int orc_sim_set_boost(void* h, double gamma_boost, double beta_boost) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->nspecies || !s->lasers.empty()) return 1;
+    s->gamma_boost = gamma_boost; s->beta_boost = beta_boost;
+    return 0;
+}
 // A species created by its plasma injector (PhysicalParticleContainer::InitData -> AddPlasma over
 // the whole domain, PhysicalParticleContainer.cpp:450-454,855-922)
 int orc_sim_add_plasma(void* h, double q, double m, const pic_plasma_injector* inj) {
@@ -525,6 +544,7 @@ int orc_sim_add_plasma(void* h, double q, double m, const pic_plasma_injector* i
     b.sp.emplace_back();
     Species& sp = b.sp.back();
     sp.q = q; sp.m = m; sp.has_injector = true; sp.inj = *inj;
+    sp.inj.gamma_boost = s->gamma_boost; sp.inj.beta_boost = s->beta_boost;
     if (s->do_moving_window)                                     // WarpX.cpp:288-307
         sp.current_injection_position = s->mw_v > 0 ? s->geom.prob_hi[s->mw_dir] : s->geom.prob_lo[s->mw_dir];
     add_plasma(sp.inj, s->geom, s->dx, s->geom.prob_lo, s->geom.prob_hi, sp.a);
@@ -537,7 +557,9 @@ int orc_sim_add_laser(void* h, const pic_laser_antenna* prm) {
     if (s->boxes.size() != 1) return -1;
     s->lasers.emplace_back();
     Sim::Laser& L = s->lasers.back();
-    L.ant = antenna_setup(*prm, s->dx);
+    pic_laser_antenna q = *prm;
+    q.gamma_boost = s->gamma_boost; q.beta_boost = s->beta_boost;
+    L.ant = antenna_setup(q, s->dx);
     antenna_init_particles(L.ant, s->geom.prob_lo, s->geom.prob_hi, L.a);     // m_laser_injection_box = ProbDomain (:224)
     return (int)s->lasers.size() - 1;
 }
@@ -567,15 +589,16 @@ void orc_apply_pec_current(const pic_fab* J, const pic_geom* g, const pic_bounda
 void orc_shift_fab(const pic_fab* f, const pic_geom* g, int num_shift, int dir, double external_field) {
     shift_fab(*f, *g, num_shift, dir, external_field);
 }
-// AddPlasma into caller arrays (x y z w; momenta are 0): returns the count, -1 if capacity is too small
+// AddPlasma into caller arrays (x y z w [uz]; ux = uy = 0): returns the count, -1 if capacity is too small
 long orc_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double* part_lo, const double* part_hi,
-                    double* x, double* y, double* z, double* w, long capacity) {
+                    double* x, double* y, double* z, double* w, long capacity, double t, double* uz) {
     double dx[3];
     for (int d = 0; d < 3; ++d) dx[d] = (g->prob_hi[d] - g->prob_lo[d]) / g->n_cell[d];
     std::vector<double> out[7];
-    const long n = add_plasma(*inj, *g, dx, part_lo, part_hi, out);
+    const long n = add_plasma(*inj, *g, dx, part_lo, part_hi, out, t);
     if (n > capacity) return -1;
     for (long i = 0; i < n; ++i) { x[i] = out[0][i]; y[i] = out[1][i]; z[i] = out[2][i]; w[i] = out[3][i]; }
+    if (uz) for (long i = 0; i < n; ++i) uz[i] = out[6][i];
     return n;
 }
 // ApplyBoundaryConditions: positions / momenta are updated in place, keep[ip] = 0 marks lost particles

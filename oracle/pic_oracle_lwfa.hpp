@@ -207,12 +207,15 @@ inline void shift_fab(const pic_fab& f, const pic_geom& g, int num_shift, int di
 }
 
 // ============================================================================================
-// Laser antenna.  LaserParticleContainer (Particles/LaserParticleContainer.cpp), lab frame, 3D.
+// Laser antenna.  LaserParticleContainer (Particles/LaserParticleContainer.cpp), 3D; lab frame or a
+// frame boosted along the propagation direction (prm.gamma_boost > 1).
 // ============================================================================================
 struct Antenna {
-    pic_laser_antenna prm;          // nvec, p_X normalised
+    pic_laser_antenna prm;          // nvec, p_X normalised; position in the simulation frame
     double p_Y[3], u_X[3], u_Y[3];
     double S_X, S_Y, mobility, weight;
+    double Z0_lab;                  // antenna plane along nvec in the lab frame (boosted runs)
+    bool boosted;
 };
 
 // Constructor (:84-270, 3D: u_X = p_X, u_Y = p_Y = nvec x p_X) + ComputeSpacing (:727-761) +
@@ -222,6 +225,13 @@ inline Antenna antenna_setup(const pic_laser_antenna& in, const double dx[3]) {
     a.prm = in;
     double s = 1.0 / std::sqrt(in.nvec[0] * in.nvec[0] + in.nvec[1] * in.nvec[1] + in.nvec[2] * in.nvec[2]);   // :179-180
     for (int d = 0; d < 3; ++d) a.prm.nvec[d] = in.nvec[d] * s;
+    a.boosted = in.gamma_boost > 1.;
+    a.Z0_lab = 0.0;
+    if (a.boosted) {                                                                                               // :183-197
+        a.Z0_lab = a.prm.nvec[0] * a.prm.position[0] + a.prm.nvec[1] * a.prm.position[1] + a.prm.nvec[2] * a.prm.position[2];
+        const double Z0_boost = a.Z0_lab / in.gamma_boost;
+        for (int d = 0; d < 3; ++d) a.prm.position[d] += (Z0_boost - a.Z0_lab) * a.prm.nvec[d];
+    }
     s = 1.0 / std::sqrt(in.p_X[0] * in.p_X[0] + in.p_X[1] * in.p_X[1] + in.p_X[2] * in.p_X[2]);                 // :199-200
     for (int d = 0; d < 3; ++d) a.prm.p_X[d] = in.p_X[d] * s;
     const double* n = a.prm.nvec; const double* p = a.prm.p_X;
@@ -235,6 +245,7 @@ inline Antenna antenna_setup(const pic_laser_antenna& in, const double dx[3]) {
     a.mobility = 0.05 / a.prm.e_max;                                                                               // :770-771
     a.weight = EP0 / a.mobility;                                                                                   // :772
     a.weight *= 1.0 * a.S_X * a.S_Y;                                                                               // :774
+    if (a.boosted) a.mobility = a.mobility / in.gamma_boost;                                                       // :775 (divides by 1 otherwise)
     return a;
 }
 
@@ -277,9 +288,12 @@ inline void antenna_init_particles(const Antenna& a, const double box_lo[3], con
 // One step of the antenna particles (LaserParticleContainer::Evolve :614-626):
 // calculate_laser_plane_coordinates (:800-848), GaussianLaserProfile::fill_amplitude
 // (LaserProfileGaussian.cpp:100-162, zeta = beta = phi2 = 0 so stretch_factor = 1 and theta_stc
-// drops out), update_laser_particle (:860-951, gamma_boost = 1, explicit push).
-inline void antenna_push(const Antenna& a, const pic_soa& P, double t, double dt) {
+// drops out), update_laser_particle (:860-951, explicit push).  In a boosted frame the profile is
+// evaluated at the lab time of the antenna plane (:573-579) and the antenna drifts with -beta c nvec.
+inline void antenna_push(const Antenna& a, const pic_soa& P, double t_sim, double dt) {
     using cplx = std::complex<double>;
+    const double gamma_boost = a.boosted ? a.prm.gamma_boost : 1.0, beta_boost = a.boosted ? a.prm.beta_boost : 0.0;
+    const double t = a.boosted ? 1. / gamma_boost * t_sim + beta_boost * a.Z0_lab / C_LIGHT : t_sim;
     const cplx I(0.0, 1.0);
     const double k0 = 2.0 * PI / a.prm.wavelength;
     const double inv_tau2 = 1.0 / (a.prm.duration * a.prm.duration);
@@ -307,10 +321,15 @@ inline void antenna_push(const Antenna& a, const pic_soa& P, double t, double dt
         // update_laser_particle (:905-949)
         const double sign_charge = (P.w[ip] > 0) ? -1.0 : 1.0;
         const double v_over_c = sign_charge * a.mobility * amplitude;
-        const double vx = C_LIGHT * v_over_c * a.prm.p_X[0];
-        const double vy = C_LIGHT * v_over_c * a.prm.p_X[1];
-        const double vz = C_LIGHT * v_over_c * a.prm.p_X[2];
-        const double gamma = 1.0 / std::sqrt(1. - v_over_c * v_over_c);
+        double vx = C_LIGHT * v_over_c * a.prm.p_X[0];
+        double vy = C_LIGHT * v_over_c * a.prm.p_X[1];
+        double vz = C_LIGHT * v_over_c * a.prm.p_X[2];
+        if (gamma_boost > 1.) {                                                                    // :908-912
+            vx -= C_LIGHT * beta_boost * a.prm.nvec[0];
+            vy -= C_LIGHT * beta_boost * a.prm.nvec[1];
+            vz -= C_LIGHT * beta_boost * a.prm.nvec[2];
+        }
+        const double gamma = gamma_boost / std::sqrt(1. - v_over_c * v_over_c);                  // :914-915
         P.ux[ip] = gamma * vx; P.uy[ip] = gamma * vy; P.uz[ip] = gamma * vz;
         P.x[ip] = x + vx * dt; P.y[ip] = y + vy * dt; P.z[ip] = z + vz * dt;
     }
@@ -318,14 +337,19 @@ inline void antenna_push(const Antenna& a, const pic_soa& P, double t, double dt
 
 // ============================================================================================
 // Plasma injection.  PhysicalParticleContainer::AddPlasma (Particles/PhysicalParticleContainer.cpp:
-// 924-1333) for injection_style = NUniformPerCell, profile = constant, momentum at rest,
-// gamma_boost = 1, one tile = the whole box (tile decomposition only changes positions at the
+// 924-1333) for injection_style = NUniformPerCell, profile = constant, momentum at rest (in the lab
+// frame; inj.gamma_boost > 1: frame boosted along z, t = t_new), one tile = the whole box (tile decomposition only changes positions at the
 // rounding level, see find_overlap).  part_lo/hi = the RealBox particles are requested in
 // (whole domain at start-up, the freshly uncovered slab for continuous injection).
 // Appends to out[0..6]; returns the number of particles added.
 // ============================================================================================
 inline long add_plasma(const pic_plasma_injector& inj, const pic_geom& g, const double dx[3],
-                       const double part_lo[3], const double part_hi[3], std::vector<double> out[7]) {
+                       const double part_lo[3], const double part_hi[3], std::vector<double> out[7],
+                       double t = 0.0) {
+    const bool boosted = inj.gamma_boost > 1.;
+    const double gamma_boost = boosted ? inj.gamma_boost : 1.0, beta_boost = boosted ? inj.beta_boost : 0.0;
+    // applyBallisticCorrection (:138-148) for a plasma at rest in the lab: betaz_bulk = 0
+    auto z_lab = [&](double z) { return gamma_boost * (z * (1.0 - beta_boost * 0.0) - C_LIGHT * t * (0.0 - beta_boost)); };
     // tile_realbox = RealBox(box, dx, prob_lo) (WarpX::getRealBox, WarpX.cpp:2852-2857)
     double tile_lo[3], tile_hi[3], ov_lo[3], ov_hi[3];
     int nov[3];
@@ -359,6 +383,7 @@ inline long add_plasma(const pic_plasma_injector& inj, const pic_geom& g, const 
                     lo[d] = ov_lo[d] + (iv[d] + 0.0) * dx[d];
                     hi[d] = ov_lo[d] + (iv[d] + 1.0) * dx[d];
                 }
+                lo[2] = z_lab(lo[2]); hi[2] = z_lab(hi[2]);                 // :1021-1022 (identity in the lab frame)
                 // overlapsWith (InjectorPosition.H:228-233)
                 if (!((inj.bound_lo[0] <= hi[0]) && (inj.bound_hi[0] >= lo[0]) && (inj.bound_lo[1] <= hi[1]) &&
                       (inj.bound_hi[1] >= lo[1]) && (inj.bound_lo[2] <= hi[2]) && (inj.bound_hi[2] >= lo[2])))
@@ -384,12 +409,20 @@ inline long add_plasma(const pic_plasma_injector& inj, const pic_geom& g, const 
                     double pos[3];
                     for (int d = 0; d < 3; ++d) pos[d] = ov_lo[d] + (iv[d] + r[d]) * dx[d];
                     if (!realbox_contains(tile_lo, tile_hi, pos)) continue;                // :1141-1156
-                    if (!inside(pos[0], pos[1], pos[2])) continue;                         // :1189-1197 (z0 = z at rest)
-                    double weight = inj.density;                                             // :1282-1283
+                    if (!inside(pos[0], pos[1], z_lab(pos[2]))) continue;                  // :1184-1197 / :1211-1224
+                    double dens = inj.density, uz = 0.0;
+                    if (boosted) {                                                           // :1232-1246, u = 0 in the lab
+                        const double gamma_lab = std::sqrt(1. + (0.0 * 0.0 + 0.0 * 0.0 + uz * uz));
+                        const double betaz_lab = uz / (gamma_lab);
+                        dens = gamma_boost * dens * (1.0 - beta_boost * betaz_lab);
+                        uz = gamma_boost * (uz - beta_boost * gamma_lab);
+                    }
+                    uz *= C_LIGHT;                                                           // :1275-1277
+                    double weight = dens;                                                    // :1282-1283
                     weight *= scale_fac;
                     out[0].push_back(pos[0]); out[1].push_back(pos[1]); out[2].push_back(pos[2]);
                     out[3].push_back(weight);
-                    out[4].push_back(0.0); out[5].push_back(0.0); out[6].push_back(0.0);
+                    out[4].push_back(0.0); out[5].push_back(0.0); out[6].push_back(uz);
                     ++added;
                 }
             }

@@ -181,12 +181,12 @@ def test_add_plasma_matches_oracle(orc, dev, ppc, slab):
     for k, name in enumerate(("x", "y", "z", "w", "ux", "uy", "uz")):
         setattr(soa, name, buf[k].data_ptr())
     soa.idcpu, soa.np = ids.data_ptr(), 7
-    n = dev.L.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(soa), cap, 500, dev.stream)
+    n = dev.L.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(soa), cap, 500, 0.0, dev.stream)
     assert n > 0, dev.L.pic_last_error().decode()
     dev.sync()
     B = [np.empty(cap) for _ in range(4)]
     dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
-    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(plo), abi.dbl3(phi), *[dp(b) for b in B], cap)
+    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(plo), abi.dbl3(phi), *[dp(b) for b in B], cap, 0.0, None)
     assert m == n
     got = buf.cpu().numpy()
     for k, b in enumerate(B):
@@ -258,7 +258,8 @@ def make_lwfa_sim(wl, capacity):
     sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"],
                      solver=wl["solver"], pusher=wl["pusher"], use_filter=wl["use_filter"], sort_interval=4,
                      boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]),
-                     moving_window=(wl["moving_window_dir"], wl["moving_window_v"]))
+                     moving_window=(wl["moving_window_dir"], wl["moving_window_v"]),
+                     gamma_boost=wl.get("gamma_boost", 1.0))
     for s in wl["species"]:
         sim.add_plasma_species(s["name"], s["q"], s["m"],
                                abi.make_injector(s["ppc"], s["bound_lo"], s["bound_hi"], s["density"],
@@ -313,6 +314,44 @@ def test_laser_acceleration_loop_matches_oracle(orc, cuda, solver, pusher):
         assert np.max(np.abs(LA[k] - LB[k])) / sim.dx[2] <= 1e-10, k
     for k in ("ux", "uy", "uz"):
         assert np.max(np.abs(LA[k] - LB[k])) / workloads.C <= 1e-10, k
+
+
+def test_boosted_laser_acceleration_loop_matches_oracle(orc, cuda):
+    """BASELINE.json config 4 in the small (workloads.laser_acceleration_boosted_3d: gamma_boost = 10, CKC, Vay,
+    order 3, filter, PEC z, moving window, boosted antenna, electrons + ions injected continuously from the
+    lab-frame plasma bounds): 40 steps through the C++ driver against the oracle -- fields, every particle of
+    both species by id, the drifting antenna, the moving domain."""
+    wl = workloads.laser_acceleration_boosted_3d()
+    sim = make_lwfa_sim(wl, capacity=16 * 16 * 200)
+    osim = make_lwfa_oracle(orc, wl)
+    assert sim.gamma_boost == 10.0 and sim.species[0].np == osim.L.orc_sim_np(osim.h, 0) == 0
+    for chunk, sync in ((23, False), (17, True)):
+        sim.Evolve(chunk, synchronize_last=sync)
+        osim.evolve(chunk, synchronize_last=sync)
+    cuda.cuda.synchronize()
+    assert sim.time == pytest.approx(osim.time(), rel=1e-15)
+    plo, phi = osim.prob_domain()
+    assert sim.prob_lo == pytest.approx(plo, rel=0, abs=1e-18) and sim.prob_hi == pytest.approx(phi, rel=0, abs=1e-18)
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        _, oa = osim.fab(c)
+        assert np.max(np.abs(oa[d.valid_slices()])) > 0, abi.COMP_NAMES[c]
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= 1e-8, abi.COMP_NAMES[c]
+    for isp in (0, 1):
+        A = sim.species_numpy(isp, sort_by_id=True)
+        B = osim.particles(isp)
+        assert len(A["x"]) == len(B["x"]) > 0 and np.array_equal(A["id"], np.arange(len(B["x"])))
+        assert np.array_equal(A["w"], B["w"])
+        for k in ("x", "y", "z"):
+            assert np.max(np.abs(A[k] - B[k])) / sim.dx[2] <= 1e-9, k
+        for k in ("ux", "uy", "uz"):
+            assert np.max(np.abs(A[k] - B[k])) / (10.0 * workloads.C) <= 1e-9, k
+    LA, LB = sim.laser_numpy(0), osim.laser_particles(0)
+    assert len(LA["x"]) == len(LB["x"]) > 0
+    for k in ("x", "y", "z"):
+        assert np.max(np.abs(LA[k] - LB[k])) / sim.dx[2] <= 1e-10, k
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(LA[k] - LB[k])) / (10.0 * workloads.C) <= 1e-10, k
 
 
 def test_laser_acceleration_golden_checksums(orc, cuda, golden):

@@ -150,6 +150,99 @@ def test_laser_antenna_setup_and_push_match_oracle(orc, hh, tilted):
             assert np.max(np.abs(getattr(P, k) - getattr(Q, k))) <= 1e-15 * dx[0]
 
 
+def test_boosted_laser_antenna_matches_oracle(orc, hh):
+    """warpx.gamma_boost = 10 along the propagation direction: the antenna plane moves to Z0 / gamma
+    (LaserParticleContainer.cpp:183-197), the profile is evaluated at the lab time of the plane (:573-579),
+    the mobility is divided by gamma (:775) and the antenna drifts with -beta c nvec (:908-915)."""
+    wl = workloads.laser_acceleration_3d()
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+    las = _laser()
+    gamma = 10.0
+    las.gamma_boost, las.beta_boost = gamma, abi.beta_of_gamma(gamma)
+    lab = _laser()
+    dxa = abi.dbl3(dx)
+    info, info_lab = (C.c_double * 4)(), (C.c_double * 4)()
+    _check(hh, hh.pic_laser_antenna_info(C.byref(las), dxa, info))
+    _check(hh, hh.pic_laser_antenna_info(C.byref(lab), dxa, info_lab))
+    assert info[2] == info_lab[2] / gamma and info[3] == info_lab[3]       # mobility / gamma, same weight
+    lo, hi = abi.dbl3(wl["prob_lo"]), abi.dbl3(wl["prob_hi"])
+    n = hh.pic_laser_antenna_particles(C.byref(las), dxa, lo, hi, None, None, None, None, 0)
+    A = [np.empty(n) for _ in range(4)]
+    assert hh.pic_laser_antenna_particles(C.byref(las), dxa, lo, hi, *[a.ctypes.data for a in A], n) == n
+    B = [np.empty(n) for _ in range(4)]
+    dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
+    assert orc.lib().orc_antenna_particles(C.byref(las), dxa, lo, hi, *[dp(b) for b in B], n) == n
+    for a, b in zip(A, B):
+        assert np.array_equal(a, b)
+    z0_lab = las.position[2]
+    assert n == 2 * 32 * 32 and np.all(A[2] == z0_lab + (z0_lab / gamma - z0_lab))
+    z = np.zeros(n)
+    dt = 8.687655225973464e-16
+    for t in (0.0, 170 * dt, 300.e-15, 610 * dt):
+        P = orc.HostParticles(x=A[0], y=A[1], z=A[2], w=A[3], ux=z, uy=z, uz=z)
+        Q = P.copy()
+        orc.lib().orc_antenna_push(C.byref(las), dxa, C.byref(P.soa), t, dt)
+        _check(hh, hh.pic_laser_antenna_push(C.byref(las), dxa, C.byref(Q.soa), t, dt, None))
+        umax = max(np.max(np.abs(P.ux)), np.max(np.abs(P.uy)))
+        assert umax > 0
+        for k in ("ux", "uy", "uz"):
+            assert np.max(np.abs(getattr(P, k) - getattr(Q, k))) <= 1e-13 * max(umax, np.max(np.abs(P.uz)))
+        for k in ("x", "y", "z"):
+            assert np.max(np.abs(getattr(P, k) - getattr(Q, k))) <= 1e-15 * dx[0]
+        # the drift: z advances by -beta c dt whatever the amplitude, uz = gamma_particle * (-beta c)
+        assert np.allclose(P.z - A[2], -las.beta_boost * workloads.C * dt, rtol=1e-12, atol=0)
+        # the lab-frame amplitude at the same lab time gives gamma times the transverse velocity
+        R = orc.HostParticles(x=A[0], y=A[1], z=A[2], w=A[3], ux=z, uy=z, uz=z)
+        t_lab = t / gamma + las.beta_boost * z0_lab / workloads.C
+        lab_here = _laser()
+        lab_here.position[2] = A[2][0]
+        orc.lib().orc_antenna_push(C.byref(lab_here), dxa, C.byref(R.soa), t_lab, dt)
+        # (polarisation along y: v_lab = gamma_boost v', u_lab = v_lab / sqrt(1 - v_lab^2/c^2),
+        #  u' = gamma_boost v' / sqrt(1 - v'^2/c^2))
+        assert np.max(np.abs(R.uy)) > 0
+        v_lab = R.uy / np.sqrt(1.0 + (R.uy / workloads.C) ** 2)
+        expect = v_lab / np.sqrt(1.0 - (v_lab / gamma / workloads.C) ** 2)
+        assert np.allclose(P.uy, expect, rtol=1e-9, atol=1e-9 * np.max(np.abs(R.uy)))
+
+
+@pytest.mark.parametrize("t", [0.0, 3.3e-14, 2.0e-13])
+@pytest.mark.parametrize("ppc", [(1, 1, 1), (2, 1, 2)])
+def test_boosted_add_plasma_matches_oracle(orc, hh, ppc, t):
+    """AddPlasma in a frame boosted along z (PhysicalParticleContainer.cpp:1017-1022,1209-1247): the
+    plasma bounds are lab-frame values tested at z_lab = gamma (z + beta c t); density x gamma;
+    uz = -gamma beta c.  The lab-frame plasma edge z_lab = 0 cuts through the slab."""
+    gamma = 10.0
+    beta = abi.beta_of_gamma(gamma)
+    n_cell, prob_lo, prob_hi = (6, 4, 24), (-30.e-6, -20.e-6, -200.e-6), (30.e-6, 20.e-6, 40.e-6)
+    geom = abi.make_geom(n_cell, prob_lo, prob_hi, periodic=(1, 1, 0))
+    inj = abi.make_injector(ppc, (-20.e-6, -20.e-6, 0.0), (20.e-6, 11.e-6, 3.e-3), 2.e23, True, gamma_boost=gamma)
+    assert inj.beta_boost == beta
+    cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
+    s, arrs, ids = _host_soa(cap)
+    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(prob_lo), abi.dbl3(prob_hi), C.byref(s), cap, 7, t, None)
+    assert n > 0, hh.pic_last_error().decode()
+    B = [np.empty(cap) for _ in range(5)]
+    dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
+    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(prob_lo), abi.dbl3(prob_hi), *[dp(b) for b in B[:4]], cap, t, dp(B[4]))
+    assert m == n
+    for k, b in zip(("x", "y", "z", "w", "uz"), B):
+        assert np.array_equal(arrs[k][:n], b[:n]), k
+    assert np.all(arrs["ux"][:n] == 0.0) and np.all(arrs["uy"][:n] == 0.0)
+    assert np.all(arrs["uz"][:n] == gamma * (0.0 - beta * 1.0) * workloads.C)
+    dv = np.prod([(prob_hi[d] - prob_lo[d]) / n_cell[d] for d in range(3)]) / np.prod(ppc)
+    assert np.allclose(arrs["w"][:n], gamma * 2.e23 * dv, rtol=1e-14)
+    # every particle lies behind the lab-frame plasma edge, and the edge moves with -beta c
+    z_lab = gamma * (arrs["z"][:n] + beta * workloads.C * t)
+    assert z_lab.min() >= 0.0 and z_lab.max() < 3.e-3
+    dz = (prob_hi[2] - prob_lo[2]) / n_cell[2]
+    assert arrs["z"][:n].min() < -beta * workloads.C * t + dz
+    # the lab-frame injector over the same box creates more particles (no edge inside the box at t = 0 ... )
+    lab = abi.make_injector(ppc, (-20.e-6, -20.e-6, -1.0), (20.e-6, 11.e-6, 1.0), 2.e23, True)
+    s2, arrs2, _ = _host_soa(cap)
+    n_lab = hh.pic_add_plasma(C.byref(lab), C.byref(geom), None, None, None, abi.dbl3(prob_lo), abi.dbl3(prob_hi), C.byref(s2), cap, 0, t, None)
+    assert n_lab > n and np.all(arrs2["uz"][:n_lab] == 0.0)
+
+
 def _host_soa(n):
     arrs = {k: np.full(n, np.nan) for k in ("x", "y", "z", "w", "ux", "uy", "uz")}
     ids = np.zeros(n, dtype=np.uint64)
@@ -183,11 +276,11 @@ def test_add_plasma_matches_oracle(orc, hh, ppc, slab):
     cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
     s, arrs, ids = _host_soa(cap + 5)
     s.np = 5                                  # appended after the particles already present
-    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s), cap + 5, 1000, None)
+    n = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s), cap + 5, 1000, 0.0, None)
     assert n >= 0, hh.pic_last_error().decode()
     B = [np.empty(cap) for _ in range(4)]
     dp = lambda a: a.ctypes.data_as(abi.c_double_p)   # noqa: E731
-    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(plo), abi.dbl3(phi), *[dp(b) for b in B], cap)
+    m = orc.lib().orc_add_plasma(C.byref(inj), C.byref(geom), abi.dbl3(plo), abi.dbl3(phi), *[dp(b) for b in B], cap, 0.0, None)
     assert m == n and n > 0
     for k, b in zip(("x", "y", "z", "w"), B):
         assert np.array_equal(arrs[k][5:5 + n], b[:n]), k
@@ -201,11 +294,11 @@ def test_add_plasma_capacity_and_empty(hh):
     geom = abi.make_geom((4, 4, 4), (0, 0, 0), (1, 1, 1), periodic=(1, 1, 0))
     inj = abi.make_injector((1, 1, 1), (0, 0, 0), (1, 1, 1), 1.0, True)
     s, arrs, ids = _host_soa(10)
-    assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == -1
+    assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, 0.0, None) == -1
     assert b"capacity" in hh.pic_last_error()
     # a slab that lies outside the plasma bounds adds nothing
     inj2 = abi.make_injector((1, 1, 1), (0, 0, 2.0), (1, 1, 3.0), 1.0, True)
-    assert hh.pic_add_plasma(C.byref(inj2), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, None) == 0
+    assert hh.pic_add_plasma(C.byref(inj2), C.byref(geom), None, None, None, abi.dbl3((0, 0, 0)), abi.dbl3((1, 1, 1)), C.byref(s), 10, 0, 0.0, None) == 0
 
 
 @pytest.mark.parametrize("pbc_z", [("absorbing", "absorbing"), ("reflecting", "absorbing")])
@@ -362,17 +455,17 @@ def test_add_plasma_on_slabs_equals_single_box(orc, hh, ppc):
     cap = n_cell[0] * n_cell[1] * n_cell[2] * ppc[0] * ppc[1] * ppc[2]
     for plo, phi in ((list(prob_lo), list(prob_hi)), ([prob_lo[0], prob_lo[1], prob_hi[2] - dz], list(prob_hi))):
         s1, a1, id1 = _host_soa(cap)
-        n1 = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s1), cap, 0, None)
+        n1 = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), C.byref(s1), cap, 0, 0.0, None)
         assert n1 > 0
-        assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, None) == n1
+        assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, None, None, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, 0.0, None) == n1
         got = {k: [] for k in ("x", "y", "z", "w")}
         ids, first = [], 0
         for klo, khi in ((0, 7), (8, 15)):
             blo, bhi = abi.int3((0, 0, klo)), abi.int3((n_cell[0] - 1, n_cell[1] - 1, khi))
             s2, a2, id2 = _host_soa(cap)
-            m = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), C.byref(s2), cap, first, None)
+            m = hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), C.byref(s2), cap, first, 0.0, None)
             assert m >= 0
-            assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, None) == m
+            assert hh.pic_add_plasma(C.byref(inj), C.byref(geom), None, blo, bhi, abi.dbl3(plo), abi.dbl3(phi), None, 0, 0, 0.0, None) == m
             for k in got:
                 got[k].append(a2[k][:m])
             ids.append(id2[:m])

@@ -268,6 +268,8 @@ def make_lwfa_oracle(orc, wl, kind="restated"):
                         use_filter=wl["use_filter"], kind=kind, solver=wl["solver"], pusher=wl["pusher"])
     sim.set_boundaries(abi.make_boundaries(wl["field_lo"], wl["field_hi"]))
     sim.set_moving_window(wl["moving_window_dir"], wl["moving_window_v"])
+    if wl.get("gamma_boost", 1.0) > 1.0:
+        sim.set_boost(wl["gamma_boost"])
     for s in wl["species"]:
         sim.add_plasma(s["q"], s["m"], abi.make_injector(s["ppc"], s["bound_lo"], s["bound_hi"], s["density"],
                                                          s["do_continuous_injection"]))
@@ -405,6 +407,97 @@ def test_shift_fab_known_answers(orc):
         # (rows below the periodic duplicate j = N: the oracle fills from the owner of a location)
         klo, vyo = ng[2], slice(ng[1], ng[1] + n[1])
         assert np.array_equal(f.a[klo - 1:khi, vyo, ng[0] - 1], b0[klo:khi + 1, vyo, ng[0] - 1 + n[0]])
+
+
+def test_boosted_antenna_emits_the_lorentz_transformed_wave(orc):
+    """Known answer for the boosted-frame antenna (LaserParticleContainer.cpp:183-197,573-579,775,908-915):
+    a plane-wave-like antenna (huge waist) in vacuum, frame boosted by gamma = 5 along the propagation
+    direction.  The forward wave must have the Doppler-shifted wavelength lambda gamma (1 + beta) and the
+    amplitude e_max / (gamma (1 + beta)); the antenna itself drifts with -beta c."""
+    gb = 5.0
+    beta = abi.beta_of_gamma(gb)
+    doppler = gb * (1 + beta)
+    lam, e0 = 0.8e-6, 1.e12
+    dz, nz, nx = lam * doppler / 20, 1024, 4
+    zlo = -160.e-6
+    sim = orc.OracleSim((nx, nx, nz), (-nx * dz / 2, -nx * dz / 2, zlo), (nx * dz / 2, nx * dz / 2, zlo + nz * dz), nox=1, cfl=1.0)
+    sim.set_boundaries(abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec")))
+    sim.set_boost(gb)
+    sim.add_laser(abi.make_laser((0, 0, -1.e-7), (0, 0, 1), (1, 0, 0), lam, e0, 1.0, 10.e-15, 30.e-15, 0.0))
+    nsteps = 600
+    sim.evolve(nsteps)
+    d, ex = sim.fab(0)
+    line = ex[d.ng[2]:-d.ng[2], d.ng[1], d.ng[0]]
+    k0 = int((0 - zlo) / dz) + 5                       # ahead of where the antenna started: the forward wave
+    k = k0 + int(np.argmax(np.abs(line[k0:])))
+    assert abs(abs(line[k]) * doppler / e0 - 1.0) < 0.02
+    seg = line[k - 60:k + 60]
+    zc = np.where(np.diff(np.sign(seg)) != 0)[0]
+    assert abs(2 * np.mean(np.diff(zc)) * dz / (lam * doppler) - 1.0) < 0.02
+    # emitted at lab time t_peak from the drifting antenna, then propagated at c
+    t = sim.time()
+    t_emit = gb * (30.e-15 - beta * (-1.e-7) / workloads.C)
+    z_expect = -1.e-7 / gb - beta * workloads.C * t_emit + workloads.C * (t - t_emit)
+    assert abs((zlo + k * dz) - z_expect) < 0.5 * lam * doppler
+    P = sim.laser_particles(0)
+    assert np.allclose(P["z"], -1.e-7 / gb - beta * workloads.C * t, rtol=1e-10)
+
+
+def test_boosted_continuous_injection_continues_the_lattice(orc):
+    """Known answer for AddPlasma + MoveWindow in a boosted frame (PhysicalParticleContainer.cpp:138-148,
+    1017-1022,1209-1247; WarpXMovingWindow.cpp:108-133,156): the plasma, at rest in the lab, streams with
+    -beta c; the injection front follows it, so the planes injected step after step continue ONE regular
+    lattice; density x gamma; the lab-frame edge z_lab = 0 sits at z = -beta c t."""
+    wl = workloads.laser_acceleration_boosted_3d(n_cell=(8, 8, 64), density=1.e20)   # tenuous: fields stay ~0
+    wl["lasers"] = []
+    for sp in wl["species"]:                           # semi-infinite plasma: z_lab >= 0
+        sp["bound_hi"] = sp["bound_hi"][:2] + (float("inf"),)
+    sim = make_lwfa_oracle(orc, wl)
+    gb, beta = wl["gamma_boost"], abi.beta_of_gamma(wl["gamma_boost"])
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+    assert sim.L.orc_sim_np(sim.h, 0) == 0            # the domain starts behind the plasma edge
+    nsteps = 30
+    sim.evolve(nsteps)
+    t = sim.time()
+    plo, phi = sim.prob_domain()
+    assert round((phi[2] - wl["prob_hi"][2]) / dx[2]) == nsteps       # the window moves with c: one cell per step (CKC, cfl 1)
+    for isp in (0, 1):
+        P = sim.particles(isp)
+        planes = np.unique(np.round(P["z"] / dx[2], 6))
+        assert len(P["z"]) == len(planes) * 8 * 8 - 0 * isp and len(planes) >= 2 * nsteps - 2
+        assert np.allclose(np.diff(planes), 1.0, atol=1e-5)           # one lattice across all injection seams
+        assert np.allclose(P["uz"], -gb * beta * workloads.C, rtol=1e-9) and np.max(np.abs(P["ux"])) < 1e-6
+        assert np.allclose(P["w"], gb * 1.e20 * dx[0] * dx[1] * dx[2], rtol=1e-13)
+        z_lab = gb * (P["z"] + beta * workloads.C * t)
+        assert z_lab.min() >= -1e-9 * dx[2] * gb and P["z"].min() < -beta * workloads.C * t + dx[2]
+        assert P["z"].max() > phi[2] - 2 * dx[2]           # floor() of the uncovered length + the cell centre
+    assert np.array_equal(sim.particles(0)["z"], sim.particles(1)["z"])
+    # the deck's plasma ends at z_lab = 3 mm: a slab of 3 mm / gamma in the boosted frame
+    wl = workloads.laser_acceleration_boosted_3d(n_cell=(8, 8, 64), density=1.e20)
+    wl["lasers"] = []
+    sim = make_lwfa_oracle(orc, wl)
+    sim.evolve(nsteps)
+    z_lab = gb * (sim.particles(0)["z"] + beta * workloads.C * sim.time())
+    assert z_lab.min() >= -1e-9 * dx[2] * gb and 0.003 - gb * dx[2] < z_lab.max() < 0.003
+
+
+def test_boosted_deck_runs_and_stays_quiet_ahead_of_the_laser(orc):
+    """The boosted laser-acceleration deck (workloads.laser_acceleration_boosted_3d): 40 steps of CKC + Vay +
+    order 3 + filter + moving window + boosted antenna + two continuously injected species.  Sanity: finite,
+    the laser field is there with the boosted amplitude scale, the neutral plasma carries the current
+    of the wake only (|jz| of the two streaming species cancels to << n q beta c)."""
+    wl = workloads.laser_acceleration_boosted_3d()
+    sim = make_lwfa_oracle(orc, wl)
+    sim.evolve(40)
+    gb, beta = wl["gamma_boost"], abi.beta_of_gamma(wl["gamma_boost"])
+    d, ey = sim.fab(1)
+    assert np.all(np.isfinite(ey))
+    emax = np.max(np.abs(ey))
+    assert 0.05 < emax * gb * (1 + beta) / 2.e12 < 1.5
+    d, jz = sim.fab(8)
+    stream = wl["species"][0]["density"] * gb * workloads.Q_E * beta * workloads.C
+    assert np.max(np.abs(jz)) < 0.2 * stream
+    assert sim.L.orc_sim_np(sim.h, 0) == sim.L.orc_sim_np(sim.h, 1) > 0
 
 
 def test_particle_energy_known_answer_and_conservation(orc):

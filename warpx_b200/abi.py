@@ -59,12 +59,13 @@ class pic_laser_antenna(C.Structure):
     _fields_ = [("position", C.c_double * 3), ("nvec", C.c_double * 3), ("p_X", C.c_double * 3),
                 ("wavelength", C.c_double), ("e_max", C.c_double), ("waist", C.c_double),
                 ("duration", C.c_double), ("t_peak", C.c_double), ("focal_distance", C.c_double),
-                ("phi0", C.c_double)]
+                ("phi0", C.c_double), ("gamma_boost", C.c_double), ("beta_boost", C.c_double)]
 
 
 class pic_plasma_injector(C.Structure):
     _fields_ = [("ppc", C.c_int * 3), ("bound_lo", C.c_double * 3), ("bound_hi", C.c_double * 3),
-                ("density", C.c_double), ("do_continuous_injection", C.c_int)]
+                ("density", C.c_double), ("do_continuous_injection", C.c_int),
+                ("gamma_boost", C.c_double), ("beta_boost", C.c_double)]
 
 
 FIELD_PERIODIC, FIELD_PEC = 0, 1
@@ -86,9 +87,16 @@ def make_boundaries(field_lo, field_hi, particle_lo=None, particle_hi=None):
     return b
 
 
+def beta_of_gamma(gamma_boost):
+    """ReadBoostedFrameParameters (Source/Utils/WarpXUtil.cpp:114-121)."""
+    import math
+    return math.sqrt(1.0 - 1.0 / gamma_boost ** 2.0) if gamma_boost > 1.0 else 0.0
+
+
 def make_laser(position, direction, polarization, wavelength, e_max, waist, duration, t_peak,
-               focal_distance, phi0=0.0):
+               focal_distance, phi0=0.0, gamma_boost=1.0):
     a = pic_laser_antenna()
+    a.gamma_boost, a.beta_boost = float(gamma_boost), beta_of_gamma(gamma_boost)
     for d in range(3):
         a.position[d], a.nvec[d], a.p_X[d] = float(position[d]), float(direction[d]), float(polarization[d])
     a.wavelength, a.e_max, a.waist, a.duration = float(wavelength), float(e_max), float(waist), float(duration)
@@ -96,8 +104,9 @@ def make_laser(position, direction, polarization, wavelength, e_max, waist, dura
     return a
 
 
-def make_injector(ppc, bound_lo, bound_hi, density, do_continuous_injection=False):
+def make_injector(ppc, bound_lo, bound_hi, density, do_continuous_injection=False, gamma_boost=1.0):
     inj = pic_plasma_injector()
+    inj.gamma_boost, inj.beta_boost = float(gamma_boost), beta_of_gamma(gamma_boost)
     for d in range(3):
         inj.ppc[d] = int(ppc[d])
         inj.bound_lo[d], inj.bound_hi[d] = float(bound_lo[d]), float(bound_hi[d])
@@ -115,7 +124,7 @@ def LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp):
         "pic_laser_antenna_info": (C.c_int, [lp, dp, dp]),
         "pic_laser_antenna_particles": (C.c_long, [lp, dp, dp, dp, vp, vp, vp, vp, C.c_long]),
         "pic_laser_antenna_push": (C.c_int, [lp, dp, soap, C.c_double, C.c_double, vp]),
-        "pic_add_plasma": (C.c_long, [jp, gp, dp, ip, ip, dp, dp, soap, C.c_long, C.c_uint64, vp]),
+        "pic_add_plasma": (C.c_long, [jp, gp, dp, ip, ip, dp, dp, soap, C.c_long, C.c_uint64, C.c_double, vp]),
         "pic_particles_owned_weights": (C.c_int, [soap, dp, dp, vp, vp]),
         "pic_deposit_charge": (C.c_int, [soap, C.c_long, C.c_long, fabp, dp, dp, ip, C.c_double, C.c_int, vp]),
         "pic_apply_pec_rho": (C.c_int, [fabp, gp, bp, vp]),

@@ -93,6 +93,7 @@ struct Engine {
     bool do_moving_window = false;
     int mw_dir = 2;
     double mw_v = 0.0, mw_x = 0.0;               // moving_window_v [m/s], moving_window_x
+    double gamma_boost = 1.0, beta_boost = 0.0;  // warpx.gamma_boost, boost_direction = z
     double cur_time = 0.0;                       // t_new[0]
     double* shift_tmp = nullptr;                 // one component-sized scratch array
     size_t shift_tmp_bytes = 0;
@@ -423,14 +424,24 @@ static int shift_component(Engine& e, int c, int num_shift, void* s) {
     return pic_shift_fab(&e.fab[c], e.shift_tmp, &e.geom, num_shift, e.mw_dir, 0.0 /* no external field */, s);
 }
 
-// WarpX::MoveWindow (Utils/WarpXMovingWindow.cpp:139-476), one level, lab frame, no PML: advance
+// WarpX::MoveWindow (Utils/WarpXMovingWindow.cpp:139-476), one level, lab or z-boosted frame, no PML: advance
 // moving_window_x; when it has covered whole cells shift E, B (and J when move_j), move the problem
 // domain, and let the continuously injected species fill the uncovered slab.
 static int move_window(Engine& e, bool move_j, int* num_moved, void* s) {
     *num_moved = 0;
     if (!e.do_moving_window) return 0;
     const int dir = e.mw_dir;
-    e.mw_x += (e.mw_v - 0.0 * C_LIGHT) / (1 - e.mw_v * 0.0 / C_LIGHT) * e.dt;            // :155 (beta_boost = 0)
+    e.mw_x += (e.mw_v - e.beta_boost * C_LIGHT) / (1 - e.mw_v * e.beta_boost / C_LIGHT) * e.dt;   // :156
+    // UpdateInjectionPosition (:59-136): a plasma at rest in the lab drifts with -beta_boost c in the
+    // boosted frame (v' = (v - c beta) / (1 - v beta / c) with v = 0, times boost_direction[dir])
+    if (e.gamma_boost > 1.)
+        for (auto& sp : e.species) {
+            if (!sp.has_injector || !sp.inj.do_continuous_injection) continue;
+            double v_shift = 0.0;
+            v_shift = (v_shift - C_LIGHT * e.beta_boost) / (1. - v_shift * e.beta_boost / C_LIGHT);
+            v_shift *= (dir == 2) ? 1 : 0;
+            sp.current_injection_position += v_shift * e.dt;
+        }
     const double cdx = e.dx[dir];
     const int nsb = static_cast<int>((e.mw_x - e.geom.prob_lo[dir]) / cdx);              // :171
     if (nsb == 0) return 0;
@@ -463,8 +474,9 @@ static int move_window(Engine& e, bool move_j, int* num_moved, void* s) {
             pic_soa& P = sp.buf[sp.cur];
             // every rank advances the id counter by the global count; the rank whose brick contains the
             // slab creates the particles (tile_realbox.contains, :1141-1156)
-            const long total = pic_add_plasma(&sp.inj, &e.geom, e.dx, nullptr, nullptr, plo, phi, nullptr, 0, 0, s);
-            const long added = pic_add_plasma(&sp.inj, &e.geom, e.dx, e.box_lo, e.box_hi, plo, phi, &P, sp.capacity, sp.next_id, s);
+            const long total = pic_add_plasma(&sp.inj, &e.geom, e.dx, nullptr, nullptr, plo, phi, nullptr, 0, 0, e.cur_time, s);
+            const long added = pic_add_plasma(&sp.inj, &e.geom, e.dx, e.box_lo, e.box_hi, plo, phi, &P, sp.capacity, sp.next_id,
+                                              e.cur_time /* t_new, already advanced (WarpXEvolve.cpp:232-246) */, s);
             if (added < 0 || total < 0) return 1;
             P.np += added;
             sp.next_id += (uint64_t)total;
@@ -737,14 +749,29 @@ extern "C" int pic_engine_set_moving_window(void* h, int dir, double v_over_c) {
     guard_cells(*e);
     return 0;
 }
+// warpx.gamma_boost (Source/Utils/WarpXUtil.cpp:114-121) with warpx.boost_direction = z
+extern "C" int pic_engine_set_boost(void* h, double gamma_boost, double beta_boost) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(gamma_boost >= 1. && beta_boost >= 0. && beta_boost < 1., "pic_engine_set_boost: need gamma_boost >= 1 and 0 <= beta_boost < 1");
+    PIC_REQUIRE((gamma_boost > 1.) == (beta_boost > 0.), "pic_engine_set_boost: gamma_boost and beta_boost disagree");
+    PIC_REQUIRE(e->lasers.empty(), "pic_engine_set_boost: call before pic_engine_add_laser");
+    for (auto& sp : e->species) PIC_REQUIRE(!sp.has_injector, "pic_engine_set_boost: call before pic_engine_set_injector");
+    e->gamma_boost = gamma_boost; e->beta_boost = beta_boost;
+    return 0;
+}
+static bool same_boost(const Engine& e, double gamma_boost, double beta_boost) {
+    const bool boosted = gamma_boost > 1.;
+    return boosted ? (gamma_boost == e.gamma_boost && beta_boost == e.beta_boost) : !(e.gamma_boost > 1.);
+}
 extern "C" int pic_engine_set_injector(void* h, int isp, const pic_plasma_injector* inj) {
     Engine* e = static_cast<Engine*>(h);
     PIC_REQUIRE(isp >= 0 && isp < (int)e->species.size(), "pic_engine_set_injector: no species %d", isp);
+    PIC_REQUIRE(same_boost(*e, inj->gamma_boost, inj->beta_boost), "pic_engine_set_injector: the injector's gamma_boost / beta_boost differ from pic_engine_set_boost");
     Species& sp = e->species[isp];
     sp.has_injector = true; sp.inj = *inj;
     // ids continue after the particles the injector created at start-up on ALL ranks
     const long created = pic_add_plasma(inj, &e->geom, e->dx, nullptr, nullptr, e->geom.prob_lo, e->geom.prob_hi,
-                                        nullptr, 0, 0, nullptr);
+                                        nullptr, 0, 0, 0.0, nullptr);
     PIC_REQUIRE(created >= 0, "pic_engine_set_injector: bad injector");
     sp.next_id = (uint64_t)created;
     if (e->do_moving_window)                            // WarpX.cpp:288-307
@@ -754,6 +781,7 @@ extern "C" int pic_engine_set_injector(void* h, int isp, const pic_plasma_inject
 extern "C" int pic_engine_add_laser(void* h, const pic_laser_antenna* prm, const pic_soa* p, long capacity) {
     Engine* e = static_cast<Engine*>(h);
     double info[4];
+    PIC_REQUIRE(same_boost(*e, prm->gamma_boost, prm->beta_boost), "pic_engine_add_laser: the antenna's gamma_boost / beta_boost differ from pic_engine_set_boost");
     ENG_CALL(pic_laser_antenna_info(prm, e->dx, info));
     PIC_REQUIRE(capacity >= p->np, "pic_engine_add_laser: capacity %ld < np %ld", capacity, (long)p->np);
     Laser L;

@@ -98,14 +98,26 @@ __global__ void compact_move_kernel(CompactArgs a) {
 struct AntennaSetup {
     double nvec[3], p_X[3], p_Y[3], u_X[3], u_Y[3];
     double S_X, S_Y, mobility, weight;
+    double position[3];              // in the simulation frame
+    double Z0_lab, gamma_boost, beta_boost;
 };
 
 // LaserParticleContainer ctor (:179-211, 3D: u_X = p_X, u_Y = p_Y = nvec x p_X), ComputeSpacing
-// (:727-761), ComputeWeightMobility (:763-781); lab frame.
+// (:727-761), ComputeWeightMobility (:763-781); in a frame boosted along nvec the plane moves to
+// Z0 / gamma_boost (:183-197) and the mobility is divided by gamma_boost (:775).
 static AntennaSetup antenna_setup(const pic_laser_antenna& in, const double dx[3]) {
     AntennaSetup a;
     double s = 1.0 / std::sqrt(in.nvec[0] * in.nvec[0] + in.nvec[1] * in.nvec[1] + in.nvec[2] * in.nvec[2]);
-    for (int d = 0; d < 3; ++d) a.nvec[d] = in.nvec[d] * s;
+    for (int d = 0; d < 3; ++d) { a.nvec[d] = in.nvec[d] * s; a.position[d] = in.position[d]; }
+    const bool boosted = in.gamma_boost > 1.;
+    a.gamma_boost = boosted ? in.gamma_boost : 1.0;
+    a.beta_boost = boosted ? in.beta_boost : 0.0;
+    a.Z0_lab = 0.0;
+    if (boosted) {
+        a.Z0_lab = a.nvec[0] * a.position[0] + a.nvec[1] * a.position[1] + a.nvec[2] * a.position[2];
+        const double Z0_boost = a.Z0_lab / in.gamma_boost;
+        for (int d = 0; d < 3; ++d) a.position[d] += (Z0_boost - a.Z0_lab) * a.nvec[d];
+    }
     s = 1.0 / std::sqrt(in.p_X[0] * in.p_X[0] + in.p_X[1] * in.p_X[1] + in.p_X[2] * in.p_X[2]);
     for (int d = 0; d < 3; ++d) a.p_X[d] = in.p_X[d] * s;
     const double* n = a.nvec; const double* p = a.p_X;
@@ -119,6 +131,7 @@ static AntennaSetup antenna_setup(const pic_laser_antenna& in, const double dx[3
     a.mobility = 0.05 / in.e_max;
     a.weight = EP0 / a.mobility;
     a.weight *= 1.0 * a.S_X * a.S_Y;
+    if (boosted) a.mobility = a.mobility / in.gamma_boost;
     return a;
 }
 
@@ -226,6 +239,8 @@ extern "C" int pic_shift_fab(const pic_fab* f, double* tmp, const pic_geom* g, i
 // ---------------------------------------------------------------------------------------------
 extern "C" int pic_laser_antenna_info(const pic_laser_antenna* prm, const double dx[3], double out[4]) {
     PIC_REQUIRE(prm->e_max > 0 && prm->wavelength > 0, "pic_laser_antenna: e_max and wavelength must be > 0");
+    PIC_REQUIRE(!(prm->gamma_boost > 1.) || (prm->beta_boost > 0. && prm->beta_boost < 1.),
+                "pic_laser_antenna: gamma_boost > 1 needs 0 < beta_boost < 1");
     const AntennaSetup a = antenna_setup(*prm, dx);
     const double dp = a.nvec[0] * a.p_X[0] + a.nvec[1] * a.p_X[1] + a.nvec[2] * a.p_X[2];
     PIC_REQUIRE(std::abs(dp) < 1.0e-14, "Laser plane vector is not perpendicular to the main polarization vector");
@@ -239,7 +254,7 @@ extern "C" long pic_laser_antenna_particles(const pic_laser_antenna* prm, const 
                                             const double box_hi[3], double* x, double* y, double* z, double* w,
                                             long capacity) {
     const AntennaSetup a = antenna_setup(*prm, dx);
-    const double* pos0 = prm->position;
+    const double* pos0 = a.position;
     int plane_lo[2] = {std::numeric_limits<int>::max(), std::numeric_limits<int>::max()};
     int plane_hi[2] = {std::numeric_limits<int>::min(), std::numeric_limits<int>::min()};
     for (int c = 0; c < 8; ++c) {
@@ -272,10 +287,12 @@ extern "C" long pic_laser_antenna_particles(const pic_laser_antenna* prm, const 
 // One step of the antenna particles at time t (beginning of the step), LaserParticleContainer::Evolve
 // :614-626: plane coordinates, Gaussian amplitude, u and x update.
 extern "C" int pic_laser_antenna_push(const pic_laser_antenna* prm, const double dx[3], const pic_soa* p,
-                                      double t, double dt, void* stream) {
+                                      double t_sim, double dt, void* stream) {
     if (p->np == 0) return 0;
     using cplx = std::complex<double>;
     const AntennaSetup s = antenna_setup(*prm, dx);
+    // boosted frame: the profile is evaluated at the lab time of the antenna plane (:573-579)
+    const double t = s.gamma_boost > 1. ? 1. / s.gamma_boost * t_sim + s.beta_boost * s.Z0_lab / C_LIGHT : t_sim;
     const cplx I(0.0, 1.0);
     constexpr double pi = 3.14159265358979323846;
     const double k0 = 2.0 * pi / prm->wavelength;
@@ -292,7 +309,8 @@ extern "C" int pic_laser_antenna_push(const pic_laser_antenna* prm, const double
     LaserArgs a;
     a.P = make_soa(*p, 0);
     a.np = p->np;
-    for (int d = 0; d < 3; ++d) { a.pos[d] = prm->position[d]; a.uX[d] = s.u_X[d]; a.uY[d] = s.u_Y[d]; a.pX[d] = s.p_X[d]; }
+    for (int d = 0; d < 3; ++d) { a.pos[d] = s.position[d]; a.uX[d] = s.u_X[d]; a.uY[d] = s.u_Y[d]; a.pX[d] = s.p_X[d]; a.nvec[d] = s.nvec[d]; }
+    a.gamma_boost = s.gamma_boost; a.beta_boost = s.beta_boost;
     a.stc_re = stc.real(); a.stc_im = stc.imag();
     a.icw_re = inv_complex_waist_2.real(); a.icw_im = inv_complex_waist_2.imag();
     a.mobility = s.mobility; a.dt = dt;
@@ -331,7 +349,15 @@ extern "C" int pic_particles_owned_weights(const pic_soa* p, const double own_lo
 extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g, const double cell_size[3],
                                const int box_lo[3], const int box_hi[3], const double part_lo[3],
                                const double part_hi[3], const pic_soa* p, long capacity, uint64_t first_id,
-                               void* stream) {
+                               double t, void* stream) {
+    const bool boosted = inj->gamma_boost > 1.;
+    if (boosted && !(inj->beta_boost > 0. && inj->beta_boost < 1.)) { fail("pic_add_plasma: gamma_boost > 1 needs 0 < beta_boost < 1"); return -1; }
+    const double gamma_boost = boosted ? inj->gamma_boost : 1.0, beta_boost = boosted ? inj->beta_boost : 0.0;
+    // applyBallisticCorrection (:138-148) for a plasma at rest in the lab (betaz_bulk = 0): the lab-frame z
+    // the bounds are tested at; the identity in the lab frame
+    auto lab = [&](int d, double z) {
+        return d == 2 ? gamma_boost * (z * (1.0 - beta_boost * 0.0) - C_LIGHT * t * (0.0 - beta_boost)) : z;
+    };
     double dx[3], tile_lo[3], tile_hi[3], ov_lo[3], ov_hi[3];
     int nov[3];
     for (int d = 0; d < 3; ++d) {
@@ -366,7 +392,7 @@ extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g
         int m_lo = -1, m_hi = -2;
         bool closed = false;
         for (int cell = 0; cell < nov[d]; ++cell) {
-            const double lo = ov_lo[d] + (cell + 0.0) * dx[d], hi = ov_lo[d] + (cell + 1.0) * dx[d];
+            const double lo = lab(d, ov_lo[d] + (cell + 0.0) * dx[d]), hi = lab(d, ov_lo[d] + (cell + 1.0) * dx[d]);   // :1017-1022
             const bool overlaps = inj->bound_lo[d] <= hi && inj->bound_hi[d] >= lo;
             const double tp[3] = {lo, (lo + hi) / 2.0, hi};
             bool any = false;
@@ -374,8 +400,9 @@ extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g
             for (int ip = 0; ip < ppc; ++ip) {
                 const double r = (0.5 + ip) / ppc;
                 const double pos = ov_lo[d] + (cell + r) * dx[d];
+                const double pos_lab = lab(d, pos);                                 // z0 / z0_lab (:1184,1211)
                 const bool ok = overlaps && any && tile_lo[d] < pos && pos < tile_hi[d] &&
-                                pos < inj->bound_hi[d] && pos >= inj->bound_lo[d];
+                                pos_lab < inj->bound_hi[d] && pos_lab >= inj->bound_lo[d];
                 const int m = cell * ppc + ip;
                 if (ok) {
                     if (closed) { fail("pic_add_plasma: the admitted lattice points along %d are not contiguous", d); return -1; }
@@ -399,7 +426,15 @@ extern "C" long pic_add_plasma(const pic_plasma_injector* inj, const pic_geom* g
     a.id = p->idcpu ? p->idcpu + p->np : nullptr;
     a.id0 = first_id;
     const long pcount = (long)inj->ppc[0] * inj->ppc[1] * inj->ppc[2];
-    a.weight = inj->density;
+    double dens = inj->density, uz = 0.0;
+    if (boosted) {                                        // Lorentz transform of a plasma at rest (:1232-1246)
+        const double gamma_lab = std::sqrt(1. + (0.0 * 0.0 + 0.0 * 0.0 + uz * uz));
+        const double betaz_lab = uz / (gamma_lab);
+        dens = gamma_boost * dens * (1.0 - beta_boost * betaz_lab);
+        uz = gamma_boost * (uz - beta_boost * gamma_lab);
+    }
+    a.uz = uz * C_LIGHT;                                  // :1275-1277
+    a.weight = dens;
     a.weight *= dx[0] * dx[1] * dx[2] / pcount;           // compute_scale_fac_volume (AddPlasmaUtilities.H:73-77)
     PIC_LAUNCH(inject_kernel, inject_body, a, a.total, stream);
     return launched_ok("pic_add_plasma") ? count : -1;

@@ -149,6 +149,7 @@ struct LaserArgs {
     double pos[3], uX[3], uY[3], pX[3];
     double stc_re, stc_im, icw_re, icw_im;
     double mobility, dt;
+    double nvec[3], gamma_boost, beta_boost;     // boosted frame (gamma_boost = 1, beta_boost = 0 in the lab)
 };
 
 PIC_HD void laser_body(long ip, const LaserArgs& a) {
@@ -163,10 +164,15 @@ PIC_HD void laser_body(long ip, const LaserArgs& a) {
     const double amplitude = a.stc_re * cr - a.stc_im * ci;
     const double sign_charge = (a.P.w[ip] > 0) ? -1.0 : 1.0;
     const double v_over_c = sign_charge * a.mobility * amplitude;
-    const double vx = C_LIGHT * v_over_c * a.pX[0];
-    const double vy = C_LIGHT * v_over_c * a.pX[1];
-    const double vz = C_LIGHT * v_over_c * a.pX[2];
-    const double gamma = 1.0 / sqrt(1. - v_over_c * v_over_c);
+    double vx = C_LIGHT * v_over_c * a.pX[0];
+    double vy = C_LIGHT * v_over_c * a.pX[1];
+    double vz = C_LIGHT * v_over_c * a.pX[2];
+    if (a.gamma_boost > 1.) {                    // the antenna drifts with the lab (LaserParticleContainer.cpp:908-912)
+        vx -= C_LIGHT * a.beta_boost * a.nvec[0];
+        vy -= C_LIGHT * a.beta_boost * a.nvec[1];
+        vz -= C_LIGHT * a.beta_boost * a.nvec[2];
+    }
+    const double gamma = a.gamma_boost / sqrt(1. - v_over_c * v_over_c);    // :914-915
     a.P.ux[ip] = gamma * vx; a.P.uy[ip] = gamma * vy; a.P.uz[ip] = gamma * vz;
     a.P.x[ip] = x + vx * a.dt; a.P.y[ip] = y + vy * a.dt; a.P.z[ip] = z + vz * a.dt;
 }
@@ -183,7 +189,7 @@ struct InjectArgs {
     uint64_t id0;
     double ov_lo[3], dx[3];
     int ppc[3], c0[3], nc[3], m_lo[3], m_hi[3];
-    double weight;
+    double weight, uz;               // uz = -gamma_boost beta_boost c in a boosted frame, 0 in the lab
     long total;
 };
 
@@ -232,7 +238,7 @@ PIC_HD void inject_body(long t, const InjectArgs& a) {
     a.P.y[slot] = cell_coord(a.ov_lo[1], iv[1] + r[1], a.dx[1]);
     a.P.z[slot] = cell_coord(a.ov_lo[2], iv[2] + r[2], a.dx[2]);
     a.P.w[slot] = a.weight;
-    a.P.ux[slot] = 0.0; a.P.uy[slot] = 0.0; a.P.uz[slot] = 0.0;
+    a.P.ux[slot] = 0.0; a.P.uy[slot] = 0.0; a.P.uz[slot] = a.uz;
     if (a.id) a.id[slot] = a.id0 + (uint64_t)slot;
 }
 

@@ -180,7 +180,8 @@ class Simulation:
     def __init__(self, n_cell, prob_lo, prob_hi, nox, galerkin=1, pusher=abi.PUSHER_BORIS,
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
                  tile=(8, 8, 8), use_bins=True, device=None, native_driver=True,
-                 use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None, nb=None):
+                 use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None, nb=None,
+                 gamma_boost=1.0):
         """boundaries: abi.pic_boundaries (boundary.field_lo/hi, boundary.particle_lo/hi; default all
         periodic); moving_window: (direction, v/c) == warpx.do_moving_window / moving_window_dir /
         moving_window_v; nb: brick grid (default parallel.brick_grid(world); a moving window needs slabs
@@ -203,6 +204,11 @@ class Simulation:
         self.st = stencil_coefficients(solver, self.dx)
         self.use_filter, self.filter_npass = bool(use_filter), tuple(int(v) for v in filter_npass)
         self.boundaries, self.moving_window = boundaries, moving_window
+        # warpx.gamma_boost with boost_direction = z; prob_lo / prob_hi are boosted-frame values already
+        # (ConvertLabParamsToBoost, Source/Utils/WarpXUtil.cpp:180-262)
+        self.gamma_boost, self.beta_boost = float(gamma_boost), abi.beta_of_gamma(gamma_boost)
+        if self.gamma_boost > 1.0 and not (native_driver and use_bins):
+            raise NotImplementedError("boosted-frame runs need the C++ driver")
         if boundaries is not None:
             for d in range(3):
                 self.geom.periodic[d] = 1 if boundaries.field_lo[d] == abi.FIELD_PERIODIC else 0
@@ -253,6 +259,8 @@ class Simulation:
                 check(self.L.pic_engine_set_boundaries(self.native, C.byref(boundaries)))
             if moving_window is not None:
                 check(self.L.pic_engine_set_moving_window(self.native, int(moving_window[0]), float(moving_window[1])))
+            if self.gamma_boost > 1.0:
+                check(self.L.pic_engine_set_boost(self.native, self.gamma_boost, self.beta_boost))
             g12 = (C.c_int * 12)()
             self.L.pic_engine_guards(self.native, g12)
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
@@ -331,6 +339,7 @@ class Simulation:
         capacity: entries of every particle array (the run must never exceed it)."""
         if not self.native:
             raise NotImplementedError("plasma injectors need the C++ driver")
+        injector.gamma_boost, injector.beta_boost = self.gamma_boost, self.beta_boost
         empty = np.empty(0)
         sp = Species(self, name, q, m, {k: empty for k in Species.NAMES}, int(capacity))
         soa = sp.soa(0)
@@ -341,13 +350,13 @@ class Simulation:
             other = parallel.Decomposition(self.n_cell, self.dec.nb, r)
             cnt = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.int3(other.box_lo),
                                         abi.int3(other.box_hi), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi), None, 0, 0,
-                                        None)
+                                        0.0, None)
             if cnt < 0:
                 raise RuntimeError("pic_b200: " + self.L.pic_last_error().decode())
             first_id += cnt
         n = self.L.pic_add_plasma(C.byref(injector), C.byref(self.geom), abi.dbl3(self.dx), abi.int3(self.box_lo),
                                   abi.int3(self.box_hi), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi), C.byref(soa),
-                                  sp.capacity, first_id, self.stream)
+                                  sp.capacity, first_id, 0.0, self.stream)
         if n < 0:
             raise RuntimeError("pic_b200: " + self.L.pic_last_error().decode())
         sp.np = int(n)
@@ -368,6 +377,7 @@ class Simulation:
         if not self.native:
             raise NotImplementedError("laser antennas need the C++ driver")
         t = self.torch
+        laser.gamma_boost, laser.beta_boost = self.gamma_boost, self.beta_boost
         dxa, lo, hi = abi.dbl3(self.dx), abi.dbl3(self.prob_lo), abi.dbl3(self.prob_hi)
         n = self.L.pic_laser_antenna_particles(C.byref(laser), dxa, lo, hi, None, None, None, None, 0)
         host = np.zeros((7, max(n, 1)))

@@ -153,6 +153,57 @@ def laser_acceleration_3d(n_cell=(32, 32, 256), max_step=100, solver=0, pusher=0
         region_of_interest=(12.0e-6, 13.0e-6))
 
 
+def boosted_domain(prob_lo, prob_hi, gamma_boost, moving_window_v=None, direction=2):
+    """ConvertLabParamsToBoost (Source/Utils/WarpXUtil.cpp:180-262): geometry.prob_lo / prob_hi along the
+    boost direction are lab-frame values in the deck; WarpX multiplies them by
+    1 / (gamma (1 - beta beta_window)), beta_window = moving_window_v / c when the window moves along the
+    boost, else beta."""
+    from . import abi
+    beta = abi.beta_of_gamma(gamma_boost)
+    beta_window = beta if moving_window_v is None else moving_window_v
+    convert_factor = 1.0 / (gamma_boost * (1 - beta * beta_window))
+    lo, hi = list(prob_lo), list(prob_hi)
+    lo[direction] *= convert_factor
+    hi[direction] *= convert_factor
+    return tuple(lo), tuple(hi)
+
+
+def max_step_boost_accelerator(zmax_plasma, zmin_domain_boost, gamma_boost, moving_window_v, dt):
+    """WarpX::computeMaxStepBoostAccelerator (Source/Initialization/WarpXInitData.cpp:820-859):
+    warpx.zmax_plasma_to_compute_max_step -> the step at which the lower end of the (boosted, moving)
+    domain passes the upper end of the plasma."""
+    from . import abi
+    beta = abi.beta_of_gamma(gamma_boost)
+    len_plasma_boost = zmax_plasma / gamma_boost
+    v_plasma_boost = -beta * C
+    interaction_time_boost = (len_plasma_boost - zmin_domain_boost) / (moving_window_v * C - v_plasma_boost)
+    return int(interaction_time_boost / dt)
+
+
+def laser_acceleration_boosted_3d(n_cell=(16, 16, 128), max_step=60, gamma_boost=10.0, density=1.e23):
+    """BASELINE.json config 4 in the small: Examples/Tests/boosted_diags/
+    inputs_test_3d_laser_acceleration_btd (CKC, Vay, order 3, bilinear filter, z moving window at c, PEC in
+    z, Gaussian antenna, electrons + ions at rest in the lab with continuous injection, gamma_boost = 10)
+    without the Gaussian beam (AMReX RNG) and the back-transformed diagnostics, on a grid fine enough for
+    omega_p dt < 1 (the regression deck itself runs at omega_p dt = 4.4).  prob_lo / prob_hi below are the
+    boosted-frame values; everything under species / lasers is lab-frame, as in the deck."""
+    M_P = 1.67262192369e-27
+    lo, hi = boosted_domain((-128.e-6, -128.e-6, -40.e-6), (128.e-6, 128.e-6, 0.0), gamma_boost, 1.0)
+    bounds = dict(bound_lo=(-120.e-6, -120.e-6, 0.0), bound_hi=(120.e-6, 120.e-6, .003))
+    return dict(
+        n_cell=tuple(n_cell), prob_lo=lo, prob_hi=hi, gamma_boost=gamma_boost,
+        field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
+        nox=3, use_filter=True, cfl=1.0, moving_window_dir=2, moving_window_v=1.0, max_step=max_step,
+        solver=1, pusher=1,
+        species=[dict(name="electrons", q=-Q_E, m=M_E, ppc=(1, 1, 1), density=density,
+                      do_continuous_injection=True, **bounds),
+                 dict(name="ions", q=Q_E, m=M_P, ppc=(1, 1, 1), density=density,
+                      do_continuous_injection=True, **bounds)],
+        lasers=[dict(name="laser1", position=(0., 0., -0.1e-6), direction=(0., 0., 1.),
+                     polarization=(0., 1., 0.), e_max=2.e12, waist=45.e-6, duration=20.e-15,
+                     t_peak=40.e-15, focal_distance=0.5e-3, wavelength=0.81e-6)])
+
+
 def staggered_coordinates(fab, prob_lo, dx):
     """x, y, z (numpy, broadcastable to the fab's [k, j, i] array) of every ALLOCATED point of a
     component, as WarpX::ComputeExternalFieldOnGridUsingParser evaluates them
