@@ -241,6 +241,24 @@ int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, const pic_geom
  * 64-88, Source/Filter/Filter.cpp:37-133) as called from WarpXComm.cpp:1357-1374. */
 int pic_apply_filter(const pic_fab* src, const pic_fab* dst, const int npass[3], void* stream);
 
+/* Godfrey's NCI corrector (particles.use_fdtd_nci_corr).
+ * _table_index / _stencil: NCIGodfreyFilter::ComputeStencils (Source/Filter/NCIGodfreyFilter.cpp:49-139) --
+ *   index = clamp(int(tab_length * cdtodz), 0, tab_length - 2); the four coefficients are interpolated between
+ *   line_lo = table[index] and line_hi = table[index + 1] of the caller's copy of the reference's tables
+ *   (Source/Utils/NCIGodfreyTables.H: galerkin / momentum x Ex_Ey_Bz / Bx_By_Ez, tab_length = 101), then combined
+ *   into stencil_z[5] with coefficient 0 halved, i.e. the contents of Filter::m_stencil_2.  A WarpX build skips
+ *   these two and passes the m_stencil_2 it already holds.
+ * pic_apply_nci_filter: PhysicalParticleContainer::applyNCIFilter (Source/Particles/PhysicalParticleContainer.cpp:
+ *   2097-2169) for one component: dst = the 5-point z filter of src over the tile box [tile_lo, tile_hi] (cells)
+ *   grown by `grow` = the particle shape order and converted to the component's index type; src zero-padded
+ *   outside its allocation (Filter::DoFilter, Source/Filter/Filter.cpp:92-133).  Ex, Ey, Bz take the Ex_Ey_Bz
+ *   stencil, Bx, By, Ez the other (:2132-2163).  The gather then reads dst instead of src. */
+int pic_nci_godfrey_table_index(double cdtodz, int tab_length);
+void pic_nci_godfrey_stencil(const double line_lo[4], const double line_hi[4], int index, int tab_length,
+                             double cdtodz, double stencil_z[5]);
+int pic_apply_nci_filter(const pic_fab* src, const pic_fab* dst, const double stencil_z[5], const int tile_lo[3],
+                         const int tile_hi[3], int grow, void* stream);
+
 /* Neighbour (multi-GPU) versions: pack the slab that the neighbour on `side` (0 = low,
  * 1 = high) of dimension `dim` needs, and unpack what it sent.  mode 0 = copy (FillBoundary),
  * mode 1 = sum (SumBoundary).  pic_halo_slab_count returns the number of doubles. */
@@ -424,6 +442,11 @@ int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
 int pic_engine_set_boundaries(void* engine, const pic_boundaries* b);
 int pic_engine_set_moving_window(void* engine, int dir, double v_over_c);
 int pic_engine_set_boost(void* engine, double gamma_boost, double beta_boost);
+/* particles.use_fdtd_nci_corr: the two z stencils (see pic_nci_godfrey_stencil).  Grows the guard cells of E and B
+ * along z (GuardCellManager.cpp:87-90,319-330): call before pic_engine_set_fields, query pic_engine_guards after.
+ * The engine owns the six filtered copies the gather of the main push reads (the half pushes of the first and
+ * last step, PushP, gather from the unfiltered fields like the reference). */
+int pic_engine_set_nci_corrector(void* engine, const double stencil_exeybz[5], const double stencil_bxbyez[5]);
 int pic_engine_set_injector(void* engine, int isp, const pic_plasma_injector* inj);
 int pic_engine_add_laser(void* engine, const pic_laser_antenna* prm, const pic_soa* p, long capacity);
 long pic_engine_laser_np(void* engine, int ilaser);

@@ -100,6 +100,10 @@ def lib(kind="restated"):
         "orc_add_plasma": (C.c_long, [C.POINTER(abi.pic_plasma_injector), gp, dp, dp, dp, dp, dp, dp, C.c_long,
                                       C.c_double, dp]),
         "orc_sim_set_boost": (C.c_int, [vp, C.c_double, C.c_double]),
+        "orc_sim_set_nci_corrector": (C.c_int, [vp, dp, dp]),
+        "orc_nci_table_index": (C.c_int, [C.c_double, C.c_int]),
+        "orc_nci_godfrey_stencil": (None, [dp, dp, C.c_int, C.c_int, C.c_double, dp]),
+        "orc_apply_nci_filter": (None, [C.POINTER(abi.pic_fab), C.POINTER(abi.pic_fab), dp, ip, ip]),
         "orc_apply_particle_boundaries": (None, [soap, gp, C.POINTER(abi.pic_boundaries), C.c_char_p]),
         "orc_antenna_particles": (C.c_long, [C.POINTER(abi.pic_laser_antenna), dp, dp, dp, dp, dp, dp, dp, C.c_long]),
         "orc_sim_rho_checksum": (C.c_double, [vp]),
@@ -215,6 +219,12 @@ class OracleSim:
         rc = self.L.orc_sim_set_boost(self.h, gamma_boost, abi.beta_of_gamma(gamma_boost))
         if rc:
             raise ValueError("orc_sim_set_boost: call before adding species / lasers")
+
+    def set_nci_corrector(self, stencil_exeybz, stencil_bxbyez):
+        """particles.use_fdtd_nci_corr with the two z stencils (m_stencil_2 of the reference's filters)."""
+        rc = self.L.orc_sim_set_nci_corrector(self.h, (C.c_double * 5)(*stencil_exeybz), (C.c_double * 5)(*stencil_bxbyez))
+        if rc:
+            raise ValueError("orc_sim_set_nci_corrector: call before adding species")
 
     def add_plasma(self, q, m, injector):
         self.nspecies += 1

@@ -72,6 +72,8 @@ struct Sim {
     int mw_dir = 2;
     double mw_v = 0.0, mw_x = 0.0;                 // moving_window_v [m/s], moving_window_x
     double gamma_boost = 1.0, beta_boost = 0.0;    // warpx.gamma_boost, boost_direction = z (WarpXUtil.cpp:114-121)
+    bool use_nci = false;                          // particles.use_fdtd_nci_corr
+    double nci_stencil[2][5];                      // [0] Ex Ey Bz, [1] Bx By Ez (m_stencil_2 of the two NCIGodfreyFilter)
     struct Laser { Antenna ant; std::vector<double> a[7]; };
     std::vector<Laser> lasers;
     double t_push = 0, t_dep = 0, t_fdtd = 0, t_halo = 0, t_other = 0;
@@ -93,6 +95,7 @@ void guard_cells(Sim& s) {
         const int ngt = s.nox;                                   // :62-64
         int ng = (ngt % 2) ? ngt + 1 : ngt;                      // :83-85 (even)
         int ngJ = ngt;                                           // :96-98
+        if (s.use_nci && d == 2) { const int n4 = ngt + 4; ng = (n4 % 2) ? n4 + 1 : n4; }   // :87-90, nci_corr_stencil = m_stencil_width = 4
         if (s.do_moving_window) { ng = std::max(ng, 2); ngJ = std::max(ngJ, 2); }   // :103-115 (max_r = 2 on one level)
         s.ng_EB[d] = ng;
         s.ng_J[d] = ngJ + (int)std::ceil(C_LIGHT * 0.5 * s.dt / s.dx[d]);   // :147,161
@@ -102,6 +105,7 @@ void guard_cells(Sim& s) {
         s.ng_EB[d] = std::max(s.ng_EB[d], s.ng_FS[d]);           // :297
         int fg = std::min((s.nox + 1) / 2, s.ng_EB[d]);          // :314-316
         fg = std::min(fg, s.ng_EB[d]);
+        if (s.use_nci && d == 2) fg = std::min(fg + 4, s.ng_EB[d]);   // :319-330
         s.ng_FG[d] = std::max(fg, s.ng_FS[d]);                   // :338
     }
 }
@@ -313,10 +317,29 @@ void one_step(Sim& s, bool last_step) {
         double xyzmin[3], xyzminJ[3]; int lo[3], loJ[3];
         lower_corner(s, b, s.ng_EB, xyzmin, lo);                   // PushPX: box.grow(ngEB), :2583
         lower_corner(s, b, s.ng_J, xyzminJ, loJ);                  // DepositCurrent: tilebox.grow(ng_J)
+        // applyNCIFilter (PhysicalParticleContainer.cpp:1900-1911,2097-2169): E and B are filtered along z
+        // into temporaries over the tile box grown by the shape order; the gather reads those
+        const pic_fab* EB = b.fab;
+        std::vector<double> nci_data[6];
+        pic_fab nci_fab[6];
+        if (s.use_nci) {
+            t0 = now();
+            for (int c = 0; c < 6; ++c) {
+                nci_fab[c] = b.fab[c];
+                nci_data[c].assign((size_t)fab_size(b.fab[c]), 0.0);
+                nci_fab[c].p = nci_data[c].data();
+                int tlo[3], thi[3];
+                for (int d = 0; d < 3; ++d) { tlo[d] = b.lo[d] - s.nox; thi[d] = b.hi[d] + s.nox + STAG[c][d]; }
+                const bool exeybz = (c == 0 || c == 1 || c == 5);                      // :2132-2163
+                apply_nci_filter(b.fab[c], nci_fab[c], s.nci_stencil[exeybz ? 0 : 1], tlo, thi);
+            }
+            EB = nci_fab;
+            s.t_other += now() - t0;
+        }
         for (auto& sp : b.sp) {
             pic_soa P = sp.soa();
             t0 = now();
-            gather_push<Leaf>(P, 0, P.np, b.fab, b.fab + 3, s.dinv, xyzmin, lo, sp.q, sp.m, s.dt,
+            gather_push<Leaf>(P, 0, P.np, EB, EB + 3, s.dinv, xyzmin, lo, sp.q, sp.m, s.dt,
                               s.nox, s.galerkin, s.pusher, 1);
             s.t_push += now() - t0;
             t0 = now();
@@ -527,6 +550,23 @@ int orc_sim_set_moving_window(void* h, int dir, double v_over_c) {
     guard_cells(*s);
     alloc_box(*s, s->boxes[0]);
     return 0;
+}
+// particles.use_fdtd_nci_corr: the two z stencils (NCIGodfreyFilter::ComputeStencils); grows the guard cells
+int orc_sim_set_nci_corrector(void* h, const double* stencil_exeybz, const double* stencil_bxbyez) {
+    Sim* s = static_cast<Sim*>(h);
+    if (s->boxes.size() != 1 || s->nspecies) return 1;
+    s->use_nci = true;
+    for (int i = 0; i < 5; ++i) { s->nci_stencil[0][i] = stencil_exeybz[i]; s->nci_stencil[1][i] = stencil_bxbyez[i]; }
+    guard_cells(*s);
+    alloc_box(*s, s->boxes[0]);
+    return 0;
+}
+int orc_nci_table_index(double cdtodz, int tab_length) { return nci_table_index(cdtodz, tab_length); }
+void orc_nci_godfrey_stencil(const double* row_lo, const double* row_hi, int index, int tab_length, double cdtodz, double* out) {
+    nci_godfrey_stencil(row_lo, row_hi, index, tab_length, cdtodz, out);
+}
+void orc_apply_nci_filter(const pic_fab* src, const pic_fab* dst, const double* stencil_z, const int* tlo, const int* thi) {
+    apply_nci_filter(*src, *dst, stencil_z, tlo, thi);
 }
 // warpx.gamma_boost with warpx.boost_direction = z; call before adding species / lasers
 int orc_sim_set_boost(void* h, double gamma_boost, double beta_boost) {

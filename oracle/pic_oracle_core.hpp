@@ -558,6 +558,57 @@ inline void apply_filter(const pic_fab& src, const pic_fab& dst, const int npass
             }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Godfrey's NCI corrector (particles.use_fdtd_nci_corr): a 5-point filter along z applied to a copy
+// of E and B before the gather.
+// NCIGodfreyFilter::ComputeStencils (Filter/NCIGodfreyFilter.cpp:49-120): the four coefficients are
+// interpolated linearly in c dt / dz between two lines of the reference's tables
+// (Utils/NCIGodfreyTables.H, tab_length = 101 lines, tab_width = 4; fitted data the caller supplies),
+// then combined into the stencil; coefficient 0 is halved because of the way DoFilter sums.
+inline int nci_table_index(double cdtodz, int tab_length) {
+    int index = static_cast<int>(tab_length * cdtodz);                            // :61-63
+    index = std::min(index, tab_length - 2);
+    index = std::max(index, 0);
+    return index;
+}
+inline void nci_godfrey_stencil(const double* row_lo /*4: table[index]*/, const double* row_hi /*4: table[index+1]*/,
+                                int index, int tab_length, double cdtodz, double* stencil_z /*5*/) {
+    const double weight_right = cdtodz - double(index) / double(tab_length);      // :64
+    double prestencil[4];
+    for (int i = 0; i < 4; ++i) prestencil[i] = (1.0 - weight_right) * row_lo[i] + weight_right * row_hi[i];   // :69-104
+    stencil_z[0] =  (256 + 128 * prestencil[0] + 96 * prestencil[1] + 80 * prestencil[2] + 70 * prestencil[3]) / 256;   // :107-111
+    stencil_z[1] = -(       64 * prestencil[0] + 64 * prestencil[1] + 60 * prestencil[2] + 56 * prestencil[3]) / 256;
+    stencil_z[2] =  (                            16 * prestencil[1] + 24 * prestencil[2] + 28 * prestencil[3]) / 256;
+    stencil_z[3] = -(                                                  4 * prestencil[2] +  8 * prestencil[3]) / 256;
+    stencil_z[4] =  (                                                                       1 * prestencil[3]) / 256;
+    stencil_z[0] /= 2.0;                                                          // :125-129
+}
+
+// Filter::ApplyStencil(FArrayBox) -> DoFilter (Filter/Filter.cpp:78-133) with the NCI stencils
+// s0 = s1 = {1/2}, s2 = stencil_z (slen = {1,1,5}), over tbx = [tlo, thi] in the index space of the
+// component (PhysicalParticleContainer::applyNCIFilter, PhysicalParticleContainer.cpp:2097-2169:
+// the tile box grown by the shape order, converted to the component's index type).
+inline void apply_nci_filter(const pic_fab& src, const pic_fab& dst, const double* stencil_z, const int tlo[3], const int thi[3]) {
+    W S(src), D(dst);
+    auto pad = [&](int i, int j, int k) -> double {
+        const bool in = i >= src.lo[0] && i <= src.hi[0] && j >= src.lo[1] && j <= src.hi[1] && k >= src.lo[2] && k <= src.hi[2];
+        return in ? S(i, j, k) : 0.0;
+    };
+    const double s0 = 1.0 / 2.0, s1 = 1.0 / 2.0;
+#pragma omp parallel for schedule(static)
+    for (int k = tlo[2]; k <= thi[2]; ++k)
+        for (int j = tlo[1]; j <= thi[1]; ++j)
+            for (int i = tlo[0]; i <= thi[0]; ++i) {
+                double d = 0.0;
+                for (int i2 = 0; i2 < 5; ++i2) {
+                    const double sss = s0 * s1 * stencil_z[i2];
+                    d += sss * (pad(i, j, k - i2) + pad(i, j, k - i2) + pad(i, j, k - i2) + pad(i, j, k - i2)
+                              + pad(i, j, k + i2) + pad(i, j, k + i2) + pad(i, j, k + i2) + pad(i, j, k + i2));
+                }
+                D(i, j, k) = d;
+            }
+}
+
 // amrex::enforcePeriodic (AMReX_ParticleUtil.H, AMReX 24.10) as applied by Redistribute
 // (WarpXEvolve.cpp:550-559): shift by the domain length until inside, then clamp round-off.
 inline void wrap_periodic(const pic_soa& P, const pic_geom& g) {

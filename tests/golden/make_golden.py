@@ -34,3 +34,26 @@ for name in ("test_3d_langmuir_multi", "test_3d_particle_pusher", "test_3d_laser
 with open(OUT, "w") as f:
     json.dump(gold, f, indent=1, sort_keys=True)
 print("wrote", OUT)
+
+# ---- a few lines of the Godfrey NCI-corrector coefficient tables (Source/Utils/NCIGodfreyTables.H): the lines
+# the parity tests interpolate between for c dt / dz = 0, 0.5, 0.9 / sqrt(3), 0.98 and 1.  The tables are fitted
+# data of the reference; a WarpX build passes the stencils it computed from them through the C ABI
+# (pic_apply_nci_filter), the tests need a handful of lines to check the restated interpolation.
+import re
+
+TABLES = "/root/reference/Source/Utils/NCIGodfreyTables.H"
+OUT2 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nci_godfrey_lines.json")
+text = open(TABLES).read()
+tab_length = int(re.search(r"const int tab_length = (\d+);", text).group(1))
+tab_width = int(re.search(r"const int tab_width = (\d+);", text).group(1))
+lines = {"_provenance": {"source": "ECP-WarpX/WarpX Source/Utils/NCIGodfreyTables.H (lines 0,1,50-53,98-100 of each table)",
+                         "tab_length": tab_length, "tab_width": tab_width}}
+WANT = (0, 1, 50, 51, 52, 53, 98, 99, 100)
+for m in re.finditer(r"table_nci_godfrey_(\w+)\[tab_length\]\[tab_width\]\{(.*?)\};", text, re.S):
+    rows = re.findall(r"\{([^{}]*)\}", m.group(2))
+    assert len(rows) == tab_length
+    parsed = [[float(v.replace("_rt", "")) for v in r.split(",")] for r in rows]
+    lines[m.group(1)] = {str(i): parsed[i] for i in WANT}
+with open(OUT2, "w") as f:
+    json.dump(lines, f, indent=1, sort_keys=True)
+print("wrote", OUT2)

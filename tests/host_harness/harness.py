@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "warpx_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libpic_lwfa_host.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SRCS = ["lwfa.cu", "charge.cu", "runtime.cu"]
+SRCS = ["lwfa.cu", "charge.cu", "nci.cu", "runtime.cu"]
 PROBES = [os.path.join(HERE, "shape_probe.cu")]
 _LIB = None
 

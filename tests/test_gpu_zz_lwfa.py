@@ -254,12 +254,18 @@ def test_particle_energy_matches_oracle(orc, dev):
 
 # ---------------------------------------------------------------------------------------------
 def make_lwfa_sim(wl, capacity):
-    from warpx_b200.engine import Simulation
+    from warpx_b200.engine import Simulation, max_dt, nci_godfrey_stencils
+    from warpx_b200.lib import lib as piclib
+    from test_oracle import _nci_lines
+    nci = None
+    if wl.get("use_fdtd_nci_corr"):
+        dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+        nci = nci_godfrey_stencils(piclib(), _nci_lines(), workloads.C * wl["cfl"] * max_dt(wl["solver"], dx) / dx[2])
     sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"],
                      solver=wl["solver"], pusher=wl["pusher"], use_filter=wl["use_filter"], sort_interval=4,
                      boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]),
                      moving_window=(wl["moving_window_dir"], wl["moving_window_v"]),
-                     gamma_boost=wl.get("gamma_boost", 1.0))
+                     gamma_boost=wl.get("gamma_boost", 1.0), nci_stencils=nci)
     for s in wl["species"]:
         sim.add_plasma_species(s["name"], s["q"], s["m"],
                                abi.make_injector(s["ppc"], s["bound_lo"], s["bound_hi"], s["density"],
@@ -318,10 +324,10 @@ def test_laser_acceleration_loop_matches_oracle(orc, cuda, solver, pusher):
 
 def test_boosted_laser_acceleration_loop_matches_oracle(orc, cuda):
     """BASELINE.json config 4 in the small (workloads.laser_acceleration_boosted_3d: gamma_boost = 10, CKC, Vay,
-    order 3, filter, PEC z, moving window, boosted antenna, electrons + ions injected continuously from the
+    order 3, filter, NCI corrector, PEC z, moving window, boosted antenna, electrons + ions injected continuously from the
     lab-frame plasma bounds): 40 steps through the C++ driver against the oracle -- fields, every particle of
     both species by id, the drifting antenna, the moving domain."""
-    wl = workloads.laser_acceleration_boosted_3d()
+    wl = workloads.laser_acceleration_boosted_3d(use_fdtd_nci_corr=True)
     sim = make_lwfa_sim(wl, capacity=16 * 16 * 200)
     osim = make_lwfa_oracle(orc, wl)
     assert sim.gamma_boost == 10.0 and sim.species[0].np == osim.L.orc_sim_np(osim.h, 0) == 0
@@ -352,6 +358,69 @@ def test_boosted_laser_acceleration_loop_matches_oracle(orc, cuda):
         assert np.max(np.abs(LA[k] - LB[k])) / sim.dx[2] <= 1e-10, k
     for k in ("ux", "uy", "uz"):
         assert np.max(np.abs(LA[k] - LB[k])) / (10.0 * workloads.C) <= 1e-10, k
+
+
+@pytest.mark.parametrize("comp", range(6))
+def test_nci_filter_matches_oracle(orc, dev, comp):
+    """pic_apply_nci_filter on the device against the oracle (the reference's summation order; the final
+    multiply-add may contract to an FMA on the device: 1e-15 of the data scale)."""
+    from test_oracle import oracle_nci_stencils
+    n, ng, nox = (40, 24, 33), (4, 4, 8), 3
+    rng = np.random.default_rng(200 + comp)
+    stz = (C.c_double * 5)(*oracle_nci_stencils(orc, 0.98)[0 if comp in (0, 1, 5) else 1])
+    src = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+    src.a[:] = rng.standard_normal(src.a.shape)
+    want = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+    want.a[:] = -7.0
+    tlo = [-nox] * 3
+    thi = [n[d] - 1 + nox + abi.YEE_STAG[comp][d] for d in range(3)]
+    orc.lib().orc_apply_nci_filter(C.byref(src.desc), C.byref(want.desc), stz, abi.int3(tlo), abi.int3(thi))
+    out = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+    out.a[:] = -7.0
+    arr, tens = dev.fabs([src, out])
+    dev.ok(dev.L.pic_apply_nci_filter(C.byref(arr[0]), C.byref(arr[1]), stz, abi.int3((0, 0, 0)), abi.int3((n[0] - 1, n[1] - 1, n[2] - 1)), nox, dev.stream))
+    dev.sync()
+    got = tens[1].cpu().numpy()
+    assert np.max(np.abs(got - want.a)) <= 1e-15 * np.max(np.abs(src.a)) * 8
+    assert np.array_equal(got == -7.0, want.a == -7.0)
+
+
+def test_nci_corrected_loop_matches_oracle(orc, cuda):
+    """particles.use_fdtd_nci_corr through the C++ driver: the streaming-plasma deck of the oracle's known-answer
+    test (periodic box, CKC at c dt = dz, Vay, order 3, filter), 60 steps, fields and particles against the oracle;
+    the guard cells grow by 4 along z."""
+    from test_oracle import nci_streaming_plasma, _nci_lines, oracle_nci_stencils
+    from warpx_b200.engine import Simulation, nci_godfrey_stencils
+    from warpx_b200.lib import lib as piclib
+    wl = nci_streaming_plasma()
+    stencils = nci_godfrey_stencils(piclib(), _nci_lines(), 1.0)
+    assert list(stencils[0]) == oracle_nci_stencils(orc, 1.0)[0]
+    sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, cfl=1.0, solver=wl["solver"], pusher=wl["pusher"],
+                     use_filter=True, sort_interval=4, nci_stencils=stencils)
+    osim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, cfl=1.0, use_filter=1, solver=wl["solver"],
+                         pusher=wl["pusher"])
+    osim.set_nci_corrector(*oracle_nci_stencils(orc, 1.0))
+    assert sim.ng_EB == osim.guards()["ng_EB"] == [4, 4, 8] and sim.ng_FG == osim.guards()["ng_FG"] == [2, 2, 6]
+    for s in wl["species"]:
+        sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+        osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.Evolve(60)
+    osim.evolve(60)
+    cuda.cuda.synchronize()
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        _, oa = osim.fab(c)
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= 1e-7, abi.COMP_NAMES[c]
+    for isp in (0, 1):
+        A = sim.species_numpy(isp, sort_by_id=True)
+        B = osim.particles(isp)
+        for k in ("x", "y", "z"):
+            assert np.max(np.abs(A[k] - B[k])) / sim.dx[2] <= 1e-9, k
+        for k in ("ux", "uy", "uz"):
+            assert np.max(np.abs(A[k] - B[k])) / (30.0 * workloads.C) <= 1e-10, k
+    e, b = sim.field_energy()
+    eo, bo = osim.field_energy()
+    assert e + b == pytest.approx(eo + bo, rel=1e-6)
 
 
 def test_laser_acceleration_golden_checksums(orc, cuda, golden):

@@ -243,6 +243,64 @@ def test_boosted_add_plasma_matches_oracle(orc, hh, ppc, t):
     assert n_lab > n and np.all(arrs2["uz"][:n_lab] == 0.0)
 
 
+@pytest.mark.parametrize("galerkin", [True, False])
+@pytest.mark.parametrize("cdtodz", [0.0, 0.5, 0.9 / math.sqrt(3), 0.98, 1.0])
+def test_nci_godfrey_stencils_match_oracle(orc, hh, cdtodz, galerkin):
+    """pic_nci_godfrey_table_index / pic_nci_godfrey_stencil and the Python helper on top of them against the
+    oracle's restatement of NCIGodfreyFilter::ComputeStencils, bit for bit."""
+    from test_oracle import oracle_nci_stencils, _nci_lines
+    from warpx_b200.engine import nci_godfrey_stencils
+    want = oracle_nci_stencils(orc, cdtodz, galerkin)
+    got = nci_godfrey_stencils(hh, _nci_lines(), cdtodz, galerkin)
+    assert hh.pic_nci_godfrey_table_index(cdtodz, 101) == orc.lib().orc_nci_table_index(cdtodz, 101)
+    assert got[0] == want[0] and got[1] == want[1]
+
+
+@pytest.mark.parametrize("comp", range(6))
+def test_nci_filter_matches_oracle(orc, hh, comp):
+    """pic_apply_nci_filter (applyNCIFilter -> Filter::DoFilter, slen = {1,1,5}) on random data, every staggering,
+    a tile box in the middle of the array and one whose grown box reaches the zero padding: bit for bit."""
+    from test_oracle import oracle_nci_stencils
+    n, ng, nox = (7, 5, 11), (4, 4, 8), 3
+    rng = np.random.default_rng(100 + comp)
+    stz = (C.c_double * 5)(*oracle_nci_stencils(orc, 0.98)[0 if comp in (0, 1, 5) else 1])
+    src = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+    src.a[:] = rng.standard_normal(src.a.shape)
+    for tile_lo, tile_hi, grow in (((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), nox), ((2, 1, 3), (4, 3, 7), nox),
+                                   ((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), 4)):
+        a = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+        b = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[comp])
+        a.a[:] = -7.0
+        b.a[:] = -7.0
+        tlo = [tile_lo[d] - grow for d in range(3)]
+        thi = [tile_hi[d] + grow + abi.YEE_STAG[comp][d] for d in range(3)]
+        orc.lib().orc_apply_nci_filter(C.byref(src.desc), C.byref(a.desc), stz, abi.int3(tlo), abi.int3(thi))
+        _check(hh, hh.pic_apply_nci_filter(C.byref(src.desc), C.byref(b.desc), stz, abi.int3(tile_lo), abi.int3(tile_hi), grow, None))
+        assert np.array_equal(a.a, b.a)
+        assert np.any(a.a != -7.0) and (grow == 4 or np.any(a.a == -7.0))
+    # the grown box must fit the destination
+    assert hh.pic_apply_nci_filter(C.byref(src.desc), C.byref(b.desc), stz, abi.int3((0, 0, 0)), abi.int3((n[0] - 1, n[1] - 1, n[2] - 1)), 9, None) != 0
+    assert b"leaves the destination" in hh.pic_last_error()
+
+
+def test_host_guard_cells_with_nci_match_oracle(orc):
+    """engine.guard_cells with the NCI corrector: 4 more cells along z for E, B and the field gather
+    (GuardCellManager.cpp:87-90,319-330), with and without the moving window, orders 1-3."""
+    from warpx_b200 import engine
+    from test_oracle import oracle_nci_stencils
+    for nox in (1, 2, 3):
+        for mw in (False, True):
+            sim = orc.OracleSim((8, 8, 16), (0, 0, 0), (8e-6, 8e-6, 16e-6), nox=nox, cfl=1.0, use_filter=1, solver=abi.SOLVER_CKC)
+            if mw:
+                sim.set_boundaries(abi.make_boundaries(("periodic", "periodic", "pec"), ("periodic", "periodic", "pec")))
+                sim.set_moving_window(2, 1.0)
+            sim.set_nci_corrector(*oracle_nci_stencils(orc, 1.0))
+            g = engine.guard_cells(nox, sim.L.orc_sim_dt(sim.h), [1e-6] * 3, True, (1, 1, 1), mw, True)
+            og = sim.guards()
+            assert g["ng_EB"] == og["ng_EB"] and g["ng_J"] == og["ng_J"] and g["ng_FG"] == og["ng_FG"], (nox, mw)
+            assert g["ng_EB"][2] == nox + 4 + (nox + 4) % 2 and g["ng_FG"][2] == min((nox + 1) // 2 + 4, g["ng_EB"][2])
+
+
 def _host_soa(n):
     arrs = {k: np.full(n, np.nan) for k in ("x", "y", "z", "w", "ux", "uy", "uz")}
     ids = np.zeros(n, dtype=np.uint64)

@@ -270,6 +270,9 @@ def make_lwfa_oracle(orc, wl, kind="restated"):
     sim.set_moving_window(wl["moving_window_dir"], wl["moving_window_v"])
     if wl.get("gamma_boost", 1.0) > 1.0:
         sim.set_boost(wl["gamma_boost"])
+    if wl.get("use_fdtd_nci_corr"):
+        dz = (wl["prob_hi"][2] - wl["prob_lo"][2]) / wl["n_cell"][2]
+        sim.set_nci_corrector(*oracle_nci_stencils(orc, workloads.C * sim.L.orc_sim_dt(sim.h) / dz))
     for s in wl["species"]:
         sim.add_plasma(s["q"], s["m"], abi.make_injector(s["ppc"], s["bound_lo"], s["bound_hi"], s["density"],
                                                          s["do_continuous_injection"]))
@@ -483,11 +486,12 @@ def test_boosted_continuous_injection_continues_the_lattice(orc):
 
 def test_boosted_deck_runs_and_stays_quiet_ahead_of_the_laser(orc):
     """The boosted laser-acceleration deck (workloads.laser_acceleration_boosted_3d): 40 steps of CKC + Vay +
-    order 3 + filter + moving window + boosted antenna + two continuously injected species.  Sanity: finite,
+    order 3 + filter + NCI corrector + moving window + boosted antenna + two continuously injected species.  Sanity: finite,
     the laser field is there with the boosted amplitude scale, the neutral plasma carries the current
     of the wake only (|jz| of the two streaming species cancels to << n q beta c)."""
-    wl = workloads.laser_acceleration_boosted_3d()
+    wl = workloads.laser_acceleration_boosted_3d(use_fdtd_nci_corr=True)
     sim = make_lwfa_oracle(orc, wl)
+    assert sim.guards() == {"ng_EB": [4, 4, 8], "ng_J": [5, 5, 5], "ng_FG": [2, 2, 6], "ng_FS": [1, 1, 1]}
     sim.evolve(40)
     gb, beta = wl["gamma_boost"], abi.beta_of_gamma(wl["gamma_boost"])
     d, ey = sim.fab(1)
@@ -498,6 +502,135 @@ def test_boosted_deck_runs_and_stays_quiet_ahead_of_the_laser(orc):
     stream = wl["species"][0]["density"] * gb * workloads.Q_E * beta * workloads.C
     assert np.max(np.abs(jz)) < 0.2 * stream
     assert sim.L.orc_sim_np(sim.h, 0) == sim.L.orc_sim_np(sim.h, 1) > 0
+
+
+def _nci_lines():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nci_godfrey_lines.json")) as f:
+        return json.load(f)
+
+
+def oracle_nci_stencils(orc, cdtodz, galerkin=True):
+    lines = _nci_lines()
+    tab_length = lines["_provenance"]["tab_length"]
+    L = orc.lib()
+    index = L.orc_nci_table_index(cdtodz, tab_length)
+    out = []
+    for which in ("Ex_Ey_Bz", "Bx_By_Ez"):
+        t = lines[("galerkin_" if galerkin else "momentum_") + which]
+        st = (C.c_double * 5)()
+        L.orc_nci_godfrey_stencil(abi.dbl4(t[str(index)]), abi.dbl4(t[str(index + 1)]), index, tab_length, cdtodz, st)
+        out.append(list(st))
+    return out
+
+
+def test_nci_godfrey_stencil_known_answers(orc):
+    """NCIGodfreyFilter::ComputeStencils (Filter/NCIGodfreyFilter.cpp:49-139) on lines of the reference's
+    tables: table index clamping, linear interpolation in c dt / dz, the 5-point combination.  Whatever the
+    four coefficients, the combination has unit DC gain (s0 + 2 (s1 + s2 + s3 + s4) = 1 with the halved s0
+    counted twice) -- the corrector must not change a uniform field."""
+    L = orc.lib()
+    assert L.orc_nci_table_index(0.0, 101) == 0 and L.orc_nci_table_index(1.0, 101) == 99      # clamped to tab_length - 2
+    assert L.orc_nci_table_index(0.5, 101) == 50 and L.orc_nci_table_index(0.9 / math.sqrt(3), 101) == 52
+    assert L.orc_nci_table_index(1.7, 101) == 99 and L.orc_nci_table_index(-0.1, 101) == 0
+    lines = _nci_lines()
+    for cdtodz in (0.0, 0.5, 0.9 / math.sqrt(3), 0.98, 1.0):
+        for galerkin in (True, False):
+            for st in oracle_nci_stencils(orc, cdtodz, galerkin):
+                assert abs(2 * st[0] + 2 * sum(st[1:]) - 1.0) < 1e-14
+    # at c dt / dz = 0 the weight of the upper line is 0: the first line of the table alone
+    st = oracle_nci_stencils(orc, 0.0)[0]
+    p = lines["galerkin_Ex_Ey_Bz"]["0"]
+    assert st[4] == p[3] / 256 and st[3] == -(4 * p[2] + 8 * p[3]) / 256
+    assert st[0] == (256 + 128 * p[0] + 96 * p[1] + 80 * p[2] + 70 * p[3]) / 256 / 2
+    # c dt / dz = 1 extrapolates beyond the last pair of lines (index 99, weight 1 - 99/101), as the reference does
+    st = oracle_nci_stencils(orc, 1.0)[1]
+    lo, hi = lines["galerkin_Bx_By_Ez"]["99"], lines["galerkin_Bx_By_Ez"]["100"]
+    w = 1.0 - 99.0 / 101.0
+    assert st[4] == ((1.0 - w) * lo[3] + w * hi[3]) / 256
+
+
+def test_nci_filter_known_answers(orc):
+    """Filter::DoFilter with the NCI stencils over the grown tile box: a uniform field is unchanged where the
+    stencil stays inside the array, a z-independent field is filtered to itself, the filter acts along z only,
+    and points outside the grown tile box are not written."""
+    L = orc.lib()
+    n, ng, nox = (6, 5, 12), (4, 4, 8), 3
+    rng = np.random.default_rng(11)
+    stz = oracle_nci_stencils(orc, 0.98)[0]
+    for c in (0, 2, 4):
+        src = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[c])
+        dst = orc.HostFab((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1), ng, abi.YEE_STAG[c])
+        plane = rng.standard_normal(src.a.shape[1:])
+        src.a[:] = plane[None, :, :]                     # no z dependence
+        dst.a[:] = np.nan
+        tlo = [-nox] * 3
+        thi = [n[d] - 1 + nox + abi.YEE_STAG[c][d] for d in range(3)]
+        L.orc_apply_nci_filter(C.byref(src.desc), C.byref(dst.desc), (C.c_double * 5)(*stz), abi.int3(tlo), abi.int3(thi))
+        o = [ng[d] - nox for d in range(3)]
+        inner = dst.a[o[2]:dst.a.shape[0] - o[2], o[1]:dst.a.shape[1] - o[1], o[0]:dst.a.shape[2] - o[0]]
+        assert np.all(np.isfinite(inner))
+        want = np.broadcast_to(plane[None, o[1]:plane.shape[0] - o[1], o[0]:plane.shape[1] - o[0]], inner.shape)
+        assert np.max(np.abs(inner - want)) <= 4e-15 * np.max(np.abs(plane))     # nox + 4 = 7 <= 8 guard cells: no zero padding reached
+        mask = np.ones(dst.a.shape, dtype=bool)
+        mask[o[2]:dst.a.shape[0] - o[2], o[1]:dst.a.shape[1] - o[1], o[0]:dst.a.shape[2] - o[0]] = False
+        assert np.all(np.isnan(dst.a[mask]))
+        # a single plane z = k0 spreads to k0 +- 4 with the stencil weights (2 x the halved centre)
+        src.a[:] = 0.0
+        k0 = ng[2] + 5
+        src.a[k0, :, :] = 1.0
+        L.orc_apply_nci_filter(C.byref(src.desc), C.byref(dst.desc), (C.c_double * 5)(*stz), abi.int3(tlo), abi.int3(thi))
+        col = dst.a[:, ng[1] + 1, ng[0] + 1]
+        for dk in range(-4, 5):
+            w = 2 * stz[0] if dk == 0 else stz[abs(dk)]
+            assert col[k0 + dk] == pytest.approx(w, rel=1e-15)
+        assert col[k0 + 5] == 0.0 and col[k0 - 5] == 0.0
+
+
+def nci_streaming_plasma(n=(16, 16, 32), length=20.e-6, density=1.e27, uz=-30.0, seed=1.e-5):
+    """A cold neutral plasma streaming along z through a periodic box (the 3D analogue of Examples/Tests/
+    nci_fdtd_stability/inputs_base_2d): the numerical Cherenkov instability grows from the tiny thermal seed
+    unless the gather is corrected.  CKC at c dt = dz, Vay, order 3, Galerkin gather, bilinear filter."""
+    lo = (-length / 2 * n[0] / n[2], -length / 2 * n[1] / n[2], -length / 2)
+    hi = tuple(-v for v in lo)
+    x, y, z = workloads.lattice_positions(n, lo, hi, (1, 1, 1))
+    w = np.full_like(x, density * (length / n[2]) ** 3)
+    u = workloads.philox_normal(7, 0, len(x)) * seed * workloads.C
+    zero = np.zeros_like(x)
+    species = [dict(name="electrons", q=-workloads.Q_E, m=workloads.M_E, x=x, y=y, z=z, w=w,
+                    ux=u[:, 0].copy(), uy=u[:, 1].copy(), uz=u[:, 2] + uz * workloads.C),
+               dict(name="ions", q=workloads.Q_E, m=1.67262192369e-27, x=x.copy(), y=y.copy(), z=z.copy(), w=w.copy(),
+                    ux=zero.copy(), uy=zero.copy(), uz=np.full_like(x, uz * workloads.C))]
+    return dict(n_cell=n, prob_lo=lo, prob_hi=hi, nox=3, cfl=1.0, use_filter=True, solver=abi.SOLVER_CKC,
+                pusher=abi.PUSHER_VAY, species=species)
+
+
+def test_nci_corrector_damps_the_instability_of_a_streaming_plasma(orc):
+    """What the corrector is for, as a known answer (the reference's own acceptance test is of this kind:
+    Examples/Tests/nci_fdtd_stability/analysis_ncicorr.py compares the field energy with a threshold 100x below
+    the uncorrected run): without it the field energy of the streaming plasma grows by ten orders of magnitude in
+    200 steps; with the two stencils on the right components it stays within a factor 1000 of the seed level."""
+    wl = nci_streaming_plasma()
+    energy = {}
+    for nci in (False, True):
+        sim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"],
+                            use_filter=wl["use_filter"], solver=wl["solver"], pusher=wl["pusher"])
+        if nci:
+            dz = (wl["prob_hi"][2] - wl["prob_lo"][2]) / wl["n_cell"][2]
+            cdtodz = workloads.C * sim.L.orc_sim_dt(sim.h) / dz
+            assert cdtodz == pytest.approx(1.0, rel=1e-12)
+            sim.set_nci_corrector(*oracle_nci_stencils(orc, cdtodz))
+            assert sim.guards()["ng_EB"] == [4, 4, 8] and sim.guards()["ng_FG"] == [2, 2, 6]
+        for s in wl["species"]:
+            sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+        sim.evolve(50, synchronize_last=False)
+        first = sum(sim.field_energy())
+        sim.evolve(150, synchronize_last=False)
+        energy[nci] = (first, sum(sim.field_energy()))
+    assert energy[False][1] > 1e8 * energy[False][0]            # the instability is there ...
+    assert energy[True][1] < 1e3 * energy[True][0]              # ... and the corrected gather holds it down
+    assert energy[True][1] < 1e-6 * energy[False][1]
 
 
 def test_particle_energy_known_answer_and_conservation(orc):

@@ -131,6 +131,9 @@ def LWFA_SIGNATURES(fabp, soap, gp, bp, lp, jp, dp, ip, vp):
         "pic_particles_boundary_workspace_ints": (C.c_long, [C.c_int]),
         "pic_particles_boundary_mark": (C.c_int, [soap, gp, bp, vp, C.c_int, vp]),
         "pic_particles_boundary_compact": (C.c_int, [soap, vp, C.c_int, C.c_int, vp]),
+        "pic_nci_godfrey_table_index": (C.c_int, [C.c_double, C.c_int]),
+        "pic_nci_godfrey_stencil": (None, [dp, dp, C.c_int, C.c_int, C.c_double, dp]),
+        "pic_apply_nci_filter": (C.c_int, [fabp, fabp, dp, ip, ip, C.c_int, vp]),
     }
 
 
@@ -173,3 +176,7 @@ def int3(v):
 
 def dbl3(v):
     return (C.c_double * 3)(*[float(a) for a in v])
+
+
+def dbl4(v):
+    return (C.c_double * 4)(*[float(a) for a in v])

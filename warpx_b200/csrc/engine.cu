@@ -94,6 +94,10 @@ struct Engine {
     int mw_dir = 2;
     double mw_v = 0.0, mw_x = 0.0;               // moving_window_v [m/s], moving_window_x
     double gamma_boost = 1.0, beta_boost = 0.0;  // warpx.gamma_boost, boost_direction = z
+    bool use_nci = false;                        // particles.use_fdtd_nci_corr
+    double nci_stencil[2][5];                    // [0] Ex Ey Bz, [1] Bx By Ez
+    pic_fab nci_fab[6];                          // filtered copies of E, B (engine-owned)
+    bool nci_alloc = false;
     double cur_time = 0.0;                       // t_new[0]
     double* shift_tmp = nullptr;                 // one component-sized scratch array
     size_t shift_tmp_bytes = 0;
@@ -179,6 +183,7 @@ static void guard_cells(Engine& e) {
         const int ngt = e.nox;
         int ng = (ngt % 2) ? ngt + 1 : ngt;
         int ngJ = ngt;
+        if (e.use_nci && d == 2) { const int n4 = ngt + 4; ng = (n4 % 2) ? n4 + 1 : n4; }   // GuardCellManager.cpp:87-90 (m_stencil_width = 4)
         if (e.do_moving_window) { ng = ng > 2 ? ng : 2; ngJ = ngJ > 2 ? ngJ : 2; }   // GuardCellManager.cpp:103-115
         e.ng_J[d] = ngJ + (int)ceil(C_LIGHT * 0.5 * e.dt / e.dx[d]);
         if (e.use_filter) e.ng_J[d] += e.npass[d];     // + stencil_length - 1, GuardCellManager.cpp:169-172
@@ -187,6 +192,7 @@ static void guard_cells(Engine& e) {
         e.ng_EB[d] = ng;
         int fg = (e.nox + 1) / 2;
         fg = fg < ng ? fg : ng;
+        if (e.use_nci && d == 2) { fg += 4; fg = fg < ng ? fg : ng; }   // :319-330
         e.ng_FG[d] = fg > e.ng_FS[d] ? fg : e.ng_FS[d];
     }
 }
@@ -298,9 +304,30 @@ static int push(Engine& e, Species& sp, double dt, int push_position, void* s) {
     lower_corner(e, e.ng_EB, xyzmin, lo);
     const pic_soa& P = sp.buf[sp.cur];
     if (push_position && sp.has_esc) cudaMemsetAsync(sp.esc.count, 0, sizeof(int), (cudaStream_t)s);
-    return pic_gather_push(&P, 0, P.np, &e.fab[0], &e.fab[3], e.dinv, xyzmin, lo, sp.q, sp.m, dt, e.nox,
+    // the main push gathers from the NCI-filtered copies (PhysicalParticleContainer.cpp:1900-1911); PushP does not
+    const pic_fab* EB = (e.use_nci && push_position) ? e.nci_fab : e.fab;
+    return pic_gather_push(&P, 0, P.np, &EB[0], &EB[3], e.dinv, xyzmin, lo, sp.q, sp.m, dt, e.nox,
                            e.galerkin, e.pusher, push_position, sp.has_bins ? &sp.bins : nullptr,
                            sp.has_esc ? &sp.esc : nullptr, s);
+}
+
+// PhysicalParticleContainer::applyNCIFilter for the rank's box (one tile): E, B -> the engine's filtered copies
+static int apply_nci(Engine& e, void* s) {
+    if (!e.nci_alloc) {
+        for (int c = 0; c < 6; ++c) {
+            e.nci_fab[c] = e.fab[c];
+            e.nci_fab[c].p = nullptr;
+            if (cudaMalloc(&e.nci_fab[c].p, sizeof(double) * (size_t)fab_size(e.fab[c])) != cudaSuccess)
+                return fail("pic_engine: cannot allocate the NCI-filtered field copies");
+            cudaMemsetAsync(e.nci_fab[c].p, 0, sizeof(double) * (size_t)fab_size(e.fab[c]), (cudaStream_t)s);
+        }
+        e.nci_alloc = true;
+    }
+    for (int c = 0; c < 6; ++c) {
+        const bool exeybz = (c == 0 || c == 1 || c == 5);              // :2132-2163
+        ENG_CALL(pic_apply_nci_filter(&e.fab[c], &e.nci_fab[c], e.nci_stencil[exeybz ? 0 : 1], e.box_lo, e.box_hi, e.nox, s));
+    }
+    return 0;
 }
 
 static int push_particles_and_deposit(Engine& e, void* s) {
@@ -308,6 +335,7 @@ static int push_particles_and_deposit(Engine& e, void* s) {
         cudaMemsetAsync(e.fab[c].p, 0, sizeof(double) * (size_t)fab_size(e.fab[c]), (cudaStream_t)s);
     double xyzmin[3]; int lo[3];
     lower_corner(e, e.ng_J, xyzmin, lo);
+    if (e.use_nci && !e.species.empty()) ENG_CALL(apply_nci(e, s));
     for (auto& sp : e.species) {
         ENG_CALL(push(e, sp, e.dt, 1, s));
         const pic_soa& P = sp.buf[sp.cur];
@@ -604,6 +632,7 @@ extern "C" void pic_engine_destroy(void* h) {
         }
         for (auto& L : e->lasers) { if (L.bnd_work) cudaFree(L.bnd_work); if (L.w_owned) cudaFree(L.w_owned); }
         if (e->shift_tmp) cudaFree(e->shift_tmp);
+        if (e->nci_alloc) for (int c = 0; c < 6; ++c) cudaFree(e->nci_fab[c].p);
         if (e->host_count) cudaFreeHost(e->host_count);
         for (int b = 0; b < 4; ++b) if (e->hbuf[b]) cudaFree(e->hbuf[b]);
     }
@@ -757,6 +786,16 @@ extern "C" int pic_engine_set_boost(void* h, double gamma_boost, double beta_boo
     PIC_REQUIRE(e->lasers.empty(), "pic_engine_set_boost: call before pic_engine_add_laser");
     for (auto& sp : e->species) PIC_REQUIRE(!sp.has_injector, "pic_engine_set_boost: call before pic_engine_set_injector");
     e->gamma_boost = gamma_boost; e->beta_boost = beta_boost;
+    return 0;
+}
+// particles.use_fdtd_nci_corr (MultiParticleContainer.cpp:327, WarpX::InitNCICorrector, WarpXInitData.cpp:858-890)
+extern "C" int pic_engine_set_nci_corrector(void* h, const double stencil_exeybz[5], const double stencil_bxbyez[5]) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(e->species.empty() && e->lasers.empty(), "pic_engine_set_nci_corrector: call before adding particles");
+    PIC_REQUIRE(e->comm == nullptr, "pic_engine_set_nci_corrector: call before pic_engine_set_comm");
+    e->use_nci = true;
+    for (int i = 0; i < 5; ++i) { e->nci_stencil[0][i] = stencil_exeybz[i]; e->nci_stencil[1][i] = stencil_bxbyez[i]; }
+    guard_cells(*e);
     return 0;
 }
 static bool same_boost(const Engine& e, double gamma_boost, double beta_boost) {

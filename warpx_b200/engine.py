@@ -66,22 +66,46 @@ def max_dt(solver, dx):
     return min(dx) / C_LIGHT
 
 
-def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1), do_moving_window=False):
-    """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-172, 310-343) for: no MR, no
-    NCI corrector, not safe_guard_cells, FDTD solver.  Returns also ng_depos_J (:165) -- ng_J itself
+def nci_godfrey_stencils(lib, lines, cdtodz, galerkin=True):
+    """The two z stencils of Godfrey's NCI corrector (WarpX::InitNCICorrector, Source/Initialization/
+    WarpXInitData.cpp:858-890 -> NCIGodfreyFilter::ComputeStencils): `lines` holds lines of the reference's
+    coefficient tables keyed like tests/golden/nci_godfrey_lines.json ({"galerkin_Ex_Ey_Bz": {"99": [4 numbers],
+    ...}, ..., "_provenance": {"tab_length": 101}}); the tables are the caller's data, not part of this package.
+    Returns (stencil_exeybz, stencil_bxbyez), each 5 numbers with coefficient 0 halved."""
+    tab_length = int(lines["_provenance"]["tab_length"])
+    index = lib.pic_nci_godfrey_table_index(cdtodz, tab_length)
+    out = []
+    for which in ("Ex_Ey_Bz", "Bx_By_Ez"):
+        table = lines[("galerkin_" if galerkin else "momentum_") + which]
+        if str(index) not in table or str(index + 1) not in table:
+            raise KeyError("nci_godfrey_stencils: the table lines %d, %d (c dt / dz = %g) were not supplied" % (index, index + 1, cdtodz))
+        st = (C.c_double * 5)()
+        lib.pic_nci_godfrey_stencil(abi.dbl4(table[str(index)]), abi.dbl4(table[str(index + 1)]), index, tab_length, cdtodz, st)
+        out.append(list(st))
+    return tuple(out)
+
+
+def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1), do_moving_window=False, use_nci=False):
+    """guardCellManager::Init (Parallelization/GuardCellManager.cpp:62-172, 310-343) for: no MR,
+    not safe_guard_cells, FDTD solver; use_nci: the NCI corrector's 4 extra cells along z (:87-90,319-330).  Returns also ng_depos_J (:165) -- ng_J itself
     grows by stencil_length-1 = npass when the bilinear filter is on (:169-172); a moving window needs
     at least 2 guard cells everywhere (:103-115, one level)."""
     ng_EB, ng_J, ng_FG, ng_FS, ng_depos_J = [], [], [], [], []
     for d in range(3):
         ngt = nox
         ng = ngt + 1 if ngt % 2 else ngt
+        if use_nci and d == 2:
+            ng = ngt + 4 + ((ngt + 4) % 2)
         ngj0 = ngt
         if do_moving_window:
             ng, ngj0 = max(ng, 2), max(ngj0, 2)
         ngj = ngj0 + int(math.ceil(C_LIGHT * 0.5 * dt / dx[d]))
         fs = 1
         ng = max(ng, fs)
-        fg = max(min((nox + 1) // 2, ng), fs)
+        fg = min((nox + 1) // 2, ng)
+        if use_nci and d == 2:
+            fg = min(fg + 4, ng)
+        fg = max(fg, fs)
         ng_depos_J.append(ngj)
         if use_filter:
             ngj += filter_npass[d]
@@ -181,7 +205,7 @@ class Simulation:
                  solver=abi.SOLVER_YEE, cfl=1.0, dt=None, dist=None, sort_interval=4,
                  tile=(8, 8, 8), use_bins=True, device=None, native_driver=True,
                  use_filter=False, filter_npass=(1, 1, 1), boundaries=None, moving_window=None, nb=None,
-                 gamma_boost=1.0):
+                 gamma_boost=1.0, nci_stencils=None):
         """boundaries: abi.pic_boundaries (boundary.field_lo/hi, boundary.particle_lo/hi; default all
         periodic); moving_window: (direction, v/c) == warpx.do_moving_window / moving_window_dir /
         moving_window_v; nb: brick grid (default parallel.brick_grid(world); a moving window needs slabs
@@ -215,9 +239,14 @@ class Simulation:
         self.nonperiodic = not all(self.geom.periodic[d] for d in range(3))
         if (self.nonperiodic or moving_window is not None) and not (native_driver and use_bins):
             raise NotImplementedError("non-periodic / moving-window runs need the C++ driver")
+        # particles.use_fdtd_nci_corr: (stencil_exeybz, stencil_bxbyez) from nci_godfrey_stencils
+        self.nci_stencils = nci_stencils
+        if nci_stencils is not None and not (native_driver and use_bins):
+            raise NotImplementedError("the NCI corrector needs the C++ driver")
         self.lasers = []
         self.time = 0.0
-        g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass, moving_window is not None)
+        g = guard_cells(nox, self.dt, self.dx, self.use_filter, self.filter_npass, moving_window is not None,
+                        nci_stencils is not None)
         self.ng_EB, self.ng_J, self.ng_FG, self.ng_FS = g["ng_EB"], g["ng_J"], g["ng_FG"], g["ng_FS"]
         self.ng_depos_J = g["ng_depos_J"]
         self._filter_tmp = None
@@ -261,6 +290,9 @@ class Simulation:
                 check(self.L.pic_engine_set_moving_window(self.native, int(moving_window[0]), float(moving_window[1])))
             if self.gamma_boost > 1.0:
                 check(self.L.pic_engine_set_boost(self.native, self.gamma_boost, self.beta_boost))
+            if nci_stencils is not None:
+                check(self.L.pic_engine_set_nci_corrector(self.native, (C.c_double * 5)(*nci_stencils[0]),
+                                                          (C.c_double * 5)(*nci_stencils[1])))
             g12 = (C.c_int * 12)()
             self.L.pic_engine_guards(self.native, g12)
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS

@@ -75,6 +75,7 @@ def lib():
         "pic_engine_set_boundaries": (C.c_int, [vp, bndp]),
         "pic_engine_set_moving_window": (C.c_int, [vp, C.c_int, C.c_double]),
         "pic_engine_set_boost": (C.c_int, [vp, C.c_double, C.c_double]),
+        "pic_engine_set_nci_corrector": (C.c_int, [vp, dp, dp]),
         "pic_engine_set_injector": (C.c_int, [vp, C.c_int, injp]),
         "pic_engine_add_laser": (C.c_int, [vp, lasp, soap, C.c_long]),
         "pic_engine_laser_np": (C.c_long, [vp, C.c_int]),

@@ -180,7 +180,8 @@ def max_step_boost_accelerator(zmax_plasma, zmin_domain_boost, gamma_boost, movi
     return int(interaction_time_boost / dt)
 
 
-def laser_acceleration_boosted_3d(n_cell=(16, 16, 128), max_step=60, gamma_boost=10.0, density=1.e23):
+def laser_acceleration_boosted_3d(n_cell=(16, 16, 128), max_step=60, gamma_boost=10.0, density=1.e23,
+                                  use_fdtd_nci_corr=False):
     """BASELINE.json config 4 in the small: Examples/Tests/boosted_diags/
     inputs_test_3d_laser_acceleration_btd (CKC, Vay, order 3, bilinear filter, z moving window at c, PEC in
     z, Gaussian antenna, electrons + ions at rest in the lab with continuous injection, gamma_boost = 10)
@@ -194,7 +195,7 @@ def laser_acceleration_boosted_3d(n_cell=(16, 16, 128), max_step=60, gamma_boost
         n_cell=tuple(n_cell), prob_lo=lo, prob_hi=hi, gamma_boost=gamma_boost,
         field_lo=("periodic", "periodic", "pec"), field_hi=("periodic", "periodic", "pec"),
         nox=3, use_filter=True, cfl=1.0, moving_window_dir=2, moving_window_v=1.0, max_step=max_step,
-        solver=1, pusher=1,
+        solver=1, pusher=1, use_fdtd_nci_corr=bool(use_fdtd_nci_corr),      # particles.use_fdtd_nci_corr = 1 in the deck
         species=[dict(name="electrons", q=-Q_E, m=M_E, ppc=(1, 1, 1), density=density,
                       do_continuous_injection=True, **bounds),
                  dict(name="ions", q=Q_E, m=M_P, ppc=(1, 1, 1), density=density,
