@@ -528,7 +528,7 @@ void* orc_sim_create(const int* n_cell, const double* prob_lo, const double* pro
 // boundary.field_lo/hi, boundary.particle_lo/hi (Utils/WarpXUtil.cpp:470-540)
 int orc_sim_set_boundaries(void* h, const pic_boundaries* b) {
     Sim* s = static_cast<Sim*>(h);
-    if (s->boxes.size() != 1 || s->nspecies) return 1;
+    if (s->nspecies) return 1;             // (several boxes are fine here; the moving window and the antennas need one)
     s->bnd = *b;
     s->any_pec = false;
     for (int d = 0; d < 3; ++d) {

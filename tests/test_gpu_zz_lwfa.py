@@ -606,7 +606,9 @@ def test_laser_injection_golden_checksums(orc, cuda, golden):
 
 
 def test_pec_particle_golden_checksums(orc, cuda, golden):
-    """PEC walls in x with two particles 2 nm from the wall (Vay, order 3, filter); jx: see tests/test_oracle.py."""
+    """PEC walls in x with two particles 2 nm from the wall (Vay, order 3, filter).  jx is a unit-in-the-last-place
+    artefact of the deposition coordinate that depends on the box decomposition: on one box it is exactly twice
+    the value stored for the reference's two-box run (tests/test_oracle.py::test_pec_particle_golden_checksums)."""
     from warpx_b200.engine import Simulation
     wl = workloads.pec_particle_3d()
     sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], use_filter=wl["use_filter"],
