@@ -184,6 +184,9 @@ def run_engine(args):
         if args.deposit_mode:
             from warpx_b200.lib import lib as _piclib
             _piclib().pic_set_deposit_mode(args.deposit_mode)
+        if args.gather_mode:
+            from warpx_b200.lib import lib as _piclib
+            _piclib().pic_set_gather_mode(args.gather_mode)
         sim = Simulation(n_cell, prob_lo, prob_hi, nox=args.order, dist=dist, sort_interval=args.sort_interval,
                          native_driver=native, use_filter=bool(args.filter))
         sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
@@ -312,7 +315,7 @@ def run_engine(args):
                                                 ", random in-cell positions" if args.jitter else "",
                                                 "on (1 pass)" if args.filter else "off (SURVEY 8d)",
                                                 args.sort_interval)),
-                       "use_filter": int(args.filter), "deposit_mode": int(args.deposit_mode),
+                       "use_filter": int(args.filter), "deposit_mode": int(args.deposit_mode), "gather_mode": int(args.gather_mode),
                        "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
                                                      % (npart_local * 56 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
@@ -347,6 +350,9 @@ def main():
                     help="pic_set_deposit_mode: 0 register runs (default), 1 shared-memory tile block, 2 two lines per "
                          "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions "
                          "(A/B measurements; every mode passes the parity tests)")
+    ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="pic_set_gather_mode: 0 one particle per lane (default), 1 two particles of a cell per lane, "
+                         "2 the same without the 128-register cap (A/B measurement; same parity tests)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

@@ -191,6 +191,15 @@ int pic_gather_push(const pic_soa* p, long offset, long np,
                     int nox, int galerkin, int pusher, int push_position,
                     const pic_bins* bins, const pic_escape_list* escaped, void* stream);
 
+/* Which kernel the cell-sorted (bins != NULL) gather uses.  PIC_GATHER_TILE (default): one particle per lane.
+ * PIC_GATHER_PAIRS: a lane takes two particles of one cell and feeds both from one set of shared-memory loads
+ * (half the loads per particle); applies where the stencils of all particles of a cell coincide -- order 3 or 1
+ * with the Galerkin gather on the Yee grid -- other configurations keep the default kernel.  Same results
+ * (each particle's own accumulation order is unchanged).  PIC_GATHER_PAIRS_WIDE: the same kernel without the
+ * 128-register cap (254 registers, one CTA per SM).  Experiments until measured. */
+enum { PIC_GATHER_TILE = 0, PIC_GATHER_PAIRS = 1, PIC_GATHER_PAIRS_WIDE = 2 };
+void pic_set_gather_mode(int mode);
+
 /* WarpXParticleContainer::DepositCurrent (WarpXParticleContainer.cpp:352-827) ->
  * doEsirkepovDepositionShapeN<nox> (Deposition/CurrentDeposition.H:642-907).
  * J = {jx,jy,jz} is ADDED to (the caller zeroes J, MultiParticleContainer.cpp:467-478).

@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <map>
+#include <string>
 #include <vector>
 
 namespace simt {
@@ -48,6 +50,7 @@ struct Block {
     // collective scratch, one slot per lane of a warp
     std::vector<std::vector<unsigned long long>> slot;   // [warp][32]
     std::function<void()> body;
+    std::map<std::string, std::vector<char>> statics;    // __shared__ variables declared inside the kernel
 };
 
 inline Block*& cur_block() { static thread_local Block* b = nullptr; return b; }
@@ -77,6 +80,12 @@ inline void trampoline() {
 }
 
 inline void* dynamic_smem() { return cur_block()->smem.data(); }
+// a statically declared __shared__ array: one zero-initialised buffer per block, keyed by its name
+inline void* block_static(const char* name, size_t bytes) {
+    std::vector<char>& v = cur_block()->statics[name];
+    if (v.size() < bytes) v.assign(bytes, 0);
+    return v.data();
+}
 
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {

@@ -711,3 +711,65 @@ def test_deposit_variants_match_oracle(orc, dev, mode, nox, kind):
                             abi.int3(lo), sp["q"], dt, -0.5 * dt, nox)
     for c in range(3):
         assert rel_linf(tens[c].cpu().numpy(), J[c].a) <= 1e-12, "j" + "xyz"[c]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nox,kind", [(3, "sorted"), (3, "drifted"), (1, "drifted"), (2, "sorted")])
+def test_gather_variants_match_oracle(orc, dev, mode, nox, kind):
+    """pic_set_gather_mode(PIC_GATHER_PAIRS / _WIDE): two particles of a cell per lane, against the oracle's gather +
+    push, cell-sorted and after a drift of most of a cell (stray lists, lone survivors); order 2 keeps the default kernel."""
+    L = orc.lib()
+    n, lx = (24, 16, 16), 1.2e-5
+    box_lo, box_hi = box(n)
+    wl, sp = _particles(orc, n, (2, 2, 2), 0.3, lx)
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    ngEB = (4, 4, 4)
+    xyzmin, lo = lower_corner(prob_lo, dx, box_lo, ngEB)
+    F = random_fields(orc, box_lo, box_hi, ngEB, 5, comps=range(6), scale=[1e10] * 3 + [30.0] * 3)
+    P = orc.HostParticles(**{k: sp[k] for k in orc.HostParticles.NAMES})
+    arr, _ = dev.fabs(F)
+    E, B = (abi.pic_fab * 3)(*arr[0:3]), (abi.pic_fab * 3)(*arr[3:6])
+    dt = 0.9 * dx[0] / workloads.C
+    Pd, buf, bins_s, _, _ = _sorted_device_species(dev, P, n, prob_lo, wl["prob_hi"])
+    if kind == "drifted":
+        buf[0:3] += dev.t.tensor([[0.9 * dx[0]], [-0.7 * dx[1]], [0.8 * dx[2]]], device="cuda")
+    host = buf.cpu().numpy()
+    P = orc.HostParticles(**{k: host[i] for i, k in enumerate(orc.HostParticles.NAMES)})
+    dev.L.pic_set_gather_mode(mode)
+    try:
+        for push_position in (1, 0):
+            dev.ok(dev.L.pic_gather_push(C.byref(Pd), 0, P.np, E, B, abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                         sp["q"], sp["m"], dt, nox, 1, abi.PUSHER_BORIS, push_position, C.byref(bins_s),
+                                         None, dev.stream))
+            L.orc_gather_push(C.byref(P.soa), 0, P.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), abi.dbl3(dinv),
+                              abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], dt, nox, 1, abi.PUSHER_BORIS, push_position)
+        dev.sync()
+    finally:
+        dev.L.pic_set_gather_mode(0)
+    got = buf.cpu().numpy()
+    for i, k in enumerate(("x", "y", "z")):
+        assert np.max(np.abs(got[i] - getattr(P, k))) <= 1e-13 * lx, k
+    for i, k in ((4, "ux"), (5, "uy"), (6, "uz")):
+        assert rel_linf(got[i], getattr(P, k)) <= 1e-13, k
+
+
+def test_loop_with_pair_gather_matches_oracle(orc, cuda):
+    """Ten steps of the uniform-plasma deck (order 3, sort every 4 steps) with the pair gather against the oracle."""
+    from warpx_b200.lib import lib as piclib
+    wl = workloads.uniform_plasma_3d(n=16, ppc=(2, 2, 2), u_th=0.05, perturbation=0.01)
+    piclib().pic_set_gather_mode(1)
+    try:
+        sim, osim = _run_both(orc, cuda, wl, 3, 10, sort_interval=4)
+    finally:
+        piclib().pic_set_gather_mode(0)
+    for c in range(9):
+        d, a = sim.field_numpy(c)
+        _, oa = osim.fab(c)
+        assert rel_linf(a[d.valid_slices()], oa[d.valid_slices()]) <= 1e-9, abi.COMP_NAMES[c]
+    A, B = _match_particles(sim, osim, 0)
+    for k in ("x", "y", "z"):
+        assert np.max(np.abs(A[k] - B[k])) / sim.dx[0] <= 1e-10, k
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(A[k] - B[k])) / workloads.C <= 1e-11, k

@@ -57,3 +57,80 @@ def test_deposit_runs_kernels_under_simt_emulation(orc, simt, variant, nox, u_th
                                   abi.int3(lo), s["q"], dt, -0.5 * dt, nox, variant) == 0
     for c in range(3):
         assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the supercell gather + push kernels of warpx_b200/csrc/gather_push_tile.cu under the same emulator
+# ---------------------------------------------------------------------------------------------------------
+def host_bins(x, y, z, prob_lo, dx, n, tile):
+    """pic_bins on the host: the supercell-major bin of every particle (bins.cuh::bin_of_cell), a stable sort by bin
+    and the cell_start table -- what the device counting sort produces."""
+    n, tile = np.asarray(n), np.asarray(tile)
+    nt = (n + tile - 1) // tile
+    cell = [np.clip(np.floor((v - prob_lo[d]) / dx[d]).astype(np.int64), 0, n[d] - 1) for d, v in enumerate((x, y, z))]
+    t = [cell[d] // tile[d] for d in range(3)]
+    li = [cell[d] - t[d] * tile[d] for d in range(3)]
+    tid = t[0] + nt[0] * (t[1] + nt[1] * t[2])
+    b = tid * int(np.prod(tile)) + li[0] + tile[0] * (li[1] + tile[1] * li[2])
+    order = np.argsort(b, kind="stable")
+    nbins = int(np.prod(nt) * np.prod(tile))
+    cell_start = np.searchsorted(b[order], np.arange(nbins + 1)).astype(np.int32)
+    return order, cell_start
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("nox,galerkin,tile,kind", [(3, 1, (8, 8, 8), "sorted"), (3, 1, (8, 8, 8), "moved"),
+                                                    (3, 1, (4, 4, 4), "moved"), (1, 1, (8, 8, 8), "moved"),
+                                                    (2, 1, (4, 4, 4), "sorted"), (3, 0, (4, 4, 4), "sorted"),
+                                                    (3, 1, (8, 8, 8), "odd")])
+def test_gather_push_tile_kernels_under_simt_emulation(orc, simt, mode, nox, galerkin, tile, kind):
+    """gather_push_tile_kernel (mode 0) and gather_push_pair_kernel (modes 1, 2: two particles of a cell per lane)
+    against the oracle's gather + push: cell-sorted particles, particles that moved up to 0.9 cell since the sort
+    (stray lists, lone survivors of a pair), cells with odd counts, the fixed 8x8x8 and the run-time supercell.
+    Orders / gathers whose stencils do not coincide inside a cell fall back to the default kernel in modes 1, 2."""
+    if mode == 2 and kind != "sorted":
+        pytest.skip("the wide instance differs only in its register cap")
+    n = (16, 8, 8) if tile == (8, 8, 8) else (8, 8, 4)
+    lx = tuple(0.5e-6 * v for v in n)
+    wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(2, 1, 2) if kind != "odd" else (1, 1, 1), u_th=0.1, lx=lx, seed=11)
+    sp = wl["species"][0]
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    rng = np.random.default_rng(17)
+    arr = {k: sp[k].copy() for k in orc.HostParticles.NAMES}
+    if kind == "odd":            # 1, 2 or 3 particles per cell
+        extra = rng.integers(0, 3, len(arr["x"]))
+        for k in arr:
+            arr[k] = np.repeat(arr[k], 1 + extra)
+        for d, k in enumerate("xyz"):
+            arr[k] = arr[k] + rng.uniform(-0.49, 0.49, len(arr[k])) * dx[d]
+    order, cell_start = host_bins(arr["x"], arr["y"], arr["z"], prob_lo, dx, n, tile)
+    arr = {k: np.ascontiguousarray(v[order]) for k, v in arr.items()}
+    if kind == "moved":          # after the sort: bins are stale but must stay correct
+        for d, k in enumerate("xyz"):
+            arr[k] = arr[k] + rng.uniform(-0.9, 0.9, len(arr[k])) * dx[d]
+    P = orc.HostParticles(**arr)
+    Q = P.copy()
+    ngEB = (4, 4, 4)
+    box_hi = tuple(v - 1 for v in n)
+    xyzmin, lo = lower_corner(prob_lo, dx, (0, 0, 0), ngEB)
+    from helpers import random_fields
+    F = random_fields(orc, (0, 0, 0), box_hi, ngEB, 5, comps=range(6), scale=[1e10] * 3 + [30.0] * 3)
+    bins = abi.pic_bins()
+    bins.cell_start = cell_start.ctypes.data
+    for d in range(3):
+        bins.box_lo[d], bins.box_hi[d], bins.tile[d] = 0, box_hi[d], tile[d]
+    bins.np_binned = P.np
+    dt = 0.9 * dx[0] / workloads.C
+    for push_position in (1, 0):
+        assert simt.simt_gather_push(C.byref(Q.soa), orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), abi.dbl3(dinv),
+                                     abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], dt, nox, galerkin,
+                                     abi.PUSHER_BORIS, push_position, C.byref(bins), mode) == 0
+        orc.lib().orc_gather_push(C.byref(P.soa), 0, P.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), abi.dbl3(dinv),
+                                  abi.dbl3(xyzmin), abi.int3(lo), sp["q"], sp["m"], dt, nox, galerkin, abi.PUSHER_BORIS,
+                                  push_position)
+    for k in ("x", "y", "z"):
+        assert np.max(np.abs(getattr(Q, k) - getattr(P, k))) <= 1e-13 * lx[0], k
+    for k in ("ux", "uy", "uz"):
+        assert rel_linf(getattr(Q, k), getattr(P, k)) <= 1e-13, k

@@ -120,6 +120,75 @@ __device__ __forceinline__ void gather_fields(const Fields& fld, const GatherGeo
 }
 
 
+// ---- two particles per lane ------------------------------------------------------------------
+// Weight type (index into DirWeights::s / j0) and order of component c along direction d, exactly
+// as gather_fields selects them.
+template <bool YEE>
+__device__ __forceinline__ int weight_type(const GatherGeom& gg, int c, int d, bool lowered) {
+    return (lowered ? 2 : 0) + ((YEE ? yee_stag(c, d) : gg.stag[c][d]) ? 0 : 1);
+}
+__host__ __device__ constexpr bool lowered_along(int c, int d) { return (c < 3) ? (c == d) : (c != d + 3); }
+
+// Do the stencils of two particles start at the same grid points for every component?  (Always true
+// for two particles of one cell at order 3 or 1 with the Galerkin gather on the Yee grid: node weights
+// of order N and cell weights of order N - 1 both start at cell - 1, resp. cell.)
+template <int N, int G, bool YEE>
+__device__ __forceinline__ bool same_stencils(const GatherGeom& gg, const DirWeights<N, G>& ax, const DirWeights<N, G>& ay,
+                                              const DirWeights<N, G>& az, const DirWeights<N, G>& bx,
+                                              const DirWeights<N, G>& by, const DirWeights<N, G>& bz) {
+    bool same = true;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const int tx = weight_type<YEE>(gg, c, 0, lowered_along(c, 0));
+        const int ty = weight_type<YEE>(gg, c, 1, lowered_along(c, 1));
+        const int tz = weight_type<YEE>(gg, c, 2, lowered_along(c, 2));
+        same = same && ax.j0[tx] == bx.j0[tx] && ay.j0[ty] == by.j0[ty] && az.j0[tz] == bz.j0[tz];
+    }
+    return same;
+}
+
+// The six components at two particles with identical stencil points (same_stencils): each grid value is
+// loaded once and contracted with both weight sets.  Same accumulation order per particle as gather_fields.
+template <int N, int G, bool YEE, class Fields>
+__device__ __forceinline__ void gather_fields_pair(const Fields& fld, const GatherGeom& gg,
+                                                   const DirWeights<N, G>& ax, const DirWeights<N, G>& ay,
+                                                   const DirWeights<N, G>& az, const DirWeights<N, G>& bx,
+                                                   const DirWeights<N, G>& by, const DirWeights<N, G>& bz,
+                                                   double FA[6], double FB[6]) {
+    constexpr int M = N - G;
+#pragma unroll
+    for (int oc = 0; oc < 6; ++oc) {
+        const int c = (oc < 3) ? oc : (8 - oc);   // 0,1,2,5,4,3
+        const bool lx = lowered_along(c, 0), ly = lowered_along(c, 1), lz = lowered_along(c, 2);
+        const int tx = weight_type<YEE>(gg, c, 0, lx), ty = weight_type<YEE>(gg, c, 1, ly), tz = weight_type<YEE>(gg, c, 2, lz);
+        const int nx = lx ? M : N, ny = ly ? M : N, nz = lz ? M : N;
+        const auto F3 = fld.at(c, gg.lo[0] + ax.j0[tx], gg.lo[1] + ay.j0[ty], gg.lo[2] + az.j0[tz]);
+        double accA = 0.0, accB = 0.0;
+#pragma unroll
+        for (int iz = 0; iz <= N; ++iz) {
+            if (iz > nz) break;
+            double accyA = 0.0, accyB = 0.0;
+#pragma unroll
+            for (int iy = 0; iy <= N; ++iy) {
+                if (iy > ny) break;
+                double accxA = 0.0, accxB = 0.0;
+#pragma unroll
+                for (int ix = 0; ix <= N; ++ix) {
+                    if (ix > nx) break;
+                    const double f = F3(ix, iy, iz);
+                    accxA += ax.s[tx][ix] * f;
+                    accxB += bx.s[tx][ix] * f;
+                }
+                accyA += ay.s[ty][iy] * accxA;
+                accyB += by.s[ty][iy] * accxB;
+            }
+            accA += az.s[tz][iz] * accyA;
+            accB += bz.s[tz][iz] * accyB;
+        }
+        FA[c] = accA; FB[c] = accB;
+    }
+}
+
 // momentum + position update of one particle (PushSelector.H:88-102, UpdatePosition.H:36-44)
 __device__ __forceinline__ void push_particle(double& xp, double& yp, double& zp, double& ux,
                                               double& uy, double& uz, const double F[6],

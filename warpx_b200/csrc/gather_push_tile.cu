@@ -9,10 +9,19 @@
 // such lane would drag its whole warp through ~250 dependent global loads -- measured +40% kernel
 // time per step since the last sort): they are appended to a list and a second, order-agnostic
 // kernel pushes them with one thread each.  Any particle order is correct.
+//
+// gather_push_pair_kernel (pic_set_gather_mode(PIC_GATHER_PAIRS); order 3 or 1, Galerkin, Yee): the gather
+// is bound by the shared-memory data return (252 LDS.64 per particle = 15.75 clk per particle per SM,
+// against ~8 clk of fp64 work).  With the node weights at order N = 3 (1) and the cell weights at the
+// Galerkin order N - 1 = 2 (0) every stencil of a particle starts at `cell - 1` (`cell`) -- the SAME
+// points for all particles of a cell.  So a lane takes TWO particles of one cell and feeds both from
+// one set of loads: 126 LDS.64 per particle.  Particles that are not in the cell of their bin (moved
+// since the sort) go to the stray lists as before.
 #include "pic_common.cuh"
 #include "gather_common.cuh"
 #include "bins.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace pic {
 
@@ -42,10 +51,18 @@ struct SmemFields {
     }
 };
 
+#ifdef PIC_SIMT_HOST      // tests/host_harness only: the SIMT emulator copies synchronously
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 struct StrayList { int* idx; int* count; int cap; };
 
@@ -53,7 +70,7 @@ template <int N, int G, bool YEE, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
                         double dt, int pusher, int push_position, EscapeView esc, StrayList stray) {
-    extern __shared__ double smem[];
+    PIC_DYNAMIC_SMEM(double, smem);
     constexpr bool FIXED = TX > 0;
     const int BD0 = FIXED ? TX + 2 * GT_HALO : bins.tile[0] + 2 * GT_HALO;
     const int BD1 = FIXED ? TY + 2 * GT_HALO : bins.tile[1] + 2 * GT_HALO;
@@ -85,14 +102,14 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
         if (in) cp_async8(smem + n, F.p + F.off(gi, gj, gk));
         else smem[n] = 0.0;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_commit();
 
     // software prefetch: the next particle of this thread is requested before the current one is
     // gathered, so the HBM latency overlaps ~700 instructions of shared-memory gather + push
     double nx = 0, ny = 0, nz = 0, nux = 0, nuy = 0, nuz = 0;
     int ip = p_begin + threadIdx.x;
     if (ip < p_end) { nx = P.x[ip]; ny = P.y[ip]; nz = P.z[ip]; nux = P.ux[ip]; nuy = P.uy[ip]; nuz = P.uz[ip]; }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cp_async_wait_all();
     __syncthreads();
 
     // Lanes of a warp hold consecutive cell-sorted particles, i.e. particles of ONE (y,z) row of
@@ -100,8 +117,9 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     // cost about one wavefront each.  A particle that changed row since the sort makes every LDS of
     // its warp conflict; such particles (isolated row among their neighbours) are deferred to a
     // CTA-local list and gathered after the main sweep, so the regular warps stay conflict-free.
-    __shared__ int s_stray[GT_LOCAL_STRAYS];
-    __shared__ int s_nstray;
+    PIC_STATIC_SMEM(int, s_stray, GT_LOCAL_STRAYS);
+    PIC_STATIC_SMEM(int, s_nstray_, 1);
+    int& s_nstray = s_nstray_[0];
     if (threadIdx.x == 0) s_nstray = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -151,6 +169,168 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     }
 }
 
+
+// ---- two particles of one cell per lane ---------------------------------------------------------
+// Shared memory: [6][BD2][BD1][BD0] doubles of fields | pair_start[tvol + 1] | s_stray[GT_LOCAL_STRAYS] | s_nstray.
+// pair_start[c] = number of lane-pairs in the cells before c of this supercell (ceil(n_c / 2) each).
+// MINB = 2: 128 registers (80 B of spill traffic at order 3), 16 warps per SM like the default kernel;
+// MINB = 1: 254 registers, no spills, 8 warps per SM.
+constexpr int GP_THREADS = 256;
+
+template <int N, int G, bool YEE, int TX, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(GP_THREADS, MINB)
+gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
+                        double dt, int pusher, int push_position, EscapeView esc, StrayList stray) {
+    PIC_DYNAMIC_SMEM(double, smem);
+    constexpr bool FIXED = TX > 0;
+    const int BD0 = FIXED ? TX + 2 * GT_HALO : bins.tile[0] + 2 * GT_HALO;
+    const int BD1 = FIXED ? TY + 2 * GT_HALO : bins.tile[1] + 2 * GT_HALO;
+    const int BD2 = FIXED ? TZ + 2 * GT_HALO : bins.tile[2] + 2 * GT_HALO;
+    const int bvol = BD0 * BD1 * BD2;
+    const int t = blockIdx.x;
+    int tc[3];
+    tile_coords(bins, t, tc);
+    const int tvol = bins.tile[0] * bins.tile[1] * bins.tile[2];
+    const int* __restrict__ cs = bins.cell_start + (long)t * tvol;
+    const int p_begin = min(cs[0], bins.np_limit);
+    const int p_end = min(cs[tvol], bins.np_limit);
+    if (p_begin >= p_end) return;
+    const int t0 = bins.box_lo[0] + tc[0] * bins.tile[0];
+    const int t1 = bins.box_lo[1] + tc[1] * bins.tile[1];
+    const int t2 = bins.box_lo[2] + tc[2] * bins.tile[2];
+    SmemFields<FIXED ? TX + 2 * GT_HALO : 0, FIXED ? TY + 2 * GT_HALO : 0, FIXED ? TZ + 2 * GT_HALO : 0> sf;
+    sf.blk = smem; sf.o0 = t0 - GT_HALO; sf.o1 = t1 - GT_HALO; sf.o2 = t2 - GT_HALO;
+    sf.rb0 = BD0; sf.rb01 = BD0 * BD1; sf.rbvol = bvol;
+    int* pair_start = reinterpret_cast<int*>(smem + 6 * bvol);
+    int* s_stray = pair_start + tvol + 1;
+    int& s_nstray = s_stray[GT_LOCAL_STRAYS];
+
+    for (int n = threadIdx.x; n < 6 * bvol; n += GP_THREADS) {          // staging as in gather_push_tile_kernel
+        const int c = n / bvol, r = n - c * bvol;
+        const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
+        const FabView& F = gf.v[c];
+        const int gi = sf.o0 + li, gj = sf.o1 + lj, gk = sf.o2 + lk;
+        const bool in = gi >= F.lo0 && gi < F.lo0 + F.n0 && gj >= F.lo1 && gj < F.lo1 + F.n1 &&
+                        gk >= F.lo2 && gk < F.lo2 + F.n2;
+        if (in) cp_async8(smem + n, F.p + F.off(gi, gj, gk));
+        else smem[n] = 0.0;
+    }
+    cp_async_commit();
+
+    // pairs per cell, then an exclusive scan by warp 0 (each lane sums a chunk, shuffle scan across lanes)
+    for (int c = threadIdx.x; c < tvol; c += GP_THREADS) {
+        const int n_c = min(cs[c + 1], bins.np_limit) - min(cs[c], bins.np_limit);
+        pair_start[c + 1] = (n_c + 1) >> 1;
+    }
+    if (threadIdx.x == 0) { pair_start[0] = 0; s_nstray = 0; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int chunk = (tvol + 31) / 32;
+        const int c0 = lane * chunk, c1 = min(c0 + chunk, tvol);
+        int sum = 0;
+        for (int c = c0; c < c1; ++c) sum += pair_start[c + 1];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - sum;                       // pairs before this lane's chunk
+        for (int c = c0; c < c1; ++c) { run += pair_start[c + 1]; pair_start[c + 1] = run; }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int npairs = pair_start[tvol];
+
+    auto in_cell = [&](double xp, double yp, double zp, int ci, int cj, int ck, bool& in_tile) -> bool {
+        const int pi = gg.lo[0] + (int)((xp - gg.xyzmin[0]) * gg.dinv[0]);
+        const int pj = gg.lo[1] + (int)((yp - gg.xyzmin[1]) * gg.dinv[1]);
+        const int pk = gg.lo[2] + (int)((zp - gg.xyzmin[2]) * gg.dinv[2]);
+        in_tile = pi >= t0 && pi < t0 + bins.tile[0] && pj >= t1 && pj < t1 + bins.tile[1] &&
+                  pk >= t2 && pk < t2 + bins.tile[2];
+        return pi == ci && pj == cj && pk == ck;
+    };
+    auto defer = [&](int ipp, bool in_tile) -> bool {          // true: listed (handled later), false: lists full
+        if (in_tile) {
+            const int n = atomicAdd(&s_nstray, 1);
+            if (n < GT_LOCAL_STRAYS) { s_stray[n] = ipp; return true; }
+            return false;
+        }
+        const int n = atomicAdd(stray.count, 1);
+        if (n < stray.cap) { stray.idx[n] = ipp; return true; }
+        return false;
+    };
+    auto single = [&](int ipp, bool in_tile) {                 // one particle, alone (rare paths)
+        double xp = P.x[ipp], yp = P.y[ipp], zp = P.z[ipp], ux = P.ux[ipp], uy = P.uy[ipp], uz = P.uz[ipp];
+        double F[6];
+        if (in_tile) gather_fields<N, G, YEE>(sf, gg, xp, yp, zp, F);
+        else gather_fields<N, G, YEE>(gf, gg, xp, yp, zp, F);
+        push_particle(xp, yp, zp, ux, uy, uz, F, qdt2m, dt, pusher, push_position);
+        P.ux[ipp] = ux; P.uy[ipp] = uy; P.uz[ipp] = uz;
+        if (push_position) { P.x[ipp] = xp; P.y[ipp] = yp; P.z[ipp] = zp; esc.note(ipp, xp, yp, zp); }
+    };
+
+    for (int p = threadIdx.x; p < npairs; p += GP_THREADS) {
+        // cell of pair p: the last c with pair_start[c] <= p
+        int lo = 0, hi = tvol;                       // invariant: pair_start[lo] <= p < pair_start[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pair_start[mid] <= p) lo = mid; else hi = mid; }
+        const int c = lo;
+        const int cbeg = min(cs[c], bins.np_limit), cend = min(cs[c + 1], bins.np_limit);
+        const int ia = cbeg + 2 * (p - pair_start[c]);
+        int ib = ia + 1 < cend ? ia + 1 : -1;
+        const int li = c % bins.tile[0], lj = (c / bins.tile[0]) % bins.tile[1], lk = c / (bins.tile[0] * bins.tile[1]);
+        const int ci = t0 + li, cj = t1 + lj, ck = t2 + lk;
+        double xa = P.x[ia], ya = P.y[ia], za = P.z[ia];
+        bool a_tile, b_tile = false;
+        bool a_ok = in_cell(xa, ya, za, ci, cj, ck, a_tile);
+        double xb = xa, yb = ya, zb = za;
+        bool b_ok = false;
+        if (ib >= 0) { xb = P.x[ib]; yb = P.y[ib]; zb = P.z[ib]; b_ok = in_cell(xb, yb, zb, ci, cj, ck, b_tile); }
+        // a particle that left the cell of its bin is listed; when the lists are full it is pushed here, alone
+        // (todo: at most two per pair, one shared copy of the single-particle body below)
+        int todo[2] = {-1, -1};
+        bool todo_tile[2] = {false, false};
+        if (!a_ok && !defer(ia, a_tile)) { todo[0] = ia; todo_tile[0] = a_tile; }
+        if (ib >= 0 && !b_ok && !defer(ib, b_tile)) { todo[1] = ib; todo_tile[1] = b_tile; }
+        if (a_ok || b_ok) {
+        if (!a_ok) { xa = xb; ya = yb; za = zb; }                   // one survivor: it rides in both slots
+        if (!b_ok) { xb = xa; yb = ya; zb = za; }
+        const int ja = a_ok ? ia : ib, jb = b_ok ? ib : ia;
+        DirWeights<N, G> ax, ay, az, bx, by, bz;
+        ax.compute((xa - gg.xyzmin[0]) * gg.dinv[0]); ay.compute((ya - gg.xyzmin[1]) * gg.dinv[1]); az.compute((za - gg.xyzmin[2]) * gg.dinv[2]);
+        bx.compute((xb - gg.xyzmin[0]) * gg.dinv[0]); by.compute((yb - gg.xyzmin[1]) * gg.dinv[1]); bz.compute((zb - gg.xyzmin[2]) * gg.dinv[2]);
+        bool both = ja != jb;
+        if (both && !same_stencils<N, G, YEE>(gg, ax, ay, az, bx, by, bz)) {
+            // same cell but different stencil origins (orders / centerings other than the tuned ones): B goes alone
+            if (!defer(jb, true)) { todo[1] = jb; todo_tile[1] = true; }
+            bx = ax; by = ay; bz = az; xb = xa; yb = ya; zb = za;
+            both = false;
+        }
+        double FA[6], FB[6];
+        gather_fields_pair<N, G, YEE>(sf, gg, ax, ay, az, bx, by, bz, FA, FB);
+        {
+            double ux = P.ux[ja], uy = P.uy[ja], uz = P.uz[ja];
+            push_particle(xa, ya, za, ux, uy, uz, FA, qdt2m, dt, pusher, push_position);
+            P.ux[ja] = ux; P.uy[ja] = uy; P.uz[ja] = uz;
+            if (push_position) { P.x[ja] = xa; P.y[ja] = ya; P.z[ja] = za; esc.note(ja, xa, ya, za); }
+        }
+        if (both) {
+            double ux = P.ux[jb], uy = P.uy[jb], uz = P.uz[jb];
+            push_particle(xb, yb, zb, ux, uy, uz, FB, qdt2m, dt, pusher, push_position);
+            P.ux[jb] = ux; P.uy[jb] = uy; P.uz[jb] = uz;
+            if (push_position) { P.x[jb] = xb; P.y[jb] = yb; P.z[jb] = zb; esc.note(jb, xb, yb, zb); }
+        }
+        }
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k)
+            if (todo[k] >= 0) single(todo[k], todo_tile[k]);
+    }
+    __syncthreads();
+    const int nloc = min(s_nstray, GT_LOCAL_STRAYS);
+    for (int t2l = threadIdx.x; t2l < nloc; t2l += GP_THREADS) single(s_stray[t2l], true);
+}
+
 // the listed strays, one thread each, fields through the read-only global path
 template <int N, int G, bool YEE>
 __global__ void __launch_bounds__(128)
@@ -169,38 +349,75 @@ gather_push_listed_kernel(SoaView P, StrayList stray, GlobalFields fld, GatherGe
     }
 }
 
+// pic_set_gather_mode: PIC_GATHER_TILE (0, default), PIC_GATHER_PAIRS (1) / PIC_GATHER_PAIRS_WIDE (2): two particles
+// of a cell per lane, used for the orders / gathers whose stencils coincide inside a cell, i.e. order 3 or 1 with
+// the Galerkin gather on the Yee grid
+int g_gather_mode = 0;
+
 template <int N, int G>
 static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const GatherGeom& gg,
                   bool yee, double qdt2m, double dt, int pusher, int push_position, const EscapeView& esc,
                   cudaStream_t s) {
     const long bvol = (long)(bv.tile[0] + 2 * GT_HALO) * (bv.tile[1] + 2 * GT_HALO) * (bv.tile[2] + 2 * GT_HALO);
-    const size_t smem = (size_t)6 * bvol * sizeof(double);
-    constexpr size_t static_smem = sizeof(int) * (GT_LOCAL_STRAYS + 2);       // s_stray + s_nstray
+    const long tvol = (long)bv.tile[0] * bv.tile[1] * bv.tile[2];
+    const bool pairs = g_gather_mode != 0 && yee && G == 1 && (N == 3 || N == 1);
+    const bool wide = g_gather_mode == 2;
+    const size_t smem = (size_t)6 * bvol * sizeof(double) + (pairs ? sizeof(int) * (size_t)(tvol + 1 + GT_LOCAL_STRAYS + 1) : 0);
+    const size_t static_smem = pairs ? 0 : sizeof(int) * (GT_LOCAL_STRAYS + 2);       // s_stray + s_nstray
     if (smem + static_smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
     const int ntiles = bv.nt[0] * bv.nt[1] * bv.nt[2];
     const bool t888 = bv.tile[0] == 8 && bv.tile[1] == 8 && bv.tile[2] == 8;
     // stray list (stream-ordered scratch): a few per mille of the particles per step since the sort
     StrayList stray;
     stray.cap = (int)(bv.np_limit / 8 + 1024);
+#ifndef PIC_SIMT_HOST
     int* scratch = nullptr;
     if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(stray.cap + 1), s) != cudaSuccess)
         return fail("pic_gather_push: cannot allocate %ld B of scratch", (long)(sizeof(int) * (stray.cap + 1)));
     stray.count = scratch; stray.idx = scratch + 1;
     cudaMemsetAsync(stray.count, 0, sizeof(int), s);
-#define PIC_LAUNCH(YEE_, TX_, TY_, TZ_) do { \
-        auto k = gather_push_tile_kernel<N, G, YEE_, TX_, TY_, TZ_>; \
+#define PIC_LAUNCH_K(KERNEL, THREADS, ...) do { \
+        auto k = KERNEL<N, G, __VA_ARGS__>; \
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - static_smem - 1024)) != cudaSuccess) \
             return fail("pic_gather_push: cannot raise the dynamic shared memory limit"); \
-        k<<<ntiles, GT_THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc, stray); } while (0)
-    if (yee && t888) PIC_LAUNCH(true, 8, 8, 8);       // the tuned instance: immediate LDS offsets
-    else if (yee) PIC_LAUNCH(true, 0, 0, 0);
-    else PIC_LAUNCH(false, 0, 0, 0);
-#undef PIC_LAUNCH
+        k<<<ntiles, THREADS, smem, s>>>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc, stray); } while (0)
+    if (pairs) {
+        if constexpr (G == 1 && (N == 3 || N == 1)) {
+            if (t888 && wide) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 1);
+            else if (t888) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 2);
+            else PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 0, 0, 0, 2);
+        }
+    }
+    else if (yee && t888) PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, true, 8, 8, 8);       // the tuned instance: immediate LDS offsets
+    else if (yee) PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, true, 0, 0, 0);
+    else PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, false, 0, 0, 0);
+#undef PIC_LAUNCH_K
     if (yee) gather_push_listed_kernel<N, G, true><<<NUM_SMS * 8, 128, 0, s>>>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc);
     else gather_push_listed_kernel<N, G, false><<<NUM_SMS * 8, 128, 0, s>>>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc);
     count_launch(2);
     cudaFreeAsync(scratch, s);
     return check_launch("pic_gather_push(tile)") ? 0 : 1;
+#else       // tests/host_harness: the same kernels under the SIMT emulator (simt_host.h)
+    (void)s; (void)t888;
+    std::vector<int> scratch((size_t)stray.cap + 1, 0);
+    stray.count = scratch.data(); stray.idx = scratch.data() + 1;
+#define PIC_LAUNCH_K(KERNEL, THREADS, ...) \
+        ::simt::launch(dim3(ntiles), dim3(THREADS), smem + 64, [&] { KERNEL<N, G, __VA_ARGS__>(P, bv, gf, gg, qdt2m, dt, pusher, push_position, esc, stray); })
+    if (pairs) {
+        if constexpr (G == 1 && (N == 3 || N == 1)) {
+            if (t888 && wide) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 1);
+            else if (t888) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 2);
+            else PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 0, 0, 0, 2);
+        }
+    }
+    else if (yee && t888) PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, true, 8, 8, 8);
+    else if (yee) PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, true, 0, 0, 0);
+    else PIC_LAUNCH_K(gather_push_tile_kernel, GT_THREADS, false, 0, 0, 0);
+#undef PIC_LAUNCH_K
+    if (yee) ::simt::launch(dim3(4), dim3(128), 64, [&] { gather_push_listed_kernel<N, G, true>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc); });
+    else ::simt::launch(dim3(4), dim3(128), 64, [&] { gather_push_listed_kernel<N, G, false>(P, stray, gf, gg, qdt2m, dt, pusher, push_position, esc); });
+    return 0;
+#endif
 }
 
 int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fab E[3],

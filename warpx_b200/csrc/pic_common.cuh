@@ -29,8 +29,10 @@ bool check_launch(const char* what);  // cudaGetLastError after a launch
 // emulator that runs the kernel source on the host, see tests/host_harness/simt_host.h).
 #ifdef PIC_SIMT_HOST
 #define PIC_DYNAMIC_SMEM(T, name) T* name = reinterpret_cast<T*>(::simt::dynamic_smem())
+#define PIC_STATIC_SMEM(T, name, n) T* name = reinterpret_cast<T*>(::simt::block_static(#name, sizeof(T) * (n)))
 #else
 #define PIC_DYNAMIC_SMEM(T, name) extern __shared__ T name[]
+#define PIC_STATIC_SMEM(T, name, n) __shared__ T name[n]
 #endif
 
 // ---- array view: amrex::Array4 indexing (Fortran order, arbitrary lower bound) --------------

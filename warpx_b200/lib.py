@@ -33,6 +33,7 @@ def lib():
         "pic_version": (C.c_char_p, []),
         "pic_launch_count": (C.c_long, []),
         "pic_set_deposit_mode": (None, [C.c_int]),
+        "pic_set_gather_mode": (None, [C.c_int]),
         "pic_evolve_b": (C.c_int, [fabp, fabp, stp, C.c_double, vp]),
         "pic_evolve_e": (C.c_int, [fabp, fabp, fabp, stp, C.c_double, vp]),
         "pic_gather_push": (C.c_int, [soap, C.c_long, C.c_long, fabp, fabp, dp, dp, ip, C.c_double,
