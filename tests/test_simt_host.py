@@ -134,3 +134,49 @@ def test_gather_push_tile_kernels_under_simt_emulation(orc, simt, mode, nox, gal
         assert np.max(np.abs(getattr(Q, k) - getattr(P, k))) <= 1e-13 * lx[0], k
     for k in ("ux", "uy", "uz"):
         assert rel_linf(getattr(Q, k), getattr(P, k)) <= 1e-13, k
+
+
+@pytest.mark.parametrize("nox", [1, 2, 3, 4])
+def test_order_agnostic_kernels_under_simt_emulation(orc, simt, nox):
+    """deposit_global<N> and gather_push_global<N, G> (one thread per particle; the path of particle shape order 4
+    and of callers without cell bins) against the oracle, unsorted thermal particles, all three pushers."""
+    n, lx = (8, 6, 6), (4e-6, 3e-6, 3e-6)
+    wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(2, 1, 2), u_th=0.4, lx=lx, seed=9)
+    s = wl["species"][0]
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    dt = 0.95 / (np.sqrt(sum(1.0 / v ** 2 for v in dx)) * workloads.C)
+    box_hi = tuple(v - 1 for v in n)
+    # current deposition
+    P = orc.HostParticles(**{k: s[k] for k in orc.HostParticles.NAMES})
+    ngJ = (nox + 2,) * 3
+    xyzmin, lo = lower_corner(prob_lo, dx, (0, 0, 0), ngJ)
+    J = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    K = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    assert orc.lib().orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                           abi.int3(lo), s["q"], dt, -0.5 * dt, nox) == 0
+    assert simt.simt_deposit_global(C.byref(P.soa), orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                    s["q"], dt, -0.5 * dt, nox) == 0
+    for c in range(3):
+        assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]
+    # gather + push
+    from helpers import random_fields
+    ngEB = (4, 4, 4)
+    xyzmin, lo = lower_corner(prob_lo, dx, (0, 0, 0), ngEB)
+    F = random_fields(orc, (0, 0, 0), box_hi, ngEB, 5, comps=range(6), scale=[1e10] * 3 + [30.0] * 3)
+    for galerkin in (1, 0):
+        for pusher in (abi.PUSHER_BORIS, abi.PUSHER_VAY, abi.PUSHER_HC):
+            A = orc.HostParticles(**{k: s[k] for k in orc.HostParticles.NAMES})
+            B = A.copy()
+            for push_position in (1, 0):
+                orc.lib().orc_gather_push(C.byref(A.soa), 0, A.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
+                                          abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), s["q"], s["m"], dt, nox, galerkin,
+                                          pusher, push_position)
+                assert simt.simt_gather_push_global(C.byref(B.soa), orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
+                                                    abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), s["q"], s["m"], dt, nox,
+                                                    galerkin, pusher, push_position) == 0
+            for k in ("x", "y", "z"):
+                assert np.max(np.abs(getattr(A, k) - getattr(B, k))) <= 1e-13 * lx[0], (galerkin, pusher, k)
+            for k in ("ux", "uy", "uz"):
+                assert rel_linf(getattr(B, k), getattr(A, k)) <= 1e-13, (galerkin, pusher, k)

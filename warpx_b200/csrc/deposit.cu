@@ -70,6 +70,7 @@ extern int g_runs_variant;      // deposit_runs.cu
 
 }  // namespace pic
 
+#ifndef PIC_SIMT_HOST      // (tests/host_harness compiles the kernels above under its SIMT emulator and launches them itself)
 using namespace pic;
 
 extern "C" void pic_set_deposit_mode(int mode) {
@@ -119,3 +120,4 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
     count_launch();
     return check_launch("pic_deposit_esirkepov") ? 0 : 1;
 }
+#endif

@@ -32,6 +32,7 @@ gather_push_global(SoaView P, long np, GlobalFields fld, GatherGeom gg, double q
 
 }  // namespace pic
 
+#ifndef PIC_SIMT_HOST      // (tests/host_harness compiles the kernel above under its SIMT emulator and launches it itself)
 using namespace pic;
 
 namespace pic {
@@ -89,3 +90,4 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     count_launch();
     return check_launch("pic_gather_push") ? 0 : 1;
 }
+#endif
