@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""A/B of the experimental kernel variants on the benchmark workload, in ONE process (the 256^3 x 8 ppc state is
+generated and uploaded once): for every deposition variant (pic_set_deposit_mode 0..6) and gather variant
+(pic_set_gather_mode 0..2) the per-stage times of the step (CUDA events around every stage, Python sequencer)
+and the whole-step time of the C++ driver.  Not a bench value -- a ranking tool for a scarce GPU slot:
+
+    gpurun --timeout 900 -- 'python tools/ab_modes.py --cells 256 > gpurun_out/ab_modes.json'
+
+Every variant passes the same parity tests (tests/test_gpu_zz_lwfa.py::test_deposit_variants_match_oracle,
+::test_gather_variants_match_oracle); this script only times them."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, default=256)
+    ap.add_argument("--ppc", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=8, help="timed steps per variant (a multiple of the sort interval)")
+    ap.add_argument("--u-th", type=float, default=0.01)
+    ap.add_argument("--deposit-modes", default="0,2,3,4,5,6")
+    ap.add_argument("--gather-modes", default="0,1,2")
+    args = ap.parse_args()
+    import torch
+    from warpx_b200 import workloads
+    from warpx_b200.engine import Simulation
+    from warpx_b200.lib import lib
+    if not torch.cuda.is_available():
+        raise SystemExit("tools/ab_modes.py needs a CUDA device")
+    L = lib()
+    n = args.cells
+    wl = workloads.uniform_plasma_3d(n_cell=(n, n, n), ppc=(args.ppc,) * 3, lx=(40.0e-6,) * 3, u_th=args.u_th)
+    s = wl["species"][0]
+    names = ("x", "y", "z", "w", "ux", "uy", "uz")
+
+    def make(native):
+        sim = Simulation((n, n, n), wl["prob_lo"], wl["prob_hi"], nox=3, sort_interval=4, native_driver=native)
+        sim.add_species("electrons", s["q"], s["m"], *[torch.from_numpy(s[k]) for k in names])
+        return sim
+
+    def timed(sim, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sim.Evolve(steps, synchronize_last=False)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    combos = [(d, 0) for d in (int(v) for v in args.deposit_modes.split(","))] + \
+             [(0, g) for g in (int(v) for v in args.gather_modes.split(",")) if g]
+    out = {"cells": n, "ppc": args.ppc ** 3, "steps": args.steps, "variants": []}
+    # whole step, C++ driver
+    sim = make(True)
+    sim.Evolve(4, synchronize_last=False)
+    for d, g in combos + [combos[0]]:                    # the default again at the end: drift of the state
+        L.pic_set_deposit_mode(d)
+        L.pic_set_gather_mode(g)
+        sim.Evolve(4, synchronize_last=False)            # warm-up of this variant (one sort period)
+        out["variants"].append({"deposit_mode": d, "gather_mode": g, "ms_per_step": timed(sim, args.steps)})
+    del sim
+    torch.cuda.empty_cache()
+    # per stage, Python sequencer
+    sim = make(False)
+    sim.Evolve(4, synchronize_last=False)
+    for v in out["variants"][:-1]:
+        L.pic_set_deposit_mode(v["deposit_mode"])
+        L.pic_set_gather_mode(v["gather_mode"])
+        sim.enable_stage_timing(False)
+        sim.Evolve(4, synchronize_last=False)            # warm-up of this variant
+        sim.enable_stage_timing(True)                    # fresh event lists
+        sim.Evolve(4, synchronize_last=False)
+        v["stage_ms"] = {k: t[0] for k, t in sim.stage_ms().items()}
+    L.pic_set_deposit_mode(0)
+    L.pic_set_gather_mode(0)
+    # best of each family together
+    best_d = min((v for v in out["variants"][:-1] if v["gather_mode"] == 0), key=lambda v: v["ms_per_step"])
+    best_g = min((v for v in out["variants"][:-1] if v["deposit_mode"] == 0), key=lambda v: v["ms_per_step"])
+    out["best"] = {"deposit_mode": best_d["deposit_mode"], "gather_mode": best_g["gather_mode"]}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
