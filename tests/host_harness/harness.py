@@ -105,3 +105,67 @@ def simt():
                                           C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
     _SIMT = L
     return L
+
+
+# --------------------------------------------------------------------------------------------
+# The WHOLE library on the host: every file of warpx_b200/csrc (kernels, argument builders, the C++ step
+# driver engine.cu) compiled by g++ against the SIMT emulator, through the source transformer of cuda2host.py
+# (kernel<<<...>>>(...) -> SIMT_LAUNCH).  "Device" memory is host memory.  Same C ABI as the product library.
+# --------------------------------------------------------------------------------------------
+HOST_OUT = os.path.join(HERE, "_build", "libpic_host.so")
+_HOST = None
+
+
+def build_host_library():
+    from . import cuda2host
+    src_dir = os.path.join(HERE, "_build", "host_src")
+    srcs = cuda2host.transform_tree(CSRC, src_dir)
+    deps = srcs + [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cuh")] + \
+        [os.path.join(HERE, "simt_host.h"), os.path.join(ROOT, "include", "pic_b200.h")]
+    if os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    cuda = os.path.dirname(os.path.dirname(NVCC))
+    common = ["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-DPIC_SIMT_HOST", "-DPIC_HOST_HARNESS", "-include",
+              os.path.join(HERE, "simt_host.h"), "-I", os.path.join(cuda, "include"), "-I", src_dir,
+              "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas"]
+    import concurrent.futures
+    objs = [s[:-4] + ".o" for s in srcs]
+
+    def one(so):
+        src, obj = so
+        if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(d) for d in deps if not d.endswith(".cpp") or d == src):
+            return
+        subprocess.run(common + ["-c", src, "-o", obj], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    with concurrent.futures.ThreadPoolExecutor(8) as ex:
+        list(ex.map(one, zip(srcs, objs)))
+    subprocess.run(["/usr/bin/g++", "-shared", "-o", HOST_OUT] + objs + ["-L", os.path.join(cuda, "lib64"), "-lcudart", "-ldl"],
+                   check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return HOST_OUT
+
+
+def host_library():
+    """The product's C ABI, executed on the host (ctypes signatures of warpx_b200.lib.bind)."""
+    global _HOST
+    if _HOST is None:
+        from warpx_b200 import lib as piclib
+        L = piclib.bind(C.CDLL(build_host_library()))
+        L.pic_set_error_mode(abi.PIC_ERR_RETURN)
+        _HOST = L
+    return _HOST
+
+
+def host_simulation_class():
+    """warpx_b200.engine.Simulation driving the host library: CPU tensors hold the "device" arrays, there are no
+    streams.  Single rank, C++ step driver."""
+    import torch
+    from warpx_b200.engine import Simulation
+
+    class HostSimulation(Simulation):
+        def _backend(self, device):
+            return torch, host_library(), torch.device("cpu")
+
+        @property
+        def stream(self):
+            return None
+
+    return HostSimulation

@@ -34,10 +34,16 @@ struct Barrier {
 
 struct Fiber {
     ucontext_t ctx;
-    std::vector<char> stack;
+    char* stack = nullptr;           // from the per-thread pool below (reused by every block, never zero-filled)
     bool done = false;
     int warp = 0, lane = 0, tid = 0;
 };
+constexpr size_t STACK_BYTES = 1 << 17;
+inline char* pooled_stack(int tid) {
+    static thread_local std::vector<char*> pool;
+    while ((int)pool.size() <= tid) pool.push_back(static_cast<char*>(std::malloc(STACK_BYTES)));
+    return pool[(size_t)tid];
+}
 
 struct Block {
     std::vector<Fiber> fibers;
@@ -107,10 +113,10 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {
                     Fiber& f = blk.fibers[(size_t)t];
                     f.tid = t; f.warp = t / 32; f.lane = t % 32;
                     blk.warp_bar[(size_t)f.warp].expected += 1;
-                    f.stack.resize(1 << 18);
+                    f.stack = pooled_stack(t);
                     getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = f.stack.data();
-                    f.ctx.uc_stack.ss_size = f.stack.size();
+                    f.ctx.uc_stack.ss_sp = f.stack;
+                    f.ctx.uc_stack.ss_size = STACK_BYTES;
                     f.ctx.uc_link = &blk.sched;
                     makecontext(&f.ctx, (void (*)())trampoline, 0);
                 }
@@ -179,6 +185,18 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     simt::barrier_wait(b->warp_bar[(size_t)f.warp]);
     return m;
 }
+inline unsigned __match_any_sync(unsigned, int value) {
+    simt::Block* b = simt::cur_block();
+    simt::Fiber& f = simt::me();
+    b->slot[(size_t)f.warp][(size_t)f.lane] = (unsigned long long)(unsigned)value | (1ull << 40);   // bit 40: the lane took part
+    simt::barrier_wait(b->warp_bar[(size_t)f.warp]);
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) if (b->slot[(size_t)f.warp][(size_t)l] == ((unsigned long long)(unsigned)value | (1ull << 40))) m |= (1u << l);
+    simt::barrier_wait(b->warp_bar[(size_t)f.warp]);
+    // the slots of lanes that do not exist / already left must not match on the next collective
+    b->slot[(size_t)f.warp][(size_t)f.lane] = 0;
+    return m;
+}
 inline unsigned __activemask() { return 0xffffffffu; }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier_wait(simt::cur_block()->warp_bar[(size_t)simt::me().warp]); }
 inline void __syncthreads() { simt::barrier_wait(simt::cur_block()->block_bar); }
@@ -186,6 +204,10 @@ inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
 inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }
@@ -198,5 +220,47 @@ inline double max(double a, double b) { return a > b ? a : b; }
 
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+
+// ---- what tests/host_harness/cuda2host.py turns `kernel<<<grid, block, smem, stream>>>(args)` into ----
+#define SIMT_LAUNCH(grid, block, smem, stream, ...) \
+    ::simt::launch(dim3(grid), dim3(block), (size_t)(smem) + 64, [&] { __VA_ARGS__; })
+
+// ---- CUDA runtime calls of the host code: "device" memory is host memory, streams do not exist ----
+namespace simt {
+inline cudaError_t Malloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> inline cudaError_t Malloc(T** p, size_t n) { return Malloc(reinterpret_cast<void**>(p), n); }
+inline cudaError_t Free(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t Memset(void* p, int v, size_t n, cudaStream_t = nullptr) { __builtin_memset(p, v, n); return cudaSuccess; }
+inline cudaError_t Memcpy(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { __builtin_memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t Sync(cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t LastError() { return cudaSuccess; }
+}  // namespace simt
+#define cudaMalloc ::simt::Malloc
+#define cudaMallocHost ::simt::Malloc
+#define cudaFree ::simt::Free
+#define cudaFreeHost ::simt::Free
+#define cudaMemsetAsync ::simt::Memset
+#define cudaMemcpyAsync ::simt::Memcpy
+#define cudaStreamSynchronize ::simt::Sync
+#define cudaDeviceSynchronize ::simt::Sync
+#define cudaGetLastError ::simt::LastError
+#define cudaFuncSetAttribute(...) cudaSuccess
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+
+// ---- the one CUB call of the sort (two-phase API) ----
+namespace cub {
+struct DeviceScan {
+    template <class In, class Out>
+    static cudaError_t ExclusiveSum(void* temp, size_t& temp_bytes, In in, Out out, int n, cudaStream_t = nullptr) {
+        if (temp == nullptr) { temp_bytes = 256; return cudaSuccess; }
+        long run = 0;
+        for (int i = 0; i < n; ++i) { const auto v = in[i]; out[i] = (decltype(v))run; run += v; }
+        return cudaSuccess;
+    }
+};
+}  // namespace cub
+#define PIC_SIMT_NO_CUB_INCLUDE 1
 
 #endif

@@ -25,7 +25,15 @@ import os
 import numpy as np
 
 from . import abi, parallel
-from .lib import check, lib, require_cuda
+from .lib import check as _check_rc, lib, require_cuda
+
+_error_source = None      # the library whose pic_last_error() a failed call reports (the one the last Simulation loaded)
+
+
+def check(rc):
+    if rc != 0:
+        _check_rc(rc, _error_source)
+
 
 C_LIGHT = 299792458.0
 EP0 = 8.8541878128e-12
@@ -210,14 +218,14 @@ class Simulation:
         periodic); moving_window: (direction, v/c) == warpx.do_moving_window / moving_window_dir /
         moving_window_v; nb: brick grid (default parallel.brick_grid(world); a moving window needs slabs
         along its direction, e.g. (1, 1, world)).  Non-periodic runs use the C++ driver."""
-        self.torch = require_cuda()
+        global _error_source
+        self.torch, self.L, self.device = self._backend(device)
+        _error_source = self.L
         t = self.torch
-        self.L = lib()
         self.L.pic_set_error_mode(abi.PIC_ERR_RETURN)   # Python raises instead of abort()
         self.dist = dist
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
-        self.device = t.device("cuda", t.cuda.current_device()) if device is None else device
         self.n_cell = tuple(int(v) for v in n_cell)
         self.prob_lo, self.prob_hi = tuple(prob_lo), tuple(prob_hi)
         self.geom = abi.make_geom(n_cell, prob_lo, prob_hi)
@@ -319,6 +327,13 @@ class Simulation:
         if getattr(self, "comm", None):
             self.L.pic_comm_destroy(self.comm)
             self.comm = None
+
+    def _backend(self, device):
+        """(torch, library, device) of this run: a CUDA device and the nvcc-built library -- there is no CPU
+        fallback.  (tests/host_harness overrides this hook to run the SAME sources, compiled by g++ against its
+        SIMT emulator, for the CPU test-suite of a container without a GPU; nothing in the package does.)"""
+        t = require_cuda()
+        return t, lib(), (t.device("cuda", t.cuda.current_device()) if device is None else device)
 
     def enable_stage_timing(self, on=True):
         """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""

@@ -19,7 +19,12 @@ def lib():
     if not os.path.exists(path) or (os.path.isdir(_build.CSRC) and _build.stale()
                                     and os.path.exists(_build.NVCC)):
         path = _build.build()
-    L = C.CDLL(path)
+    _LIB = bind(C.CDLL(path))
+    return _LIB
+
+
+def bind(L):
+    """Declare argtypes / restype of every entry point of include/pic_b200.h on the loaded library."""
     fabp, soap, stp, gp, bp = (C.POINTER(abi.pic_fab), C.POINTER(abi.pic_soa),
                                C.POINTER(abi.pic_stencil), C.POINTER(abi.pic_geom),
                                C.POINTER(abi.pic_bins))
@@ -89,7 +94,6 @@ def lib():
         fn.restype = res
         fn.argtypes = args
     L._declared = sorted(sig)
-    _LIB = L
     return L
 
 
