@@ -168,4 +168,97 @@ def host_simulation_class():
         def stream(self):
             return None
 
+        def _sync(self):
+            pass
+
     return HostSimulation
+
+
+# --------------------------------------------------------------------------------------------
+# Several "ranks" on the host: threads of this process, each with its own engine instance of the host library,
+# exchanging through fake_nccl.cpp (selected with PIC_NCCL_LIBRARY) -- the multi-rank paths of the C++ step driver
+# (NCCL halo sweeps, particle migration, slabs along a non-periodic axis) without a GPU.
+# --------------------------------------------------------------------------------------------
+FAKE_NCCL = os.path.join(HERE, "_build", "libpic_fake_nccl.so")
+
+
+def build_fake_nccl():
+    src = os.path.join(HERE, "fake_nccl.cpp")
+    if not os.path.exists(FAKE_NCCL) or os.path.getmtime(src) > os.path.getmtime(FAKE_NCCL):
+        os.makedirs(os.path.dirname(FAKE_NCCL), exist_ok=True)
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-o", FAKE_NCCL, src],
+                       check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return FAKE_NCCL
+
+
+class ThreadDist:
+    """The few torch.distributed calls warpx_b200.engine.Simulation makes, between threads."""
+
+    class ReduceOp:
+        SUM, MAX = "sum", "max"
+
+    class _Shared:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, shared, rank):
+        self.shared, self.rank = shared, rank
+
+    def get_rank(self):
+        return self.rank
+
+    def get_world_size(self):
+        return self.shared.world
+
+    def barrier(self):
+        self.shared.barrier.wait()
+
+    def broadcast(self, tensor, src):
+        sh = self.shared
+        if self.rank == src:
+            sh.slots[src] = tensor.clone()
+        sh.barrier.wait()
+        if self.rank != src:
+            tensor.copy_(sh.slots[src])
+        sh.barrier.wait()
+
+    def all_reduce(self, tensor, op=None):
+        import torch
+        sh = self.shared
+        sh.slots[self.rank] = tensor.clone()
+        sh.barrier.wait()
+        stack = torch.stack(sh.slots)
+        res = stack.max(dim=0).values if op == self.ReduceOp.MAX else stack.sum(dim=0)
+        sh.barrier.wait()
+        tensor.copy_(res)
+
+
+def run_ranks(world, fn):
+    """fn(rank, dist) on `world` threads; returns the list of results (re-raises the first exception)."""
+    import threading
+    os.environ["PIC_NCCL_LIBRARY"] = build_fake_nccl()
+    host_library()                       # build / load once, before the threads start
+    shared = ThreadDist._Shared(world)
+    out, err = [None] * world, [None] * world
+
+    def target(r):
+        try:
+            out[r] = fn(r, ThreadDist(shared, r))
+        except BaseException as e:       # noqa: BLE001 -- reported to the caller below
+            err[r] = e
+            shared.barrier.abort()
+    threads = [threading.Thread(target=target, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in err:
+        if e is not None:
+            raise e
+    return out

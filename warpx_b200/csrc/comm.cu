@@ -11,6 +11,7 @@
 #include "pic_common.cuh"
 #include "comm.cuh"
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 
 namespace pic {
@@ -20,6 +21,8 @@ NcclApi g_nccl;
 static void* nccl_handle() {
     static void* h = nullptr;
     if (h) return h;
+    // PIC_NCCL_LIBRARY: bind this library instead of the libnccl.so.2 already loaded / found by the loader
+    if (const char* path = getenv("PIC_NCCL_LIBRARY")) { h = dlopen(path, RTLD_NOW | RTLD_GLOBAL); return h; }
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (h) return h; }   // already loaded?
     for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) return h; }

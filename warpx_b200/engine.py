@@ -313,7 +313,7 @@ class Simulation:
                     ident.copy_(t.tensor(list(raw), dtype=t.uint8))
                 dist.broadcast(ident, 0)
                 raw = (C.c_ubyte * 128)(*ident.cpu().tolist())
-                t.cuda.synchronize()
+                self._sync()
                 self.comm = self.L.pic_comm_create(raw, self.world, self.rank)
                 if not self.comm:
                     raise RuntimeError(self.L.pic_last_error().decode())
@@ -335,6 +335,9 @@ class Simulation:
         t = require_cuda()
         return t, lib(), (t.device("cuda", t.cuda.current_device()) if device is None else device)
 
+    def _sync(self):
+        self.torch.cuda.synchronize()
+
     def enable_stage_timing(self, on=True):
         """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""
         self.stage_events = {} if on else None
@@ -352,7 +355,7 @@ class Simulation:
 
     def stage_ms(self):
         """Average milliseconds per call of every timed stage (synchronises)."""
-        self.torch.cuda.synchronize()
+        self._sync()
         return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in self.stage_events.items()}
 
     # ------------------------------------------------------------------------------------
