@@ -67,9 +67,9 @@ _SIMT = None
 
 def build_simt():
     deps = [os.path.join(HERE, "simt_host.h"), os.path.join(HERE, "simt_deposit.cpp"), os.path.join(HERE, "simt_gather.cpp"),
-            os.path.join(HERE, "simt_global.cpp"), os.path.join(ROOT, "include", "pic_b200.h")] + \
+            os.path.join(ROOT, "include", "pic_b200.h")] + \
            [os.path.join(CSRC, f) for f in ("deposit_runs.cu", "deposit_common.cuh", "pic_common.cuh", "runtime.cu",
-                                            "gather_push_tile.cu", "gather_common.cuh", "bins.cuh", "deposit.cu", "gather_push.cu")]
+                                            "gather_push_tile.cu", "gather_common.cuh", "bins.cuh")]
     if os.path.exists(SIMT_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SIMT_OUT) for d in deps):
         return SIMT_OUT
     os.makedirs(os.path.dirname(SIMT_OUT), exist_ok=True)
@@ -77,8 +77,7 @@ def build_simt():
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DPIC_SIMT_HOST", "-include",
            os.path.join(HERE, "simt_host.h"), "-x", "c++", "-I", os.path.join(cuda, "include"), "-I", CSRC,
            "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas",
-           os.path.join(HERE, "simt_deposit.cpp"), os.path.join(HERE, "simt_gather.cpp"), os.path.join(HERE, "simt_global.cpp"),
-           os.path.join(CSRC, "runtime.cu"),
+           os.path.join(HERE, "simt_deposit.cpp"), os.path.join(HERE, "simt_gather.cpp"), os.path.join(CSRC, "runtime.cu"),
            "-o", SIMT_OUT,
            "-L", os.path.join(cuda, "lib64"), "-lcudart"]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
@@ -97,12 +96,6 @@ def simt():
     L.simt_gather_push.restype = C.c_int
     L.simt_gather_push.argtypes = [soap, fabp, fabp, abi.c_double_p, abi.c_double_p, abi.c_int_p, C.c_double, C.c_double,
                                    C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.pic_bins), C.c_int]
-    L.simt_deposit_global.restype = C.c_int
-    L.simt_deposit_global.argtypes = [soap, fabp, abi.c_double_p, abi.c_double_p, abi.c_int_p, C.c_double, C.c_double,
-                                      C.c_double, C.c_int]
-    L.simt_gather_push_global.restype = C.c_int
-    L.simt_gather_push_global.argtypes = [soap, fabp, fabp, abi.c_double_p, abi.c_double_p, abi.c_int_p, C.c_double,
-                                          C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
     _SIMT = L
     return L
 

@@ -137,9 +137,12 @@ def test_gather_push_tile_kernels_under_simt_emulation(orc, simt, mode, nox, gal
 
 
 @pytest.mark.parametrize("nox", [1, 2, 3, 4])
-def test_order_agnostic_kernels_under_simt_emulation(orc, simt, nox):
+def test_order_agnostic_kernels_under_simt_emulation(orc, nox):
     """deposit_global<N> and gather_push_global<N, G> (one thread per particle; the path of particle shape order 4
-    and of callers without cell bins) against the oracle, unsorted thermal particles, all three pushers."""
+    and of callers without cell bins) against the oracle, unsorted thermal particles, all three pushers -- through
+    the C ABI of the host library (pic_deposit_esirkepov / pic_gather_push with bins = NULL)."""
+    from host_harness import harness
+    hl = harness.host_library()
     n, lx = (8, 6, 6), (4e-6, 3e-6, 3e-6)
     wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(2, 1, 2), u_th=0.4, lx=lx, seed=9)
     s = wl["species"][0]
@@ -156,8 +159,8 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, simt, nox):
     K = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
     assert orc.lib().orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
                                            abi.int3(lo), s["q"], dt, -0.5 * dt, nox) == 0
-    assert simt.simt_deposit_global(C.byref(P.soa), orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
-                                    s["q"], dt, -0.5 * dt, nox) == 0
+    assert hl.pic_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                    s["q"], dt, -0.5 * dt, nox, None, None) == 0, hl.pic_last_error()
     for c in range(3):
         assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]
     # gather + push
@@ -173,9 +176,9 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, simt, nox):
                 orc.lib().orc_gather_push(C.byref(A.soa), 0, A.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
                                           abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), s["q"], s["m"], dt, nox, galerkin,
                                           pusher, push_position)
-                assert simt.simt_gather_push_global(C.byref(B.soa), orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
-                                                    abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), s["q"], s["m"], dt, nox,
-                                                    galerkin, pusher, push_position) == 0
+                assert hl.pic_gather_push(C.byref(B.soa), 0, B.np, orc.fab_array(F[0:3]), orc.fab_array(F[3:6]),
+                                          abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo), s["q"], s["m"], dt, nox,
+                                          galerkin, pusher, push_position, None, None, None) == 0, hl.pic_last_error()
             for k in ("x", "y", "z"):
                 assert np.max(np.abs(getattr(A, k) - getattr(B, k))) <= 1e-13 * lx[0], (galerkin, pusher, k)
             for k in ("ux", "uy", "uz"):
