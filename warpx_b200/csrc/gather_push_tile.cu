@@ -52,10 +52,12 @@ struct SmemFields {
 };
 
 #ifdef PIC_SIMT_HOST      // tests/host_harness only: the SIMT emulator copies synchronously
+__device__ __forceinline__ void prefetch_l1(const void*) {}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
 #else
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
@@ -282,6 +284,8 @@ gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
         const int li = c % bins.tile[0], lj = (c / bins.tile[0]) % bins.tile[1], lk = c / (bins.tile[0] * bins.tile[1]);
         const int ci = t0 + li, cj = t1 + lj, ck = t2 + lk;
         double xa = P.x[ia], ya = P.y[ia], za = P.z[ia];
+        // the momenta are needed only after ~1500 instructions of gather: request the lines now (no registers held)
+        prefetch_l1(P.ux + ia); prefetch_l1(P.uy + ia); prefetch_l1(P.uz + ia);
         bool a_tile, b_tile = false;
         bool a_ok = in_cell(xa, ya, za, ci, cj, ck, a_tile);
         double xb = xa, yb = ya, zb = za;
