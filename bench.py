@@ -41,6 +41,31 @@ class ClockSampler:
         self.rows, self.proc, self.idx = [], None, gpu_index
 
     def start(self):
+        # NVML (pynvml) when it loads: a sample every 5 ms, so that even a 100 ms timed region is covered;
+        # otherwise the nvidia-smi loop of the recipe (one sample per 100 ms)
+        self.nvml_rows, self._stop, self._thread = [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(h)                                   # raises here if unsupported, before the thread starts
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.nvml_rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), smax,
+                                               int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -53,7 +78,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    # NVML clocks-event-reason bits (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
     def stop(self):
+        if getattr(self, "_thread", None) is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            sm = sorted(r[0] for r in self.nvml_rows)
+            reasons = set()
+            for r in self.nvml_rows:
+                for bit, name in self.NVML_REASONS:
+                    if r[2] & bit:
+                        reasons.add(name)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.nvml_rows[0][1] if sm else None,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -72,7 +111,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
