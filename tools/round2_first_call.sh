@@ -6,7 +6,7 @@
 # Usage:  gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 set -u
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/gpu_tests.txt 2>&1
+python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/gpu_tests.txt 2>&1
 echo "pytest exit: $?" >> gpurun_out/gpu_tests.txt
 tail -5 gpurun_out/gpu_tests.txt
 python tools/ab_modes.py --cells 256 > gpurun_out/ab_modes.json 2> gpurun_out/ab_modes.err
