@@ -434,6 +434,18 @@ double pic_engine_dt(void* engine);
 void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);
 int pic_engine_set_fields(void* engine, const pic_fab fabs[9]);
 int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
+/* The engine's decomposition as a guard-cell context (an engine created only for this needs pic_engine_create,
+ * pic_engine_set_boundaries for non-periodic axes and pic_engine_set_comm; with one rank no communicator):
+ *   pic_halo_copy  <- ablastr::utils::communication::FillBoundary(mf, ng, ..., period)
+ *                     (Source/ablastr/utils/Communication.cpp:71-115; WarpX::FillBoundaryE/B, WarpXComm.cpp:699-827)
+ *   pic_halo_add   <- ablastr::utils::communication::SumBoundary(mf, icomp, ncomp, src_ng, dst_ng, ..., period)
+ *                     (:148-175; WarpXSumGuardCells.cpp:17-24 passes dst_ng = all guards)
+ * for nfab components of this rank's box (all with at least ng / src_ng / dst_ng allocated guard cells): axis sweeps
+ * with local copies where the box spans a periodic axis, pack -> ncclSend/ncclRecv -> unpack(+add) elsewhere; guard
+ * cells beyond a non-periodic domain face have no image and keep their values (pic_halo_add: their own deposits;
+ * along a non-periodic direction src_ng must equal dst_ng, as in every SumBoundary WarpX issues). */
+int pic_halo_copy(void* engine, const pic_fab* fabs, int nfab, const int ng[3], void* stream);
+int pic_halo_add(void* engine, const pic_fab* fabs, int nfab, const int src_ng[3], const int dst_ng[3], void* stream);
 /* Non-periodic runs (one rank; call in this order, before pic_engine_set_fields / add_species):
  *   set_boundaries     boundary.field_lo/hi + boundary.particle_lo/hi (PEC walls, absorbing / reflecting particles);
  *   set_moving_window  warpx.do_moving_window / moving_window_dir / moving_window_v [c] (grows the guard

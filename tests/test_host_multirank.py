@@ -110,3 +110,82 @@ def test_z_slabs_with_moving_window_match_oracle(orc, hh, world):
     for k in ("ux", "uy", "uz"):
         a = np.concatenate([res[r]["parts"][k] for r in range(world)])[order]
         assert np.max(np.abs(a - B[k])) / workloads.C <= 1e-10, k
+
+
+@pytest.mark.parametrize("nb,periodic", [((2, 1, 1), (1, 1, 1)), ((2, 2, 2), (1, 1, 1)), ((1, 1, 2), (1, 1, 0))])
+def test_halo_copy_and_add_match_oracle(orc, hh, nb, periodic):
+    """pic_halo_copy / pic_halo_add -- the one-call replacements of ablastr's FillBoundary / SumBoundary -- on random
+    data over bricks (thread ranks, NCCL stand-in) against the oracle's multi-box FillBoundary / SumBoundary: every
+    staggering, ng below and at the allocated width, a non-periodic axis split into slabs."""
+    import ctypes as C
+    L = hh.host_library()
+    world = nb[0] * nb[1] * nb[2]
+    n = tuple(8 * v for v in nb)
+    ngalloc = (3, 3, 3)
+    geom = abi.make_geom(n, (0.0, 0.0, 0.0), tuple(float(v) for v in n), periodic=periodic)
+    comps = (0, 4, 8, 6)                      # Ex, By, jz, jx staggerings
+    decs = [parallel.Decomposition(n, nb, r) for r in range(world)]
+    rng = np.random.default_rng(3)
+    # valid points from one global array per component, so that the points shared by neighbouring boxes and the periodic
+    # duplicates hold equal values (what every FillBoundary / SumBoundary of a run sees); guard cells start random
+    start = [[None] * len(comps) for _ in decs]
+    for k, c in enumerate(comps):
+        stag = abi.YEE_STAG[c]
+        G = rng.standard_normal(tuple(n[2 - ax] + stag[2 - ax] for ax in range(3)))
+        for d in range(3):
+            if periodic[d] and stag[d]:
+                ax = 2 - d
+                hi, lo = [slice(None)] * 3, [slice(None)] * 3
+                hi[ax], lo[ax] = n[d], 0
+                G[tuple(hi)] = G[tuple(lo)]
+        for r, dec in enumerate(decs):
+            f = abi.make_fab(None, dec.box_lo, dec.box_hi, ngalloc, stag)
+            a = rng.standard_normal(f.shape)
+            sl = tuple(slice(dec.box_lo[2 - ax], dec.box_hi[2 - ax] + 1 + stag[2 - ax]) for ax in range(3))
+            a[f.valid_slices()] = G[sl]
+            start[r][k] = a
+
+    def run(op, ng, src_ng=None):
+        def rank_fn(rank, dist):
+            ident = __import__("torch").zeros(128, dtype=__import__("torch").uint8)
+            if rank == 0:
+                raw = (C.c_ubyte * 128)()
+                assert L.pic_comm_unique_id(raw) == 0
+                ident.copy_(__import__("torch").tensor(list(raw), dtype=__import__("torch").uint8))
+            dist.broadcast(ident, 0)
+            comm = L.pic_comm_create((C.c_ubyte * 128)(*ident.tolist()), world, rank)
+            assert comm
+            d = decs[rank]
+            eng = L.pic_engine_create(C.byref(geom), abi.int3(d.box_lo), abi.int3(d.box_hi), 1, 1, 0, 0, 1.0, 0.0, 4, 0, abi.int3((1, 1, 1)))
+            if not all(periodic):
+                names = ["periodic" if p else "pec" for p in periodic]
+                assert L.pic_engine_set_boundaries(eng, C.byref(abi.make_boundaries(names, names))) == 0
+            assert L.pic_engine_set_comm(eng, comm, abi.int3(nb)) == 0, L.pic_last_error()
+            fabs = [orc.HostFab(d.box_lo, d.box_hi, ngalloc, abi.YEE_STAG[c], data=start[rank][k].copy()) for k, c in enumerate(comps)]
+            arr = orc.fab_array(fabs)
+            if op == "copy":
+                rc = L.pic_halo_copy(eng, arr, len(fabs), abi.int3(ng), None)
+            else:
+                rc = L.pic_halo_add(eng, arr, len(fabs), abi.int3(src_ng), abi.int3(ng), None)
+            assert rc == 0, L.pic_last_error()
+            dist.barrier()
+            L.pic_engine_destroy(eng)
+            L.pic_comm_destroy(comm)
+            return [f.a.copy() for f in fabs]
+        return hh.run_ranks(world, rank_fn)
+
+    for op, ng, src_ng in (("copy", (2, 1, 3), None), ("copy", (3, 3, 3), None), ("add", (3, 3, 3), (2, 2, 2) if all(periodic) else (2, 2, 3)),
+                           ("add", (3, 3, 3), (3, 3, 3))):
+        got = run(op, ng, src_ng)
+        for k, c in enumerate(comps):
+            boxes = [orc.HostFab(d.box_lo, d.box_hi, ngalloc, abi.YEE_STAG[c], data=start[r][k].copy()) for r, d in enumerate(decs)]
+            arr = orc.fab_array(boxes)
+            if op == "copy":
+                orc.lib().orc_fill_boundary(arr, world, abi.int3(ng), C.byref(geom))
+            else:
+                orc.lib().orc_sum_boundary(arr, world, abi.int3(src_ng), abi.int3(ng), C.byref(geom))
+            for r in range(world):
+                # AMReX touches the box grown by ng only; the axis sweeps here also rewrite (never-read) cells beyond it
+                sl = tuple(slice(ngalloc[2 - ax] - ng[2 - ax], boxes[r].a.shape[ax] - (ngalloc[2 - ax] - ng[2 - ax])) for ax in range(3))
+                scale = np.max(np.abs(boxes[r].a[sl]))
+                assert np.max(np.abs(got[r][k][sl] - boxes[r].a[sl])) <= 1e-14 * scale, (op, ng, src_ng, abi.COMP_NAMES[c], r)

@@ -730,6 +730,38 @@ extern "C" int pic_engine_set_comm(void* h, void* comm, const int nb[3]) {
     }
     return 0;
 }
+// ---- the decomposition as a guard-cell context: the one-call replacements of the reference's comm wrappers ----
+// ablastr::utils::communication::FillBoundary(mf, ng, ..., period) (Source/ablastr/utils/Communication.cpp:71-115) as
+// called by WarpX::FillBoundaryE/B (Source/Parallelization/WarpXComm.cpp:699-827): guards <- valid, over the bricks.
+extern "C" int pic_halo_copy(void* h, const pic_fab* fabs, int nfab, const int ng[3], void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(fabs && nfab > 0, "pic_halo_copy: no components");
+    for (int c = 0; c < nfab; ++c)
+        for (int d = 0; d < 3; ++d) PIC_REQUIRE(ng[d] >= 0 && ng[d] <= fabs[c].ng[d], "pic_halo_copy: ng[%d] = %d exceeds the allocated guard cells", d, ng[d]);
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(*e, fabs, nfab, d, ng[d], 0, stream));
+    return 0;
+}
+// ablastr::utils::communication::SumBoundary(mf, icomp, ncomp, src_ng, dst_ng, ..., period) (:148-175) as called by
+// WarpXSumGuardCells (Source/Parallelization/WarpXSumGuardCells.cpp:17-24): valid += guards of the neighbours within
+// src_ng, then the first dst_ng guard cells take the summed values (WarpX passes dst_ng = all guards).
+extern "C" int pic_halo_add(void* h, const pic_fab* fabs, int nfab, const int src_ng[3], const int dst_ng[3], void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(fabs && nfab > 0, "pic_halo_add: no components");
+    for (int c = 0; c < nfab; ++c)
+        for (int d = 0; d < 3; ++d)
+            PIC_REQUIRE(src_ng[d] >= 0 && src_ng[d] <= fabs[c].ng[d] && dst_ng[d] >= 0 && dst_ng[d] <= fabs[c].ng[d],
+                        "pic_halo_add: src_ng / dst_ng exceed the allocated guard cells along %d", d);
+    // beyond a non-periodic domain face AMReX zeroes the guard layers between src_ng and dst_ng (they are not in its
+    // temporary); WarpX always sums with src_ng = dst_ng = all guards there (WarpXComm.cpp:1396-1420), which is the
+    // case built here
+    for (int d = 0; d < 3; ++d)
+        PIC_REQUIRE(e->geom.periodic[d] || src_ng[d] == dst_ng[d],
+                    "pic_halo_add: along the non-periodic direction %d src_ng (%d) and dst_ng (%d) must be equal", d, src_ng[d], dst_ng[d]);
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(*e, fabs, nfab, d, src_ng[d], 1, stream));
+    for (int d = 0; d < 3; ++d) ENG_CALL(halo_sweep(*e, fabs, nfab, d, dst_ng[d], 0, stream, true));
+    return 0;
+}
+
 // ---- non-periodic runs ------------------------------------------------------------------------
 static int alloc_boundary_scratch(long capacity, int** work, int* cap) {
     const long c = capacity / 16 + 65536;
