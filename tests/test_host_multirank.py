@@ -64,6 +64,38 @@ def test_two_bricks_periodic_loop_matches_oracle(orc, hh):
         assert err[c] <= 1e-10 * scale[c], abi.COMP_NAMES[c]
 
 
+def test_eight_bricks_order3_thermal_loop_matches_oracle(orc, hh):
+    """2 x 2 x 2 bricks of 8^3 cells, order 3, bilinear filter, thermal particles at u_th = 0.3 c (every brick trades
+    particles with its face, edge and corner neighbours): 6 steps against the single-box oracle."""
+    HS = hh.host_simulation_class()
+    n, world, nsteps = 16, 8, 6
+    full = workloads.uniform_plasma_3d(n=n, ppc=(2, 1, 1), u_th=0.3, perturbation=0.01)
+    s = full["species"][0]
+
+    def rank_fn(rank, dist):
+        dec = parallel.Decomposition((n, n, n), parallel.brick_grid(world), rank)
+        sim = HS(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=3, dist=dist, sort_interval=4, use_filter=True)
+        cell = [np.floor((s[k] - full["prob_lo"][d]) / sim.dx[d]).astype(int) for d, k in enumerate("xyz")]
+        m = np.ones(len(s["x"]), dtype=bool)
+        for d in range(3):
+            m &= (cell[d] >= dec.box_lo[d]) & (cell[d] <= dec.box_hi[d])
+        sim.add_species(s["name"], s["q"], s["m"], *[s[k][m] for k in ("x", "y", "z", "w", "ux", "uy", "uz")])
+        n0, mine = sim.total_particles(), sim.species[0].np
+        sim.Evolve(nsteps)
+        assert sim.total_particles() == n0
+        return dict(fields={c: sim.field_numpy(c) for c in range(9)}, box=(sim.box_lo, sim.box_hi),
+                    moved=sim.species[0].np != mine)
+
+    res = hh.run_ranks(world, rank_fn)
+    assert any(r["moved"] for r in res)
+    osim = orc.OracleSim(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=3, use_filter=True)
+    osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    osim.evolve(nsteps)
+    err, scale = _gather_fields(res, osim, world)
+    for c in range(9):
+        assert err[c] <= 1e-11 * scale[c], abi.COMP_NAMES[c]
+
+
 @pytest.mark.parametrize("world", [4])
 def test_z_slabs_with_moving_window_match_oracle(orc, hh, world):
     """The laser-acceleration deck in the small (12 x 12 x 64, order 3, filter, PEC z, moving window at c, antenna,
