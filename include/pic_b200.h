@@ -477,6 +477,12 @@ int pic_engine_add_species(void* engine, double q, double m, const pic_soa* bufA
                            long capacity, int* cell_start, const int tile[3], void* sort_work, void* stream);
 int pic_engine_species_buffer(void* engine, int isp, long* np);
 int pic_engine_evolve(void* engine, int numsteps, int synchronize_last, void* stream);
+/* WarpX::HandleParticlesAtBoundaries (Source/Evolve/WarpXEvolve.cpp:533-564) as one call, for a host that keeps its own
+ * step loop: periodic wrap, ApplyBoundaryConditions on the non-periodic faces + removal (WarpXParticleContainer.cpp:
+ * 1574-1638), RedistributeLocal(1) -- every particle that left this rank's brick goes to the neighbour that owns it
+ * (at most one brick per call and direction).  Species / antennas registered with the engine; read the new counts
+ * with pic_engine_species_buffer / pic_engine_laser_np.  Cell bins are stale afterwards. */
+int pic_engine_redistribute(void* engine, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Reduced diagnostics used as parity metrics

@@ -221,3 +221,58 @@ def test_halo_copy_and_add_match_oracle(orc, hh, nb, periodic):
                 sl = tuple(slice(ngalloc[2 - ax] - ng[2 - ax], boxes[r].a.shape[ax] - (ngalloc[2 - ax] - ng[2 - ax])) for ax in range(3))
                 scale = np.max(np.abs(boxes[r].a[sl]))
                 assert np.max(np.abs(got[r][k][sl] - boxes[r].a[sl])) <= 1e-14 * scale, (op, ng, src_ng, abi.COMP_NAMES[c], r)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_redistribute_moves_every_particle_to_its_owner(orc, hh, world):
+    """pic_engine_redistribute (HandleParticlesAtBoundaries as one call): particles displaced by up to 0.9 cell in every
+    direction -- across brick faces, edges, corners and the periodic domain boundary -- end up on the rank that owns
+    their cell, wrapped exactly like amrex's enforcePeriodic (the oracle's restatement), none lost, none duplicated."""
+    import ctypes as C
+    HS = hh.host_simulation_class()
+    n = 16
+    full = workloads.uniform_plasma_3d(n=n, ppc=(1, 1, 2), u_th=0.0)
+    s = full["species"][0]
+    dx = [(full["prob_hi"][d] - full["prob_lo"][d]) / n for d in range(3)]
+    rng = np.random.default_rng(8)
+    shift = [rng.uniform(-0.9, 0.9, len(s["x"])) * dx[d] for d in range(3)]
+    gid = np.arange(len(s["x"]), dtype=np.float64)          # carried in uz: identifies a particle after the move
+
+    def rank_fn(rank, dist):
+        dec = parallel.Decomposition((n, n, n), parallel.brick_grid(world), rank)
+        sim = HS(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=1, dist=dist, sort_interval=4)
+        cell = [np.floor((s[k] - full["prob_lo"][d]) / dx[d]).astype(int) for d, k in enumerate("xyz")]
+        m = np.ones(len(s["x"]), dtype=bool)
+        for d in range(3):
+            m &= (cell[d] >= dec.box_lo[d]) & (cell[d] <= dec.box_hi[d])
+        sim.add_species(s["name"], s["q"], s["m"], s["x"][m], s["y"][m], s["z"][m], s["w"][m], s["ux"][m], s["uy"][m], gid[m])
+        sp = sim.species[0]
+        torch = __import__("torch")
+        who = sp.array("uz").to(torch.int64)               # the engine sorted the particles when they were registered
+        for d, k in enumerate("xyz"):                       # the "push": host arrays are the device arrays here
+            sp.array(k).add_(torch.from_numpy(shift[d])[who])
+        assert sim.L.pic_engine_redistribute(sim.native, None) == 0, sim.L.pic_last_error()
+        sim._sync_from_native()
+        P = sim.species_numpy(0)
+        return dict(P=P, box=(dec.box_lo, dec.box_hi))
+
+    res = hh.run_ranks(world, rank_fn)
+    got_id = np.concatenate([r["P"]["uz"] for r in res])
+    assert len(got_id) == len(gid) and np.array_equal(np.sort(got_id), gid)          # none lost, none duplicated
+    # expected positions: the displaced particles after the oracle's periodic wrap
+    Q = orc.HostParticles(x=s["x"] + shift[0], y=s["y"] + shift[1], z=s["z"] + shift[2], w=s["w"], ux=s["ux"], uy=s["uy"], uz=gid)
+    geom = abi.make_geom(full["n_cell"], full["prob_lo"], full["prob_hi"])
+    orc.lib().orc_wrap_periodic(C.byref(Q.soa), C.byref(geom))
+    moved_rank = 0
+    for r in res:
+        P, (blo, bhi) = r["P"], r["box"]
+        idx = P["uz"].astype(np.int64)
+        for d, k in enumerate("xyz"):
+            assert np.array_equal(P[k], getattr(Q, k)[idx]), (k, float(np.max(np.abs(P[k] - getattr(Q, k)[idx]))),
+                                                                  int(np.sum(P[k] != getattr(Q, k)[idx])))
+            c = np.floor((P[k] - full["prob_lo"][d]) / dx[d]).astype(int)
+            c = np.clip(c, 0, n - 1)                        # a particle wrapped onto prob_hi belongs to the last cell
+            assert np.all((c >= blo[d]) & (c <= bhi[d])), (k, "a particle is on a rank that does not own its cell")
+        cell0 = [np.floor((s[k][idx] - full["prob_lo"][d]) / dx[d]).astype(int) for d, k in enumerate("xyz")]
+        moved_rank += int(np.sum(~np.all([(cell0[d] >= blo[d]) & (cell0[d] <= bhi[d]) for d in range(3)], axis=0)))
+    assert moved_rank > 100                                  # the test did move particles between ranks

@@ -762,6 +762,24 @@ extern "C" int pic_halo_add(void* h, const pic_fab* fabs, int nfab, const int sr
     return 0;
 }
 
+// WarpX::HandleParticlesAtBoundaries (Source/Evolve/WarpXEvolve.cpp:533-564) as one call, for a host that keeps its
+// own step loop: periodic wrap (amrex enforcePeriodic), ApplyBoundaryConditions on the non-periodic faces + removal,
+// and the move of every particle that left this rank's brick to the neighbour that owns it (RedistributeLocal(1):
+// at most one brick per call and direction).  Acts on the species and antennas registered with the engine; the
+// particle counts are read back with pic_engine_species_buffer / pic_engine_laser_np.  The cell bins of a species
+// are stale afterwards (particles appended / removed): sort before the next binned gather.
+extern "C" int pic_engine_redistribute(void* h, void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    for (auto& sp : e->species) ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e->geom, stream));
+    for (auto& L : e->lasers) ENG_CALL(pic_particles_wrap_periodic(&L.P, &e->geom, stream));
+    ENG_CALL(apply_particle_boundaries(*e, stream));
+    for (auto& sp : e->species) {
+        if (e->comm) ENG_CALL(migrate(*e, sp, stream));
+        sp.bins_stale = true;
+    }
+    return 0;
+}
+
 // ---- non-periodic runs ------------------------------------------------------------------------
 static int alloc_boundary_scratch(long capacity, int** work, int* cap) {
     const long c = capacity / 16 + 65536;

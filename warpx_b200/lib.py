@@ -81,6 +81,7 @@ def bind(L):
         "pic_engine_set_boundaries": (C.c_int, [vp, bndp]),
         "pic_engine_set_moving_window": (C.c_int, [vp, C.c_int, C.c_double]),
         "pic_engine_set_boost": (C.c_int, [vp, C.c_double, C.c_double]),
+        "pic_engine_redistribute": (C.c_int, [vp, vp]),
         "pic_halo_copy": (C.c_int, [vp, fabp, C.c_int, ip, vp]),
         "pic_halo_add": (C.c_int, [vp, fabp, C.c_int, ip, ip, vp]),
         "pic_engine_set_nci_corrector": (C.c_int, [vp, dp, dp]),
