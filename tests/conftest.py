@@ -4,6 +4,11 @@ import sys
 
 import pytest
 
+# The oracle is OpenMP code on all host cores.  Let idle threads sleep instead of spinning, so that a box that is
+# shared (or grants fewer cores than it reports) does not turn every barrier into a time slice: set before libgomp loads.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
