@@ -5,6 +5,7 @@ for a container without a GPU:
 
     python tests/host_harness/run_gpu_tests_on_host.py                     # everything (about an hour of emulation)
     python tests/host_harness/run_gpu_tests_on_host.py boosted nci order4  # the tests whose names contain one of the words
+    python tests/host_harness/run_gpu_tests_on_host.py -langmuir_loop      # ... all but those containing the word
 
 The test functions run unchanged, with their own tolerances.  Substitutions: warpx_b200.engine.Simulation -> the host
 subclass of harness.host_simulation_class(); the library loader -> harness.host_library; the `cuda` fixture -> an
@@ -92,14 +93,15 @@ SKIP = {"test_full_size_properties": "benchmark-size arrays", "test_two_gpu_halo
 
 
 def main():
-    words = sys.argv[1:]
+    words = [w for w in sys.argv[1:] if not w.startswith("-")]
+    minus = [w[1:] for w in sys.argv[1:] if w.startswith("-")]
     golden = json.load(open(os.path.join(TESTS, "golden", "warpx_checksums.json")))
     npass = nfail = 0
     for mod in (TP, TL):
         for name, fn in sorted(vars(mod).items()):
             if not name.startswith("test_") or not inspect.isfunction(fn) or fn.__module__ != mod.__name__:
                 continue
-            if words and not any(w in name for w in words):
+            if (words and not any(w in name for w in words)) or any(w in name for w in minus):
                 continue
             if name in SKIP:
                 print("SKIP", name, "--", SKIP[name], flush=True)
