@@ -4,6 +4,7 @@
 // Semantics kept: messages between a pair of ranks arrive in the order they were sent; sends are buffered, receives
 // posted inside a group complete at ncclGroupEnd (outside a group, immediately); ncclAllReduce(max / sum) over all
 // ranks of the communicator.  Select with PIC_NCCL_LIBRARY=<this library>.
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -33,14 +34,18 @@ thread_local std::vector<PendingRecv> t_pending;
 
 size_t dtype_bytes(int dt) { return dt == 2 ? 4 : dt == 8 ? 8 : dt == 7 ? 4 : 1; }   // int32, float64, float32
 
-void complete(const PendingRecv& r) {
+// a peer that died (a failed assertion in its thread) must not hang the test-suite: give up after two minutes
+constexpr std::chrono::seconds PATIENCE(120);
+
+int complete(const PendingRecv& r) {
     World* w = r.c->w;
     std::unique_lock<std::mutex> lk(w->mu);
     auto& q = w->box[{r.peer, r.c->rank}];
-    w->cv.wait(lk, [&] { return !q.empty(); });
+    if (!w->cv.wait_for(lk, PATIENCE, [&] { return !q.empty(); })) return 1;
     Message m = std::move(q.front());
     q.pop_front();
     std::memcpy(r.p, m.data.data(), std::min(r.bytes, m.data.size()));
+    return 0;
 }
 }  // namespace
 
@@ -68,7 +73,9 @@ int ncclGroupEnd() {
     if (--t_group == 0) {
         std::vector<PendingRecv> todo;
         todo.swap(t_pending);
-        for (const auto& r : todo) complete(r);
+        int rc = 0;
+        for (const auto& r : todo) rc |= complete(r);
+        return rc;
     }
     return 0;
 }
@@ -85,15 +92,15 @@ int ncclSend(const void* p, size_t count, int dtype, int peer, void* comm, void*
 }
 int ncclRecv(void* p, size_t count, int dtype, int peer, void* comm, void*) {
     PendingRecv r{p, count * dtype_bytes(dtype), peer, static_cast<Comm*>(comm)};
-    if (t_group > 0) t_pending.push_back(r); else complete(r);
-    return 0;
+    if (t_group > 0) { t_pending.push_back(r); return 0; }
+    return complete(r);
 }
 int ncclAllReduce(const void* in, void* out, size_t count, int dtype, int op, void* comm, void*) {
     Comm* c = static_cast<Comm*>(comm);
     World* w = c->w;
     const size_t bytes = count * dtype_bytes(dtype);
     std::unique_lock<std::mutex> lk(w->mu);
-    w->cv.wait(lk, [&] { return w->departed == 0 || w->arrived > 0; });     // previous round fully drained
+    if (!w->cv.wait_for(lk, PATIENCE, [&] { return w->departed == 0 || w->arrived > 0; })) return 1;   // previous round fully drained
     const unsigned long gen = w->generation;
     if (w->arrived == 0) w->acc.assign(static_cast<const char*>(in), static_cast<const char*>(in) + bytes);
     else
@@ -104,10 +111,10 @@ int ncclAllReduce(const void* in, void* out, size_t count, int dtype, int op, vo
                    a[i] = op == 2 ? (v > a[i] ? v : a[i]) : a[i] + v; }
         }
     if (++w->arrived == c->nranks) { w->departed = c->nranks; w->arrived = 0; ++w->generation; w->cv.notify_all(); }
-    else w->cv.wait(lk, [&] { return w->generation != gen; });
+    else if (!w->cv.wait_for(lk, PATIENCE, [&] { return w->generation != gen; })) return 1;
     std::memcpy(out, w->acc.data(), bytes);
     if (--w->departed == 0) w->cv.notify_all();
     return 0;
 }
-const char* ncclGetErrorString(int) { return "fake nccl"; }
+const char* ncclGetErrorString(int) { return "stand-in NCCL: a peer did not answer"; }
 }

@@ -11,6 +11,9 @@ import pytest
 from warpx_b200 import abi, parallel, workloads
 
 
+pytestmark = pytest.mark.timeout(900)
+
+
 @pytest.fixture(scope="module")
 def hh():
     from host_harness import harness
