@@ -82,6 +82,12 @@ def main():
     best_g = min((v for v in out["variants"][:-1] if v["deposit_mode"] == 0), key=lambda v: v["ms_per_step"])
     out["best"] = {"deposit_mode": best_d["deposit_mode"], "gather_mode": best_g["gather_mode"]}
     print(json.dumps(out, indent=1))
+    # the same, compact, for the tail of a gpurun log (stderr, so that stdout stays one JSON document)
+    for v in out["variants"]:
+        st = v.get("stage_ms", {})
+        print("deposit_mode %d gather_mode %d : %7.2f ms/step   gather %6.2f  deposit %6.2f" %
+              (v["deposit_mode"], v["gather_mode"], v["ms_per_step"], st.get("gather_push", float("nan")),
+               st.get("deposit", float("nan"))), file=sys.stderr)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,6 @@ python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/gpu_tests.txt 2>&1
 echo "pytest exit: $?" >> gpurun_out/gpu_tests.txt
 tail -5 gpurun_out/gpu_tests.txt
 python tools/ab_modes.py --cells 256 > gpurun_out/ab_modes.json 2> gpurun_out/ab_modes.err
-tail -30 gpurun_out/ab_modes.json
+cat gpurun_out/ab_modes.err | tail -12
 python bench.py --steps 8 --warmup 4 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 cat gpurun_out/bench_default.json
