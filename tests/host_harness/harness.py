@@ -1,11 +1,18 @@
-"""TEST INFRASTRUCTURE -- host harness for the thin kernels of warpx_b200/csrc/lwfa.cu.
+"""TEST INFRASTRUCTURE -- the host harness: the product's CUDA sources executed on the host, for a container
+without a GPU.  Four builds, all into tests/host_harness/_build/, none of them part of the product:
 
-The authoring container has no GPU.  lwfa.cu keeps every kernel as a `__host__ __device__` body
-(lwfa_body.cuh) behind a launch macro; compiled with -DPIC_HOST_HARNESS the launches become host
-loops over the same thread ids.  This module builds that variant into tests/host_harness/_build/
-and loads it, so that the CPU test-suite can check the bodies and the host-side argument builders
-(index ranges, closed-form slots, laser constants) against the oracle.  It proves nothing about
-launch geometry or device memory -- the `-m gpu` tests do that through the real library -- and it is
+  lib()           the thin kernels of lwfa.cu / charge.cu / nci.cu: `__host__ __device__` bodies behind a launch
+                  macro; -DPIC_HOST_HARNESS turns the launches into host loops over the same thread ids (nvcc,
+                  host code only);
+  simt()          deposit_runs.cu and gather_push_tile.cu, unmodified, under the SIMT emulator of simt_host.h
+                  (g++; every CUDA thread a cooperative fiber, warp collectives as lock-step exchanges);
+  host_library()  EVERY file of warpx_b200/csrc -- kernels, argument builders, the C++ step driver -- through the
+                  launch-syntax transformer of cuda2host.py and the same emulator: the product's C ABI on the host;
+                  host_simulation_class() drives it with warpx_b200.engine.Simulation, run_ranks() runs several
+                  "ranks" as threads over the NCCL stand-in of fake_nccl.cpp.
+
+They check indexing, lane roles, step sequence and arithmetic against the oracle; they prove nothing about races,
+launch geometry, device memory or speed -- the `-m gpu` tests do that through the real library -- and they are
 never imported by the product package."""
 import ctypes as C
 import os
