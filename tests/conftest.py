@@ -7,6 +7,10 @@ import pytest
 # The oracle is OpenMP code on all host cores.  Let idle threads sleep instead of spinning, so that a box that is
 # shared (or grants fewer cores than it reports) does not turn every barrier into a time slice: set before libgomp loads.
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+try:
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, len(os.sched_getaffinity(0)))))
+except AttributeError:            # not Linux
+    pass
 os.environ.setdefault("GOMP_SPINCOUNT", "0")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
