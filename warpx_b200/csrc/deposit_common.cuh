@@ -31,12 +31,10 @@ struct EsirkepovWeights {
         const double wq = dg.q * wp;                                     // :691
         wqx = wq * dg.invdtd[0]; wqy = wq * dg.invdtd[1]; wqz = wq * dg.invdtd[2];
         // new and old positions in grid units (:725-736)
-        const double x_new = (xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0];
-        const double x_old = x_new - dg.dt * dg.dinv[0] * uxp * gaminv;
-        const double y_new = (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1];
-        const double y_old = y_new - dg.dt * dg.dinv[1] * uyp * gaminv;
-        const double z_new = (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2];
-        const double z_old = z_new - dg.dt * dg.dinv[2] * uzp * gaminv;
+        double x_new, x_old, y_new, y_old, z_new, z_old;
+        deposit_coords(xp, dg.xyzmin[0], dg.tshift, uxp, gaminv, dg.dinv[0], dg.dt, x_new, x_old);
+        deposit_coords(yp, dg.xyzmin[1], dg.tshift, uyp, gaminv, dg.dinv[1], dg.dt, y_new, y_old);
+        deposit_coords(zp, dg.xyzmin[2], dg.tshift, uzp, gaminv, dg.dinv[2], dg.dt, z_new, z_old);
 #pragma unroll
         for (int n = 0; n < N + 3; ++n) {
             sx_new[n] = sx_old[n] = sy_new[n] = sy_old[n] = sz_new[n] = sz_old[n] = 0.0;

@@ -78,12 +78,9 @@ __device__ __forceinline__ ParticleGeom particle_geom(double xp, double yp, doub
     ParticleGeom g;
     const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);  // :687-689
     g.wq = dg.q * wp;
-    g.pos_new[0] = (xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0];   // :725-736
-    g.pos_new[1] = (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1];
-    g.pos_new[2] = (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2];
-    g.pos_old[0] = g.pos_new[0] - dg.dt * dg.dinv[0] * uxp * gaminv;
-    g.pos_old[1] = g.pos_new[1] - dg.dt * dg.dinv[1] * uyp * gaminv;
-    g.pos_old[2] = g.pos_new[2] - dg.dt * dg.dinv[2] * uzp * gaminv;
+    deposit_coords(xp, dg.xyzmin[0], dg.tshift, uxp, gaminv, dg.dinv[0], dg.dt, g.pos_new[0], g.pos_old[0]);   // :725-736
+    deposit_coords(yp, dg.xyzmin[1], dg.tshift, uyp, gaminv, dg.dinv[1], dg.dt, g.pos_new[1], g.pos_old[1]);
+    deposit_coords(zp, dg.xyzmin[2], dg.tshift, uzp, gaminv, dg.dinv[2], dg.dt, g.pos_new[2], g.pos_old[2]);
     return g;
 }
 

@@ -330,12 +330,10 @@ deposit_tile_kernel(SoaView P, BinsView bins, FabView Jx, FabView Jy, FabView Jz
         if (lane < nval) {
             const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);
             const double wq = dg.q * wp;
-            const double pos_new[3] = {(xp - dg.xyzmin[0] + dg.tshift * uxp * gaminv) * dg.dinv[0],
-                                       (yp - dg.xyzmin[1] + dg.tshift * uyp * gaminv) * dg.dinv[1],
-                                       (zp - dg.xyzmin[2] + dg.tshift * uzp * gaminv) * dg.dinv[2]};
-            const double pos_old[3] = {pos_new[0] - dg.dt * dg.dinv[0] * uxp * gaminv,
-                                       pos_new[1] - dg.dt * dg.dinv[1] * uyp * gaminv,
-                                       pos_new[2] - dg.dt * dg.dinv[2] * uzp * gaminv};
+            double pos_new[3], pos_old[3];
+            deposit_coords(xp, dg.xyzmin[0], dg.tshift, uxp, gaminv, dg.dinv[0], dg.dt, pos_new[0], pos_old[0]);
+            deposit_coords(yp, dg.xyzmin[1], dg.tshift, uyp, gaminv, dg.dinv[1], dg.dt, pos_new[1], pos_old[1]);
+            deposit_coords(zp, dg.xyzmin[2], dg.tshift, uzp, gaminv, dg.dinv[2], dg.dt, pos_new[2], pos_old[2]);
             double sn[3][S], so[3][S];
             int inew[3], sh[3];
 #pragma unroll

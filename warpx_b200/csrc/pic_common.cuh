@@ -81,6 +81,40 @@ inline SoaView make_soa(const pic_soa& p, long offset) {
     return s;
 }
 
+// ---- products / sums rounded separately (no FMA contraction) ----------------------------------
+// The deposition coordinates x_new, x_old (CurrentDeposition.H:725-736) are evaluated by the CPU
+// reference as individually rounded operations; where a particle's displacement per step is below
+// the spacing of doubles at its grid coordinate (test_3d_pec_particle) a fused multiply-add changes
+// x_old by one unit in the last place and with it the deposited current.  These helpers keep nvcc
+// from contracting (the host build of the harness compiles with -ffp-contract=off anyway).
+__host__ __device__ __forceinline__ double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+__host__ __device__ __forceinline__ double sub_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+// x_new = (xp - xmin + tshift*u*gaminv)*dinv ; x_old = x_new - dt*dinv*u*gaminv, left to right
+__host__ __device__ __forceinline__ void deposit_coords(double xp, double xmin, double tshift, double u, double gaminv,
+                                                        double dinv, double dt, double& x_new, double& x_old) {
+    x_new = mul_rn(add_rn(sub_rn(xp, xmin), mul_rn(mul_rn(tshift, u), gaminv)), dinv);
+    x_old = sub_rn(x_new, mul_rn(mul_rn(mul_rn(dt, dinv), u), gaminv));
+}
+
 // ---- B-spline shape factors (Source/Particles/ShapeFactors.H:27-84) --------------------------
 // Written for the evaluation order of the reference; returns the leftmost index.
 // Quartic spline around the nearest node, d in [-1/2, 1/2] (ShapeFactors.H:66-77).
