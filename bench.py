@@ -115,12 +115,16 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=False):
+def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=False, solver="yee"):
     """The reference algorithm on the host cores: the oracle's whole-loop driver (OpenMP, all
     cores) on a bounded sample of the workload (n^3 cells of the same plasma).  Test infrastructure
     used as the measured CPU baseline -- the only place bench.py executes oracle/."""
+    # threads pinned to cores (set before libgomp starts): the same box gave 4x different numbers unpinned
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
     from oracle import oracle
-    from warpx_b200 import workloads
+    from warpx_b200 import abi, workloads
     oracle.build(ref=False)
     # same cell size and plasma as the GPU run (dx = 40um/256), smaller box
     lx = 40.0e-6 * n / 256.0
@@ -139,7 +143,8 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=False):
     npart = len(s["x"])
     best = None
     for threads in candidates:
-        sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind, use_filter=use_filter)
+        sim = oracle.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=nox, kind=kind, use_filter=use_filter,
+                               solver=abi.SOLVER_CKC if solver == "ckc" else abi.SOLVER_YEE)
         sim.L.orc_set_num_threads(threads)
         sim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
         sim.evolve(max(warmup, 1), synchronize_last=False)
@@ -152,9 +157,10 @@ def cpu_reference_run(n, ppc, steps, warmup, nox=3, use_filter=False):
     dt, cores, timers = best
     return dict(value=npart * steps / dt, unit="particle-steps/s", cores=cores,
                 kind="reference-leaves+port" if kind == "reference" else "port",
-                sample="%d^3 cells x %d ppc (%d particles), order %d, bilinear filter %s, %d steps, OpenMP %d threads "
-                       "(best of %s); oracle = loop-for-loop restatement of the reference CPU path"
-                       % (n, ppc[0] * ppc[1] * ppc[2], npart, nox, "on" if use_filter else "off", steps, cores, candidates),
+                sample="%d^3 cells x %d ppc (%d particles), order %d, %s, bilinear filter %s, %d steps, OpenMP %d threads "
+                       "pinned to cores (best of %s); oracle = loop-for-loop restatement of the reference CPU path"
+                       % (n, ppc[0] * ppc[1] * ppc[2], npart, nox, solver.upper(), "on" if use_filter else "off", steps,
+                          cores, candidates),
                 seconds=dt, ms_per_step=1e3 * dt / steps, timers=timers)
 
 
@@ -162,23 +168,44 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ppc = (2, 2, 2)
-    r = cpu_reference_run(args.cpu_n, ppc, args.steps, args.warmup, use_filter=bool(args.filter))
+    ppc = (args.ppc,) * 3
+    steps = max(2, min(args.steps, 10))          # a bounded sample: the whole arm ends within a few minutes
+    r = cpu_reference_run(args.cpu_n, ppc, steps, min(args.warmup, 2), nox=args.order, use_filter=bool(args.filter),
+                          solver=args.solver)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D uniform plasma, Yee FDTD, Boris, order-3 Esirkepov, 8 ppc; CPU sample "
-                                   + r["sample"], "use_filter": int(args.filter)},
+            "config": {"workload": "3D uniform plasma, %s FDTD, Boris, order-%d Esirkepov, %d ppc; CPU sample "
+                                   % (args.solver.upper(), args.order, args.ppc ** 3) + r["sample"],
+                       "use_filter": int(args.filter), "timed_steps_of_the_sample": steps},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+def start_watchdog(rank):
+    """A hang must name its line: dump every thread's Python stack to stderr after 4 minutes and leave (status 3)
+    after 11 -- before an outer limit kills the job without a trace."""
+    import faulthandler
+
+    def watch():
+        time.sleep(240)
+        sys.stderr.write("[bench watchdog] rank %d still running after 240 s\n" % rank)
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        time.sleep(420)
+        sys.stderr.write("[bench watchdog] rank %d still running after 660 s: giving up\n" % rank)
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=watch, daemon=True).start()
 
 
 # ---------------------------------------------------------------------------------------------
 def run_engine(args):
     import numpy as np
     import torch
-    from warpx_b200 import workloads
+    from warpx_b200 import abi, engine, workloads
     from warpx_b200.engine import Simulation
     from warpx_b200.lib import lib
     from warpx_b200 import parallel
@@ -186,6 +213,7 @@ def run_engine(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    start_watchdog(rank)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the CUDA engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -194,13 +222,16 @@ def run_engine(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = lib()
+    L.pic_set_deposit_mode(args.deposit_mode)
+    L.pic_set_gather_mode(args.gather_mode)
 
     n, ppc = args.n, (args.ppc,) * 3
     nb = parallel.brick_grid(world)
     n_cell = tuple(n * nb[d] for d in range(3))               # weak scaling: n^3 cells per GPU
-    lx = 40.0e-6 * np.array(nb)                                # same dx as configs[1]
+    lx = 40.0e-6 * np.array(nb) * (n / 256.0)                  # same dx as configs[1]
     dec = parallel.Decomposition(n_cell, nb, rank)
     prob_lo = tuple(-0.5 * lx); prob_hi = tuple(0.5 * lx)
+    solver = abi.SOLVER_CKC if args.solver == "ckc" else abi.SOLVER_YEE
 
     # ---- synthetic input, generated on the host into pinned memory (seeded, counter based) ----
     t_gen = time.perf_counter()
@@ -219,15 +250,9 @@ def run_engine(args):
     npart_local = len(s["x"])
     t_gen = time.perf_counter() - t_gen
 
-    def make_sim(native=True):
-        if args.deposit_mode:
-            from warpx_b200.lib import lib as _piclib
-            _piclib().pic_set_deposit_mode(args.deposit_mode)
-        if args.gather_mode:
-            from warpx_b200.lib import lib as _piclib
-            _piclib().pic_set_gather_mode(args.gather_mode)
+    def make_sim():
         sim = Simulation(n_cell, prob_lo, prob_hi, nox=args.order, dist=dist, sort_interval=args.sort_interval,
-                         native_driver=native, use_filter=bool(args.filter))
+                         solver=solver, use_filter=bool(args.filter))
         sim.add_species("electrons", s["q"], s["m"], *[pinned[k] for k in names])
         return sim
 
@@ -237,13 +262,23 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # =================== device-resident measurement (`value`) ===================
     sim = make_sim()
     ntot = sim.total_particles()
+    # spin-up: the NUniformPerCell lattice decays into random in-cell positions within ~50 steps (u_th dt = 0.006 dx
+    # per step); particles then change cell all the time and the kernels see their steady-state load
+    sim.Evolve(args.spinup, synchronize_last=False)
     sim.Evolve(args.warmup, synchronize_last=False)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()       # before the barrier: spawning the sampler must not delay rank 0 inside the timed region
+    sim.enable_stage_timing(True)       # CUDA events around every stage, inside the same timed steps
     barrier()
     launches0 = L.pic_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,63 +288,56 @@ def run_engine(args):
     t_host_enqueue = time.perf_counter() - t_host0      # host time to issue the K steps
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = L.pic_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
+    stage = sim.stage_ms()                               # {stage: (ms per call, calls)} of the timed steps
+    sim.enable_stage_timing(False)
     fe = sim.field_energy()
     value = ntot * args.steps / (ms * 1e-3)
-    # per-kernel durations for the roofline: a second, separately timed pass with CUDA events around
-    # every stage (Python sequencer; the timed region above ran the C++ driver on one rank)
+    sim.close()
     del sim
     torch.cuda.empty_cache()
-    sim = make_sim(native=False)
-    sim.Evolve(args.warmup, synchronize_last=False)
-    sim.enable_stage_timing(True)
-    sim.Evolve(min(args.steps, 4), synchronize_last=False)
-    stage = sim.stage_ms()
 
-    if args.profile_only:
-        if rank == 0:
-            print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps,
-                              "host_enqueue_ms_per_step": 1e3 * t_host_enqueue / args.steps,
-                              "stage_ms": {k: v[0] for k, v in stage.items()}}))
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    e2e = None
+    if not args.profile_only:
+        # =================== end-to-end through the public API (`e2e`) ===================
+        # Job-level: every rank uploads its initial particle state from pinned host memory, runs K
+        # steps through Simulation.Evolve, and reads the FieldEnergy reduced diagnostic back to the
+        # host after EVERY step (what a WarpX run with reduced diagnostics does).  A PIC run has no
+        # per-step host input: the upload happens once and is reported separately as well.
+        barrier()
+        t0 = time.perf_counter()
+        sim2 = make_sim()
+        torch.cuda.synchronize()
+        t_up = time.perf_counter() - t0
+        d2h = 0
+        for _ in range(args.steps):
+            sim2.Evolve(1, synchronize_last=False)
+            sim2.field_energy()
+            d2h += 16
+        barrier()
+        t_all = max_over_ranks(time.perf_counter() - t0)
+        t_up = max_over_ranks(t_up)
+        h2d_total = npart_local * 7 * 8
+        e2e = {"value": ntot * args.steps / t_all, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "upload_and_first_sort_s": t_up, "loop_s": t_all - t_up,
+               "loop_value": ntot * args.steps / max(t_all - t_up, 1e-9),
+               "definition": "job-level wall clock, max over ranks: H2D upload of the initial particle state from pinned "
+                             "host memory + initial cell sort (upload_and_first_sort_s) + K steps via Simulation.Evolve "
+                             "with a D2H read of the FieldEnergy diagnostic after every step (loop_s; these steps start "
+                             "from the lattice, not from the spun-up state)"}
+        sim2.close()
+        del sim2
 
-    # =================== end-to-end through the public API (`e2e`) ===================
-    # Job-level: every rank uploads its initial particle state from pinned host memory, runs K
-    # steps through Simulation.Evolve, and reads the FieldEnergy reduced diagnostic back to the
-    # host after EVERY step (what a WarpX run with reduced diagnostics does).
-    del sim
-    torch.cuda.empty_cache()
+    # =================== teardown, collective and explicit, BEFORE the CPU leg ===================
     barrier()
-    t0 = time.perf_counter()
-    sim2 = make_sim()
-    d2h = 0
-    for _ in range(args.steps):
-        sim2.Evolve(1, synchronize_last=False)
-        sim2.field_energy()
-        d2h += 16
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
-    h2d_total = npart_local * 7 * 8
-    e2e = {"value": ntot * args.steps / t_e2e, "unit": "particle-steps/s",
-           "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-           "definition": "job-level: H2D upload of the initial particle state from pinned host memory + initial "
-                         "cell sort + K steps via Simulation.Evolve + per-step D2H of the FieldEnergy diagnostic, "
-                         "wall clock, max over ranks"}
-    del sim2
-
+        engine.release_comm(dist)
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
 
     # =================== roofline of the kernels (algorithmic bytes / CUDA-event time) ==========
@@ -321,8 +349,6 @@ def run_engine(args):
         "evolve_e": 96.0 * ncell,
         "gather_push": 96.0 * npart_local + 48.0 * ncell,
         "deposit": 56.0 * npart_local + 72.0 * ncell,
-        # 3 components x (filter: read + write, copy back: read + write) over the allocated J points
-        "filter": 3 * 32.0 * float(n + 1 + 2 * 5) ** 3,
     }
     try:     # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -340,42 +366,58 @@ def run_engine(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
                 "kernels": kernels,
-                "note": "gather_push and deposit are fp64-FMA / shared-memory bound at order 3 (DESIGN.md); the "
-                        "HBM fraction is reported because BASELINE.json asks for it"}
-
-    cpu = cpu_reference_run(args.cpu_n, ppc, 2, 1, use_filter=bool(args.filter))
+                "note": "stage durations from CUDA events recorded by the C++ driver inside the timed steps (a stage = "
+                        "its main kernel plus the small ones it needs: stray / listed particles); gather_push and "
+                        "deposit are fp64-FMA / shared-memory bound at order 3 (DESIGN.md); the HBM fraction is "
+                        "reported because BASELINE.json asks for it"}
+    step_sum = sum(t * c for t, c in stage.values()) / args.steps
     line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D uniform plasma %dx%dx%d cells (%d^3 per GPU), %d ppc (%d particles), Yee FDTD, "
+            "config": {"workload": "3D uniform plasma %dx%dx%d cells (%d^3 per GPU), %d ppc (%d particles), %s FDTD, "
                                    "Boris pusher, order-%d Esirkepov, Galerkin gather, cfl 1, u_th %gc%s, "
                                    "bilinear current filter %s, cell sort every %d steps"
-                                   % (n_cell + (n, args.ppc ** 3, ntot, args.order, args.u_th,
+                                   % (n_cell + (n, args.ppc ** 3, ntot, args.solver.upper(), args.order, args.u_th,
                                                 ", random in-cell positions" if args.jitter else "",
                                                 "on (1 pass)" if args.filter else "off (SURVEY 8d)",
                                                 args.sort_interval)),
+                       "state": "steady state: %d untimed spin-up steps + %d warm-up steps before the timed region "
+                                "(the initial lattice has decayed into random in-cell positions)" % (args.spinup, args.warmup),
                        "use_filter": int(args.filter), "deposit_mode": int(args.deposit_mode), "gather_mode": int(args.gather_mode),
                        "brick_grid": list(nb), "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2"
                                                      % (npart_local * 56 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
-            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "stage_ms": {k: v[0] for k, v in stage.items()}, "field_energy_J": list(fe),
-            "host_generation_s": t_gen}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+            "stage_ms": {k: v[0] for k, v in stage.items()}, "stage_calls": {k: v[1] for k, v in stage.items()},
+            "stage_sum_ms_per_step": step_sum, "host_enqueue_ms_per_step": 1e3 * t_host_enqueue / args.steps,
+            "field_energy_J": list(fe), "host_generation_s": t_gen}
+    if args.profile_only:
+        line["profile_only"] = True
+    else:
+        try:         # last: NCCL and the engines are gone, a slow or failing CPU leg cannot hang a collective
+            cpu = cpu_reference_run(args.cpu_n, ppc, args.cpu_steps, 1, nox=args.order, use_filter=bool(args.filter),
+                                    solver=args.solver)
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:     # noqa: BLE001 -- the GPU line must still be printed
+            line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port",
+                                    "sample": "failed: %r" % (exc,)}
+    print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cells", dest="n", type=int, default=256, help="cells per GPU and direction")
-    ap.add_argument("--cpu-cells", dest="cpu_n", type=int, default=64, help="cells per direction of the CPU sample")
+    ap.add_argument("--cpu-cells", dest="cpu_n", type=int, default=128, help="cells per direction of the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=5, help="timed steps of the in-line cpu_baseline sample")
     ap.add_argument("--sort-interval", type=int, default=4)
-    ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
+    ap.add_argument("--spinup", type=int, default=60,
+                    help="untimed steps before the warm-up that take the lattice to its steady state (0: measure the "
+                         "fresh lattice)")
+    ap.add_argument("--solver", default="yee", choices=["yee", "ckc"], help="algo.maxwell_solver (configs[2] uses ckc)")
+    ap.add_argument("--profile-only", action="store_true", help="spin-up + warm-up + steps only (for runs under ncu)")
     ap.add_argument("--ppc", type=int, default=2, help="particles per cell and direction (2 -> 8 ppc, 4 -> 64 ppc)")
     ap.add_argument("--u-th", type=float, default=0.01, help="thermal momentum spread u/c")
     ap.add_argument("--jitter", action="store_true", help="stress variant: random positions inside the cells "
@@ -385,10 +427,10 @@ def main():
                     help="warpx.use_filter: bilinear current filter, 1 pass.  Off by default: SURVEY.md 8(d) "
                          "fixes use_filter = 0 for the benchmark configurations; --filter 1 measures the "
                          "reference's own default (WarpX.cpp:158)")
-    ap.add_argument("--deposit-mode", type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6],
-                    help="pic_set_deposit_mode: 0 register runs (default), 1 shared-memory tile block, 2 two lines per "
-                         "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions "
-                         "(A/B measurements; every mode passes the parity tests)")
+    ap.add_argument("--deposit-mode", type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6, 7],
+                    help="pic_set_deposit_mode: 0 register runs, 1 shared-memory tile block, 2 two lines per "
+                         "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions, "
+                         "7 one lane per cell (every mode passes the parity tests)")
     ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 1, 2],
                     help="pic_set_gather_mode: 0 one particle per lane (default), 1 two particles of a cell per lane, "
                          "2 the same without the 128-register cap (A/B measurement; same parity tests)")
@@ -399,6 +441,10 @@ def main():
         run_reference(args)
     else:
         run_engine(args)
+    # the line is out and flushed; nothing below may hang the job (interpreter teardown of CUDA / NCCL state)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

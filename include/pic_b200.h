@@ -224,7 +224,7 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
  * Analogous to WarpX's runtime switch warpx.do_shared_mem_current_deposition
  * (Source/WarpX.cpp:126, Docs/source/usage/parameters.rst:2608-2623). */
 enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1, PIC_DEPOSIT_RUNS2 = 2, PIC_DEPOSIT_RUNS_SLOTRED = 3,
-       PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6 };
+       PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6, PIC_DEPOSIT_CELLS = 7 };
 void pic_set_deposit_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------
@@ -432,6 +432,14 @@ void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box
 void pic_engine_destroy(void* engine);
 double pic_engine_dt(void* engine);
 void pic_engine_guards(void* engine, int out[12] /* ng_EB[3] ng_J[3] ng_FieldGather[3] ng_FieldSolver[3] */);
+/* Per-stage timing of pic_engine_evolve: CUDA events recorded on the launching stream around every stage of
+ * the step (the instrumentation a WarpX run gets from its TinyProfiler regions, WarpXEvolve.cpp BL_PROFILE).
+ * enable_timing(1) resets the sums; stage_ms fills total milliseconds and call counts of the
+ * pic_engine_stage_count() stages named by pic_engine_stage_name(n) (it waits for the recorded events). */
+int pic_engine_enable_timing(void* engine, int on);
+int pic_engine_stage_count(void);
+const char* pic_engine_stage_name(int n);
+int pic_engine_stage_ms(void* engine, double ms[], long calls[]);
 int pic_engine_set_fields(void* engine, const pic_fab fabs[9]);
 int pic_engine_set_comm(void* engine, void* comm, const int nb[3]);
 /* The engine's decomposition as a guard-cell context (an engine created only for this needs pic_engine_create,

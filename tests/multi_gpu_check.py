@@ -19,12 +19,14 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle  # noqa: E402  (test infrastructure: the checker)
-from warpx_b200 import abi, parallel, workloads  # noqa: E402
+from warpx_b200 import abi, engine, parallel, workloads  # noqa: E402
 from warpx_b200.engine import Simulation  # noqa: E402
 
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    import faulthandler
+    faulthandler.dump_traceback_later(600, exit=True)      # a hang names its line instead of running into the job limit
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     ok = True
@@ -104,6 +106,7 @@ def main():
             ok &= good
             print(f"[order3 x{world} filter={int(filt)} native={int(native)}] field energy E {e:.12e} vs oracle {eo:.12e}; "
                   f"B {b:.12e} vs {bo:.12e}; particles {npart}: {'ok' if good else 'FAIL'}")
+        sim3.close()
         del sim3
     # ---------------- laser-acceleration deck on z slabs: moving window over several ranks ----------------
     # (PEC walls on the end slabs, neighbour planes pulled in by the window shift, one cell layer of
@@ -149,13 +152,23 @@ def main():
             good = int(v[9 + 7]) == 22 * 22 * (45 + 98)
             ok &= good
             print(f"[lwfa z-slabs x{world}] particles {int(v[9 + 7])}: {'ok' if good else 'FAIL'}")
+        simw.close()
         del simw
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
+    code = 0 if int(flag.item()) else 1
+    # collective, explicit teardown: engines closed above, every rank releases the private communicator at the
+    # same point, then torch's process group; no NCCL object is left for the interpreter's shutdown
+    sim.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    engine.release_comm(dist)
+    dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    sys.stdout.flush()
+    os._exit(code)
 
 
 if __name__ == "__main__":

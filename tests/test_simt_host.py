@@ -183,3 +183,67 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, nox):
                 assert np.max(np.abs(getattr(A, k) - getattr(B, k))) <= 1e-13 * lx[0], (galerkin, pusher, k)
             for k in ("ux", "uy", "uz"):
                 assert rel_linf(getattr(B, k), getattr(A, k)) <= 1e-13, (galerkin, pusher, k)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the lane-per-cell deposition kernel of warpx_b200/csrc/deposit_cells.cu (PIC_DEPOSIT_CELLS) under the emulator
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nox,n,ppc,u_th,kind", [
+    (3, (16, 8, 8), (2, 2, 2), 0.02, "sorted"),       # the benchmark's situation: every particle quiet in its bin
+    (3, (16, 8, 8), (2, 1, 2), 0.3, "sorted"),        # relativistic: many particles change cell during the step
+    (3, (16, 8, 8), (2, 2, 1), 0.05, "moved"),        # bins stale by up to 0.9 cell: listed particles
+    (3, (12, 8, 10), (1, 1, 1), 0.1, "odd"),          # box not a multiple of the supercell, 1..3 particles per cell
+    (1, (16, 8, 8), (2, 1, 2), 0.05, "moved"),
+    (1, (12, 8, 10), (1, 1, 1), 0.3, "odd"),
+    (3, (8, 8, 8), (2, 2, 2), 0.02, "tail"),          # particles appended behind the binned range
+])
+def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind):
+    from host_harness import harness
+    hl = harness.host_library()
+    lx = tuple(0.5e-6 * v for v in n)
+    wl = workloads.uniform_plasma_3d(n_cell=n, ppc=ppc, u_th=u_th, lx=lx, seed=21)
+    sp = wl["species"][0]
+    prob_lo = wl["prob_lo"]
+    dx = [(wl["prob_hi"][d] - prob_lo[d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    dt = 0.95 / (np.sqrt(sum(1.0 / v ** 2 for v in dx)) * workloads.C)
+    rng = np.random.default_rng(23)
+    arr = {k: sp[k].copy() for k in orc.HostParticles.NAMES}
+    if kind == "odd":
+        extra = rng.integers(0, 3, len(arr["x"]))
+        for k in arr:
+            arr[k] = np.repeat(arr[k], 1 + extra)
+        for d, k in enumerate("xyz"):
+            arr[k] = arr[k] + rng.uniform(-0.49, 0.49, len(arr[k])) * dx[d]
+    order, cell_start = host_bins(arr["x"], arr["y"], arr["z"], prob_lo, dx, n, (8, 8, 8))
+    arr = {k: np.ascontiguousarray(v[order]) for k, v in arr.items()}
+    np_binned = len(arr["x"])
+    if kind == "moved":
+        for d, k in enumerate("xyz"):
+            arr[k] = arr[k] + rng.uniform(-0.9, 0.9, len(arr[k])) * dx[d]
+    if kind == "tail":           # 100 unsorted particles behind the bins (injected after the sort)
+        for k in arr:
+            arr[k] = np.concatenate([arr[k], arr[k][rng.integers(0, np_binned, 100)]])
+        for d, k in enumerate("xyz"):
+            arr[k][np_binned:] += rng.uniform(-0.4, 0.4, 100) * dx[d]
+    P = orc.HostParticles(**arr)
+    ngJ = (nox + 2,) * 3
+    box_hi = tuple(v - 1 for v in n)
+    xyzmin, lo = lower_corner(prob_lo, dx, (0, 0, 0), ngJ)
+    J = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    K = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    bins = abi.pic_bins()
+    bins.cell_start = cell_start.ctypes.data
+    for d in range(3):
+        bins.box_lo[d], bins.box_hi[d], bins.tile[d] = 0, box_hi[d], 8
+    bins.np_binned = np_binned
+    assert orc.lib().orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                           abi.int3(lo), sp["q"], dt, -0.5 * dt, nox) == 0
+    hl.pic_set_deposit_mode(abi.PIC_DEPOSIT_CELLS)
+    try:
+        assert hl.pic_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                        abi.int3(lo), sp["q"], dt, -0.5 * dt, nox, C.byref(bins), None) == 0, hl.pic_last_error()
+    finally:
+        hl.pic_set_deposit_mode(0)
+    for c in range(3):
+        assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]

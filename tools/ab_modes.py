@@ -22,7 +22,8 @@ def main():
     ap.add_argument("--ppc", type=int, default=2)
     ap.add_argument("--steps", type=int, default=8, help="timed steps per variant (a multiple of the sort interval)")
     ap.add_argument("--u-th", type=float, default=0.01)
-    ap.add_argument("--deposit-modes", default="0,2,3,4,5,6")
+    ap.add_argument("--jitter", action="store_true", help="random in-cell positions (the steady state of the lattice)")
+    ap.add_argument("--deposit-modes", default="0,7,2,5,6")
     ap.add_argument("--gather-modes", default="0,1,2")
     args = ap.parse_args()
     import torch
@@ -35,6 +36,13 @@ def main():
     n = args.cells
     wl = workloads.uniform_plasma_3d(n_cell=(n, n, n), ppc=(args.ppc,) * 3, lx=(40.0e-6,) * 3, u_th=args.u_th)
     s = wl["species"][0]
+    if args.jitter:
+        import numpy as np
+        rng = np.random.default_rng(1234)
+        for d, k in enumerate(("x", "y", "z")):
+            dxd = 40.0e-6 / n
+            cell = np.floor((s[k] - wl["prob_lo"][d]) / dxd)
+            s[k] = wl["prob_lo"][d] + (cell + rng.uniform(0.0, 1.0, len(cell))) * dxd
     names = ("x", "y", "z", "w", "ux", "uy", "uz")
 
     def make(native):
@@ -62,17 +70,13 @@ def main():
         L.pic_set_gather_mode(g)
         sim.Evolve(4, synchronize_last=False)            # warm-up of this variant (one sort period)
         out["variants"].append({"deposit_mode": d, "gather_mode": g, "ms_per_step": timed(sim, args.steps)})
-    del sim
-    torch.cuda.empty_cache()
-    # per stage, Python sequencer
-    sim = make(False)
-    sim.Evolve(4, synchronize_last=False)
+    # per stage: CUDA events of the C++ driver
     for v in out["variants"][:-1]:
         L.pic_set_deposit_mode(v["deposit_mode"])
         L.pic_set_gather_mode(v["gather_mode"])
         sim.enable_stage_timing(False)
         sim.Evolve(4, synchronize_last=False)            # warm-up of this variant
-        sim.enable_stage_timing(True)                    # fresh event lists
+        sim.enable_stage_timing(True)                    # fresh sums
         sim.Evolve(4, synchronize_last=False)
         v["stage_ms"] = {k: t[0] for k, t in sim.stage_ms().items()}
     L.pic_set_deposit_mode(0)

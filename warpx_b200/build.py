@@ -46,8 +46,10 @@ def build(force=False, verbose=False, extra=()):
         ok = ok and p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()            # link beside the target, then rename: never a half-written library
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-lcudart"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

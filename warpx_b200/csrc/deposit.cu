@@ -64,6 +64,8 @@ int deposit_tile_launch(const pic_soa* p, long offset, long np, const pic_fab J[
                         const DepositGeom& dg, int nox, const pic_bins* bins, cudaStream_t s);
 int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
                         const DepositGeom& dg, int nox, cudaStream_t s);
+int deposit_cells_launch(const pic_soa* p, long offset, long np, const pic_fab J[3], const DepositGeom& dg, int nox,
+                         const pic_bins* bins, cudaStream_t s);
 
 static int g_deposit_mode = PIC_DEPOSIT_RUNS;
 extern int g_runs_variant;      // deposit_runs.cu
@@ -99,11 +101,17 @@ extern "C" int pic_deposit_esirkepov(const pic_soa* p, long offset, long np, con
     dg.invdtd[2] = (1.0 / dt) * dinv[0] * dinv[1];
     cudaStream_t s = (cudaStream_t)stream;
     if (bins && nox <= 3) {        // order 4: order-agnostic kernel (the run kernels are built for orders 1..3)
+        // (the run kernels do not read the bins and accept any range; the bin-driven ones need the whole tile)
         // cell-sorted particles: warp-segmented register reduction (deposit_runs.cu).  The
         // shared-memory-block variant (deposit_tile.cu) is kept for comparison: pic_set_deposit_mode().
         PIC_REQUIRE(np < (1L << 31), "pic_deposit_esirkepov: more than 2^31 particles in one tile");
-        if (g_deposit_mode != PIC_DEPOSIT_TILE) return deposit_runs_launch(p, offset, np, J, dg, nox, s);
-        if (int rc = deposit_tile_launch(p, offset, np, J, dg, nox, bins, s)) return rc;
+        const bool cells = g_deposit_mode == PIC_DEPOSIT_CELLS && (nox == 1 || nox == 3) && offset == 0 &&
+                           bins->tile[0] == 8 && bins->tile[1] == 8 && bins->tile[2] == 8;
+        if (g_deposit_mode != PIC_DEPOSIT_TILE && !cells) return deposit_runs_launch(p, offset, np, J, dg, nox, s);
+        // the two bin-driven kernels cover [0, np_binned) of the tile
+        PIC_REQUIRE(offset == 0, "pic_deposit_esirkepov: the bin-driven kernels take the whole tile (offset 0)");
+        if (cells) { if (int rc = deposit_cells_launch(p, offset, np, J, dg, nox, bins, s)) return rc; }
+        else if (int rc = deposit_tile_launch(p, offset, np, J, dg, nox, bins, s)) return rc;
         if (bins->np_binned >= np) return 0;
         offset = bins->np_binned;           // particles appended after the last sort
         np -= bins->np_binned;

@@ -51,5 +51,45 @@ struct EsirkepovWeights {
     }
 };
 
+// ---- shared by the register-run kernels (deposit_runs.cu) and the lane-per-cell kernel (deposit_cells.cu) ----
+struct J3 { FabView v[3]; };
+
+// weights of the new (wn) and old (wo) position and the slot shift of the old stencil
+template <int N>
+__device__ __forceinline__ int dr_dir(double x_new, double x_old, double* wn, double* wo, int& sh) {
+    const int i_new = shape_factor<N>(wn, x_new);
+    int i_old;
+    if constexpr (N == 1) {   // order 1 uses floor for the old position (ShapeFactors.H:110)
+        const int i = (int)floor(x_old);
+        const double d = x_old - (double)i;
+        wo[0] = 1.0 - d; wo[1] = d;
+        i_old = i;
+    } else {
+        i_old = shape_factor<N>(wo, x_old);
+    }
+    sh = i_old - i_new;
+    return i_new;
+}
+
+struct ParticleGeom {   // new/old positions in grid units and charge factor of one particle
+    double pos_new[3], pos_old[3], wq;
+};
+__device__ __forceinline__ ParticleGeom particle_geom(double xp, double yp, double zp, double wp, double uxp,
+                                                      double uyp, double uzp, const DepositGeom& dg) {
+    ParticleGeom g;
+    const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);  // :687-689
+    g.wq = dg.q * wp;
+    deposit_coords(xp, dg.xyzmin[0], dg.tshift, uxp, gaminv, dg.dinv[0], dg.dt, g.pos_new[0], g.pos_old[0]);   // :725-736
+    deposit_coords(yp, dg.xyzmin[1], dg.tshift, uyp, gaminv, dg.dinv[1], dg.dt, g.pos_new[1], g.pos_old[1]);
+    deposit_coords(zp, dg.xyzmin[2], dg.tshift, uzp, gaminv, dg.dinv[2], dg.dt, g.pos_new[2], g.pos_old[2]);
+    return g;
+}
+
+// anchor (global index of slot 0 of the stencil) packed relative to the J arrays, 10 bits each
+struct KeyBase { int b0, b1, b2; };
+__device__ __forceinline__ int pack_key(int gx, int gy, int gz, const KeyBase& kb) {
+    return (gx - kb.b0) | ((gy - kb.b1) << 10) | ((gz - kb.b2) << 20);
+}
+
 }  // namespace pic
 #endif

@@ -53,43 +53,6 @@ __device__ __forceinline__ void dr_place_old(double* so /*N+3*/, const double* w
     }
 }
 
-// weights of the new (wn) and old (wo) position and the slot shift of the old stencil
-template <int N>
-__device__ __forceinline__ int dr_dir(double x_new, double x_old, double* wn, double* wo, int& sh) {
-    const int i_new = shape_factor<N>(wn, x_new);
-    int i_old;
-    if constexpr (N == 1) {   // order 1 uses floor for the old position (ShapeFactors.H:110)
-        const int i = (int)floor(x_old);
-        const double d = x_old - (double)i;
-        wo[0] = 1.0 - d; wo[1] = d;
-        i_old = i;
-    } else {
-        i_old = shape_factor<N>(wo, x_old);
-    }
-    sh = i_old - i_new;
-    return i_new;
-}
-
-struct ParticleGeom {   // new/old positions in grid units and charge factor of one particle
-    double pos_new[3], pos_old[3], wq;
-};
-__device__ __forceinline__ ParticleGeom particle_geom(double xp, double yp, double zp, double wp, double uxp,
-                                                      double uyp, double uzp, const DepositGeom& dg) {
-    ParticleGeom g;
-    const double gaminv = 1.0 / sqrt(1.0 + uxp * uxp * INV_C2 + uyp * uyp * INV_C2 + uzp * uzp * INV_C2);  // :687-689
-    g.wq = dg.q * wp;
-    deposit_coords(xp, dg.xyzmin[0], dg.tshift, uxp, gaminv, dg.dinv[0], dg.dt, g.pos_new[0], g.pos_old[0]);   // :725-736
-    deposit_coords(yp, dg.xyzmin[1], dg.tshift, uyp, gaminv, dg.dinv[1], dg.dt, g.pos_new[1], g.pos_old[1]);
-    deposit_coords(zp, dg.xyzmin[2], dg.tshift, uzp, gaminv, dg.dinv[2], dg.dt, g.pos_new[2], g.pos_old[2]);
-    return g;
-}
-
-// anchor (global index of slot 0 of the stencil) packed relative to the J arrays, 10 bits each
-struct KeyBase { int b0, b1, b2; };
-__device__ __forceinline__ int pack_key(int gx, int gy, int gz, const KeyBase& kb) {
-    return (gx - kb.b0) | ((gy - kb.b1) << 10) | ((gz - kb.b2) << 20);
-}
-
 // ================================================================================================
 // quiet particles
 // ================================================================================================
@@ -118,7 +81,6 @@ template <int N, int VL = 1> struct QuietCfg {
 // Direction roles.  The kernel is written for "role" directions X (the direction along which
 // consecutive cells are visited and the register window slides), Y and Z; R0/R1/R2 say which
 // physical direction plays each role (the bins are numbered x-fastest, so X = x).
-struct J3 { FabView v[3]; };
 __device__ __forceinline__ long fab_stride(const FabView& F, int d) { return d == 0 ? 1 : (d == 1 ? F.sj : F.sk); }
 
 // SLOTRED = true: the NG particle slots of a pass are not summed by shuffles before a plane is retired --
@@ -640,6 +602,42 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     return 0;
 }
 #endif
+
+// The listed particles of another deposition kernel (deposit_cells.cu) through deposit_general_kernel.
+template <int N>
+static int launch_general(SoaView P, const int* list, const int* list_count, const pic_fab J[3], const DepositGeom& dg,
+                          cudaStream_t s) {
+    constexpr int NWG = 8;
+    using TG = GeneralCfg<N>;
+    for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < 3; ++c)
+            if (J[c].hi[d] - J[c].lo[d] + 2 > 1022) return fail("pic_deposit_esirkepov: J extent > 1020 points per rank");
+    KeyBase kb;
+    kb.b0 = min(J[0].lo[0], min(J[1].lo[0], J[2].lo[0])) - 1;
+    kb.b1 = min(J[0].lo[1], min(J[1].lo[1], J[2].lo[1])) - 1;
+    kb.b2 = min(J[0].lo[2], min(J[1].lo[2], J[2].lo[2])) - 1;
+    const size_t smem_g = (size_t)NWG * TG::NF * DR_CHP * sizeof(double);
+    auto kg = deposit_general_kernel<N, NWG>;
+#ifndef PIC_SIMT_HOST
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+        attr_done = true;
+    }
+    const int nblk = NUM_SMS;
+#else
+    const int nblk = 4;
+#endif
+    kg<<<nblk, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
+    count_launch();
+    return check_launch("pic_deposit_esirkepov(general)") ? 0 : 1;
+}
+int deposit_general_launch(SoaView P, const int* list, const int* list_count, const pic_fab J[3], const DepositGeom& dg,
+                           int nox, cudaStream_t s) {
+    if (nox == 1) return launch_general<1>(P, list, list_count, J, dg, s);
+    if (nox == 2) return launch_general<2>(P, list, list_count, J, dg, s);
+    return launch_general<3>(P, list, list_count, J, dg, s);
+}
 
 int deposit_runs_launch(const pic_soa* p, long offset, long np, const pic_fab J[3],
                         const DepositGeom& dg, int nox, cudaStream_t s) {

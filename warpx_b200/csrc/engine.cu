@@ -68,7 +68,28 @@ struct Laser {
     double* w_owned = nullptr;   // multi-rank: weights masked to this rank's brick (engine-owned)
 };
 
+// Per-stage CUDA-event timing of the step driver (pic_engine_enable_timing / pic_engine_stage_ms): the events are
+// recorded on the stream the stages are launched on, inside the same pic_engine_evolve calls a benchmark times.
+enum { ST_FILL_EB = 0, ST_GATHER_PUSH, ST_ZERO_J, ST_DEPOSIT, ST_SYNC_J, ST_EVOLVE_B, ST_FILL_B, ST_EVOLVE_E, ST_FILL_E,
+       ST_WRAP, ST_MIGRATE, ST_SORT, ST_NCI, ST_WINDOW, ST_PUSHP, ST_COUNT };
+static const char* const stage_names[ST_COUNT] = {"fill_boundary_eb", "gather_push", "zero_j", "deposit", "sync_current",
+    "evolve_b", "fill_boundary_b", "evolve_e", "fill_boundary_e", "wrap", "migrate", "sort", "nci_filter", "move_window", "push_p"};
+struct StageRec { int st; cudaEvent_t a, b; };
+struct Timing {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<StageRec> recs;
+    double ms[ST_COUNT] = {};
+    long calls[ST_COUNT] = {};
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t ev = nullptr; cudaEventCreate(&ev); pool.push_back(ev); }
+        return pool[used++];
+    }
+};
+
 struct Engine {
+    Timing tm;
     pic_geom geom;
     int box_lo[3], box_hi[3];
     int nox, galerkin, pusher, solver, sort_interval;
@@ -104,6 +125,32 @@ struct Engine {
     int* host_count = nullptr;                   // pinned host int (particles lost per boundary pass)
     std::vector<Laser> lasers;
 };
+
+struct Stage {      // records the events of one stage when timing is on
+    Engine& e; int st; cudaStream_t s; cudaEvent_t a = nullptr;
+    Stage(Engine& e_, int st_, void* s_) : e(e_), st(st_), s((cudaStream_t)s_) {
+#ifndef PIC_SIMT_HOST
+        if (e.tm.on) { a = e.tm.get(); cudaEventRecord(a, s); }
+#endif
+    }
+    ~Stage() {
+#ifndef PIC_SIMT_HOST
+        if (a) { cudaEvent_t b = e.tm.get(); cudaEventRecord(b, s); e.tm.recs.push_back({st, a, b}); }
+#endif
+    }
+};
+// fold the recorded events into the per-stage sums (synchronises on the last event)
+static void collect_timing(Engine& e) {
+#ifndef PIC_SIMT_HOST
+    for (const StageRec& r : e.tm.recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { e.tm.ms[r.st] += ms; e.tm.calls[r.st] += 1; }
+    }
+#endif
+    e.tm.recs.clear();
+    e.tm.used = 0;
+}
 
 static bool spans(const Engine& e, int dim) { return e.comm == nullptr || e.nb[dim] == 1; }
 static int neighbour(const Engine& e, int dim, int side) {
@@ -207,6 +254,22 @@ static void lower_corner(const Engine& e, const int ng[3], double xyzmin[3], int
 
 #define ENG_CALL(x) do { if (int rc_ = (x)) return rc_; } while (0)
 
+// The four halo message buffers hold at least n doubles each.  A failed allocation leaves the engine without
+// buffers (size 0, null pointers) instead of dangling ones: a later sweep allocates again or fails cleanly.
+static int grow_halo_buffers(Engine& e, size_t n) {
+    if (n <= e.hbuf_doubles) return 0;
+    e.hbuf_doubles = 0;
+    for (int b = 0; b < 4; ++b) { if (e.hbuf[b]) cudaFree(e.hbuf[b]); e.hbuf[b] = nullptr; }
+    for (int b = 0; b < 4; ++b)
+        if (cudaMalloc(&e.hbuf[b], sizeof(double) * n) != cudaSuccess) {
+            cudaGetLastError();
+            for (int c = 0; c < 4; ++c) { if (e.hbuf[c]) cudaFree(e.hbuf[c]); e.hbuf[c] = nullptr; }
+            return fail("pic_engine: halo buffer allocation failed");
+        }
+    e.hbuf_doubles = n;
+    return 0;
+}
+
 // One axis sweep of FillBoundary (mode 0) / SumBoundary (mode 1) over nfab components: local kernels
 // when this rank spans the periodic domain along dim, otherwise pack -> NCCL -> unpack(+add) with
 // one message per direction carrying the slabs of all components.
@@ -220,13 +283,7 @@ static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng,
         size_t n = 0;
         for (int c = 0; c < nfab; ++c) n += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
         if (n == 0) return 0;
-        if (n > e.hbuf_doubles) {
-            for (int b = 0; b < 4; ++b) {
-                if (e.hbuf[b]) cudaFree(e.hbuf[b]);
-                if (cudaMalloc(&e.hbuf[b], sizeof(double) * n) != cudaSuccess) return fail("pic_engine: halo buffer allocation failed");
-            }
-            e.hbuf_doubles = n;
-        }
+        ENG_CALL(grow_halo_buffers(e, n));
         for (int side = 0; side < 2; ++side) {
             if (!has_neighbour(e, dim, side)) continue;
             size_t off = 0;
@@ -257,13 +314,7 @@ static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng,
     }
     size_t n = 0;
     for (int c = 0; c < nfab; ++c) n += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);
-    if (n > e.hbuf_doubles) {
-        for (int b = 0; b < 4; ++b) {
-            if (e.hbuf[b]) cudaFree(e.hbuf[b]);
-            if (cudaMalloc(&e.hbuf[b], sizeof(double) * n) != cudaSuccess) return fail("pic_engine: halo buffer allocation failed");
-        }
-        e.hbuf_doubles = n;
-    }
+    ENG_CALL(grow_halo_buffers(e, n));
     ENG_CALL(pic_halo_pack_multi(fabs, nfab, dim, ng, mode, e.hbuf[0], e.hbuf[1], s));
     ENG_CALL(exchange(e, dim, e.hbuf[0], e.hbuf[1], e.hbuf[2], e.hbuf[3], n, (cudaStream_t)s));
     ENG_CALL(pic_halo_unpack_multi(fabs, nfab, dim, ng, mode, e.hbuf[2], e.hbuf[3], s));
@@ -331,14 +382,18 @@ static int apply_nci(Engine& e, void* s) {
 }
 
 static int push_particles_and_deposit(Engine& e, void* s) {
-    for (int c = 6; c < 9; ++c)                         // J.setVal(0), MultiParticleContainer.cpp:467-478
-        cudaMemsetAsync(e.fab[c].p, 0, sizeof(double) * (size_t)fab_size(e.fab[c]), (cudaStream_t)s);
+    {
+        Stage t(e, ST_ZERO_J, s);
+        for (int c = 6; c < 9; ++c)                     // J.setVal(0), MultiParticleContainer.cpp:467-478
+            cudaMemsetAsync(e.fab[c].p, 0, sizeof(double) * (size_t)fab_size(e.fab[c]), (cudaStream_t)s);
+    }
     double xyzmin[3]; int lo[3];
     lower_corner(e, e.ng_J, xyzmin, lo);
-    if (e.use_nci && !e.species.empty()) ENG_CALL(apply_nci(e, s));
+    if (e.use_nci && !e.species.empty()) { Stage t(e, ST_NCI, s); ENG_CALL(apply_nci(e, s)); }
     for (auto& sp : e.species) {
-        ENG_CALL(push(e, sp, e.dt, 1, s));
+        { Stage t(e, ST_GATHER_PUSH, s); ENG_CALL(push(e, sp, e.dt, 1, s)); }
         const pic_soa& P = sp.buf[sp.cur];
+        Stage t(e, ST_DEPOSIT, s);
         ENG_CALL(pic_deposit_esirkepov(&P, 0, P.np, &e.fab[6], e.dinv, xyzmin, lo, sp.q, e.dt, -0.5 * e.dt,
                                        e.nox, sp.has_bins ? &sp.bins : nullptr, s));
     }
@@ -425,6 +480,9 @@ static int migrate(Engine& e, Species& sp, void* stream) {
     P.np = np_new;
     long want = 16384;
     while (want < 8L * seen + 1024) want *= 2;
+    // A window shift sends one whole layer of cells to the slab below, also right after steps that saw only
+    // thermal crossers (c dt < dz: most steps do not shift): the capacity stays at the layer bound then.
+    if (e.do_moving_window && e.nb[e.mw_dir] > 1) want = sp.mig_cap_max;
     sp.mig_cap = (int)(want < sp.mig_cap_max ? want : sp.mig_cap_max);
     return 0;
 }
@@ -549,46 +607,51 @@ static int apply_particle_boundaries(Engine& e, void* stream) {
 static int one_step(Engine& e, bool last, void* s) {
     // ---- ExplicitFillBoundaryEBUpdateAux ----
     if (e.is_synchronized) {
-        ENG_CALL(fill_boundary(e, 0, 6, e.ng_EB, s));                    // ng_alloc_EB, :487-488
-        for (auto& sp : e.species) ENG_CALL(push(e, sp, -0.5 * e.dt, 0, s));   // PushP(-dt/2), :492-504
+        { Stage t(e, ST_FILL_EB, s); ENG_CALL(fill_boundary(e, 0, 6, e.ng_EB, s)); }                    // ng_alloc_EB, :487-488
+        { Stage t(e, ST_PUSHP, s); for (auto& sp : e.species) ENG_CALL(push(e, sp, -0.5 * e.dt, 0, s)); }   // PushP(-dt/2), :492-504
         e.is_synchronized = false;
     } else {
+        Stage t(e, ST_FILL_EB, s);
         ENG_CALL(fill_boundary(e, 0, 6, e.ng_FG, s));                    // :515-516
     }
     // ---- OneStep_nosub ----
     ENG_CALL(push_particles_and_deposit(e, s));
-    ENG_CALL(sync_current(e, s));
-    ENG_CALL(evolve_b(e, 0.5 * e.dt, s));
-    ENG_CALL(fill_boundary(e, 3, 6, e.ng_FS, s));
-    ENG_CALL(evolve_e(e, e.dt, s));
-    ENG_CALL(fill_boundary(e, 0, 3, e.ng_FS, s));
-    ENG_CALL(evolve_b(e, 0.5 * e.dt, s));
+    { Stage t(e, ST_SYNC_J, s); ENG_CALL(sync_current(e, s)); }
+    { Stage t(e, ST_EVOLVE_B, s); ENG_CALL(evolve_b(e, 0.5 * e.dt, s)); }
+    { Stage t(e, ST_FILL_B, s); ENG_CALL(fill_boundary(e, 3, 6, e.ng_FS, s)); }
+    { Stage t(e, ST_EVOLVE_E, s); ENG_CALL(evolve_e(e, e.dt, s)); }
+    { Stage t(e, ST_FILL_E, s); ENG_CALL(fill_boundary(e, 0, 3, e.ng_FS, s)); }
+    { Stage t(e, ST_EVOLVE_B, s); ENG_CALL(evolve_b(e, 0.5 * e.dt, s)); }
     if (last) {                                                           // Synchronize(), :64-91
-        ENG_CALL(fill_boundary(e, 0, 6, e.ng_FG, s));
-        for (auto& sp : e.species) ENG_CALL(push(e, sp, 0.5 * e.dt, 0, s));
+        { Stage t(e, ST_FILL_EB, s); ENG_CALL(fill_boundary(e, 0, 6, e.ng_FG, s)); }
+        { Stage t(e, ST_PUSHP, s); for (auto& sp : e.species) ENG_CALL(push(e, sp, 0.5 * e.dt, 0, s)); }
         e.is_synchronized = true;
     }
     const long step = e.istep++;
     e.cur_time += e.dt;                                                   // :232
     // ---- MoveWindow(step+1, move_j = is_synchronized), :247 ----
     int num_moved = 0;
-    ENG_CALL(move_window(e, e.is_synchronized, &num_moved, s));
+    { Stage t(e, ST_WINDOW, s); ENG_CALL(move_window(e, e.is_synchronized, &num_moved, s)); }
     // ---- HandleParticlesAtBoundaries ----
-    for (auto& sp : e.species) {
-        // amrex enforcePeriodic: only the particles the push of this step moved out of the domain
-        // (done before the removal below, while the indices listed by the push are still valid; the
-        // two act on different directions)
-        if (sp.has_esc) ENG_CALL(pic_particles_wrap_listed(&sp.buf[sp.cur], &e.geom, &sp.esc, s));
-        else ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
+    {
+        Stage t(e, ST_WRAP, s);
+        for (auto& sp : e.species) {
+            // amrex enforcePeriodic: only the particles the push of this step moved out of the domain
+            // (done before the removal below, while the indices listed by the push are still valid; the
+            // two act on different directions)
+            if (sp.has_esc) ENG_CALL(pic_particles_wrap_listed(&sp.buf[sp.cur], &e.geom, &sp.esc, s));
+            else ENG_CALL(pic_particles_wrap_periodic(&sp.buf[sp.cur], &e.geom, s));
+        }
+        for (auto& L : e.lasers) ENG_CALL(pic_particles_wrap_periodic(&L.P, &e.geom, s));
+        ENG_CALL(apply_particle_boundaries(e, s));
     }
-    for (auto& L : e.lasers) ENG_CALL(pic_particles_wrap_periodic(&L.P, &e.geom, s));
-    ENG_CALL(apply_particle_boundaries(e, s));
     for (auto& sp : e.species) {
-        if (e.comm) ENG_CALL(migrate(e, sp, s));
+        if (e.comm) { Stage t(e, ST_MIGRATE, s); ENG_CALL(migrate(e, sp, s)); }
         const bool due = e.sort_interval > 0 && (step + 1) % e.sort_interval == 0;
-        if (sp.sort_work && (due || (sp.bins_stale && sp.has_bins))) ENG_CALL(sort_species(e, sp, s));
+        if (sp.sort_work && (due || (sp.bins_stale && sp.has_bins))) { Stage t(e, ST_SORT, s); ENG_CALL(sort_species(e, sp, s)); }
         sp.bins_stale = false;
     }
+    if (e.tm.on && e.tm.recs.size() > 4096) collect_timing(e);          // bound the event pool of long runs
     return 0;
 }
 
@@ -621,6 +684,9 @@ extern "C" void pic_engine_destroy(void* h) {
     Engine* e = static_cast<Engine*>(h);
     if (e && e->filter_tmp) cudaFree(e->filter_tmp);
     if (e) {
+#ifndef PIC_SIMT_HOST
+        for (cudaEvent_t ev : e->tm.pool) cudaEventDestroy(ev);
+#endif
         for (auto& sp : e->species) {
             if (sp.has_esc) cudaFree(sp.esc.count);
             if (sp.mig_counts) cudaFree(sp.mig_counts);
@@ -639,6 +705,24 @@ extern "C" void pic_engine_destroy(void* h) {
     delete e;
 }
 extern "C" double pic_engine_dt(void* h) { return static_cast<Engine*>(h)->dt; }
+// Per-stage timing of pic_engine_evolve with CUDA events on the launching stream: switch on (the sums are reset),
+// run steps, read with pic_engine_stage_ms (synchronises on the recorded events).
+extern "C" int pic_engine_enable_timing(void* h, int on) {
+    Engine* e = static_cast<Engine*>(h);
+    collect_timing(*e);
+    for (int n = 0; n < ST_COUNT; ++n) { e->tm.ms[n] = 0.0; e->tm.calls[n] = 0; }
+    e->tm.on = on != 0;
+    return 0;
+}
+extern "C" int pic_engine_stage_count(void) { return ST_COUNT; }
+extern "C" const char* pic_engine_stage_name(int n) { return (n >= 0 && n < ST_COUNT) ? stage_names[n] : ""; }
+// total milliseconds and number of calls of every stage since pic_engine_enable_timing(h, 1)
+extern "C" int pic_engine_stage_ms(void* h, double ms[], long calls[]) {
+    Engine* e = static_cast<Engine*>(h);
+    collect_timing(*e);
+    for (int n = 0; n < ST_COUNT; ++n) { ms[n] = e->tm.ms[n]; calls[n] = e->tm.calls[n]; }
+    return 0;
+}
 extern "C" void pic_engine_guards(void* h, int out[12]) {
     Engine* e = static_cast<Engine*>(h);
     for (int d = 0; d < 3; ++d) { out[d] = e->ng_EB[d]; out[3 + d] = e->ng_J[d]; out[6 + d] = e->ng_FG[d]; out[9 + d] = e->ng_FS[d]; }
@@ -651,6 +735,12 @@ extern "C" int pic_engine_set_fields(void* h, const pic_fab fabs[9]) {
         for (int d = 0; d < 3; ++d)
             PIC_REQUIRE(fabs[c].ng[d] >= ng[d], "pic_engine_set_fields: component %d has %d guard cells, needs %d", c, fabs[c].ng[d], ng[d]);
     }
+    // the guard cells are final now (the moving window and the NCI corrector may have grown ng_J after
+    // pic_engine_set_boundaries checked it): a box along a non-periodic direction must hold both mirror images
+    for (int d = 0; d < 3; ++d)
+        PIC_REQUIRE(e->geom.periodic[d] || e->box_hi[d] - e->box_lo[d] + 1 >= 2 * e->ng_J[d],
+                    "pic_engine_set_fields: the box is too thin along the non-periodic direction %d (%d cells, ng_J = %d)",
+                    d, e->box_hi[d] - e->box_lo[d] + 1, e->ng_J[d]);
     return 0;
 }
 // bufA holds the particles; bufB is the sort target.  cell_start / sort_work may be NULL (no bins).

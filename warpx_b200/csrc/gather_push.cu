@@ -62,6 +62,8 @@ extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic
     cudaStream_t s = (cudaStream_t)stream;
     const EscapeView esc = make_escape(escaped, push_position);
     if (bins && nox <= 3) {        // the supercell kernel is built for orders 1..3; order 4 takes the order-agnostic one
+        // the bins index the whole tile: a sub-range would push particles outside it (or the tail twice)
+        PIC_REQUIRE(offset == 0 && np == p->np, "pic_gather_push: with cell bins the call must cover the whole tile (offset 0, np = %ld)", (long)p->np);
         if (int rc = gather_push_tile_launch(p, offset, np, E, B, gg, qdt2m, dt, nox, galerkin, pusher,
                                              push_position, bins, esc, s)) return rc;
         if (bins->np_binned >= np) return 0;

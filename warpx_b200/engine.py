@@ -21,6 +21,7 @@ There is no CPU path: constructing a Simulation without a CUDA device raises.
 import ctypes as C
 import math
 import os
+import weakref
 
 import numpy as np
 
@@ -121,11 +122,42 @@ def guard_cells(nox, dt, dx, use_filter=False, filter_npass=(1, 1, 1), do_moving
     return dict(ng_EB=ng_EB, ng_J=ng_J, ng_FG=ng_FG, ng_FS=ng_FS, ng_depos_J=ng_depos_J)
 
 
+def shared_comm(L, dist, torch, device):
+    """The ONE private NCCL communicator of this process (csrc/comm.cu), created on first use and reused by every
+    Simulation: rank 0 draws the 128-byte id, torch.distributed broadcasts it.  Kept on the `dist` object; release it
+    with release_comm(dist) on every rank at the same point of the program (after a barrier), before
+    torch.distributed.destroy_process_group()."""
+    comm = getattr(dist, "_pic_comm", None)
+    if comm:
+        return comm
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        raw = (C.c_ubyte * 128)()
+        check(L.pic_comm_unique_id(raw))
+        ident.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    raw = (C.c_ubyte * 128)(*ident.cpu().tolist())
+    comm = L.pic_comm_create(raw, world, rank)
+    if not comm:
+        raise RuntimeError(L.pic_last_error().decode())
+    dist._pic_comm, dist._pic_comm_lib = comm, L
+    return comm
+
+
+def release_comm(dist):
+    """Destroy the process's private communicator (collective in effect: call on every rank, engines closed)."""
+    comm = getattr(dist, "_pic_comm", None)
+    if comm:
+        dist._pic_comm_lib.pic_comm_destroy(comm)
+        dist._pic_comm = None
+
+
 class _DeviceOps:
     """pack/unpack/local guard-cell kernels for parallel.HaloExchanger."""
 
     def __init__(self, sim):
-        self.sim = sim
+        self.sim = weakref.proxy(sim)        # no reference cycle: a dropped Simulation is destroyed at once
 
     def empty(self, n):
         return self.sim.torch.empty(n, dtype=self.sim.torch.float64, device=self.sim.device)
@@ -165,7 +197,7 @@ class Species:
 
     def __init__(self, sim, name, q, m, arrays, capacity):
         t = sim.torch
-        self.sim, self.name, self.q, self.m = sim, name, q, m
+        self.sim, self.name, self.q, self.m = weakref.proxy(sim), name, q, m
         self.np = len(arrays["x"])
         self.capacity = max(capacity, self.np)
         # two SoA buffers: the counting sort permutes from one into the other
@@ -306,27 +338,28 @@ class Simulation:
             assert list(g12) == self.ng_EB + self.ng_J + self.ng_FG + self.ng_FS
             assert self.L.pic_engine_dt(self.native) == self.dt
             if self.world > 1:
-                ident = t.zeros(128, dtype=t.uint8, device=self.device)
-                if self.rank == 0:
-                    raw = (C.c_ubyte * 128)()
-                    check(self.L.pic_comm_unique_id(raw))
-                    ident.copy_(t.tensor(list(raw), dtype=t.uint8))
-                dist.broadcast(ident, 0)
-                raw = (C.c_ubyte * 128)(*ident.cpu().tolist())
                 self._sync()
-                self.comm = self.L.pic_comm_create(raw, self.world, self.rank)
-                if not self.comm:
-                    raise RuntimeError(self.L.pic_last_error().decode())
+                self.comm = shared_comm(self.L, dist, t, self.device)
                 check(self.L.pic_engine_set_comm(self.native, self.comm, abi.int3(self.dec.nb)))
             check(self.L.pic_engine_set_fields(self.native, (abi.pic_fab * 9)(*self.fab)))
 
+    def close(self):
+        """Destroy the C++ driver of this run (device scratch, events).  The NCCL communicator is the process's shared
+        one (shared_comm) and outlives the Simulation.  Idempotent; __del__ calls it."""
+        native, self.native = getattr(self, "native", None), None
+        if native:
+            try:
+                self._sync()
+            except Exception:            # interpreter shutdown
+                pass
+            self.L.pic_engine_destroy(native)
+        self.comm = None
+
     def __del__(self):
-        if getattr(self, "native", None):
-            self.L.pic_engine_destroy(self.native)
-            self.native = None
-        if getattr(self, "comm", None):
-            self.L.pic_comm_destroy(self.comm)
-            self.comm = None
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _backend(self, device):
         """(torch, library, device) of this run: a CUDA device and the nvcc-built library -- there is no CPU
@@ -339,7 +372,12 @@ class Simulation:
         self.torch.cuda.synchronize()
 
     def enable_stage_timing(self, on=True):
-        """Record CUDA events (on the launching stream) around every stage; read with stage_ms()."""
+        """CUDA events (on the launching stream) around every stage; read with stage_ms().  With the C++ driver the
+        events are recorded inside pic_engine_evolve (pic_engine_enable_timing), otherwise by the Python sequencer."""
+        if self.native:
+            check(self.L.pic_engine_enable_timing(self.native, 1 if on else 0))
+            self._native_timing = bool(on)
+            return
         self.stage_events = {} if on else None
 
     def _timed(self, name, fn, *a):
@@ -354,7 +392,12 @@ class Simulation:
         return r
 
     def stage_ms(self):
-        """Average milliseconds per call of every timed stage (synchronises)."""
+        """{stage: (average milliseconds per call, calls)} of every timed stage (synchronises)."""
+        if self.native:
+            n = self.L.pic_engine_stage_count()
+            ms, calls = (C.c_double * n)(), (C.c_long * n)()
+            check(self.L.pic_engine_stage_ms(self.native, ms, calls))
+            return {self.L.pic_engine_stage_name(k).decode(): (ms[k] / calls[k], int(calls[k])) for k in range(n) if calls[k]}
         self._sync()
         return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in self.stage_events.items()}
 
@@ -663,7 +706,7 @@ class Simulation:
         self.is_synchronized = True
 
     def Evolve(self, numsteps, synchronize_last=True):
-        if self.native and self.stage_events is None:
+        if self.native:
             check(self.L.pic_engine_evolve(self.native, numsteps, 1 if synchronize_last else 0, self.stream))
             self.istep += numsteps
             self.is_synchronized = bool(synchronize_last)
@@ -676,8 +719,6 @@ class Simulation:
                 self.geom.prob_lo[d], self.geom.prob_hi[d] = dom[d], dom[3 + d]
             self.time = self.L.pic_engine_time(self.native)
             return
-        if self.native:
-            raise RuntimeError("per-stage timing needs Simulation(native_driver=False)")
         for n in range(numsteps):
             self.ExplicitFillBoundaryEBUpdateAux()
             self.OneStep_nosub()

@@ -16,9 +16,19 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if not os.path.exists(path) or (os.path.isdir(_build.CSRC) and _build.stale()
-                                    and os.path.exists(_build.NVCC)):
-        path = _build.build()
+
+    def needs_build():
+        return not os.path.exists(path) or (os.path.isdir(_build.CSRC) and _build.stale() and os.path.exists(_build.NVCC))
+    if needs_build():
+        # one process per GPU: only one rank compiles, the others wait for the lock and find the library fresh
+        import fcntl
+        with open(os.path.join(_build.HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if needs_build():
+                    path = _build.build()
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     _LIB = bind(C.CDLL(path))
     return _LIB
 
@@ -70,6 +80,10 @@ def bind(L):
         "pic_engine_destroy": (None, [vp]),
         "pic_engine_dt": (C.c_double, [vp]),
         "pic_engine_guards": (None, [vp, ip]),
+        "pic_engine_enable_timing": (C.c_int, [vp, C.c_int]),
+        "pic_engine_stage_count": (C.c_int, []),
+        "pic_engine_stage_name": (C.c_char_p, [C.c_int]),
+        "pic_engine_stage_ms": (C.c_int, [vp, dp, C.POINTER(C.c_long)]),
         "pic_engine_set_fields": (C.c_int, [vp, fabp]),
         "pic_engine_add_species": (C.c_int, [vp, C.c_double, C.c_double, soap, soap, C.c_long, vp, ip, vp, vp]),
         "pic_engine_set_comm": (C.c_int, [vp, vp, ip]),
