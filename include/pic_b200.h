@@ -241,6 +241,9 @@ int pic_fill_boundary_local(const pic_fab* f, int dim, int ng, const pic_geom* g
  * periodic images of guard points (and the duplicate nodal point)
  * (WarpXComm.cpp:1386-1424 -> WarpXSumGuardCells.cpp:17-24 -> Communication.cpp:148-175). */
 int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, const pic_geom* g, void* stream);
+/* pic_fill_boundary_local (mode 0) / pic_sum_boundary_local (mode 1, ng = src_ng) of up to 8 components with one
+ * launch (the step driver's form: one launch per axis sweep of an exchange). */
+int pic_boundary_local_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, const pic_geom* g, void* stream);
 
 /* Bilinear (binomial) filter of one component: dst(i,j,k) = sum of the (1,2,1)/4 kernel applied
  * npass[d] times along each direction d, over every allocated point of dst (valid + guards),

@@ -306,11 +306,8 @@ static int halo_sweep(Engine& e, const pic_fab* fabs, int nfab, int dim, int ng,
     if (spans(e, dim)) {
         pic_geom gfull = e.geom;
         if (all_guards) gfull.periodic[0] = gfull.periodic[1] = gfull.periodic[2] = 1;
-        for (int c = 0; c < nfab; ++c) {
-            if (mode == 0) ENG_CALL(pic_fill_boundary_local(&fabs[c], dim, ng, all_guards ? &gfull : &e.geom, s));
-            else ENG_CALL(pic_sum_boundary_local(&fabs[c], dim, ng, &e.geom, s));
-        }
-        return 0;
+        // all components of the exchange in one launch
+        return pic_boundary_local_multi(fabs, nfab, dim, ng, mode, (mode == 0 && all_guards) ? &gfull : &e.geom, s);
     }
     size_t n = 0;
     for (int c = 0; c < nfab; ++c) n += (size_t)pic_halo_slab_count(&fabs[c], dim, ng, mode);

@@ -108,6 +108,53 @@ __global__ void multi_slab_kernel(MultiSlab m, double* __restrict__ buf_lo, doub
     else F(i, j, k) = buf[t];
 }
 
+// The local (self-neighbour) sweeps of up to HALO_MAX components in ONE launch: the x-grid walks the concatenated
+// slabs; every thread does what fill_local_kernel / sum_local_kernel do for its component.
+struct MultiLocal {
+    FabView v[HALO_MAX];
+    Slab sl[HALO_MAX];
+    long off[HALO_MAX + 1];
+    int vl[HALO_MAX], vh[HALO_MAX], nodal[HALO_MAX];
+    int n, dim, N, ng;
+};
+__global__ void multi_local_kernel(MultiLocal m, int mode) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m.off[m.n]) return;
+    int f = 0;
+#pragma unroll
+    for (int q = 1; q < HALO_MAX; ++q) if (q < m.n && t >= m.off[q]) f = q;
+    const Slab& sl = m.sl[f];
+    const FabView& F = m.v[f];
+    const int dim = m.dim, N = m.N, vl = m.vl[f], vh = m.vh[f];
+    int a, b, c;
+    decode(t - m.off[f], sl.n, a, b, c);
+    int idx[3] = {sl.start[0] + a, sl.start[1] + b, sl.start[2] + c};
+    const int layer = (dim == 0) ? a : ((dim == 1) ? b : c);
+    if (mode == 0) {            // fill_local_kernel
+        const int ng = m.ng;
+        int src[3] = {idx[0], idx[1], idx[2]};
+        if (layer < ng) { idx[dim] = vl - ng + layer; src[dim] = idx[dim] + N; }
+        else { idx[dim] = vh + 1 + (layer - ng); src[dim] = idx[dim] - N; }
+        F(idx[0], idx[1], idx[2]) = F(src[0], src[1], src[2]);
+        return;
+    }
+    // sum_local_kernel
+    const int g = m.nodal[f] ? layer : layer + 1;
+    int lo_i[3] = {idx[0], idx[1], idx[2]}, hi_i[3] = {idx[0], idx[1], idx[2]};
+    if (g == 0) {
+        lo_i[dim] = vl; hi_i[dim] = vh;
+        const double s2 = F(lo_i[0], lo_i[1], lo_i[2]) + F(hi_i[0], hi_i[1], hi_i[2]);
+        F(lo_i[0], lo_i[1], lo_i[2]) = s2;
+        F(hi_i[0], hi_i[1], hi_i[2]) = s2;
+        return;
+    }
+    int tgt[3] = {idx[0], idx[1], idx[2]};
+    lo_i[dim] = vl - g; tgt[dim] = vl - g + N;
+    F(tgt[0], tgt[1], tgt[2]) += F(lo_i[0], lo_i[1], lo_i[2]);
+    hi_i[dim] = vh + g; tgt[dim] = vh + g - N;
+    F(tgt[0], tgt[1], tgt[2]) += F(hi_i[0], hi_i[1], hi_i[2]);
+}
+
 static void full_extent(const pic_fab& f, Slab& sl) {
     for (int d = 0; d < 3; ++d) { sl.start[d] = f.lo[d]; sl.n[d] = f.hi[d] - f.lo[d] + 1; }
 }
@@ -166,6 +213,42 @@ extern "C" int pic_sum_boundary_local(const pic_fab* f, int dim, int src_ng, con
         make_view(*f), dim, N, vl, vh, src_ng, nodal, sl, total);
     count_launch();
     return check_launch("pic_sum_boundary_local") ? 0 : 1;
+}
+
+// pic_fill_boundary_local (mode 0, ng guard layers) / pic_sum_boundary_local (mode 1, ng = src_ng) of nfab
+// components with one launch.
+extern "C" int pic_boundary_local_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, const pic_geom* g,
+                                        void* stream) {
+    PIC_REQUIRE(nfab >= 1 && nfab <= HALO_MAX, "pic_boundary_local_multi: 1..%d components", HALO_MAX);
+    PIC_REQUIRE(dim >= 0 && dim < 3 && (mode == 0 || mode == 1), "pic_boundary_local_multi: bad arguments");
+    PIC_REQUIRE(g->periodic[dim], "pic_boundary_local_multi: dimension %d is not periodic", dim);
+    if (mode == 0 && ng == 0) return 0;
+    MultiLocal m;
+    m.n = nfab; m.dim = dim; m.N = g->n_cell[dim]; m.ng = ng;
+    m.off[0] = 0;
+    for (int f = 0; f < nfab; ++f) {
+        const pic_fab& F = fabs[f];
+        const int vl = vlo(F, dim), vh = vhi(F, dim), nodal = F.stag[dim];
+        PIC_REQUIRE(vh - vl + 1 - nodal == m.N, "pic_boundary_local_multi: box does not span the domain in dim %d", dim);
+        PIC_REQUIRE(ng <= F.ng[dim] && (mode == 0 ? ng <= m.N : 2 * ng + 1 <= m.N), "pic_boundary_local_multi: ng=%d too large", ng);
+        m.v[f] = make_view(F); m.vl[f] = vl; m.vh[f] = vh; m.nodal[f] = nodal;
+        Slab& sl = m.sl[f];
+        full_extent(F, sl); sl.dim = dim;
+        if (mode == 0) {
+            sl.n[dim] = 2 * ng;
+            for (int d = 0; d < 3; ++d)          // see pic_fill_boundary_local
+                if (d != dim && !g->periodic[d]) { sl.start[d] = vlo(F, d); sl.n[d] = vhi(F, d) - vlo(F, d) + 1; }
+        } else {
+            sl.n[dim] = ng + nodal;
+        }
+        m.off[f + 1] = m.off[f] + (long)sl.n[0] * sl.n[1] * sl.n[2];
+    }
+    for (int f = nfab; f < HALO_MAX; ++f) m.off[f + 1] = m.off[nfab];
+    const long total = m.off[nfab];
+    if (total == 0) return 0;
+    multi_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m, mode);
+    count_launch();
+    return check_launch("pic_boundary_local_multi") ? 0 : 1;
 }
 
 extern "C" long pic_halo_slab_count(const pic_fab* f, int dim, int ng, int mode) {
