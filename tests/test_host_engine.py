@@ -61,6 +61,30 @@ def test_periodic_loop_on_the_host_matches_oracle(orc, HostSimulation):
     assert e == pytest.approx(eo, rel=1e-10)
 
 
+def test_order3_loop_with_lane_per_cell_deposition_on_the_host_matches_oracle(orc, HostSimulation):
+    """Config 2 in the small (16^3, 8 ppc, order 3, hot enough that particles cross cell faces every step): nine steps of
+    the C++ driver with pic_set_deposit_mode(PIC_DEPOSIT_CELLS) -- slices, extra rounds for the particles that left the
+    cell of their bin (the sort runs every 4 steps), the list for those that left the supercell -- under emulation."""
+    from host_harness import harness
+    wl = workloads.uniform_plasma_3d(n=16, ppc=(2, 2, 2), u_th=0.1, lx=2.5e-6, perturbation=0.01)
+    hl = harness.host_library()
+    hl.pic_set_deposit_mode(abi.PIC_DEPOSIT_CELLS)
+    try:
+        sim = HostSimulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, sort_interval=4)
+        osim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3)
+        for s in wl["species"]:
+            sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+            osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+        sim.Evolve(9)
+        osim.evolve(9)
+    finally:
+        hl.pic_set_deposit_mode(abi.PIC_DEPOSIT_RUNS)
+    _compare(sim, osim, 1)
+    e, b = sim.field_energy()
+    eo, bo = osim.field_energy()
+    assert e == pytest.approx(eo, rel=1e-10)
+
+
 def test_boosted_deck_with_every_feature_on_the_host_matches_oracle(orc, HostSimulation):
     """BASELINE.json config 4 in the very small: gamma_boost = 10, CKC, Vay, order 3, bilinear filter, Godfrey NCI
     corrector, PEC walls in z, moving window, boosted Gaussian antenna, electrons + ions injected continuously from

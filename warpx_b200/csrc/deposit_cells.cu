@@ -1,9 +1,8 @@
 // Esirkepov deposition for cell-sorted particles, one LANE PER CELL (pic_set_deposit_mode(PIC_DEPOSIT_CELLS);
 // replaces doEsirkepovDepositionShapeN, Source/Particles/Deposition/CurrentDeposition.H:642-907).
 //
-// For a particle whose old and new position lie in the cell of its bin ("quiet", > 95 % of a thermal plasma)
-// the stencil is anchored at the cell: ALL particles of a cell add into the same (N+1)^2 x N nodes per
-// component,
+// For a particle whose old and new position lie in one cell ("quiet", > 95 % of a thermal plasma) the stencil
+// is anchored at that cell: ALL quiet particles of a cell add into the same (N+1)^2 x N nodes per component,
 //     Jx[i][j][k] += cx[i] * (Sy_new[j] Az[k] + Sy_old[j] Bz[k]),   cx = prefix sums of wq/(dt dy dz)(Sx_old - Sx_new),
 //     Az = Sz_new/3 + Sz_old/6,  Bz = Sz_old/3 + Sz_new/6            (cyclically for Jy, Jz).
 // deposit_runs.cu gives every stencil LINE a lane and walks the particles: each lane re-reads the particle's
@@ -16,13 +15,23 @@
 // role does not always land on the same SM sub-partition):
 //   producer   lane = cell; slice s = the s-th particle of every cell of a group of 32 cells (4 rows along
 //              x): positions, shape factors, prefix sums -> one record per lane in shared memory (double
-//              buffered); particles that are not quiet in their bin's cell go to a list;
+//              buffered), and a header telling the consumers what the buffer holds;
 //   consumer c (c = x, y, z)   same lane = cell mapping; reads the record of its lane and accumulates component c.
 // After the last slice of a group a consumer adds its sums into the CTA's shared-memory J block of its
 // component with plain read-modify-writes: it is the only writer of that block, and inside one instruction the
 // lanes (distinct cells, same stencil offset) touch distinct nodes.  At the end the block goes to J with one
 // fp64 red.global per touched node (7 per cell instead of the 40 of deposit_runs.cu, 540 per particle in
-// the reference).  The listed particles take deposit_general_kernel (deposit_runs.cu).
+// the reference).
+//
+// Particles that are not quiet in the cell of their bin -- they crossed a cell face during this step, or moved
+// since the last sort -- are split into sub-particles of the quiet form: a particle that changes cell along a
+// direction is exactly the sum of two quiet-form stencils anchored at consecutive cells (window slots 0..N with
+// prefix entries 0..N-1, and slot N+1 with prefix entry N: the same products as the full stencil, term by
+// term).  The sub-particle anchored at the lane's own cell rides in the regular slice; the others are queued in
+// shared memory and deposited after the groups in EXTRA ROUNDS: a lane takes one queued sub-particle of any cell
+// (distinct cells within a round, __match_any_sync), the consumers accumulate it like a slice and add it at the
+// record's own anchor.  Only particles with a sub-particle outside the supercell go to the list of
+// deposit_general_kernel (deposit_runs.cu): about one in eight of the movers.
 // Orders 1 and 3 (the stencil of every particle of a cell starts at the same node; not so at order 2).
 #include "pic_common.cuh"
 #include "deposit_common.cuh"
@@ -44,11 +53,17 @@ template <int N> struct CellsCfg {
     static constexpr int PX = 12, PY = T + QS - 1, PZ = T + QS - 1;   // J block: pitch 12 keeps rows r, r+2 in disjoint banks
     static constexpr int TS = PX * PY * PZ;       // doubles per component
     static constexpr int NCP = (QP + 1) / 2;      // double2 elements of one component's prefix sums
-    // record (double2 per lane): (Sx_new,Sx_old)[QS], (Sy_new,Sy_old)[QS], (Ay,By)[QS], (Az,Bz)[QS], cds x/y/z [NCP] each
-    static constexpr int F_SX = 0, F_SY = QS, F_ABY = 2 * QS, F_ABZ = 3 * QS, F_CDS = 4 * QS;
-    static constexpr int NF = 4 * QS + 3 * NCP;
-    static constexpr size_t smem_bytes = sizeof(double2) * 2 * NF * 32 + sizeof(double) * 3 * TS;
+    // record (double2 per lane): (Sx_new,Sx_old)[QS], (Sy_new,Sy_old)[QS], (Ay,By)[QS], (Az,Bz)[QS], cds x/y/z [NCP] each,
+    // then one element of integers {active, offset of the anchor cell in the J block} (extra rounds only)
+    static constexpr int F_SX = 0, F_SY = QS, F_ABY = 2 * QS, F_ABZ = 3 * QS, F_CDS = 4 * QS, F_META = 4 * QS + 3 * NCP;
+    static constexpr int NF = F_META + 1;
+    static constexpr int QCAP = 768;              // queued sub-particles per supercell (8 bytes each)
+    static constexpr size_t smem_bytes = sizeof(double2) * 2 * NF * 32 + sizeof(double) * 3 * TS + sizeof(int2) * QCAP + 64;
 };
+
+// what the consumers do with a record buffer (written by the producer before the barrier)
+struct CellsHeader { int kind, retire, g, pad; };
+constexpr int DC_END = 0, DC_SLICE = 1, DC_EXTRA = 2;
 
 template <int N, int MINB>
 __global__ void __launch_bounds__(128, MINB)
@@ -57,114 +72,96 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
     using T = CellsCfg<N>;
     constexpr int QS = T::QS, QP = T::QP, NF = T::NF, NCP = T::NCP, PX = T::PX, PY = T::PY, TS = T::TS;
     PIC_DYNAMIC_SMEM(double2, smem2);
-    double2* rec = smem2;                                            // [2][NF][32]
-    double* tile = reinterpret_cast<double*>(smem2 + 2 * NF * 32);   // [3][TS]
+    double2* rec = smem2;                                                  // [2][NF][32]
+    double* tile = reinterpret_cast<double*>(smem2 + 2 * NF * 32);         // [3][TS]
+    int2* queue = reinterpret_cast<int2*>(tile + 3 * TS);                  // [QCAP] (particle, code)
+    CellsHeader* hdr = reinterpret_cast<CellsHeader*>(queue + T::QCAP);    // [2]
+    int* q_count = reinterpret_cast<int*>(hdr + 2);      // [0] entries requested, [1] first slot that did not fit
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int role = (warp + blockIdx.x) & 3;                        // 0 producer, 1..3 consumer of component role-1
+    const int role = (warp + blockIdx.x) & 3;                              // 0 producer, 1..3 consumer of component role-1
     const bool producer = role == 0;
     const int comp = role - 1;
 
-    // supercell of this CTA
     int tc[3];
-    tile_coords(bins, blockIdx.x, tc);
+    tile_coords(bins, blockIdx.x, tc);                                     // supercell of this CTA
     const long bin0 = (long)blockIdx.x * (T::T * T::T * T::T);
     // lane -> cell of a group: 8 cells along x, rows 0,2,1,3 (rows r, r+2 share a half-warp: disjoint banks)
     const int lx = lane & 7, rsel = lane >> 3, lrow = ((rsel & 1) << 1) | (rsel >> 1);
 
     for (int n = threadIdx.x; n < 3 * TS; n += 128) tile[n] = 0.0;
     for (int n = threadIdx.x; n < 2 * NF * 32; n += 128) rec[n] = make_double2(0.0, 0.0);
-
-    // ---- group walk shared by all roles: (g, s) = slice s of group g; maxn = largest cell of the group ----
-    struct Walk { int g, s, maxn, p0, n; bool done; };
-    auto load_group = [&](Walk& w) {
-        // next group with particles
-        while (true) {
-            ++w.g;
-            if (w.g >= 16) { w.done = true; return; }
-            const int ly = ((w.g & 1) << 2) + lrow, lz = w.g >> 1;
-            const long b = bin0 + lx + T::T * (ly + T::T * lz);
-            int p0 = bins.cell_start[b], p1 = bins.cell_start[b + 1];
-            p0 = (int)min((long)p0, np_lim); p1 = (int)min((long)p1, np_lim);
-            w.p0 = p0; w.n = p1 - p0;
-            int m = w.n;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) m = max(m, __shfl_xor_sync(DC_FULL, m, o));
-            w.maxn = m;
-            w.s = 0;
-            if (m > 0) return;
-        }
-    };
-    auto advance = [&](Walk& w) {
-        if (++w.s >= w.maxn) load_group(w);
-    };
-
+    if (threadIdx.x == 0) { q_count[0] = 0; q_count[1] = T::QCAP; }
     __syncthreads();
 
     if (producer) {
-        // ======================= producer =======================
-        Walk w{-1, 0, 0, 0, 0, false};
-        load_group(w);
-        // expected leftmost index of the new position's stencil for a particle of the lane's cell
-        const int off[3] = {bins.box_lo[0] - dg.lo[0] + T::O0, bins.box_lo[1] - dg.lo[1] + T::O0, bins.box_lo[2] - dg.lo[2] + T::O0};
-        double pf[7] = {0, 0, 0, 0, 0, 0, 0};
-        int it = 0;
-        auto produce = [&](double2* buf) {
-            const bool valid = w.s < w.n;
-            const long ip = (long)w.p0 + w.s;
-            double xp, yp, zp, wp, uxp, uyp, uzp;
-            if (w.s == 0) {
-                if (valid) { pf[0] = P.x[ip]; pf[1] = P.y[ip]; pf[2] = P.z[ip]; pf[3] = P.w[ip]; pf[4] = P.ux[ip]; pf[5] = P.uy[ip]; pf[6] = P.uz[ip]; }
+        // ============================== producer ==============================
+        // anchor (leftmost index of a quiet particle's stencil, CurrentDeposition.H:759) of the supercell's cell 0
+        const int amin[3] = {tc[0] * T::T + bins.box_lo[0] - dg.lo[0] + T::O0, tc[1] * T::T + bins.box_lo[1] - dg.lo[1] + T::O0,
+                             tc[2] * T::T + bins.box_lo[2] - dg.lo[2] + T::O0};
+        struct Part {
+            double wn[3][N + 1], wo[3][N + 1], wq;
+            int t[3];       // anchor of the low sub-particle, in cells of the supercell
+            int sh[3];      // i_old - i_new
+            bool inside;    // every sub-particle is anchored at a cell of this supercell
+        };
+        auto compute = [&](long ip, Part& q) {
+            const ParticleGeom pg = particle_geom(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip], dg);
+            q.wq = pg.wq;
+            bool in = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int inew = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], q.wn[d], q.wo[d], q.sh[d]);
+                q.t[d] = inew + (q.sh[d] < 0 ? q.sh[d] : 0) - amin[d];
+                in = in && q.sh[d] >= -1 && q.sh[d] <= 1 && q.t[d] >= 0 && q.t[d] + (q.sh[d] ? 1 : 0) < T::T;
             }
-            xp = pf[0]; yp = pf[1]; zp = pf[2]; wp = pf[3]; uxp = pf[4]; uyp = pf[5]; uzp = pf[6];
-            if (w.s + 1 < w.n) {       // request the next slice of this cell
-                pf[0] = P.x[ip + 1]; pf[1] = P.y[ip + 1]; pf[2] = P.z[ip + 1]; pf[3] = P.w[ip + 1];
-                pf[4] = P.ux[ip + 1]; pf[5] = P.uy[ip + 1]; pf[6] = P.uz[ip + 1];
-            }
-            bool ok = false;
-            double2* r = buf + lane;
-            if (valid) {
-                const ParticleGeom pg = particle_geom(xp, yp, zp, wp, uxp, uyp, uzp, dg);
-                double wn[3][N + 1], wo[3][N + 1];
-                int inew[3], sh[3];
+            q.inside = in;
+        };
+        // The record of sub-particle v (v[d] = 0 low, 1 high) of q.  Window slot s (0..N+1) of direction d holds
+        //   wn5[s] = wn[s - (sh < 0)],  wo5[s] = wo[s - (sh > 0)]   (0 outside 0..N),
+        // c5[i] = prefix sum of wq/(dt dA) (wo5 - wn5) up to slot i; low: slots 0..N, c5[0..N-1]; high: slot N+1, c5[N].
+        auto emit = [&](const Part& q, const int v[3], double2* r, int active, int base) {
+            double2 s2[3][QS];
+            double cds[3][2 * NCP];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn[d], wo[d], sh[d]);
-                const int ly = ((w.g & 1) << 2) + lrow, lz = w.g >> 1;
-                const int ex = tc[0] * T::T + lx + off[0], ey = tc[1] * T::T + ly + off[1], ez = tc[2] * T::T + lz + off[2];
-                ok = (sh[0] | sh[1] | sh[2]) == 0 && inew[0] == ex && inew[1] == ey && inew[2] == ez;
-                if (ok) {
+            for (int d = 0; d < 3; ++d) {
+                const bool nsh = q.sh[d] < 0, osh = q.sh[d] > 0, hi = v[d] != 0;
+                const double wqd = q.wq * dg.invdtd[d];
+                double run = 0.0;
 #pragma unroll
-                    for (int s = 0; s < QS; ++s) {
-                        r[(T::F_SX + s) * 32] = make_double2(wn[0][s], wo[0][s]);
-                        r[(T::F_SY + s) * 32] = make_double2(wn[1][s], wo[1][s]);
-                        r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * wn[1][s] + (1.0 / 6.0) * wo[1][s],
-                                                              (1.0 / 3.0) * wo[1][s] + (1.0 / 6.0) * wn[1][s]);
-                        r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * wn[2][s] + (1.0 / 6.0) * wo[2][s],
-                                                              (1.0 / 3.0) * wo[2][s] + (1.0 / 6.0) * wn[2][s]);
-                    }
-                    // prefix sums over the first N nodes (the sum over all N+1 vanishes and is not deposited:
-                    // loop trimming of CurrentDeposition.H:777-788 with dl = du = 1)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const double wqd = pg.wq * dg.invdtd[d];
-                        double cds[2 * NCP];
-                        cds[2 * NCP - 1] = 0.0;
-                        double run = 0.0;
-#pragma unroll
-                        for (int i = 0; i < QP; ++i) {
-                            run += wqd * (wo[d][i] - wn[d][i]);
-                            cds[i] = run;
-                        }
-#pragma unroll
-                        for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[2 * m], cds[2 * m + 1]);
-                    }
+                for (int s = 0; s <= N; ++s) {
+                    const double n5 = nsh ? (s >= 1 ? q.wn[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wn[d][s];
+                    const double o5 = osh ? (s >= 1 ? q.wo[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wo[d][s];
+                    run += wqd * (o5 - n5);
+                    if (s < QP) cds[d][s] = hi ? 0.0 : run;
+                    s2[d][s] = hi ? make_double2(0.0, 0.0) : make_double2(n5, o5);
+                }
+                if (2 * NCP > QP) cds[d][2 * NCP - 1] = 0.0;
+                if (hi) {     // slot N+1 and prefix entry N, at the local positions N and N-1 of the next cell
+                    s2[d][N] = make_double2(nsh ? q.wn[d][N] : 0.0, osh ? q.wo[d][N] : 0.0);
+                    cds[d][QP - 1] = run;            // c5[N]
                 }
             }
-            if (!ok) {     // nothing to add from this lane: zero prefix sums (the weights left in the record are finite)
 #pragma unroll
-                for (int m = 0; m < 3 * NCP; ++m) r[(T::F_CDS + m) * 32] = make_double2(0.0, 0.0);
+            for (int s = 0; s < QS; ++s) {
+                r[(T::F_SX + s) * 32] = s2[0][s];
+                r[(T::F_SY + s) * 32] = s2[1][s];
+                r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * s2[1][s].x + (1.0 / 6.0) * s2[1][s].y,
+                                                      (1.0 / 3.0) * s2[1][s].y + (1.0 / 6.0) * s2[1][s].x);
+                r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * s2[2][s].x + (1.0 / 6.0) * s2[2][s].y,
+                                                      (1.0 / 3.0) * s2[2][s].y + (1.0 / 6.0) * s2[2][s].x);
             }
-            // particles of the bin that are not quiet in the bin's cell: list for the general kernel
-            const bool listed = valid && !ok;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[d][2 * m], cds[d][2 * m + 1]);
+            *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(active, base);
+        };
+        auto emit_nothing = [&](double2* r) {    // zero prefix sums: the weights left in the record are finite
+#pragma unroll
+            for (int m = 0; m < 3 * NCP; ++m) r[(T::F_CDS + m) * 32] = make_double2(0.0, 0.0);
+            *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(0, 0);
+        };
+        auto to_list = [&](bool listed, long ip) {   // particles for deposit_general_kernel (warp-aggregated append)
             const unsigned mm = __ballot_sync(DC_FULL, listed);
             if (mm) {
                 int basei = 0;
@@ -173,18 +170,119 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                 if (listed) list[basei + __popc(mm & ((1u << lane) - 1u))] = (int)ip;
             }
         };
-        if (!w.done) produce(rec);
-        __syncthreads();
-        while (!w.done) {           // the consumers process slice `it` while slice it+1 is produced
-            advance(w);
-            if (!w.done) produce(rec + (size_t)((it + 1) & 1) * NF * 32);
-            __syncthreads();
-            ++it;
+
+        // The particles of a group are one contiguous range (the bins are numbered group after group); while a group
+        // is processed the lines of the next one are requested: every lane 2 sectors of each of the 7 arrays.
+        auto prefetch_group = [&](int g) {
+#ifndef PIC_SIMT_HOST
+            if (g >= 16) return;
+            const long first = bins.cell_start[bin0 + 32 * g], last = min((long)bins.cell_start[bin0 + 32 * g + 32], np_lim);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long ip = first + 4 * (lane + 32 * k);
+                if (ip < last) {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.x + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.y + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.z + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.w + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.ux + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.uy + ip));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.uz + ip));
+                }
+            }
+#else
+            (void)g;
+#endif
+        };
+        prefetch_group(0);
+        int it = 0;
+        // ---------------- the groups: slice s = the s-th particle of each of the 32 cells ----------------
+        for (int g = 0; g < 16; ++g) {
+            prefetch_group(g + 1);
+            const int ly = ((g & 1) << 2) + lrow, lz = g >> 1;
+            const long b = bin0 + lx + T::T * (ly + T::T * lz);
+            const int p0 = (int)min((long)bins.cell_start[b], np_lim), p1 = (int)min((long)bins.cell_start[b + 1], np_lim);
+            const int n = p1 - p0;
+            int maxn = n;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) maxn = max(maxn, __shfl_xor_sync(DC_FULL, maxn, o));
+            const int lc[3] = {lx, ly, lz};
+            for (int s = 0; s < maxn; ++s) {
+                double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
+                const bool valid = s < n;
+                const long ip = (long)p0 + s;
+                bool listed = false, sent = false;
+                if (valid) {
+                    Part q;
+                    compute(ip, q);
+                    if (!q.inside) listed = true;
+                    else {
+                        int vreg[3];
+                        bool has_reg = true;
+                        int nvirt = 1;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            vreg[d] = lc[d] - q.t[d];
+                            has_reg = has_reg && (vreg[d] == 0 || (vreg[d] == 1 && q.sh[d] != 0));
+                            nvirt *= q.sh[d] ? 2 : 1;
+                        }
+                        const int nq = nvirt - (has_reg ? 1 : 0);
+                        bool room = true;
+                        if (nq > 0) {
+                            int slot = atomicAdd(q_count, nq);
+                            room = slot + nq <= T::QCAP;
+                            if (!room) atomicMin(q_count + 1, slot);      // later requests start beyond: they do not fit either
+                            if (room) {
+#pragma unroll 1
+                                for (int v = 0; v < 8; ++v) {
+                                    const int vx = v & 1, vy = (v >> 1) & 1, vz = v >> 2;
+                                    if ((vx && !q.sh[0]) || (vy && !q.sh[1]) || (vz && !q.sh[2])) continue;
+                                    if (has_reg && vx == vreg[0] && vy == vreg[1] && vz == vreg[2]) continue;
+                                    queue[slot++] = make_int2((int)ip, v | ((q.t[0] + vx) << 3) | ((q.t[1] + vy) << 6) | ((q.t[2] + vz) << 9));
+                                }
+                            }
+                        }
+                        if (!room) listed = true;           // queue full: the whole particle goes to the list
+                        else if (has_reg) { emit(q, vreg, r, 1, 0); sent = true; }
+                    }
+                }
+                if (!sent) emit_nothing(r);
+                to_list(listed, ip);
+                if (lane == 0) hdr[it & 1] = CellsHeader{DC_SLICE, s == maxn - 1 ? 1 : 0, g, 0};
+                __syncthreads();
+                ++it;
+            }
         }
+        // ---------------- extra rounds: the queued sub-particles, one per lane, distinct cells per round ----------------
+        __syncwarp();
+        const int nq_total = min(q_count[0], q_count[1]);
+        for (int qb = 0; qb < nq_total; qb += 32) {
+            bool pend = qb + lane < nq_total;
+            const int2 e = pend ? queue[qb + lane] : make_int2(0, 0);
+            const int akey = (e.y >> 3) & 511;
+            while (__ballot_sync(DC_FULL, pend)) {
+                const unsigned m = __match_any_sync(DC_FULL, pend ? akey : 512 + lane);
+                const bool go = pend && lane == __ffs(m) - 1;
+                double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
+                if (go) {
+                    Part q;
+                    compute(e.x, q);
+                    const int v[3] = {e.y & 1, (e.y >> 1) & 1, (e.y >> 2) & 1};
+                    const int ax = (e.y >> 3) & 7, ay = (e.y >> 6) & 7, az = (e.y >> 9) & 7;
+                    emit(q, v, r, 1, ax + PX * (ay + PY * az));
+                } else {
+                    emit_nothing(r);
+                }
+                if (lane == 0) hdr[it & 1] = CellsHeader{DC_EXTRA, 1, 0, 0};
+                __syncthreads();
+                ++it;
+                pend = pend && !go;
+            }
+        }
+        if (lane == 0) hdr[it & 1] = CellsHeader{DC_END, 0, 0, 0};
+        __syncthreads();
     } else {
-        // ======================= consumer of component comp =======================
-        Walk w{-1, 0, 0, 0, 0, false};
-        load_group(w);
+        // ============================== consumer of component comp ==============================
         // component roles: acc[a][b][p] += cds[p] * (A[a].x B[b].x + A[a].y B[b].y)
         //   Jx: a = y (Sy),  b = z (ABz), p = x     Jy: a = x (Sx), b = z (ABz), p = y     Jz: a = x (Sx), b = y (ABy), p = z
         const int fA = (comp == 0) ? T::F_SY : T::F_SX;
@@ -202,10 +300,12 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
 #pragma unroll
                 for (int p = 0; p < QP; ++p) acc[a][b][p] = 0.0;
         int it = 0;
-        __syncthreads();             // slice 0 is in the record
-        while (!w.done) {
+        while (true) {
+            __syncthreads();             // the producer has filled buffer it & 1 and its header
+            const CellsHeader h = hdr[it & 1];
+            if (h.kind == DC_END) break;
+            const double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
             {
-                const double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
                 double cds[2 * NCP];
 #pragma unroll
                 for (int m = 0; m < NCP; ++m) {
@@ -226,12 +326,12 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                     }
                 }
             }
-            if (w.s == w.maxn - 1) {
+            if (h.retire && h.kind == DC_SLICE) {
                 // ---- last slice of the group: add the lane's sums into the CTA's J block of this component.
                 // Lanes are distinct cells, so one instruction (fixed stencil offset) touches distinct nodes; two
                 // offsets that differ along z never meet (the cells of a group share z), the others are ordered
                 // by __syncwarp.
-                const int ly = ((w.g & 1) << 2) + lrow, lz = w.g >> 1;
+                const int ly = ((h.g & 1) << 2) + lrow, lz = h.g >> 1;
                 double* base = tl + lx + PX * (ly + PY * lz);
                 if (comp == 2) {                 // z is the prefix direction
 #pragma unroll
@@ -260,9 +360,25 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                             __syncwarp();
                         }
                 }
+            } else if (h.kind == DC_EXTRA) {
+                // ---- extra round: every lane carries one sub-particle of ITS OWN cell (distinct cells within the
+                // round): add at the record's anchor, one stencil offset at a time (the cells differ in every
+                // direction now, so every step is ordered).
+                const int2 mt = *reinterpret_cast<const int2*>(&r[T::F_META * 32]);
+                double* base = tl + mt.y;
+                const bool active = mt.x != 0;
+#pragma unroll
+                for (int a = 0; a < QS; ++a)
+#pragma unroll
+                    for (int b = 0; b < QS; ++b)
+#pragma unroll
+                        for (int p = 0; p < QP; ++p) {
+                            double* q = base + a * sa + b * sb + p * sp;
+                            if (active) *q += acc[a][b][p];
+                            acc[a][b][p] = 0.0;
+                            __syncwarp();
+                        }
             }
-            advance(w);
-            __syncthreads();
             ++it;
         }
     }
