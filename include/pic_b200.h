@@ -155,6 +155,9 @@ typedef struct pic_plasma_injector {
 enum { PIC_ERR_ABORT = 0, PIC_ERR_RETURN = 1 };
 void pic_set_error_mode(int mode);
 const char* pic_last_error(void);
+/* Kernel-variant defaults from the environment: PIC_FDTD_MODE, PIC_DEPOSIT_MODE, PIC_GATHER_MODE (values as the
+ * pic_set_*_mode calls).  The Python loader calls it once after dlopen. */
+void pic_apply_env_defaults(void);
 const char* pic_version(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -171,6 +174,12 @@ int pic_evolve_b(const pic_fab B[3], const pic_fab E[3], const pic_stencil* st, 
  * WarpX::EvolveE (WarpXPushFieldsEM.cpp:958-962).  E += c^2 dt (curl B - mu0 J). */
 int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3],
                  const pic_stencil* st, double dt, void* stream);
+/* How the Yee kernels read their source field: 1 (default) = bulk-asynchronous copies (cp.async.bulk, completion on an
+ * mbarrier) stage the rows a CTA needs into a shared-memory ring, plane after plane (csrc/fdtd_bulk.cu); 0 = plain
+ * read-only loads (csrc/fdtd.cu).  CKC's EvolveB and arrays whose base is not 16-byte aligned always take the plain
+ * kernels.  Same arithmetic either way. */
+void pic_set_fdtd_mode(int mode);
+long pic_fdtd_bulk_launches(void);   /* launches of the bulk-staged kernels so far (tests: the path really ran) */
 
 /* ------------------------------------------------------------------------------------------
  * Particles  (replaces PhysicalParticleContainer::PushPX / PushP and

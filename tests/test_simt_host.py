@@ -247,3 +247,42 @@ def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind)
         hl.pic_set_deposit_mode(0)
     for c in range(3):
         assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the FDTD kernels on the host: plain loads (fdtd.cu) and the bulk-asynchronous staging of fdtd_bulk.cu (the emulator
+# performs the bulk copies synchronously: ring indexing, row / plane clamps, alignment widening, tail element)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("algo", [abi.SOLVER_YEE, abi.SOLVER_CKC])
+@pytest.mark.parametrize("n,ng", [((16, 12, 10), (2, 2, 2)), ((70, 9, 37), (1, 2, 1)), ((7, 6, 5), (4, 4, 4))])
+def test_fdtd_kernels_under_simt_emulation(orc, mode, algo, n, ng):
+    from host_harness import harness
+    from helpers import random_fields
+    hl = harness.host_library()
+    L = orc.lib()
+    box_lo, box_hi = (0, 0, 0), tuple(v - 1 for v in n)
+    dx = [1e-6, 1.5e-6, 0.8e-6]
+    st = abi.pic_stencil()
+    L.orc_stencil_coefs(algo, (C.c_double * 3)(*dx), C.byref(st))
+    scale = [1e9] * 3 + [3.0] * 3 + [1e12] * 3
+    F = random_fields(orc, box_lo, box_hi, ng, 11, comps=range(9), scale=scale)
+    G = random_fields(orc, box_lo, box_hi, ng, 11, comps=range(9), scale=scale)
+    dt = 1.1e-15
+    hl.pic_set_fdtd_mode(mode)
+    before = hl.pic_fdtd_bulk_launches()
+    try:
+        E, B, J = orc.fab_array(G[0:3]), orc.fab_array(G[3:6]), orc.fab_array(G[6:9])
+        assert hl.pic_evolve_b(B, E, C.byref(st), 0.5 * dt, None) == 0, hl.pic_last_error()
+        assert hl.pic_evolve_e(E, B, J, C.byref(st), dt, None) == 0, hl.pic_last_error()
+        assert hl.pic_evolve_b(B, E, C.byref(st), 0.5 * dt, None) == 0, hl.pic_last_error()
+    finally:
+        hl.pic_set_fdtd_mode(1)
+    # EvolveE is staged for both solvers, EvolveB for Yee (numpy arrays are 16-byte aligned)
+    assert hl.pic_fdtd_bulk_launches() - before == (0 if mode == 0 else (3 if algo == abi.SOLVER_YEE else 1))
+    Eo, Bo, Jo = orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), orc.fab_array(F[6:9])
+    L.orc_evolve_b(Bo, Eo, C.byref(st), 0.5 * dt)
+    L.orc_evolve_e(Eo, Bo, Jo, C.byref(st), dt)
+    L.orc_evolve_b(Bo, Eo, C.byref(st), 0.5 * dt)
+    for c in range(6):
+        assert rel_linf(G[c].a, F[c].a) <= 1e-13, abi.COMP_NAMES[c]

@@ -624,13 +624,15 @@ static int launch_general(SoaView P, const int* list, const int* list_count, con
         cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
         attr_done = true;
     }
-    const int nblk = NUM_SMS;
-#else
-    const int nblk = 4;
-#endif
-    kg<<<nblk, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
+    kg<<<NUM_SMS, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
     count_launch();
     return check_launch("pic_deposit_esirkepov(general)") ? 0 : 1;
+#else       // tests/host_harness (this file is also compiled untransformed): the emulator's launch
+    (void)s; (void)kg;
+    const FabView v0 = make_view(J[0]), v1 = make_view(J[1]), v2 = make_view(J[2]);
+    ::simt::launch(dim3(4), dim3(NWG * 32), smem_g, [&] { deposit_general_kernel<N, NWG>(P, list, list_count, v0, v1, v2, dg, kb); });
+    return 0;
+#endif
 }
 int deposit_general_launch(SoaView P, const int* list, const int* list_count, const pic_fab J[3], const DepositGeom& dg,
                            int nox, cudaStream_t s) {

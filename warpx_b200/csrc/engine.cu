@@ -659,6 +659,22 @@ using namespace pic;
 static int alloc_boundary_scratch(long capacity, int** work, int* cap);
 static int grow_host_counts(Engine& e);
 
+// Defaults of the kernel-variant switches from the environment (PIC_FDTD_MODE, PIC_DEPOSIT_MODE, PIC_GATHER_MODE):
+// lets a launcher pin a variant without touching the host code.  Applied once, when the library is loaded.
+extern "C" void pic_set_fdtd_mode(int mode);
+extern "C" void pic_set_deposit_mode(int mode);
+extern "C" void pic_set_gather_mode(int mode);
+namespace {
+struct EnvDefaults {
+    EnvDefaults() {
+        if (const char* v = getenv("PIC_FDTD_MODE")) pic_set_fdtd_mode(atoi(v));
+        if (const char* v = getenv("PIC_DEPOSIT_MODE")) pic_set_deposit_mode(atoi(v));
+        if (const char* v = getenv("PIC_GATHER_MODE")) pic_set_gather_mode(atoi(v));
+    }
+};
+}  // namespace
+extern "C" void pic_apply_env_defaults(void) { static EnvDefaults once; (void)once; }
+
 extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], const int box_hi[3], int nox,
                                    int galerkin, int pusher, int solver, double cfl, double dt,
                                    int sort_interval, int use_filter, const int filter_npass[3]) {

@@ -137,6 +137,12 @@ static int check_guards(const pic_fab B[3], const pic_fab E[3], const pic_stenci
     return 0;
 }
 
+// fdtd_bulk.cu: the Yee kernels with bulk-asynchronous staging (done = false: not applicable, take the kernels here)
+int evolve_b_bulk_launch(const pic_fab B[3], const pic_fab E[3], const pic_stencil* st, const int lo[3], const int n[3],
+                         double dt, cudaStream_t s, bool* done);
+int evolve_e_bulk_launch(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3], const pic_stencil* st, const int lo[3],
+                         const int n[3], double dt, cudaStream_t s, bool* done);
+
 }  // namespace pic
 
 using namespace pic;
@@ -150,6 +156,11 @@ extern "C" int pic_evolve_b(const pic_fab B[3], const pic_fab E[3], const pic_st
     dim3 block(FDTD_BX, FDTD_BY, 1);
     dim3 grid((pb.n[0] + FDTD_BX - 1) / FDTD_BX, (pb.n[1] + FDTD_BY - 1) / FDTD_BY, pb.n[2]);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        bool done = false;
+        if (int rc = evolve_b_bulk_launch(B, E, st, pb.lo, pb.n, dt, s, &done)) return rc;
+        if (done) return 0;
+    }
     if (st->algo == PIC_SOLVER_YEE)
         evolve_b_kernel<PIC_SOLVER_YEE><<<grid, block, 0, s>>>(make_view(B[0]), make_view(B[1]), make_view(B[2]),
             make_view(E[0]), make_view(E[1]), make_view(E[2]), cf, pb, dt);
@@ -171,6 +182,11 @@ extern "C" int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fa
     for (int n = 0; n < 5; ++n) { cf.x[n] = st->cx[n]; cf.y[n] = st->cy[n]; cf.z[n] = st->cz[n]; }
     dim3 block(FDTD_BX, FDTD_BY, 1);
     dim3 grid((pb.n[0] + FDTD_BX - 1) / FDTD_BX, (pb.n[1] + FDTD_BY - 1) / FDTD_BY, pb.n[2]);
+    {
+        bool done = false;
+        if (int rc = evolve_e_bulk_launch(E, B, J, st, pb.lo, pb.n, dt, (cudaStream_t)stream, &done)) return rc;
+        if (done) return 0;
+    }
     evolve_e_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(make_view(E[0]), make_view(E[1]), make_view(E[2]),
         make_view(B[0]), make_view(B[1]), make_view(B[2]), make_view(J[0]), make_view(J[1]), make_view(J[2]),
         cf, pb, dt);

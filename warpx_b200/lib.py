@@ -30,6 +30,7 @@ def lib():
             finally:
                 fcntl.flock(lock, fcntl.LOCK_UN)
     _LIB = bind(C.CDLL(path))
+    _LIB.pic_apply_env_defaults()
     return _LIB
 
 
@@ -46,9 +47,12 @@ def bind(L):
         "pic_set_error_mode": (None, [C.c_int]),
         "pic_last_error": (C.c_char_p, []),
         "pic_version": (C.c_char_p, []),
+        "pic_apply_env_defaults": (None, []),
         "pic_launch_count": (C.c_long, []),
         "pic_set_deposit_mode": (None, [C.c_int]),
         "pic_set_gather_mode": (None, [C.c_int]),
+        "pic_set_fdtd_mode": (None, [C.c_int]),
+        "pic_fdtd_bulk_launches": (C.c_long, []),
         "pic_evolve_b": (C.c_int, [fabp, fabp, stp, C.c_double, vp]),
         "pic_evolve_e": (C.c_int, [fabp, fabp, fabp, stp, C.c_double, vp]),
         "pic_gather_push": (C.c_int, [soap, C.c_long, C.c_long, fabp, fabp, dp, dp, ip, C.c_double,
