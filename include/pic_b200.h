@@ -492,6 +492,7 @@ int pic_engine_set_injector(void* engine, int isp, const pic_plasma_injector* in
 int pic_engine_add_laser(void* engine, const pic_laser_antenna* prm, const pic_soa* p, long capacity);
 long pic_engine_laser_np(void* engine, int ilaser);
 double pic_engine_time(void* engine);
+int pic_engine_set_step(void* engine, long istep, double time);   /* restart: WarpX::InitFromCheckpoint, Diagnostics/WarpXIO.cpp */
 void pic_engine_prob_domain(void* engine, double out[6]);
 int pic_engine_add_species(void* engine, double q, double m, const pic_soa* bufA, const pic_soa* bufB,
                            long capacity, int* cell_start, const int tile[3], void* sort_work, void* stream);

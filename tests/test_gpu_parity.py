@@ -447,6 +447,31 @@ def test_langmuir_loop_golden_and_oracle(orc, cuda, golden, use_bins):
     assert b == pytest.approx(bo, rel=1e-7)     # B is at round-off level in this electrostatic mode
 
 
+def test_plotfile_golden_checksums(orc, cuda, golden, tmp_path):
+    """The reference's own regression loop, closed through files: config 1 for 40 steps on the GPU, dumped with
+    warpx_b200.diagnostics.write_plotfile in the layout of `diag.format = plotfile`, read back the way
+    Regression/Checksum/checksum.py reads a plotfile (tests/plotfile_reader.py stands in for yt), compared with every
+    key of test_3d_langmuir_multi.json at WarpX's rtol 1e-9 (rho and part_per_cell are separate diagnostics functors)."""
+    from warpx_b200 import diagnostics
+    from warpx_b200.engine import Simulation
+    import plotfile_reader
+    wl = workloads.langmuir_3d()
+    sim = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=1, sort_interval=4)
+    for s in wl["species"]:
+        sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.Evolve(40)
+    cuda.cuda.synchronize()
+    root = diagnostics.write_plotfile(sim, str(tmp_path / "diags" / "plt"))
+    got = plotfile_reader.checksums(root, species=("electrons", "positrons"))
+    g = golden["test_3d_langmuir_multi"]
+    for name in abi.COMP_NAMES:
+        assert abs(got["lev=0"][name] - g["lev=0"][name]) <= 1e-9 * abs(g["lev=0"][name]), name
+    for sname in ("electrons", "positrons"):
+        for key, gv in g[sname].items():
+            assert abs(got[sname][key] - gv) <= 1e-9 * abs(gv), (sname, key)
+    sim.close()
+
+
 @pytest.mark.parametrize("solver,pusher,native", [(abi.SOLVER_YEE, abi.PUSHER_BORIS, True),
                                                   (abi.SOLVER_YEE, abi.PUSHER_BORIS, False),
                                                   (abi.SOLVER_CKC, abi.PUSHER_VAY, True)])

@@ -125,3 +125,65 @@ def test_boosted_deck_with_every_feature_on_the_host_matches_oracle(orc, HostSim
     assert len(LA["x"]) == len(LB["x"]) > 0
     for k in ("x", "y", "z"):
         assert np.max(np.abs(LA[k] - LB[k])) / dx[2] <= 1e-10, k
+
+
+def test_plotfile_of_a_host_run_reproduces_the_oracle_checksums(orc, HostSimulation, tmp_path):
+    """warpx_b200.diagnostics.write_plotfile (the reference's `diag.format = plotfile` layout) read back with
+    tests/plotfile_reader.py: the per-field / per-species sums the reference's checksum.py forms from a plotfile equal
+    the oracle's own (cell-centred averages of ablastr/coarsen/sample.H, momenta in SI units)."""
+    from warpx_b200 import diagnostics
+    import plotfile_reader
+    wl = workloads.langmuir_3d(n=8)
+    sim = HostSimulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=1, sort_interval=4)
+    osim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=1)
+    for s in wl["species"]:
+        sim.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+        osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    sim.Evolve(5)
+    osim.evolve(5)
+    root = diagnostics.write_plotfile(sim, str(tmp_path / "plt"))
+    assert root.endswith("plt00005")
+    got = plotfile_reader.checksums(root, species=("electrons", "positrons"))
+    for c, name in enumerate(abi.COMP_NAMES):
+        want = osim.checksum_field(c)
+        tol = 1e-9 if c not in (3, 4, 5) else 1e-2         # B is round-off noise in this electrostatic mode
+        assert abs(got["lev=0"][name] - want) <= tol * abs(want) + 1e-30, name
+    for isp, sname in enumerate(("electrons", "positrons")):
+        P = osim.particles(isp)
+        assert got[sname]["particle_position_x"] == pytest.approx(float(np.sum(np.abs(P["x"]))), rel=1e-12)
+        assert got[sname]["particle_momentum_z"] == pytest.approx(float(np.sum(np.abs(P["uz"]))) * workloads.M_E, rel=1e-9)
+        assert got[sname]["particle_weight"] == pytest.approx(float(np.sum(P["w"])), rel=1e-12)
+    _, hdr = plotfile_reader.read_fields(root)
+    assert hdr["step"] == 5 and hdr["n_cell"] == [8, 8, 8] and hdr["names"] == list(abi.COMP_NAMES)
+
+
+def test_checkpoint_restart_on_the_host_continues_the_run(orc, HostSimulation, tmp_path):
+    """FlushFormatCheckpoint / InitFromCheckpoint in the small: 6 steps, checkpoint, restart in a new Simulation, 4 more
+    steps == 10 steps in one go (the summation order of the deposition differs after the restart's sort: 1e-12)."""
+    from warpx_b200 import diagnostics
+    wl = workloads.uniform_plasma_3d(n=16, ppc=(1, 1, 2), u_th=0.05, lx=2.5e-6, perturbation=0.01)
+
+    def fresh():
+        return HostSimulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, sort_interval=4)
+    s = wl["species"][0]
+    ref = fresh()
+    ref.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    ref.Evolve(6)
+    ref.Evolve(4)
+    a = fresh()
+    a.add_species(s["name"], s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    a.Evolve(6)
+    root = diagnostics.write_checkpoint(a, str(tmp_path / "chk"))
+    b = fresh()
+    assert diagnostics.read_checkpoint(b, root) == 6
+    b.Evolve(4)
+    assert b.istep == ref.istep == 10 and b.time == pytest.approx(ref.time, rel=1e-14)
+    for c in range(9):
+        _, x = ref.field_numpy(c)
+        _, y = b.field_numpy(c)
+        assert np.max(np.abs(x - y)) <= 1e-11 * max(np.max(np.abs(x)), 1e-300), abi.COMP_NAMES[c]
+    A, B = ref.species_numpy(0, sort_by_id=True), b.species_numpy(0, sort_by_id=True)
+    assert np.array_equal(A["id"], B["id"])
+    for k in ("x", "y", "z", "ux", "uy", "uz"):
+        scale = ref.dx[0] if k in "xyz" else workloads.C
+        assert np.max(np.abs(A[k] - B[k])) / scale <= 1e-11, k

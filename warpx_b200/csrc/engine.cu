@@ -986,6 +986,13 @@ extern "C" int pic_engine_add_laser(void* h, const pic_laser_antenna* prm, const
 }
 extern "C" long pic_engine_laser_np(void* h, int il) { return (long)static_cast<Engine*>(h)->lasers[il].P.np; }
 extern "C" double pic_engine_time(void* h) { return static_cast<Engine*>(h)->cur_time; }
+// restart from a checkpoint: istep / t_new (WarpX::InitFromCheckpoint, Source/Diagnostics/WarpXIO.cpp:118-140)
+extern "C" int pic_engine_set_step(void* h, long istep, double time) {
+    Engine* e = static_cast<Engine*>(h);
+    PIC_REQUIRE(istep >= 0, "pic_engine_set_step: negative step");
+    e->istep = istep; e->cur_time = time;
+    return 0;
+}
 extern "C" void pic_engine_prob_domain(void* h, double out[6]) {
     Engine* e = static_cast<Engine*>(h);
     for (int d = 0; d < 3; ++d) { out[d] = e->geom.prob_lo[d]; out[3 + d] = e->geom.prob_hi[d]; }

@@ -43,9 +43,11 @@ __device__ __forceinline__ void fb_bulk(double* dst, const double* src, unsigned
 }
 __device__ __forceinline__ void fb_wait(unsigned long long* bar, unsigned parity) {
     unsigned done = 0;
-    while (!done) {
+    // bounded: a copy that never completes (a bug) must end the kernel with an error, not hang the device
+    for (unsigned spins = 0; !done; ++spins) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(fb_smem(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
     }
 }
 #endif

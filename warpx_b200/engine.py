@@ -195,7 +195,7 @@ class _DeviceOps:
 class Species:
     NAMES = ("x", "y", "z", "w", "ux", "uy", "uz")
 
-    def __init__(self, sim, name, q, m, arrays, capacity):
+    def __init__(self, sim, name, q, m, arrays, capacity, ids=None):
         t = sim.torch
         self.sim, self.name, self.q, self.m = weakref.proxy(sim), name, q, m
         self.np = len(arrays["x"])
@@ -204,7 +204,10 @@ class Species:
         self.buf = [t.empty((7, self.capacity), dtype=t.float64, device=sim.device) for _ in range(2)]
         # 64-bit particle id (the reference's idcpu): rank in the upper bits, local index below
         self.ids = [t.empty(self.capacity, dtype=t.int64, device=sim.device) for _ in range(2)]
-        self.ids[0][:self.np] = t.arange(self.np, dtype=t.int64, device=sim.device) + (sim.rank << 40)
+        if ids is None:
+            self.ids[0][:self.np] = t.arange(self.np, dtype=t.int64, device=sim.device) + (sim.rank << 40)
+        else:               # restart: the ids a checkpoint carries
+            self.ids[0][:self.np].copy_(t.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)))
         self.cur = 0
         for n, name_ in enumerate(self.NAMES):
             a = arrays[name_]
@@ -406,13 +409,14 @@ class Simulation:
     def stream(self):
         return self.torch.cuda.current_stream().cuda_stream
 
-    def add_species(self, name, q, m, x, y, z, w, ux, uy, uz, capacity_factor=None):
-        """Particles must lie inside this rank's box (use workloads.* with box_lo/box_hi)."""
+    def add_species(self, name, q, m, x, y, z, w, ux, uy, uz, capacity_factor=None, ids=None):
+        """Particles must lie inside this rank's box (use workloads.* with box_lo/box_hi).  ids: 64-bit particle ids
+        (default: rank << 40 | index)."""
         if capacity_factor is None:
             capacity_factor = 1.0 if self.world == 1 else 1.25
         arrays = dict(x=x, y=y, z=z, w=w, ux=ux, uy=uy, uz=uz)
         cap = int(len(x) * capacity_factor) + (0 if self.world == 1 else 65536)
-        sp = Species(self, name, q, m, arrays, cap)
+        sp = Species(self, name, q, m, arrays, cap, ids=ids)
         self.species.append(sp)
         if self.native:
             self._alloc_sort_scratch(sp)
@@ -727,6 +731,12 @@ class Simulation:
             step = self.istep
             self.istep += 1
             self.HandleParticlesAtBoundaries(step)
+
+    def set_step(self, istep, time):
+        """Restart: continue counting steps (cell-sort cadence) and time from a checkpoint."""
+        self.istep, self.time = int(istep), float(time)
+        if self.native:
+            check(self.L.pic_engine_set_step(self.native, int(istep), float(time)))
 
     # ---- diagnostics -------------------------------------------------------------------
     def field_energy(self):

@@ -108,6 +108,7 @@ def bind(L):
         "pic_engine_add_laser": (C.c_int, [vp, lasp, soap, C.c_long]),
         "pic_engine_laser_np": (C.c_long, [vp, C.c_int]),
         "pic_engine_time": (C.c_double, [vp]),
+        "pic_engine_set_step": (C.c_int, [vp, C.c_long, C.c_double]),
         "pic_engine_prob_domain": (None, [vp, dp]),
     }
     sig.update(abi.LWFA_SIGNATURES(fabp, soap, gp, bndp, lasp, injp, dp, ip, vp))
