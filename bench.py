@@ -431,7 +431,7 @@ def main():
                     help="pic_set_deposit_mode: 0 register runs, 1 shared-memory tile block, 2 two lines per "
                          "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions, "
                          "7 one lane per cell (every mode passes the parity tests)")
-    ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 1, 2, 3],
                     help="pic_set_gather_mode: 0 one particle per lane (default), 1 two particles of a cell per lane, "
                          "2 the same without the 128-register cap (A/B measurement; same parity tests)")
     args = ap.parse_args()

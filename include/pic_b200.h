@@ -206,7 +206,8 @@ int pic_gather_push(const pic_soa* p, long offset, long np,
  * with the Galerkin gather on the Yee grid -- other configurations keep the default kernel.  Same results
  * (each particle's own accumulation order is unchanged).  PIC_GATHER_PAIRS_WIDE: the same kernel without the
  * 128-register cap (254 registers, one CTA per SM).  Experiments until measured. */
-enum { PIC_GATHER_TILE = 0, PIC_GATHER_PAIRS = 1, PIC_GATHER_PAIRS_WIDE = 2 };
+enum { PIC_GATHER_TILE = 0, PIC_GATHER_PAIRS = 1, PIC_GATHER_PAIRS_WIDE = 2,
+       PIC_GATHER_PAIRS_192 = 3 /* the pair kernel with 192 threads per CTA: 168 registers, no spills, 12 warps per SM */ };
 void pic_set_gather_mode(int mode);
 
 /* WarpXParticleContainer::DepositCurrent (WarpXParticleContainer.cpp:352-827) ->

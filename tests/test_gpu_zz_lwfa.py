@@ -727,7 +727,7 @@ def test_deposit_variants_match_oracle(orc, dev, mode, nox, kind):
         assert rel_linf(tens[c].cpu().numpy(), J[c].a) <= 1e-12, "j" + "xyz"[c]
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("nox,kind", [(3, "sorted"), (3, "drifted"), (1, "drifted"), (2, "sorted")])
 def test_gather_variants_match_oracle(orc, dev, mode, nox, kind):
     """pic_set_gather_mode(PIC_GATHER_PAIRS / _WIDE): two particles of a cell per lane, against the oracle's gather +

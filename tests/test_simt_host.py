@@ -78,7 +78,7 @@ def host_bins(x, y, z, prob_lo, dx, n, tile):
     return order, cell_start
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("nox,galerkin,tile,kind", [(3, 1, (8, 8, 8), "sorted"), (3, 1, (8, 8, 8), "moved"),
                                                     (3, 1, (4, 4, 4), "moved"), (1, 1, (8, 8, 8), "moved"),
                                                     (2, 1, (4, 4, 4), "sorted"), (3, 0, (4, 4, 4), "sorted"),
@@ -88,8 +88,8 @@ def test_gather_push_tile_kernels_under_simt_emulation(orc, simt, mode, nox, gal
     against the oracle's gather + push: cell-sorted particles, particles that moved up to 0.9 cell since the sort
     (stray lists, lone survivors of a pair), cells with odd counts, the fixed 8x8x8 and the run-time supercell.
     Orders / gathers whose stencils do not coincide inside a cell fall back to the default kernel in modes 1, 2."""
-    if mode == 2 and kind != "sorted":
-        pytest.skip("the wide instance differs only in its register cap")
+    if mode in (2, 3) and kind not in ("sorted", "odd"):
+        pytest.skip("the wide / 192-thread instances differ only in their launch shape")
     n = (16, 8, 8) if tile == (8, 8, 8) else (8, 8, 4)
     lx = tuple(0.5e-6 * v for v in n)
     wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(2, 1, 2) if kind != "odd" else (1, 1, 1), u_th=0.1, lx=lx, seed=11)

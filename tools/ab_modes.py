@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--u-th", type=float, default=0.01)
     ap.add_argument("--jitter", action="store_true", help="random in-cell positions (the steady state of the lattice)")
     ap.add_argument("--deposit-modes", default="0,7,2,5,6")
-    ap.add_argument("--gather-modes", default="0,1,2")
+    ap.add_argument("--gather-modes", default="0,1,2,3")
     args = ap.parse_args()
     import torch
     from warpx_b200 import workloads

@@ -42,7 +42,7 @@ int gather_push_tile_launch(const pic_soa* p, long offset, long np, const pic_fa
 }
 
 namespace pic { extern int g_gather_mode; }      // gather_push_tile.cu
-extern "C" void pic_set_gather_mode(int mode) { pic::g_gather_mode = (mode == PIC_GATHER_PAIRS) ? 1 : (mode == PIC_GATHER_PAIRS_WIDE) ? 2 : 0; }
+extern "C" void pic_set_gather_mode(int mode) { pic::g_gather_mode = (mode >= PIC_GATHER_PAIRS && mode <= PIC_GATHER_PAIRS_192) ? mode : 0; }
 
 extern "C" int pic_gather_push(const pic_soa* p, long offset, long np, const pic_fab E[3],
                                const pic_fab B[3], const double dinv[3], const double xyzmin[3],

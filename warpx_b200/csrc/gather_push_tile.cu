@@ -175,12 +175,12 @@ gather_push_tile_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
 // ---- two particles of one cell per lane ---------------------------------------------------------
 // Shared memory: [6][BD2][BD1][BD0] doubles of fields | pair_start[tvol + 1] | s_stray[GT_LOCAL_STRAYS] | s_nstray.
 // pair_start[c] = number of lane-pairs in the cells before c of this supercell (ceil(n_c / 2) each).
-// MINB = 2: 128 registers (80 B of spill traffic at order 3), 16 warps per SM like the default kernel;
-// MINB = 1: 254 registers, no spills, 8 warps per SM.
+// MINB = 2: 128 registers (116 B of spill traffic at order 3), 16 warps per SM like the default kernel;
+// MINB = 1: 254 registers, no spills, 8 warps per SM; 192 threads with MINB = 2: 168 registers, no spills, 12 warps.
 constexpr int GP_THREADS = 256;
 
-template <int N, int G, bool YEE, int TX, int TY, int TZ, int MINB>
-__global__ void __launch_bounds__(GP_THREADS, MINB)
+template <int N, int G, bool YEE, int TX, int TY, int TZ, int MINB, int NT = GP_THREADS>
+__global__ void __launch_bounds__(NT, MINB)
 gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg, double qdt2m,
                         double dt, int pusher, int push_position, EscapeView esc, StrayList stray) {
     PIC_DYNAMIC_SMEM(double, smem);
@@ -207,7 +207,7 @@ gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     int* s_stray = pair_start + tvol + 1;
     int& s_nstray = s_stray[GT_LOCAL_STRAYS];
 
-    for (int n = threadIdx.x; n < 6 * bvol; n += GP_THREADS) {          // staging as in gather_push_tile_kernel
+    for (int n = threadIdx.x; n < 6 * bvol; n += NT) {          // staging as in gather_push_tile_kernel
         const int c = n / bvol, r = n - c * bvol;
         const int li = r % BD0, lj = (r / BD0) % BD1, lk = r / (BD0 * BD1);
         const FabView& F = gf.v[c];
@@ -220,7 +220,7 @@ gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     cp_async_commit();
 
     // pairs per cell, then an exclusive scan by warp 0 (each lane sums a chunk, shuffle scan across lanes)
-    for (int c = threadIdx.x; c < tvol; c += GP_THREADS) {
+    for (int c = threadIdx.x; c < tvol; c += NT) {
         const int n_c = min(cs[c + 1], bins.np_limit) - min(cs[c], bins.np_limit);
         pair_start[c + 1] = (n_c + 1) >> 1;
     }
@@ -273,7 +273,7 @@ gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
         if (push_position) { P.x[ipp] = xp; P.y[ipp] = yp; P.z[ipp] = zp; esc.note(ipp, xp, yp, zp); }
     };
 
-    for (int p = threadIdx.x; p < npairs; p += GP_THREADS) {
+    for (int p = threadIdx.x; p < npairs; p += NT) {
         // cell of pair p: the last c with pair_start[c] <= p
         int lo = 0, hi = tvol;                       // invariant: pair_start[lo] <= p < pair_start[hi]
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pair_start[mid] <= p) lo = mid; else hi = mid; }
@@ -332,7 +332,7 @@ gather_push_pair_kernel(SoaView P, BinsView bins, GlobalFields gf, GatherGeom gg
     }
     __syncthreads();
     const int nloc = min(s_nstray, GT_LOCAL_STRAYS);
-    for (int t2l = threadIdx.x; t2l < nloc; t2l += GP_THREADS) single(s_stray[t2l], true);
+    for (int t2l = threadIdx.x; t2l < nloc; t2l += NT) single(s_stray[t2l], true);
 }
 
 // the listed strays, one thread each, fields through the read-only global path
@@ -365,7 +365,7 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
     const long bvol = (long)(bv.tile[0] + 2 * GT_HALO) * (bv.tile[1] + 2 * GT_HALO) * (bv.tile[2] + 2 * GT_HALO);
     const long tvol = (long)bv.tile[0] * bv.tile[1] * bv.tile[2];
     const bool pairs = g_gather_mode != 0 && yee && G == 1 && (N == 3 || N == 1);
-    const bool wide = g_gather_mode == 2;
+    const bool wide = g_gather_mode == 2, mid = g_gather_mode == 3;
     const size_t smem = (size_t)6 * bvol * sizeof(double) + (pairs ? sizeof(int) * (size_t)(tvol + 1 + GT_LOCAL_STRAYS + 1) : 0);
     const size_t static_smem = pairs ? 0 : sizeof(int) * (GT_LOCAL_STRAYS + 2);       // s_stray + s_nstray
     if (smem + static_smem > 227 * 1024) return fail("pic_gather_push: supercell too large for shared memory (%zu B)", smem);
@@ -388,6 +388,7 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
     if (pairs) {
         if constexpr (G == 1 && (N == 3 || N == 1)) {
             if (t888 && wide) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 1);
+            else if (t888 && mid) PIC_LAUNCH_K(gather_push_pair_kernel, 192, true, 8, 8, 8, 2, 192);
             else if (t888) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 2);
             else PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 0, 0, 0, 2);
         }
@@ -410,6 +411,7 @@ static int launch(SoaView P, const BinsView& bv, const GlobalFields& gf, const G
     if (pairs) {
         if constexpr (G == 1 && (N == 3 || N == 1)) {
             if (t888 && wide) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 1);
+            else if (t888 && mid) PIC_LAUNCH_K(gather_push_pair_kernel, 192, true, 8, 8, 8, 2, 192);
             else if (t888) PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 8, 8, 8, 2);
             else PIC_LAUNCH_K(gather_push_pair_kernel, GP_THREADS, true, 0, 0, 0, 2);
         }
