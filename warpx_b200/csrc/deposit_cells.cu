@@ -104,8 +104,8 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
             int sh[3];      // i_old - i_new
             bool inside;    // every sub-particle is anchored at a cell of this supercell
         };
-        auto compute = [&](long ip, Part& q) {
-            const ParticleGeom pg = particle_geom(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip], dg);
+        auto compute = [&](const double* v7, Part& q) {      // v7 = x y z w ux uy uz of the particle
+            const ParticleGeom pg = particle_geom(v7[0], v7[1], v7[2], v7[3], v7[4], v7[5], v7[6], dg);
             q.wq = pg.wq;
             bool in = true;
 #pragma unroll
@@ -156,6 +156,32 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                 for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[d][2 * m], cds[d][2 * m + 1]);
             *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(active, base);
         };
+        // the record of a particle that is quiet in the lane's own cell (no shifts): the hot path, no selects
+        auto emit_simple = [&](const Part& q, double2* r) {
+#pragma unroll
+            for (int s = 0; s < QS; ++s) {
+                r[(T::F_SX + s) * 32] = make_double2(q.wn[0][s], q.wo[0][s]);
+                r[(T::F_SY + s) * 32] = make_double2(q.wn[1][s], q.wo[1][s]);
+                r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * q.wn[1][s] + (1.0 / 6.0) * q.wo[1][s],
+                                                      (1.0 / 3.0) * q.wo[1][s] + (1.0 / 6.0) * q.wn[1][s]);
+                r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * q.wn[2][s] + (1.0 / 6.0) * q.wo[2][s],
+                                                      (1.0 / 3.0) * q.wo[2][s] + (1.0 / 6.0) * q.wn[2][s]);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double wqd = q.wq * dg.invdtd[d];
+                double cds[2 * NCP];
+                cds[2 * NCP - 1] = 0.0;
+                double run = 0.0;
+#pragma unroll
+                for (int i = 0; i < QP; ++i) {
+                    run += wqd * (q.wo[d][i] - q.wn[d][i]);
+                    cds[i] = run;
+                }
+#pragma unroll
+                for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[2 * m], cds[2 * m + 1]);
+            }
+        };
         auto emit_nothing = [&](double2* r) {    // zero prefix sums: the weights left in the record are finite
 #pragma unroll
             for (int m = 0; m < 3 * NCP; ++m) r[(T::F_CDS + m) * 32] = make_double2(0.0, 0.0);
@@ -195,6 +221,7 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
 #endif
         };
         prefetch_group(0);
+        double pf[7] = {0, 0, 0, 0, 0, 0, 0};
         int it = 0;
         // ---------------- the groups: slice s = the s-th particle of each of the 32 cells ----------------
         for (int g = 0; g < 16; ++g) {
@@ -211,39 +238,42 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                 double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
                 const bool valid = s < n;
                 const long ip = (long)p0 + s;
+                // this particle was requested during the previous slice (registers); the first of a cell is loaded here
+                double v7[7];
+                if (s == 0) {
+                    if (valid) { v7[0] = P.x[ip]; v7[1] = P.y[ip]; v7[2] = P.z[ip]; v7[3] = P.w[ip]; v7[4] = P.ux[ip]; v7[5] = P.uy[ip]; v7[6] = P.uz[ip]; }
+                    else { v7[0] = v7[1] = v7[2] = v7[3] = v7[4] = v7[5] = v7[6] = 0.0; }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) v7[c] = pf[c];
+                }
+                if (s + 1 < n) {
+                    pf[0] = P.x[ip + 1]; pf[1] = P.y[ip + 1]; pf[2] = P.z[ip + 1]; pf[3] = P.w[ip + 1];
+                    pf[4] = P.ux[ip + 1]; pf[5] = P.uy[ip + 1]; pf[6] = P.uz[ip + 1];
+                }
                 bool listed = false, sent = false;
                 if (valid) {
                     Part q;
-                    compute(ip, q);
-                    if (!q.inside) listed = true;
+                    compute(v7, q);
+                    // hot path: quiet in the lane's own cell.  Everything else -- every sub-particle of it -- waits
+                    // in the queue for the extra rounds (or goes to the list when it reaches outside the supercell).
+                    const bool simple = q.inside && (q.sh[0] | q.sh[1] | q.sh[2]) == 0 && q.t[0] == lc[0] && q.t[1] == lc[1] && q.t[2] == lc[2];
+                    if (simple) { emit_simple(q, r); sent = true; }
+                    else if (!q.inside) listed = true;
                     else {
-                        int vreg[3];
-                        bool has_reg = true;
-                        int nvirt = 1;
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            vreg[d] = lc[d] - q.t[d];
-                            has_reg = has_reg && (vreg[d] == 0 || (vreg[d] == 1 && q.sh[d] != 0));
-                            nvirt *= q.sh[d] ? 2 : 1;
-                        }
-                        const int nq = nvirt - (has_reg ? 1 : 0);
-                        bool room = true;
-                        if (nq > 0) {
-                            int slot = atomicAdd(q_count, nq);
-                            room = slot + nq <= T::QCAP;
-                            if (!room) atomicMin(q_count + 1, slot);      // later requests start beyond: they do not fit either
-                            if (room) {
+                        const int nq = (q.sh[0] ? 2 : 1) * (q.sh[1] ? 2 : 1) * (q.sh[2] ? 2 : 1);
+                        int slot = atomicAdd(q_count, nq);
+                        if (slot + nq > T::QCAP) {           // queue full: the whole particle goes to the list
+                            atomicMin(q_count + 1, slot);    // later requests start beyond: they do not fit either
+                            listed = true;
+                        } else {
 #pragma unroll 1
-                                for (int v = 0; v < 8; ++v) {
-                                    const int vx = v & 1, vy = (v >> 1) & 1, vz = v >> 2;
-                                    if ((vx && !q.sh[0]) || (vy && !q.sh[1]) || (vz && !q.sh[2])) continue;
-                                    if (has_reg && vx == vreg[0] && vy == vreg[1] && vz == vreg[2]) continue;
-                                    queue[slot++] = make_int2((int)ip, v | ((q.t[0] + vx) << 3) | ((q.t[1] + vy) << 6) | ((q.t[2] + vz) << 9));
-                                }
+                            for (int v = 0; v < 8; ++v) {
+                                const int vx = v & 1, vy = (v >> 1) & 1, vz = v >> 2;
+                                if ((vx && !q.sh[0]) || (vy && !q.sh[1]) || (vz && !q.sh[2])) continue;
+                                queue[slot++] = make_int2((int)ip, v | ((q.t[0] + vx) << 3) | ((q.t[1] + vy) << 6) | ((q.t[2] + vz) << 9));
                             }
                         }
-                        if (!room) listed = true;           // queue full: the whole particle goes to the list
-                        else if (has_reg) { emit(q, vreg, r, 1, 0); sent = true; }
                     }
                 }
                 if (!sent) emit_nothing(r);
@@ -266,7 +296,9 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                 double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
                 if (go) {
                     Part q;
-                    compute(e.x, q);
+                    const long ip = e.x;
+                    const double v7[7] = {P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip]};
+                    compute(v7, q);
                     const int v[3] = {e.y & 1, (e.y >> 1) & 1, (e.y >> 2) & 1};
                     const int ax = (e.y >> 3) & 7, ay = (e.y >> 6) & 7, az = (e.y >> 9) & 7;
                     emit(q, v, r, 1, ax + PX * (ay + PY * az));

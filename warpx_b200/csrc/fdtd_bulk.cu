@@ -19,6 +19,7 @@ struct BulkBox { int lo[3]; int n[3]; };   // points visited: cells + the upper 
 
 constexpr int FB_SLOTS = 3;
 constexpr int FB_TX = 64, FB_TY = 4;       // 256 threads: 64 lanes along x, 4 rows
+constexpr int FB_IT = 5;                   // points of a row per thread: rows up to FB_TX * FB_IT = 320 points
 
 #ifdef PIC_SIMT_HOST      // tests/host_harness: the emulator copies synchronously, barriers are always complete
 __device__ __forceinline__ void fb_mbar_init(unsigned long long*, int) {}
@@ -151,18 +152,30 @@ evolve_b_bulk_kernel(FabView Bx, FabView By, FabView Bz, BulkSrc Ex, BulkSrc Ey,
         const double* ey1 = e1 + chunk + shifts[s1 * 3 + 1] + ty * Ey.F.sj;
         const int k = pb.lo[2] + lk, j = pb.lo[1] + lj;
         if (row_ok) {
-            for (int li = tx; li < pb.n[0]; li += FB_TX) {
-                const int i = pb.lo[0] + li;
-                const bool in_x = li < pb.n[0] - 1;
+            // all read-modify-write loads of this thread first (up to 3 x FB_IT in flight), then the arithmetic and the
+            // stores: the loop over the row must not serialise one memory latency per iteration
+            double vbx[FB_IT], vby[FB_IT], vbz[FB_IT];
+#pragma unroll
+            for (int t = 0; t < FB_IT; ++t) {
+                const int li = tx + t * FB_TX, i = pb.lo[0] + li;
+                const bool in = li < pb.n[0], in_x = li < pb.n[0] - 1;
+                vbx[t] = (in && in_y && in_z) ? Bx(i, j, k) : 0.0;
+                vby[t] = (in && in_x && in_z) ? By(i, j, k) : 0.0;
+                vbz[t] = (in && in_x && in_y) ? Bz(i, j, k) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < FB_IT; ++t) {
+                const int li = tx + t * FB_TX, i = pb.lo[0] + li;
+                const bool in = li < pb.n[0], in_x = li < pb.n[0] - 1;
                 const int ax = i - Ex.F.lo0, ay = i - Ey.F.lo0, az = i - Ez.F.lo0;
-                if (in_y && in_z) {   // Bx(1,0,0)  EvolveB.cpp:168-171
-                    Bx(i, j, k) += dt * (cf.cz * (ey1[ay] - ey0[ay])) - dt * (cf.cy * (ez0[az + Ez.F.sj] - ez0[az]));
+                if (in && in_y && in_z) {   // Bx(1,0,0)  EvolveB.cpp:168-171
+                    Bx(i, j, k) = vbx[t] + (dt * (cf.cz * (ey1[ay] - ey0[ay])) - dt * (cf.cy * (ez0[az + Ez.F.sj] - ez0[az])));
                 }
-                if (in_x && in_z) {   // By(0,1,0)  :175-178
-                    By(i, j, k) += dt * (cf.cx * (ez0[az + 1] - ez0[az])) - dt * (cf.cz * (ex1[ax] - ex0[ax]));
+                if (in && in_x && in_z) {   // By(0,1,0)  :175-178
+                    By(i, j, k) = vby[t] + (dt * (cf.cx * (ez0[az + 1] - ez0[az])) - dt * (cf.cz * (ex1[ax] - ex0[ax])));
                 }
-                if (in_x && in_y) {   // Bz(0,0,1)  :182-185
-                    Bz(i, j, k) += dt * (cf.cy * (ex0[ax + Ex.F.sj] - ex0[ax])) - dt * (cf.cx * (ey0[ay + 1] - ey0[ay]));
+                if (in && in_x && in_y) {   // Bz(0,0,1)  :182-185
+                    Bz(i, j, k) = vbz[t] + (dt * (cf.cy * (ex0[ax + Ex.F.sj] - ex0[ax])) - dt * (cf.cx * (ey0[ay + 1] - ey0[ay])));
                 }
             }
         }
@@ -239,21 +252,31 @@ evolve_e_bulk_kernel(FabView Ex, FabView Ey, FabView Ez, BulkSrc Bx, BulkSrc By,
         const bool in_z = lk < pb.n[2] - 1;
         const int k = pb.lo[2] + lk, j = pb.lo[1] + lj;
         if (row_ok) {
-            for (int li = tx; li < pb.n[0]; li += FB_TX) {
-                const int i = pb.lo[0] + li;
-                const bool in_x = li < pb.n[0] - 1;
+            double vex[FB_IT], vey[FB_IT], vez[FB_IT], vjx[FB_IT], vjy[FB_IT], vjz[FB_IT];
+#pragma unroll
+            for (int t = 0; t < FB_IT; ++t) {      // the six global loads of every point of this thread, all in flight
+                const int li = tx + t * FB_TX, i = pb.lo[0] + li;
+                const bool in = li < pb.n[0], in_x = li < pb.n[0] - 1;
+                vex[t] = (in && in_x) ? Ex(i, j, k) : 0.0;  vjx[t] = (in && in_x) ? jx.ld(i, j, k) : 0.0;
+                vey[t] = (in && in_y) ? Ey(i, j, k) : 0.0;  vjy[t] = (in && in_y) ? jy.ld(i, j, k) : 0.0;
+                vez[t] = (in && in_z) ? Ez(i, j, k) : 0.0;  vjz[t] = (in && in_z) ? jz.ld(i, j, k) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < FB_IT; ++t) {
+                const int li = tx + t * FB_TX, i = pb.lo[0] + li;
+                const bool in = li < pb.n[0], in_x = li < pb.n[0] - 1;
                 const int ax = i - Bx.F.lo0, ay = i - By.F.lo0, az = i - Bz.F.lo0;
-                if (in_x) {           // Ex(0,1,1)  EvolveE.cpp:185-188
-                    Ex(i, j, k) += c2 * dt * (-(cf.cz * (by[ay] - bym[ay])) + cf.cy * (bz[az] - bz[az - Bz.F.sj])
-                                              - MU0 * jx.ld(i, j, k));
+                if (in && in_x) {           // Ex(0,1,1)  EvolveE.cpp:185-188
+                    Ex(i, j, k) = vex[t] + c2 * dt * (-(cf.cz * (by[ay] - bym[ay])) + cf.cy * (bz[az] - bz[az - Bz.F.sj])
+                                                      - MU0 * vjx[t]);
                 }
-                if (in_y) {           // Ey(1,0,1)  :201-204
-                    Ey(i, j, k) += c2 * dt * (-(cf.cx * (bz[az] - bz[az - 1])) + cf.cz * (bx[ax] - bxm[ax])
-                                              - MU0 * jy.ld(i, j, k));
+                if (in && in_y) {           // Ey(1,0,1)  :201-204
+                    Ey(i, j, k) = vey[t] + c2 * dt * (-(cf.cx * (bz[az] - bz[az - 1])) + cf.cz * (bx[ax] - bxm[ax])
+                                                      - MU0 * vjy[t]);
                 }
-                if (in_z) {           // Ez(1,1,0)  :210-213
-                    Ez(i, j, k) += c2 * dt * (-(cf.cy * (bx[ax] - bx[ax - Bx.F.sj])) + cf.cx * (by[ay] - by[ay - 1])
-                                              - MU0 * jz.ld(i, j, k));
+                if (in && in_z) {           // Ez(1,1,0)  :210-213
+                    Ez(i, j, k) = vez[t] + c2 * dt * (-(cf.cy * (bx[ax] - bx[ax - Bx.F.sj])) + cf.cx * (by[ay] - by[ay - 1])
+                                                      - MU0 * vjz[t]);
                 }
             }
         }
@@ -272,7 +295,8 @@ static BulkSrc bulk_src(const pic_fab& f) {
 }
 
 // shared-memory budget: the ring holds 3 slots x 3 components x (TJ+1) rows (+2 elements of alignment slack)
-static bool bulk_plan(const pic_fab src[3], int* chunk, size_t* smem) {
+static bool bulk_plan(const pic_fab src[3], const int n[3], int* chunk, size_t* smem) {
+    if (n[0] > FB_TX * FB_IT) return false;                                       // longer rows: the plain kernels
     long row = 0;
     for (int c = 0; c < 3; ++c) {
         const long r = src[c].hi[0] - src[c].lo[0] + 1;
@@ -289,7 +313,7 @@ int evolve_b_bulk_launch(const pic_fab B[3], const pic_fab E[3], const pic_stenc
                          double dt, cudaStream_t s, bool* done) {
     *done = false;
     int chunk; size_t smem;
-    if (!g_fdtd_bulk || st->algo != PIC_SOLVER_YEE || !bulk_plan(E, &chunk, &smem)) return 0;
+    if (!g_fdtd_bulk || st->algo != PIC_SOLVER_YEE || !bulk_plan(E, n, &chunk, &smem)) return 0;
     BulkBox pb;
     for (int d = 0; d < 3; ++d) { pb.lo[d] = lo[d]; pb.n[d] = n[d]; }
     BulkCoefs cf{st->cx[0], st->cy[0], st->cz[0]};
@@ -312,7 +336,7 @@ int evolve_e_bulk_launch(const pic_fab E[3], const pic_fab B[3], const pic_fab J
                          const int n[3], double dt, cudaStream_t s, bool* done) {
     *done = false;
     int chunk; size_t smem;
-    if (!g_fdtd_bulk || !bulk_plan(B, &chunk, &smem)) return 0;
+    if (!g_fdtd_bulk || !bulk_plan(B, n, &chunk, &smem)) return 0;
     BulkBox pb;
     for (int d = 0; d < 3; ++d) { pb.lo[d] = lo[d]; pb.n[d] = n[d]; }
     BulkCoefs cf{st->cx[0], st->cy[0], st->cz[0]};
