@@ -20,6 +20,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "particle-steps/sec (3D uniform plasma, 256^3, 8 ppc)"
+_LINE_FD = None        # the process's original stdout; everything else written to fd 1 is sent to stderr (see main)
+
+
+def emit_line(line):
+    """The ONE JSON line, on the original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _LINE_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_LINE_FD, data)
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -180,7 +190,7 @@ def run_reference(args):
                        "use_filter": int(args.filter), "timed_steps_of_the_sample": steps},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def start_watchdog(rank):
@@ -400,7 +410,7 @@ def run_engine(args):
         except Exception as exc:     # noqa: BLE001 -- the GPU line must still be printed
             line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port",
                                     "sample": "failed: %r" % (exc,)}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def main():
@@ -435,6 +445,12 @@ def main():
                     help="pic_set_gather_mode: 0 one particle per lane (default), 1 two particles of a cell per lane, "
                          "2 the same without the 128-register cap (A/B measurement; same parity tests)")
     args = ap.parse_args()
+    # Only the JSON line may reach stdout: libraries write there too (NCCL prints its version line when NCCL_DEBUG is
+    # set).  Keep the original stdout for the line and point fd 1 at stderr for everybody else.
+    global _LINE_FD
+    sys.stdout.flush()
+    _LINE_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3
     if args.impl == "reference":

@@ -20,7 +20,7 @@ class _Event:
         return 2.0
 
 
-def test_bench_engine_arm_prints_one_complete_line(monkeypatch, capsys):
+def test_bench_engine_arm_prints_one_complete_line(monkeypatch, capfd):
     import torch
     from host_harness import harness
     import bench
@@ -48,7 +48,7 @@ def test_bench_engine_arm_prints_one_complete_line(monkeypatch, capsys):
     with pytest.raises(SystemExit) as e:
         bench.main()
     assert e.value.code == 0
-    out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    out = [ln for ln in capfd.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -62,13 +62,13 @@ def test_bench_engine_arm_prints_one_complete_line(monkeypatch, capsys):
     harness.host_library().pic_set_deposit_mode(0)
 
 
-def test_bench_reference_arm_prints_one_line(monkeypatch, capsys):
+def test_bench_reference_arm_prints_one_line(monkeypatch, capfd):
     import bench
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--cpu-cells", "16", "--steps", "2", "--warmup", "1"])
     monkeypatch.setattr(bench.os, "_exit", lambda code: (_ for _ in ()).throw(SystemExit(code)))
     with pytest.raises(SystemExit):
         bench.main()
-    out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    out = [ln for ln in capfd.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1
     line = json.loads(out[0])
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["value"] == line["value"]

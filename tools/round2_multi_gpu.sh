@@ -19,3 +19,10 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_ref_$N.json 2> gpurun_out/bench_ref_$N.err
 echo "reference arm exit: $?"
 cat gpurun_out/bench_ref_$N.json
+if [ "$N" = "8" ]; then
+    # BASELINE configs[2]: 512^3 split 2x2x2 over 8 GPUs, CKC solver, NCCL halos
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
+        bench.py --gpus $N --steps 20 --warmup 5 --solver ckc > gpurun_out/bench_ckc_$N.json 2> gpurun_out/bench_ckc_$N.err
+    echo "ckc bench exit: $?"
+    cat gpurun_out/bench_ckc_$N.json
+fi
