@@ -81,6 +81,18 @@ def main():
         v["stage_ms"] = {k: t[0] for k, t in sim.stage_ms().items()}
     L.pic_set_deposit_mode(0)
     L.pic_set_gather_mode(0)
+    # the two FDTD data paths (stage times only)
+    out["fdtd"] = {}
+    for fm in (0, 1):
+        L.pic_set_fdtd_mode(fm)
+        sim.enable_stage_timing(False)
+        sim.Evolve(2, synchronize_last=False)
+        sim.enable_stage_timing(True)
+        sim.Evolve(4, synchronize_last=False)
+        st = sim.stage_ms()
+        out["fdtd"]["bulk" if fm else "plain"] = {k: st[k][0] for k in ("evolve_b", "evolve_e")}
+        print("fdtd mode %d : evolve_b %.3f ms  evolve_e %.3f ms" % (fm, st["evolve_b"][0], st["evolve_e"][0]), file=sys.stderr)
+    L.pic_set_fdtd_mode(1)
     # best of each family together
     best_d = min((v for v in out["variants"][:-1] if v["gather_mode"] == 0), key=lambda v: v["ms_per_step"])
     best_g = min((v for v in out["variants"][:-1] if v["deposit_mode"] == 0), key=lambda v: v["ms_per_step"])

@@ -1,18 +1,18 @@
 #!/bin/bash
-# Third GPU call of the next round: profiles of the chosen kernel variants (after tools/ab_modes.py picked them).
-#   Usage:  gpurun --timeout 1500 -- 'bash tools/round2_profile.sh <deposit_mode> <gather_mode>'
-# Brings back: the launch list of one bench run (shares of the step), and one `--set full` capture each of the
-# deposition and the gather kernel (128^3 cells keep the ~40 replays per launch short).  Read here with
-#   ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | python profiles/summarize.py
-#   ncu -i gpurun_out/<name>.ncu-rep --page source --csv | python profiles/srcstalls.py
+# Profiling call: steady-state timings of the current variants, then one `ncu --set full` capture each of the
+# lane-per-cell deposition, the supercell gather and the two bulk-staged FDTD kernels.
+#   Usage:  gpurun --timeout 1500 -- 'bash tools/round2_profile.sh'
+# Read here with   ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | python profiles/summarize.py
+#                  ncu -i gpurun_out/<name>.ncu-rep --page source --csv | python profiles/srcstalls.py
 set -u
-D=${1:-0}
-G=${2:-0}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_d${D}_g${G}.csv \
-    python bench.py --steps 4 --warmup 3 --deposit-mode $D --gather-mode $G --profile-only > gpurun_out/launches_run.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:deposit_quiet -s 6 -c 2 -o gpurun_out/deposit_d${D} \
-    python bench.py --cells 128 --steps 2 --warmup 3 --deposit-mode $D --gather-mode $G --profile-only > gpurun_out/ncu_deposit.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gather_push_ -s 6 -c 2 -o gpurun_out/gather_g${G} \
-    python bench.py --cells 128 --steps 2 --warmup 3 --deposit-mode $D --gather-mode $G --profile-only > gpurun_out/ncu_gather.log 2>&1
+timeout 500 python tools/ab_modes.py --cells 256 --jitter --deposit-modes 0,7 --gather-modes 0 > gpurun_out/ab2.json 2> gpurun_out/ab2.err
+tail -8 gpurun_out/ab2.err
+NCU="ncu --set full --clock-control none --import-source on"
+timeout 300 $NCU -k regex:deposit_cells -s 4 -c 1 -f -o gpurun_out/r2_cells \
+    python bench.py --cells 128 --spinup 0 --jitter --steps 2 --warmup 3 --deposit-mode 7 --profile-only > gpurun_out/ncu_cells.log 2>&1
+timeout 300 $NCU -k regex:gather_push_tile -s 4 -c 1 -f -o gpurun_out/r2_gather \
+    python bench.py --cells 128 --spinup 0 --jitter --steps 2 --warmup 3 --profile-only > gpurun_out/ncu_gather.log 2>&1
+timeout 300 $NCU -k regex:evolve_._bulk -s 6 -c 2 -f -o gpurun_out/r2_fdtd \
+    python bench.py --cells 256 --spinup 0 --steps 2 --warmup 3 --profile-only > gpurun_out/ncu_fdtd.log 2>&1
 ls -la gpurun_out | tail -8
