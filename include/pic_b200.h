@@ -174,10 +174,11 @@ int pic_evolve_b(const pic_fab B[3], const pic_fab E[3], const pic_stencil* st, 
  * WarpX::EvolveE (WarpXPushFieldsEM.cpp:958-962).  E += c^2 dt (curl B - mu0 J). */
 int pic_evolve_e(const pic_fab E[3], const pic_fab B[3], const pic_fab J[3],
                  const pic_stencil* st, double dt, void* stream);
-/* How the Yee kernels read their source field: 1 (default) = bulk-asynchronous copies (cp.async.bulk, completion on an
- * mbarrier) stage the rows a CTA needs into a shared-memory ring, plane after plane (csrc/fdtd_bulk.cu); 0 = plain
- * read-only loads (csrc/fdtd.cu).  CKC's EvolveB and arrays whose base is not 16-byte aligned always take the plain
- * kernels.  Same arithmetic either way. */
+/* How the Yee kernels read their source field, a bit mask: bit 0 (default on) = EvolveB, bit 1 = EvolveE through
+ * bulk-asynchronous copies (cp.async.bulk, completion on an mbarrier) that stage the rows a CTA needs into a
+ * shared-memory ring, plane after plane (csrc/fdtd_bulk.cu); bit clear = plain read-only loads (csrc/fdtd.cu).
+ * CKC's EvolveB and arrays whose base is not 16-byte aligned always take the plain kernels.  Same arithmetic either way.
+ * (Measured on a B200 at 256^3: EvolveB 0.236 ms either way, EvolveE 0.34 ms staged vs 0.29 ms plain.) */
 void pic_set_fdtd_mode(int mode);
 long pic_fdtd_bulk_launches(void);   /* launches of the bulk-staged kernels so far (tests: the path really ran) */
 
@@ -234,7 +235,8 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
  * Analogous to WarpX's runtime switch warpx.do_shared_mem_current_deposition
  * (Source/WarpX.cpp:126, Docs/source/usage/parameters.rst:2608-2623). */
 enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1, PIC_DEPOSIT_RUNS2 = 2, PIC_DEPOSIT_RUNS_SLOTRED = 3,
-       PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6, PIC_DEPOSIT_CELLS = 7 };
+       PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6, PIC_DEPOSIT_CELLS = 7,
+       PIC_DEPOSIT_CELLS2 = 8, PIC_DEPOSIT_CELLS2_WIDE = 9 /* lane per cell with two producer warps (3 / 2 CTAs per SM) */ };
 void pic_set_deposit_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------

@@ -61,14 +61,15 @@ def test_periodic_loop_on_the_host_matches_oracle(orc, HostSimulation):
     assert e == pytest.approx(eo, rel=1e-10)
 
 
-def test_order3_loop_with_lane_per_cell_deposition_on_the_host_matches_oracle(orc, HostSimulation):
+@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2])
+def test_order3_loop_with_lane_per_cell_deposition_on_the_host_matches_oracle(orc, HostSimulation, mode):
     """Config 2 in the small (16^3, 8 ppc, order 3, hot enough that particles cross cell faces every step): nine steps of
     the C++ driver with pic_set_deposit_mode(PIC_DEPOSIT_CELLS) -- slices, extra rounds for the particles that left the
     cell of their bin (the sort runs every 4 steps), the list for those that left the supercell -- under emulation."""
     from host_harness import harness
     wl = workloads.uniform_plasma_3d(n=16, ppc=(2, 2, 2), u_th=0.1, lx=2.5e-6, perturbation=0.01)
     hl = harness.host_library()
-    hl.pic_set_deposit_mode(abi.PIC_DEPOSIT_CELLS)
+    hl.pic_set_deposit_mode(mode)
     try:
         sim = HostSimulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3, sort_interval=4)
         osim = orc.OracleSim(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=3)

@@ -197,7 +197,8 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, nox):
     (1, (12, 8, 10), (1, 1, 1), 0.3, "odd"),
     (3, (8, 8, 8), (2, 2, 2), 0.02, "tail"),          # particles appended behind the binned range
 ])
-def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind):
+@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2])
+def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind, mode):
     from host_harness import harness
     hl = harness.host_library()
     lx = tuple(0.5e-6 * v for v in n)
@@ -239,7 +240,7 @@ def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind)
     bins.np_binned = np_binned
     assert orc.lib().orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
                                            abi.int3(lo), sp["q"], dt, -0.5 * dt, nox) == 0
-    hl.pic_set_deposit_mode(abi.PIC_DEPOSIT_CELLS)
+    hl.pic_set_deposit_mode(mode)
     try:
         assert hl.pic_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin),
                                         abi.int3(lo), sp["q"], dt, -0.5 * dt, nox, C.byref(bins), None) == 0, hl.pic_last_error()
@@ -253,7 +254,7 @@ def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind)
 # the FDTD kernels on the host: plain loads (fdtd.cu) and the bulk-asynchronous staging of fdtd_bulk.cu (the emulator
 # performs the bulk copies synchronously: ring indexing, row / plane clamps, alignment widening, tail element)
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [3, 1, 0])
 @pytest.mark.parametrize("algo", [abi.SOLVER_YEE, abi.SOLVER_CKC])
 @pytest.mark.parametrize("n,ng", [((16, 12, 10), (2, 2, 2)), ((70, 9, 37), (1, 2, 1)), ((7, 6, 5), (4, 4, 4))])
 def test_fdtd_kernels_under_simt_emulation(orc, mode, algo, n, ng):
@@ -279,7 +280,8 @@ def test_fdtd_kernels_under_simt_emulation(orc, mode, algo, n, ng):
     finally:
         hl.pic_set_fdtd_mode(1)
     # EvolveE is staged for both solvers, EvolveB for Yee (numpy arrays are 16-byte aligned)
-    assert hl.pic_fdtd_bulk_launches() - before == (0 if mode == 0 else (3 if algo == abi.SOLVER_YEE else 1))
+    want = (2 if (mode & 1) and algo == abi.SOLVER_YEE else 0) + (1 if mode & 2 else 0)
+    assert hl.pic_fdtd_bulk_launches() - before == want
     Eo, Bo, Jo = orc.fab_array(F[0:3]), orc.fab_array(F[3:6]), orc.fab_array(F[6:9])
     L.orc_evolve_b(Bo, Eo, C.byref(st), 0.5 * dt)
     L.orc_evolve_e(Eo, Bo, Jo, C.byref(st), dt)

@@ -83,7 +83,7 @@ def main():
     L.pic_set_gather_mode(0)
     # the two FDTD data paths (stage times only)
     out["fdtd"] = {}
-    for fm in (0, 1):
+    for fm in (0, 3):
         L.pic_set_fdtd_mode(fm)
         sim.enable_stage_timing(False)
         sim.Evolve(2, synchronize_last=False)

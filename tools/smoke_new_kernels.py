@@ -38,13 +38,14 @@ def main():
     ok = True
     torch.cuda.set_device(0)
     ref = run(32, 7, fdtd=0, deposit=0)
-    for name, modes in (("fdtd bulk staging", dict(fdtd=1, deposit=0)), ("deposit lane-per-cell", dict(fdtd=0, deposit=7)),
-                        ("gather pairs", dict(fdtd=0, deposit=0, gather=1)), ("all three", dict(fdtd=1, deposit=7, gather=1))):
+    for name, modes in (("fdtd bulk staging", dict(fdtd=3, deposit=0)), ("deposit lane-per-cell", dict(fdtd=0, deposit=7)),
+                        ("deposit lane-per-cell, 2 producers", dict(fdtd=0, deposit=8)), ("the same, wide", dict(fdtd=0, deposit=9)),
+                        ("gather pairs", dict(fdtd=0, deposit=0, gather=1)), ("all three", dict(fdtd=3, deposit=7, gather=1))):
         got = run(32, 7, **modes)
         err = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) for a, b in zip(got[:3] + got[6:], ref[:3] + ref[6:]))
         good = err <= 1e-9
         ok &= good
-        print("[smoke] %-24s rel. difference to the round-1 kernels %.2e  %s" % (name, err, "ok" if good else "FAIL"), flush=True)
+        print("[smoke] %-36s rel. difference to the round-1 kernels %.2e  %s" % (name, err, "ok" if good else "FAIL"), flush=True)
     print("SMOKE_NEW_KERNELS", "PASS" if ok else "FAIL", flush=True)
     sys.exit(0 if ok else 1)
 

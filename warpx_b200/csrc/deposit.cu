@@ -69,6 +69,7 @@ int deposit_cells_launch(const pic_soa* p, long offset, long np, const pic_fab J
 
 static int g_deposit_mode = PIC_DEPOSIT_RUNS;
 extern int g_runs_variant;      // deposit_runs.cu
+extern int g_cells_two_producers;   // deposit_cells.cu
 
 }  // namespace pic
 
@@ -76,6 +77,8 @@ using namespace pic;
 
 extern "C" void pic_set_deposit_mode(int mode) {
     g_deposit_mode = mode;
+    g_cells_two_producers = (mode == PIC_DEPOSIT_CELLS2) ? 1 : (mode == PIC_DEPOSIT_CELLS2_WIDE) ? 2 : 0;
+    if (mode == PIC_DEPOSIT_CELLS2 || mode == PIC_DEPOSIT_CELLS2_WIDE) g_deposit_mode = PIC_DEPOSIT_CELLS;
     g_runs_variant = (mode == PIC_DEPOSIT_RUNS2) ? 1 : (mode == PIC_DEPOSIT_RUNS_SLOTRED) ? 2 : (mode == PIC_DEPOSIT_RUNS2_SLOTRED) ? 3
                    : (mode == PIC_DEPOSIT_RUNS4) ? 4 : (mode == PIC_DEPOSIT_RUNS4_SLOTRED) ? 6 : 0;
 }

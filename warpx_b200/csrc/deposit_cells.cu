@@ -65,12 +65,286 @@ template <int N> struct CellsCfg {
 struct CellsHeader { int kind, retire, g, pad; };
 constexpr int DC_END = 0, DC_SLICE = 1, DC_EXTRA = 2;
 
+// ---- what a producer warp does with one particle ---------------------------------------------------------------
+template <int N> struct CellsPart {
+    double wn[3][N + 1], wo[3][N + 1], wq;
+    int t[3];       // anchor of the low sub-particle, in cells of the supercell
+    int sh[3];      // i_old - i_new
+    bool inside;    // every sub-particle is anchored at a cell of this supercell
+};
+
+template <int N> struct CellsProducer {
+    using T = CellsCfg<N>;
+    static constexpr int QS = T::QS, QP = T::QP, NCP = T::NCP;
+    SoaView P; DepositGeom dg;
+    int amin[3];            // anchor (leftmost index of a quiet particle's stencil, CurrentDeposition.H:759) of the supercell's cell 0
+    int* list; int* list_count;
+    int lane;
+
+    __device__ __forceinline__ void load(long ip, double* v7) const {
+        v7[0] = P.x[ip]; v7[1] = P.y[ip]; v7[2] = P.z[ip]; v7[3] = P.w[ip]; v7[4] = P.ux[ip]; v7[5] = P.uy[ip]; v7[6] = P.uz[ip];
+    }
+    __device__ __forceinline__ void compute(const double* v7, CellsPart<N>& q) const {      // v7 = x y z w ux uy uz
+        const ParticleGeom pg = particle_geom(v7[0], v7[1], v7[2], v7[3], v7[4], v7[5], v7[6], dg);
+        q.wq = pg.wq;
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int inew = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], q.wn[d], q.wo[d], q.sh[d]);
+            q.t[d] = inew + (q.sh[d] < 0 ? q.sh[d] : 0) - amin[d];
+            in = in && q.sh[d] >= -1 && q.sh[d] <= 1 && q.t[d] >= 0 && q.t[d] + (q.sh[d] ? 1 : 0) < T::T;
+        }
+        q.inside = in;
+    }
+    // quiet in the cell (lc) of the lane: the hot path
+    __device__ __forceinline__ bool simple(const CellsPart<N>& q, const int lc[3]) const {
+        return q.inside && (q.sh[0] | q.sh[1] | q.sh[2]) == 0 && q.t[0] == lc[0] && q.t[1] == lc[1] && q.t[2] == lc[2];
+    }
+    // The record of sub-particle v (v[d] = 0 low, 1 high) of q.  Window slot s (0..N+1) of direction d holds
+    //   wn5[s] = wn[s - (sh < 0)],  wo5[s] = wo[s - (sh > 0)]   (0 outside 0..N),
+    // c5[i] = prefix sum of wq/(dt dA) (wo5 - wn5) up to slot i; low: slots 0..N, c5[0..N-1]; high: slot N+1, c5[N].
+    __device__ __forceinline__ void emit(const CellsPart<N>& q, const int v[3], double2* r, int active, int base) const {
+        double2 s2[3][QS];
+        double cds[3][2 * NCP];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const bool nsh = q.sh[d] < 0, osh = q.sh[d] > 0, hi = v[d] != 0;
+            const double wqd = q.wq * dg.invdtd[d];
+            double run = 0.0;
+#pragma unroll
+            for (int s = 0; s <= N; ++s) {
+                const double n5 = nsh ? (s >= 1 ? q.wn[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wn[d][s];
+                const double o5 = osh ? (s >= 1 ? q.wo[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wo[d][s];
+                run += wqd * (o5 - n5);
+                if (s < QP) cds[d][s] = hi ? 0.0 : run;
+                s2[d][s] = hi ? make_double2(0.0, 0.0) : make_double2(n5, o5);
+            }
+            if (2 * NCP > QP) cds[d][2 * NCP - 1] = 0.0;
+            if (hi) {     // slot N+1 and prefix entry N, at the local positions N and N-1 of the next cell
+                s2[d][N] = make_double2(nsh ? q.wn[d][N] : 0.0, osh ? q.wo[d][N] : 0.0);
+                cds[d][QP - 1] = run;            // c5[N]
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < QS; ++s) {
+            r[(T::F_SX + s) * 32] = s2[0][s];
+            r[(T::F_SY + s) * 32] = s2[1][s];
+            r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * s2[1][s].x + (1.0 / 6.0) * s2[1][s].y,
+                                                  (1.0 / 3.0) * s2[1][s].y + (1.0 / 6.0) * s2[1][s].x);
+            r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * s2[2][s].x + (1.0 / 6.0) * s2[2][s].y,
+                                                  (1.0 / 3.0) * s2[2][s].y + (1.0 / 6.0) * s2[2][s].x);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[d][2 * m], cds[d][2 * m + 1]);
+        *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(active, base);
+    }
+    // the record of a particle that is quiet in the lane's own cell (no shifts): no selects
+    __device__ __forceinline__ void emit_simple(const CellsPart<N>& q, double2* r) const {
+#pragma unroll
+        for (int s = 0; s < QS; ++s) {
+            r[(T::F_SX + s) * 32] = make_double2(q.wn[0][s], q.wo[0][s]);
+            r[(T::F_SY + s) * 32] = make_double2(q.wn[1][s], q.wo[1][s]);
+            r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * q.wn[1][s] + (1.0 / 6.0) * q.wo[1][s],
+                                                  (1.0 / 3.0) * q.wo[1][s] + (1.0 / 6.0) * q.wn[1][s]);
+            r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * q.wn[2][s] + (1.0 / 6.0) * q.wo[2][s],
+                                                  (1.0 / 3.0) * q.wo[2][s] + (1.0 / 6.0) * q.wn[2][s]);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double wqd = q.wq * dg.invdtd[d];
+            double cds[2 * NCP];
+            cds[2 * NCP - 1] = 0.0;
+            double run = 0.0;
+#pragma unroll
+            for (int i = 0; i < QP; ++i) {
+                run += wqd * (q.wo[d][i] - q.wn[d][i]);
+                cds[i] = run;
+            }
+#pragma unroll
+            for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[2 * m], cds[2 * m + 1]);
+        }
+    }
+    __device__ __forceinline__ void emit_nothing(double2* r) const {    // zero prefix sums: the weights left in the record are finite
+#pragma unroll
+        for (int m = 0; m < 3 * NCP; ++m) r[(T::F_CDS + m) * 32] = make_double2(0.0, 0.0);
+        *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(0, 0);
+    }
+    // A particle that is not simple: every sub-particle into the queue (returns false: no room / outside -> the list)
+    __device__ __forceinline__ bool enqueue(const CellsPart<N>& q, long ip, int2* queue, int* q_count) const {
+        if (!q.inside) return false;
+        const int nq = (q.sh[0] ? 2 : 1) * (q.sh[1] ? 2 : 1) * (q.sh[2] ? 2 : 1);
+        int slot = atomicAdd(q_count, nq);
+        if (slot + nq > T::QCAP) {           // queue full: the whole particle goes to the list
+            atomicMin(q_count + 1, slot);    // later requests start beyond: they do not fit either
+            return false;
+        }
+#pragma unroll 1
+        for (int v = 0; v < 8; ++v) {
+            const int vx = v & 1, vy = (v >> 1) & 1, vz = v >> 2;
+            if ((vx && !q.sh[0]) || (vy && !q.sh[1]) || (vz && !q.sh[2])) continue;
+            queue[slot++] = make_int2((int)ip, v | ((q.t[0] + vx) << 3) | ((q.t[1] + vy) << 6) | ((q.t[2] + vz) << 9));
+        }
+        return true;
+    }
+    __device__ __forceinline__ void to_list(bool listed, long ip) const {   // for deposit_general_kernel (warp-aggregated append)
+        const unsigned mm = __ballot_sync(DC_FULL, listed);
+        if (mm) {
+            int basei = 0;
+            if (lane == 0) basei = atomicAdd(list_count, __popc(mm));
+            basei = __shfl_sync(DC_FULL, basei, 0);
+            if (listed) list[basei + __popc(mm & ((1u << lane) - 1u))] = (int)ip;
+        }
+    }
+};
+
+// ---- what a consumer warp does with one record buffer ----------------------------------------------------------
+// component roles: acc[a][b][p] += cds[p] * (A[a].x B[b].x + A[a].y B[b].y)
+//   Jx: a = y (Sy),  b = z (ABz), p = x     Jy: a = x (Sx), b = z (ABz), p = y     Jz: a = x (Sx), b = y (ABy), p = z
+template <int N> struct CellsConsumer {
+    using T = CellsCfg<N>;
+    static constexpr int QS = T::QS, QP = T::QP, NCP = T::NCP, PX = T::PX, PY = T::PY;
+    int comp, fA, fB, fC, sa, sb, sp;
+    double* tl;
+    int lx, lrow;
+    double acc[QS][QS][QP];
+
+    __device__ __forceinline__ void init(int comp_, double* tile, int lx_, int lrow_) {
+        comp = comp_; lx = lx_; lrow = lrow_;
+        fA = (comp == 0) ? T::F_SY : T::F_SX;
+        fB = (comp == 2) ? T::F_ABY : T::F_ABZ;
+        fC = T::F_CDS + comp * NCP;
+        sa = (comp == 0) ? PX : 1;
+        sb = (comp == 2) ? PX : PX * PY;
+        sp = (comp == 0) ? 1 : ((comp == 1) ? PX : PX * PY);
+        tl = tile + (size_t)comp * T::TS;
+#pragma unroll
+        for (int a = 0; a < QS; ++a)
+#pragma unroll
+            for (int b = 0; b < QS; ++b)
+#pragma unroll
+                for (int p = 0; p < QP; ++p) acc[a][b][p] = 0.0;
+    }
+    __device__ __forceinline__ void consume(const double2* r) {
+        double cds[2 * NCP];
+#pragma unroll
+        for (int m = 0; m < NCP; ++m) {
+            const double2 c2 = r[(fC + m) * 32];
+            cds[2 * m] = c2.x; cds[2 * m + 1] = c2.y;
+        }
+        double2 B[QS];
+#pragma unroll
+        for (int b = 0; b < QS; ++b) B[b] = r[(fB + b) * 32];
+#pragma unroll
+        for (int a = 0; a < QS; ++a) {
+            const double2 A = r[(fA + a) * 32];
+#pragma unroll
+            for (int b = 0; b < QS; ++b) {
+                const double wab = A.x * B[b].x + A.y * B[b].y;
+#pragma unroll
+                for (int p = 0; p < QP; ++p) acc[a][b][p] += cds[p] * wab;
+            }
+        }
+    }
+    // last slice of group g: add the lane's sums into the CTA's J block of this component.  Lanes are distinct cells,
+    // so one instruction (fixed stencil offset) touches distinct nodes; two offsets that differ along z never meet (the
+    // cells of a group share z), the others are ordered by __syncwarp.
+    __device__ __forceinline__ void retire_group(int g) {
+        const int ly = ((g & 1) << 2) + lrow, lz = g >> 1;
+        double* base = tl + lx + PX * (ly + PY * lz);
+        if (comp == 2) {                 // z is the prefix direction
+#pragma unroll
+            for (int a = 0; a < QS; ++a)
+#pragma unroll
+                for (int b = 0; b < QS; ++b) {
+                    double* q = base + a * sa + b * sb;
+                    double v[QP];
+#pragma unroll
+                    for (int p = 0; p < QP; ++p) v[p] = q[p * sp];
+#pragma unroll
+                    for (int p = 0; p < QP; ++p) { q[p * sp] = v[p] + acc[a][b][p]; acc[a][b][p] = 0.0; }
+                    __syncwarp();
+                }
+        } else {                         // z is line direction b
+#pragma unroll
+            for (int a = 0; a < QS; ++a)
+#pragma unroll
+                for (int p = 0; p < QP; ++p) {
+                    double* q = base + a * sa + p * sp;
+                    double v[QS];
+#pragma unroll
+                    for (int b = 0; b < QS; ++b) v[b] = q[b * sb];
+#pragma unroll
+                    for (int b = 0; b < QS; ++b) { q[b * sb] = v[b] + acc[a][b][p]; acc[a][b][p] = 0.0; }
+                    __syncwarp();
+                }
+        }
+    }
+    // extra round: every lane carries one sub-particle of ITS OWN cell (distinct cells within the round): add at the
+    // record's anchor, one stencil offset at a time (the cells differ in every direction now, so every step is ordered)
+    __device__ __forceinline__ void retire_extra(const double2* r) {
+        const int2 mt = *reinterpret_cast<const int2*>(&r[T::F_META * 32]);
+        double* base = tl + mt.y;
+        const bool active = mt.x != 0;
+#pragma unroll
+        for (int a = 0; a < QS; ++a)
+#pragma unroll
+            for (int b = 0; b < QS; ++b)
+#pragma unroll
+                for (int p = 0; p < QP; ++p) {
+                    double* q = base + a * sa + b * sb + p * sp;
+                    if (active) *q += acc[a][b][p];
+                    acc[a][b][p] = 0.0;
+                    __syncwarp();
+                }
+    }
+};
+
+// the J block goes to the arrays: one reduction per touched node
+template <int N, int NT>
+__device__ __forceinline__ void cells_flush(const double* tile, const BinsView& bins, const int tc[3], const J3& Jp) {
+    using T = CellsCfg<N>;
+    constexpr int PX = T::PX, PY = T::PY, TS = T::TS;
+    const int org[3] = {bins.box_lo[0] + tc[0] * T::T + T::O0, bins.box_lo[1] + tc[1] * T::T + T::O0,
+                        bins.box_lo[2] + tc[2] * T::T + T::O0};
+    for (int n = threadIdx.x; n < 3 * TS; n += NT) {
+        const double v = tile[n];
+        if (v == 0.0) continue;
+        const int c = n / TS, r = n - c * TS;
+        const int tz = r / (PX * PY), r2 = r - tz * (PX * PY), ty = r2 / PX, tx = r2 - ty * PX;
+        const FabView& F = Jp.v[c];
+        const int gx = org[0] + tx, gy = org[1] + ty, gz = org[2] + tz;
+        if (gx < F.lo0 || gy < F.lo1 || gz < F.lo2 || gx >= F.lo0 + F.n0 || gy >= F.lo1 + F.n1 || gz >= F.lo2 + F.n2) continue;
+        atomicAdd(F.p + F.off(gx, gy, gz), v);
+    }
+}
+
+// the cell of lane `lane` in group g, its bin, and the bin's particles
+template <int N>
+struct CellsGroup {
+    int p0, n, maxn, lc[3];
+    __device__ __forceinline__ void load(const BinsView& bins, long bin0, long np_lim, int g, int lx, int lrow) {
+        using T = CellsCfg<N>;
+        lc[0] = lx; lc[1] = ((g & 1) << 2) + lrow; lc[2] = g >> 1;
+        const long b = bin0 + lx + T::T * (lc[1] + T::T * lc[2]);
+        p0 = (int)min((long)bins.cell_start[b], np_lim);
+        n = (int)min((long)bins.cell_start[b + 1], np_lim) - p0;
+        maxn = n;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) maxn = max(maxn, __shfl_xor_sync(DC_FULL, maxn, o));
+    }
+};
+
+// ==================================================================================================================
+// One producer, three consumers (128 threads)
+// ==================================================================================================================
 template <int N, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom dg,
                      int* __restrict__ list, int* __restrict__ list_count) {
     using T = CellsCfg<N>;
-    constexpr int QS = T::QS, QP = T::QP, NF = T::NF, NCP = T::NCP, PX = T::PX, PY = T::PY, TS = T::TS;
+    constexpr int NF = T::NF, PX = T::PX, PY = T::PY, TS = T::TS;
     PIC_DYNAMIC_SMEM(double2, smem2);
     double2* rec = smem2;                                                  // [2][NF][32]
     double* tile = reinterpret_cast<double*>(smem2 + 2 * NF * 32);         // [3][TS]
@@ -79,9 +353,6 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
     int* q_count = reinterpret_cast<int*>(hdr + 2);      // [0] entries requested, [1] first slot that did not fit
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int role = (warp + blockIdx.x) & 3;                              // 0 producer, 1..3 consumer of component role-1
-    const bool producer = role == 0;
-    const int comp = role - 1;
-
     int tc[3];
     tile_coords(bins, blockIdx.x, tc);                                     // supercell of this CTA
     const long bin0 = (long)blockIdx.x * (T::T * T::T * T::T);
@@ -93,192 +364,42 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
     if (threadIdx.x == 0) { q_count[0] = 0; q_count[1] = T::QCAP; }
     __syncthreads();
 
-    if (producer) {
+    if (role == 0) {
         // ============================== producer ==============================
-        // anchor (leftmost index of a quiet particle's stencil, CurrentDeposition.H:759) of the supercell's cell 0
-        const int amin[3] = {tc[0] * T::T + bins.box_lo[0] - dg.lo[0] + T::O0, tc[1] * T::T + bins.box_lo[1] - dg.lo[1] + T::O0,
-                             tc[2] * T::T + bins.box_lo[2] - dg.lo[2] + T::O0};
-        struct Part {
-            double wn[3][N + 1], wo[3][N + 1], wq;
-            int t[3];       // anchor of the low sub-particle, in cells of the supercell
-            int sh[3];      // i_old - i_new
-            bool inside;    // every sub-particle is anchored at a cell of this supercell
-        };
-        auto compute = [&](const double* v7, Part& q) {      // v7 = x y z w ux uy uz of the particle
-            const ParticleGeom pg = particle_geom(v7[0], v7[1], v7[2], v7[3], v7[4], v7[5], v7[6], dg);
-            q.wq = pg.wq;
-            bool in = true;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int inew = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], q.wn[d], q.wo[d], q.sh[d]);
-                q.t[d] = inew + (q.sh[d] < 0 ? q.sh[d] : 0) - amin[d];
-                in = in && q.sh[d] >= -1 && q.sh[d] <= 1 && q.t[d] >= 0 && q.t[d] + (q.sh[d] ? 1 : 0) < T::T;
-            }
-            q.inside = in;
-        };
-        // The record of sub-particle v (v[d] = 0 low, 1 high) of q.  Window slot s (0..N+1) of direction d holds
-        //   wn5[s] = wn[s - (sh < 0)],  wo5[s] = wo[s - (sh > 0)]   (0 outside 0..N),
-        // c5[i] = prefix sum of wq/(dt dA) (wo5 - wn5) up to slot i; low: slots 0..N, c5[0..N-1]; high: slot N+1, c5[N].
-        auto emit = [&](const Part& q, const int v[3], double2* r, int active, int base) {
-            double2 s2[3][QS];
-            double cds[3][2 * NCP];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const bool nsh = q.sh[d] < 0, osh = q.sh[d] > 0, hi = v[d] != 0;
-                const double wqd = q.wq * dg.invdtd[d];
-                double run = 0.0;
-#pragma unroll
-                for (int s = 0; s <= N; ++s) {
-                    const double n5 = nsh ? (s >= 1 ? q.wn[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wn[d][s];
-                    const double o5 = osh ? (s >= 1 ? q.wo[d][s >= 1 ? s - 1 : 0] : 0.0) : q.wo[d][s];
-                    run += wqd * (o5 - n5);
-                    if (s < QP) cds[d][s] = hi ? 0.0 : run;
-                    s2[d][s] = hi ? make_double2(0.0, 0.0) : make_double2(n5, o5);
-                }
-                if (2 * NCP > QP) cds[d][2 * NCP - 1] = 0.0;
-                if (hi) {     // slot N+1 and prefix entry N, at the local positions N and N-1 of the next cell
-                    s2[d][N] = make_double2(nsh ? q.wn[d][N] : 0.0, osh ? q.wo[d][N] : 0.0);
-                    cds[d][QP - 1] = run;            // c5[N]
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < QS; ++s) {
-                r[(T::F_SX + s) * 32] = s2[0][s];
-                r[(T::F_SY + s) * 32] = s2[1][s];
-                r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * s2[1][s].x + (1.0 / 6.0) * s2[1][s].y,
-                                                      (1.0 / 3.0) * s2[1][s].y + (1.0 / 6.0) * s2[1][s].x);
-                r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * s2[2][s].x + (1.0 / 6.0) * s2[2][s].y,
-                                                      (1.0 / 3.0) * s2[2][s].y + (1.0 / 6.0) * s2[2][s].x);
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-#pragma unroll
-                for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[d][2 * m], cds[d][2 * m + 1]);
-            *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(active, base);
-        };
-        // the record of a particle that is quiet in the lane's own cell (no shifts): the hot path, no selects
-        auto emit_simple = [&](const Part& q, double2* r) {
-#pragma unroll
-            for (int s = 0; s < QS; ++s) {
-                r[(T::F_SX + s) * 32] = make_double2(q.wn[0][s], q.wo[0][s]);
-                r[(T::F_SY + s) * 32] = make_double2(q.wn[1][s], q.wo[1][s]);
-                r[(T::F_ABY + s) * 32] = make_double2((1.0 / 3.0) * q.wn[1][s] + (1.0 / 6.0) * q.wo[1][s],
-                                                      (1.0 / 3.0) * q.wo[1][s] + (1.0 / 6.0) * q.wn[1][s]);
-                r[(T::F_ABZ + s) * 32] = make_double2((1.0 / 3.0) * q.wn[2][s] + (1.0 / 6.0) * q.wo[2][s],
-                                                      (1.0 / 3.0) * q.wo[2][s] + (1.0 / 6.0) * q.wn[2][s]);
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const double wqd = q.wq * dg.invdtd[d];
-                double cds[2 * NCP];
-                cds[2 * NCP - 1] = 0.0;
-                double run = 0.0;
-#pragma unroll
-                for (int i = 0; i < QP; ++i) {
-                    run += wqd * (q.wo[d][i] - q.wn[d][i]);
-                    cds[i] = run;
-                }
-#pragma unroll
-                for (int m = 0; m < NCP; ++m) r[(T::F_CDS + d * NCP + m) * 32] = make_double2(cds[2 * m], cds[2 * m + 1]);
-            }
-        };
-        auto emit_nothing = [&](double2* r) {    // zero prefix sums: the weights left in the record are finite
-#pragma unroll
-            for (int m = 0; m < 3 * NCP; ++m) r[(T::F_CDS + m) * 32] = make_double2(0.0, 0.0);
-            *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(0, 0);
-        };
-        auto to_list = [&](bool listed, long ip) {   // particles for deposit_general_kernel (warp-aggregated append)
-            const unsigned mm = __ballot_sync(DC_FULL, listed);
-            if (mm) {
-                int basei = 0;
-                if (lane == 0) basei = atomicAdd(list_count, __popc(mm));
-                basei = __shfl_sync(DC_FULL, basei, 0);
-                if (listed) list[basei + __popc(mm & ((1u << lane) - 1u))] = (int)ip;
-            }
-        };
-
-        // The particles of a group are one contiguous range (the bins are numbered group after group); while a group
-        // is processed the lines of the next one are requested: every lane 2 sectors of each of the 7 arrays.
-        auto prefetch_group = [&](int g) {
-#ifndef PIC_SIMT_HOST
-            if (g >= 16) return;
-            const long first = bins.cell_start[bin0 + 32 * g], last = min((long)bins.cell_start[bin0 + 32 * g + 32], np_lim);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const long ip = first + 4 * (lane + 32 * k);
-                if (ip < last) {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.x + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.y + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.z + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.w + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.ux + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.uy + ip));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(P.uz + ip));
-                }
-            }
-#else
-            (void)g;
-#endif
-        };
-        prefetch_group(0);
+        CellsProducer<N> pr{P, dg, {tc[0] * T::T + bins.box_lo[0] - dg.lo[0] + T::O0, tc[1] * T::T + bins.box_lo[1] - dg.lo[1] + T::O0,
+                                    tc[2] * T::T + bins.box_lo[2] - dg.lo[2] + T::O0}, list, list_count, lane};
         double pf[7] = {0, 0, 0, 0, 0, 0, 0};
         int it = 0;
         // ---------------- the groups: slice s = the s-th particle of each of the 32 cells ----------------
         for (int g = 0; g < 16; ++g) {
-            prefetch_group(g + 1);
-            const int ly = ((g & 1) << 2) + lrow, lz = g >> 1;
-            const long b = bin0 + lx + T::T * (ly + T::T * lz);
-            const int p0 = (int)min((long)bins.cell_start[b], np_lim), p1 = (int)min((long)bins.cell_start[b + 1], np_lim);
-            const int n = p1 - p0;
-            int maxn = n;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) maxn = max(maxn, __shfl_xor_sync(DC_FULL, maxn, o));
-            const int lc[3] = {lx, ly, lz};
-            for (int s = 0; s < maxn; ++s) {
+            CellsGroup<N> G;
+            G.load(bins, bin0, np_lim, g, lx, lrow);
+            for (int s = 0; s < G.maxn; ++s) {
                 double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
-                const bool valid = s < n;
-                const long ip = (long)p0 + s;
+                const bool valid = s < G.n;
+                const long ip = (long)G.p0 + s;
                 // this particle was requested during the previous slice (registers); the first of a cell is loaded here
                 double v7[7];
                 if (s == 0) {
-                    if (valid) { v7[0] = P.x[ip]; v7[1] = P.y[ip]; v7[2] = P.z[ip]; v7[3] = P.w[ip]; v7[4] = P.ux[ip]; v7[5] = P.uy[ip]; v7[6] = P.uz[ip]; }
+                    if (valid) pr.load(ip, v7);
                     else { v7[0] = v7[1] = v7[2] = v7[3] = v7[4] = v7[5] = v7[6] = 0.0; }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 7; ++c) v7[c] = pf[c];
                 }
-                if (s + 1 < n) {
-                    pf[0] = P.x[ip + 1]; pf[1] = P.y[ip + 1]; pf[2] = P.z[ip + 1]; pf[3] = P.w[ip + 1];
-                    pf[4] = P.ux[ip + 1]; pf[5] = P.uy[ip + 1]; pf[6] = P.uz[ip + 1];
-                }
+                if (s + 1 < G.n) pr.load(ip + 1, pf);
                 bool listed = false, sent = false;
                 if (valid) {
-                    Part q;
-                    compute(v7, q);
+                    CellsPart<N> q;
+                    pr.compute(v7, q);
                     // hot path: quiet in the lane's own cell.  Everything else -- every sub-particle of it -- waits
                     // in the queue for the extra rounds (or goes to the list when it reaches outside the supercell).
-                    const bool simple = q.inside && (q.sh[0] | q.sh[1] | q.sh[2]) == 0 && q.t[0] == lc[0] && q.t[1] == lc[1] && q.t[2] == lc[2];
-                    if (simple) { emit_simple(q, r); sent = true; }
-                    else if (!q.inside) listed = true;
-                    else {
-                        const int nq = (q.sh[0] ? 2 : 1) * (q.sh[1] ? 2 : 1) * (q.sh[2] ? 2 : 1);
-                        int slot = atomicAdd(q_count, nq);
-                        if (slot + nq > T::QCAP) {           // queue full: the whole particle goes to the list
-                            atomicMin(q_count + 1, slot);    // later requests start beyond: they do not fit either
-                            listed = true;
-                        } else {
-#pragma unroll 1
-                            for (int v = 0; v < 8; ++v) {
-                                const int vx = v & 1, vy = (v >> 1) & 1, vz = v >> 2;
-                                if ((vx && !q.sh[0]) || (vy && !q.sh[1]) || (vz && !q.sh[2])) continue;
-                                queue[slot++] = make_int2((int)ip, v | ((q.t[0] + vx) << 3) | ((q.t[1] + vy) << 6) | ((q.t[2] + vz) << 9));
-                            }
-                        }
-                    }
+                    if (pr.simple(q, G.lc)) { pr.emit_simple(q, r); sent = true; }
+                    else listed = !pr.enqueue(q, ip, queue, q_count);
                 }
-                if (!sent) emit_nothing(r);
-                to_list(listed, ip);
-                if (lane == 0) hdr[it & 1] = CellsHeader{DC_SLICE, s == maxn - 1 ? 1 : 0, g, 0};
+                if (!sent) pr.emit_nothing(r);
+                pr.to_list(listed, ip);
+                if (lane == 0) hdr[it & 1] = CellsHeader{DC_SLICE, s == G.maxn - 1 ? 1 : 0, g, 0};
                 __syncthreads();
                 ++it;
             }
@@ -295,15 +416,15 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
                 const bool go = pend && lane == __ffs(m) - 1;
                 double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
                 if (go) {
-                    Part q;
-                    const long ip = e.x;
-                    const double v7[7] = {P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip]};
-                    compute(v7, q);
+                    CellsPart<N> q;
+                    double v7[7];
+                    pr.load(e.x, v7);
+                    pr.compute(v7, q);
                     const int v[3] = {e.y & 1, (e.y >> 1) & 1, (e.y >> 2) & 1};
                     const int ax = (e.y >> 3) & 7, ay = (e.y >> 6) & 7, az = (e.y >> 9) & 7;
-                    emit(q, v, r, 1, ax + PX * (ay + PY * az));
+                    pr.emit(q, v, r, 1, ax + PX * (ay + PY * az));
                 } else {
-                    emit_nothing(r);
+                    pr.emit_nothing(r);
                 }
                 if (lane == 0) hdr[it & 1] = CellsHeader{DC_EXTRA, 1, 0, 0};
                 __syncthreads();
@@ -314,126 +435,185 @@ deposit_cells_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom d
         if (lane == 0) hdr[it & 1] = CellsHeader{DC_END, 0, 0, 0};
         __syncthreads();
     } else {
-        // ============================== consumer of component comp ==============================
-        // component roles: acc[a][b][p] += cds[p] * (A[a].x B[b].x + A[a].y B[b].y)
-        //   Jx: a = y (Sy),  b = z (ABz), p = x     Jy: a = x (Sx), b = z (ABz), p = y     Jz: a = x (Sx), b = y (ABy), p = z
-        const int fA = (comp == 0) ? T::F_SY : T::F_SX;
-        const int fB = (comp == 2) ? T::F_ABY : T::F_ABZ;
-        const int fC = T::F_CDS + comp * NCP;
-        const int sa = (comp == 0) ? PX : 1;
-        const int sb = (comp == 2) ? PX : PX * PY;
-        const int sp = (comp == 0) ? 1 : ((comp == 1) ? PX : PX * PY);
-        double* tl = tile + (size_t)comp * TS;
-        double acc[QS][QS][QP];
-#pragma unroll
-        for (int a = 0; a < QS; ++a)
-#pragma unroll
-            for (int b = 0; b < QS; ++b)
-#pragma unroll
-                for (int p = 0; p < QP; ++p) acc[a][b][p] = 0.0;
+        // ============================== consumer of component role - 1 ==============================
+        CellsConsumer<N> co;
+        co.init(role - 1, tile, lx, lrow);
         int it = 0;
         while (true) {
             __syncthreads();             // the producer has filled buffer it & 1 and its header
             const CellsHeader h = hdr[it & 1];
             if (h.kind == DC_END) break;
             const double2* r = rec + (size_t)(it & 1) * NF * 32 + lane;
-            {
-                double cds[2 * NCP];
-#pragma unroll
-                for (int m = 0; m < NCP; ++m) {
-                    const double2 c2 = r[(fC + m) * 32];
-                    cds[2 * m] = c2.x; cds[2 * m + 1] = c2.y;
-                }
-                double2 B[QS];
-#pragma unroll
-                for (int b = 0; b < QS; ++b) B[b] = r[(fB + b) * 32];
-#pragma unroll
-                for (int a = 0; a < QS; ++a) {
-                    const double2 A = r[(fA + a) * 32];
-#pragma unroll
-                    for (int b = 0; b < QS; ++b) {
-                        const double wab = A.x * B[b].x + A.y * B[b].y;
-#pragma unroll
-                        for (int p = 0; p < QP; ++p) acc[a][b][p] += cds[p] * wab;
-                    }
-                }
-            }
-            if (h.retire && h.kind == DC_SLICE) {
-                // ---- last slice of the group: add the lane's sums into the CTA's J block of this component.
-                // Lanes are distinct cells, so one instruction (fixed stencil offset) touches distinct nodes; two
-                // offsets that differ along z never meet (the cells of a group share z), the others are ordered
-                // by __syncwarp.
-                const int ly = ((h.g & 1) << 2) + lrow, lz = h.g >> 1;
-                double* base = tl + lx + PX * (ly + PY * lz);
-                if (comp == 2) {                 // z is the prefix direction
-#pragma unroll
-                    for (int a = 0; a < QS; ++a)
-#pragma unroll
-                        for (int b = 0; b < QS; ++b) {
-                            double* q = base + a * sa + b * sb;
-                            double v[QP];
-#pragma unroll
-                            for (int p = 0; p < QP; ++p) v[p] = q[p * sp];
-#pragma unroll
-                            for (int p = 0; p < QP; ++p) { q[p * sp] = v[p] + acc[a][b][p]; acc[a][b][p] = 0.0; }
-                            __syncwarp();
-                        }
-                } else {                         // z is line direction b
-#pragma unroll
-                    for (int a = 0; a < QS; ++a)
-#pragma unroll
-                        for (int p = 0; p < QP; ++p) {
-                            double* q = base + a * sa + p * sp;
-                            double v[QS];
-#pragma unroll
-                            for (int b = 0; b < QS; ++b) v[b] = q[b * sb];
-#pragma unroll
-                            for (int b = 0; b < QS; ++b) { q[b * sb] = v[b] + acc[a][b][p]; acc[a][b][p] = 0.0; }
-                            __syncwarp();
-                        }
-                }
-            } else if (h.kind == DC_EXTRA) {
-                // ---- extra round: every lane carries one sub-particle of ITS OWN cell (distinct cells within the
-                // round): add at the record's anchor, one stencil offset at a time (the cells differ in every
-                // direction now, so every step is ordered).
-                const int2 mt = *reinterpret_cast<const int2*>(&r[T::F_META * 32]);
-                double* base = tl + mt.y;
-                const bool active = mt.x != 0;
-#pragma unroll
-                for (int a = 0; a < QS; ++a)
-#pragma unroll
-                    for (int b = 0; b < QS; ++b)
-#pragma unroll
-                        for (int p = 0; p < QP; ++p) {
-                            double* q = base + a * sa + b * sb + p * sp;
-                            if (active) *q += acc[a][b][p];
-                            acc[a][b][p] = 0.0;
-                            __syncwarp();
-                        }
-            }
+            co.consume(r);
+            if (h.kind == DC_SLICE) { if (h.retire) co.retire_group(h.g); }
+            else co.retire_extra(r);
             ++it;
         }
     }
-
-    // ---- the J block goes to the arrays: one reduction per touched node ----
     __syncthreads();
-    const int org[3] = {bins.box_lo[0] + tc[0] * T::T + T::O0, bins.box_lo[1] + tc[1] * T::T + T::O0,
-                        bins.box_lo[2] + tc[2] * T::T + T::O0};
-    for (int n = threadIdx.x; n < 3 * TS; n += 128) {
-        const double v = tile[n];
-        if (v == 0.0) continue;
-        const int c = n / TS, r = n - c * TS;
-        const int tz = r / (PX * PY), r2 = r - tz * (PX * PY), ty = r2 / PX, tx = r2 - ty * PX;
-        const FabView& F = Jp.v[c];
-        const int gx = org[0] + tx, gy = org[1] + ty, gz = org[2] + tz;
-        if (gx < F.lo0 || gy < F.lo1 || gz < F.lo2 || gx >= F.lo0 + F.n0 || gy >= F.lo1 + F.n1 || gz >= F.lo2 + F.n2) continue;
-        atomicAdd(F.p + F.off(gx, gy, gz), v);
+    cells_flush<N, 128>(tile, bins, tc, Jp);
+}
+
+// ==================================================================================================================
+// Two producers, three consumers (160 threads).  profiles/r2_ncu_cells_1p.txt: with one producer the consumers spend
+// 65 % of their time at the barrier -- the producer's ~400 instructions per slice (plus the latency of its loads) are the
+// critical path.  Here the items (slices, then extra rounds) alternate between two producer warps, and each item takes
+// TWO barrier intervals: part 1 (load, geometry, shape factors, classification, queue / list) in interval k, part 2
+// (record and header into buffer k & 1) in interval k+1; the consumers take it in interval k+2.  In every interval one
+// producer runs a part 1 and the other a part 2.  Producer 0 owns the extra rounds (their duplicate-cell bookkeeping lives
+// in its registers): in that phase producer 1's items are empty.  `stop` (shared memory) ends the loop of every warp
+// after the same barrier.
+// ==================================================================================================================
+constexpr int DC_NOP = 3;
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(160, MINB)
+deposit_cells2_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom dg,
+                      int* __restrict__ list, int* __restrict__ list_count) {
+    using T = CellsCfg<N>;
+    constexpr int NF = T::NF, PX = T::PX, PY = T::PY, TS = T::TS;
+    PIC_DYNAMIC_SMEM(double2, smem2);
+    double2* rec = smem2;                                                  // [2][NF][32]
+    double* tile = reinterpret_cast<double*>(smem2 + 2 * NF * 32);         // [3][TS]
+    int2* queue = reinterpret_cast<int2*>(tile + 3 * TS);                  // [QCAP] (particle, code)
+    CellsHeader* hdr = reinterpret_cast<CellsHeader*>(queue + T::QCAP);    // [2]
+    int* q_count = reinterpret_cast<int*>(hdr + 2);      // [0] entries requested, [1] first slot that did not fit, [2] stop
+    volatile int* stop = q_count + 2;                    // index of the END item once known
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = (warp + blockIdx.x) % 5;            // 0, 1 producers (even / odd items), 2..4 consumers
+    int tc[3];
+    tile_coords(bins, blockIdx.x, tc);
+    const long bin0 = (long)blockIdx.x * (T::T * T::T * T::T);
+    const int lx = lane & 7, rsel = lane >> 3, lrow = ((rsel & 1) << 1) | (rsel >> 1);
+
+    for (int n = threadIdx.x; n < 3 * TS; n += 160) tile[n] = 0.0;
+    for (int n = threadIdx.x; n < 2 * NF * 32; n += 160) rec[n] = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) { q_count[0] = 0; q_count[1] = T::QCAP; q_count[2] = 0x7fffffff; }
+    __syncthreads();
+
+    if (role < 2) {
+        // ============================== producer of the items with parity `role` ==============================
+        CellsProducer<N> pr{P, dg, {tc[0] * T::T + bins.box_lo[0] - dg.lo[0] + T::O0, tc[1] * T::T + bins.box_lo[1] - dg.lo[1] + T::O0,
+                                    tc[2] * T::T + bins.box_lo[2] - dg.lo[2] + T::O0}, list, list_count, lane};
+        // the walk over the slices: (g, s) is item number `k`; exhausted: k = number of slices
+        CellsGroup<N> G;
+        int g = -1, s = 0, k = 0;
+        bool slices_left = true;
+        auto next_group = [&]() {
+            while (true) {
+                if (++g >= 16) { slices_left = false; return; }
+                G.load(bins, bin0, np_lim, g, lx, lrow);
+                if (G.maxn > 0) { s = 0; return; }
+            }
+        };
+        auto step = [&]() { if (slices_left) { ++k; if (++s >= G.maxn) next_group(); } };
+        next_group();
+        if (role == 1) step();                           // producer 1 starts at item 1
+        // what part 1 leaves for part 2
+        CellsPart<N> q;
+        int kind = DC_NOP, h_retire = 0, h_g = 0, x_base = 0, x_v = 0;
+        bool send = false;
+        double pf[7] = {0, 0, 0, 0, 0, 0, 0};
+        bool pf_ok = false;                              // pf holds the particle of this producer's next slice
+        // extra rounds (producer 0)
+        int nq_total = -1, qb = 0;
+        bool pend = false;
+        int2 e = make_int2(0, 0);
+        bool ending = false;
+
+        for (int t = 0;; ++t) {
+            if ((t & 1) == role) {
+                // ------------------------------ part 1 of item t ------------------------------
+                kind = DC_NOP; send = false;
+                if (slices_left) {                       // the walk points at item t: a slice
+                    const bool valid = s < G.n;
+                    const long ip = (long)G.p0 + s;
+                    double v7[7];
+                    if (pf_ok) {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) v7[c] = pf[c];
+                    } else if (valid) pr.load(ip, v7);
+                    else { v7[0] = v7[1] = v7[2] = v7[3] = v7[4] = v7[5] = v7[6] = 0.0; }
+                    // this producer's next slice is s + 2 of the same cells when the group has it
+                    pf_ok = s + 2 < G.maxn;              // warp-uniform
+                    if (s + 2 < G.n) pr.load(ip + 2, pf);
+                    bool listed = false;
+                    if (valid) {
+                        pr.compute(v7, q);
+                        if (pr.simple(q, G.lc)) send = true;
+                        else listed = !pr.enqueue(q, ip, queue, q_count);
+                    }
+                    pr.to_list(listed, ip);
+                    kind = DC_SLICE; h_retire = (s == G.maxn - 1) ? 1 : 0; h_g = g;
+                    step(); step();                      // to this producer's next item
+                } else if (role == 0 && !ending) {       // an extra round, or the end
+                    if (nq_total < 0) { nq_total = min(q_count[0], q_count[1]); qb = -32; }
+                    if (!__ballot_sync(DC_FULL, pend)) {             // next batch of 32 queued sub-particles
+                        qb += 32;
+                        pend = qb + lane < nq_total;
+                        e = pend ? queue[qb + lane] : make_int2(0, 0);
+                    }
+                    if (qb >= nq_total) { ending = true; kind = DC_END; }
+                    else {
+                        const unsigned m = __match_any_sync(DC_FULL, pend ? ((e.y >> 3) & 511) : 512 + lane);
+                        const bool go = pend && lane == __ffs(m) - 1;
+                        if (go) {
+                            double v7[7];
+                            pr.load(e.x, v7);
+                            pr.compute(v7, q);
+                            x_v = e.y & 7;
+                            x_base = ((e.y >> 3) & 7) + PX * (((e.y >> 6) & 7) + PY * ((e.y >> 9) & 7));
+                            send = true;
+                        }
+                        pend = pend && !go;
+                        kind = DC_EXTRA;
+                    }
+                }
+            } else if (t >= 1) {
+                // ------------------------------ part 2 of item t - 1 ------------------------------
+                const int kk = t - 1;
+                double2* r = rec + (size_t)(kk & 1) * NF * 32 + lane;
+                if (kind == DC_SLICE) {
+                    if (send) pr.emit_simple(q, r); else pr.emit_nothing(r);
+                } else if (kind == DC_EXTRA) {
+                    const int v[3] = {x_v & 1, (x_v >> 1) & 1, (x_v >> 2) & 1};
+                    if (send) pr.emit(q, v, r, 1, x_base); else pr.emit_nothing(r);
+                }
+                if (lane == 0) {
+                    hdr[kk & 1] = CellsHeader{kind == DC_END ? DC_NOP : kind, kind == DC_EXTRA ? 1 : h_retire, h_g, 0};
+                    if (kind == DC_END) *stop = kk;
+                }
+            }
+            __syncthreads();
+            if (*stop <= t - 1) break;
+        }
+    } else {
+        // ============================== consumer of component role - 2 ==============================
+        CellsConsumer<N> co;
+        co.init(role - 2, tile, lx, lrow);
+        for (int t = 0;; ++t) {
+            if (t >= 2) {                                // item t - 2 sits in buffer t & 1
+                const CellsHeader h = hdr[t & 1];
+                if (h.kind == DC_SLICE || h.kind == DC_EXTRA) {
+                    const double2* r = rec + (size_t)(t & 1) * NF * 32 + lane;
+                    co.consume(r);
+                    if (h.kind == DC_SLICE) { if (h.retire) co.retire_group(h.g); }
+                    else co.retire_extra(r);
+                }
+            }
+            __syncthreads();
+            if (*stop <= t - 1) break;
+        }
     }
+    __syncthreads();
+    cells_flush<N, 160>(tile, bins, tc, Jp);
 }
 
 // deposit_runs.cu: the listed particles (full stencil)
 int deposit_general_launch(SoaView P, const int* list, const int* list_count, const pic_fab J[3], const DepositGeom& dg,
                            int nox, cudaStream_t s);
+
+int g_cells_two_producers = 0;      // 1: PIC_DEPOSIT_CELLS2 (three CTAs per SM, 128 registers), 2: PIC_DEPOSIT_CELLS2_WIDE (two CTAs)
 
 template <int N>
 static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeom& dg, const pic_bins* pb, cudaStream_t s) {
@@ -445,18 +625,20 @@ static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeo
     const unsigned grid = (unsigned)(bins.nt[0] * bins.nt[1] * bins.nt[2]);
     J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
     constexpr int MINB = 3;
-    auto k = deposit_cells_kernel<N, MINB>;
+    const int two = g_cells_two_producers;
+    auto k = two == 2 ? deposit_cells2_kernel<N, 2> : two == 1 ? deposit_cells2_kernel<N, MINB> : deposit_cells_kernel<N, MINB>;
+    const int nthreads = two ? 160 : 128;
 #ifndef PIC_SIMT_HOST
     int* scratch = nullptr;
     if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(np + 1), s) != cudaSuccess)
         return fail("pic_deposit_esirkepov: cannot allocate %ld B of scratch", (long)(sizeof(int) * (np + 1)));
     cudaMemsetAsync(scratch, 0, sizeof(int), s);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[two]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::smem_bytes);
-        attr_done = true;
+        attr_done[two] = true;
     }
-    k<<<grid, 128, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
+    k<<<grid, nthreads, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
     count_launch();
     int rc = check_launch("pic_deposit_esirkepov(cells)") ? 0 : 1;
     if (!rc) rc = deposit_general_launch(P, scratch + 1, scratch, J, dg, N, s);
@@ -465,7 +647,7 @@ static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeo
 #else
     std::vector<int> scratch_h((size_t)np + 1, 0);
     int* scratch = scratch_h.data();
-    k<<<grid, 128, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
+    k<<<grid, nthreads, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
     return deposit_general_launch(P, scratch + 1, scratch, J, dg, N, s);
 #endif
 }

@@ -135,8 +135,29 @@ evolve_b_bulk_kernel(FabView Bx, FabView By, FabView Bz, BulkSrc Ex, BulkSrc Ey,
     const int lj = lj0 + ty;
     const bool row_ok = lj < pb.n[1];
     const bool in_y = lj < pb.n[1] - 1;
+    const int j = pb.lo[1] + lj;
+    // the read-modify-write values of this thread for one plane (FB_IT points of its row, three components); the
+    // loads of plane lk+1 are issued before plane lk is computed (and before the wait for its source planes)
+    double nbx[FB_IT], nby[FB_IT], nbz[FB_IT];
+    auto load_b = [&](int lk) {
+        const int k = pb.lo[2] + lk;
+        const bool in_z = lk < pb.n[2] - 1;
+#pragma unroll
+        for (int t = 0; t < FB_IT; ++t) {
+            const int li = tx + t * FB_TX, i = pb.lo[0] + li;
+            const bool in = row_ok && lk < lk1 && li < pb.n[0], in_x = li < pb.n[0] - 1;
+            nbx[t] = (in && in_y && in_z) ? Bx(i, j, k) : 0.0;
+            nby[t] = (in && in_x && in_z) ? By(i, j, k) : 0.0;
+            nbz[t] = (in && in_x && in_y) ? Bz(i, j, k) : 0.0;
+        }
+    };
+    load_b(lk0);
     for (int lk = lk0; lk < lk1; ++lk) {
         if (tid == 0 && lk + 2 <= lk_last) issue_plane(lk + 2);     // slot (lk+2)%3 was released by the barrier below
+        double vbx[FB_IT], vby[FB_IT], vbz[FB_IT];
+#pragma unroll
+        for (int t = 0; t < FB_IT; ++t) { vbx[t] = nbx[t]; vby[t] = nby[t]; vbz[t] = nbz[t]; }
+        load_b(lk + 1);
         const int s0 = lk % FB_SLOTS, s1 = (lk + 1) % FB_SLOTS;
         fb_wait(bar + s0, ((lk - lk0) / FB_SLOTS) & 1);
         const bool in_z = lk < pb.n[2] - 1;
@@ -150,19 +171,8 @@ evolve_b_bulk_kernel(FabView Bx, FabView By, FabView Bz, BulkSrc Ex, BulkSrc Ey,
         const double* ez0 = e0 + 2 * chunk + shifts[s0 * 3 + 2] + ty * Ez.F.sj;
         const double* ex1 = e1 + shifts[s1 * 3 + 0] + ty * Ex.F.sj;
         const double* ey1 = e1 + chunk + shifts[s1 * 3 + 1] + ty * Ey.F.sj;
-        const int k = pb.lo[2] + lk, j = pb.lo[1] + lj;
+        const int k = pb.lo[2] + lk;
         if (row_ok) {
-            // all read-modify-write loads of this thread first (up to 3 x FB_IT in flight), then the arithmetic and the
-            // stores: the loop over the row must not serialise one memory latency per iteration
-            double vbx[FB_IT], vby[FB_IT], vbz[FB_IT];
-#pragma unroll
-            for (int t = 0; t < FB_IT; ++t) {
-                const int li = tx + t * FB_TX, i = pb.lo[0] + li;
-                const bool in = li < pb.n[0], in_x = li < pb.n[0] - 1;
-                vbx[t] = (in && in_y && in_z) ? Bx(i, j, k) : 0.0;
-                vby[t] = (in && in_x && in_z) ? By(i, j, k) : 0.0;
-                vbz[t] = (in && in_x && in_y) ? Bz(i, j, k) : 0.0;
-            }
 #pragma unroll
             for (int t = 0; t < FB_IT; ++t) {
                 const int li = tx + t * FB_TX, i = pb.lo[0] + li;
@@ -285,7 +295,7 @@ evolve_e_bulk_kernel(FabView Ex, FabView Ey, FabView Ez, BulkSrc Bx, BulkSrc By,
 }
 
 long g_fdtd_bulk_launches = 0;
-int g_fdtd_bulk = 1;      // pic_set_fdtd_mode: 1 bulk-asynchronous staging (default where it applies), 0 plain loads
+int g_fdtd_bulk = 1;      // pic_set_fdtd_mode bits: 1 = EvolveB staged (default), 2 = EvolveE staged; 0 = plain loads
 
 static BulkSrc bulk_src(const pic_fab& f) {
     BulkSrc s;
@@ -313,7 +323,7 @@ int evolve_b_bulk_launch(const pic_fab B[3], const pic_fab E[3], const pic_stenc
                          double dt, cudaStream_t s, bool* done) {
     *done = false;
     int chunk; size_t smem;
-    if (!g_fdtd_bulk || st->algo != PIC_SOLVER_YEE || !bulk_plan(E, n, &chunk, &smem)) return 0;
+    if (!(g_fdtd_bulk & 1) || st->algo != PIC_SOLVER_YEE || !bulk_plan(E, n, &chunk, &smem)) return 0;
     BulkBox pb;
     for (int d = 0; d < 3; ++d) { pb.lo[d] = lo[d]; pb.n[d] = n[d]; }
     BulkCoefs cf{st->cx[0], st->cy[0], st->cz[0]};
@@ -336,7 +346,7 @@ int evolve_e_bulk_launch(const pic_fab E[3], const pic_fab B[3], const pic_fab J
                          const int n[3], double dt, cudaStream_t s, bool* done) {
     *done = false;
     int chunk; size_t smem;
-    if (!g_fdtd_bulk || !bulk_plan(B, n, &chunk, &smem)) return 0;
+    if (!(g_fdtd_bulk & 2) || !bulk_plan(B, n, &chunk, &smem)) return 0;
     BulkBox pb;
     for (int d = 0; d < 3; ++d) { pb.lo[d] = lo[d]; pb.n[d] = n[d]; }
     BulkCoefs cf{st->cx[0], st->cy[0], st->cz[0]};
@@ -358,5 +368,5 @@ int evolve_e_bulk_launch(const pic_fab E[3], const pic_fab B[3], const pic_fab J
 
 }  // namespace pic
 
-extern "C" void pic_set_fdtd_mode(int mode) { pic::g_fdtd_bulk = mode ? 1 : 0; }
+extern "C" void pic_set_fdtd_mode(int mode) { pic::g_fdtd_bulk = mode & 3; }
 extern "C" long pic_fdtd_bulk_launches(void) { return pic::g_fdtd_bulk_launches; }
