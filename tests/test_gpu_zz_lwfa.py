@@ -690,7 +690,7 @@ def test_charge_deposition_matches_oracle(orc, dev, nox):
 # Experimental variants of the register-run deposition (pic_set_deposit_mode 2, 3, 4):
 # same parity bar as the default kernel.  (Checked under the SIMT emulator on the host: test_simt_host.py.)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("nox,kind", [(3, "sorted"), (3, "drifted"), (1, "sorted"), (2, "sorted"), (3, "relativistic")])
 def test_deposit_variants_match_oracle(orc, dev, mode, nox, kind):
     if mode in (5, 6) and nox != 3:

@@ -61,7 +61,7 @@ def test_periodic_loop_on_the_host_matches_oracle(orc, HostSimulation):
     assert e == pytest.approx(eo, rel=1e-10)
 
 
-@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2])
+@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2, abi.PIC_DEPOSIT_CELLS3])
 def test_order3_loop_with_lane_per_cell_deposition_on_the_host_matches_oracle(orc, HostSimulation, mode):
     """Config 2 in the small (16^3, 8 ppc, order 3, hot enough that particles cross cell faces every step): nine steps of
     the C++ driver with pic_set_deposit_mode(PIC_DEPOSIT_CELLS) -- slices, extra rounds for the particles that left the

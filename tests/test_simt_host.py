@@ -197,7 +197,7 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, nox):
     (1, (12, 8, 10), (1, 1, 1), 0.3, "odd"),
     (3, (8, 8, 8), (2, 2, 2), 0.02, "tail"),          # particles appended behind the binned range
 ])
-@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2])
+@pytest.mark.parametrize("mode", [abi.PIC_DEPOSIT_CELLS, abi.PIC_DEPOSIT_CELLS2, abi.PIC_DEPOSIT_CELLS3])
 def test_deposit_cells_kernel_under_simt_emulation(orc, nox, n, ppc, u_th, kind, mode):
     from host_harness import harness
     hl = harness.host_library()

@@ -40,6 +40,7 @@ def main():
     ref = run(32, 7, fdtd=0, deposit=0)
     for name, modes in (("fdtd bulk staging", dict(fdtd=3, deposit=0)), ("deposit lane-per-cell", dict(fdtd=0, deposit=7)),
                         ("deposit lane-per-cell, 2 producers", dict(fdtd=0, deposit=8)), ("the same, wide", dict(fdtd=0, deposit=9)),
+                        ("decoupled pipeline", dict(fdtd=0, deposit=10)), ("decoupled pipeline, wide", dict(fdtd=0, deposit=11)),
                         ("gather pairs", dict(fdtd=0, deposit=0, gather=1)), ("all three", dict(fdtd=3, deposit=7, gather=1))):
         got = run(32, 7, **modes)
         err = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) for a, b in zip(got[:3] + got[6:], ref[:3] + ref[6:]))

@@ -77,8 +77,8 @@ using namespace pic;
 
 extern "C" void pic_set_deposit_mode(int mode) {
     g_deposit_mode = mode;
-    g_cells_two_producers = (mode == PIC_DEPOSIT_CELLS2) ? 1 : (mode == PIC_DEPOSIT_CELLS2_WIDE) ? 2 : 0;
-    if (mode == PIC_DEPOSIT_CELLS2 || mode == PIC_DEPOSIT_CELLS2_WIDE) g_deposit_mode = PIC_DEPOSIT_CELLS;
+    g_cells_two_producers = (mode >= PIC_DEPOSIT_CELLS2 && mode <= PIC_DEPOSIT_CELLS3_WIDE) ? mode - PIC_DEPOSIT_CELLS2 + 1 : 0;
+    if (g_cells_two_producers) g_deposit_mode = PIC_DEPOSIT_CELLS;
     g_runs_variant = (mode == PIC_DEPOSIT_RUNS2) ? 1 : (mode == PIC_DEPOSIT_RUNS_SLOTRED) ? 2 : (mode == PIC_DEPOSIT_RUNS2_SLOTRED) ? 3
                    : (mode == PIC_DEPOSIT_RUNS4) ? 4 : (mode == PIC_DEPOSIT_RUNS4_SLOTRED) ? 6 : 0;
 }

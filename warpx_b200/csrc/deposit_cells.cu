@@ -172,11 +172,11 @@ template <int N> struct CellsProducer {
         *reinterpret_cast<int2*>(&r[T::F_META * 32]) = make_int2(0, 0);
     }
     // A particle that is not simple: every sub-particle into the queue (returns false: no room / outside -> the list)
-    __device__ __forceinline__ bool enqueue(const CellsPart<N>& q, long ip, int2* queue, int* q_count) const {
+    __device__ __forceinline__ bool enqueue(const CellsPart<N>& q, long ip, int2* queue, int* q_count, int qcap = T::QCAP) const {
         if (!q.inside) return false;
         const int nq = (q.sh[0] ? 2 : 1) * (q.sh[1] ? 2 : 1) * (q.sh[2] ? 2 : 1);
         int slot = atomicAdd(q_count, nq);
-        if (slot + nq > T::QCAP) {           // queue full: the whole particle goes to the list
+        if (slot + nq > qcap) {              // queue full: the whole particle goes to the list
             atomicMin(q_count + 1, slot);    // later requests start beyond: they do not fit either
             return false;
         }
@@ -284,7 +284,9 @@ template <int N> struct CellsConsumer {
     // extra round: every lane carries one sub-particle of ITS OWN cell (distinct cells within the round): add at the
     // record's anchor, one stencil offset at a time (the cells differ in every direction now, so every step is ordered)
     __device__ __forceinline__ void retire_extra(const double2* r) {
-        const int2 mt = *reinterpret_cast<const int2*>(&r[T::F_META * 32]);
+        retire_extra_at(*reinterpret_cast<const int2*>(&r[T::F_META * 32]));
+    }
+    __device__ __forceinline__ void retire_extra_at(const int2 mt) {      // mt = {active, offset of the anchor cell}
         double* base = tl + mt.y;
         const bool active = mt.x != 0;
 #pragma unroll
@@ -609,11 +611,195 @@ deposit_cells2_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom 
     cells_flush<N, 160>(tile, bins, tc, Jp);
 }
 
+// ==================================================================================================================
+// Two producers, three consumers, DECOUPLED (160 threads): no per-item __syncthreads.  Three record slots; producer and
+// consumers meet on mbarriers -- full[slot] (32 producer lanes arrive after their stores), empty[slot] (96 consumer lanes
+// arrive after their loads).  A producer computes an item (loads, geometry, shape factors, classification) BEFORE it
+// waits for its slot, so a load stall of one warp no longer stalls the others; the consumers take the items in order.
+// Items k = 0 .. K-1 are the slices (owner k mod 2), then producer 0 alone produces the extra rounds (it waits on
+// `bdone` until producer 1 has classified its last slice: the queue is complete) and the END item.
+// ==================================================================================================================
+#ifdef PIC_SIMT_HOST      // tests/host_harness: a counter the fibers poll cooperatively
+struct DcBar { int count, arrived, phase, pad; };
+__device__ __forceinline__ void dc_bar_init(DcBar* b, int count) { b->count = count; b->arrived = 0; b->phase = 0; }
+__device__ __forceinline__ void dc_bar_fence_init() {}
+__device__ __forceinline__ void dc_bar_arrive(DcBar* b) { if (++b->arrived == b->count) { b->arrived = 0; b->phase ^= 1; } }
+__device__ __forceinline__ void dc_bar_wait(DcBar* b, int parity) { while (b->phase == parity) ::simt::yield(); }
+#else
+struct DcBar { unsigned long long v, pad; };
+__device__ __forceinline__ unsigned dc_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dc_bar_init(DcBar* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dc_smem(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dc_bar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void dc_bar_arrive(DcBar* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(dc_smem(b)) : "memory");
+}
+__device__ __forceinline__ void dc_bar_wait(DcBar* b, int parity) {      // returns when the phase of that parity is complete
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(dc_smem(b)), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();       // a protocol bug must end the kernel with an error, not hang the device
+    }
+}
+#endif
+
+template <int N> struct Cells3Cfg {
+    using T = CellsCfg<N>;
+    static constexpr int NB = 3;                   // record slots
+    static constexpr int QCAP = 512;
+    static constexpr size_t smem_bytes = sizeof(double2) * NB * T::NF * 32 + sizeof(double) * 3 * T::TS + sizeof(int2) * QCAP +
+                                         sizeof(CellsHeader) * NB + sizeof(DcBar) * (2 * NB + 1) + 16;
+};
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(160, MINB)
+deposit_cells3_kernel(SoaView P, long np_lim, BinsView bins, J3 Jp, DepositGeom dg,
+                      int* __restrict__ list, int* __restrict__ list_count) {
+    using T = CellsCfg<N>;
+    using T3 = Cells3Cfg<N>;
+    constexpr int NF = T::NF, PX = T::PX, PY = T::PY, TS = T::TS, NB = T3::NB;
+    PIC_DYNAMIC_SMEM(double2, smem2);
+    double2* rec = smem2;                                                  // [NB][NF][32]
+    double* tile = reinterpret_cast<double*>(smem2 + NB * NF * 32);        // [3][TS]
+    int2* queue = reinterpret_cast<int2*>(tile + 3 * TS);                  // [QCAP]
+    CellsHeader* hdr = reinterpret_cast<CellsHeader*>(queue + T3::QCAP);   // [NB]
+    DcBar* full = reinterpret_cast<DcBar*>(hdr + NB);                      // [NB]
+    DcBar* empty = full + NB;                                              // [NB]
+    DcBar* bdone = empty + NB;
+    int* q_count = reinterpret_cast<int*>(bdone + 1);                      // [0] requested, [1] first slot that did not fit
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = (warp + blockIdx.x) % 5;            // 0, 1 producers (even / odd slices), 2..4 consumers
+    int tc[3];
+    tile_coords(bins, blockIdx.x, tc);
+    const long bin0 = (long)blockIdx.x * (T::T * T::T * T::T);
+    const int lx = lane & 7, rsel = lane >> 3, lrow = ((rsel & 1) << 1) | (rsel >> 1);
+
+    for (int n = threadIdx.x; n < 3 * TS; n += 160) tile[n] = 0.0;
+    for (int n = threadIdx.x; n < NB * NF * 32; n += 160) rec[n] = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) {
+        q_count[0] = 0; q_count[1] = T3::QCAP;
+        for (int b = 0; b < NB; ++b) { dc_bar_init(full + b, 32); dc_bar_init(empty + b, 96); }
+        dc_bar_init(bdone, 32);
+        dc_bar_fence_init();
+    }
+    __syncthreads();
+
+    if (role < 2) {
+        // ============================== producer ==============================
+        CellsProducer<N> pr{P, dg, {tc[0] * T::T + bins.box_lo[0] - dg.lo[0] + T::O0, tc[1] * T::T + bins.box_lo[1] - dg.lo[1] + T::O0,
+                                    tc[2] * T::T + bins.box_lo[2] - dg.lo[2] + T::O0}, list, list_count, lane};
+        // hand an item over: wait until the consumers have released the slot's previous use, store, publish
+        auto slot_of = [&](int k) -> double2* {
+            const int slot = k % NB, use = k / NB;
+            if (use >= 1) dc_bar_wait(empty + slot, (use - 1) & 1);
+            return rec + (size_t)slot * NF * 32 + lane;
+        };
+        auto publish = [&](int k, int kind, int retire, int g) {
+            const int slot = k % NB;
+            if (lane == 0) hdr[slot] = CellsHeader{kind, retire, g, 0};
+            dc_bar_arrive(full + slot);
+        };
+        CellsGroup<N> G;
+        int g = -1, s = 0, k = 0;
+        bool slices_left = true;
+        auto next_group = [&]() {
+            while (true) {
+                if (++g >= 16) { slices_left = false; return; }
+                G.load(bins, bin0, np_lim, g, lx, lrow);
+                if (G.maxn > 0) { s = 0; return; }
+            }
+        };
+        auto step = [&]() { if (slices_left) { ++k; if (++s >= G.maxn) next_group(); } };
+        next_group();
+        if (role == 1) step();
+        double pf[7] = {0, 0, 0, 0, 0, 0, 0};
+        bool pf_ok = false;
+        // ---------------- this producer's slices ----------------
+        while (slices_left) {
+            const bool valid = s < G.n;
+            const long ip = (long)G.p0 + s;
+            double v7[7];
+            if (pf_ok) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) v7[c] = pf[c];
+            } else if (valid) pr.load(ip, v7);
+            else { v7[0] = v7[1] = v7[2] = v7[3] = v7[4] = v7[5] = v7[6] = 0.0; }
+            pf_ok = s + 2 < G.maxn;                      // this producer's next slice belongs to the same group
+            if (s + 2 < G.n) pr.load(ip + 2, pf);
+            bool listed = false, send = false;
+            CellsPart<N> q;
+            if (valid) {
+                pr.compute(v7, q);
+                if (pr.simple(q, G.lc)) send = true;
+                else listed = !pr.enqueue(q, ip, queue, q_count, T3::QCAP);
+            }
+            pr.to_list(listed, ip);
+            double2* r = slot_of(k);
+            if (send) pr.emit_simple(q, r); else pr.emit_nothing(r);
+            publish(k, DC_SLICE, s == G.maxn - 1 ? 1 : 0, g);
+            step(); step();
+        }
+        if (role == 1) {
+            dc_bar_arrive(bdone);                        // every slice of producer 1 is classified: the queue is complete
+        } else {
+            // ---------------- producer 0: the extra rounds, then END; item numbers continue at k = number of slices ----------------
+            dc_bar_wait(bdone, 0);
+            const int nq_total = min(q_count[0], q_count[1]);
+            for (int qb = 0; qb < nq_total; qb += 32) {
+                bool pend = qb + lane < nq_total;
+                const int2 e = pend ? queue[qb + lane] : make_int2(0, 0);
+                while (__ballot_sync(DC_FULL, pend)) {
+                    const unsigned m = __match_any_sync(DC_FULL, pend ? ((e.y >> 3) & 511) : 512 + lane);
+                    const bool go = pend && lane == __ffs(m) - 1;
+                    CellsPart<N> q;
+                    if (go) {
+                        double v7[7];
+                        pr.load(e.x, v7);
+                        pr.compute(v7, q);
+                    }
+                    double2* r = slot_of(k);
+                    if (go) {
+                        const int v[3] = {e.y & 1, (e.y >> 1) & 1, (e.y >> 2) & 1};
+                        pr.emit(q, v, r, 1, ((e.y >> 3) & 7) + PX * (((e.y >> 6) & 7) + PY * ((e.y >> 9) & 7)));
+                    } else pr.emit_nothing(r);
+                    publish(k, DC_EXTRA, 1, 0);
+                    ++k;
+                    pend = pend && !go;
+                }
+            }
+            slot_of(k);
+            publish(k, DC_END, 0, 0);
+        }
+    } else {
+        // ============================== consumer of component role - 2 ==============================
+        CellsConsumer<N> co;
+        co.init(role - 2, tile, lx, lrow);
+        for (int k = 0;; ++k) {
+            const int slot = k % NB;
+            dc_bar_wait(full + slot, (k / NB) & 1);
+            const CellsHeader h = hdr[slot];
+            if (h.kind == DC_END) break;
+            const double2* r = rec + (size_t)slot * NF * 32 + lane;
+            co.consume(r);
+            int2 mt = make_int2(0, 0);
+            if (h.kind == DC_EXTRA) mt = *reinterpret_cast<const int2*>(&r[T::F_META * 32]);
+            dc_bar_arrive(empty + slot);                 // the record is in registers: the slot may be refilled
+            if (h.kind == DC_SLICE) { if (h.retire) co.retire_group(h.g); }
+            else co.retire_extra_at(mt);
+        }
+    }
+    __syncthreads();
+    cells_flush<N, 160>(tile, bins, tc, Jp);
+}
+
 // deposit_runs.cu: the listed particles (full stencil)
 int deposit_general_launch(SoaView P, const int* list, const int* list_count, const pic_fab J[3], const DepositGeom& dg,
                            int nox, cudaStream_t s);
 
-int g_cells_two_producers = 0;      // 1: PIC_DEPOSIT_CELLS2 (three CTAs per SM, 128 registers), 2: PIC_DEPOSIT_CELLS2_WIDE (two CTAs)
+int g_cells_two_producers = 0;      // 1: PIC_DEPOSIT_CELLS2 (three CTAs per SM, 128 registers), 2: PIC_DEPOSIT_CELLS2_WIDE (two CTAs),
+                                    // 3 / 4: PIC_DEPOSIT_CELLS3 / _WIDE (decoupled pipeline)
 
 template <int N>
 static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeom& dg, const pic_bins* pb, cudaStream_t s) {
@@ -626,19 +812,21 @@ static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeo
     J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
     constexpr int MINB = 3;
     const int two = g_cells_two_producers;
-    auto k = two == 2 ? deposit_cells2_kernel<N, 2> : two == 1 ? deposit_cells2_kernel<N, MINB> : deposit_cells_kernel<N, MINB>;
+    auto k = two == 4 ? deposit_cells3_kernel<N, 2> : two == 3 ? deposit_cells3_kernel<N, MINB>
+           : two == 2 ? deposit_cells2_kernel<N, 2> : two == 1 ? deposit_cells2_kernel<N, MINB> : deposit_cells_kernel<N, MINB>;
     const int nthreads = two ? 160 : 128;
+    const size_t smem_bytes = two >= 3 ? Cells3Cfg<N>::smem_bytes : T::smem_bytes;
 #ifndef PIC_SIMT_HOST
     int* scratch = nullptr;
     if (cudaMallocAsync((void**)&scratch, sizeof(int) * (size_t)(np + 1), s) != cudaSuccess)
         return fail("pic_deposit_esirkepov: cannot allocate %ld B of scratch", (long)(sizeof(int) * (np + 1)));
     cudaMemsetAsync(scratch, 0, sizeof(int), s);
-    static bool attr_done[3] = {false, false, false};
+    static bool attr_done[5] = {false, false, false, false, false};
     if (!attr_done[two]) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::smem_bytes);
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         attr_done[two] = true;
     }
-    k<<<grid, nthreads, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
+    k<<<grid, nthreads, smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
     count_launch();
     int rc = check_launch("pic_deposit_esirkepov(cells)") ? 0 : 1;
     if (!rc) rc = deposit_general_launch(P, scratch + 1, scratch, J, dg, N, s);
@@ -647,7 +835,7 @@ static int launch_cells(SoaView P, long np, const pic_fab J[3], const DepositGeo
 #else
     std::vector<int> scratch_h((size_t)np + 1, 0);
     int* scratch = scratch_h.data();
-    k<<<grid, nthreads, T::smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
+    k<<<grid, nthreads, smem_bytes, s>>>(P, np_lim, bins, j3, dg, scratch + 1, scratch);
     return deposit_general_launch(P, scratch + 1, scratch, J, dg, N, s);
 #endif
 }
