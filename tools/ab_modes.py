@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8, help="timed steps per variant (a multiple of the sort interval)")
     ap.add_argument("--u-th", type=float, default=0.01)
     ap.add_argument("--jitter", action="store_true", help="random in-cell positions (the steady state of the lattice)")
+    ap.add_argument("--fresh", action="store_true", help="a new Simulation per variant: stage times on the FRESH state "
+                    "(steps 4..12 after the upload) instead of one long-running state")
     ap.add_argument("--deposit-modes", default="0,7,2,5,6")
     ap.add_argument("--gather-modes", default="0,1,2,3")
     args = ap.parse_args()
@@ -59,6 +61,27 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    if args.fresh:
+        out = {"cells": n, "ppc": args.ppc ** 3, "steps": args.steps, "fresh": True, "variants": []}
+        for d in (int(v) for v in args.deposit_modes.split(",")):
+            for g in (int(v) for v in args.gather_modes.split(",")):
+                L.pic_set_deposit_mode(d)
+                L.pic_set_gather_mode(g)
+                sim = make(True)
+                sim.Evolve(4, synchronize_last=False)
+                sim.enable_stage_timing(True)
+                ms = timed(sim, args.steps)
+                st = {k: t[0] for k, t in sim.stage_ms().items()}
+                sim.close()
+                del sim
+                torch.cuda.empty_cache()
+                out["variants"].append({"deposit_mode": d, "gather_mode": g, "ms_per_step": ms, "stage_ms": st})
+                print("fresh: deposit_mode %d gather_mode %d : %7.2f ms/step   gather %6.2f  deposit %6.2f" %
+                      (d, g, ms, st.get("gather_push", float("nan")), st.get("deposit", float("nan"))), file=sys.stderr)
+        L.pic_set_deposit_mode(0)
+        L.pic_set_gather_mode(0)
+        print(json.dumps(out, indent=1))
+        return
     combos = [(d, 0) for d in (int(v) for v in args.deposit_modes.split(","))] + \
              [(0, g) for g in (int(v) for v in args.gather_modes.split(",")) if g]
     out = {"cells": n, "ppc": args.ppc ** 3, "steps": args.steps, "variants": []}
