@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8, help="timed steps per variant (a multiple of the sort interval)")
     ap.add_argument("--u-th", type=float, default=0.01)
     ap.add_argument("--jitter", action="store_true", help="random in-cell positions (the steady state of the lattice)")
+    ap.add_argument("--sort-intervals", default="", help="comma list: steady-state ms/step for each cell-sort interval "
+                    "(64 spin-up steps, then 16 timed), default kernels")
     ap.add_argument("--fresh", action="store_true", help="a new Simulation per variant: stage times on the FRESH state "
                     "(steps 4..12 after the upload) instead of one long-running state")
     ap.add_argument("--deposit-modes", default="0,7,2,5,6")
@@ -61,6 +63,23 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    if args.sort_intervals:
+        out = {"cells": n, "ppc": args.ppc ** 3, "sort_intervals": []}
+        for si in (int(v) for v in args.sort_intervals.split(",")):
+            sim = Simulation((n, n, n), wl["prob_lo"], wl["prob_hi"], nox=3, sort_interval=si)
+            sim.add_species("electrons", s["q"], s["m"], *[torch.from_numpy(s[k]) for k in names])
+            sim.Evolve(64, synchronize_last=False)
+            sim.enable_stage_timing(True)
+            ms = timed(sim, 16)
+            st = {k: (t[0], t[1]) for k, t in sim.stage_ms().items()}
+            sim.close()
+            del sim
+            torch.cuda.empty_cache()
+            out["sort_intervals"].append({"sort_interval": si, "ms_per_step": ms, "stage_ms": st})
+            print("sort every %2d steps : %7.2f ms/step   gather %6.2f  deposit %6.2f  sort %5.2f x %d" %
+                  (si, ms, st["gather_push"][0], st["deposit"][0], st.get("sort", (0, 0))[0], st.get("sort", (0, 0))[1]), file=sys.stderr)
+        print(json.dumps(out, indent=1))
+        return
     if args.fresh:
         out = {"cells": n, "ppc": args.ppc ** 3, "steps": args.steps, "fresh": True, "variants": []}
         for d in (int(v) for v in args.deposit_modes.split(",")):
