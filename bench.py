@@ -437,7 +437,7 @@ def main():
                     help="warpx.use_filter: bilinear current filter, 1 pass.  Off by default: SURVEY.md 8(d) "
                          "fixes use_filter = 0 for the benchmark configurations; --filter 1 measures the "
                          "reference's own default (WarpX.cpp:158)")
-    ap.add_argument("--deposit-mode", type=int, default=0, choices=list(range(13)),
+    ap.add_argument("--deposit-mode", type=int, default=0, choices=list(range(12)),
                     help="pic_set_deposit_mode: 0 register runs, 1 shared-memory tile block, 2 two lines per "
                          "lane, 3 per-slot reductions, 4 both, 5 four lines per lane, 6 four lines + per-slot reductions, "
                          "7 one lane per cell (every mode passes the parity tests)")

@@ -237,8 +237,7 @@ int pic_deposit_esirkepov(const pic_soa* p, long offset, long np,
 enum { PIC_DEPOSIT_RUNS = 0, PIC_DEPOSIT_TILE = 1, PIC_DEPOSIT_RUNS2 = 2, PIC_DEPOSIT_RUNS_SLOTRED = 3,
        PIC_DEPOSIT_RUNS2_SLOTRED = 4, PIC_DEPOSIT_RUNS4 = 5, PIC_DEPOSIT_RUNS4_SLOTRED = 6, PIC_DEPOSIT_CELLS = 7,
        PIC_DEPOSIT_CELLS2 = 8, PIC_DEPOSIT_CELLS2_WIDE = 9 /* lane per cell with two producer warps (3 / 2 CTAs per SM) */,
-       PIC_DEPOSIT_CELLS3 = 10, PIC_DEPOSIT_CELLS3_WIDE = 11 /* the same, producers and consumers decoupled by mbarriers */,
-       PIC_DEPOSIT_RUNS_NOSPLIT = 12 /* PIC_DEPOSIT_RUNS as in round 1: every particle that changes cell takes the general kernel */ };
+       PIC_DEPOSIT_CELLS3 = 10, PIC_DEPOSIT_CELLS3_WIDE = 11 /* the same, producers and consumers decoupled by mbarriers */ };
 void pic_set_deposit_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------

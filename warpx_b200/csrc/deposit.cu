@@ -70,7 +70,6 @@ int deposit_cells_launch(const pic_soa* p, long offset, long np, const pic_fab J
 static int g_deposit_mode = PIC_DEPOSIT_RUNS;
 extern int g_runs_variant;      // deposit_runs.cu
 extern int g_cells_two_producers;   // deposit_cells.cu
-extern int g_split_movers;          // deposit_runs.cu
 
 }  // namespace pic
 
@@ -78,8 +77,6 @@ using namespace pic;
 
 extern "C" void pic_set_deposit_mode(int mode) {
     g_deposit_mode = mode;
-    g_split_movers = (mode == PIC_DEPOSIT_RUNS_NOSPLIT) ? 0 : 1;
-    if (mode == PIC_DEPOSIT_RUNS_NOSPLIT) g_deposit_mode = PIC_DEPOSIT_RUNS;
     g_cells_two_producers = (mode >= PIC_DEPOSIT_CELLS2 && mode <= PIC_DEPOSIT_CELLS3_WIDE) ? mode - PIC_DEPOSIT_CELLS2 + 1 : 0;
     if (g_cells_two_producers) g_deposit_mode = PIC_DEPOSIT_CELLS;
     g_runs_variant = (mode == PIC_DEPOSIT_RUNS2) ? 1 : (mode == PIC_DEPOSIT_RUNS_SLOTRED) ? 2 : (mode == PIC_DEPOSIT_RUNS2_SLOTRED) ? 3

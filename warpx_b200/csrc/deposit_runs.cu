@@ -35,7 +35,6 @@ namespace pic {
 // bit 0: two v-lines per lane where N+1 is even; bit 1: per-slot reductions instead of the shuffle fold;
 // bit 2: four v-lines per lane (order 3 only; 168 registers -> 3 CTAs of 4 warps per SM)
 int g_runs_variant = 0;
-int g_split_movers = 1;       // pic_set_deposit_mode(PIC_DEPOSIT_RUNS_NOSPLIT) switches the mover split off (A/B)
 
 constexpr int DR_CH = 32;          // particles per chunk
 constexpr int DR_CHP = DR_CH + 1;  // record pitch (odd: conflict-free column access)
@@ -89,7 +88,7 @@ __device__ __forceinline__ long fab_stride(const FabView& F, int d) { return d =
 template <int N, int NW, int MINB, int R0, int R1, int R2, int VL = 1, bool SLOTRED = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom dg, KeyBase kbp,
-                     int* __restrict__ list, int* __restrict__ list_count, int split_movers) {
+                     int* __restrict__ list, int* __restrict__ list_count) {
     // role views of the physical arrays / geometry
     const FabView& Jx = Jp.v[R0]; const FabView& Jy = Jp.v[R1]; const FabView& Jz = Jp.v[R2];
     const long stX = fab_stride(Jx, R0), stY = fab_stride(Jy, R1), stZ = fab_stride(Jz, R2);
@@ -251,18 +250,15 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
         const double xp = pf[0], yp = pf[1], zp = pf[2], wp = pf[3], uxp = pf[4], uyp = pf[5], uzp = pf[6];
         prefetch(ch + 1);
         // ---------------- phase 1: lane = particle ----------------
-        int key = -2, xkey = -2;
-        bool moved = false;          // goes to the list of the general kernel
-        bool split = false;          // changes cell along exactly one direction: two sub-particles of the quiet form
+        int key = -2;
+        bool moved = false;
         if (lane < nval) {
             const ParticleGeom pg = particle_geom(xp, yp, zp, wp, uxp, uyp, uzp, dg);
             double wn[3][N + 1], wo[3][N + 1];
             int inew[3], sh[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn[d], wo[d], sh[d]);
-            const int nmov = (sh[0] != 0) + (sh[1] != 0) + (sh[2] != 0);
-            moved = nmov != 0;
-            split = split_movers && nmov == 1 && (sh[0] | sh[1] | sh[2]) * (sh[0] | sh[1] | sh[2]) == 1;   // one of them is +-1
+            moved = (sh[0] != 0) || (sh[1] != 0) || (sh[2] != 0);
             if (!moved) {
                 key = pack_key(dg.lo[R0] + inew[R0] - 1, dg.lo[R1] + inew[R1] - 1, dg.lo[R2] + inew[R2] - 1, kb);
                 // slots 1..N+1 hold wn[0..N] (new) and wo[0..N] (old, no shift); role X/Y/Z = dir R0/R1/R2
@@ -298,81 +294,7 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                 key = -1;
             }
         }
-        // A particle that changes cell along ONE direction is exactly the sum of two stencils of the quiet form anchored
-        // at consecutive cells (window slots 0..N with prefix entries 0..N-1, and slot N+1 with prefix entry N: the same
-        // products as the full stencil, term by term).  The sub-particle anchored at the OLD cell takes the particle's
-        // own record column and joins the run of its cell; the one anchored at the new cell goes to one of the NX
-        // padding columns of the record block and is deposited like a lone particle.  Only what is left -- diagonal
-        // movers, more than NX movers in a chunk -- goes to the list of the general kernel.
-        constexpr int NX = (CHP - DR_CH) < 2 ? (CHP - DR_CH) : 2;
-        const unsigned smask = __ballot_sync(FULL, split);
-        int nsplit = 0;
-        if (smask) {
-            const int rank = __popc(smask & ((1u << lane) - 1u));
-            if (split && rank >= NX) split = false;
-            nsplit = min(__popc(smask), NX);
-            if (split) {
-                moved = false;
-                // the rare path recomputes the weights instead of keeping them live across the common one
-                const ParticleGeom pg = particle_geom(xp, yp, zp, wp, uxp, uyp, uzp, dg);
-                const double wq = pg.wq;
-                double wn[3][N + 1], wo[3][N + 1];
-                int inew[3], sh[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) inew[d] = dr_dir<N>(pg.pos_new[d], pg.pos_old[d], wn[d], wo[d], sh[d]);
-                const int dm = sh[0] ? 0 : (sh[1] ? 1 : 2);
-                const bool old_is_low = (sh[0] + sh[1] + sh[2]) < 0;     // sh = i_old - i_new: the window starts at the old cell
-                int alo[3];                                               // anchor of the LOW sub-particle
-#pragma unroll
-                for (int d = 0; d < 3; ++d) alo[d] = inew[d] + ((d == dm && old_is_low) ? -1 : 0);
-#pragma unroll
-                for (int which = 0; which < 2; ++which) {                 // 0: the old-cell sub-particle (own column), 1: the other
-                    const bool hi = (which == 0) ? !old_is_low : old_is_low;
-                    const int col = which == 0 ? lane : DR_CH + rank;
-                    double2 pr[3][QS];
-                    double cds[3 * QP + 1];
-                    cds[3 * QP] = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        constexpr int RR[3] = {R0, R1, R2};
-                        const int d = RR[r];
-                        const bool mv = d == dm, nsh = mv && sh[d] < 0, osh = mv && sh[d] > 0, h = mv && hi;
-                        const double wqd = wq * dg.invdtd[d];
-                        double run = 0.0;
-#pragma unroll
-                        for (int s2 = 0; s2 <= N; ++s2) {
-                            const double n5 = nsh ? (s2 >= 1 ? wn[d][s2 >= 1 ? s2 - 1 : 0] : 0.0) : wn[d][s2];
-                            const double o5 = osh ? (s2 >= 1 ? wo[d][s2 >= 1 ? s2 - 1 : 0] : 0.0) : wo[d][s2];
-                            run += wqd * (o5 - n5);
-                            if (s2 < QP) cds[r * QP + s2] = h ? 0.0 : run;
-                            pr[r][s2] = h ? make_double2(0.0, 0.0) : make_double2(n5, o5);
-                        }
-                        if (h) {      // window slot N+1 and prefix entry N, at the local positions N and N-1 of the next cell
-                            pr[r][N] = make_double2(nsh ? wn[d][N] : 0.0, osh ? wo[d][N] : 0.0);
-                            cds[r * QP + QP - 1] = run;
-                        }
-                    }
-#pragma unroll
-                    for (int s2 = 0; s2 < QS; ++s2) {
-                        rec[(T::F_SX + s2) * CHP + col] = pr[0][s2];
-                        rec[(T::F_SY + s2) * CHP + col] = pr[1][s2];
-                        rec[(T::F_ABY + s2) * CHP + col] = make_double2((1.0 / 3.0) * pr[1][s2].x + (1.0 / 6.0) * pr[1][s2].y,
-                                                                        (1.0 / 3.0) * pr[1][s2].y + (1.0 / 6.0) * pr[1][s2].x);
-                        rec[(T::F_ABZ + s2) * CHP + col] = make_double2((1.0 / 3.0) * pr[2][s2].x + (1.0 / 6.0) * pr[2][s2].y,
-                                                                        (1.0 / 3.0) * pr[2][s2].y + (1.0 / 6.0) * pr[2][s2].x);
-                    }
-#pragma unroll
-                    for (int m = 0; m < T::NCDS; ++m)
-                        rec[(T::F_CDS + m) * CHP + col] = make_double2(cds[2 * m], cds[2 * m + 1]);
-                    int an[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) an[d] = alo[d] + ((d == dm && hi) ? 1 : 0);
-                    const int kk = pack_key(dg.lo[R0] + an[R0] - 1, dg.lo[R1] + an[R1] - 1, dg.lo[R2] + an[R2] - 1, kb);
-                    if (which == 0) key = kk; else xkey = kk;
-                }
-            }
-        }
-        // what is left of the particles that changed cell: append to the list (warp-aggregated)
+        // particles that changed cell: append to the list (warp-aggregated)
         {
             const unsigned mm = __ballot_sync(FULL, moved);
             if (mm) {
@@ -380,16 +302,6 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                 if (lane == 0) basei = atomicAdd(list_count, __popc(mm));
                 basei = __shfl_sync(FULL, basei, 0);
                 if (moved) list[basei + __popc(mm & ((1u << lane) - 1u))] = (int)(base + lane);
-            }
-        }
-        // keys of the padding columns: column DR_CH + e belongs to the e-th split lane
-        int ekey[2] = {-2, -2};
-#pragma unroll
-        for (int e2 = 0; e2 < 2; ++e2) {
-            if (e2 < nsplit) {
-                unsigned m2 = smask;
-                for (int q2 = 0; q2 < e2; ++q2) m2 &= m2 - 1;            // drop the e2 lowest set bits
-                ekey[e2] = __shfl_sync(FULL, xkey, __ffs(m2) - 1);
             }
         }
         __syncwarp();
@@ -446,8 +358,6 @@ deposit_quiet_kernel(SoaView P, long np, int chunks_per_warp, J3 Jp, DepositGeom
                 if (active_q)
                     for (int pq = start + g; pq < end; pq += NG) accumulate(pq);
             }
-            // the new-cell halves of the split movers of this chunk
-            for (int e2 = 0; e2 < nsplit; ++e2) deposit_lone(ekey[e2], DR_CH + e2);
         }
         __syncwarp();
     }
@@ -653,7 +563,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     const long nwarps = (nchunks + cpw - 1) / cpw;
     const unsigned grid_q = (unsigned)((nwarps + NWQ - 1) / NWQ);
     J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
-    kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
+    kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, j3, dg, kb, list, list_count);
     kg<<<NUM_SMS, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
     count_launch(2);
     cudaFreeAsync(scratch, s);
@@ -680,12 +590,12 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     const FabView v0 = make_view(J[0]), v1 = make_view(J[1]), v2 = make_view(J[2]);
     (void)s;
     ::simt::launch(dim3(grid_q), dim3(NWQ * 32), smem_q, [&] {
-        if (four && slotred) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, true>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
-        else if (four) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, false>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
-        else if (two && slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
-        else if (two) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
-        else if (slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
-        else deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>(P, np, cpw, j3, dg, kb, list, list_count, g_split_movers);
+        if (four && slotred) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (four) deposit_quiet_kernel<N, NWQ, 3, 0, 1, 2, VL4, false>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (two && slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (two) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, VL2, false>(P, np, cpw, j3, dg, kb, list, list_count);
+        else if (slotred) deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, true>(P, np, cpw, j3, dg, kb, list, list_count);
+        else deposit_quiet_kernel<N, NWQ, MINB, 0, 1, 2, 1, false>(P, np, cpw, j3, dg, kb, list, list_count);
     });
     ::simt::launch(dim3(4), dim3(NWG * 32), smem_g,
                    [&] { deposit_general_kernel<N, NWG>(P, list, list_count, v0, v1, v2, dg, kb); });
