@@ -380,7 +380,7 @@ template <int N> struct GeneralCfg {
 };
 
 template <int N, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 3 : 1))
 deposit_general_kernel(SoaView P, const int* __restrict__ list, const int* __restrict__ list_count,
                        FabView Jx, FabView Jy, FabView Jz, DepositGeom dg, KeyBase kb) {
     using T = GeneralCfg<N>;
@@ -506,7 +506,7 @@ deposit_general_kernel(SoaView P, const int* __restrict__ list, const int* __res
 
 template <int N>
 static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom& dg, cudaStream_t s) {
-    constexpr int NWQ = 4, MINB = 4, NWG = 8;
+    constexpr int NWQ = 4, MINB = 4, NWG = 4;        // general kernel: 4 warps x 3 CTAs per SM (was 8 x 1: latency bound)
     using TQ = QuietCfg<N>;
     using TG = GeneralCfg<N>;
     for (int d = 0; d < 3; ++d)
@@ -564,7 +564,7 @@ static int launch_runs(SoaView P, long np, const pic_fab J[3], const DepositGeom
     const unsigned grid_q = (unsigned)((nwarps + NWQ - 1) / NWQ);
     J3 j3; j3.v[0] = make_view(J[0]); j3.v[1] = make_view(J[1]); j3.v[2] = make_view(J[2]);
     kq<<<grid_q, NWQ * 32, smem_q, s>>>(P, np, cpw, j3, dg, kb, list, list_count);
-    kg<<<NUM_SMS, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
+    kg<<<NUM_SMS * 3, NWG * 32, smem_g, s>>>(P, list, list_count, make_view(J[0]), make_view(J[1]), make_view(J[2]), dg, kb);
     count_launch(2);
     cudaFreeAsync(scratch, s);
     return check_launch("pic_deposit_esirkepov(runs)") ? 0 : 1;
