@@ -148,7 +148,8 @@ def host_library():
     global _HOST
     if _HOST is None:
         from warpx_b200 import lib as piclib
-        L = piclib.bind(C.CDLL(build_host_library()))
+        # PIC_HOST_LIBRARY: a differently built copy (e.g. -fsanitize=address, see tools/host_asan.sh)
+        L = piclib.bind(C.CDLL(os.environ.get("PIC_HOST_LIBRARY") or build_host_library()))
         L.pic_set_error_mode(abi.PIC_ERR_RETURN)
         _HOST = L
     return _HOST

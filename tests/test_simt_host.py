@@ -185,6 +185,36 @@ def test_order_agnostic_kernels_under_simt_emulation(orc, nox):
                 assert rel_linf(getattr(B, k), getattr(A, k)) <= 1e-13, (galerkin, pusher, k)
 
 
+def test_weightless_particles_outside_the_fab_deposit_nothing(orc):
+    """The antenna of a multi-rank run is replicated on every rank with zero weights outside the owning brick
+    (engine.cu, lasers): such particles lie far outside the rank's J fabs and must not be turned into addresses.
+    (Found on 4 GPUs: the zero adds of the three non-owning slabs went out of bounds.)"""
+    from host_harness import harness
+    hl = harness.host_library()
+    n, lx, nox = (8, 6, 6), (4e-6, 3e-6, 3e-6), 3
+    wl = workloads.uniform_plasma_3d(n_cell=n, ppc=(1, 1, 1), u_th=0.1, lx=lx, seed=4)
+    s = wl["species"][0]
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / n[d] for d in range(3)]
+    dinv = [1.0 / v for v in dx]
+    dt = 0.95 / (np.sqrt(sum(1.0 / v ** 2 for v in dx)) * workloads.C)
+    box_hi = tuple(v - 1 for v in n)
+    ngJ = (nox + 2,) * 3
+    xyzmin, lo = lower_corner(wl["prob_lo"], dx, (0, 0, 0), ngJ)
+    real = {k: s[k] for k in orc.HostParticles.NAMES}
+    ghost = {k: np.concatenate([s[k], s[k][:16]]) for k in orc.HostParticles.NAMES}
+    ghost["z"][-16:] += 3.0e6 * dx[2]                 # three million cells above the box
+    ghost["w"][-16:] = 0.0
+    P, G = orc.HostParticles(**real), orc.HostParticles(**ghost)
+    J = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    K = [orc.HostFab((0, 0, 0), box_hi, ngJ, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    assert orc.lib().orc_deposit_esirkepov(C.byref(P.soa), 0, P.np, orc.fab_array(J), abi.dbl3(dinv), abi.dbl3(xyzmin),
+                                           abi.int3(lo), s["q"], dt, -0.5 * dt, nox) == 0
+    assert hl.pic_deposit_esirkepov(C.byref(G.soa), 0, G.np, orc.fab_array(K), abi.dbl3(dinv), abi.dbl3(xyzmin), abi.int3(lo),
+                                    s["q"], dt, -0.5 * dt, nox, None, None) == 0, hl.pic_last_error()
+    for c in range(3):
+        assert rel_linf(K[c].a, J[c].a) <= 1e-13, "j" + "xyz"[c]
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the lane-per-cell deposition kernel of warpx_b200/csrc/deposit_cells.cu (PIC_DEPOSIT_CELLS) under the emulator
 # ---------------------------------------------------------------------------------------------------------

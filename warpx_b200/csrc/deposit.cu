@@ -23,9 +23,19 @@ __global__ void __launch_bounds__(128)
 deposit_global(SoaView P, long np, FabView Jx, FabView Jy, FabView Jz, DepositGeom dg) {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= np) return;
+    // a weightless particle deposits nothing and is not required to lie inside the fab: the replicated antenna of a
+    // multi-rank run carries zero weights outside the brick that owns each particle (engine.cu, lasers)
+    if (P.w[ip] == 0.0) return;
     EsirkepovWeights<N> ew;
     ew.compute(P.x[ip], P.y[ip], P.z[ip], P.w[ip], P.ux[ip], P.uy[ip], P.uz[ip], dg);
     const int bi = dg.lo[0] + ew.i_new - 1, bj = dg.lo[1] + ew.j_new - 1, bk = dg.lo[2] + ew.k_new - 1;
+#ifdef PIC_DEBUG_BOUNDS
+    if (bi < Jx.lo0 || bi + N + 2 >= Jx.lo0 + Jx.n0 || bj < Jx.lo1 || bj + N + 2 >= Jx.lo1 + Jx.n1 || bk < Jx.lo2 ||
+        bk + N + 2 >= Jx.lo2 + Jx.n2)
+        printf("deposit_global: ip %ld of %ld base %d %d %d fab lo %d %d %d n %d %d %d  x %.17g %.17g %.17g u %g %g %g w %g xyzmin %g %g %g\n",
+               ip, np, bi, bj, bk, Jx.lo0, Jx.lo1, Jx.lo2, Jx.n0, Jx.n1, Jx.n2, P.x[ip], P.y[ip], P.z[ip], P.ux[ip], P.uy[ip], P.uz[ip], P.w[ip],
+               dg.xyzmin[0], dg.xyzmin[1], dg.xyzmin[2]);
+#endif
     constexpr double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
     // Same loop nests, trimming and accumulation order as CurrentDeposition.H:792-824.
     for (int k = ew.dkl; k <= N + 2 - ew.dku; ++k)
