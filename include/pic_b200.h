@@ -326,6 +326,21 @@ int pic_particles_classify(const pic_soa* p, const pic_geom* g, int dim, int cel
                                                 p->np is only an upper bound for the launch */,
                            void* stream);
 
+/* The same classification over a CANDIDATE list instead of every particle: `candidates` is the list the preceding
+ * pic_gather_push wrote with lo/hi set to the rank's brick (every particle that left the brick is in it; the periodic
+ * wrap has been applied since).  Entries that point behind the current particle count are dropped (set to -1: a tail
+ * particle that an earlier sweep moved into a hole is reached through the hole's entry).  When the list overflowed
+ * (count > capacity) every particle is visited, as pic_particles_classify does.  After pic_migrate_unpack,
+ * pic_migrate_note_appended adds the particles that sweep appended behind the old count (`work` = the unpack's
+ * workspace), so that the next axis sweep forwards arrivals that have to travel on (edges, corners).  Arrivals that
+ * filled holes need no entry: the holes are candidates already. */
+int pic_particles_classify_listed(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
+                                  int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
+                                  const int* np_dev, const pic_escape_list* candidates, void* stream);
+int pic_migrate_note_appended(const void* work, const pic_escape_list* candidates, void* stream);
+/* how many axis sweeps of this process classified from the candidate list (tests: the list path really ran) */
+long pic_engine_listed_sweeps(void);
+
 /* Neighbour migration, steps 2 and 3 (pack / unpack phases of Redistribute).  A message is
  * pic_migrate_message_doubles(cap) doubles: header (true particle count) + 8 rows of cap doubles
  * (x y z w ux uy uz id) -- a FIXED size, so the send/recv pair needs no count exchange.

@@ -30,7 +30,7 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     ok = True
-    sections = os.environ.get("PIC_CHECK_SECTIONS", "order3,lwfa").split(",")     # debugging: skip the slower sections
+    sections = os.environ.get("PIC_CHECK_SECTIONS", "order3,lwfa,boosted").split(",")     # debugging: skip the slower sections
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "warpx_checksums.json")))["test_3d_langmuir_multi"]
     L = oracle.lib()
 
@@ -155,6 +155,74 @@ def main():
             print(f"[lwfa z-slabs x{world}] particles {int(v[9 + 7])}: {'ok' if good else 'FAIL'}")
         simw.close()
         del simw
+    # ---------------- BASELINE.json configs[3] in the small: boosted-frame laser acceleration on z slabs ----------------
+    # (gamma_boost = 10, CKC, Vay, order 3, filter, Godfrey NCI corrector, PEC z, moving window, boosted antenna, electrons
+    #  + ions injected continuously) -- every rank runs the small single-box oracle and compares its own slab and its own
+    #  particles (by global id) with it.
+    if "boosted" in sections and 128 % world == 0 and 128 // world >= 17:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_oracle import make_lwfa_oracle, _nci_lines
+        from warpx_b200.engine import max_dt, nci_godfrey_stencils
+        from warpx_b200.lib import lib as piclib
+        wl = workloads.laser_acceleration_boosted_3d(use_fdtd_nci_corr=True)
+        dxb = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+        nci = nci_godfrey_stencils(piclib(), _nci_lines(), workloads.C * wl["cfl"] * max_dt(wl["solver"], dxb) / dxb[2])
+        simb = Simulation(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], dist=dist,
+                          solver=wl["solver"], pusher=wl["pusher"], use_filter=True, sort_interval=4, nb=(1, 1, world),
+                          boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]),
+                          moving_window=(wl["moving_window_dir"], wl["moving_window_v"]),
+                          gamma_boost=wl["gamma_boost"], nci_stencils=nci)
+        for sp in wl["species"]:
+            simb.add_plasma_species(sp["name"], sp["q"], sp["m"],
+                                    abi.make_injector(sp["ppc"], sp["bound_lo"], sp["bound_hi"], sp["density"], True),
+                                    capacity=16 * 16 * 200)
+        la = wl["lasers"][0]
+        simb.add_laser(abi.make_laser(la["position"], la["direction"], la["polarization"], la["wavelength"], la["e_max"],
+                                      la["waist"], la["duration"], la["t_peak"], la["focal_distance"]))
+        osim = make_lwfa_oracle(oracle, wl)
+        simb.Evolve(40)
+        osim.evolve(40)
+        torch.cuda.synchronize()
+        err, scale = [], []
+        for c in range(9):
+            d, a = simb.field_numpy(c)
+            od, oa = osim.fab(c)
+            sl = tuple(slice(od.ng[2 - ax] + simb.box_lo[2 - ax], od.ng[2 - ax] + simb.box_hi[2 - ax] + 1 + abi.YEE_STAG[c][2 - ax])
+                       for ax in range(3))
+            err.append(float(np.max(np.abs(a[d.valid_slices()] - oa[sl]))))
+            scale.append(float(np.max(np.abs(oa))))
+        perr, nmine = 0.0, 0
+        for isp in (0, 1):
+            A = simb.species_numpy(isp, sort_by_id=False)
+            B = osim.particles(isp)
+            ids = A["id"].astype(np.int64)
+            nmine += len(ids)
+            if len(ids):
+                assert ids.min() >= 0 and ids.max() < len(B["x"])
+                for k in ("x", "y", "z"):
+                    perr = max(perr, float(np.max(np.abs(A[k] - B[k][ids]))) / simb.dx[2])
+                for k in ("ux", "uy", "uz"):
+                    perr = max(perr, float(np.max(np.abs(A[k] - B[k][ids]))) / (10.0 * workloads.C))
+        ntotal = len(osim.particles(0)["x"]) + len(osim.particles(1)["x"])
+        t = torch.tensor(err + [perr], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([nmine], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        v = t.cpu().numpy()
+        if rank == 0:
+            for group in ((0, 1, 2), (3, 4, 5), (6, 7, 8)):
+                sg = max(scale[c] for c in group)
+                for c in group:
+                    good = sg > 0 and v[c] <= 1e-8 * sg
+                    ok &= good
+                    print(f"[boosted z-slabs x{world}] {abi.COMP_NAMES[c]}: max |difference to the single-box oracle| {v[c]:.3e} "
+                          f"of scale {sg:.3e}: {'ok' if good else 'FAIL'}")
+            good = v[9] <= 1e-9 and int(cnt.item()) == ntotal > 0
+            ok &= good
+            print(f"[boosted z-slabs x{world}] electrons + ions by id: {int(cnt.item())} of {ntotal} particles, "
+                  f"max difference {v[9]:.3e} (cells, 10 c): {'ok' if good else 'FAIL'}")
+        simb.close()
+        del simb
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")

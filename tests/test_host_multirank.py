@@ -89,8 +89,11 @@ def test_eight_bricks_order3_thermal_loop_matches_oracle(orc, hh):
         return dict(fields={c: sim.field_numpy(c) for c in range(9)}, box=(sim.box_lo, sim.box_hi),
                     moved=sim.species[0].np != mine)
 
+    swept = hh.host_library().pic_engine_listed_sweeps()
     res = hh.run_ranks(world, rank_fn)
     assert any(r["moved"] for r in res)
+    # the migration classified from the push's list of brick leavers (3 axis sweeps x 6 steps x 8 ranks), not by sweeping
+    assert hh.host_library().pic_engine_listed_sweeps() - swept == 3 * nsteps * world
     osim = orc.OracleSim(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=3, use_filter=True)
     osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
     osim.evolve(nsteps)
@@ -145,6 +148,60 @@ def test_z_slabs_with_moving_window_match_oracle(orc, hh, world):
     for k in ("ux", "uy", "uz"):
         a = np.concatenate([res[r]["parts"][k] for r in range(world)])[order]
         assert np.max(np.abs(a - B[k])) / workloads.C <= 1e-10, k
+
+
+def test_boosted_frame_z_slabs_match_oracle(orc, hh):
+    """BASELINE.json configs[3] in the small (laser acceleration in the boosted frame, gamma = 10: CKC, Vay, order 3,
+    filter, Godfrey NCI corrector, PEC z, moving window, boosted antenna, electrons + ions injected continuously from
+    the lab-frame plasma bounds) on FOUR slabs along z: fields and both species (by id) against the single-box oracle."""
+    from test_oracle import make_lwfa_oracle, _nci_lines
+    from warpx_b200.engine import max_dt, nci_godfrey_stencils
+    HS = hh.host_simulation_class()
+    world, nsteps = 4, 24
+    wl = workloads.laser_acceleration_boosted_3d(n_cell=(12, 12, 96), density=1.e22, use_fdtd_nci_corr=True)
+    dx = [(wl["prob_hi"][d] - wl["prob_lo"][d]) / wl["n_cell"][d] for d in range(3)]
+    # six cells of vacuum above the antenna, as in tests/test_host_engine.py (the coarse grid's guard-cell tie at the wall)
+    wl["prob_lo"] = wl["prob_lo"][:2] + (wl["prob_lo"][2] + 6 * dx[2],)
+    wl["prob_hi"] = wl["prob_hi"][:2] + (wl["prob_hi"][2] + 6 * dx[2],)
+    nci = nci_godfrey_stencils(hh.host_library(), _nci_lines(), workloads.C * wl["cfl"] * max_dt(wl["solver"], dx) / dx[2])
+
+    def rank_fn(rank, dist):
+        sim = HS(wl["n_cell"], wl["prob_lo"], wl["prob_hi"], nox=wl["nox"], cfl=wl["cfl"], dist=dist,
+                 solver=wl["solver"], pusher=wl["pusher"], use_filter=True, sort_interval=4, nb=(1, 1, world),
+                 boundaries=abi.make_boundaries(wl["field_lo"], wl["field_hi"]),
+                 moving_window=(wl["moving_window_dir"], wl["moving_window_v"]),
+                 gamma_boost=wl["gamma_boost"], nci_stencils=nci)
+        for sp in wl["species"]:
+            sim.add_plasma_species(sp["name"], sp["q"], sp["m"],
+                                   abi.make_injector(sp["ppc"], sp["bound_lo"], sp["bound_hi"], sp["density"], True),
+                                   capacity=12 * 12 * 200)
+        la = wl["lasers"][0]
+        sim.add_laser(abi.make_laser(la["position"], la["direction"], la["polarization"], la["wavelength"], la["e_max"],
+                                     la["waist"], la["duration"], la["t_peak"], la["focal_distance"]))
+        sim.Evolve(nsteps)
+        return dict(fields={c: sim.field_numpy(c) for c in range(9)}, box=(sim.box_lo, sim.box_hi),
+                    parts=[sim.species_numpy(i, sort_by_id=False) for i in (0, 1)], dz=sim.dx[2])
+
+    res = hh.run_ranks(world, rank_fn)
+    osim = make_lwfa_oracle(orc, wl)
+    osim.evolve(nsteps)
+    err, scale = _gather_fields(res, osim, world)
+    for group in ((0, 1, 2), (3, 4, 5), (6, 7, 8)):
+        s = max(scale[c] for c in group)
+        assert s > 0
+        for c in group:
+            assert err[c] <= 1e-9 * s, abi.COMP_NAMES[c]
+    for isp in (0, 1):
+        B = osim.particles(isp)
+        ids = np.concatenate([res[r]["parts"][isp]["id"] for r in range(world)])
+        order = np.argsort(ids)
+        assert len(B["x"]) > 0 and np.array_equal(ids[order], np.arange(len(B["x"])))
+        for k in ("x", "y", "z"):
+            a = np.concatenate([res[r]["parts"][isp][k] for r in range(world)])[order]
+            assert np.max(np.abs(a - B[k])) / res[0]["dz"] <= 1e-9, (isp, k)
+        for k in ("ux", "uy", "uz"):
+            a = np.concatenate([res[r]["parts"][isp][k] for r in range(world)])[order]
+            assert np.max(np.abs(a - B[k])) / (10.0 * workloads.C) <= 1e-9, (isp, k)
 
 
 @pytest.mark.parametrize("nb,periodic", [((2, 1, 1), (1, 1, 1)), ((2, 2, 2), (1, 1, 1)), ((1, 1, 2), (1, 1, 0))])
@@ -279,3 +336,55 @@ def test_redistribute_moves_every_particle_to_its_owner(orc, hh, world):
         cell0 = [np.floor((s[k][idx] - full["prob_lo"][d]) / dx[d]).astype(int) for d, k in enumerate("xyz")]
         moved_rank += int(np.sum(~np.all([(cell0[d] >= blo[d]) & (cell0[d] <= bhi[d]) for d in range(3)], axis=0)))
     assert moved_rank > 100                                  # the test did move particles between ranks
+
+
+def test_classify_from_candidate_list_matches_full_sweep(orc, hh):
+    """pic_particles_classify_listed (the migration's axis sweep over the push's list of brick leavers) against
+    pic_particles_classify (every particle): same leavers when the list holds them, dead entries dropped, the full
+    sweep when the list overflowed; pic_migrate_note_appended adds [np_old, np_new) of the last unpack."""
+    import ctypes as C
+    L = hh.host_library()
+    rng = np.random.default_rng(3)
+    n, npart = 16, 4000
+    geom = abi.make_geom((n, n, n), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    P = orc.HostParticles(**{k: rng.uniform(0.0, 1.0, npart) for k in orc.HostParticles.NAMES})
+    lo, hi, cap = 4, 11, 4096
+
+    def run(listed, cand=None):
+        counts = np.zeros(2, dtype=np.int32)
+        idx = [np.full(cap, -7, dtype=np.int32) for _ in range(2)]
+        args = [C.byref(P.soa), C.byref(geom), 1, lo, hi, 0, counts.ctypes.data, idx[0].ctypes.data, idx[1].ctypes.data, cap, None]
+        if listed:
+            assert L.pic_particles_classify_listed(*args, C.byref(cand), None) == 0, L.pic_last_error()
+        else:
+            assert L.pic_particles_classify(*args, None) == 0, L.pic_last_error()
+        return [set(idx[s][:counts[s]].tolist()) for s in range(2)], counts
+
+    want, wc = run(False)
+    assert wc[0] > 100 and wc[1] > 100 and wc[0] + wc[1] < npart
+    cell = np.floor(P.y * n).astype(int)
+    leavers = np.nonzero((cell < lo) | (cell > hi))[0]
+    stay = np.nonzero((cell >= lo) & (cell <= hi))[0][:50]
+    # the list: every leaver, some particles that stay, two entries behind the particle count, one dropped earlier
+    entries = np.concatenate([leavers, stay, [npart + 5, npart], [-1]]).astype(np.int32)
+    rng.shuffle(entries)
+    store = np.concatenate([entries, np.full(64, -9, dtype=np.int32)])
+    count = np.array([len(entries)], dtype=np.int32)
+    cand = abi.pic_escape_list()
+    cand.idx, cand.count, cand.capacity = store.ctypes.data, count.ctypes.data, len(store)
+    got, gc = run(True, cand)
+    assert got == want and list(gc) == list(wc)
+    assert set(store[:len(entries)][entries >= npart].tolist()) == {-1}        # dead entries are dropped for good
+    # appended arrivals of an unpack (work[4] = count before, work[5] = after) become candidates
+    work = np.zeros(8, dtype=np.int32)
+    work[4], work[5] = npart - 10, npart
+    assert L.pic_migrate_note_appended(work.ctypes.data, C.byref(cand), None) == 0, L.pic_last_error()
+    assert count[0] == len(entries) + 10 and store[len(entries):len(entries) + 10].tolist() == list(range(npart - 10, npart))
+    work[4], work[5] = npart, npart - 3                                       # a net loss appends nothing
+    assert L.pic_migrate_note_appended(work.ctypes.data, C.byref(cand), None) == 0
+    assert count[0] == len(entries) + 10
+    work[4], work[5] = 0, 1000                                                # more than the list holds: overflow mark
+    assert L.pic_migrate_note_appended(work.ctypes.data, C.byref(cand), None) == 0
+    assert count[0] == len(store) + 1
+    got, gc = run(True, cand)                                                 # overflowed list: every particle is visited
+    assert got == want and list(gc) == list(wc)

@@ -27,6 +27,7 @@
 #include "pic_common.cuh"
 #include "comm.cuh"
 #include <cmath>
+#include <atomic>
 #include <vector>
 
 namespace pic {
@@ -38,8 +39,9 @@ struct Species {
     pic_bins bins;
     bool has_bins;
     void* sort_work;
-    pic_escape_list esc;   // particles the last position push moved out of the domain (engine-owned)
-    bool has_esc;
+    pic_escape_list esc;   // particles the last position push moved out of the domain -- over several ranks: out of
+    bool has_esc;          // the rank's brick (engine-owned)
+    bool esc_valid = false;  // the list describes the current particle order (set by the push, cleared by whatever reorders)
     // neighbour migration (multi-rank), engine-owned device scratch
     long capacity = 0;           // entries of every SoA array of both buffers
     int mig_cap_max = 0, mig_cap = 0;
@@ -351,7 +353,23 @@ static int push(Engine& e, Species& sp, double dt, int push_position, void* s) {
     double xyzmin[3]; int lo[3];
     lower_corner(e, e.ng_EB, xyzmin, lo);
     const pic_soa& P = sp.buf[sp.cur];
-    if (push_position && sp.has_esc) cudaMemsetAsync(sp.esc.count, 0, sizeof(int), (cudaStream_t)s);
+    if (push_position && sp.has_esc) {
+        cudaMemsetAsync(sp.esc.count, 0, sizeof(int), (cudaStream_t)s);
+        // Over several ranks the push lists what leaves the BRICK (a superset by 1e-6 cell, so that round-off at a face
+        // cannot hide a particle from the classification, which decides by cell index): the periodic wrap and the
+        // migration sweeps then visit the listed particles only.  The domain moves with the window: set every step.
+        for (int d = 0; d < 3; ++d) {
+            const double eps = 1e-6 * e.dx[d];
+            if (!spans(e, d)) {
+                sp.esc.lo[d] = e.geom.prob_lo[d] + e.dx[d] * e.box_lo[d] + eps;
+                sp.esc.hi[d] = e.geom.prob_lo[d] + e.dx[d] * (e.box_hi[d] + 1) - eps;
+            } else {
+                sp.esc.lo[d] = e.geom.periodic[d] ? e.geom.prob_lo[d] : -INFINITY;
+                sp.esc.hi[d] = e.geom.periodic[d] ? e.geom.prob_hi[d] : INFINITY;
+            }
+        }
+        sp.esc_valid = true;
+    }
     // the main push gathers from the NCI-filtered copies (PhysicalParticleContainer.cpp:1900-1911); PushP does not
     const pic_fab* EB = (e.use_nci && push_position) ? e.nci_fab : e.fab;
     return pic_gather_push(&P, 0, P.np, &EB[0], &EB[3], e.dinv, xyzmin, lo, sp.q, sp.m, dt, e.nox,
@@ -426,6 +444,7 @@ static int sort_species(Engine& e, Species& sp, void* s) {
     sp.bins.np_binned = in.np;
     sp.cur = 1 - sp.cur;
     sp.has_bins = true;
+    sp.esc_valid = false;
     return 0;
 }
 
@@ -436,6 +455,12 @@ __global__ void peak_kernel(int* peak, const int* counts) { *peak = max(*peak, m
 // (csrc/migrate.cu).  The particle count stays on the device (work[0]) while the sweeps chain; the
 // host reads {count, status, peak per-face count} once.  Every rank sizes the next step's messages
 // from the all-reduced peak (8x headroom); the first step uses the worst case (one layer of cells).
+// PIC_MIGRATE_FULL_SWEEP=1: classify every particle in every axis sweep (the round-1 path), for comparison
+static const bool g_migrate_full_sweep = [] { const char* v = getenv("PIC_MIGRATE_FULL_SWEEP"); return v && atoi(v) != 0; }();
+
+static std::atomic<long> g_listed_sweeps{0};
+extern "C" long pic_engine_listed_sweeps(void) { return g_listed_sweeps.load(); }
+
 static int migrate(Engine& e, Species& sp, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     pic_soa& P = sp.buf[sp.cur];
@@ -447,9 +472,18 @@ static int migrate(Engine& e, Species& sp, void* stream) {
     const int* np_dev = sp.mig_work;
     pic_soa view = P;
     view.np = sp.capacity;                       // launch bound only: the kernels read the count from np_dev
+    // Who can leave: the particles the push of this step listed (nothing else moved since: periodic particle boundaries
+    // remove nobody, no window shift re-drew the brick) -- else every particle is classified.
+    const bool listed = sp.has_esc && sp.esc_valid && e.all_periodic && !e.do_moving_window && !g_migrate_full_sweep;
     for (int dim = 0; dim < 3; ++dim) {
         if (spans(e, dim)) continue;
         const bool np_dim = !e.geom.periodic[dim];
+        if (listed) ++g_listed_sweeps;
+        if (listed)
+            ENG_CALL(pic_particles_classify_listed(&view, &e.geom, dim, e.box_lo[dim], e.box_hi[dim],
+                                                   np_dim ? 2 : (e.nb[dim] == 2 ? 1 : 0), sp.mig_counts, sp.mig_idx[0],
+                                                   sp.mig_idx[1], cap, np_dev, &sp.esc, s));
+        else
         ENG_CALL(pic_particles_classify(&view, &e.geom, dim, e.box_lo[dim], e.box_hi[dim],
                                         np_dim ? 2 : (e.nb[dim] == 2 ? 1 : 0),
                                         sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], cap, np_dev, s));
@@ -466,7 +500,9 @@ static int migrate(Engine& e, Species& sp, void* stream) {
         ENG_CALL(exchange(e, dim, sp.mig_msg[0], sp.mig_msg[1], sp.mig_msg[2], sp.mig_msg[3], nmsg, s));
         ENG_CALL(pic_migrate_unpack(&view, sp.mig_counts, sp.mig_idx[0], sp.mig_idx[1], sp.mig_msg[2], sp.mig_msg[3], cap,
                                     sp.capacity, sp.mig_work, np_dev, s));
+        if (listed) ENG_CALL(pic_migrate_note_appended(sp.mig_work, &sp.esc, s));     // arrivals may have to travel on
     }
+    sp.esc_valid = false;            // holes were filled, tails moved: the list is spent
     ENG_NCCL(g_nccl.AllReduce(sp.mig_work + 6, sp.mig_work + 6, 1, PIC_NCCL_INT32, PIC_NCCL_MAX, e.comm->comm, s));
     cudaMemcpyAsync(sp.mig_head, sp.mig_work, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) return fail("pic_engine: migration failed (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -877,6 +913,7 @@ extern "C" int pic_engine_redistribute(void* h, void* stream) {
     for (auto& L : e->lasers) ENG_CALL(pic_particles_wrap_periodic(&L.P, &e->geom, stream));
     ENG_CALL(apply_particle_boundaries(*e, stream));
     for (auto& sp : e->species) {
+        sp.esc_valid = false;            // the caller moved the particles, not the push: classify every one
         if (e->comm) ENG_CALL(migrate(*e, sp, stream));
         sp.bins_stale = true;
     }

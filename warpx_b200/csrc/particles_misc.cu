@@ -94,7 +94,23 @@ __global__ void sort_scatter_kernel(SoaView in, SoaView out, const uint64_t* __r
     if (id_in && id_out) id_out[pos] = id_in[ip];
 }
 
-// which particles leave the rank's brick along one axis (cell index of the wrapped position)
+// which particles leave the rank's brick along one axis (cell index of the wrapped position).
+// Neighbour ownership is periodic: cells just above cell_hi (or wrapped to the bottom of the domain when this brick is
+// the last one) belong to the high neighbour.  both_up: 1 = two ranks along a periodic dim (both neighbours are the same
+// rank); 2 = non-periodic dim (ownership does not wrap: above the brick -> high neighbour, below -> low neighbour).
+__device__ __forceinline__ void classify_one(long ip, const double* __restrict__ pos, double plo, double dinv, int ncell,
+                                             int cell_lo, int cell_hi, int both_up, int* __restrict__ counts,
+                                             int* __restrict__ idx_lo, int* __restrict__ idx_hi, int capacity) {
+    int c = (int)floor((pos[ip] - plo) * dinv);
+    c = min(max(c, 0), ncell - 1);
+    if (c >= cell_lo && c <= cell_hi) return;
+    const int width = cell_hi - cell_lo + 1;
+    const int up_lo = (cell_hi + 1) % ncell;                       // first cell of the high neighbour
+    const bool up = both_up == 2 ? (c > cell_hi) : (both_up || (c >= up_lo && c < up_lo + width));
+    if (up) { const int n = atomicAdd(&counts[1], 1); if (n < capacity) idx_hi[n] = (int)ip; }
+    else    { const int n = atomicAdd(&counts[0], 1); if (n < capacity) idx_lo[n] = (int)ip; }
+}
+
 __global__ void classify_kernel(const double* __restrict__ pos, long np_host, const int* __restrict__ np_dev,
                                 double plo, double dinv, int ncell,
                                 int cell_lo, int cell_hi, int both_up, int* __restrict__ counts,
@@ -102,18 +118,41 @@ __global__ void classify_kernel(const double* __restrict__ pos, long np_host, co
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long np = np_dev ? (long)*np_dev : np_host;
     if (ip >= np) return;
-    int c = (int)floor((pos[ip] - plo) * dinv);
-    c = min(max(c, 0), ncell - 1);
-    if (c >= cell_lo && c <= cell_hi) return;
-    // neighbour ownership is periodic: cells just above cell_hi (or wrapped to the bottom of the
-    // domain when this brick is the last one) belong to the high neighbour
-    const int width = cell_hi - cell_lo + 1;
-    const int up_lo = (cell_hi + 1) % ncell;                       // first cell of the high neighbour
-    // both_up: 1 = two ranks along a periodic dim (both neighbours are the same rank); 2 = non-periodic
-    // dim (ownership does not wrap: above the brick -> high neighbour, below -> low neighbour)
-    const bool up = both_up == 2 ? (c > cell_hi) : (both_up || (c >= up_lo && c < up_lo + width));
-    if (up) { const int n = atomicAdd(&counts[1], 1); if (n < capacity) idx_hi[n] = (int)ip; }
-    else    { const int n = atomicAdd(&counts[0], 1); if (n < capacity) idx_lo[n] = (int)ip; }
+    classify_one(ip, pos, plo, dinv, ncell, cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
+}
+
+// candidates only (the list of the push, extended by pic_migrate_note_appended); every particle if the list overflowed
+__global__ void classify_listed_kernel(const double* __restrict__ pos, long np_host, const int* __restrict__ np_dev,
+                                       double plo, double dinv, int ncell, int cell_lo, int cell_hi, int both_up,
+                                       int* __restrict__ counts, int* __restrict__ idx_lo, int* __restrict__ idx_hi,
+                                       int capacity, int* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+    const long np = np_dev ? (long)*np_dev : np_host;
+    const int n = *cand_count;
+    if (n <= cand_cap) {
+        for (long t = tid; t < n; t += stride) {
+            const int ip = cand[t];
+            if (ip < 0) continue;
+            if (ip >= np) { cand[t] = -1; continue; }
+            classify_one(ip, pos, plo, dinv, ncell, cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
+        }
+    } else {
+        for (long ip = tid; ip < np; ip += stride)
+            classify_one(ip, pos, plo, dinv, ncell, cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
+    }
+}
+
+// one CTA: the particles the last unpack appended, [np_old, np_new), become candidates of the next axis sweep
+__global__ void note_appended_kernel(const int* __restrict__ work, int* __restrict__ cand, int* __restrict__ cand_count,
+                                     int cand_cap) {
+    const int np_old = work[4], np_new = work[5];
+    const int base = *cand_count;
+    __syncthreads();
+    if (base > cand_cap || np_new <= np_old) return;
+    const int n = np_new - np_old;
+    if (base + n > cand_cap) { if (threadIdx.x == 0) *cand_count = cand_cap + 1; return; }    // overflow: full sweeps from here
+    for (int t = threadIdx.x; t < n; t += blockDim.x) cand[base + t] = np_old + t;
+    if (threadIdx.x == 0) *cand_count = base + n;
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -165,6 +204,30 @@ extern "C" int pic_particles_classify(const pic_soa* p, const pic_geom* g, int d
                                                                   cell_lo, cell_hi, both_up, counts, idx_lo, idx_hi, capacity);
     count_launch();
     return check_launch("pic_particles_classify") ? 0 : 1;
+}
+
+extern "C" int pic_particles_classify_listed(const pic_soa* p, const pic_geom* g, int dim, int cell_lo, int cell_hi,
+                                             int both_up, int* counts, int* idx_lo, int* idx_hi, int capacity,
+                                             const int* np_dev, const pic_escape_list* cand, void* stream) {
+    PIC_REQUIRE(dim >= 0 && dim < 3, "pic_particles_classify_listed: bad dimension");
+    PIC_REQUIRE(cand && cand->idx && cand->count, "pic_particles_classify_listed: no candidate list");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(counts, 0, 2 * sizeof(int), s);
+    if (p->np == 0) return 0;
+    const double* pos = dim == 0 ? p->x : (dim == 1 ? p->y : p->z);
+    const double dinv = 1.0 / ((g->prob_hi[dim] - g->prob_lo[dim]) / g->n_cell[dim]);
+    classify_listed_kernel<<<148 * 8, 256, 0, s>>>(pos, p->np, np_dev, g->prob_lo[dim], dinv, g->n_cell[dim], cell_lo, cell_hi,
+                                                   both_up, counts, idx_lo, idx_hi, capacity, cand->idx, cand->count,
+                                                   cand->capacity);
+    count_launch();
+    return check_launch("pic_particles_classify_listed") ? 0 : 1;
+}
+
+extern "C" int pic_migrate_note_appended(const void* work, const pic_escape_list* cand, void* stream) {
+    PIC_REQUIRE(work && cand && cand->idx && cand->count, "pic_migrate_note_appended: no workspace / candidate list");
+    note_appended_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const int*)work, cand->idx, cand->count, cand->capacity);
+    count_launch();
+    return check_launch("pic_migrate_note_appended") ? 0 : 1;
 }
 
 extern "C" long pic_bins_count(const int box_lo[3], const int box_hi[3], const int tile[3]) {
