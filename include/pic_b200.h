@@ -292,7 +292,11 @@ int pic_halo_pack(const pic_fab* f, int dim, int side, int ng, int mode, double*
 int pic_halo_unpack(const pic_fab* f, int dim, int side, int ng, int mode, const double* buf,
                     void* stream);
 /* All components of one exchange (e.g. Ex Ey Ez Bx By Bz) and both sides in ONE launch: buf_lo /
- * buf_hi hold the slabs for the low / high neighbour concatenated in component order (nfab <= 8). */
+ * buf_hi hold the slabs for the low / high neighbour concatenated in component order (nfab <= 8).
+ * The multi calls also take mode 2 = SumBoundary AND the FillBoundary that follows it (WarpXSumGuardCells.H:
+ * SumBoundary then FillBoundary of J / rho) as ONE exchange between two ranks along a periodic axis: each side packs
+ * its whole overlap zone (ng valid layers, the shared node, ng guards) and adds what it receives; needs
+ * 2 ng + nodal <= box width. */
 int pic_halo_pack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, double* buf_lo,
                         double* buf_hi, void* stream);
 int pic_halo_unpack_multi(const pic_fab* fabs, int nfab, int dim, int ng, int mode, const double* buf_lo,
@@ -340,6 +344,8 @@ int pic_particles_classify_listed(const pic_soa* p, const pic_geom* g, int dim, 
 int pic_migrate_note_appended(const void* work, const pic_escape_list* candidates, void* stream);
 /* how many axis sweeps of this process classified from the candidate list (tests: the list path really ran) */
 long pic_engine_listed_sweeps(void);
+/* how many J exchanges of this process ran as the fused sum + refresh (halo mode 2) */
+long pic_engine_fused_sum_exchanges(void);
 
 /* Neighbour migration, steps 2 and 3 (pack / unpack phases of Redistribute).  A message is
  * pic_migrate_message_doubles(cap) doubles: header (true particle count) + 8 rows of cap doubles

@@ -102,6 +102,40 @@ def test_eight_bricks_order3_thermal_loop_matches_oracle(orc, hh):
         assert err[c] <= 1e-11 * scale[c], abi.COMP_NAMES[c]
 
 
+def test_two_wide_bricks_order3_fused_current_exchange_matches_oracle(orc, hh):
+    """Two bricks of 16^3 cells, order 3, bilinear filter, u_th = 0.3 c: wide enough for the fused SumBoundary +
+    refresh of J (halo mode 2: one exchange per axis instead of two) -- 6 steps against the single-box oracle, and the
+    fused exchange really ran (one per step and rank)."""
+    HS = hh.host_simulation_class()
+    n_cell, world, nsteps = (32, 16, 16), 2, 6
+    full = workloads.uniform_plasma_3d(n_cell=n_cell, ppc=(2, 1, 1), u_th=0.3, lx=(4e-6, 2e-6, 2e-6), perturbation=0.01)
+    s = full["species"][0]
+
+    def rank_fn(rank, dist):
+        dec = parallel.Decomposition(n_cell, parallel.brick_grid(world), rank)
+        sim = HS(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=3, dist=dist, sort_interval=4, use_filter=True)
+        cell = [np.floor((s[k] - full["prob_lo"][d]) / sim.dx[d]).astype(int) for d, k in enumerate("xyz")]
+        m = np.ones(len(s["x"]), dtype=bool)
+        for d in range(3):
+            m &= (cell[d] >= dec.box_lo[d]) & (cell[d] <= dec.box_hi[d])
+        sim.add_species(s["name"], s["q"], s["m"], *[s[k][m] for k in ("x", "y", "z", "w", "ux", "uy", "uz")])
+        n0 = sim.total_particles()
+        sim.Evolve(nsteps)
+        assert sim.total_particles() == n0
+        return dict(fields={c: sim.field_numpy(c) for c in range(9)}, box=(sim.box_lo, sim.box_hi))
+
+    assert parallel.brick_grid(world) == (2, 1, 1)
+    before = hh.host_library().pic_engine_fused_sum_exchanges()
+    res = hh.run_ranks(world, rank_fn)
+    assert hh.host_library().pic_engine_fused_sum_exchanges() - before == nsteps * world
+    osim = orc.OracleSim(full["n_cell"], full["prob_lo"], full["prob_hi"], nox=3, use_filter=True)
+    osim.add_species(s["q"], s["m"], s["x"], s["y"], s["z"], s["w"], s["ux"], s["uy"], s["uz"])
+    osim.evolve(nsteps)
+    err, scale = _gather_fields(res, osim, world)
+    for c in range(9):
+        assert err[c] <= 1e-11 * scale[c], abi.COMP_NAMES[c]
+
+
 @pytest.mark.parametrize("world", [4])
 def test_z_slabs_with_moving_window_match_oracle(orc, hh, world):
     """The laser-acceleration deck in the small (12 x 12 x 64, order 3, filter, PEC z, moving window at c, antenna,

@@ -168,10 +168,17 @@ static void slab_range(const pic_fab& f, int dim, int side, int ng, int mode, in
         count = ng;
         if (!unpack) first = side ? (hc + 1 - ng) : (lc + st);
         else first = side ? (hc + 1 + st) : (lc - ng);
-    } else {                   // sum: send guards (+ shared node), add into valid
+    } else if (mode == 1) {    // sum: send guards (+ shared node), add into valid
         count = ng + st;
         if (!unpack) first = side ? (hc + 1) : (lc - ng);
         else first = side ? (hc + 1 - ng) : lc;
+    } else {                   // sum and refresh in one exchange (PIC_HALO_SUM_REFRESH): both ranks send the whole
+        // overlap zone of the face -- ng valid layers, the shared node, ng guards -- and add what they receive to their
+        // own partial sums; a + b = b + a bit for bit, so valid points hold SumBoundary's result and the guards the
+        // copies FillBoundary would bring.  Needs 2 ng + st <= box width (a point shared by two ranks only): the
+        // same bound SumBoundary's source width has.
+        count = 2 * ng + st;
+        first = side ? (hc + 1 - ng) : (lc - ng);
     }
 }
 
@@ -254,7 +261,7 @@ extern "C" int pic_boundary_local_multi(const pic_fab* fabs, int nfab, int dim, 
 extern "C" long pic_halo_slab_count(const pic_fab* f, int dim, int ng, int mode) {
     long n = 1;
     for (int d = 0; d < 3; ++d) if (d != dim) n *= (f->hi[d] - f->lo[d] + 1);
-    return n * (mode == 0 ? ng : ng + f->stag[dim]);
+    return n * (mode == 0 ? ng : (mode == 1 ? ng + f->stag[dim] : 2 * ng + f->stag[dim]));
 }
 
 static int slab_launch(const pic_fab* f, int dim, int side, int ng, int mode, double* buf, int unpack, void* stream) {
@@ -275,12 +282,14 @@ static int slab_launch(const pic_fab* f, int dim, int side, int ng, int mode, do
 static int multi_launch(const pic_fab* fabs, int nfab, int dim, int ng, int mode, double* buf_lo, double* buf_hi,
                         int unpack, void* stream) {
     PIC_REQUIRE(nfab >= 1 && nfab <= HALO_MAX, "pic_halo_*_multi: 1..%d components", HALO_MAX);
-    PIC_REQUIRE(dim >= 0 && dim < 3 && (mode == 0 || mode == 1), "pic_halo_*_multi: bad arguments");
+    PIC_REQUIRE(dim >= 0 && dim < 3 && mode >= 0 && mode <= 2, "pic_halo_*_multi: bad arguments");
     MultiSlab m;
     m.n = nfab;
     m.off[0] = 0;
     for (int f = 0; f < nfab; ++f) {
         PIC_REQUIRE(ng <= fabs[f].ng[dim], "pic_halo_*_multi: ng=%d exceeds allocated guards", ng);
+        PIC_REQUIRE(mode != 2 || 2 * ng + fabs[f].stag[dim] <= vhi(fabs[f], dim) - vlo(fabs[f], dim) + 1 - fabs[f].stag[dim],
+                    "pic_halo_*_multi: the box is too thin for the fused sum + refresh (ng=%d)", ng);
         m.v[f] = make_view(fabs[f]);
         long cnt = 0;
         for (int side = 0; side < 2; ++side) {

@@ -72,6 +72,7 @@ def bind(L):
         "pic_particles_classify_listed": (C.c_int, [soap, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, escp, vp]),
         "pic_migrate_note_appended": (C.c_int, [vp, escp, vp]),
         "pic_engine_listed_sweeps": (C.c_long, []),
+        "pic_engine_fused_sum_exchanges": (C.c_long, []),
         "pic_halo_pack_multi": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "pic_halo_unpack_multi": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "pic_migrate_message_doubles": (C.c_long, [C.c_int]),
