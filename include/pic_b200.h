@@ -265,6 +265,11 @@ int pic_boundary_local_multi(const pic_fab* fabs, int nfab, int dim, int ng, int
  * Replaces BilinearFilter::ComputeStencils + Filter::ApplyStencil (Source/Filter/BilinearFilter.cpp:
  * 64-88, Source/Filter/Filter.cpp:37-133) as called from WarpXComm.cpp:1357-1374. */
 int pic_apply_filter(const pic_fab* src, const pic_fab* dst, const int npass[3], void* stream);
+/* The same for up to three components in ONE launch (Jx, Jy, Jz of WarpX::ApplyFilterJ): for npass = (1,1,1) a
+ * streaming kernel that walks every column along z with the last three xy-filtered planes in registers (same nesting of
+ * the sums, same bits as pic_apply_filter).  The step driver deposits into its own scratch copies of J and filters
+ * from there INTO the caller's J arrays, so there is no copy back. */
+int pic_apply_filter_multi(const pic_fab* src, const pic_fab* dst, int nfab, const int npass[3], void* stream);
 
 /* Godfrey's NCI corrector (particles.use_fdtd_nci_corr).
  * _table_index / _stencil: NCIGodfreyFilter::ComputeStencils (Source/Filter/NCIGodfreyFilter.cpp:49-139) --

@@ -348,6 +348,31 @@ def test_bilinear_filter_matches_oracle(orc, dev, stag_comp, npass):
     assert dev.L.pic_apply_filter(C.byref(arr[0]), C.byref(arr[0]), abi.int3(npass), dev.stream) != 0
 
 
+def test_bilinear_filter_three_components_in_one_launch(orc, dev):
+    """pic_apply_filter_multi (Jx, Jy, Jz of ApplyFilterJ in one launch; the streaming kernel of npass = (1,1,1)) against
+    the oracle, on a box longer than one chunk of planes and ragged against the CTA; PIC-internal consistency: the
+    single-component call gives the same bits."""
+    L = orc.lib()
+    n = (70, 21, 40)
+    box_lo, box_hi = box(n)
+    ng = (5, 5, 5)
+    src = random_fields(orc, box_lo, box_hi, ng, 17, comps=[6, 7, 8])
+    want = [orc.HostFab(box_lo, box_hi, ng, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    for a, b in zip(src, want):
+        L.orc_apply_filter(C.byref(a.desc), C.byref(b.desc), abi.int3((1, 1, 1)))
+    arr, tens = dev.fabs(list(src) + want)
+    for t in tens[3:]:
+        t.fill_(7.0)
+    dev.ok(dev.L.pic_apply_filter_multi((abi.pic_fab * 3)(*arr[0:3]), (abi.pic_fab * 3)(*arr[3:6]), 3, abi.int3((1, 1, 1)), dev.stream))
+    dev.sync()
+    for c in range(3):
+        assert rel_linf(tens[3 + c].cpu().numpy(), want[c].a) <= 1e-14, c
+    keep = tens[4].clone()
+    dev.ok(dev.L.pic_apply_filter(C.byref(arr[1]), C.byref(arr[4]), abi.int3((1, 1, 1)), dev.stream))
+    dev.sync()
+    assert bool((tens[4] == keep).all())
+
+
 def test_wrap_periodic_and_field_energy(orc, dev):
     L = orc.lib()
     n = (8, 8, 8)

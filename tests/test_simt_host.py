@@ -318,3 +318,39 @@ def test_fdtd_kernels_under_simt_emulation(orc, mode, algo, n, ng):
     L.orc_evolve_b(Bo, Eo, C.byref(st), 0.5 * dt)
     for c in range(6):
         assert rel_linf(G[c].a, F[c].a) <= 1e-13, abi.COMP_NAMES[c]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bilinear filter: the streaming (marching) kernel of npass = (1,1,1) and the direct kernel, under the emulator
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("npass", [(1, 1, 1), (2, 1, 3)])
+def test_bilinear_filter_kernels_under_simt_emulation(orc, npass):
+    """pic_apply_filter / pic_apply_filter_multi of the host library against the oracle's Filter::DoFilter: three
+    components of different staggering in one launch, a box that is ragged against the 32 x 8 CTA and longer than one
+    chunk of planes, zero padding at the array edge, a destination larger than the source; the single-component call
+    gives the same bits as the multi call."""
+    from host_harness import harness
+    from helpers import random_fields
+    hl = harness.host_library()
+    n = (37, 11, 35)
+    box_lo, box_hi = (0, 0, 0), tuple(v - 1 for v in n)
+    ng = (3, 2, 2)
+    src = random_fields(orc, box_lo, box_hi, ng, 31, comps=[6, 7, 8])
+    want = [orc.HostFab(box_lo, box_hi, ng, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    for a, b in zip(src, want):
+        orc.lib().orc_apply_filter(C.byref(a.desc), C.byref(b.desc), abi.int3(npass))
+    got = [orc.HostFab(box_lo, box_hi, ng, abi.YEE_STAG[c]) for c in (6, 7, 8)]
+    for g in got:
+        g.a[...] = 7.0                                        # every point of dst must be overwritten
+    assert hl.pic_apply_filter_multi(orc.fab_array(src), orc.fab_array(got), 3, abi.int3(npass), None) == 0, hl.pic_last_error()
+    for c in range(3):
+        assert rel_linf(got[c].a, want[c].a) <= 1e-14, c
+    one = orc.HostFab(box_lo, box_hi, ng, abi.YEE_STAG[7])
+    assert hl.pic_apply_filter(C.byref(src[1].desc), C.byref(one.desc), abi.int3(npass), None) == 0, hl.pic_last_error()
+    assert np.array_equal(one.a, got[1].a)
+    # a destination with more guard cells than the source: zero padding outside the source's allocation
+    big = orc.HostFab(box_lo, box_hi, (4, 4, 3), abi.YEE_STAG[6])
+    wbig = orc.HostFab(box_lo, box_hi, (4, 4, 3), abi.YEE_STAG[6])
+    orc.lib().orc_apply_filter(C.byref(src[0].desc), C.byref(wbig.desc), abi.int3(npass))
+    assert hl.pic_apply_filter(C.byref(src[0].desc), C.byref(big.desc), abi.int3(npass), None) == 0, hl.pic_last_error()
+    assert rel_linf(big.a, wbig.a) <= 1e-14

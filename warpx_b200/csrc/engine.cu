@@ -98,8 +98,10 @@ struct Engine {
     double dx[3], dinv[3], dt;
     int ng_EB[3], ng_J[3], ng_FG[3], ng_FS[3];
     int use_filter = 0, npass[3] = {1, 1, 1};   // warpx.use_filter / filter_npass_each_dir
-    double* filter_tmp = nullptr;               // one J-component-sized scratch array
-    size_t filter_tmp_bytes = 0;
+    // With the filter the particles deposit into the engine's own copies of J and ApplyFilterJ writes from there
+    // straight into the caller's arrays (no copy back): jdep[c] = fab[6 + c] with its own memory.
+    pic_fab jdep[3];
+    bool jdep_alloc = false;
     pic_stencil st;
     pic_fab fab[9];        // Ex Ey Ez Bx By Bz jx jy jz
     std::vector<Species> species;
@@ -332,22 +334,9 @@ static std::atomic<long> g_fused_sum_exchanges{0};
 extern "C" long pic_engine_fused_sum_exchanges(void) { return g_fused_sum_exchanges.load(); }
 
 static int sync_current(Engine& e, void* s) {
-    if (e.use_filter)
-        for (int c = 6; c < 9; ++c) {
-            // WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter into a temporary over the grown box, copy back
-            const size_t bytes = sizeof(double) * (size_t)fab_size(e.fab[c]);
-            if (bytes > e.filter_tmp_bytes) {
-                if (e.filter_tmp) cudaFree(e.filter_tmp);
-                if (cudaMalloc(&e.filter_tmp, bytes) != cudaSuccess) return fail("pic_engine: filter scratch allocation failed");
-                e.filter_tmp_bytes = bytes;
-            }
-            pic_fab tmp = e.fab[c];
-            tmp.p = e.filter_tmp;
-            ENG_CALL(pic_apply_filter(&e.fab[c], &tmp, e.npass, s));
-            cudaMemcpyAsync(e.fab[c].p, tmp.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
-        }
-    // SumBoundaryJ: src = ng_depos_J (+ stencil_length-1 with the filter, WarpXComm.cpp:1413-1416) == ng_J
-    // either way; then all guards of J are refreshed (WarpXSumGuardCells.cpp:22-23)
+    // WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter over the grown box into a temporary, copy back -- here the
+    // temporary is where the particles deposited and the result lands in J itself, three components per launch
+    if (e.use_filter) ENG_CALL(pic_apply_filter_multi(e.jdep, &e.fab[6], 3, e.npass, s));
     // Between two ranks along a periodic axis both passes are ONE exchange (halo.cu, mode 2: each rank sends the whole
     // overlap zone and adds what it receives): three exchanges less per step on a 2 x 2 x 2 brick grid.
     bool fused[3];
@@ -415,9 +404,20 @@ static int apply_nci(Engine& e, void* s) {
 static int push_particles_and_deposit(Engine& e, void* s) {
     {
         Stage t(e, ST_ZERO_J, s);
-        for (int c = 6; c < 9; ++c)                     // J.setVal(0), MultiParticleContainer.cpp:467-478
-            cudaMemsetAsync(e.fab[c].p, 0, sizeof(double) * (size_t)fab_size(e.fab[c]), (cudaStream_t)s);
+        if (e.use_filter && !e.jdep_alloc) {
+            for (int c = 0; c < 3; ++c) {
+                e.jdep[c] = e.fab[6 + c];
+                e.jdep[c].p = nullptr;
+                if (cudaMalloc(&e.jdep[c].p, sizeof(double) * (size_t)fab_size(e.fab[6 + c])) != cudaSuccess)
+                    return fail("pic_engine: cannot allocate the deposition copy of J (filter)");
+            }
+            e.jdep_alloc = true;
+        }
+        const pic_fab* Jd = e.use_filter ? e.jdep : &e.fab[6];
+        for (int c = 0; c < 3; ++c)                     // J.setVal(0), MultiParticleContainer.cpp:467-478
+            cudaMemsetAsync(Jd[c].p, 0, sizeof(double) * (size_t)fab_size(Jd[c]), (cudaStream_t)s);
     }
+    const pic_fab* Jd = e.use_filter ? e.jdep : &e.fab[6];
     double xyzmin[3]; int lo[3];
     lower_corner(e, e.ng_J, xyzmin, lo);
     if (e.use_nci && !e.species.empty()) { Stage t(e, ST_NCI, s); ENG_CALL(apply_nci(e, s)); }
@@ -425,7 +425,7 @@ static int push_particles_and_deposit(Engine& e, void* s) {
         { Stage t(e, ST_GATHER_PUSH, s); ENG_CALL(push(e, sp, e.dt, 1, s)); }
         const pic_soa& P = sp.buf[sp.cur];
         Stage t(e, ST_DEPOSIT, s);
-        ENG_CALL(pic_deposit_esirkepov(&P, 0, P.np, &e.fab[6], e.dinv, xyzmin, lo, sp.q, e.dt, -0.5 * e.dt,
+        ENG_CALL(pic_deposit_esirkepov(&P, 0, P.np, Jd, e.dinv, xyzmin, lo, sp.q, e.dt, -0.5 * e.dt,
                                        e.nox, sp.has_bins ? &sp.bins : nullptr, s));
     }
     // the antennas come after the species in allcontainers (MultiParticleContainer.cpp:60-75);
@@ -445,7 +445,7 @@ static int push_particles_and_deposit(Engine& e, void* s) {
             ENG_CALL(pic_particles_owned_weights(&L.P, own_lo, own_hi, L.w_owned, s));
             dep.w = L.w_owned;
         }
-        ENG_CALL(pic_deposit_esirkepov(&dep, 0, dep.np, &e.fab[6], e.dinv, xyzmin, lo, 1.0, e.dt, -0.5 * e.dt,
+        ENG_CALL(pic_deposit_esirkepov(&dep, 0, dep.np, Jd, e.dinv, xyzmin, lo, 1.0, e.dt, -0.5 * e.dt,
                                        e.nox, nullptr, s));
     }
     return 0;
@@ -747,7 +747,7 @@ extern "C" void* pic_engine_create(const pic_geom* geom, const int box_lo[3], co
 }
 extern "C" void pic_engine_destroy(void* h) {
     Engine* e = static_cast<Engine*>(h);
-    if (e && e->filter_tmp) cudaFree(e->filter_tmp);
+    if (e && e->jdep_alloc) for (int c = 0; c < 3; ++c) cudaFree(e->jdep[c].p);
     if (e) {
 #ifndef PIC_SIMT_HOST
         for (cudaEvent_t ev : e->tm.pool) cudaEventDestroy(ev);
@@ -794,6 +794,7 @@ extern "C" void pic_engine_guards(void* h, int out[12]) {
 }
 extern "C" int pic_engine_set_fields(void* h, const pic_fab fabs[9]) {
     Engine* e = static_cast<Engine*>(h);
+    if (e->jdep_alloc) { for (int c = 0; c < 3; ++c) cudaFree(e->jdep[c].p); e->jdep_alloc = false; }   // new shapes
     for (int c = 0; c < 9; ++c) {
         e->fab[c] = fabs[c];
         const int* ng = c < 6 ? e->ng_EB : e->ng_J;

@@ -64,6 +64,7 @@ def bind(L):
         "pic_sum_boundary_local": (C.c_int, [fabp, C.c_int, C.c_int, gp, vp]),
         "pic_boundary_local_multi": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, gp, vp]),
         "pic_apply_filter": (C.c_int, [fabp, fabp, ip, vp]),
+        "pic_apply_filter_multi": (C.c_int, [fabp, fabp, C.c_int, ip, vp]),
         "pic_halo_slab_count": (C.c_long, [fabp, C.c_int, C.c_int, C.c_int]),
         "pic_halo_pack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pic_halo_unpack": (C.c_int, [fabp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
