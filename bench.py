@@ -359,6 +359,7 @@ def run_engine(args):
         "evolve_e": 96.0 * ncell,
         "gather_push": 96.0 * npart_local + 48.0 * ncell,
         "deposit": 56.0 * npart_local + 72.0 * ncell,
+        "filter_j": 48.0 * ncell,        # --filter 1: three components, one read + one write each (no copy back)
     }
     try:     # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:

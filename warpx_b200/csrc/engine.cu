@@ -73,9 +73,9 @@ struct Laser {
 // Per-stage CUDA-event timing of the step driver (pic_engine_enable_timing / pic_engine_stage_ms): the events are
 // recorded on the stream the stages are launched on, inside the same pic_engine_evolve calls a benchmark times.
 enum { ST_FILL_EB = 0, ST_GATHER_PUSH, ST_ZERO_J, ST_DEPOSIT, ST_SYNC_J, ST_EVOLVE_B, ST_FILL_B, ST_EVOLVE_E, ST_FILL_E,
-       ST_WRAP, ST_MIGRATE, ST_SORT, ST_NCI, ST_WINDOW, ST_PUSHP, ST_COUNT };
+       ST_WRAP, ST_MIGRATE, ST_SORT, ST_NCI, ST_WINDOW, ST_PUSHP, ST_FILTER, ST_COUNT };
 static const char* const stage_names[ST_COUNT] = {"fill_boundary_eb", "gather_push", "zero_j", "deposit", "sync_current",
-    "evolve_b", "fill_boundary_b", "evolve_e", "fill_boundary_e", "wrap", "migrate", "sort", "nci_filter", "move_window", "push_p"};
+    "evolve_b", "fill_boundary_b", "evolve_e", "fill_boundary_e", "wrap", "migrate", "sort", "nci_filter", "move_window", "push_p", "filter_j"};
 struct StageRec { int st; cudaEvent_t a, b; };
 struct Timing {
     bool on = false;
@@ -334,9 +334,8 @@ static std::atomic<long> g_fused_sum_exchanges{0};
 extern "C" long pic_engine_fused_sum_exchanges(void) { return g_fused_sum_exchanges.load(); }
 
 static int sync_current(Engine& e, void* s) {
-    // WarpX::ApplyFilterJ (WarpXComm.cpp:1357-1374): filter over the grown box into a temporary, copy back -- here the
-    // temporary is where the particles deposited and the result lands in J itself, three components per launch
-    if (e.use_filter) ENG_CALL(pic_apply_filter_multi(e.jdep, &e.fab[6], 3, e.npass, s));
+    // (WarpX::ApplyFilterJ, WarpXComm.cpp:1357-1374 -- filter over the grown box into a temporary, copy back -- ran just
+    //  before as its own stage: the temporary is where the particles deposited, the result landed in J itself)
     // Between two ranks along a periodic axis both passes are ONE exchange (halo.cu, mode 2: each rank sends the whole
     // overlap zone and adds what it receives): three exchanges less per step on a 2 x 2 x 2 brick grid.
     bool fused[3];
@@ -665,6 +664,7 @@ static int one_step(Engine& e, bool last, void* s) {
     }
     // ---- OneStep_nosub ----
     ENG_CALL(push_particles_and_deposit(e, s));
+    if (e.use_filter) { Stage t(e, ST_FILTER, s); ENG_CALL(pic_apply_filter_multi(e.jdep, &e.fab[6], 3, e.npass, s)); }
     { Stage t(e, ST_SYNC_J, s); ENG_CALL(sync_current(e, s)); }
     { Stage t(e, ST_EVOLVE_B, s); ENG_CALL(evolve_b(e, 0.5 * e.dt, s)); }
     { Stage t(e, ST_FILL_B, s); ENG_CALL(fill_boundary(e, 3, 6, e.ng_FS, s)); }
